@@ -1,0 +1,137 @@
+/* t3d_b200 -- C ABI of the B200-native Frustum-PointNet hot path of yewsiang/Transferable3D.
+ *
+ * The reference has no FFI: its boundary is Python functions that build a TF1 graph plus
+ * sess.run (sunrgbd_detection/test_semisup.py:221-226, train_boxpc.py:365-366).  Each entry point
+ * below replaces the TF ops behind one of those reference functions (cited per function) and is
+ * what a binding for this path would bind.
+ *
+ * Conventions: every pointer is a DEVICE pointer to contiguous memory unless marked `host`;
+ * the caller owns all buffers including workspaces (the library never allocates); `stream` is a
+ * cudaStream_t (NULL = legacy default stream); calls are asynchronous on that stream and
+ * re-entrant for distinct streams/buffers.  Return value: 0 ok, <0 invalid argument
+ * (T3D_ERR_*), >0 a cudaError_t.  float = IEEE fp32, int = int32.
+ */
+#ifndef T3D_B200_H_
+#define T3D_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define T3D_VERSION 100
+#define T3D_ERR_ARG (-1)      /* null pointer / bad enum */
+#define T3D_ERR_SHAPE (-2)    /* unsupported shape */
+#define T3D_ERR_ALIGN (-3)    /* pointer not aligned as required */
+
+typedef void* t3d_stream_t;
+
+int t3d_version(void);
+const char* t3d_error_string(int code);
+
+/* activation ids of tf_util.conv2d / fully_connected activation_fn (models/tf_util.py:1321,1497) */
+enum { T3D_ACT_NONE = 0, T3D_ACT_RELU = 1, T3D_ACT_LEAKY_RELU = 2, T3D_ACT_TANH = 3 };
+
+/* One conv2d(1x1) / fully_connected layer in fp32 with BN folded by the caller
+ * (models/tf_util.py:1258-1323, 1463-1499):  Y = act(X.W + bias + gbias[row / rows_per_group]) * rowmask[row].
+ * W is [K,N] row-major (the TF [Cin,Cout] layout).  If gmax != NULL (zero-initialised [groups,N]) the
+ * max over the rows of each group is accumulated there (tf_util.max_pool2d over the points,
+ * models/tf_util.py:1501-1524, on post-ReLU / masked values >= 0); Y may then be NULL. */
+int t3d_linear_f32(const float* X, int ldx, const float* W, int ldw, const float* bias,
+                   const float* gbias, int rows_per_group, float* Y, int ldy, int M, int K, int N,
+                   int act, const float* rowmask, float* gmax, t3d_stream_t stream);
+
+/* semisup_models.subtract_points_mean (semisup_models.py:145-162) and model_util.point_cloud_masking
+ * (model_util.py:241-272): mask = float(l0 < l1), count, mean = sum(mask*xyz)/max(count,1),
+ * xyz_stage1 = xyz - mean, plus idx = ascending indices of the masked-in points (compaction).
+ * Any of mask / count / mean / xyz_stage1 / idx may be NULL. */
+int t3d_mask_centroid(const float* logits, const float* pc, int B, int N, int C, float* mask,
+                      int* count, float* mean, float* xyz_stage1, int* idx, t3d_stream_t stream);
+
+/* model_util.tf_gather_object_pc / mask_to_indices (model_util.py:61-91).
+ * mode 0: Philox4x32-10 counter RNG keyed (seed, frustum) -- see oracle/model_util.py;
+ * mode 1: `choice` holds rank-space choice arrays [B,npoints] drawn by the host (numpy stream).
+ * indices [B,npoints,2] = {frustum, point}; object_pc [B,npoints,c_out] = (xyz - mean, features). */
+int t3d_resample(const int* idx, const int* count, int B, int N, int npoints, int mode, uint64_t seed,
+                 const int* choice, int* indices, const float* pc, int C, const float* mean, int c_out,
+                 float* object_pc, t3d_stream_t stream);
+
+/* tile table for the ragged tcgen05 chains: tiles = int32[<= sum ceil(count/tile_pts)][4] */
+int t3d_build_tiles(const int* count, int B, int tile_pts, void* tiles, int* num_tiles, t3d_stream_t stream);
+
+/* fp32-mode inputs: xyz - center (semisup_models.py:204-209) and the BoxPC representation
+ * tf_util.tf_get_box_pc_representation (tf_util.py:764-795): out[B,N,C+6]. */
+int t3d_prepare_xyz(const float* pc, int B, int N, int C, const float* center, float* out, t3d_stream_t stream);
+int t3d_boxpc_features(const float* pc, int B, int N, int C, const float* center, const float* dims,
+                       const float* orient, float* out, t3d_stream_t stream);
+
+/* Output parsing (semisup_models.py:265-290, semisup_v1_sunrgbd.py:203-222, model_util.parse_output_to_tensors
+ * model_util.py:178-210) fused with tf_convert_box_params_from_anchor_to_reg_format_multi (tf_util.py:1001-1041). */
+typedef struct {
+  const float* output;         /* [B, 3+2NH+4NS] */
+  const float* stage1_center;  /* [B,3] or NULL */
+  const float* mean_size;      /* [NS,3] */
+  const float* orient_anchors; /* [NH] */
+  int B, NH, NS;
+  float *center, *heading_scores, *heading_res_norm, *heading_res, *size_scores, *size_res_norm, *size_res;
+  float *reg_center, *reg_dims, *reg_orient;
+} t3d_parse_args;
+int t3d_parse_box(const t3d_parse_args* args /* host */, t3d_stream_t stream);
+
+int t3d_anchor_to_reg(const float* center, const float* dims_cls, const float* dims_reg, const float* orient_cls,
+                      const float* orient_reg, const float* dims_anchors, const float* orient_anchors, int B, int NS,
+                      int NH, float* out_center, float* out_dims, float* out_orient, t3d_stream_t stream);
+
+/* boxpc_sunrgbd.get_model output slicing (boxpc_sunrgbd.py:70-95) + one refine step of
+ * test_semisup.get_model (test_semisup.py:116-134). */
+typedef struct {
+  const float* out9;
+  int B, weigh_pred_by_conf, weigh_during_test;
+  float *fit_logits, *fit_prob; int* pred_fit;
+  float *delta_center, *delta_size, *delta_angle;
+  float *box_center, *box_dims, *box_orient;
+  float *tot_center, *tot_size, *tot_angle;
+} t3d_refine_args;
+int t3d_boxpc_refine(const t3d_refine_args* args /* host */, t3d_stream_t stream);
+/* F2_* end points (test_semisup.py:136-142) */
+int t3d_f2(const float* f_center, const float* f_hres, const float* f_sres, const float* tot_center,
+           const float* tot_angle, const float* tot_size, int B, int NH, int NS, float* f2_center,
+           float* f2_hres, float* f2_sres, t3d_stream_t stream);
+
+/* model_util.get_box3d_corners_helper (model_util.py:94-119) and get_box3d_corners(_sunrgbd) (:121-167) */
+int t3d_box3d_corners_helper(const float* centers, const float* headings, const float* sizes, int n, float* out,
+                             t3d_stream_t stream);
+int t3d_box3d_corners_all(const float* center, const float* heading_res, const float* size_res, const float* mean_size,
+                          const float* orient_anchors, int B, int NH, int NS, float* out, t3d_stream_t stream);
+
+/* ---- tcgen05 (bf16 in / fp32 accumulate) fused per-point MLP chains ------------------------------------
+ * kind: 0 inst_seg conv1-5 + max (semisup_models.py:76-97), 1 tnet convs + max (:172-189, model_util.py:300-316),
+ *       2 box_est convs + max (:224-245), 3 box_pc_mask_model convs + max with the BoxPC features computed
+ *       in the first-layer prologue (:334-376).
+ * Weights are packed once into a caller-owned arena (BN already folded; W[l] is [K,N] row-major fp32 on device). */
+enum { T3D_CHAIN_SEG1 = 0, T3D_CHAIN_TNET = 1, T3D_CHAIN_BOX = 2, T3D_CHAIN_BOXPC = 3 };
+size_t t3d_chain_arena_bytes(int kind);
+int t3d_chain_num_layers(int kind);     /* layer 1 + hidden + final */
+int t3d_chain_tile_points(int kind);
+int t3d_chain_out_channels(int kind);
+int t3d_pack_chain(int kind, const float* const* W /* host array of device ptrs */,
+                   const float* const* bias /* host array of device ptrs */, void* arena, t3d_stream_t stream);
+/* out [B,FC] is zeroed by the call. idx/count/tiles/num_tiles describe compacted (or gathered) points;
+ * all NULL = dense over the N points.  emit (seg1 only): bf16 [B*N,64] point_feat for stage 2. */
+int t3d_chain_max_bf16(int kind, const float* pc, int B, int N, int C, const float* center, const int* idx,
+                       int idx_stride, const int* count, const void* tiles, const int* num_tiles,
+                       const float* box_center, const float* box_dims, const float* box_orient,
+                       const void* arena, float* out, void* emit, t3d_stream_t stream);
+
+/* inst_seg conv6'..conv10 (semisup_models.py:107-135) with conv6's global half folded into gbias [B,512]. */
+size_t t3d_seg2_arena_bytes(void);
+int t3d_pack_seg2(const float* W6p /* [64,512] */, const float* W7 /* [512,256] */, const float* W8 /* [256,128] */,
+                  const float* W9 /* [128,128] */, const float* b7, const float* b8, const float* b9,
+                  const float* W10 /* [128,2] */, const float* b10, void* arena, t3d_stream_t stream);
+int t3d_seg_stage2_bf16(const void* point_feat /* bf16 [B*N,64] */, const float* gbias, const void* arena,
+                        float* logits, int B, int N, t3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

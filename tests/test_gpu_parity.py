@@ -1,0 +1,286 @@
+"""-m gpu: parity of the B200 path (through the C ABI) against the oracle on the same seeded inputs.
+
+Bars (BASELINE north_star): integer / index outputs bit-exact when fed identical logits;
+fp32 mode within 1e-4 (relative to the tensor scale); bf16 mode within rel 1e-2 / abs 1e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+from util import model_F_setup, oracle_model_F, assert_close, err_stats
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from transferable3d_b200 import runtime as rt, semisup_models as sm, model_util as mu
+    from transferable3d_b200 import test_semisup as ts, boxpc_sunrgbd as bp, tf_util as tu
+    from transferable3d_b200 import frustum_pointnets_v1 as fpn, weights, synth, config
+
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def setup():
+    variables, batch, FLAGS, info = model_F_setup(4)
+    ologits, oep = oracle_model_F(variables, batch, FLAGS)
+    store = rt.VariableStore(variables, DEV)
+    rt.set_default_store(store)
+    pc = torch.as_tensor(batch['pc']).to(DEV)
+    oh = torch.as_tensor(batch['one_hot']).to(DEV)
+    return dict(variables=variables, batch=batch, FLAGS=FLAGS, ologits=ologits, oep=oep, store=store, pc=pc, oh=oh)
+
+
+def scale_close(got, ref, tol, what):
+    """max |got-ref| <= tol * mean|ref| (fp32-mode bar: 1e-4 of the tensor scale)."""
+    got, ref = got.detach().float().cpu().numpy(), ref.detach().float().cpu().numpy()
+    s = err_stats(got, ref)
+    assert np.isfinite(got).all(), what
+    assert s['max_abs'] <= tol * max(s['ref_scale'], 1e-6), (what, s)
+
+
+# ------------------------------------------------------------------------------------------ unit kernels
+
+@pytest.mark.parametrize('M,K,N,act', [(100, 3, 128, 'relu'), (257, 522, 67, None), (2048, 64, 64, 'leaky_relu'),
+                                       (33, 1034, 512, 'tanh'), (4096, 128, 2, None)])
+def test_linear_f32(M, K, N, act, built_lib):
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(K, N, generator=g) / np.sqrt(K)
+    b = torch.randn(N, generator=g)
+    ref = x.double() @ w.double() + b.double()
+    ref = {'relu': torch.relu, 'leaky_relu': lambda t: torch.nn.functional.leaky_relu(t, 0.2), 'tanh': torch.tanh,
+           None: lambda t: t}[act](ref)
+    y, _ = rt.linear(x.to(DEV), w.to(DEV), b.to(DEV), act)
+    assert_close(y.cpu().numpy(), ref.numpy(), 1e-5, 1e-5, 'linear')
+
+
+def test_linear_f32_group_bias_mask_and_max(built_lib):
+    g = torch.Generator().manual_seed(3)
+    B, n, K, N = 5, 192, 70, 130
+    x = torch.randn(B * n, K, generator=g)
+    w = torch.randn(K, N, generator=g) / np.sqrt(K)
+    b = torch.randn(N, generator=g)
+    gb = torch.randn(B, N, generator=g)
+    rm = (torch.rand(B * n, generator=g) > 0.4).float()
+    rm[2 * n:3 * n] = 0                                                    # an all-masked group -> zeros
+    ref = torch.relu(x.double() @ w.double() + b.double() + gb.double().repeat_interleave(n, dim=0)) * rm.double()[:, None]
+    y, gm = rt.linear(x.to(DEV), w.to(DEV), b.to(DEV), 'relu', gbias=gb.to(DEV), rows_per_group=n,
+                      rowmask=rm.to(DEV), gmax_groups=B)
+    assert_close(y.cpu().numpy(), ref.numpy(), 1e-5, 1e-5, 'linear y')
+    assert_close(gm.cpu().numpy(), ref.reshape(B, n, N).max(dim=1).values.numpy(), 1e-5, 1e-5, 'linear gmax')
+    assert float(gm[2].abs().max()) == 0.0
+
+
+def test_mask_centroid_compaction_bit_exact(built_lib):
+    from oracle import semisup_models as osm
+    g = torch.Generator().manual_seed(0)
+    B, N = 7, 2048
+    pc = torch.randn(B, N, 6, generator=g)
+    logits = torch.randn(B, N, 2, generator=g)
+    logits[0, :, 0] = logits[0, :, 1]                # all ties -> empty mask
+    logits[1, :, 0] = logits[1, :, 1] - 1            # full mask
+    logits[2, 5:, 0] = logits[2, 5:, 1] + 1          # 5 points
+    logits[3, ::2, 0] = logits[3, ::2, 1]            # ties on every other point
+    omask, omean, _, oxyz1 = osm.subtract_points_mean(pc, logits)
+    mask, count, mean, xyz1, idx = rt.mask_centroid(logits.to(DEV), pc.to(DEV), want_xyz_stage1=True)
+    assert torch.equal(mask.cpu(), omask[..., 0])
+    assert torch.equal(count.cpu().long(), omask[..., 0].sum(dim=1).long())
+    assert count[0].item() == 0 and count[1].item() == N and count[2].item() == 5
+    for b in range(B):
+        n = int(count[b])
+        assert np.array_equal(idx[b, :n].cpu().numpy(), np.where(omask[b, :, 0].numpy() > 0.5)[0])
+    assert_close(mean.cpu().numpy(), omean[:, 0].numpy(), 1e-5, 1e-5, 'mean')
+    assert_close(xyz1.cpu().numpy(), oxyz1.numpy(), 1e-5, 1e-5, 'xyz_stage1')
+
+
+@pytest.mark.parametrize('mode', ['philox', 'numpy_legacy'])
+def test_resample_indices_bit_exact(mode, built_lib):
+    from oracle import model_util as omu
+    rng = np.random.RandomState(1)
+    N, M = 2048, 512
+    counts = [0, 1, 5, 511, 512, 513, 1000, 2048]
+    B = len(counts)
+    mask = np.zeros((B, N), np.float32)
+    for i, c in enumerate(counts):
+        mask[i, rng.permutation(N)[:c]] = 1
+    pc = torch.randn(B, N, 6, generator=torch.Generator().manual_seed(4))
+    mu.set_resample_rng(mode, seed=1234)
+    obj, ind = mu.tf_gather_object_pc(pc.to(DEV), torch.as_tensor(mask).to(DEV), M)
+    oobj, oind = omu.tf_gather_object_pc(pc, torch.as_tensor(mask), M, rng_mode=mode, rng=np.random.RandomState(1234), seed=1234)
+    assert ind.dtype == torch.int32
+    assert np.array_equal(ind.cpu().numpy(), oind)
+    assert torch.equal(obj.cpu(), oobj)                       # pure gather: bit-exact
+    mu.set_resample_rng('philox', seed=0)
+
+
+def test_head_kernels_vs_oracle(built_lib, setup):
+    from oracle import tf_util as otu, model_util as omu
+    from transferable3d_b200.constants import MEAN_DIMS_ARR, ORIENT_ANCHORS
+    g = torch.Generator().manual_seed(8)
+    B = 37
+    out = torch.randn(B, 67, generator=g)
+    out[3, 3:15] = 0.25                                        # argmax ties -> first
+    s1 = torch.randn(B, 3, generator=g)
+    st = setup['store']
+    p = tu.parse_box_output(out.to(DEV), s1.to(DEV), st.const('MEAN_DIMS_ARR', MEAN_DIMS_ARR), st.const('ORIENT_ANCHORS', ORIENT_ANCHORS))
+    from oracle.semisup_models import parse_box_output as oparse
+    oep = {}
+    opred = oparse(out, s1, oep, '')
+    for k in ('center', 'heading_scores', 'heading_residuals', 'size_scores', 'size_residuals', 'size_residuals_normalized'):
+        assert_close(p[k].cpu().numpy(), oep[k].numpy(), 1e-6, 1e-6, k)
+    da = torch.as_tensor(MEAN_DIMS_ARR, dtype=torch.float32)
+    oa = torch.as_tensor(ORIENT_ANCHORS, dtype=torch.float32)
+    oreg = otu.tf_convert_box_params_from_anchor_to_reg_format_multi(opred, None, da, oa)
+    for a, b in zip(p['reg'], oreg):
+        assert_close(a.cpu().numpy(), b.numpy(), 1e-6, 1e-6, 'reg')
+    reg2 = tu.tf_convert_box_params_from_anchor_to_reg_format_multi(tuple(t.to(DEV) for t in opred), None, da.to(DEV), oa.to(DEV))
+    for a, b in zip(reg2, oreg):
+        assert_close(a.cpu().numpy(), b.numpy(), 1e-6, 1e-6, 'reg2')
+    corners = mu.get_box3d_corners_sunrgbd(p['center'], p['heading_residuals'], p['size_residuals'])
+    ocorners = omu.get_box3d_corners_sunrgbd(oep['center'], oep['heading_residuals'], oep['size_residuals'])
+    assert_close(corners.cpu().numpy(), ocorners.numpy(), 1e-5, 1e-5, 'corners')
+    rep = tu.tf_get_box_pc_representation(tuple(t.to(DEV) for t in oreg), setup['pc'][:1].repeat(B, 1, 1))
+    orep = otu.tf_get_box_pc_representation(oreg, setup['pc'][:1].cpu().repeat(B, 1, 1))
+    assert_close(rep.cpu().numpy(), orep.numpy(), 1e-5, 1e-5, 'boxpc rep')
+
+
+# ------------------------------------------------------------------------------------------ model F
+
+def test_model_F_fp32_mode_vs_oracle(built_lib, setup):
+    with rt.precision('fp32'), torch.no_grad():
+        logits, ep = ts.build_graph(setup['FLAGS'], setup['pc'], setup['oh'])
+    scale_close(logits, setup['ologits'], 1e-4, 'logits')
+    # the mask is a strict compare of two fp32 logits: allow the rare 1-ulp flip, then compare downstream
+    agree = ((logits[..., 0] < logits[..., 1]).cpu() == (setup['ologits'][..., 0] < setup['ologits'][..., 1])).float().mean()
+    assert agree > 0.9995
+    if agree == 1.0:
+        for k in ('stage1_center', 'feats_lv1', 'F_center', 'F_heading_scores', 'F_heading_residuals', 'F_size_scores',
+                  'F_size_residuals', 'F2_center', 'F2_heading_residuals', 'F2_size_residuals', 'boxpc_fit_prob'):
+            scale_close(ep[k], setup['oep'][k], 2e-4, k)
+
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 2e-4), ('bf16', None)])
+def test_stages_on_identical_inputs(mode, tol, built_lib, setup):
+    """Every stage fed the ORACLE's inputs (identical logits / centres / boxes)."""
+    oep, ologits, FLAGS, pc, oh = setup['oep'], setup['ologits'], setup['FLAGS'], setup['pc'], setup['oh']
+
+    def chk(got, ref, what):
+        if tol is not None:
+            scale_close(got, ref, tol, what)
+        else:   # bf16: rel 1e-2 / abs 1e-3 of the tensor scale
+            g, r = got.detach().float().cpu().numpy(), ref.detach().float().cpu().numpy()
+            sc = max(float(np.abs(r).mean()), 1e-6)
+            assert_close(g / sc, r / sc, 1e-2, 1e-2, what, frac=0.995)
+    with rt.precision(mode), torch.no_grad():
+        olog = ologits.to(DEV).contiguous()
+        mask, mean, xyz, xyz1 = sm.subtract_points_mean(pc, olog)
+        assert torch.equal(mask.cpu(), (ologits[..., 0:1] < ologits[..., 1:2]).float())      # bit-exact
+        ep = {}
+        with rt.variable_scope('class_agnostic'):
+            s1 = sm.v1_tnet(xyz1, mask, mean, None, ep, False, scope='tnet')
+            chk(s1, oep['stage1_center'], 'stage1_center')
+            os1 = oep['stage1_center'].to(DEV)
+            sm.v1_box_est(sm.subtract_1st_stage_center(xyz, os1), os1, mask, None, ep, False, scope='box_est')
+            chk(ep['feats_lv1'], oep['feats_lv1'], 'feats_lv1')
+            chk(ep['box_params'], oep['box_params'], 'box_params')
+        obox = tuple(t.to(DEV).contiguous() for t in oep['F_pred_box_reg'])
+        with rt.variable_scope('D_boxpc_branch'):
+            _, bep = bp.get_model((obox, pc), False, oh, use_one_hot_vec=False, c=FLAGS)
+        chk(bep['boxpc_feats_dict']['box_pc_mask_model_feats_lv1'], oep['boxpc_feats_dict']['box_pc_mask_model_feats_lv1'], 'boxpc lv1')
+        chk(bep['boxpc_delta_center'], oep['boxpc_delta_center'], 'boxpc delta center')
+        chk(bep['logits_for_weigh'], oep['boxpc_fit_prob'], 'boxpc fit prob')
+
+
+def test_seg_bf16_vs_oracle(built_lib, setup):
+    with rt.precision('bf16'), torch.no_grad():
+        logits = sm.v1_inst_seg(setup['pc'], None, None, {}, False, scope='class_agnostic/inst_seg')
+    g, r = logits.cpu().numpy(), setup['ologits'].numpy()
+    assert np.isfinite(g).all()
+    assert_close(g, r, 1e-2, 1e-3, 'seg logits bf16', frac=0.97)
+    s = err_stats(g, r)
+    assert s['max_abs'] <= 0.05 * s['ref_scale'], s
+
+
+def test_cfg3_pipeline_fp32_vs_oracle(built_lib):
+    """F-PointNet v1 pipeline (gather-512, philox RNG) with model-A variables."""
+    from oracle.tf_layers import VarStore
+    from oracle import semisup_models as osm, model_util as omu
+    from transferable3d_b200.constants import MEAN_DIMS_ARR
+    variables, info = weights.standard_model_A()
+    b = synth.make_batch(3, 2048, 6, seed=77)
+    pc_c, oh_c = torch.as_tensor(b['pc']), torch.as_tensor(b['one_hot'])
+    vs = VarStore(variables)
+    with torch.no_grad():
+        oep = {}
+        ologits = osm.v1_inst_seg(pc_c, None, oh_c, oep, False, vs, scope='inst_seg')
+    store = rt.VariableStore(variables, DEV)
+    rt.set_default_store(store)
+    mu.set_resample_rng('philox', seed=5)
+    with rt.precision('fp32'), torch.no_grad():
+        ep = fpn.get_model(pc_c.to(DEV), oh_c.to(DEV), False)
+    scale_close(ep['mask_logits'], ologits, 1e-4, 'cfg3 logits')
+    # continue the oracle from the GPU logits so the masks are identical, then everything must agree
+    with torch.no_grad():
+        glog = ep['mask_logits'].cpu()
+        obj, omean, oep = omu.point_cloud_masking(pc_c, glog, oep, rng_mode='philox', seed=5)
+        assert np.array_equal(ep['object_pc_indices'].cpu().numpy(), oep['object_pc_indices'])
+        with vs.variable_scope('tnet'):
+            delta, _ = omu.get_center_regression_net(obj, oh_c, False, None, oep, vs)
+        s1 = delta + omean
+        from oracle.tf_layers import conv2d, fully_connected, max_pool_points
+        with vs.variable_scope('box_est'):
+            net = obj - delta.unsqueeze(1)
+            for nm, c in (('conv-reg1', 128), ('conv-reg2', 128), ('conv-reg3', 256), ('conv-reg4', 512)):
+                net = conv2d(net, c, [1, 1], vs, nm, True, False)
+            net = torch.cat([max_pool_points(net), oh_c], dim=1)
+            net = fully_connected(net, 512, vs, 'fc1', True, False)
+            net = fully_connected(net, 256, vs, 'fc2', True, False)
+            out = fully_connected(net, 67, vs, 'fc3', activation_fn=None)
+        oep = omu.parse_output_to_tensors(out, oep, 12, MEAN_DIMS_ARR)
+    scale_close(ep['stage1_center'], s1, 2e-4, 'cfg3 stage1_center')
+    scale_close(ep['center'], oep['center_boxnet'] + s1, 2e-4, 'cfg3 center')
+    scale_close(ep['size_residuals'], oep['size_residuals'], 2e-4, 'cfg3 size residuals')
+    scale_close(ep['heading_scores'], oep['heading_scores'], 2e-4, 'cfg3 heading scores')
+    rt.set_default_store(None)
+
+
+def test_inference_runner_matches_oracle_runner(built_lib, setup):
+    from oracle.tf_layers import VarStore
+    from oracle import test_semisup as ots
+    b, FLAGS = setup['batch'], setup['FLAGS']
+    rt.set_default_store(setup['store'])
+    sess, ops = ts.get_model(4, 2048, 6, FLAGS, setup['store'])
+    with rt.precision('fp32'):
+        res = ts.inference(sess, ops, b['pc'], b['one_hot'], 2, prefix='F2_', use_boxpc_fit_prob=True)
+    ores = ots.inference(VarStore(setup['variables']), FLAGS, b['pc'], b['one_hot'], 2, prefix='F2_', use_boxpc_fit_prob=True)
+    assert (res[0] == ores[0]).mean() > 0.9995                      # pred_seg
+    assert np.array_equal(res[2], ores[2]) and np.array_equal(res[4], ores[4])
+    if (res[0] == ores[0]).all():
+        assert_close(res[1], ores[1], 1e-3, 1e-3, 'centers')
+        assert_close(res[6], ores[6], 1e-3, 1e-3, 'scores')
+
+
+def test_size_independent_properties_bf16(built_lib, setup):
+    """Properties that hold at any size: the max-pool is invariant to the order of the points and to
+    duplicated points, frustums are independent of their batch neighbours, empty mask -> zero features."""
+    pc, FLAGS = setup['pc'], setup['FLAGS']
+    st = setup['store']
+    rt.set_default_store(st)
+    with rt.precision('bf16'), torch.no_grad():
+        arena = st.chain_arena('class_agnostic/inst_seg', rt.CHAIN_SEG1, ['conv1', 'conv2', 'conv3', 'conv4', 'conv5'])
+        g1 = rt.chain_max(rt.CHAIN_SEG1, pc, arena)
+        perm = torch.randperm(2048, device=DEV)
+        g2 = rt.chain_max(rt.CHAIN_SEG1, pc[:, perm].contiguous(), arena)
+        assert torch.equal(g1, g2)
+        g3 = rt.chain_max(rt.CHAIN_SEG1, pc[1:3].contiguous(), arena)
+        assert torch.equal(g1[1:3], g3)
+        dup = torch.cat([pc[:, :1024], pc[:, :1024]], dim=1).contiguous()
+        half = rt.chain_max(rt.CHAIN_SEG1, pc[:, :1024].contiguous(), arena)
+        assert torch.equal(rt.chain_max(rt.CHAIN_SEG1, dup, arena), half)
+        # empty mask -> zero T-Net feature -> stage1_center = fc(0) + 0 for every frustum alike
+        logits = torch.zeros(4, 2048, 2, device=DEV)
+        mask, mean, xyz, xyz1 = sm.subtract_points_mean(pc, logits)
+        assert float(mask.sum()) == 0 and float(mean.abs().sum()) == 0
+        ep = {}
+        s1 = sm.v1_tnet(xyz1, mask, mean, None, ep, False, scope='class_agnostic/tnet')
+        assert torch.equal(s1[0], s1[1]) and torch.isfinite(s1).all()

@@ -1,0 +1,225 @@
+"""CPU tests of the oracle itself: the only numeric example the reference holds (softmax weight
+table, models/config.py:137-142), published Philox KAT vectors, numpy-stream equivalences behind
+mask_to_indices, closed forms checked against literal restatements, tiny hand-computed cases,
+and the committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import tf_util, model_util, semisup_models, weak_losses
+from oracle.tf_layers import VarStore
+from transferable3d_b200 import weights, synth, config
+from transferable3d_b200.constants import MEAN_DIMS_ARR
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def test_softmax_weight_table_from_reference_config():
+    # models/config.py:137-142 -- the reference's only numeric example
+    pts = np.array([0, 0.1, 0.2, 0.4, 0.6, 0.8, 0.9, 1.0])
+    table = {1: [0.071, 0.079, 0.087, 0.106, 0.13, 0.158, 0.175, 0.194],
+             5: [0.003, 0.005, 0.008, 0.023, 0.062, 0.168, 0.276, 0.455],
+             10: [0.0, 0.0, 0.0, 0.002, 0.012, 0.089, 0.241, 0.656],
+             20: [0.0, 0.0, 0.0, 0.0, 0.0, 0.016, 0.117, 0.867],
+             40: [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.018, 0.982]}
+    p2 = torch.tensor(np.stack([pts, pts], axis=1))[None]               # (1,8,2)
+    for scale, w in table.items():
+        # right-closeness softmax weights are what tf_get_2D_softmax_bbox_of_points uses for `right`
+        got = torch.softmax(torch.tensor((pts - pts.min()) / (pts.max() - pts.min()) * scale), dim=0).numpy()
+        assert np.allclose(got, w, atol=6e-4), (scale, got)
+        box = tf_util.tf_get_2D_softmax_bbox_of_points(p2, float(scale))[0].numpy()
+        assert abs(box[2] - float((pts * got).sum())) < 1e-9
+        assert box[0] < box[2] and abs(box[0] - (1 - box[2])) < 1e-9      # symmetric point set
+
+
+def test_philox_published_kat_vectors():
+    # Random123 kat_vectors, philox4x32 10 rounds
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, exp in kats:
+        o = model_util.philox4x32_10(*[np.array([c], dtype=np.uint32) for c in ctr], key[0], key[1])
+        assert tuple(int(x[0]) for x in o) == exp
+
+
+def test_numpy_stream_equivalences_behind_mask_to_indices():
+    # choice(replace=False) == permutation[:k]; choice(replace=True) == randint
+    a = np.random.RandomState(5).choice(700, 512, replace=False)
+    b = np.random.RandomState(5).permutation(700)[:512]
+    assert (a == b).all()
+    a = np.random.RandomState(5).choice(100, 412, replace=True)
+    b = np.random.RandomState(5).randint(0, 100, 412)
+    assert (a == b).all()
+
+
+@pytest.mark.parametrize('mode', ['numpy_legacy', 'philox'])
+def test_mask_to_indices_properties(mode):
+    rng = np.random.RandomState(0)
+    N, M = 2048, 512
+    counts = [0, 1, 5, 511, 512, 513, 2048]
+    mask = np.zeros((len(counts), N), np.float32)
+    for i, c in enumerate(counts):
+        mask[i, rng.permutation(N)[:c]] = 1
+    kw = dict(rng_mode=mode, rng=np.random.RandomState(3), seed=77)
+    ind = model_util.mask_to_indices(mask, M, **kw)
+    assert ind.dtype == np.int32 and ind.shape == (len(counts), M, 2)
+    for i, c in enumerate(counts):
+        assert (ind[i, :, 0] == i).all()
+        pts = ind[i, :, 1]
+        if c == 0:
+            assert (pts == 0).all()                         # empty mask -> point 0 repeated
+            continue
+        assert mask[i, pts].all()                           # only masked-in points
+        if c > M:
+            assert len(set(pts.tolist())) == M              # without replacement
+        else:
+            assert set(pts.tolist()) == set(np.where(mask[i] > 0.5)[0].tolist())   # every point at least once
+    # deterministic
+    kw2 = dict(rng_mode=mode, rng=np.random.RandomState(3), seed=77)
+    assert (model_util.mask_to_indices(mask, M, **kw2) == ind).all()
+
+
+def test_box_pc_representation_closed_form():
+    # literal restatement (surface points + normals) vs the closed form the kernels use
+    g = torch.Generator().manual_seed(0)
+    B, N = 3, 50
+    pc = torch.randn(B, N, 6, generator=g, dtype=torch.float64)
+    center = torch.randn(B, 3, generator=g, dtype=torch.float64)
+    dims = torch.rand(B, 3, generator=g, dtype=torch.float64) + 0.5
+    th = torch.rand(B, generator=g, dtype=torch.float64) * 6 - 3
+    rep = tf_util.tf_get_box_pc_representation((center, dims, th), pc)
+    d = pc[:, :, :3] - center[:, None]
+    c, s = torch.cos(th)[:, None], torch.sin(th)[:, None]
+    xr, zr = c * d[..., 0] - s * d[..., 2], s * d[..., 0] + c * d[..., 2]
+    l, w, h = dims[:, 0:1], dims[:, 1:2], dims[:, 2:3]
+    closed = torch.stack([l / 2 - xr, l / 2 + xr, h / 2 - d[..., 1], h / 2 + d[..., 1], w / 2 - zr, w / 2 + zr], dim=2)
+    assert torch.allclose(rep[:, :, 6:], closed, atol=1e-12)
+    assert torch.equal(rep[:, :, :6], pc)
+
+
+def test_reprojection_corner_set_matches_get_3d_box():
+    # tf_create_3D_box_by_vertices_multi == get_3d_box corners as a set
+    g = torch.Generator().manual_seed(1)
+    B = 5
+    center = torch.randn(B, 3, generator=g, dtype=torch.float64)
+    dims = torch.rand(B, 3, generator=g, dtype=torch.float64) + 0.5
+    th = torch.rand(B, generator=g, dtype=torch.float64) * 6 - 3
+    _, c1 = tf_util.tf_create_3D_box_by_vertices_multi((center, dims, th), apply_translation=True)
+    c2 = model_util.get_box3d_corners_helper(center, th, dims)
+    for b in range(B):
+        a = sorted(map(tuple, np.round(c1[b].numpy(), 9).tolist()))
+        bb = sorted(map(tuple, np.round(c2[b].numpy(), 9).tolist()))
+        assert np.allclose(a, bb, atol=1e-8)
+
+
+def test_synth_projection_matches_oracle_projection():
+    b = synth.make_batch(4, 64, 6, seed=5)
+    pts = torch.randn(4, 8, 3, dtype=torch.float64) + torch.tensor([0., 0., 4.], dtype=torch.float64)
+    uv1 = synth.project_upright_camera_to_image(pts.numpy(), b['Rtilt'].astype(np.float64), b['K'].astype(np.float64))
+    depth = tf_util.project_upright_camera_to_upright_depth(pts)
+    uv2, _ = tf_util.project_upright_depth_to_image(depth, torch.as_tensor(b['Rtilt'], dtype=torch.float64),
+                                                    torch.as_tensor(b['K'], dtype=torch.float64))
+    assert np.allclose(uv1, uv2.numpy(), atol=1e-9)
+
+
+def test_tiny_hand_computed_mask_and_centroid():
+    pc = torch.tensor([[[1., 2., 3., 9., 9., 9.], [3., 4., 5., 9., 9., 9.], [10., 10., 10., 0., 0., 0.], [0., 0., 0., 0., 0., 0.]],
+                       [[1., 1., 1., 0., 0., 0.]] * 4])
+    logits = torch.tensor([[[0., 1.], [0.5, 0.6], [1., 0.], [2., 2.]],      # tie -> 0
+                           [[1., 0.]] * 4])                                   # empty mask
+    mask, mean, xyz, xyz1 = semisup_models.subtract_points_mean(pc, logits)
+    assert mask[..., 0].tolist() == [[1., 1., 0., 0.], [0., 0., 0., 0.]]
+    assert torch.allclose(mean[0, 0], torch.tensor([2., 3., 4.]))
+    assert torch.allclose(mean[1, 0], torch.zeros(3))                         # divides by max(count,1)
+    assert torch.allclose(xyz1[0, 2], torch.tensor([8., 7., 6.]))
+
+
+def test_anchor_to_reg_first_max_and_clamp():
+    center = torch.zeros(2, 3)
+    dims_cls = torch.tensor([[1., 3., 3.] + [0.] * 7, [0.] * 10])            # tie -> first
+    dims_reg = torch.zeros(2, 10, 3)
+    dims_reg[0, 1] = torch.tensor([-10., 0.1, 0.2])                          # clamp at 1e-5
+    orient_cls = torch.zeros(2, 12)
+    orient_cls[0, 5] = 1.
+    orient_reg = torch.arange(24, dtype=torch.float32).reshape(2, 12) * 0.01
+    da = torch.as_tensor(MEAN_DIMS_ARR, dtype=torch.float32)
+    oa = torch.as_tensor(np.arange(0, 2 * np.pi, 2 * np.pi / 12), dtype=torch.float32)
+    c, d, o = tf_util.tf_convert_box_params_from_anchor_to_reg_format_multi((center, dims_cls, dims_reg, orient_cls, orient_reg), None, da, oa)
+    assert abs(d[0, 0].item() - 1e-5) < 1e-12 and abs(d[0, 1].item() - (MEAN_DIMS_ARR[1, 1] + 0.1)) < 1e-6
+    assert torch.allclose(d[1], da[0])
+    assert abs(o[0].item() - (5 * 2 * np.pi / 12 + 0.05)) < 1e-6 and abs(o[1].item() - 0.12) < 1e-6
+
+
+def test_intraclass_variance_empty_group_is_zero():
+    dims = torch.tensor([[1., 1., 1.], [3., 1., 1.], [5., 5., 5.]])
+    cls = torch.tensor([0, 0, 2])
+    train = [True, True, True] + [False] * 7
+    l = weak_losses.get_intraclass_variance_loss_v1(dims, cls, train, 10, True, 0.2, 'huber')
+    # class 0: mean (2,1,1): errors 1,0,0,1,0,0 -> huber .5 each -> sum 1 / 6 elements; class 1 empty -> 0; class 2 -> 0
+    assert abs(l.item() - (1.0 / 6.0) / 3.0) < 1e-7
+
+
+def test_bn_fold_equals_unfolded_layer_and_folded_conv6():
+    v = weights.make_weights_model_F(seed=3)
+    b = synth.make_batch(2, 64, 6, seed=9)
+    vs = VarStore(v, dtype=torch.float64)
+    pc = torch.as_tensor(b['pc'], dtype=torch.float64)
+    ep = {}
+    with torch.no_grad(), vs.variable_scope('class_agnostic'):
+        lit = semisup_models.v1_inst_seg(pc, None, None, ep, False, vs, scope='inst_seg')
+        vs.literal = False
+        fold = semisup_models.v1_inst_seg(pc, None, None, ep, False, vs, scope='inst_seg')
+    assert torch.allclose(lit, fold, atol=1e-10)
+    w, bb = weights.fold_bn(v, 'class_agnostic/inst_seg/conv1')
+    y = np.maximum(b['pc'].reshape(-1, 6).astype(np.float64) @ w.astype(np.float64) + bb, 0)
+    from oracle.tf_layers import conv2d
+    with torch.no_grad(), vs.variable_scope('class_agnostic/inst_seg'):
+        y2 = conv2d(pc, 64, [1, 6], vs, 'conv1', True, False)
+    assert np.allclose(y, y2.reshape(-1, 64).numpy(), atol=1e-5)
+
+
+def test_masked_max_equals_max_over_compacted_points():
+    # the identity the B200 path relies on: max_n(relu(.)*mask) == max(0, max over masked-in points)
+    g = torch.Generator().manual_seed(2)
+    act = torch.relu(torch.randn(3, 40, 7, generator=g))
+    mask = (torch.rand(3, 40, 1, generator=g) > 0.5).float()
+    mask[2] = 0
+    ref = (act * mask).max(dim=1).values
+    for b in range(3):
+        sel = act[b][mask[b, :, 0] > 0.5]
+        got = sel.max(dim=0).values if sel.shape[0] else torch.zeros(7)
+        assert torch.equal(ref[b], got)
+
+
+def test_training_mode_bn_updates_moving_stats():
+    v = weights.make_weights_model_F(seed=3)
+    vs = VarStore(v)
+    x = torch.randn(16, 512)
+    before = vs.vars['class_agnostic/box_est/fc1/bn/moving_mean'].clone()
+    from oracle.tf_layers import fully_connected
+    with vs.variable_scope('class_agnostic/box_est'):
+        y = fully_connected(x, 512, vs, 'fc1', True, True, bn_decay=0.5)
+    after = vs.vars['class_agnostic/box_est/fc1/bn/moving_mean']
+    assert not torch.allclose(before, after)
+    pre = x @ vs.vars['class_agnostic/box_est/fc1/weights'] + vs.vars['class_agnostic/box_est/fc1/biases']
+    assert torch.allclose(after, 0.5 * before + 0.5 * pre.mean(0), atol=1e-5)
+
+
+def test_golden_model_F_fixture():
+    """Committed fixture generated by tests/golden/make_golden.py from the oracle (the reference cannot
+    run here, so this pins the oracle against regressions, not against TF)."""
+    path = os.path.join(GOLDEN, 'model_F_tiny.npz')
+    z = np.load(path)
+    variables = weights.make_weights_model_F(seed=int(z['weight_seed']), with_boxpc=True)
+    b = synth.make_batch(int(z['B']), int(z['N']), 6, seed=int(z['data_seed']))
+    from oracle import test_semisup
+    vs = VarStore(variables)
+    with torch.no_grad():
+        logits, ep = test_semisup.run_graph(vs, config.cfg(), torch.as_tensor(b['pc']), torch.as_tensor(b['one_hot']))
+    assert np.allclose(logits.numpy(), z['logits'], atol=2e-5)
+    for k in ('F2_center', 'F_size_residuals', 'F_heading_scores', 'boxpc_fit_prob', 'stage1_center'):
+        assert np.allclose(ep[k].numpy(), z[k], atol=2e-5), k

@@ -1,0 +1,107 @@
+"""ctypes binding of libt3d_b200.so (C ABI in include/t3d_b200.h).
+
+There is no CPU or library fallback: if the shared object is missing, or a call is made with
+tensors that are not on a CUDA device, this module raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libt3d_b200.so')
+
+_c = ctypes
+_P = _c.c_void_p
+_I = _c.c_int
+
+
+class t3d_parse_args(_c.Structure):
+    _fields_ = [('output', _P), ('stage1_center', _P), ('mean_size', _P), ('orient_anchors', _P),
+                ('B', _I), ('NH', _I), ('NS', _I),
+                ('center', _P), ('heading_scores', _P), ('heading_res_norm', _P), ('heading_res', _P),
+                ('size_scores', _P), ('size_res_norm', _P), ('size_res', _P),
+                ('reg_center', _P), ('reg_dims', _P), ('reg_orient', _P)]
+
+
+class t3d_refine_args(_c.Structure):
+    _fields_ = [('out9', _P), ('B', _I), ('weigh_pred_by_conf', _I), ('weigh_during_test', _I),
+                ('fit_logits', _P), ('fit_prob', _P), ('pred_fit', _P),
+                ('delta_center', _P), ('delta_size', _P), ('delta_angle', _P),
+                ('box_center', _P), ('box_dims', _P), ('box_orient', _P),
+                ('tot_center', _P), ('tot_size', _P), ('tot_angle', _P)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/t3d_b200.h
+SIGNATURES = {
+    't3d_version': (_I, []),
+    't3d_error_string': (_c.c_char_p, [_I]),
+    't3d_linear_f32': (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    't3d_mask_centroid': (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    't3d_resample': (_I, [_P, _P, _I, _I, _I, _I, _c.c_uint64, _P, _P, _P, _I, _P, _I, _P, _P]),
+    't3d_build_tiles': (_I, [_P, _I, _I, _P, _P, _P]),
+    't3d_prepare_xyz': (_I, [_P, _I, _I, _I, _P, _P, _P]),
+    't3d_boxpc_features': (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    't3d_parse_box': (_I, [_c.POINTER(t3d_parse_args), _P]),
+    't3d_anchor_to_reg': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    't3d_boxpc_refine': (_I, [_c.POINTER(t3d_refine_args), _P]),
+    't3d_f2': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    't3d_box3d_corners_helper': (_I, [_P, _P, _P, _I, _P, _P]),
+    't3d_box3d_corners_all': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P]),
+    't3d_chain_arena_bytes': (_c.c_size_t, [_I]),
+    't3d_chain_num_layers': (_I, [_I]),
+    't3d_chain_tile_points': (_I, [_I]),
+    't3d_chain_out_channels': (_I, [_I]),
+    't3d_pack_chain': (_I, [_I, _c.POINTER(_P), _c.POINTER(_P), _P, _P]),
+    't3d_chain_max_bf16': (_I, [_I, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    't3d_seg2_arena_bytes': (_c.c_size_t, []),
+    't3d_pack_seg2': (_I, [_P] * 10 + [_P]),
+    't3d_seg_stage2_bf16': (_I, [_P, _P, _P, _P, _I, _I, _P]),
+}
+
+_lib = None
+
+
+class T3DError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (no compute). Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise T3DError('%s is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                           '(nvcc, sm_100a). There is no CPU fallback.' % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        msg = load().t3d_error_string(int(code))
+        raise (ValueError if code < 0 else T3DError)('t3d call failed (%d): %s' % (code, msg.decode()))
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise T3DError('t3d_b200 ops need CUDA tensors (no CPU fallback)')
+    if not t.is_contiguous():
+        raise ValueError('t3d_b200 ops need contiguous tensors')
+    return _P(t.data_ptr())
+
+
+def stream():
+    return _P(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))

@@ -1,0 +1,266 @@
+// Instance-segmentation stage 2 on tcgen05/TMEM: point_feat(64) -> conv6'(512) -> conv7(256) ->
+// conv8(128) -> conv9(128) -> conv10(2) = mask logits (semisup_models.py:107-135, eval mode, BN folded).
+//
+// The reference tiles the 1024(+10)-wide global feature to every point and runs conv6 on the
+// 1088-wide concat; here the global half of conv6 is folded into a per-frustum bias
+// gbias[b] = b6 + [gfeat_b, one_hot_b] . W6[64:], so conv6' is a K=64 GEMM.
+//
+// Per 128-point tile (points on the UMMA M dimension, channels on N):
+//   conv6' is produced in 4 blocks of 128 channels; each block's epilogue (+gbias, ReLU, bf16)
+//   becomes a K=128 slice of conv7's A operand, so the 512-wide activation only ever exists as two
+//   32 KB slices.  conv7 accumulates its 256 outputs in TMEM across the 4 slices.  conv10 (128->2) is
+//   evaluated on CUDA cores from the fp32 conv9 epilogue registers.
+// TMEM: R6[0]=cols 0..127, R6[1]=128..255 (conv6' blocks, later conv8 / conv9), R7=256..511 (conv7).
+#pragma once
+#include "common.cuh"
+#include "chain_max.cuh"
+
+namespace t3d {
+
+constexpr int kSeg2Chunks = 26;   // per tile: 4 (W6') + 16 (W7) + 4 (W8) + 2 (W9), consumption order below
+// arena = [26 chunk images][b7 256][b8 128][b9 128][W10 128x2][b10 2] fp32
+constexpr int kSeg2Floats = 256 + 128 + 128 + 256 + 2;
+constexpr size_t kSeg2ArenaBytes = (size_t)kSeg2Chunks * kChunkBytes + sizeof(float) * kSeg2Floats;
+
+struct Seg2Args {
+  const __nv_bfloat16* point_feat;   // [B*N, 64] bf16 (emitted by stage 1)
+  const float* gbias;                // [B, 512] fp32 per-frustum conv6 bias (global half + b6, BN folded)
+  const uint8_t* arena;
+  float* logits;                     // [B, N, 2]
+  int B, N;
+};
+
+struct Seg2Smem {
+  static constexpr int IN = 0;                       // [128 x 64] bf16, 16 KB
+  static constexpr int A6 = 16384;                   // 2 x [128 x 128] bf16 (2 K-blocks each), 64 KB
+  static constexpr int A7 = A6 + 65536;              // [128 x 256] bf16 (4 K-blocks), 64 KB
+  static constexpr int RING = A7 + 65536;            // 4 x 16 KB
+  static constexpr int GB = RING + kRingStages * kChunkBytes;   // 2 x 512 fp32
+  static constexpr int FL = GB + 2 * 512 * 4;        // b7,b8,b9,W10,b10
+  static constexpr int BARS = FL + ((kSeg2Floats * 4 + 15) / 16) * 16;
+  // ring_full[4], ring_empty[4], acc_full[3], acc_empty[3], in_ready, in_free, a6_ready[2], a6_free[2], a7_ready, a8_ready
+  static constexpr int NBARS = 2 * kRingStages + 6 + 2 + 4 + 2;
+  static constexpr int TMEM_SLOT = BARS + 8 * NBARS;
+  static constexpr int TOTAL = TMEM_SLOT + 16;
+};
+
+__global__ void __launch_bounds__(384, 1) seg_stage2_kernel(const Seg2Args args) {
+  using L = Seg2Smem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t bar0 = sbase + L::BARS;
+  auto ring_full = [&](int s) { return bar0 + 8u * s; };
+  auto ring_empty = [&](int s) { return bar0 + 8u * (kRingStages + s); };
+  auto acc_full = [&](int r) { return bar0 + 8u * (2 * kRingStages + r); };        // r: 0,1 = R6[r], 2 = R7
+  auto acc_empty = [&](int r) { return bar0 + 8u * (2 * kRingStages + 3 + r); };
+  const uint32_t in_ready = bar0 + 8u * (2 * kRingStages + 6);
+  const uint32_t in_free = bar0 + 8u * (2 * kRingStages + 7);
+  auto a6_ready = [&](int b) { return bar0 + 8u * (2 * kRingStages + 8 + b); };
+  auto a6_free = [&](int b) { return bar0 + 8u * (2 * kRingStages + 10 + b); };
+  const uint32_t a7_ready = bar0 + 8u * (2 * kRingStages + 12);
+  const uint32_t a8_ready = bar0 + 8u * (2 * kRingStages + 13);
+  auto region_col = [&](int r) -> uint32_t { return r == 2 ? 256u : (uint32_t)(r * 128); };
+
+  const int tiles_per_frustum = (args.N + 127) / 128;
+  const int num_tiles = args.B * tiles_per_frustum;
+  const int tile_begin = (int)(((long long)num_tiles * blockIdx.x) / gridDim.x);
+  const int tile_end = (int)(((long long)num_tiles * (blockIdx.x + 1)) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRingStages; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), 1); }
+    for (int r = 0; r < 3; ++r) { mbar_init(acc_full(r), 1); mbar_init(acc_empty(r), 4); }
+    mbar_init(in_ready, 4); mbar_init(in_free, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(a6_ready(b), 4); mbar_init(a6_free(b), 1); }
+    mbar_init(a7_ready, 4); mbar_init(a8_ready, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(sbase + L::TMEM_SLOT);
+  {
+    const float* fsrc = reinterpret_cast<const float*>(args.arena + (size_t)kSeg2Chunks * kChunkBytes);
+    float* fdst = reinterpret_cast<float*>(smem + L::FL);
+    for (int i = threadIdx.x; i < kSeg2Floats; i += blockDim.x) fdst[i] = fsrc[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_SLOT);
+
+  if (warp == 0) {
+    // ================================================================ weight producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int t = tile_begin; t < tile_end; ++t)
+        for (int c = 0; c < kSeg2Chunks; ++c, ++it) {
+          const int s = it % kRingStages;
+          mbar_wait(ring_empty(s), ((it / kRingStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(ring_full(s), kChunkBytes);
+          bulk_g2s(sbase + L::RING + s * kChunkBytes, args.arena + (size_t)c * kChunkBytes, kChunkBytes, ring_full(s));
+        }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, acc_cnt[3] = {0, 0, 0}, a6r_cnt[2] = {0, 0}, tile_iter = 0;
+      const uint32_t idesc = make_idesc_bf16(128, 128);
+      auto mma_chunk = [&](uint32_t a_addr, uint32_t d, bool acc_first) {
+        const int s = it % kRingStages;
+        mbar_wait(ring_full(s), (it / kRingStages) & 1);
+        tc_fence_after();
+        const uint32_t b_addr = sbase + L::RING + s * kChunkBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(d, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32), idesc, (acc_first || k > 0) ? 1u : 0u);
+        umma_commit(ring_empty(s));
+        ++it;
+      };
+      auto job6 = [&](int nb) {
+        const int r = nb & 1;
+        mbar_wait(acc_empty(r), (acc_cnt[r] & 1) ^ 1);
+        tc_fence_after();
+        mma_chunk(sbase + L::IN, tmem_base + region_col(r), false);
+        umma_commit(acc_full(r)); acc_cnt[r]++;
+        if (nb == 3) umma_commit(in_free);
+      };
+      auto job7 = [&](int nb) {
+        const int b = nb & 1;
+        mbar_wait(a6_ready(b), a6r_cnt[b] & 1); a6r_cnt[b]++;
+        if (nb == 0) mbar_wait(acc_empty(2), (acc_cnt[2] & 1) ^ 1);
+        tc_fence_after();
+        for (int nh = 0; nh < 2; ++nh)
+          for (int kb = 0; kb < 2; ++kb)
+            mma_chunk(sbase + L::A6 + b * 32768 + kb * 16384, tmem_base + region_col(2) + nh * 128, (nb | kb) != 0);
+        umma_commit(a6_free(b));
+        if (nb == 3) { umma_commit(acc_full(2)); acc_cnt[2]++; }
+      };
+      for (int t = tile_begin; t < tile_end; ++t, ++tile_iter) {
+        const uint32_t tpar = tile_iter & 1;
+        mbar_wait(in_ready, tpar);
+        tc_fence_after();
+        job6(0); job6(1); job7(0); job6(2); job7(1); job6(3); job7(2); job7(3);
+        // conv8: A = A7 (4 K-blocks), D = R6[0]
+        mbar_wait(a7_ready, tpar);
+        mbar_wait(acc_empty(0), (acc_cnt[0] & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < 4; ++kb) mma_chunk(sbase + L::A7 + kb * 16384, tmem_base + region_col(0), kb != 0);
+        umma_commit(acc_full(0)); acc_cnt[0]++;
+        // conv9: A = A8 (in the A6[0] buffer, 2 K-blocks), D = R6[1]
+        mbar_wait(a8_ready, tpar);
+        mbar_wait(acc_empty(1), (acc_cnt[1] & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < 2; ++kb) mma_chunk(sbase + L::A6 + kb * 16384, tmem_base + region_col(1), kb != 0);
+        umma_commit(acc_full(1)); acc_cnt[1]++;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ================================================================ epilogue warps
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const float* fl = reinterpret_cast<const float*>(smem + L::FL);
+    const float* b7 = fl, *b8 = fl + 256, *b9 = fl + 384, *w10 = fl + 512, *b10 = fl + 768;
+    uint32_t acc_cnt[3] = {0, 0, 0}, tile_iter = 0;
+
+    // reads NCOLS accumulator columns of region r, adds bias, ReLU, packs to bf16 and writes them as
+    // K-blocks of 64 into the operand buffer at `obuf` (row-major 128 B rows, SW128).
+    auto epi_to_smem = [&](int r, int ncols, const float* bias, uint32_t obuf) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_sel + region_col(r) + c0, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float2 b2 = *reinterpret_cast<const float2*>(bias + c0 + 2 * j);
+          pk[j] = pack_bf16_relu(__uint_as_float(v[2 * j]) + b2.x, __uint_as_float(v[2 * j + 1]) + b2.y);
+        }
+        const int kb = c0 >> 6, j0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          st_shared_v4(obuf + kb * 16384 + sw128_offset(row, j0 + jj), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+      }
+    };
+    auto release = [&](int r, uint32_t ready_bar) {
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) { if (ready_bar) mbar_arrive(ready_bar); mbar_arrive(acc_empty(r)); }
+    };
+
+    for (int t = tile_begin; t < tile_end; ++t, ++tile_iter) {
+      const int fr = t / tiles_per_frustum;
+      const int start = (t % tiles_per_frustum) * 128;
+      const int npts = min(128, args.N - start);
+      const float* gb = reinterpret_cast<const float*>(smem + L::GB) + (tile_iter & 1) * 512;
+      mbar_wait(in_ready, tile_iter & 1);            // gbias of this tile is in smem (written by the front warps)
+      for (int nb = 0; nb < 4; ++nb) {
+        const int r = nb & 1;
+        mbar_wait(acc_full(r), acc_cnt[r] & 1); acc_cnt[r]++;
+        if (nb >= 2) mbar_wait(a6_free(r), 0);       // commit #(2*tile) of this buffer, see header
+        tc_fence_after();
+        epi_to_smem(r, 128, gb + nb * 128, sbase + L::A6 + r * 32768);
+        release(r, a6_ready(r));
+      }
+      mbar_wait(acc_full(2), acc_cnt[2] & 1); acc_cnt[2]++;
+      tc_fence_after();
+      epi_to_smem(2, 256, b7, sbase + L::A7);
+      release(2, a7_ready);
+      mbar_wait(acc_full(0), acc_cnt[0] & 1); acc_cnt[0]++;
+      tc_fence_after();
+      epi_to_smem(0, 128, b8, sbase + L::A6);          // act8 reuses the A6[0] buffer
+      release(0, a8_ready);
+      mbar_wait(acc_full(1), acc_cnt[1] & 1); acc_cnt[1]++;
+      tc_fence_after();
+      float l0 = b10[0], l1 = b10[1];
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + lane_sel + region_col(1) + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float a = fmaxf(__uint_as_float(v[j]) + b9[c0 + j], 0.0f);
+          const float2 w = *reinterpret_cast<const float2*>(w10 + 2 * (c0 + j));
+          l0 = fmaf(a, w.x, l0);
+          l1 = fmaf(a, w.y, l1);
+        }
+      }
+      if (row < npts)
+        *reinterpret_cast<float2*>(args.logits + ((size_t)fr * args.N + start + row) * 2) = make_float2(l0, l1);
+      release(1, 0);
+    }
+  } else if (warp >= 8) {
+    // ================================================================ front warps: point_feat tile + gbias -> smem
+    const int p = threadIdx.x - 256;
+    uint32_t tile_iter = 0;
+    for (int t = tile_begin; t < tile_end; ++t, ++tile_iter) {
+      const int fr = t / tiles_per_frustum;
+      const int start = (t % tiles_per_frustum) * 128;
+      const int npts = min(128, args.N - start);
+      if (tile_iter > 0) mbar_wait(in_free, (tile_iter - 1) & 1);
+      const int j = start + min(p, npts - 1);
+      const uint4* src = reinterpret_cast<const uint4*>(args.point_feat + ((size_t)fr * args.N + j) * 64);
+      uint4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = src[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) st_shared_v4(sbase + L::IN + sw128_offset(p, i), v[i].x, v[i].y, v[i].z, v[i].w);
+      float* gdst = reinterpret_cast<float*>(smem + L::GB) + (tile_iter & 1) * 512;
+      const float4* gsrc = reinterpret_cast<const float4*>(args.gbias + (size_t)fr * 512);
+      reinterpret_cast<float4*>(gdst)[p] = gsrc[p];
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(in_ready);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace t3d

@@ -1,0 +1,351 @@
+// extern "C" entry points of libt3d_b200.so (declared in include/t3d_b200.h).
+#include "../../include/t3d_b200.h"
+#include "common.cuh"
+#include "simt_ops.cuh"
+#include "chain_max.cuh"
+#include "seg_stage2.cuh"
+
+using namespace t3d;
+
+#define T3D_CHECK_LAUNCH()                          \
+  do {                                              \
+    cudaError_t e__ = cudaGetLastError();           \
+    if (e__ != cudaSuccess) return (int)e__;        \
+  } while (0)
+#define T3D_CUDA(x)                                 \
+  do {                                              \
+    cudaError_t e__ = (x);                          \
+    if (e__ != cudaSuccess) return (int)e__;        \
+  } while (0)
+
+static inline cudaStream_t S(t3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+extern "C" int t3d_version(void) { return T3D_VERSION; }
+
+extern "C" const char* t3d_error_string(int code) {
+  if (code == 0) return "ok";
+  if (code == T3D_ERR_ARG) return "t3d: invalid argument";
+  if (code == T3D_ERR_SHAPE) return "t3d: unsupported shape";
+  if (code == T3D_ERR_ALIGN) return "t3d: misaligned pointer";
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "t3d: unknown error";
+}
+
+extern "C" int t3d_linear_f32(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* gbias,
+                              int rows_per_group, float* Y, int ldy, int M, int K, int N, int act, const float* rowmask,
+                              float* gmax, t3d_stream_t stream) {
+  if (!X || !W || (!Y && !gmax)) return T3D_ERR_ARG;
+  if (M <= 0 || K <= 0 || N <= 0 || act < 0 || act > 3) return T3D_ERR_SHAPE;
+  if ((gbias || gmax) && rows_per_group <= 0) return T3D_ERR_SHAPE;
+  LinearArgs a{X, ldx, W, ldw, bias, gbias, rows_per_group, Y, ldy, M, K, N, act, rowmask, gmax};
+  dim3 grid((M + 63) / 64, (N + 63) / 64);
+  linear_f32_kernel<<<grid, 256, 0, S(stream)>>>(a);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_mask_centroid(const float* logits, const float* pc, int B, int N, int C, float* mask, int* count,
+                                 float* mean, float* xyz_stage1, int* idx, t3d_stream_t stream) {
+  if (!logits || !pc) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0 || C < 3) return T3D_ERR_SHAPE;
+  if ((uintptr_t)logits & 7) return T3D_ERR_ALIGN;
+  mask_centroid_kernel<<<B, 256, 0, S(stream)>>>(logits, pc, N, C, mask, count, mean, xyz_stage1, idx);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_resample(const int* idx, const int* count, int B, int N, int npoints, int mode, uint64_t seed,
+                            const int* choice, int* indices, const float* pc, int C, const float* mean, int c_out,
+                            float* object_pc, t3d_stream_t stream) {
+  if (!idx || !count || !indices) return T3D_ERR_ARG;
+  if (mode != 0 && mode != 1) return T3D_ERR_ARG;
+  if (mode == 1 && !choice) return T3D_ERR_ARG;
+  if (object_pc && (!pc || !mean || c_out < 3 || c_out > C)) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0 || N > 2048 || npoints <= 0 || npoints > 2048) return T3D_ERR_SHAPE;
+  resample_kernel<<<B, 1024, 0, S(stream)>>>(idx, count, N, npoints, mode, (unsigned long long)seed, choice, indices, pc, C,
+                                             mean, c_out, object_pc);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_build_tiles(const int* count, int B, int tile_pts, void* tiles, int* num_tiles, t3d_stream_t stream) {
+  if (!count || !tiles || !num_tiles) return T3D_ERR_ARG;
+  if (B <= 0 || tile_pts <= 0) return T3D_ERR_SHAPE;
+  build_tiles_kernel<<<1, 1024, 0, S(stream)>>>(count, B, tile_pts, reinterpret_cast<int4*>(tiles), num_tiles);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_prepare_xyz(const float* pc, int B, int N, int C, const float* center, float* out, t3d_stream_t stream) {
+  if (!pc || !out) return T3D_ERR_ARG;
+  const size_t n = (size_t)B * N;
+  prepare_xyz_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(pc, B, N, C, center, out);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_boxpc_features(const float* pc, int B, int N, int C, const float* center, const float* dims,
+                                  const float* orient, float* out, t3d_stream_t stream) {
+  if (!pc || !center || !dims || !orient || !out) return T3D_ERR_ARG;
+  const size_t n = (size_t)B * N;
+  boxpc_features_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(pc, B, N, C, center, dims, orient, out);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_parse_box(const t3d_parse_args* p, t3d_stream_t stream) {
+  if (!p || !p->output || !p->mean_size || !p->orient_anchors) return T3D_ERR_ARG;
+  if (p->reg_center && (!p->reg_dims || !p->reg_orient)) return T3D_ERR_ARG;
+  if (p->B <= 0 || p->NH <= 0 || p->NS <= 0) return T3D_ERR_SHAPE;
+  ParseArgs a{p->output, p->stage1_center, p->mean_size, p->orient_anchors, p->B, p->NH, p->NS,
+              p->center, p->heading_scores, p->heading_res_norm, p->heading_res, p->size_scores, p->size_res_norm,
+              p->size_res, p->reg_center, p->reg_dims, p->reg_orient};
+  parse_box_kernel<<<(p->B + 127) / 128, 128, 0, S(stream)>>>(a);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_anchor_to_reg(const float* center, const float* dims_cls, const float* dims_reg, const float* orient_cls,
+                                 const float* orient_reg, const float* dims_anchors, const float* orient_anchors, int B, int NS,
+                                 int NH, float* out_center, float* out_dims, float* out_orient, t3d_stream_t stream) {
+  if (!center || !dims_cls || !dims_reg || !orient_cls || !orient_reg || !dims_anchors || !orient_anchors || !out_center ||
+      !out_dims || !out_orient)
+    return T3D_ERR_ARG;
+  anchor_to_reg_kernel<<<(B + 127) / 128, 128, 0, S(stream)>>>(center, dims_cls, dims_reg, orient_cls, orient_reg, dims_anchors,
+                                                               orient_anchors, B, NS, NH, out_center, out_dims, out_orient);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_boxpc_refine(const t3d_refine_args* p, t3d_stream_t stream) {
+  if (!p || !p->out9) return T3D_ERR_ARG;
+  if (p->delta_center && !p->delta_size) return T3D_ERR_ARG;
+  if (p->box_center && (!p->box_dims || !p->box_orient)) return T3D_ERR_ARG;
+  if (p->tot_center && (!p->tot_size || !p->tot_angle)) return T3D_ERR_ARG;
+  RefineArgs a{p->out9, p->B, p->weigh_pred_by_conf, p->weigh_during_test, p->fit_logits, p->fit_prob, p->pred_fit,
+               p->delta_center, p->delta_size, p->delta_angle, p->box_center, p->box_dims, p->box_orient,
+               p->tot_center, p->tot_size, p->tot_angle};
+  boxpc_refine_kernel<<<(p->B + 127) / 128, 128, 0, S(stream)>>>(a);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_f2(const float* f_center, const float* f_hres, const float* f_sres, const float* tot_center,
+                      const float* tot_angle, const float* tot_size, int B, int NH, int NS, float* f2_center, float* f2_hres,
+                      float* f2_sres, t3d_stream_t stream) {
+  if (!f_center || !f_hres || !f_sres || !tot_center || !tot_angle || !tot_size || !f2_center || !f2_hres || !f2_sres)
+    return T3D_ERR_ARG;
+  f2_kernel<<<(B + 127) / 128, 128, 0, S(stream)>>>(f_center, f_hres, f_sres, tot_center, tot_angle, tot_size, B, NH, NS,
+                                                    f2_center, f2_hres, f2_sres);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_box3d_corners_helper(const float* centers, const float* headings, const float* sizes, int n, float* out,
+                                        t3d_stream_t stream) {
+  if (!centers || !headings || !sizes || !out) return T3D_ERR_ARG;
+  box3d_corners_helper_kernel<<<(n + 127) / 128, 128, 0, S(stream)>>>(centers, headings, sizes, n, out);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_box3d_corners_all(const float* center, const float* heading_res, const float* size_res,
+                                     const float* mean_size, const float* orient_anchors, int B, int NH, int NS, float* out,
+                                     t3d_stream_t stream) {
+  if (!center || !heading_res || !size_res || !mean_size || !orient_anchors || !out) return T3D_ERR_ARG;
+  const int n = B * NH * NS;
+  box3d_corners_all_kernel<<<(n + 127) / 128, 128, 0, S(stream)>>>(center, heading_res, size_res, mean_size, orient_anchors, B,
+                                                                   NH, NS, out);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- tcgen05 chains
+struct PackTable { PackDesc d[32]; };
+__global__ void __launch_bounds__(256) pack_table_kernel(const PackTable tab, uint8_t* arena) {
+  const PackDesc d = tab.d[blockIdx.x];
+  uint8_t* dst = arena + (size_t)blockIdx.x * kChunkBytes;
+  for (int e = threadIdx.x; e < 128 * 64; e += 256) {
+    const int r = e >> 6, kk = e & 63;
+    float v = 0.0f;
+    if (r < d.nrows && d.k0 + kk < d.k_total) v = d.W[(size_t)(d.k0 + kk) * d.ldw + d.row0 + r];
+    *reinterpret_cast<__nv_bfloat16*>(dst + sw128_offset(r, kk >> 3) + (kk & 7) * 2) = __float2bfloat16_rn(v);
+  }
+}
+
+template <int KIND>
+static int pack_chain_impl(const float* const* W, const float* const* bias, uint8_t* arena, cudaStream_t st) {
+  using Sp = ChainSpec<KIND>;
+  PackTable tab;
+  int n = 0;
+  for (int l = 0; l < Sp::NH; ++l)
+    for (int nb = 0; nb < (Sp::HN(l) + 127) / 128; ++nb)
+      for (int kb = 0; kb < Sp::HK(l) / 64; ++kb)
+        tab.d[n++] = PackDesc{W[1 + l], Sp::HN(l), Sp::HK(l), kb * 64, nb * 128, Sp::HN(l) - nb * 128 < 128 ? Sp::HN(l) - nb * 128 : 128};
+  for (int mt = 0; mt < Sp::FC / 128; ++mt)
+    for (int kb = 0; kb < Sp::FK / 64; ++kb)
+      tab.d[n++] = PackDesc{W[1 + Sp::NH], Sp::FC, Sp::FK, kb * 64, mt * 128, 128};
+  if (n != chain_num_chunks<Sp>() || n > 32) return T3D_ERR_SHAPE;
+  pack_table_kernel<<<n, 256, 0, st>>>(tab, arena);
+  T3D_CHECK_LAUNCH();
+  float* f = reinterpret_cast<float*>(arena + (size_t)n * kChunkBytes);
+  T3D_CUDA(cudaMemcpyAsync(f, W[0], sizeof(float) * Sp::CIN * Sp::C1, cudaMemcpyDeviceToDevice, st));
+  f += Sp::CIN * Sp::C1;
+  T3D_CUDA(cudaMemcpyAsync(f, bias[0], sizeof(float) * Sp::C1, cudaMemcpyDeviceToDevice, st));
+  f += Sp::C1;
+  for (int l = 0; l < Sp::NH; ++l) {
+    T3D_CUDA(cudaMemcpyAsync(f, bias[1 + l], sizeof(float) * Sp::HN(l), cudaMemcpyDeviceToDevice, st));
+    f += Sp::HN(l);
+  }
+  T3D_CUDA(cudaMemcpyAsync(f, bias[1 + Sp::NH], sizeof(float) * Sp::FC, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+template <int KIND>
+static int chain_launch(const ChainArgs& a, int out_elems, cudaStream_t st) {
+  using Sp = ChainSpec<KIND>;
+  using L = ChainSmem<Sp>;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    T3D_CUDA(cudaGetDevice(&dev));
+    T3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    T3D_CUDA(cudaFuncSetAttribute(chain_max_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL + 1024));
+  }
+  T3D_CUDA(cudaMemsetAsync(a.out, 0, sizeof(float) * (size_t)out_elems, st));
+  int grid = sms;
+  if (!a.tiles) {
+    const int nt = a.B * ((a.N + L::TILE - 1) / L::TILE);
+    if (nt < grid) grid = nt;
+  }
+  chain_max_kernel<KIND><<<grid, 384, L::TOTAL + 1024, st>>>(a);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+#define CHAIN_SWITCH(kind, EXPR)                         \
+  switch (kind) {                                        \
+    case CHAIN_SEG1: { constexpr int K_ = CHAIN_SEG1; EXPR; } break;   \
+    case CHAIN_TNET: { constexpr int K_ = CHAIN_TNET; EXPR; } break;   \
+    case CHAIN_BOX: { constexpr int K_ = CHAIN_BOX; EXPR; } break;     \
+    case CHAIN_BOXPC: { constexpr int K_ = CHAIN_BOXPC; EXPR; } break; \
+    default: return T3D_ERR_ARG;                         \
+  }
+
+extern "C" size_t t3d_chain_arena_bytes(int kind) {
+  size_t r = 0;
+  switch (kind) {
+    case CHAIN_SEG1: r = chain_arena_bytes<ChainSpec<CHAIN_SEG1>>(); break;
+    case CHAIN_TNET: r = chain_arena_bytes<ChainSpec<CHAIN_TNET>>(); break;
+    case CHAIN_BOX: r = chain_arena_bytes<ChainSpec<CHAIN_BOX>>(); break;
+    case CHAIN_BOXPC: r = chain_arena_bytes<ChainSpec<CHAIN_BOXPC>>(); break;
+    default: r = 0;
+  }
+  return r;
+}
+extern "C" int t3d_chain_num_layers(int kind) {
+  switch (kind) {
+    case CHAIN_SEG1: return 2 + ChainSpec<CHAIN_SEG1>::NH;
+    case CHAIN_TNET: return 2 + ChainSpec<CHAIN_TNET>::NH;
+    case CHAIN_BOX: return 2 + ChainSpec<CHAIN_BOX>::NH;
+    case CHAIN_BOXPC: return 2 + ChainSpec<CHAIN_BOXPC>::NH;
+    default: return T3D_ERR_ARG;
+  }
+}
+extern "C" int t3d_chain_tile_points(int kind) {
+  switch (kind) {
+    case CHAIN_SEG1: return 128 * ChainSpec<CHAIN_SEG1>::NSUB;
+    case CHAIN_TNET: return 128 * ChainSpec<CHAIN_TNET>::NSUB;
+    case CHAIN_BOX: return 128 * ChainSpec<CHAIN_BOX>::NSUB;
+    case CHAIN_BOXPC: return 128 * ChainSpec<CHAIN_BOXPC>::NSUB;
+    default: return T3D_ERR_ARG;
+  }
+}
+extern "C" int t3d_chain_out_channels(int kind) {
+  switch (kind) {
+    case CHAIN_SEG1: return ChainSpec<CHAIN_SEG1>::FC;
+    case CHAIN_TNET: return ChainSpec<CHAIN_TNET>::FC;
+    case CHAIN_BOX: return ChainSpec<CHAIN_BOX>::FC;
+    case CHAIN_BOXPC: return ChainSpec<CHAIN_BOXPC>::FC;
+    default: return T3D_ERR_ARG;
+  }
+}
+
+extern "C" int t3d_pack_chain(int kind, const float* const* W, const float* const* bias, void* arena, t3d_stream_t stream) {
+  if (!W || !bias || !arena) return T3D_ERR_ARG;
+  if ((uintptr_t)arena & 1023) return T3D_ERR_ALIGN;
+  CHAIN_SWITCH(kind, return pack_chain_impl<K_>(W, bias, reinterpret_cast<uint8_t*>(arena), S(stream)));
+  return 0;
+}
+
+extern "C" int t3d_chain_max_bf16(int kind, const float* pc, int B, int N, int C, const float* center, const int* idx,
+                                  int idx_stride, const int* count, const void* tiles, const int* num_tiles,
+                                  const float* box_center, const float* box_dims, const float* box_orient, const void* arena,
+                                  float* out, void* emit, t3d_stream_t stream) {
+  if (!pc || !arena || !out) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0) return T3D_ERR_SHAPE;
+  if ((uintptr_t)arena & 15) return T3D_ERR_ALIGN;
+  if ((tiles != nullptr) != (num_tiles != nullptr)) return T3D_ERR_ARG;
+  if (idx && idx_stride <= 0) return T3D_ERR_SHAPE;
+  if (kind == CHAIN_BOXPC && (!box_center || !box_dims || !box_orient)) return T3D_ERR_ARG;
+  if (kind == CHAIN_BOXPC ? C != 6 : (kind == CHAIN_SEG1 ? C != 6 : C < 3)) return T3D_ERR_SHAPE;
+  if (emit && (kind != CHAIN_SEG1 || ((uintptr_t)emit & 15))) return T3D_ERR_ARG;
+  ChainArgs a{pc, B, N, C, center, idx, idx_stride, count, reinterpret_cast<const int4*>(tiles), num_tiles,
+              box_center, box_dims, box_orient, reinterpret_cast<const uint8_t*>(arena), out,
+              reinterpret_cast<__nv_bfloat16*>(emit)};
+  CHAIN_SWITCH(kind, return chain_launch<K_>(a, B * ChainSpec<K_>::FC, S(stream)));
+  return 0;
+}
+
+extern "C" size_t t3d_seg2_arena_bytes(void) { return kSeg2ArenaBytes; }
+
+extern "C" int t3d_pack_seg2(const float* W6p, const float* W7, const float* W8, const float* W9, const float* b7,
+                             const float* b8, const float* b9, const float* W10, const float* b10, void* arena,
+                             t3d_stream_t stream) {
+  if (!W6p || !W7 || !W8 || !W9 || !b7 || !b8 || !b9 || !W10 || !b10 || !arena) return T3D_ERR_ARG;
+  if ((uintptr_t)arena & 1023) return T3D_ERR_ALIGN;
+  cudaStream_t st = S(stream);
+  PackTable tab;
+  int n = 0;
+  auto c6 = [&](int nb) { tab.d[n++] = PackDesc{W6p, 512, 64, 0, nb * 128, 128}; };
+  auto c7 = [&](int nb) {
+    for (int nh = 0; nh < 2; ++nh)
+      for (int kb = 0; kb < 2; ++kb) tab.d[n++] = PackDesc{W7, 256, 512, nb * 128 + kb * 64, nh * 128, 128};
+  };
+  // consumption order of seg_stage2_kernel: j6(0) j6(1) j7(0) j6(2) j7(1) j6(3) j7(2) j7(3) conv8 conv9
+  c6(0); c6(1); c7(0); c6(2); c7(1); c6(3); c7(2); c7(3);
+  for (int kb = 0; kb < 4; ++kb) tab.d[n++] = PackDesc{W8, 128, 256, kb * 64, 0, 128};
+  for (int kb = 0; kb < 2; ++kb) tab.d[n++] = PackDesc{W9, 128, 128, kb * 64, 0, 128};
+  if (n != kSeg2Chunks) return T3D_ERR_SHAPE;
+  uint8_t* ar = reinterpret_cast<uint8_t*>(arena);
+  pack_table_kernel<<<n, 256, 0, st>>>(tab, ar);
+  T3D_CHECK_LAUNCH();
+  float* f = reinterpret_cast<float*>(ar + (size_t)n * kChunkBytes);
+  T3D_CUDA(cudaMemcpyAsync(f, b7, 4 * 256, cudaMemcpyDeviceToDevice, st));
+  T3D_CUDA(cudaMemcpyAsync(f + 256, b8, 4 * 128, cudaMemcpyDeviceToDevice, st));
+  T3D_CUDA(cudaMemcpyAsync(f + 384, b9, 4 * 128, cudaMemcpyDeviceToDevice, st));
+  T3D_CUDA(cudaMemcpyAsync(f + 512, W10, 4 * 256, cudaMemcpyDeviceToDevice, st));
+  T3D_CUDA(cudaMemcpyAsync(f + 768, b10, 4 * 2, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int t3d_seg_stage2_bf16(const void* point_feat, const float* gbias, const void* arena, float* logits, int B, int N,
+                                   t3d_stream_t stream) {
+  if (!point_feat || !gbias || !arena || !logits) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0) return T3D_ERR_SHAPE;
+  if (((uintptr_t)point_feat & 15) || ((uintptr_t)gbias & 15) || ((uintptr_t)logits & 7) || ((uintptr_t)arena & 15))
+    return T3D_ERR_ALIGN;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    T3D_CUDA(cudaGetDevice(&dev));
+    T3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    T3D_CUDA(cudaFuncSetAttribute(seg_stage2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2Smem::TOTAL + 1024));
+  }
+  Seg2Args a{reinterpret_cast<const __nv_bfloat16*>(point_feat), gbias, reinterpret_cast<const uint8_t*>(arena), logits, B, N};
+  const int nt = B * ((N + 127) / 128);
+  const int grid = nt < sms ? nt : sms;
+  seg_stage2_kernel<<<grid, 384, Seg2Smem::TOTAL + 1024, S(stream)>>>(a);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}

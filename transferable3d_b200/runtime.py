@@ -1,0 +1,217 @@
+"""Host-side runtime of the B200 path: the variable store (stands in for the TF variable
+collection + tf.variable_scope, models/tf_util.py:1151-1190), BN folding / weight packing caches,
+the precision switch, and thin wrappers over the C ABI.
+
+Precision modes (BASELINE north_star): 'bf16' = tcgen05 kernels, bf16 operands / fp32 accumulate;
+'fp32' = CUDA-core fp32 kernels layer by layer (1e-4 parity mode).  FC heads are fp32 in both.
+Only eval-mode graphs (is_training=False) are implemented on the GPU path in this round.
+"""
+import contextlib
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ptr, stream, call
+from .weights import fold_bn
+
+ACT = {'none': 0, None: 0, 'relu': 1, 'leaky_relu': 2, 'tanh': 3}
+CHAIN_SEG1, CHAIN_TNET, CHAIN_BOX, CHAIN_BOXPC = 0, 1, 2, 3
+
+_state = {'store': None, 'precision': 'bf16'}
+
+
+def set_precision(mode):
+    if mode not in ('bf16', 'fp32'):
+        raise ValueError(mode)
+    _state['precision'] = mode
+
+
+def get_precision():
+    return _state['precision']
+
+
+@contextlib.contextmanager
+def precision(mode):
+    old = _state['precision']
+    set_precision(mode)
+    try:
+        yield
+    finally:
+        _state['precision'] = old
+
+
+class VariableStore(object):
+    """Variables by TF checkpoint name (numpy, host) + device-side caches derived from them."""
+
+    def __init__(self, variables, device=None):
+        self.variables = {k: np.asarray(v) for k, v in variables.items()}
+        self.device = torch.device(device if device is not None else 'cuda')
+        self._scope = []
+        self._folded = {}      # layer -> (W [K,N] f32 dev, b [N] f32 dev)
+        self._arenas = {}      # (key) -> packed uint8 dev tensor
+        self._consts = {}
+
+    # --- scopes ---------------------------------------------------------------------------
+    @contextlib.contextmanager
+    def variable_scope(self, name):
+        self._scope.append(name)
+        try:
+            yield
+        finally:
+            self._scope.pop()
+
+    def scope_name(self, name=None):
+        parts = [s for s in self._scope if s]
+        if name:
+            parts.append(name)
+        return '/'.join(parts)
+
+    # --- derived device tensors -------------------------------------------------------------
+    def folded(self, layer):
+        """(W[Cin,Cout], b[Cout]) fp32 on device with eval-mode BN folded in."""
+        if layer not in self._folded:
+            if layer + '/weights' not in self.variables:
+                raise KeyError('variable %s/weights not found' % layer)
+            w, b = fold_bn(self.variables, layer)
+            self._folded[layer] = (torch.from_numpy(w).to(self.device), torch.from_numpy(b).to(self.device))
+        return self._folded[layer]
+
+    def const(self, name, array):
+        if name not in self._consts:
+            self._consts[name] = torch.as_tensor(np.asarray(array, dtype=np.float32)).to(self.device).contiguous()
+        return self._consts[name]
+
+    def _new_arena(self, nbytes):
+        # 1024-byte aligned base (torch allocations are 512-byte aligned)
+        raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
+        off = (-raw.data_ptr()) % 1024
+        return raw[off:off + nbytes]
+
+    def chain_arena(self, scope, kind, layers, w1_rows=None):
+        """Packed tcgen05 weights of one per-point chain. `layers` = TF layer names under `scope`:
+        [layer1, hidden..., final]."""
+        key = ('chain', scope, kind)
+        if key not in self._arenas:
+            lib = _lib.load()
+            assert lib.t3d_chain_num_layers(kind) == len(layers)
+            ws, bs = [], []
+            for name in layers:
+                w, b = self.folded('%s/%s' % (scope, name))
+                ws.append(w.contiguous())
+                bs.append(b.contiguous())
+            arena = self._new_arena(lib.t3d_chain_arena_bytes(kind))
+            PA = ctypes.c_void_p * len(layers)
+            call('t3d_pack_chain', kind, PA(*[w.data_ptr() for w in ws]), PA(*[b.data_ptr() for b in bs]),
+                 ptr(arena), stream())
+            torch.cuda.current_stream().synchronize()       # ws/bs may be freed after this
+            self._arenas[key] = arena
+        return self._arenas[key]
+
+    def seg2_arena(self, scope):
+        key = ('seg2', scope)
+        if key not in self._arenas:
+            lib = _lib.load()
+            w6, _ = self.folded(scope + '/conv6')
+            w6p = w6[:64].contiguous()
+            w7, b7 = self.folded(scope + '/conv7')
+            w8, b8 = self.folded(scope + '/conv8')
+            w9, b9 = self.folded(scope + '/conv9')
+            w10, b10 = self.folded(scope + '/conv10')
+            arena = self._new_arena(lib.t3d_seg2_arena_bytes())
+            call('t3d_pack_seg2', ptr(w6p), ptr(w7), ptr(w8), ptr(w9), ptr(b7), ptr(b8), ptr(b9), ptr(w10), ptr(b10),
+                 ptr(arena), stream())
+            torch.cuda.current_stream().synchronize()
+            self._arenas[key] = arena
+        return self._arenas[key]
+
+
+def set_default_store(store):
+    _state['store'] = store
+
+
+def store():
+    if _state['store'] is None:
+        raise RuntimeError('no VariableStore: call runtime.set_default_store(VariableStore(variables))')
+    return _state['store']
+
+
+@contextlib.contextmanager
+def variable_scope(name):
+    """tf.variable_scope analogue on the default store."""
+    with store().variable_scope(name):
+        yield
+
+
+def require_eval(is_training):
+    if bool(is_training):
+        raise NotImplementedError('training-mode (batch-statistics BN, dropout) graphs are not implemented on the '
+                                  'B200 path yet; only is_training=False')
+
+
+def f32(t):
+    return t.to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------ op wrappers
+
+def linear(x, w, b=None, act=None, gbias=None, rows_per_group=0, rowmask=None, gmax_groups=0, want_y=True):
+    """t3d_linear_f32. x: (M,K) f32 (row stride = K), w: (K,N). Returns (y or None, gmax or None)."""
+    x = f32(x)
+    M, K = x.shape
+    N = w.shape[1]
+    assert w.shape[0] == K, (tuple(w.shape), tuple(x.shape))
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device) if want_y else None
+    gmax = torch.zeros((gmax_groups, N), dtype=torch.float32, device=x.device) if gmax_groups else None
+    call('t3d_linear_f32', ptr(x), K, ptr(w), N, ptr(b), ptr(gbias), int(rows_per_group), ptr(y), N, M, K, N,
+         ACT[act], ptr(rowmask), ptr(gmax), stream())
+    return y, gmax
+
+
+def mask_centroid(logits, pc, want_mask=True, want_xyz_stage1=False, want_idx=True):
+    B, N, C = pc.shape
+    dev = pc.device
+    mask = torch.empty((B, N), dtype=torch.float32, device=dev) if want_mask else None
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    mean = torch.empty((B, 3), dtype=torch.float32, device=dev)
+    xyz1 = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if want_xyz_stage1 else None
+    idx = torch.empty((B, N), dtype=torch.int32, device=dev) if want_idx else None
+    call('t3d_mask_centroid', ptr(f32(logits)), ptr(pc), B, N, C, ptr(mask), ptr(count), ptr(mean), ptr(xyz1), ptr(idx),
+         stream())
+    return mask, count, mean, xyz1, idx
+
+
+def build_tiles(count, tile_pts, max_per_frustum):
+    B = count.shape[0]
+    tiles = torch.empty((B * ((max_per_frustum + tile_pts - 1) // tile_pts), 4), dtype=torch.int32, device=count.device)
+    num = torch.empty((1,), dtype=torch.int32, device=count.device)
+    call('t3d_build_tiles', ptr(count), B, tile_pts, ptr(tiles), ptr(num), stream())
+    return tiles, num
+
+
+def chain_max(kind, pc, arena, center=None, idx=None, count=None, box=None, emit=None):
+    """Fused per-point chain + max on tcgen05. Returns (B, FC) fp32."""
+    lib = _lib.load()
+    B, N, C = pc.shape
+    fc = lib.t3d_chain_out_channels(kind)
+    out = torch.empty((B, fc), dtype=torch.float32, device=pc.device)
+    tiles = num = None
+    idx_stride = 0
+    if idx is not None:
+        idx_stride = idx.shape[1]
+        if count is None:
+            count = torch.full((B,), idx_stride, dtype=torch.int32, device=pc.device)
+        tiles, num = build_tiles(count, lib.t3d_chain_tile_points(kind), idx_stride)
+    bc = bd = bo = None
+    if box is not None:
+        bc, bd, bo = [f32(t) for t in box]
+    call('t3d_chain_max_bf16', kind, ptr(pc), B, N, C, ptr(center), ptr(idx), idx_stride, ptr(count), ptr(tiles), ptr(num),
+         ptr(bc), ptr(bd), ptr(bo), ptr(arena), ptr(out), ptr(emit), stream())
+    return out
+
+
+def seg_stage2(point_feat, gbias, arena, B, N):
+    logits = torch.empty((B, N, 2), dtype=torch.float32, device=gbias.device)
+    call('t3d_seg_stage2_bf16', ptr(point_feat), ptr(gbias), ptr(arena), ptr(logits), B, N, stream())
+    return logits

@@ -1,0 +1,113 @@
+"""Mirror of sunrgbd/sunrgbd_detection/semisup_v1_sunrgbd.py model definitions
+(placeholder_inputs :37-67, get_semi_model :69-79, get_semi_model_backbone :81-130,
+get_semi_model_final :132-230) on the B200 path; same returned tuples and end_points keys.
+Losses (:236-553) are evaluated by the oracle only in this round (SURVEY 8a a23-a26 'next').
+"""
+import numpy as np
+import torch
+
+from . import runtime as rt
+from . import tf_util, semisup_models
+from .constants import NUM_HEADING_BIN, NUM_SIZE_CLUSTER, NUM_CLASS, MEAN_DIMS_ARR, ORIENT_ANCHORS
+
+INPUT_IMG_CHANNELS = 3
+
+
+def placeholder_inputs(batch_size, num_point, num_channel, device='cuda'):
+    """semisup_v1_sunrgbd.py:37-67: the 18 inputs, in the reference order, as zero tensors of the
+    placeholder shape/dtype (img has no static H,W -> (B,0,0,3))."""
+    f, i = torch.float32, torch.int32
+    B, N, C = batch_size, num_point, num_channel
+    Z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=device)
+    return (Z((B, N, C), f), Z((B, N, C), f), Z((B, 0, 0, INPUT_IMG_CHANNELS), f), Z((B, NUM_CLASS), f),
+            Z((B, N), i), Z((B, 3), f), Z((B,), i), Z((B,), f), Z((B,), i), Z((B, 3), f),
+            Z((B, 3, 3), f), Z((B, 3, 4), f), Z((B, 3, 3), f), Z((B, 3, 3), f),
+            Z((B, 1), f), Z((B, 4), f), Z((B, 2), f), Z((B,), i))
+
+
+def _base_end_points(pc, one_hot_vec):
+    st = rt.store()
+    return {'point_cloud': pc, 'class_one_hot': one_hot_vec,
+            'class_ids': torch.argmax(one_hot_vec, dim=1).to(torch.int32),
+            'dims_anchors': st.const('MEAN_DIMS_ARR', MEAN_DIMS_ARR),
+            'orient_anchors': st.const('ORIENT_ANCHORS', ORIENT_ANCHORS)}
+
+
+def get_semi_model(pc, bg_pc, img, one_hot_vec, is_training, use_one_hot, oracle_mask=None, norm_box2D=None,
+                   bn_decay=None, c=None):
+    """semisup_v1_sunrgbd.py:69-79."""
+    if c.SEMI_MODEL == 'A':
+        return get_semi_model_backbone(pc, bg_pc, img, one_hot_vec, is_training, use_one_hot, oracle_mask=oracle_mask,
+                                       norm_box2D=norm_box2D, bn_decay=bn_decay, c=c)
+    elif c.SEMI_MODEL == 'F':
+        return get_semi_model_final(pc, bg_pc, img, one_hot_vec, is_training, use_one_hot, oracle_mask=oracle_mask,
+                                    norm_box2D=norm_box2D, bn_decay=bn_decay, c=c)
+    else:
+        raise Exception('Not implemented SEMI_MODEL: %s' % c.SEMI_MODEL)
+
+
+def get_semi_model_backbone(pc, bg_pc, img, one_hot_vec, is_training, use_one_hot, oracle_mask=None, norm_box2D=None,
+                            bn_decay=None, c=None):
+    """semisup_v1_sunrgbd.py:81-130 (model A)."""
+    end_points = _base_end_points(pc, one_hot_vec)
+    img_feats = None
+    if not use_one_hot:
+        one_hot_vec = None
+    if oracle_mask is not None:
+        raise NotImplementedError
+    if not c.USE_NORMALIZED_BOX2D_AS_FEATS:
+        norm_box2D = None
+    logits = semisup_models.v1_inst_seg(pc, img_feats, one_hot_vec, end_points, is_training, bn_decay=bn_decay,
+                                        scope='inst_seg')
+    end_points['soft_mask'] = torch.softmax(logits, dim=-1)[:, :, 1]
+    mask, mask_xyz_mean, pc_xyz, pc_xyz_stage1 = semisup_models.subtract_points_mean(pc, logits, scope='subtract_points_mean')
+    stage1_center = semisup_models.v1_tnet(pc_xyz_stage1, mask, mask_xyz_mean, one_hot_vec, end_points, is_training,
+                                           norm_box2D=norm_box2D, bn_decay=bn_decay, scope='tnet')
+    pc_xyz_submean = semisup_models.subtract_1st_stage_center(pc_xyz, stage1_center, scope='subtract_tnet_center')
+    pred_box = semisup_models.v1_box_est(pc_xyz_submean, stage1_center, mask, one_hot_vec, end_points, is_training,
+                                         norm_box2D=norm_box2D, bn_decay=bn_decay, c=c, scope='box_est')
+    end_points['S_pred_box'] = pred_box
+    end_points['S_pred_box_reg'] = end_points.pop('_box_reg_fused')      # anchor->reg fused into the parse kernel
+    pred = (logits, pred_box)
+    return pred, end_points
+
+
+def get_semi_model_final(pc, bg_pc, img, one_hot_vec, is_training, use_one_hot, oracle_mask=None, norm_box2D=None,
+                         bn_decay=None, c=None):
+    """semisup_v1_sunrgbd.py:132-230 (model F)."""
+    end_points = _base_end_points(pc, one_hot_vec)
+    img_feats = None
+    if not c.USE_NORMALIZED_BOX2D_AS_FEATS:
+        norm_box2D = None
+    with rt.variable_scope('class_agnostic'):
+        logits = semisup_models.v1_inst_seg(pc, img_feats, None, end_points, is_training, bn_decay=bn_decay,
+                                            scope='inst_seg')
+        if oracle_mask is not None:
+            om = oracle_mask.to(torch.float32)
+            logits = torch.stack([1 - om, om], dim=2).contiguous()
+        mask, mask_xyz_mean, pc_xyz, pc_xyz_stage1 = semisup_models.subtract_points_mean(pc, logits,
+                                                                                       scope='subtract_points_mean')
+        end_points['_mask'] = mask
+        stage1_center = semisup_models.v1_tnet(pc_xyz_stage1, mask, mask_xyz_mean, None, end_points, is_training,
+                                               norm_box2D=norm_box2D, bn_decay=bn_decay, scope='tnet')
+        pc_xyz_submean = semisup_models.subtract_1st_stage_center(pc_xyz, stage1_center, scope='subtract_tnet_center')
+        W_pred_box = semisup_models.v1_box_est(pc_xyz_submean, stage1_center, mask, None, end_points, is_training,
+                                               norm_box2D=norm_box2D, bn_decay=bn_decay, c=c, scope='box_est')
+        end_points.pop('_box_reg_fused')
+    with rt.variable_scope('class_dependent'):
+        curr_feat = end_points['feats_lv1']
+        if use_one_hot:
+            curr_feat = torch.cat([curr_feat, rt.f32(one_hot_vec)], dim=1).contiguous()
+        output_dims = 3 + NUM_HEADING_BIN * 2 + NUM_SIZE_CLUSTER * 4
+        activation_fn = 'leaky_relu' if c.SEMI_ADV_LEAKY_RELU else 'relu'
+        last_layer_fn = 'tanh' if c.SEMI_ADV_TANH_FOR_LAST_LAYER_OF_G else activation_fn
+        dropout = c.SEMI_ADV_DROPOUTS_FOR_G
+        F_output = semisup_models.mlps_with_dropout(curr_feat, layers=[512, 256, output_dims],
+                                                    activation_fns=[activation_fn, last_layer_fn, None],
+                                                    keep_probs=[dropout, dropout, None], is_training=is_training,
+                                                    bn=True, bn_decay=bn_decay, c=c, scope='box_refine', reuse=None)
+        end_points['F_output'] = F_output
+        F_pred_box, F_reg = semisup_models.parse_into_end_points(F_output, stage1_center, end_points, 'F_')
+    end_points['F_pred_box_reg'] = F_reg
+    pred = (logits, W_pred_box, F_pred_box)
+    return pred, end_points

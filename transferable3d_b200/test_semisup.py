@@ -1,0 +1,163 @@
+"""Mirror of the inference side of sunrgbd/sunrgbd_detection/test_semisup.py: get_model (:61-179,
+model F + BoxPC refine loop -> F2_* end points) and inference (:187-260).
+
+The reference builds a static TF graph for a fixed batch size and returns (sess, ops); here
+get_model returns (sess, ops) where `sess.run(fetches, feed_dict)` evaluates the same graph on
+the B200 for whatever batch is fed (ops hold placeholder names).
+"""
+import numpy as np
+import torch
+
+from . import runtime as rt
+from . import tf_util, semisup_v1_sunrgbd as MODEL, boxpc_sunrgbd
+from ._lib import ptr, stream, call
+from .constants import NUM_HEADING_BIN, NUM_SIZE_CLUSTER
+
+
+def build_graph(FLAGS, pc, one_hot_vec, box2D=None, img_dim=None, oracle_mask=None, is_training=False):
+    """Body of test_semisup.get_model (test_semisup.py:74-149) on device tensors -> (logits, end_points)."""
+    norm_box2D = None
+    if box2D is not None and img_dim is not None:
+        norm_box2D = tf_util.tf_normalize_2D_bboxes(box2D, img_dim)
+    pred, end_points = MODEL.get_semi_model(pc, None, None, one_hot_vec, is_training, norm_box2D=norm_box2D,
+                                            use_one_hot=FLAGS.use_one_hot, oracle_mask=oracle_mask, c=FLAGS)
+    logits = pred[0]
+    prefix = 'F_'
+    n_refine = int(FLAGS.refine)
+    B = pc.shape[0]
+    dev = pc.device
+    curr_box = tuple(t.clone() for t in end_points[prefix + 'pred_box_reg'])
+    totals = (torch.zeros((B, 3), device=dev), torch.zeros((B, 3), device=dev), torch.zeros((B,), device=dev))
+    boxpc_fit_prob = None
+    for i in range(n_refine):
+        if FLAGS.mask_pc_for_boxpc:
+            mask = torch.argmax(logits, dim=2).to(torch.float32).unsqueeze(2)
+            fake_pc = (pc * mask).contiguous()
+        else:
+            fake_pc = pc
+        box_in = tuple(t.clone() for t in curr_box)
+        with rt.variable_scope('D_boxpc_branch'):
+            _, ep = boxpc_sunrgbd.get_model((box_in, fake_pc), False, one_hot_vec=one_hot_vec, use_one_hot_vec=False,
+                                            c=FLAGS,
+                                            _refine=dict(curr_box=curr_box, totals=totals,
+                                                         weigh_during_test=FLAGS.SEMI_WEIGH_BOXPC_DELTA_DURING_TEST))
+        boxpc_fit_prob = ep['logits_for_weigh']
+        for k in ('boxpc_delta_center', 'boxpc_delta_size', 'boxpc_delta_angle', 'boxpc_feats_dict', 'pred_boxpc_fit',
+                  'boxpc_fit_logits'):
+            end_points[k] = ep[k]
+    st = rt.store()
+    f2c = torch.empty((B, 3), device=dev)
+    f2h = torch.empty((B, NUM_HEADING_BIN), device=dev)
+    f2s = torch.empty((B, NUM_SIZE_CLUSTER, 3), device=dev)
+    call('t3d_f2', ptr(end_points[prefix + 'center']), ptr(end_points[prefix + 'heading_residuals']),
+         ptr(end_points[prefix + 'size_residuals']), ptr(totals[0]), ptr(totals[2]), ptr(totals[1]), B,
+         NUM_HEADING_BIN, NUM_SIZE_CLUSTER, ptr(f2c), ptr(f2h), ptr(f2s), stream())
+    end_points.update({'boxpc_fit_prob': boxpc_fit_prob, 'F2_center': f2c,
+                       'F2_heading_scores': end_points[prefix + 'heading_scores'], 'F2_heading_residuals': f2h,
+                       'F2_size_scores': end_points[prefix + 'size_scores'], 'F2_size_residuals': f2s})
+    end_points['logits'] = logits
+    return logits, end_points
+
+
+class Session(object):
+    """Stands in for the tf.Session of test_semisup.get_model: run(fetches, feed_dict)."""
+
+    def __init__(self, FLAGS, store, use_oracle_mask=False):
+        self.FLAGS, self.store, self.use_oracle_mask = FLAGS, store, use_oracle_mask
+
+    def run(self, fetches, feed_dict):
+        dev = self.store.device
+        T = lambda v, dt=torch.float32: torch.as_tensor(np.asarray(v)).to(device=dev, dtype=dt).contiguous() \
+            if not torch.is_tensor(v) else v.to(device=dev, dtype=dt).contiguous()
+        if bool(feed_dict.get('is_training_pl', False)):
+            raise NotImplementedError('is_training=True')
+        pc = T(feed_dict['pc_pl'])
+        one_hot = T(feed_dict['one_hot_vec_pl'])
+        om = T(feed_dict['y_seg_pl']) if (self.use_oracle_mask and 'y_seg_pl' in feed_dict) else None
+        rt.set_default_store(self.store)
+        with torch.no_grad():
+            logits, ep = build_graph(self.FLAGS, pc, one_hot, oracle_mask=om)
+        out = []
+        for f in fetches:
+            out.append(ep[f] if isinstance(f, str) else f)
+        return out
+
+
+def get_model(batch_size, num_point, num_channel, FLAGS, variables, use_oracle_mask=False, device='cuda'):
+    """test_semisup.get_model (test_semisup.py:61-179) -> (sess, ops). `variables` = {TF name: array}
+    (what saver.restore would load, :158-159)."""
+    store = variables if isinstance(variables, rt.VariableStore) else rt.VariableStore(variables, device)
+    sess = Session(FLAGS, store, use_oracle_mask)
+    ops = {k: k for k in ('pc_pl', 'one_hot_vec_pl', 'y_seg_pl', 'y_centers_pl', 'y_orient_cls_pl', 'y_orient_reg_pl',
+                          'y_dims_cls_pl', 'y_dims_reg_pl', 'R0_rect_pl', 'P_pl', 'Rtilt_pl', 'K_pl', 'rot_frust_pl',
+                          'box2D_pl', 'img_dim_pl', 'is_training_pl')}
+    ops['logits'] = 'logits'
+    ops['end_points'] = _KeyDict()
+    return sess, ops
+
+
+class _KeyDict(dict):
+    """ops['end_points'][name] -> name, so fetch lists are written exactly like the reference's."""
+
+    def __missing__(self, key):
+        return key
+
+
+def softmax(x):
+    """test_semisup.py:181-185."""
+    shape = x.shape
+    probs = np.exp(x - np.max(x, axis=len(shape) - 1, keepdims=True))
+    probs /= np.sum(probs, axis=len(shape) - 1, keepdims=True)
+    return probs
+
+
+def inference(sess, ops, pc, one_hot_vec, batch_size, prefix='', use_boxpc_fit_prob=False, oracle_mask=None):
+    """test_semisup.py:187-260: batches through sess.run, host-side numpy scores and argmax-selects."""
+    assert pc.shape[0] % batch_size == 0
+    num_batches = pc.shape[0] // batch_size
+    n = pc.shape[0]
+    boxpc_fit_prob = np.zeros((n,))
+    logits = np.zeros((n, pc.shape[1], 2))
+    centers = np.zeros((n, 3))
+    heading_logits = np.zeros((n, NUM_HEADING_BIN))
+    heading_residuals = np.zeros((n, NUM_HEADING_BIN))
+    size_logits = np.zeros((n, NUM_SIZE_CLUSTER))
+    size_residuals = np.zeros((n, NUM_SIZE_CLUSTER, 3))
+    scores = np.zeros((n,))
+    ep = ops['end_points']
+    for i in range(num_batches):
+        sl = slice(i * batch_size, (i + 1) * batch_size)
+        feed_dict = {ops['pc_pl']: pc[sl, ...], ops['one_hot_vec_pl']: one_hot_vec[sl, :], ops['is_training_pl']: False}
+        if oracle_mask is not None:
+            feed_dict.update({ops['y_seg_pl']: oracle_mask[sl]})
+        run_ops = [ops['logits'], ep[prefix + 'center'], ep[prefix + 'heading_scores'], ep[prefix + 'heading_residuals'],
+                   ep[prefix + 'size_scores'], ep[prefix + 'size_residuals']]
+        if use_boxpc_fit_prob:
+            run_ops.append(ep['boxpc_fit_prob'])
+        res = [r.detach().cpu().numpy().astype(np.float64) for r in sess.run(run_ops, feed_dict=feed_dict)]
+        batch_logits, batch_centers, batch_hs, batch_hr, batch_ss, batch_sr = res[:6]
+        logits[sl, ...] = batch_logits
+        centers[sl, ...] = batch_centers
+        heading_logits[sl, ...] = batch_hs
+        heading_residuals[sl, ...] = batch_hr
+        size_logits[sl, ...] = batch_ss
+        size_residuals[sl, ...] = batch_sr
+        batch_seg_prob = softmax(batch_logits)[:, :, 1]
+        batch_seg_mask = np.argmax(batch_logits, 2)
+        mask_mean_prob = np.sum(batch_seg_prob * batch_seg_mask, 1)
+        mask_mean_prob = mask_mean_prob / (np.sum(batch_seg_mask, 1) + 1)
+        heading_prob = np.max(softmax(batch_hs), 1)
+        size_prob = np.max(softmax(batch_ss), 1)
+        if use_boxpc_fit_prob:
+            boxpc_fit_prob[sl] = res[6]
+            batch_scores = np.log(res[6] + 0.01) + np.log(mask_mean_prob + 0.01) + np.log(heading_prob + 0.01) + \
+                np.log(size_prob + 0.01)
+        else:
+            batch_scores = np.log(mask_mean_prob + 0.01) + np.log(heading_prob + 0.01) + np.log(size_prob + 0.01)
+        scores[sl] = batch_scores
+    heading_cls = np.argmax(heading_logits, 1)
+    size_cls = np.argmax(size_logits, 1)
+    pred_seg = np.argmax(logits, 2)
+    pred_orient_reg = np.array([heading_residuals[i, heading_cls[i]] for i in range(n)])
+    pred_dims_reg = np.vstack([size_residuals[i, size_cls[i], :] for i in range(n)])
+    return pred_seg, centers, heading_cls, pred_orient_reg, size_cls, pred_dims_reg, scores
