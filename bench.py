@@ -1,0 +1,442 @@
+"""bench.py -- frustums/sec of the Frustum-PointNet hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps K --warmup W
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference algorithm (oracle, PyTorch-CPU) on the host cores
+
+Workload (config.workload): BASELINE.json cfg3 = full Frustum PointNet v1 pipeline inference
+(seg -> mask / centroid / resample 512 -> T-Net -> box-est NH=12 NS=10), 8192 frustums of
+2048 pts x 6 ch + 10-class one-hot, sharded contiguously over the N GPUs with no collective
+(strong scaling).  `--workload cfg2` times the instance-seg chain alone at batch 1024 per GPU.
+A step = one pass of the pipeline over the rank's shard, processed in chunks of --chunk frustums.
+`value`: inputs already resident in HBM.  `e2e`: the same pass through the public API
+(frustum_pointnets_v1.get_model) from pinned HOST buffers, H2D of every chunk's inputs and D2H of
+its results (mask logits + box outputs) inside the timed region, copies overlapped with compute.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOTAL_FRUSTUMS = {'cfg3': 8192, 'cfg2': 1024}
+N_POINTS, N_CH = 2048, 6
+UNIQUE = 512            # unique synthetic frustums generated on the host, tiled to the workload size
+# algorithmic FLOPs (2*MAC) per point, SURVEY 8(d) / DESIGN.md
+FLOP_SEG1_PT = 295680
+FLOP_SEG2_PT = 426496
+FLOP_SEG_GLOBAL_FR = 2 * (1024 + 10) * 512
+FLOP_TNET_PT, FLOP_BOX_PT = 99072, 361216
+FLOP_FC_FR = 2 * (98688 + 2560 + 410368 + 5120)
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16=d['bf16_tflops_sustained'], bf16_burst=d['bf16_tflops'], hbm=d['hbm_gbs'], src='measured')
+    return dict(bf16=1400.0, bf16_burst=1590.0, hbm=6650.0, src='fallback')
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_host_data(workload, n_local, seed):
+    from transferable3d_b200 import synth
+    u = min(UNIQUE, n_local)
+    b = synth.make_batch(u, N_POINTS, N_CH, seed=seed)
+    reps = (n_local + u - 1) // u
+    pc = np.tile(b['pc'], (reps, 1, 1))[:n_local]
+    oh = np.tile(b['one_hot'], (reps, 1))[:n_local]
+    return np.ascontiguousarray(pc), np.ascontiguousarray(oh)
+
+
+def standard_variables(workload):
+    from transferable3d_b200 import weights
+    if workload == 'cfg3':
+        return weights.standard_model_A()
+    v, info = weights.standard_model_F()
+    return v, info
+
+
+# ------------------------------------------------------------------------------------------ reference arm (CPU)
+
+def run_reference(args):
+    """The reference algorithm (oracle restatement of the TF1 graph, literal tiled-global conv6, every
+    activation materialised) on the host cores; PyTorch-CPU with all threads.  Not TensorFlow."""
+    import torch
+    from oracle.tf_layers import VarStore
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    workload = args.workload
+    variables, _ = standard_variables(workload)
+    sample = args.ref_sample
+    pc, oh = make_host_data(workload, sample, 1234 + (3 if workload == 'cfg3' else 2))
+    torch.set_num_threads(os.cpu_count() or 1)
+    vs = VarStore(variables)
+    vs.literal = True
+    pc_t, oh_t = torch.as_tensor(pc), torch.as_tensor(oh)
+
+    def step():
+        with torch.no_grad():
+            if workload == 'cfg3':
+                oracle_cfg3(vs, pc_t, oh_t)
+            else:
+                from oracle import semisup_models as osm
+                with vs.variable_scope('class_agnostic'):
+                    osm.v1_inst_seg(pc_t, None, None, {}, False, vs, scope='inst_seg')
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = sample / dt
+    line = {'impl': 'reference', 'metric': 'frustums_per_sec', 'value': value, 'unit': 'frustums/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(workload, args, sample_note='reference arm: %d frustums per step' % sample),
+            'cpu_baseline': {'value': value, 'unit': 'frustums/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                             'sample': '%d frustums per step, oracle restatement of the TF1 graph on PyTorch-CPU' % sample},
+            'e2e': {'value': value, 'unit': 'frustums/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def oracle_cfg3(vs, pc_t, oh_t, seed=5):
+    """SURVEY 3.2 pipeline on the oracle (model-A variable names)."""
+    import torch
+    from oracle import semisup_models as osm, model_util as omu
+    from oracle.tf_layers import conv2d, fully_connected, max_pool_points
+    from transferable3d_b200.constants import MEAN_DIMS_ARR
+    ep = {}
+    logits = osm.v1_inst_seg(pc_t, None, oh_t, ep, False, vs, scope='inst_seg')
+    obj, mean, ep = omu.point_cloud_masking(pc_t, logits, ep, rng_mode='philox', seed=seed)
+    with vs.variable_scope('tnet'):
+        delta, _ = omu.get_center_regression_net(obj, oh_t, False, None, ep, vs)
+    s1 = delta + mean
+    with vs.variable_scope('box_est'):
+        net = obj - delta.unsqueeze(1)
+        for nm, c in (('conv-reg1', 128), ('conv-reg2', 128), ('conv-reg3', 256), ('conv-reg4', 512)):
+            net = conv2d(net, c, [1, 1], vs, nm, True, False)
+        net = torch.cat([max_pool_points(net), oh_t], dim=1)
+        net = fully_connected(net, 512, vs, 'fc1', True, False)
+        net = fully_connected(net, 256, vs, 'fc2', True, False)
+        out = fully_connected(net, 67, vs, 'fc3', activation_fn=None)
+    ep = omu.parse_output_to_tensors(out, ep, 12, MEAN_DIMS_ARR)
+    ep['center'] = ep['center_boxnet'] + s1
+    ep['mask_logits'] = logits
+    return ep
+
+
+def workload_config(workload, args, sample_note=None):
+    c = {'workload': ('cfg3: Frustum PointNet v1 pipeline inference (seg -> mask/centroid/resample 512 -> T-Net -> '
+                      'box-est NH=12 NS=10), 8192 frustums x 2048 pts x 6 ch + one-hot, sharded over the GPUs')
+         if workload == 'cfg3' else 'cfg2: instance-seg per-point MLP chain alone, 1024 frustums x 2048 pts x 6 ch per GPU',
+         'global_frustums': TOTAL_FRUSTUMS[workload] * (args.gpus if workload == 'cfg2' else 1),
+         'num_point': N_POINTS, 'num_channel': N_CH, 'chunk_frustums': args.chunk, 'parallelism': 'shard%d' % args.gpus,
+         'precision': 'bf16 operands / fp32 accumulate (tcgen05), fp32 heads',
+         'weights': 'synthetic Xavier (seed 42), seg logits calibrated (margin std 2.0, 40% masked-in)',
+         'resample_rng': 'philox', 'l2': 'per-step inputs (>= 400 MB per GPU at N=1) exceed the 126 MB L2; no explicit flush'}
+    if sample_note:
+        c['sample'] = sample_note
+    return c
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='t3d', choices=['t3d', 'reference'])
+    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg2'])
+    ap.add_argument('--chunk', type=int, default=1024)
+    ap.add_argument('--ref-sample', type=int, default=8)
+    ap.add_argument('--cpu-sample', type=int, default=8)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from transferable3d_b200 import runtime as rt, _lib, model_util as mu, semisup_models as sm
+    from transferable3d_b200 import frustum_pointnets_v1 as fpn
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device: the B200 path has no CPU fallback')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == args.gpus, 'launch with torchrun --nproc-per-node %d' % args.gpus
+    workload = args.workload
+    total = TOTAL_FRUSTUMS[workload]
+    n_local = total // world if workload == 'cfg3' else total
+    chunk = min(args.chunk, n_local)
+    assert n_local % chunk == 0
+
+    variables, winfo = standard_variables(workload)
+    store = rt.VariableStore(variables, dev)
+    rt.set_default_store(store)
+    rt.set_precision('bf16')
+    mu.set_resample_rng('philox', seed=5)
+    pc_h, oh_h = make_host_data(workload, n_local, 1234 + (3 if workload == 'cfg3' else 2))
+    pc_pin = torch.from_numpy(pc_h).pin_memory()
+    oh_pin = torch.from_numpy(oh_h).pin_memory()
+    pc_dev, oh_dev = pc_pin.to(dev), oh_pin.to(dev)
+
+    # launch counting + per-kernel timing of the dominant kernel (CUDA events on the launching stream)
+    launches = {'n': 0}
+    KERNELS_PER_CALL = {'t3d_chain_max_bf16': 1, 't3d_seg_stage2_bf16': 1, 't3d_linear_f32': 1, 't3d_mask_centroid': 1,
+                        't3d_resample': 1, 't3d_build_tiles': 1, 't3d_parse_box': 1, 't3d_prepare_xyz': 1,
+                        't3d_boxpc_features': 1, 't3d_anchor_to_reg': 1, 't3d_boxpc_refine': 1, 't3d_f2': 1,
+                        't3d_box3d_corners_helper': 1, 't3d_box3d_corners_all': 1}
+    dom = {'events': [], 'on': False}
+    orig_call = _lib.call
+
+    def counting_call(name, *a):
+        launches['n'] += KERNELS_PER_CALL.get(name, 0)
+        if dom['on'] and name == 't3d_seg_stage2_bf16':
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig_call(name, *a)
+            e1.record()
+            dom['events'].append((e0, e1))
+        else:
+            orig_call(name, *a)
+    for mod in (rt, sm, mu, _lib):
+        if hasattr(mod, 'call'):
+            mod.call = counting_call
+    import transferable3d_b200.tf_util as tu
+    import transferable3d_b200.boxpc_sunrgbd as bp
+    import transferable3d_b200.test_semisup as ts
+    for mod in (tu, bp, ts):
+        mod.call = counting_call
+
+    def pipeline(pc, oh):
+        if workload == 'cfg3':
+            return fpn.get_model(pc, oh, False)
+        return {'mask_logits': sm.v1_inst_seg(pc, None, None, {}, False, scope='class_agnostic/inst_seg')}
+
+    OUT_KEYS = ('mask_logits', 'center', 'heading_scores', 'heading_residuals', 'size_scores', 'size_residuals') \
+        if workload == 'cfg3' else ('mask_logits',)
+
+    def step_resident():
+        with torch.no_grad():
+            for c0 in range(0, n_local, chunk):
+                pipeline(pc_dev[c0:c0 + chunk], oh_dev[c0:c0 + chunk])
+
+    # e2e: double-buffered H2D / compute / D2H
+    copy_s, back_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    in_bufs = [(torch.empty((chunk, N_POINTS, N_CH), device=dev), torch.empty((chunk, 10), device=dev)) for _ in range(2)]
+    host_out = {}
+    bytes_io = {'h2d': 0, 'd2h': 0}
+
+    def step_e2e():
+        comp = torch.cuda.current_stream()
+        bytes_io['h2d'] = bytes_io['d2h'] = 0
+        nchunks = n_local // chunk
+        ready = [None, None]
+        consumed = [None, None]
+        outs_done = []
+
+        def issue_copy(i):
+            s = i % 2
+            with torch.cuda.stream(copy_s):
+                if consumed[s] is not None:
+                    copy_s.wait_event(consumed[s])
+                in_bufs[s][0].copy_(pc_pin[i * chunk:(i + 1) * chunk], non_blocking=True)
+                in_bufs[s][1].copy_(oh_pin[i * chunk:(i + 1) * chunk], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_s)
+                ready[s] = ev
+            bytes_io['h2d'] += in_bufs[s][0].numel() * 4 + in_bufs[s][1].numel() * 4
+        issue_copy(0)
+        with torch.no_grad():
+            for i in range(nchunks):
+                s = i % 2
+                if i + 1 < nchunks:
+                    issue_copy(i + 1)
+                comp.wait_event(ready[s])
+                ep = pipeline(in_bufs[s][0], in_bufs[s][1])
+                ev = torch.cuda.Event()
+                ev.record(comp)
+                consumed[s] = ev
+                with torch.cuda.stream(back_s):
+                    back_s.wait_event(ev)
+                    for k in OUT_KEYS:
+                        t = ep[k]
+                        key = (k, i % 2)
+                        if key not in host_out:
+                            host_out[key] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                        host_out[key].copy_(t, non_blocking=True)
+                        t.record_stream(back_s)
+                        bytes_io['d2h'] += t.numel() * t.element_size()
+                    e2 = torch.cuda.Event()
+                    e2.record(back_s)
+                    outs_done.append(e2)
+        for e in outs_done:
+            comp.wait_event(e)
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        launches['n'] = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches['n'], clocks
+
+    dom['on'] = True
+    ms, n_launch, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    dom['on'] = False
+    dom_ms = [a.elapsed_time(b) for a, b in dom['events'][-(args.steps * (n_local // chunk)):]]
+    ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
+
+    total_units = n_local * world
+    value = total_units / ms * 1e3
+    e2e_value = total_units / ms_e2e * 1e3
+    pk = peaks()
+    roof = None
+    if dom_ms:
+        avg = float(np.mean(dom_ms))
+        flops = FLOP_SEG2_PT * chunk * N_POINTS
+        ach = flops / (avg * 1e-3) / 1e12
+        roof = {'kernel': 'seg_stage2_kernel (conv6..conv10, tcgen05)', 'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16'],
+                'unit': 'TFLOP/s', 'frac': ach / pk['bf16'], 'traffic': None, 'avg_launch_ms': avg,
+                'algorithmic_flops_per_launch': flops, 'peak_source': '%s, sustained bf16 (kernel timed inside a long step)' % pk['src']}
+    if workload == 'cfg3':
+        flops_fr = (FLOP_SEG1_PT + FLOP_SEG2_PT) * N_POINTS + FLOP_SEG_GLOBAL_FR + (FLOP_TNET_PT + FLOP_BOX_PT) * 512 + FLOP_FC_FR
+    else:
+        flops_fr = (FLOP_SEG1_PT + FLOP_SEG2_PT) * N_POINTS + 2 * 1024 * 512
+    line = {'metric': 'frustums_per_sec', 'value': value, 'unit': 'frustums/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
+            'scaling': 'strong' if workload == 'cfg3' else 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': workload_config(workload, args), 'clocks': clocks,
+            'e2e': {'value': e2e_value, 'unit': 'frustums/s', 'h2d_bytes_per_step': bytes_io['h2d'],
+                    'd2h_bytes_per_step': bytes_io['d2h'], 'ms_per_step': ms_e2e},
+            'gpu_launches': n_launch, 'roofline': roof,
+            'pipeline_tflops': value * flops_fr / 1e12, 'pipeline_frac_of_bf16_peak': value * flops_fr / 1e12 / (pk['bf16'] * world)}
+
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            line['cpu_baseline'] = cpu_baseline(workload, variables, args.cpu_sample)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(workload, variables, sample):
+    """Oracle (literal TF1-graph restatement, PyTorch-CPU fp32, all host threads) on a bounded sample."""
+    import torch
+    from oracle.tf_layers import VarStore
+    torch.set_num_threads(os.cpu_count() or 1)
+    pc, oh = make_host_data(workload, sample, 99)
+    vs = VarStore(variables)
+    vs.literal = True
+    pc_t, oh_t = torch.as_tensor(pc), torch.as_tensor(oh)
+
+    def step():
+        with torch.no_grad():
+            if workload == 'cfg3':
+                oracle_cfg3(vs, pc_t, oh_t)
+            else:
+                from oracle import semisup_models as osm
+                with vs.variable_scope('class_agnostic'):
+                    osm.v1_inst_seg(pc_t, None, None, {}, False, vs, scope='inst_seg')
+    step()
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 3 or time.perf_counter() - t0 < 10.0:
+        step()
+        reps += 1
+        if time.perf_counter() - t0 > 30.0:
+            break
+    dt = (time.perf_counter() - t0) / reps
+    return {'value': sample / dt, 'unit': 'frustums/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '%d frustums x %d reps, oracle restatement of the TF1 graph (literal conv6) on PyTorch-CPU' % (sample, reps)}
+
+
+if __name__ == '__main__':
+    main()

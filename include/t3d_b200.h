@@ -131,6 +131,11 @@ int t3d_pack_seg2(const float* W6p /* [64,512] */, const float* W7 /* [512,256] 
 int t3d_seg_stage2_bf16(const void* point_feat /* bf16 [B*N,64] */, const float* gbias, const void* arena,
                         float* logits, int B, int N, t3d_stream_t stream);
 
+/* Debug hook (not part of the reference-facing surface): install a device buffer of
+ * 4 * 8192 uint64 into which CTA 0 of the tcgen05 kernels records (clock64 << 8 | tag) per role
+ * (0 weight producer, 1 MMA issuer, 2 epilogue warp, 3 front warp); NULL switches tracing off. */
+int t3d_set_trace_buffer(void* dev_buf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,7 @@ SIGNATURES = {
     't3d_seg2_arena_bytes': (_c.c_size_t, []),
     't3d_pack_seg2': (_I, [_P] * 10 + [_P]),
     't3d_seg_stage2_bf16': (_I, [_P, _P, _P, _P, _I, _I, _P]),
+    't3d_set_trace_buffer': (_I, [_P]),
 }
 
 _lib = None

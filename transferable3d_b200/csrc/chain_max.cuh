@@ -101,6 +101,7 @@ struct ChainArgs {
   const uint8_t* arena;     // packed weights
   float* out;               // [B, FC] fp32, zero-initialised by the caller; atomic max target
   __nv_bfloat16* emit;      // [B*N, HN[EMIT_LAYER]] bf16 (seg1: point_feat) or null
+  unsigned long long* trace; // debug timeline of CTA 0 (null: off)
 };
 
 // smem carve-up (offsets from the 1024-aligned base)
@@ -183,10 +184,12 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
     if (lane == 0) {
       constexpr int NCH = chain_num_chunks<S>();
       uint32_t it = 0;
+      Tracer tr; tr.init(args.trace, 0);
       for (int t = tile_begin; t < tile_end; ++t) {
         for (int c = 0; c < NCH; ++c, ++it) {
           const int s = it % kRingStages;
           mbar_wait(ring_empty(s), ((it / kRingStages) & 1) ^ 1);
+          tr.mark(1);
           mbar_arrive_expect_tx(ring_full(s), kChunkBytes);
           bulk_g2s(sbase + L::RING + s * kChunkBytes, args.arena + (size_t)c * kChunkBytes, kChunkBytes, ring_full(s));
         }
@@ -198,11 +201,14 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
       uint32_t it = 0;                       // ring iteration
       uint32_t acc_cnt[3] = {0, 0, 0};       // uses of each TMEM region so far
       uint32_t tile_iter = 0;
+      Tracer tr; tr.init(args.trace, 1);
       for (int t = tile_begin; t < tile_end; ++t, ++tile_iter) {
         const uint32_t tpar = tile_iter & 1;
+        tr.mark(0x10);
 #pragma unroll
         for (int l = 0; l < S::NH; ++l) {
           mbar_wait(act_ready(l), tpar);
+          tr.mark(0x20 + l);
           for (int sub = 0; sub < NSUB; ++sub) {
             const int r = hidden_region(sub);
             mbar_wait(acc_empty(r), (acc_cnt[r] & 1) ^ 1);
@@ -229,16 +235,19 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
             }
           }
           for (int sub = 0; sub < NSUB; ++sub) { const int r = hidden_region(sub); umma_commit(acc_full(r)); acc_cnt[r]++; }
+          tr.mark(0x30 + l);
           if (l == S::FRONT_FREE_LAYER) umma_commit(front_free);
         }
         // final layer: channels on M, points on N
         mbar_wait(act_ready(S::NH), tpar);
+        tr.mark(0x40);
         tc_fence_after();
         const uint32_t b_buf = sbase + L::buf_off(S::ACT_BUF(S::NH));
         const uint32_t idesc_f = make_idesc_bf16(128, TILE);
         for (int mt = 0; mt < NCHUNK_FINAL_MT; ++mt) {
           const int r = mt & 1;
           mbar_wait(acc_empty(r), (acc_cnt[r] & 1) ^ 1);
+          tr.mark(0x50 + mt);
           tc_fence_after();
           const uint32_t d = tmem_base + region_col(r);
           for (int kb = 0; kb < S::FK / 64; ++kb, ++it) {
@@ -254,6 +263,7 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
           }
           umma_commit(acc_full(r));
           acc_cnt[r]++;
+          tr.mark(0x60 + mt);
         }
         if (S::NH == 0) umma_commit(front_free);
       }
@@ -270,10 +280,12 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
     const float* hbias = reinterpret_cast<const float*>(smem + L::HB);
     const float* fbias = reinterpret_cast<const float*>(args.arena + (size_t)chain_num_chunks<S>() * kChunkBytes) +
                          S::CIN * S::C1 + S::C1 + chain_hidden_bias_count<S>();
+    Tracer tr; tr.init((warp == 4 && lane == 0) ? args.trace : nullptr, 2);
     for (int t = tile_begin; t < tile_end; ++t) {
       int fr, start, npts;
       tile_info(t, fr, start, npts);
       int hb_off = 0;
+      tr.mark(0x10);
 #pragma unroll
       for (int l = 0; l < S::NH; ++l) {
         const uint32_t o_buf = sbase + L::buf_off(S::ACT_BUF(l + 1));
@@ -281,6 +293,7 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
           const int r = hidden_region(sub);
           mbar_wait(acc_full(r), acc_cnt[r] & 1);
           acc_cnt[r]++;
+          tr.mark(0x20 + l * 2 + sub);
           tc_fence_after();
           const uint32_t grow = sub * 128 + row;         // row inside the tile
 #pragma unroll 1
@@ -313,6 +326,7 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(act_ready(l + 1));
+        tr.mark(0x30 + l);
       }
       // final layer: this thread owns channel mt*128+row, columns are the tile's points
 #pragma unroll
@@ -320,6 +334,7 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
         const int r = mt & 1;
         mbar_wait(acc_full(r), acc_cnt[r] & 1);
         acc_cnt[r]++;
+        tr.mark(0x50 + mt);
         tc_fence_after();
         float m = run_max[mt];
 #pragma unroll 1
@@ -334,6 +349,7 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty(r));
+        tr.mark(0x60 + mt);
       }
       // flush when the frustum changes (or at the end of this CTA's range)
       bool flush = (t + 1 == tile_end);
@@ -355,10 +371,12 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
     const float* B1 = reinterpret_cast<const float*>(smem + L::B1);
     const uint32_t o_buf = sbase + L::buf_off(S::ACT_BUF(0));
     uint32_t tile_iter = 0;
+    Tracer tr; tr.init((warp == 8 && lane == 0) ? args.trace : nullptr, 3);
     for (int t = tile_begin; t < tile_end; ++t, ++tile_iter) {
       int fr, start, npts;
       tile_info(t, fr, start, npts);
       if (tile_iter > 0) mbar_wait(front_free, (tile_iter - 1) & 1);
+      tr.mark(0x10);
       float cx = 0.f, cy = 0.f, cz = 0.f;
       if (args.center) { cx = args.center[fr * 3 + 0]; cy = args.center[fr * 3 + 1]; cz = args.center[fr * 3 + 2]; }
       float bc[3] = {0, 0, 0}, hl = 0, hw = 0, hh = 0, ct = 1, st = 0;
@@ -404,6 +422,7 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(act_ready(0));
+      tr.mark(0x11);
     }
   }
 

@@ -140,4 +140,17 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ----------------------------------------------------------------------------- tracing (debug hook)
+// When a trace buffer is installed (t3d_set_trace_buffer) CTA 0 records (clock64 << 8 | tag) per role.
+constexpr int kTraceSlots = 8192;
+struct Tracer {
+  unsigned long long* buf; int n;
+  __device__ __forceinline__ void init(unsigned long long* base, int role) {
+    buf = (base != nullptr && blockIdx.x == 0) ? base + (size_t)role * kTraceSlots : nullptr; n = 0;
+  }
+  __device__ __forceinline__ void mark(int tag) {
+    if (buf != nullptr && n < kTraceSlots) buf[n++] = ((unsigned long long)clock64() << 8) | (unsigned long long)(tag & 0xff);
+  }
+};
+
 }  // namespace t3d

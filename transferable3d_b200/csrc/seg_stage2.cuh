@@ -28,6 +28,7 @@ struct Seg2Args {
   const uint8_t* arena;
   float* logits;                     // [B, N, 2]
   int B, N;
+  unsigned long long* trace;
 };
 
 struct Seg2Smem {
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(384, 1) seg_stage2_kernel(const Seg2Args args)
     if (lane == 0) {
       uint32_t it = 0, acc_cnt[3] = {0, 0, 0}, a6r_cnt[2] = {0, 0}, tile_iter = 0;
       const uint32_t idesc = make_idesc_bf16(128, 128);
+      Tracer tr; tr.init(args.trace, 1);
       auto mma_chunk = [&](uint32_t a_addr, uint32_t d, bool acc_first) {
         const int s = it % kRingStages;
         mbar_wait(ring_full(s), (it / kRingStages) & 1);
@@ -121,38 +123,47 @@ __global__ void __launch_bounds__(384, 1) seg_stage2_kernel(const Seg2Args args)
         const int r = nb & 1;
         mbar_wait(acc_empty(r), (acc_cnt[r] & 1) ^ 1);
         tc_fence_after();
+        tr.mark(0x20 + nb);
         mma_chunk(sbase + L::IN, tmem_base + region_col(r), false);
         umma_commit(acc_full(r)); acc_cnt[r]++;
+        tr.mark(0x28 + nb);
         if (nb == 3) umma_commit(in_free);
       };
       auto job7 = [&](int nb) {
         const int b = nb & 1;
         mbar_wait(a6_ready(b), a6r_cnt[b] & 1); a6r_cnt[b]++;
         if (nb == 0) mbar_wait(acc_empty(2), (acc_cnt[2] & 1) ^ 1);
+        tr.mark(0x30 + nb);
         tc_fence_after();
         for (int nh = 0; nh < 2; ++nh)
           for (int kb = 0; kb < 2; ++kb)
             mma_chunk(sbase + L::A6 + b * 32768 + kb * 16384, tmem_base + region_col(2) + nh * 128, (nb | kb) != 0);
         umma_commit(a6_free(b));
         if (nb == 3) { umma_commit(acc_full(2)); acc_cnt[2]++; }
+        tr.mark(0x38 + nb);
       };
       for (int t = tile_begin; t < tile_end; ++t, ++tile_iter) {
         const uint32_t tpar = tile_iter & 1;
         mbar_wait(in_ready, tpar);
+        tr.mark(0x10);
         tc_fence_after();
         job6(0); job6(1); job7(0); job6(2); job7(1); job6(3); job7(2); job7(3);
         // conv8: A = A7 (4 K-blocks), D = R6[0]
         mbar_wait(a7_ready, tpar);
         mbar_wait(acc_empty(0), (acc_cnt[0] & 1) ^ 1);
+        tr.mark(0x40);
         tc_fence_after();
         for (int kb = 0; kb < 4; ++kb) mma_chunk(sbase + L::A7 + kb * 16384, tmem_base + region_col(0), kb != 0);
         umma_commit(acc_full(0)); acc_cnt[0]++;
+        tr.mark(0x41);
         // conv9: A = A8 (in the A6[0] buffer, 2 K-blocks), D = R6[1]
         mbar_wait(a8_ready, tpar);
         mbar_wait(acc_empty(1), (acc_cnt[1] & 1) ^ 1);
+        tr.mark(0x50);
         tc_fence_after();
         for (int kb = 0; kb < 2; ++kb) mma_chunk(sbase + L::A6 + kb * 16384, tmem_base + region_col(1), kb != 0);
         umma_commit(acc_full(1)); acc_cnt[1]++;
+        tr.mark(0x51);
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -163,6 +174,7 @@ __global__ void __launch_bounds__(384, 1) seg_stage2_kernel(const Seg2Args args)
     const float* fl = reinterpret_cast<const float*>(smem + L::FL);
     const float* b7 = fl, *b8 = fl + 256, *b9 = fl + 384, *w10 = fl + 512, *b10 = fl + 768;
     uint32_t acc_cnt[3] = {0, 0, 0}, tile_iter = 0;
+    Tracer tr; tr.init((warp == 4 && lane == 0) ? args.trace : nullptr, 2);
 
     // reads NCOLS accumulator columns of region r, adds bias, ReLU, packs to bf16 and writes them as
     // K-blocks of 64 into the operand buffer at `obuf` (row-major 128 B rows, SW128).
@@ -201,19 +213,26 @@ __global__ void __launch_bounds__(384, 1) seg_stage2_kernel(const Seg2Args args)
         const int r = nb & 1;
         mbar_wait(acc_full(r), acc_cnt[r] & 1); acc_cnt[r]++;
         if (nb >= 2) mbar_wait(a6_free(r), 0);       // commit #(2*tile) of this buffer, see header
+        tr.mark(0x20 + nb);
         tc_fence_after();
         epi_to_smem(r, 128, gb + nb * 128, sbase + L::A6 + r * 32768);
         release(r, a6_ready(r));
+        tr.mark(0x28 + nb);
       }
       mbar_wait(acc_full(2), acc_cnt[2] & 1); acc_cnt[2]++;
+      tr.mark(0x30);
       tc_fence_after();
       epi_to_smem(2, 256, b7, sbase + L::A7);
       release(2, a7_ready);
+      tr.mark(0x31);
       mbar_wait(acc_full(0), acc_cnt[0] & 1); acc_cnt[0]++;
+      tr.mark(0x40);
       tc_fence_after();
       epi_to_smem(0, 128, b8, sbase + L::A6);          // act8 reuses the A6[0] buffer
       release(0, a8_ready);
+      tr.mark(0x41);
       mbar_wait(acc_full(1), acc_cnt[1] & 1); acc_cnt[1]++;
+      tr.mark(0x50);
       tc_fence_after();
       float l0 = b10[0], l1 = b10[1];
 #pragma unroll 1
@@ -232,6 +251,7 @@ __global__ void __launch_bounds__(384, 1) seg_stage2_kernel(const Seg2Args args)
       if (row < npts)
         *reinterpret_cast<float2*>(args.logits + ((size_t)fr * args.N + start + row) * 2) = make_float2(l0, l1);
       release(1, 0);
+      tr.mark(0x51);
     }
   } else if (warp >= 8) {
     // ================================================================ front warps: point_feat tile + gbias -> smem

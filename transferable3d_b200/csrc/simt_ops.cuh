@@ -238,7 +238,9 @@ __global__ void __launch_bounds__(1024) resample_kernel(const int* __restrict__ 
   if (n > 0 && mode == 0) {
     const bool sub = n > npoints;
     const int len = sub ? n : npoints;
-    for (int t = tid; t < 2048; t += 1024) {
+    int P = 512;                         // sort size: smallest power of two >= len
+    while (P < len) P <<= 1;
+    for (int t = tid; t < P; t += 1024) {
       unsigned long long key = ~0ull;
       if (t < len) {
         uint32_t o[4];
@@ -255,9 +257,9 @@ __global__ void __launch_bounds__(1024) resample_kernel(const int* __restrict__ 
     }
     __syncthreads();
     // bitonic sort of (key, payload) ascending, ties by payload (== numpy stable argsort)
-    for (int k = 2; k <= 2048; k <<= 1) {
+    for (int k = 2; k <= P; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int t = tid; t < 2048; t += 1024) {
+        for (int t = tid; t < P; t += 1024) {
           const int ixj = t ^ j;
           if (ixj > t) {
             const unsigned long long ka = keys[t], kb = keys[ixj];
@@ -469,15 +471,5 @@ __global__ void box3d_corners_all_kernel(const float* center, const float* headi
 // chunk image: [128 rows x 64 K] bf16, K-major SWIZZLE_128B; row r = output channel row0+r, K = k0..k0+63 of
 // W[K_total, Nout] (row-major, TF layout).  Rows >= nrows and k >= K_total are zero.
 struct PackDesc { const float* W; int ldw; int k_total; int k0; int row0; int nrows; };
-__global__ void __launch_bounds__(256) pack_chunks_kernel(const PackDesc* __restrict__ descs, uint8_t* __restrict__ arena) {
-  const PackDesc d = descs[blockIdx.x];
-  uint8_t* dst = arena + (size_t)blockIdx.x * 16384;
-  for (int e = threadIdx.x; e < 128 * 64; e += 256) {
-    const int r = e >> 6, kk = e & 63;
-    float v = 0.0f;
-    if (r < d.nrows && d.k0 + kk < d.k_total) v = d.W[(size_t)(d.k0 + kk) * d.ldw + d.row0 + r];
-    *reinterpret_cast<__nv_bfloat16*>(dst + sw128_offset(r, kk >> 3) + (kk & 7) * 2) = __float2bfloat16_rn(v);
-  }
-}
 
 }  // namespace t3d

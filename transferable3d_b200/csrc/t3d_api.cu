@@ -18,6 +18,9 @@ using namespace t3d;
     if (e__ != cudaSuccess) return (int)e__;        \
   } while (0)
 
+static unsigned long long* g_trace = nullptr;
+extern "C" int t3d_set_trace_buffer(void* dev_buf) { g_trace = reinterpret_cast<unsigned long long*>(dev_buf); return 0; }
+
 static inline cudaStream_t S(t3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 extern "C" int t3d_version(void) { return T3D_VERSION; }
@@ -292,7 +295,7 @@ extern "C" int t3d_chain_max_bf16(int kind, const float* pc, int B, int N, int C
   if (emit && (kind != CHAIN_SEG1 || ((uintptr_t)emit & 15))) return T3D_ERR_ARG;
   ChainArgs a{pc, B, N, C, center, idx, idx_stride, count, reinterpret_cast<const int4*>(tiles), num_tiles,
               box_center, box_dims, box_orient, reinterpret_cast<const uint8_t*>(arena), out,
-              reinterpret_cast<__nv_bfloat16*>(emit)};
+              reinterpret_cast<__nv_bfloat16*>(emit), g_trace};
   CHAIN_SWITCH(kind, return chain_launch<K_>(a, B * ChainSpec<K_>::FC, S(stream)));
   return 0;
 }
@@ -342,7 +345,7 @@ extern "C" int t3d_seg_stage2_bf16(const void* point_feat, const float* gbias, c
     T3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     T3D_CUDA(cudaFuncSetAttribute(seg_stage2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2Smem::TOTAL + 1024));
   }
-  Seg2Args a{reinterpret_cast<const __nv_bfloat16*>(point_feat), gbias, reinterpret_cast<const uint8_t*>(arena), logits, B, N};
+  Seg2Args a{reinterpret_cast<const __nv_bfloat16*>(point_feat), gbias, reinterpret_cast<const uint8_t*>(arena), logits, B, N, g_trace};
   const int nt = B * ((N + 127) / 128);
   const int grid = nt < sms ? nt : sms;
   seg_stage2_kernel<<<grid, 384, Seg2Smem::TOTAL + 1024, S(stream)>>>(a);
