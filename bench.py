@@ -186,7 +186,7 @@ def workload_config(workload, args, sample_note=None):
                       'box-est NH=12 NS=10), 8192 frustums x 2048 pts x 6 ch + one-hot, sharded over the GPUs')
          if workload == 'cfg3' else 'cfg2: instance-seg per-point MLP chain alone, 1024 frustums x 2048 pts x 6 ch per GPU',
          'global_frustums': TOTAL_FRUSTUMS[workload] * (args.gpus if workload == 'cfg2' else 1),
-         'num_point': N_POINTS, 'num_channel': N_CH, 'chunk_frustums': args.chunk, 'parallelism': 'shard%d' % args.gpus,
+         'num_point': N_POINTS, 'num_channel': N_CH, 'chunk_frustums': args.resident_chunk, 'e2e_chunk_frustums': args.chunk, 'parallelism': 'shard%d' % args.gpus,
          'precision': 'bf16 operands / fp32 accumulate (tcgen05), fp32 heads',
          'weights': 'synthetic Xavier (seed 42), seg logits calibrated (margin std 2.0, 40% masked-in)',
          'resample_rng': 'philox', 'l2': 'per-step inputs (>= 400 MB per GPU at N=1) exceed the 126 MB L2; no explicit flush'}
@@ -204,10 +204,12 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='t3d', choices=['t3d', 'reference'])
     ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg2'])
-    ap.add_argument('--chunk', type=int, default=1024)
+    ap.add_argument('--chunk', type=int, default=2048, help='frustums per chunk of the e2e (H2D/compute/D2H) pipeline')
+    ap.add_argument('--resident-chunk', type=int, default=8192, help='frustums per pass when inputs are resident in HBM')
     ap.add_argument('--ref-sample', type=int, default=8)
     ap.add_argument('--cpu-sample', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--breakdown', action='store_true', help='per-entry-point CUDA-event times of the resident step (stderr)')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -234,7 +236,8 @@ def main():
     total = TOTAL_FRUSTUMS[workload]
     n_local = total // world if workload == 'cfg3' else total
     chunk = min(args.chunk, n_local)
-    assert n_local % chunk == 0
+    rchunk = min(args.resident_chunk, n_local)
+    assert n_local % chunk == 0 and n_local % rchunk == 0
 
     variables, winfo = standard_variables(workload)
     store = rt.VariableStore(variables, dev)
@@ -252,17 +255,28 @@ def main():
                         't3d_resample': 1, 't3d_build_tiles': 1, 't3d_parse_box': 1, 't3d_prepare_xyz': 1,
                         't3d_boxpc_features': 1, 't3d_anchor_to_reg': 1, 't3d_boxpc_refine': 1, 't3d_f2': 1,
                         't3d_box3d_corners_helper': 1, 't3d_box3d_corners_all': 1}
-    dom = {'events': [], 'on': False}
+    dom = {'events': [], 'events_mp': [], 'on': False}
     orig_call = _lib.call
+
+    bd = {'on': False, 'ev': []}
 
     def counting_call(name, *a):
         launches['n'] += KERNELS_PER_CALL.get(name, 0)
-        if dom['on'] and name == 't3d_seg_stage2_bf16':
+        if bd['on']:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             orig_call(name, *a)
             e1.record()
-            dom['events'].append((e0, e1))
+            bd['ev'].append((name + (':%d' % a[0] if name == 't3d_chain_max_bf16' else ''), e0, e1))
+            return
+        is_seg2 = name == 't3d_seg_stage2_bf16'
+        is_seg1 = name == 't3d_chain_max_bf16' and a[0] == 0
+        if dom['on'] and (is_seg2 or is_seg1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig_call(name, *a)
+            e1.record()
+            dom['events' if is_seg2 else 'events_mp'].append((e0, e1))
         else:
             orig_call(name, *a)
     for mod in (rt, sm, mu, _lib):
@@ -284,8 +298,8 @@ def main():
 
     def step_resident():
         with torch.no_grad():
-            for c0 in range(0, n_local, chunk):
-                pipeline(pc_dev[c0:c0 + chunk], oh_dev[c0:c0 + chunk])
+            for c0 in range(0, n_local, rchunk):
+                pipeline(pc_dev[c0:c0 + rchunk], oh_dev[c0:c0 + rchunk])
 
     # e2e: double-buffered H2D / compute / D2H
     copy_s, back_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
@@ -370,9 +384,22 @@ def main():
     dom['on'] = True
     ms, n_launch, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
     dom['on'] = False
-    dom_ms = [a.elapsed_time(b) for a, b in dom['events'][-(args.steps * (n_local // chunk)):]]
+    dom_ms = [a.elapsed_time(b) for a, b in dom['events'][-(args.steps * (n_local // rchunk)):]]
     ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
 
+    if args.breakdown and rank == 0:
+        bd['on'] = True
+        step_resident()
+        torch.cuda.synchronize()
+        bd['on'] = False
+        agg = {}
+        for name, a, b in bd['ev']:
+            agg.setdefault(name, [0, 0.0])
+            agg[name][0] += 1
+            agg[name][1] += a.elapsed_time(b)
+        tot = sum(v[1] for v in agg.values())
+        for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            sys.stderr.write('  %-28s n=%3d  %8.3f ms  %.3f\n' % (name, n, t, t / tot))
     total_units = n_local * world
     value = total_units / ms * 1e3
     e2e_value = total_units / ms_e2e * 1e3
@@ -380,11 +407,20 @@ def main():
     roof = None
     if dom_ms:
         avg = float(np.mean(dom_ms))
-        flops = FLOP_SEG2_PT * chunk * N_POINTS
+        flops = FLOP_SEG2_PT * rchunk * N_POINTS
         ach = flops / (avg * 1e-3) / 1e12
         roof = {'kernel': 'seg_stage2_kernel (conv6..conv10, tcgen05)', 'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16'],
                 'unit': 'TFLOP/s', 'frac': ach / pk['bf16'], 'traffic': None, 'avg_launch_ms': avg,
                 'algorithmic_flops_per_launch': flops, 'peak_source': '%s, sustained bf16 (kernel timed inside a long step)' % pk['src']}
+    roof_mp = None
+    mp_ms = [a.elapsed_time(b) for a, b in dom['events_mp'][-(args.steps * (n_local // rchunk)):]]
+    if mp_ms:
+        avg = float(np.mean(mp_ms))
+        flops = FLOP_SEG1_PT * rchunk * N_POINTS
+        ach = flops / (avg * 1e-3) / 1e12
+        roof_mp = {'kernel': 'chain_max_kernel<SEG1> (conv1..conv5 + max-pool fused, tcgen05)', 'bound': 'tensor', 'achieved': ach,
+                   'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': ach / pk['bf16'], 'frac_of_burst_peak': ach / pk['bf16_burst'],
+                   'avg_launch_ms': avg, 'algorithmic_flops_per_launch': flops}
     if workload == 'cfg3':
         flops_fr = (FLOP_SEG1_PT + FLOP_SEG2_PT) * N_POINTS + FLOP_SEG_GLOBAL_FR + (FLOP_TNET_PT + FLOP_BOX_PT) * 512 + FLOP_FC_FR
     else:
@@ -395,7 +431,7 @@ def main():
             'config': workload_config(workload, args), 'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'frustums/s', 'h2d_bytes_per_step': bytes_io['h2d'],
                     'd2h_bytes_per_step': bytes_io['d2h'], 'ms_per_step': ms_e2e},
-            'gpu_launches': n_launch, 'roofline': roof,
+            'gpu_launches': n_launch, 'roofline': roof, 'roofline_fused_maxpool': roof_mp,
             'pipeline_tflops': value * flops_fr / 1e12, 'pipeline_frac_of_bf16_peak': value * flops_fr / 1e12 / (pk['bf16'] * world)}
 
     if rank == 0:

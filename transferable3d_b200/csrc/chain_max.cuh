@@ -14,7 +14,10 @@
 //                                     epilogue thread owns one channel and the max over points is a
 //                                     register reduction over its TMEM columns
 // Weights stream from L2 through a ring of 16 KB stages with cp.async.bulk (TMA engine) in
-// pre-swizzled chunk images [<=128 rows x 64 K]; mbarriers order producer / MMA / epilogue.
+// pre-swizzled chunk images [<=128 rows x 64 K]; the two CTAs of a cluster each fetch half of every
+// chunk and multicast it to both, halving L2 traffic.  mbarriers order producer / MMA / epilogue.
+// The two 128-point sub-tiles of a tile are independent chains through the hidden layers and are
+// ping-ponged (MMA of one overlaps the epilogue of the other); 8 epilogue warps split the columns.
 // Masked stacks run on compacted (masked-in) points only, which is exactly the reference's
 // max(act*mask): post-ReLU activations are >= 0 and the output is zero-initialised.
 #pragma once
@@ -115,45 +118,55 @@ template <typename S> struct ChainSmem {
   static constexpr int B1 = W1 + 4 * S::CIN * S::C1;
   static constexpr int HB = B1 + 4 * S::C1;                                  // hidden biases
   static constexpr int BARS = (HB + 4 * chain_hidden_bias_count<S>() + 15) / 16 * 16;
-  // barriers: ring_full[4], ring_empty[4], acc_full[3], acc_empty[3], act_ready[4], front_free
-  static constexpr int NBARS = 2 * kRingStages + 6 + 4 + 1;
+  // barriers: ring_full[4], ring_empty[4], acc_full[3], acc_empty[3], act_ready[4][2], front_free
+  static constexpr int NBARS = 2 * kRingStages + 6 + 8 + 1;
   static constexpr int TMEM_SLOT = BARS + 8 * NBARS;
   static constexpr int TOTAL = TMEM_SLOT + 16;
   static constexpr int buf_off(int b) { return b == 0 ? BUF0 : (b == 1 ? BUF1 : BUF2); }
 };
 
+constexpr int kChainThreads = 512;   // warp 0 producer, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 epilogue, 12-15 front
+constexpr int kClusterSize = 2;
+
 template <int KIND>
-__global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args) {
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kChainThreads, 1) chain_max_kernel(const ChainArgs args) {
   using S = ChainSpec<KIND>;
   using L = ChainSmem<S>;
   constexpr int TILE = L::TILE;
   constexpr int NSUB = S::NSUB;
-  constexpr int NCHUNK_FINAL_MT = S::FC / 128;
+  constexpr int NMT = S::FC / 128;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  constexpr uint16_t kAllCtas = (1u << kClusterSize) - 1;
 
   const uint32_t bar0 = sbase + L::BARS;
   auto ring_full = [&](int s) { return bar0 + 8u * s; };
   auto ring_empty = [&](int s) { return bar0 + 8u * (kRingStages + s); };
   auto acc_full = [&](int r) { return bar0 + 8u * (2 * kRingStages + r); };
   auto acc_empty = [&](int r) { return bar0 + 8u * (2 * kRingStages + 3 + r); };
-  auto act_ready = [&](int a) { return bar0 + 8u * (2 * kRingStages + 6 + a); };
-  const uint32_t front_free = bar0 + 8u * (2 * kRingStages + 10);
+  auto act_ready = [&](int a, int sub) { return bar0 + 8u * (2 * kRingStages + 6 + a * 2 + sub); };
+  const uint32_t front_free = bar0 + 8u * (2 * kRingStages + 14);
 
   // TMEM regions (column bases): NSUB==2: R0=0, R1=256 shared by hidden(sub) and final(mt&1);
   //                              NSUB==1: final R0=0, R1=128, hidden R2=256.
   auto region_col = [&](int r) -> uint32_t { return NSUB == 2 ? (uint32_t)(r * 256) : (r == 2 ? 256u : (uint32_t)(r * 128)); };
   auto hidden_region = [&](int sub) { return NSUB == 2 ? sub : 2; };
 
-  // tile range of this CTA (contiguous => consecutive tiles mostly share a frustum)
+  // Tiles: every cluster owns a contiguous range; its two CTAs take alternate tiles and run the SAME
+  // number of iterations (the weight ring is shared in lock-step); a CTA without a tile of its own
+  // repeats the cluster's last tile (all outputs are idempotent: max / identical stores).
   const int tiles_per_frustum = (args.N + TILE - 1) / TILE;
   const int num_tiles = args.tiles ? *args.num_tiles_ptr : args.B * tiles_per_frustum;
-  const int tile_begin = (int)(((long long)num_tiles * blockIdx.x) / gridDim.x);
-  const int tile_end = (int)(((long long)num_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const int ncl = gridDim.x / kClusterSize, cl = blockIdx.x / kClusterSize;
+  const int cbegin = (int)(((long long)num_tiles * cl) / ncl);
+  const int cend = (int)(((long long)num_tiles * (cl + 1)) / ncl);
+  const int iters = (cend - cbegin + kClusterSize - 1) / kClusterSize;
+  auto tile_of = [&](int i) { return min(cbegin + i * kClusterSize + (int)crank, cend - 1); };
   auto tile_info = [&](int t, int& fr, int& start, int& npts) {
     if (args.tiles) { int4 d = args.tiles[t]; fr = d.x; start = d.y; npts = d.z; }
     else { fr = t / tiles_per_frustum; start = (t % tiles_per_frustum) * TILE; npts = min(TILE, args.N - start); }
@@ -161,9 +174,10 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
 
   // ------------------------------------------------------------------ setup
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kRingStages; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), 1); }
-    for (int r = 0; r < 3; ++r) { mbar_init(acc_full(r), 1); mbar_init(acc_empty(r), 4); }
-    for (int a = 0; a < 4; ++a) mbar_init(act_ready(a), 4);
+    for (int s = 0; s < kRingStages; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), kClusterSize); }
+    for (int r = 0; r < 3; ++r) { mbar_init(acc_full(r), 1); mbar_init(acc_empty(r), 8); }
+    for (int a = 0; a < 4; ++a)
+      for (int sub = 0; sub < 2; ++sub) mbar_init(act_ready(a, sub), a == 0 ? 4 : 8);
     mbar_init(front_free, 1);
     fence_barrier_init();
   }
@@ -176,75 +190,87 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();              // peer barriers are initialised before any multicast reaches them
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_SLOT);
 
   if (warp == 0) {
-    // ================================================================ weight producer
+    // ================================================================ weight producer (half of every chunk, multicast)
     if (lane == 0) {
       constexpr int NCH = chain_num_chunks<S>();
+      constexpr uint32_t kHalf = kChunkBytes / kClusterSize;
       uint32_t it = 0;
       Tracer tr; tr.init(args.trace, 0);
-      for (int t = tile_begin; t < tile_end; ++t) {
+      for (int i = 0; i < iters; ++i) {
         for (int c = 0; c < NCH; ++c, ++it) {
           const int s = it % kRingStages;
           mbar_wait(ring_empty(s), ((it / kRingStages) & 1) ^ 1);
           tr.mark(1);
           mbar_arrive_expect_tx(ring_full(s), kChunkBytes);
-          bulk_g2s(sbase + L::RING + s * kChunkBytes, args.arena + (size_t)c * kChunkBytes, kChunkBytes, ring_full(s));
+          bulk_g2s_mc(sbase + L::RING + s * kChunkBytes + crank * kHalf, args.arena + (size_t)c * kChunkBytes + crank * kHalf,
+                      kHalf, ring_full(s), kAllCtas);
         }
       }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     if (lane == 0) {
-      uint32_t it = 0;                       // ring iteration
+      uint32_t it = 0;                       // ring iteration of the first chunk of the current layer
       uint32_t acc_cnt[3] = {0, 0, 0};       // uses of each TMEM region so far
-      uint32_t tile_iter = 0;
       Tracer tr; tr.init(args.trace, 1);
-      for (int t = tile_begin; t < tile_end; ++t, ++tile_iter) {
-        const uint32_t tpar = tile_iter & 1;
+      for (int i = 0; i < iters; ++i) {
+        const uint32_t tpar = i & 1;
+        int fr, start, npts;
+        tile_info(tile_of(i), fr, start, npts);
         tr.mark(0x10);
 #pragma unroll
         for (int l = 0; l < S::NH; ++l) {
-          mbar_wait(act_ready(l), tpar);
-          tr.mark(0x20 + l);
+          const uint32_t a_buf = sbase + L::buf_off(S::ACT_BUF(l));
+          const int nbn = (S::HN(l) + 127) / 128, kbn = S::HK(l) / 64;
           for (int sub = 0; sub < NSUB; ++sub) {
             const int r = hidden_region(sub);
+            mbar_wait(act_ready(l, sub), tpar);
+            tr.mark(0x20 + l * 2 + sub);
+            if (S::EMIT_LAYER >= 0 && l == S::EMIT_LAYER + 1 && args.emit != nullptr) {
+              // point_feat of this sub-tile: the swizzled [128 x 64] bf16 operand image goes to HBM as is
+              const size_t trow = ((size_t)fr * tiles_per_frustum + start / TILE) * TILE + sub * 128;
+              bulk_s2g(reinterpret_cast<uint8_t*>(args.emit) + trow * 128, a_buf + sub * (128 * 128), 128 * 128);
+            }
             mbar_wait(acc_empty(r), (acc_cnt[r] & 1) ^ 1);
-          }
-          tc_fence_after();
-          const uint32_t a_buf = sbase + L::buf_off(S::ACT_BUF(l));
-          const int nbn = (S::HN(l) + 127) / 128;
-          for (int nb = 0; nb < nbn; ++nb) {
-            const int ncols = min(128, S::HN(l) - nb * 128);
-            const uint32_t idesc = make_idesc_bf16(128, ncols);
-            for (int kb = 0; kb < S::HK(l) / 64; ++kb, ++it) {
-              const int s = it % kRingStages;
-              mbar_wait(ring_full(s), (it / kRingStages) & 1);
-              tc_fence_after();
-              const uint32_t b_addr = sbase + L::RING + s * kChunkBytes;
-              for (int sub = 0; sub < NSUB; ++sub) {
+            tc_fence_after();
+            for (int nb = 0; nb < nbn; ++nb) {
+              const int ncols = min(128, S::HN(l) - nb * 128);
+              const uint32_t idesc = make_idesc_bf16(128, ncols);
+              for (int kb = 0; kb < kbn; ++kb) {
+                const uint32_t itc = it + nb * kbn + kb;
+                const int s = itc % kRingStages;
+                if (sub == 0) { mbar_wait(ring_full(s), (itc / kRingStages) & 1); tc_fence_after(); }
+                const uint32_t b_addr = sbase + L::RING + s * kChunkBytes;
                 const uint32_t a_addr = a_buf + kb * (TILE * 128) + sub * (128 * 128);
-                const uint32_t d = tmem_base + region_col(hidden_region(sub)) + nb * 128;
+                const uint32_t d = tmem_base + region_col(r) + nb * 128;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   umma_bf16(d, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32), idesc, (kb | k) != 0);
+                if (sub == NSUB - 1) umma_commit_mc(ring_empty(s), kAllCtas);
               }
-              umma_commit(ring_empty(s));
             }
+            umma_commit(acc_full(r));
+            acc_cnt[r]++;
+            tr.mark(0x30 + l * 2 + sub);
           }
-          for (int sub = 0; sub < NSUB; ++sub) { const int r = hidden_region(sub); umma_commit(acc_full(r)); acc_cnt[r]++; }
-          tr.mark(0x30 + l);
-          if (l == S::FRONT_FREE_LAYER) umma_commit(front_free);
+          it += nbn * kbn;
+          if (l == S::FRONT_FREE_LAYER) {
+            if (S::EMIT_LAYER >= 0 && args.emit != nullptr) bulk_wait_read_all();   // emit has left the smem buffer
+            umma_commit(front_free);
+          }
         }
         // final layer: channels on M, points on N
-        mbar_wait(act_ready(S::NH), tpar);
+        for (int sub = 0; sub < NSUB; ++sub) mbar_wait(act_ready(S::NH, sub), tpar);
         tr.mark(0x40);
         tc_fence_after();
         const uint32_t b_buf = sbase + L::buf_off(S::ACT_BUF(S::NH));
         const uint32_t idesc_f = make_idesc_bf16(128, TILE);
-        for (int mt = 0; mt < NCHUNK_FINAL_MT; ++mt) {
+        for (int mt = 0; mt < NMT; ++mt) {
           const int r = mt & 1;
           mbar_wait(acc_empty(r), (acc_cnt[r] & 1) ^ 1);
           tr.mark(0x50 + mt);
@@ -259,7 +285,7 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(d, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32), idesc_f, (kb | k) != 0);
-            umma_commit(ring_empty(s));
+            umma_commit_mc(ring_empty(s), kAllCtas);
           }
           umma_commit(acc_full(r));
           acc_cnt[r]++;
@@ -267,28 +293,47 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
         }
         if (S::NH == 0) umma_commit(front_free);
       }
+      if (S::EMIT_LAYER >= 0 && args.emit != nullptr) bulk_wait_all();
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ================================================================ epilogue warps (TMEM lane quarter = warp&3)
+  } else if (warp >= 4 && warp < 12) {
+    // ================================================================ epilogue warps: TMEM lane quarter = warp&3, column half = (warp-4)>>2
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int row = q * 32 + lane;                 // TMEM lane owned by this thread
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     uint32_t acc_cnt[3] = {0, 0, 0};
-    float run_max[NCHUNK_FINAL_MT];
+    float run_max[NMT];
 #pragma unroll
-    for (int i = 0; i < NCHUNK_FINAL_MT; ++i) run_max[i] = -3.0e38f;
-    const float* hbias = reinterpret_cast<const float*>(smem + L::HB);
+    for (int i = 0; i < NMT; ++i) run_max[i] = -3.0e38f;
+    const uint32_t hbias = sbase + L::HB;            // fp32 hidden biases in smem (byte address)
     const float* fbias = reinterpret_cast<const float*>(args.arena + (size_t)chain_num_chunks<S>() * kChunkBytes) +
                          S::CIN * S::C1 + S::C1 + chain_hidden_bias_count<S>();
     Tracer tr; tr.init((warp == 4 && lane == 0) ? args.trace : nullptr, 2);
-    for (int t = tile_begin; t < tile_end; ++t) {
+
+    // 32 accumulator columns [c0, c0+32) of this thread's row: +bias, ReLU, bf16, into the next operand
+    auto store_group = [&](const uint32_t (&v)[32], uint32_t bias, int c0, uint32_t o_buf, uint32_t grow) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = ld_shared_f4(bias + 4u * (c0 + 4 * j));
+        pk[2 * j] = pack_bf16_relu(__uint_as_float(v[4 * j]) + b4.x, __uint_as_float(v[4 * j + 1]) + b4.y);
+        pk[2 * j + 1] = pack_bf16_relu(__uint_as_float(v[4 * j + 2]) + b4.z, __uint_as_float(v[4 * j + 3]) + b4.w);
+      }
+      const int kb = c0 >> 6, j0 = (c0 & 63) >> 3;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        st_shared_v4(o_buf + kb * (TILE * 128) + sw128_offset(grow, j0 + jj), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+    };
+
+    for (int i = 0; i < iters; ++i) {
       int fr, start, npts;
-      tile_info(t, fr, start, npts);
+      tile_info(tile_of(i), fr, start, npts);
       int hb_off = 0;
       tr.mark(0x10);
 #pragma unroll
       for (int l = 0; l < S::NH; ++l) {
         const uint32_t o_buf = sbase + L::buf_off(S::ACT_BUF(l + 1));
+        const int span = S::HN(l) / 2, cbeg = half * span;
         for (int sub = 0; sub < NSUB; ++sub) {
           const int r = hidden_region(sub);
           mbar_wait(acc_full(r), acc_cnt[r] & 1);
@@ -296,54 +341,51 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
           tr.mark(0x20 + l * 2 + sub);
           tc_fence_after();
           const uint32_t grow = sub * 128 + row;         // row inside the tile
-#pragma unroll 1
-          for (int c0 = 0; c0 < S::HN(l); c0 += 32) {
+          const uint32_t taddr = tmem_base + lane_sel + region_col(r);
+          if (span == 32) {
             uint32_t v[32];
-            tmem_ld32(tmem_base + lane_sel + region_col(r) + c0, v);
+            tmem_ld32(taddr + cbeg, v);
             tmem_ld_wait();
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 b2 = *reinterpret_cast<const float2*>(hbias + hb_off + c0 + 2 * j);
-              pk[j] = pack_bf16_relu(__uint_as_float(v[2 * j]) + b2.x, __uint_as_float(v[2 * j + 1]) + b2.y);
-            }
-            const int kb = c0 >> 6;
-            const int j0 = (c0 & 63) >> 3;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              st_shared_v4(o_buf + kb * (TILE * 128) + sw128_offset(grow, j0 + jj), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
-            if (l == S::EMIT_LAYER && args.emit != nullptr && (int)grow < npts) {
-              uint4* dst = reinterpret_cast<uint4*>(args.emit + ((size_t)fr * args.N + start + grow) * S::HN(l) + c0);
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) dst[jj] = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+            store_group(v, hbias + 4u * hb_off, cbeg, o_buf, grow);
+          } else {
+#pragma unroll 1
+            for (int c0 = cbeg; c0 < cbeg + span; c0 += 64) {
+              uint32_t va[32], vb[32];
+              tmem_ld32(taddr + c0, va);
+              tmem_ld32(taddr + c0 + 32, vb);
+              tmem_ld_wait();
+              store_group(va, hbias + 4u * hb_off, c0, o_buf, grow);
+              store_group(vb, hbias + 4u * hb_off, c0 + 32, o_buf, grow);
             }
           }
           tc_fence_before();
+          fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty(r));
+          if (lane == 0) { mbar_arrive(act_ready(l + 1, sub)); mbar_arrive(acc_empty(r)); }
+          tr.mark(0x30 + l * 2 + sub);
         }
         hb_off += S::HN(l);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(act_ready(l + 1));
-        tr.mark(0x30 + l);
       }
-      // final layer: this thread owns channel mt*128+row, columns are the tile's points
+      // final layer: this thread owns channel mt*128+row, columns [half*TILE/2, +TILE/2) are points
 #pragma unroll
-      for (int mt = 0; mt < NCHUNK_FINAL_MT; ++mt) {
+      for (int mt = 0; mt < NMT; ++mt) {
         const int r = mt & 1;
         mbar_wait(acc_full(r), acc_cnt[r] & 1);
         acc_cnt[r]++;
         tr.mark(0x50 + mt);
         tc_fence_after();
         float m = run_max[mt];
+        const uint32_t taddr = tmem_base + lane_sel + region_col(r) + half * (TILE / 2);
 #pragma unroll 1
-        for (int c0 = 0; c0 < TILE; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + lane_sel + region_col(r) + c0, v);
+        for (int c0 = 0; c0 < TILE / 2; c0 += 64) {
+          uint32_t va[32], vb[32];
+          tmem_ld32(taddr + c0, va);
+          tmem_ld32(taddr + c0 + 32, vb);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) m = fmax3(m, __uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          for (int j = 0; j < 16; ++j) m = fmax3(m, __uint_as_float(va[2 * j]), __uint_as_float(va[2 * j + 1]));
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m = fmax3(m, __uint_as_float(vb[2 * j]), __uint_as_float(vb[2 * j + 1]));
         }
         run_max[mt] = m;
         tc_fence_before();
@@ -352,11 +394,11 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
         tr.mark(0x60 + mt);
       }
       // flush when the frustum changes (or at the end of this CTA's range)
-      bool flush = (t + 1 == tile_end);
-      if (!flush) { int f2, s2, n2; tile_info(t + 1, f2, s2, n2); flush = (f2 != fr); }
+      bool flush = (i + 1 == iters);
+      if (!flush) { int f2, s2, n2; tile_info(tile_of(i + 1), f2, s2, n2); flush = (f2 != fr); }
       if (flush) {
 #pragma unroll
-        for (int mt = 0; mt < NCHUNK_FINAL_MT; ++mt) {
+        for (int mt = 0; mt < NMT; ++mt) {
           const int ch = mt * 128 + row;
           const float v = fmaxf(run_max[mt] + fbias[ch], 0.0f);
           atomicMax(reinterpret_cast<int*>(args.out + (size_t)fr * S::FC + ch), __float_as_int(v));
@@ -364,18 +406,16 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ================================================================ front warps: load points, layer 1 on CUDA cores
-    const int p = threadIdx.x - 256;               // 0..127
-    const float* W1 = reinterpret_cast<const float*>(smem + L::W1);
-    const float* B1 = reinterpret_cast<const float*>(smem + L::B1);
+    const int p = threadIdx.x - 384;               // 0..127
+    const uint32_t W1 = sbase + L::W1, B1 = sbase + L::B1;      // fp32 layer-1 weights / bias in smem (byte addresses)
     const uint32_t o_buf = sbase + L::buf_off(S::ACT_BUF(0));
-    uint32_t tile_iter = 0;
-    Tracer tr; tr.init((warp == 8 && lane == 0) ? args.trace : nullptr, 3);
-    for (int t = tile_begin; t < tile_end; ++t, ++tile_iter) {
+    Tracer tr; tr.init((warp == 12 && lane == 0) ? args.trace : nullptr, 3);
+    for (int i = 0; i < iters; ++i) {
       int fr, start, npts;
-      tile_info(t, fr, start, npts);
-      if (tile_iter > 0) mbar_wait(front_free, (tile_iter - 1) & 1);
+      tile_info(tile_of(i), fr, start, npts);
+      if (i > 0) mbar_wait(front_free, (i - 1) & 1);
       tr.mark(0x10);
       float cx = 0.f, cy = 0.f, cz = 0.f;
       if (args.center) { cx = args.center[fr * 3 + 0]; cy = args.center[fr * 3 + 1]; cz = args.center[fr * 3 + 2]; }
@@ -406,22 +446,24 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
 #pragma unroll 1
         for (int c0 = 0; c0 < S::C1; c0 += 8) {
           float a[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) a[e] = B1[c0 + e];
+          {
+            const float4 b0 = ld_shared_f4(B1 + 4u * c0), b1 = ld_shared_f4(B1 + 4u * (c0 + 4));
+            a[0] = b0.x; a[1] = b0.y; a[2] = b0.z; a[3] = b0.w; a[4] = b1.x; a[5] = b1.y; a[6] = b1.z; a[7] = b1.w;
+          }
 #pragma unroll
           for (int k = 0; k < S::CIN; ++k) {
-            const float4 w0 = *reinterpret_cast<const float4*>(W1 + k * S::C1 + c0);
-            const float4 w1 = *reinterpret_cast<const float4*>(W1 + k * S::C1 + c0 + 4);
+            const float4 w0 = ld_shared_f4(W1 + 4u * (k * S::C1 + c0));
+            const float4 w1 = ld_shared_f4(W1 + 4u * (k * S::C1 + c0 + 4));
             a[0] = fmaf(x[k], w0.x, a[0]); a[1] = fmaf(x[k], w0.y, a[1]); a[2] = fmaf(x[k], w0.z, a[2]); a[3] = fmaf(x[k], w0.w, a[3]);
             a[4] = fmaf(x[k], w1.x, a[4]); a[5] = fmaf(x[k], w1.y, a[5]); a[6] = fmaf(x[k], w1.z, a[6]); a[7] = fmaf(x[k], w1.w, a[7]);
           }
           st_shared_v4(o_buf + (c0 >> 6) * (TILE * 128) + sw128_offset(grow, (c0 & 63) >> 3),
                        pack_bf16_relu(a[0], a[1]), pack_bf16_relu(a[2], a[3]), pack_bf16_relu(a[4], a[5]), pack_bf16_relu(a[6], a[7]));
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(act_ready(0, sub));
       }
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(act_ready(0));
       tr.mark(0x11);
     }
   }
@@ -429,6 +471,7 @@ __global__ void __launch_bounds__(384, 1) chain_max_kernel(const ChainArgs args)
   // ------------------------------------------------------------------ teardown
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();              // no CTA exits while its peer may still multicast into it
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 

@@ -216,12 +216,13 @@ static int chain_launch(const ChainArgs& a, int out_elems, cudaStream_t st) {
     T3D_CUDA(cudaFuncSetAttribute(chain_max_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL + 1024));
   }
   T3D_CUDA(cudaMemsetAsync(a.out, 0, sizeof(float) * (size_t)out_elems, st));
-  int grid = sms;
+  int grid = sms - (sms % kClusterSize);
   if (!a.tiles) {
     const int nt = a.B * ((a.N + L::TILE - 1) / L::TILE);
-    if (nt < grid) grid = nt;
+    const int need = ((nt + kClusterSize - 1) / kClusterSize) * kClusterSize;
+    if (need < grid) grid = need;
   }
-  chain_max_kernel<KIND><<<grid, 384, L::TOTAL + 1024, st>>>(a);
+  chain_max_kernel<KIND><<<grid, kChainThreads, L::TOTAL + 1024, st>>>(a);
   T3D_CHECK_LAUNCH();
   return 0;
 }
@@ -311,12 +312,13 @@ extern "C" int t3d_pack_seg2(const float* W6p, const float* W7, const float* W8,
   PackTable tab;
   int n = 0;
   auto c6 = [&](int nb) { tab.d[n++] = PackDesc{W6p, 512, 64, 0, nb * 128, 128}; };
-  auto c7 = [&](int nb) {
-    for (int nh = 0; nh < 2; ++nh)
-      for (int kb = 0; kb < 2; ++kb) tab.d[n++] = PackDesc{W7, 256, 512, nb * 128 + kb * 64, nh * 128, 128};
+  auto c7 = [&](int nb) {      // per K-block: rows 0-127 then rows 128-255 (one N=256 operand over two ring stages)
+    for (int kb = 0; kb < 2; ++kb)
+      for (int nh = 0; nh < 2; ++nh) tab.d[n++] = PackDesc{W7, 256, 512, nb * 128 + kb * 64, nh * 128, 128};
   };
-  // consumption order of seg_stage2_kernel: j6(0) j6(1) j7(0) j6(2) j7(1) j6(3) j7(2) j7(3) conv8 conv9
-  c6(0); c6(1); c7(0); c6(2); c7(1); c6(3); c7(2); c7(3);
+  // consumption order of seg_stage2_kernel: j6(0) j6(1) j7(0) j6(2) j6(3) j7(1) j7(2) j7(3) conv8 conv9
+  // (every conv7 chunk pair starts at an even position of the chunk stream = even ring stage)
+  c6(0); c6(1); c7(0); c6(2); c6(3); c7(1); c7(2); c7(3);
   for (int kb = 0; kb < 4; ++kb) tab.d[n++] = PackDesc{W8, 128, 256, kb * 64, 0, 128};
   for (int kb = 0; kb < 2; ++kb) tab.d[n++] = PackDesc{W9, 128, 128, kb * 64, 0, 128};
   if (n != kSeg2Chunks) return T3D_ERR_SHAPE;
@@ -347,8 +349,10 @@ extern "C" int t3d_seg_stage2_bf16(const void* point_feat, const float* gbias, c
   }
   Seg2Args a{reinterpret_cast<const __nv_bfloat16*>(point_feat), gbias, reinterpret_cast<const uint8_t*>(arena), logits, B, N, g_trace};
   const int nt = B * ((N + 127) / 128);
-  const int grid = nt < sms ? nt : sms;
-  seg_stage2_kernel<<<grid, 384, Seg2Smem::TOTAL + 1024, S(stream)>>>(a);
+  int grid = sms - (sms % kClusterSize);
+  const int need = ((nt + kClusterSize - 1) / kClusterSize) * kClusterSize;
+  if (need < grid) grid = need;
+  seg_stage2_kernel<<<grid, kSeg2Threads, Seg2Smem::TOTAL + 1024, S(stream)>>>(a);
   T3D_CHECK_LAUNCH();
   return 0;
 }

@@ -86,7 +86,8 @@ def v1_inst_seg(point_cloud, img_feats, one_hot_vec, end_points, is_training, bn
                 raise ValueError('the tcgen05 inst_seg kernel is built for 6-channel frustums (got %d)' % D)
             arena1 = st.chain_arena(full, rt.CHAIN_SEG1, ['conv1', 'conv2', 'conv3', 'conv4', 'conv5'])
             arena2 = st.seg2_arena(full)
-            point_feat = torch.empty((B * N, 64), dtype=torch.bfloat16, device=pc.device)
+            # stage 1 emits conv3's output as the swizzled operand images of stage 2 (one [256 x 64] image per tile)
+            point_feat = torch.empty((B * ((N + 255) // 256) * 256, 64), dtype=torch.bfloat16, device=pc.device)
             gfeat = rt.chain_max(rt.CHAIN_SEG1, pc, arena1, emit=point_feat)                 # (B,1024)
             g = _cat([gfeat, one_hot_vec])
             gbias, _ = rt.linear(g, w6[64:].contiguous(), b6)                               # conv6 global half
