@@ -131,6 +131,37 @@ int t3d_pack_seg2(const float* W6p /* [64,512] */, const float* W7 /* [512,256] 
 int t3d_seg_stage2_bf16(const void* point_feat /* bf16 [B*N,64] */, const float* gbias, const void* arena,
                         float* logits, int B, int N, t3d_stream_t stream);
 
+/* ---- training-step kernels (fp32, CUDA cores) ---------------------------------------------------------
+ * The TF ops behind train_boxpc.train (train_boxpc.py:219-300) and the trainable part of train_semisup_adv.train:
+ * conv2d / fully_connected forward, dgrad and wgrad as one strided GEMM, training-mode batch norm
+ * (tf.contrib.layers.batch_norm, tf_util.py:1645-1664) fused with ReLU, max_pool2d with its gradient, dropout
+ * (tf_util.py:1720-1741), the BoxPC loss (boxpc_sunrgbd.py:106-193) and tf.train.AdamOptimizer. */
+/* C[M,N] (+)= sum_k A(m,k) B(k,n), element strides (sam,sak) / (sbk,sbn) with one of each pair == 1;
+ * splitk > 1 accumulates partial sums atomically (C is zeroed by the call). */
+int t3d_gemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
+                 int ldc, int M, int N, int K, int splitk, const float* bias, t3d_stream_t stream);
+/* mode 0: o0 = sum_r x, o1 = sum_r x^2; mode 1: o0 = sum_r dy, o1 = sum_r dy*xhat with dy = X*(out>0), xhat=(y-mean)*rstd */
+int t3d_colstats(const float* X, const float* out, const float* y, const float* mean, const float* rstd, float* o0,
+                 float* o1, int M, int C, int mode, t3d_stream_t stream);
+int t3d_bn_finalize(const float* sum, const float* sumsq, int M, int C, float eps, float decay, float* mean, float* rstd,
+                    float* moving_mean, float* moving_var, t3d_stream_t stream);
+int t3d_bn_apply(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta, float* out,
+                 int M, int C, int act, t3d_stream_t stream);
+int t3d_bn_backward(float* dOut, const float* out, const float* y, const float* mean, const float* rstd, const float* gamma,
+                    const float* s1, const float* s2, int M, int C, t3d_stream_t stream);
+int t3d_maxpool_fwd(const float* x, int B, int N, int C, float* out, int* arg, t3d_stream_t stream);
+int t3d_maxpool_bwd(const float* dout, const int* arg, int B, int N, int C, float* dx, t3d_stream_t stream);
+int t3d_scale_mask(const float* x, const float* mask, float scale, float* out, long long n, t3d_stream_t stream);
+typedef struct {
+  const float *out9, *y_iou, *y_dc, *y_ds, *y_da;
+  int B; float fit_bound, w_cls, w_delta, wc, ws, wa; int huber;
+  float *cls_losses, *delta_losses, *total, *grad;
+} t3d_boxpc_loss_args;
+int t3d_boxpc_loss(const t3d_boxpc_loss_args* args /* host */, t3d_stream_t stream);
+/* theta -= lr_t * m / (sqrt(v) + eps), lr_t = lr*sqrt(1-b2^t)/(1-b1^t) supplied by the host (TF Adam) */
+int t3d_adam(float* param, const float* grad, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
+             float eps, float grad_scale, t3d_stream_t stream);
+
 /* Debug hook (not part of the reference-facing surface): install a device buffer of
  * 4 * 8192 uint64 into which CTA 0 of the tcgen05 kernels records (clock64 << 8 | tag) per role
  * (0 weight producer, 1 MMA issuer, 2 epilogue warp, 3 front warp); NULL switches tracing off. */

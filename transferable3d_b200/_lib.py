@@ -32,6 +32,16 @@ class t3d_refine_args(_c.Structure):
                 ('tot_center', _P), ('tot_size', _P), ('tot_angle', _P)]
 
 
+class t3d_boxpc_loss_args(_c.Structure):
+    _fields_ = [('out9', _P), ('y_iou', _P), ('y_dc', _P), ('y_ds', _P), ('y_da', _P),
+                ('B', _I), ('fit_bound', _c.c_float), ('w_cls', _c.c_float), ('w_delta', _c.c_float),
+                ('wc', _c.c_float), ('ws', _c.c_float), ('wa', _c.c_float), ('huber', _I),
+                ('cls_losses', _P), ('delta_losses', _P), ('total', _P), ('grad', _P)]
+
+
+_L = _c.c_longlong
+_F = _c.c_float
+
 # name -> (restype, argtypes); every symbol declared in include/t3d_b200.h
 SIGNATURES = {
     't3d_version': (_I, []),
@@ -58,6 +68,16 @@ SIGNATURES = {
     't3d_pack_seg2': (_I, [_P] * 10 + [_P]),
     't3d_seg_stage2_bf16': (_I, [_P, _P, _P, _P, _I, _I, _P]),
     't3d_set_trace_buffer': (_I, [_P]),
+    't3d_gemm_f32': (_I, [_P, _L, _L, _P, _L, _L, _P, _I, _I, _I, _I, _I, _P, _P]),
+    't3d_colstats': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    't3d_bn_finalize': (_I, [_P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P]),
+    't3d_bn_apply': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    't3d_bn_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    't3d_maxpool_fwd': (_I, [_P, _I, _I, _I, _P, _P, _P]),
+    't3d_maxpool_bwd': (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    't3d_scale_mask': (_I, [_P, _P, _F, _P, _L, _P]),
+    't3d_boxpc_loss': (_I, [_c.POINTER(t3d_boxpc_loss_args), _P]),
+    't3d_adam': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _P]),
 }
 
 _lib = None

@@ -4,6 +4,7 @@
 #include "simt_ops.cuh"
 #include "chain_max.cuh"
 #include "seg_stage2.cuh"
+#include "train_ops.cuh"
 
 using namespace t3d;
 
@@ -353,6 +354,102 @@ extern "C" int t3d_seg_stage2_bf16(const void* point_feat, const float* gbias, c
   const int need = ((nt + kClusterSize - 1) / kClusterSize) * kClusterSize;
   if (need < grid) grid = need;
   seg_stage2_kernel<<<grid, kSeg2Threads, Seg2Smem::TOTAL + 1024, S(stream)>>>(a);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- training-step kernels
+extern "C" int t3d_gemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
+                            int ldc, int M, int N, int K, int splitk, const float* bias, t3d_stream_t stream) {
+  if (!A || !B || !C) return T3D_ERR_ARG;
+  if (M <= 0 || N <= 0 || K <= 0 || splitk <= 0 || ldc < N) return T3D_ERR_SHAPE;
+  if ((sam != 1 && sak != 1) || (sbk != 1 && sbn != 1)) return T3D_ERR_SHAPE;
+  if (splitk > 1) T3D_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, S(stream)));
+  GemmArgs a{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias};
+  dim3 grid((M + 63) / 64, (N + 63) / 64, splitk);
+  gemm_f32_kernel<<<grid, 256, 0, S(stream)>>>(a);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_colstats(const float* X, const float* out, const float* y, const float* mean, const float* rstd, float* o0,
+                            float* o1, int M, int C, int mode, t3d_stream_t stream) {
+  if (!X || !o0 || !o1 || (mode == 1 && (!y || !mean || !rstd))) return T3D_ERR_ARG;
+  if (M <= 0 || C <= 0 || (mode != 0 && mode != 1)) return T3D_ERR_SHAPE;
+  T3D_CUDA(cudaMemsetAsync(o0, 0, sizeof(float) * C, S(stream)));
+  T3D_CUDA(cudaMemsetAsync(o1, 0, sizeof(float) * C, S(stream)));
+  ColStatArgs a{X, out, y, mean, rstd, o0, o1, M, C, mode};
+  int chunks = (M + 511) / 512;
+  if (chunks > 1024) chunks = 1024;
+  dim3 grid((C + 31) / 32, chunks);
+  colstats_kernel<<<grid, 256, 0, S(stream)>>>(a);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_bn_finalize(const float* sum, const float* sumsq, int M, int C, float eps, float decay, float* mean,
+                               float* rstd, float* moving_mean, float* moving_var, t3d_stream_t stream) {
+  if (!sum || !sumsq || !mean || !rstd || ((moving_mean != nullptr) != (moving_var != nullptr))) return T3D_ERR_ARG;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, S(stream)>>>(sum, sumsq, M, C, eps, decay, mean, rstd, moving_mean, moving_var);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_bn_apply(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                            float* out, int M, int C, int act, t3d_stream_t stream) {
+  if (!y || !mean || !rstd || !gamma || !beta || !out) return T3D_ERR_ARG;
+  const size_t total = (size_t)M * C;
+  bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(y, mean, rstd, gamma, beta, out, total, C, act);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_bn_backward(float* dOut, const float* out, const float* y, const float* mean, const float* rstd,
+                               const float* gamma, const float* s1, const float* s2, int M, int C, t3d_stream_t stream) {
+  if (!dOut || !y || !mean || !rstd || !gamma || !s1 || !s2) return T3D_ERR_ARG;
+  const size_t total = (size_t)M * C;
+  bn_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(dOut, out, y, mean, rstd, gamma, s1, s2, total, C, M);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_maxpool_fwd(const float* x, int B, int N, int C, float* out, int* arg, t3d_stream_t stream) {
+  if (!x || !out || !arg) return T3D_ERR_ARG;
+  maxpool_fwd_kernel<<<(B * C + 255) / 256, 256, 0, S(stream)>>>(x, B, N, C, out, arg);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_maxpool_bwd(const float* dout, const int* arg, int B, int N, int C, float* dx, t3d_stream_t stream) {
+  if (!dout || !arg || !dx) return T3D_ERR_ARG;
+  T3D_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * N * C, S(stream)));
+  maxpool_bwd_kernel<<<(B * C + 255) / 256, 256, 0, S(stream)>>>(dout, arg, B, N, C, dx);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_scale_mask(const float* x, const float* mask, float scale, float* out, long long n, t3d_stream_t stream) {
+  if (!x || !mask || !out || n <= 0) return T3D_ERR_ARG;
+  scale_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(x, mask, scale, out, (size_t)n);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_boxpc_loss(const t3d_boxpc_loss_args* p, t3d_stream_t stream) {
+  if (!p || !p->out9 || !p->y_iou || !p->y_dc || !p->y_ds || !p->y_da || !p->total) return T3D_ERR_ARG;
+  if (p->B <= 0) return T3D_ERR_SHAPE;
+  T3D_CUDA(cudaMemsetAsync(p->total, 0, sizeof(float), S(stream)));
+  BoxpcLossArgs a{p->out9, p->y_iou, p->y_dc, p->y_ds, p->y_da, p->B, p->fit_bound, p->w_cls, p->w_delta, p->wc, p->ws, p->wa,
+                  p->huber, p->cls_losses, p->delta_losses, p->total, p->grad};
+  boxpc_loss_kernel<<<(p->B + 127) / 128, 128, 0, S(stream)>>>(a);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_adam(float* param, const float* grad, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
+                        float eps, float grad_scale, t3d_stream_t stream) {
+  if (!param || !grad || !m || !v || n <= 0) return T3D_ERR_ARG;
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(param, grad, m, v, (size_t)n, lr_t, beta1, beta2, eps, grad_scale);
   T3D_CHECK_LAUNCH();
   return 0;
 }

@@ -1,0 +1,258 @@
+// fp32 CUDA-core kernels of the training step (BoxPC-Fit training, train_boxpc.py:219-300, and the building
+// blocks of the semi-supervised step): general strided GEMM with split-K (forward / dgrad / wgrad of
+// tf_util.conv2d / fully_connected), training-mode batch norm (tf.contrib.layers.batch_norm, tf_util.py:1645-1664)
+// forward + backward fused with ReLU, max-pool over points with argmax + scatter backward, dropout, the
+// BoxPC loss (boxpc_sunrgbd.py:106-193) forward + backward, and TF-style Adam on a flat arena.
+#pragma once
+#include "common.cuh"
+
+namespace t3d {
+
+// ----------------------------------------------------------------------------- general GEMM
+// C[M,N] (+)= sum_k A(m,k) * B(k,n) with arbitrary element strides; split-K partials are atomically added
+// into a zero-initialised C.  Either stride of A (and of B) must be 1.
+struct GemmArgs {
+  const float* A; long long sam, sak;
+  const float* B; long long sbk, sbn;
+  float* C; int ldc;
+  int M, N, K, splitk;
+  const float* bias;        // [N], added by split 0 (may be null)
+};
+
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs a) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kchunk = ((a.K + a.splitk - 1) / a.splitk + BK - 1) / BK * BK;
+  const int kbeg = blockIdx.z * kchunk, kend = min(a.K, kbeg + kchunk);
+  float acc[4][4] = {};
+  const bool a_kmajor = (a.sak == 1), b_nmajor = (a.sbn == 1);
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    if (a_kmajor) {
+      const int r = tid >> 2, kk = (tid & 3) * 4, gm = m0 + r;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gk = k0 + kk + e;
+        As[kk + e][r] = (gm < a.M && gk < kend) ? a.A[(long long)gm * a.sam + gk] : 0.0f;
+      }
+    } else {
+      const int kk = tid >> 4, r = (tid & 15) * 4, gk = k0 + kk;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gm = m0 + r + e;
+        As[kk][r + e] = (gm < a.M && gk < kend) ? a.A[(long long)gk * a.sak + gm] : 0.0f;
+      }
+    }
+    if (b_nmajor) {
+      const int kk = tid >> 4, nn = (tid & 15) * 4, gk = k0 + kk;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gn = n0 + nn + e;
+        Bs[kk][nn + e] = (gk < kend && gn < a.N) ? a.B[(long long)gk * a.sbk + gn] : 0.0f;
+      }
+    } else {
+      const int nn = tid >> 2, kk = (tid & 3) * 4, gn = n0 + nn;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int gk = k0 + kk + e;
+        Bs[kk + e][nn] = (gk < kend && gn < a.N) ? a.B[(long long)gn * a.sbn + gk] : 0.0f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= a.N) continue;
+      float v = acc[i][j];
+      if (a.bias && blockIdx.z == 0) v += a.bias[gn];
+      if (a.splitk > 1) atomicAdd(a.C + (size_t)gm * a.ldc + gn, v);
+      else a.C[(size_t)gm * a.ldc + gn] = v;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- column statistics
+// out0[c] += sum_r f0, out1[c] += sum_r f1 over the rows of X[M,C] (zero-initialised outputs, atomics).
+//  mode 0: f0 = x,            f1 = x*x                      (BN forward: mean / variance)
+//  mode 1: f0 = dy,           f1 = dy * xhat                 (BN backward; dy = dOut * (out > 0) if out != null)
+//          xhat = (y - mean[c]) * rstd[c]
+struct ColStatArgs {
+  const float* X;           // mode 0: x ; mode 1: dOut
+  const float* out;         // mode 1: post-activation output (ReLU mask) or null
+  const float* y;           // mode 1: pre-BN values
+  const float* mean; const float* rstd;
+  float* o0; float* o1;
+  int M, C, mode;
+};
+__global__ void __launch_bounds__(256) colstats_kernel(const ColStatArgs a) {
+  // block: 32 columns x 8 row-lanes; grid.x over column groups, grid.y over row chunks
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  const int rows_per_block = (a.M + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(a.M, r0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < a.C) {
+    const float mu = a.mode == 1 ? a.mean[c] : 0.f, rs = a.mode == 1 ? a.rstd[c] : 0.f;
+    for (int r = r0 + rl; r < r1; r += 8) {
+      const size_t i = (size_t)r * a.C + c;
+      if (a.mode == 0) { const float x = a.X[i]; s0 += x; s1 = fmaf(x, x, s1); }
+      else {
+        float dy = a.X[i];
+        if (a.out && !(a.out[i] > 0.0f)) dy = 0.0f;
+        s0 += dy; s1 = fmaf(dy, (a.y[i] - mu) * rs, s1);
+      }
+    }
+  }
+  __shared__ float sh0[8][32], sh1[8][32];
+  sh0[rl][threadIdx.x & 31] = s0; sh1[rl][threadIdx.x & 31] = s1;
+  __syncthreads();
+  if (rl == 0 && c < a.C) {
+    for (int k = 1; k < 8; ++k) { s0 += sh0[k][threadIdx.x]; s1 += sh1[k][threadIdx.x]; }
+    atomicAdd(a.o0 + c, s0); atomicAdd(a.o1 + c, s1);
+  }
+}
+
+// finalize BN statistics: mean, biased var -> rstd; moving <- decay*moving + (1-decay)*batch (unbiased var into
+// the moving variance, TF1 fused-BN behaviour)
+__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, int M, int C, float eps, float decay,
+                                   float* mean, float* rstd, float* moving_mean, float* moving_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float mu = sum[c] / (float)M;
+  const float var = fmaxf(sumsq[c] / (float)M - mu * mu, 0.0f);
+  mean[c] = mu; rstd[c] = rsqrtf(var + eps);
+  if (moving_mean) {
+    moving_mean[c] = decay * moving_mean[c] + (1.0f - decay) * mu;
+    const float unb = var * ((float)M / (float)max(M - 1, 1));
+    moving_var[c] = decay * moving_var[c] + (1.0f - decay) * unb;
+  }
+}
+
+// out = act(gamma * (y - mean) * rstd + beta) ; act: 0 none, 1 relu
+__global__ void bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
+                                size_t total, int C, int act) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  float v = gamma[c] * (y[i] - mean[c]) * rstd[c] + beta[c];
+  if (act == 1) v = fmaxf(v, 0.0f);
+  out[i] = v;
+}
+
+// dY = gamma*rstd * (dy - s1/M - xhat*s2/M), dy = dOut*(out>0) ; written over dOut (in place)
+__global__ void bn_backward_kernel(float* __restrict__ dOut, const float* __restrict__ out, const float* __restrict__ y,
+                                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                   const float* __restrict__ s1, const float* __restrict__ s2, size_t total, int C, int M) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  float dy = dOut[i];
+  if (out && !(out[i] > 0.0f)) dy = 0.0f;
+  const float xh = (y[i] - mean[c]) * rstd[c];
+  const float inv = 1.0f / (float)M;
+  dOut[i] = gamma[c] * rstd[c] * (dy - s1[c] * inv - xh * s2[c] * inv);
+}
+
+// ----------------------------------------------------------------------------- max-pool over points with argmax
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, int B, int N, int C, float* __restrict__ out, int* __restrict__ arg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;        // over B*C
+  if (i >= B * C) return;
+  const int b = i / C, c = i % C;
+  const float* p = x + (size_t)b * N * C + c;
+  float m = p[0]; int am = 0;
+  for (int n = 1; n < N; ++n) { const float v = p[(size_t)n * C]; if (v > m) { m = v; am = n; } }    // first max wins
+  out[i] = m; arg[i] = am;
+}
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ arg, int B, int N, int C, float* __restrict__ dx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i % C;
+  dx[((size_t)b * N + arg[i]) * C + c] = dout[i];             // dx is zero-initialised by the caller
+}
+
+// out = x * mask * scale  (tf.nn.dropout forward and backward with the same keep mask, scale = 1/keep_prob)
+__global__ void scale_mask_kernel(const float* __restrict__ x, const float* __restrict__ mask, float scale, float* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = x[i] * mask[i] * scale;
+}
+
+// ----------------------------------------------------------------------------- BoxPC loss (boxpc_sunrgbd.py:106-193)
+// per sample: cls = softmaxCE(onehot(iou > fit_bound), fit logits); delta = wc*mean3 huber(dc) + ws*mean3 huber(ds) + wa*huber(da)
+// total = mean_B(w_cls*cls + w_delta*delta).  out9 = [dc(3), ds(3), da, l0, l1].  grad (B,9) = d total / d out9.
+struct BoxpcLossArgs {
+  const float* out9; const float* y_iou; const float* y_dc; const float* y_ds; const float* y_da;
+  int B; float fit_bound, w_cls, w_delta, wc, ws, wa; int huber;     // huber=1, else mse
+  float* cls_losses; float* delta_losses; float* total; float* grad;
+};
+__device__ __forceinline__ void huber1(float err, float& loss, float& dloss) {   // tf.losses.huber_loss delta=1 on (pred-label)
+  const float a = fabsf(err), q = fminf(a, 1.0f);
+  loss = 0.5f * q * q + (a - q);
+  dloss = a <= 1.0f ? err : (err > 0.f ? 1.0f : -1.0f);
+}
+__global__ void boxpc_loss_kernel(const BoxpcLossArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  float contrib = 0.f;
+  if (b < a.B) {
+    const float* o = a.out9 + (size_t)b * 9;
+    float g[9];
+    const float l0 = o[7], l1 = o[8], mx = fmaxf(l0, l1);
+    const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), z = e0 + e1;
+    const int lab = a.y_iou[b] > a.fit_bound ? 1 : 0;
+    const float cls = logf(z) + mx - (lab ? l1 : l0);
+    const float inv_b = 1.0f / (float)a.B;
+    g[7] = a.w_cls * inv_b * (e0 / z - (lab == 0 ? 1.f : 0.f));
+    g[8] = a.w_cls * inv_b * (e1 / z - (lab == 1 ? 1.f : 0.f));
+    float lc = 0.f, ls = 0.f, la, d;
+    for (int k = 0; k < 3; ++k) {
+      float l;
+      if (a.huber) huber1(o[k] - a.y_dc[b * 3 + k], l, d); else { const float e = o[k] - a.y_dc[b * 3 + k]; l = e * e; d = 2.f * e; }
+      lc += l; g[k] = a.w_delta * inv_b * a.wc * d / 3.0f;
+      if (a.huber) huber1(o[3 + k] - a.y_ds[b * 3 + k], l, d); else { const float e = o[3 + k] - a.y_ds[b * 3 + k]; l = e * e; d = 2.f * e; }
+      ls += l; g[3 + k] = a.w_delta * inv_b * a.ws * d / 3.0f;
+    }
+    if (a.huber) huber1(o[6] - a.y_da[b], la, d); else { const float e = o[6] - a.y_da[b]; la = e * e; d = 2.f * e; }
+    g[6] = a.w_delta * inv_b * a.wa * d;
+    const float delta = a.wc * lc / 3.0f + a.ws * ls / 3.0f + a.wa * la;
+    if (a.cls_losses) a.cls_losses[b] = cls;
+    if (a.delta_losses) a.delta_losses[b] = delta;
+    if (a.grad) for (int k = 0; k < 9; ++k) a.grad[(size_t)b * 9 + k] = g[k];
+    contrib = (a.w_cls * cls + a.w_delta * delta) * inv_b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(a.total, contrib);          // total is zero-initialised by the caller
+}
+
+// ----------------------------------------------------------------------------- TF Adam
+// lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the host; theta -= lr_t * m / (sqrt(v) + eps)
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            size_t n, float lr_t, float b1, float b2, float eps, float gscale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * gscale;
+  const float mi = b1 * m[i] + (1.0f - b1) * gi;
+  const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+}
+
+}  // namespace t3d

@@ -177,7 +177,8 @@ def mask_centroid(logits, pc, want_mask=True, want_xyz_stage1=False, want_idx=Tr
     mean = torch.empty((B, 3), dtype=torch.float32, device=dev)
     xyz1 = torch.empty((B, N, 3), dtype=torch.float32, device=dev) if want_xyz_stage1 else None
     idx = torch.empty((B, N), dtype=torch.int32, device=dev) if want_idx else None
-    call('t3d_mask_centroid', ptr(f32(logits)), ptr(pc), B, N, C, ptr(mask), ptr(count), ptr(mean), ptr(xyz1), ptr(idx),
+    logits = f32(logits)                                          # keep alive until the launch
+    call('t3d_mask_centroid', ptr(logits), ptr(pc), B, N, C, ptr(mask), ptr(count), ptr(mean), ptr(xyz1), ptr(idx),
          stream())
     return mask, count, mean, xyz1, idx
 

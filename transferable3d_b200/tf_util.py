@@ -87,8 +87,9 @@ def tf_convert_box_params_from_anchor_to_reg_format_multi(box_params, y_classes,
     oc = torch.empty((B, 3), dtype=torch.float32, device=dev)
     od = torch.empty((B, 3), dtype=torch.float32, device=dev)
     oo = torch.empty((B,), dtype=torch.float32, device=dev)
+    da, oa = rt.f32(dims_anchors), rt.f32(orient_anchors)       # keep alive until the launch
     call('t3d_anchor_to_reg', ptr(center), ptr(dims_cls), ptr(dims_reg), ptr(orient_cls), ptr(orient_reg),
-         ptr(rt.f32(dims_anchors)), ptr(rt.f32(orient_anchors)), B, NS, NH, ptr(oc), ptr(od), ptr(oo), stream())
+         ptr(da), ptr(oa), B, NS, NH, ptr(oc), ptr(od), ptr(oo), stream())
     return oc, od, oo
 
 
