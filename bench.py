@@ -7,8 +7,9 @@
 
 Workload (config.workload): BASELINE.json cfg3 = full Frustum PointNet v1 pipeline inference
 (seg -> mask / centroid / resample 512 -> T-Net -> box-est NH=12 NS=10), 8192 frustums of
-2048 pts x 6 ch + 10-class one-hot, sharded contiguously over the N GPUs with no collective
-(strong scaling).  `--workload cfg2` times the instance-seg chain alone at batch 1024 per GPU.
+2048 pts x 6 ch + 10-class one-hot.  Frustums are independent, so the GPUs shard them with no data-path
+collective; `--scaling weak` (default) gives every GPU the full batch of 8192, `--scaling strong` splits
+one global batch of 8192 contiguously.  `--workload cfg2` times the instance-seg chain alone at batch 1024 per GPU.
 A step = one pass of the pipeline over the rank's shard, processed in chunks of --chunk frustums.
 `value`: inputs already resident in HBM.  `e2e`: the same pass through the public API
 (frustum_pointnets_v1.get_model) from pinned HOST buffers, H2D of every chunk's inputs and D2H of
@@ -47,14 +48,30 @@ def peaks():
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock / power / clock-event reasons sampled DURING the timed region: NVML polled every 5 ms from a
+    thread of this process (a timed region of a few steps lasts tens of ms, too short for `nvidia-smi -lms 200`);
+    falls back to the profiling recipe's nvidia-smi loop if NVML is unavailable."""
     Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.samples, self._stop = None, [], threading.Event()
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(',')) else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '200'],
@@ -64,11 +81,33 @@ class ClockSampler(object):
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append((float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)),
+                                     int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h)),
+                                     n.nvmlDeviceGetPowerUsage(self.h) / 1000.0))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=1)
+            n = self.nvml
+            names = (('hw_slowdown', n.nvmlClocksEventReasonHwSlowdown), ('hw_thermal_slowdown', n.nvmlClocksEventReasonHwThermalSlowdown),
+                     ('sw_thermal_slowdown', n.nvmlClocksEventReasonSwThermalSlowdown), ('sw_power_cap', n.nvmlClocksEventReasonSwPowerCap))
+            reasons = sorted({nm for _, r, _ in self.samples for nm, bit in names if r & bit})
+            sm = [x[0] for x in self.samples]
+            pw = [x[2] for x in self.samples]
+            return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.sm_max, 'reasons': reasons,
+                    'samples': len(sm), 'power_w_max': max(pw) if pw else None, 'source': 'nvml, 5 ms poll during the timed region'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -90,7 +129,7 @@ class ClockSampler(object):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi -lms 200'}
 
 
 def make_host_data(workload, n_local, seed):
@@ -147,7 +186,7 @@ def run_reference(args):
     value = sample / dt
     line = {'impl': 'reference', 'metric': 'frustums_per_sec', 'value': value, 'unit': 'frustums/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
-            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'scaling': args.scaling if workload == 'cfg3' else 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': workload_config(workload, args, sample_note='reference arm: %d frustums per step' % sample),
             'cpu_baseline': {'value': value, 'unit': 'frustums/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                              'sample': '%d frustums per step, oracle restatement of the TF1 graph on PyTorch-CPU' % sample},
@@ -183,9 +222,11 @@ def oracle_cfg3(vs, pc_t, oh_t, seed=5):
 
 def workload_config(workload, args, sample_note=None):
     c = {'workload': ('cfg3: Frustum PointNet v1 pipeline inference (seg -> mask/centroid/resample 512 -> T-Net -> '
-                      'box-est NH=12 NS=10), 8192 frustums x 2048 pts x 6 ch + one-hot, sharded over the GPUs')
+                      'box-est NH=12 NS=10), 8192 frustums x 2048 pts x 6 ch + one-hot %s, frustums sharded over the GPUs, '
+                      'no collective' % ('per GPU' if args.scaling == 'weak' else 'in total'))
          if workload == 'cfg3' else 'cfg2: instance-seg per-point MLP chain alone, 1024 frustums x 2048 pts x 6 ch per GPU',
-         'global_frustums': TOTAL_FRUSTUMS[workload] * (args.gpus if workload == 'cfg2' else 1),
+         'global_frustums': TOTAL_FRUSTUMS[workload] * (1 if (workload == 'cfg3' and args.scaling == 'strong') else args.gpus),
+         'frustums_per_gpu': TOTAL_FRUSTUMS[workload] // (args.gpus if (workload == 'cfg3' and args.scaling == 'strong') else 1),
          'num_point': N_POINTS, 'num_channel': N_CH, 'chunk_frustums': args.resident_chunk, 'e2e_chunk_frustums': args.chunk, 'parallelism': 'shard%d' % args.gpus,
          'precision': 'bf16 operands / fp32 accumulate (tcgen05), fp32 heads',
          'weights': 'synthetic Xavier (seed 42), seg logits calibrated (margin std 2.0, 40% masked-in)',
@@ -206,6 +247,9 @@ def main():
     ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg2'])
     ap.add_argument('--chunk', type=int, default=2048, help='frustums per chunk of the e2e (H2D/compute/D2H) pipeline')
     ap.add_argument('--resident-chunk', type=int, default=8192, help='frustums per pass when inputs are resident in HBM')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: every GPU processes the full cfg3 batch of 8192 frustums (no data-path collective); '
+                         'strong: one global batch of 8192 split over the GPUs')
     ap.add_argument('--ref-sample', type=int, default=8)
     ap.add_argument('--cpu-sample', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -234,7 +278,7 @@ def main():
     assert world == args.gpus, 'launch with torchrun --nproc-per-node %d' % args.gpus
     workload = args.workload
     total = TOTAL_FRUSTUMS[workload]
-    n_local = total // world if workload == 'cfg3' else total
+    n_local = total // world if (workload == 'cfg3' and args.scaling == 'strong') else total
     chunk = min(args.chunk, n_local)
     rchunk = min(args.resident_chunk, n_local)
     assert n_local % chunk == 0 and n_local % rchunk == 0
@@ -427,7 +471,7 @@ def main():
         flops_fr = (FLOP_SEG1_PT + FLOP_SEG2_PT) * N_POINTS + 2 * 1024 * 512
     line = {'metric': 'frustums_per_sec', 'value': value, 'unit': 'frustums/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
-            'scaling': 'strong' if workload == 'cfg3' else 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'scaling': args.scaling if workload == 'cfg3' else 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': workload_config(workload, args), 'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'frustums/s', 'h2d_bytes_per_step': bytes_io['h2d'],
                     'd2h_bytes_per_step': bytes_io['d2h'], 'ms_per_step': ms_e2e},

@@ -140,15 +140,18 @@ int t3d_seg_stage2_bf16(const void* point_feat /* bf16 [B*N,64] */, const float*
  * splitk > 1 accumulates partial sums atomically (C is zeroed by the call). */
 int t3d_gemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
                  int ldc, int M, int N, int K, int splitk, const float* bias, t3d_stream_t stream);
-/* mode 0: o0 = sum_r x, o1 = sum_r x^2; mode 1: o0 = sum_r dy, o1 = sum_r dy*xhat with dy = X*(out>0), xhat=(y-mean)*rstd */
+/* mode 0: o0 = sum_r d, o1 = sum_r d^2 with d = x - y[c] when y != NULL (a per-column shift, e.g. row 0 of X: keeps the
+ * variance E[d^2] - E[d]^2 free of cancellation), else d = x; mode 1: o0 = sum_r dy, o1 = sum_r dy*xhat with dy = X*act'(out), xhat=(y-mean)*rstd
+ * (act = the T3D_ACT_* the forward applied after the batch norm) */
 int t3d_colstats(const float* X, const float* out, const float* y, const float* mean, const float* rstd, float* o0,
-                 float* o1, int M, int C, int mode, t3d_stream_t stream);
-int t3d_bn_finalize(const float* sum, const float* sumsq, int M, int C, float eps, float decay, float* mean, float* rstd,
-                    float* moving_mean, float* moving_var, t3d_stream_t stream);
+                 float* o1, int M, int C, int mode, int act, t3d_stream_t stream);
+/* sum / sumsq as produced by t3d_colstats mode 0 with the same `shift` (NULL: none) */
+int t3d_bn_finalize(const float* sum, const float* sumsq, const float* shift, int M, int C, float eps, float decay, float* mean,
+                    float* rstd, float* moving_mean, float* moving_var, t3d_stream_t stream);
 int t3d_bn_apply(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta, float* out,
                  int M, int C, int act, t3d_stream_t stream);
 int t3d_bn_backward(float* dOut, const float* out, const float* y, const float* mean, const float* rstd, const float* gamma,
-                    const float* s1, const float* s2, int M, int C, t3d_stream_t stream);
+                    const float* s1, const float* s2, int M, int C, int act, t3d_stream_t stream);
 int t3d_maxpool_fwd(const float* x, int B, int N, int C, float* out, int* arg, t3d_stream_t stream);
 int t3d_maxpool_bwd(const float* dout, const int* arg, int B, int N, int C, float* dx, t3d_stream_t stream);
 int t3d_scale_mask(const float* x, const float* mask, float scale, float* out, long long n, t3d_stream_t stream);
@@ -161,6 +164,43 @@ int t3d_boxpc_loss(const t3d_boxpc_loss_args* args /* host */, t3d_stream_t stre
 /* theta -= lr_t * m / (sqrt(v) + eps), lr_t = lr*sqrt(1-b2^t)/(1-b1^t) supplied by the host (TF Adam) */
 int t3d_adam(float* param, const float* grad, float* m, float* v, long long n, float lr_t, float beta1, float beta2,
              float eps, float grad_scale, t3d_stream_t stream);
+
+/* ---- semi-supervised training step (train_semisup_adv.py:267-425): losses with gradients ---------------------
+ * mean_N softmax cross-entropy of the mask logits per frustum (semisup_v1_sunrgbd.py:430-431) */
+int t3d_seg_ce(const float* logits, const int* labels, int B, int N, float* out, t3d_stream_t stream);
+/* per-class sums / counts of dims_reg over the batch (group means of weak_losses.get_intraclass_variance_loss_v1) */
+int t3d_class_dims_stats(const float* dims_reg, const float* one_hot, int B, int NC, float* cls_sum, float* cls_cnt,
+                         t3d_stream_t stream);
+/* semisup_v1_sunrgbd.get_semi_loss_final (:323-421) = get_strong_loss(prefix F_) (:423-553) + weak_losses.get_reprojection_loss
+ * (weak_losses.py:69-238) + get_intraclass_variance_loss_v1 (:267-291) + the BoxPC fit loss, with d total / d F_output,
+ * d / d stage1_center, d / d F_pred_box_reg (g_reg, the part that flows through the regression-format box) and d / d fit_logits. */
+typedef struct {
+  const float *out, *stage1_center, *mask_losses, *one_hot;
+  const float* y_center; const int* y_orient_cls; const float* y_orient_reg; const int* y_dims_cls; const float* y_dims_reg;
+  const float *Rtilt, *K, *rot_frust, *box2D, *img_dim;
+  const int* is_data_2D;
+  const float *fit_logits, *mean_size, *cls_sum, *cls_cnt;
+  int B, NH, NS, NC;
+  unsigned icv_train_mask;
+  float w_ce, box_mult, w_center, w_ocls, w_dcls, w_oreg, w_dreg, w_tnet, w_corner;
+  float weak_mult, w_icv, w_reproj, w_fit;
+  int reproj_only_2d, fit_only_2d, use_softmax_proj;
+  float softmax_scale, dilate;
+  int clip_lower_b, clip_pred_box, reproj_mse, icv_mse, train_box_mask;
+  float inv_n3d;
+  float *dF, *ds1, *g_reg, *dfit, *per_sample, *total;
+} t3d_semi_loss_args;
+int t3d_semi_loss(const t3d_semi_loss_args* args /* host */, t3d_stream_t stream);
+/* dF += chain of g_reg [B,7] through tf_convert_box_params_from_anchor_to_reg_format (tf_util.py:1001-1041); ds1 += g_reg[:,0:3] */
+int t3d_box_reg_backward(const float* out, const float* g_reg, const float* mean_size, int B, int NH, int NS, float* dF,
+                         float* ds1, t3d_stream_t stream);
+/* backward of tf_get_box_pc_representation (tf_util.py:764-795) w.r.t. the box: g6 [B*N,6] -> g_box [B,7] (+=) */
+int t3d_boxpc_features_bwd(const float* pc, int B, int N, int C, const float* center, const float* orient, const float* g6,
+                           float* g_box, t3d_stream_t stream);
+int t3d_act_bwd(float* dout, const float* out, long long n, int act, t3d_stream_t stream);
+int t3d_rowmask_mul(const float* x, const float* rowmask, float* out, long long M, int C, t3d_stream_t stream);
+/* out[b,c] = scale * sum_n x[b,n,c], C <= 8 */
+int t3d_group_sum(const float* x, int B, int N, int C, float scale, float* out, t3d_stream_t stream);
 
 /* Debug hook (not part of the reference-facing surface): install a device buffer of
  * 4 * 8192 uint64 into which CTA 0 of the tcgen05 kernels records (clock64 << 8 | tag) per role

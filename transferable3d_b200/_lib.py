@@ -39,6 +39,20 @@ class t3d_boxpc_loss_args(_c.Structure):
                 ('cls_losses', _P), ('delta_losses', _P), ('total', _P), ('grad', _P)]
 
 
+class t3d_semi_loss_args(_c.Structure):
+    _fields_ = ([(n, _P) for n in ('out', 'stage1_center', 'mask_losses', 'one_hot', 'y_center', 'y_orient_cls', 'y_orient_reg',
+                                   'y_dims_cls', 'y_dims_reg', 'Rtilt', 'K', 'rot_frust', 'box2D', 'img_dim', 'is_data_2D',
+                                   'fit_logits', 'mean_size', 'cls_sum', 'cls_cnt')] +
+                [(n, _I) for n in ('B', 'NH', 'NS', 'NC')] + [('icv_train_mask', _c.c_uint)] +
+                [(n, _c.c_float) for n in ('w_ce', 'box_mult', 'w_center', 'w_ocls', 'w_dcls', 'w_oreg', 'w_dreg', 'w_tnet',
+                                           'w_corner', 'weak_mult', 'w_icv', 'w_reproj', 'w_fit')] +
+                [(n, _I) for n in ('reproj_only_2d', 'fit_only_2d', 'use_softmax_proj')] +
+                [('softmax_scale', _c.c_float), ('dilate', _c.c_float)] +
+                [(n, _I) for n in ('clip_lower_b', 'clip_pred_box', 'reproj_mse', 'icv_mse', 'train_box_mask')] +
+                [('inv_n3d', _c.c_float)] +
+                [(n, _P) for n in ('dF', 'ds1', 'g_reg', 'dfit', 'per_sample', 'total')])
+
+
 _L = _c.c_longlong
 _F = _c.c_float
 
@@ -69,15 +83,23 @@ SIGNATURES = {
     't3d_seg_stage2_bf16': (_I, [_P, _P, _P, _P, _I, _I, _P]),
     't3d_set_trace_buffer': (_I, [_P]),
     't3d_gemm_f32': (_I, [_P, _L, _L, _P, _L, _L, _P, _I, _I, _I, _I, _I, _P, _P]),
-    't3d_colstats': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
-    't3d_bn_finalize': (_I, [_P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P]),
+    't3d_colstats': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    't3d_bn_finalize': (_I, [_P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P]),
     't3d_bn_apply': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
-    't3d_bn_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    't3d_bn_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     't3d_maxpool_fwd': (_I, [_P, _I, _I, _I, _P, _P, _P]),
     't3d_maxpool_bwd': (_I, [_P, _P, _I, _I, _I, _P, _P]),
     't3d_scale_mask': (_I, [_P, _P, _F, _P, _L, _P]),
     't3d_boxpc_loss': (_I, [_c.POINTER(t3d_boxpc_loss_args), _P]),
     't3d_adam': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _P]),
+    't3d_seg_ce': (_I, [_P, _P, _I, _I, _P, _P]),
+    't3d_class_dims_stats': (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    't3d_semi_loss': (_I, [_c.POINTER(t3d_semi_loss_args), _P]),
+    't3d_box_reg_backward': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    't3d_boxpc_features_bwd': (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _P]),
+    't3d_act_bwd': (_I, [_P, _P, _L, _I, _P]),
+    't3d_rowmask_mul': (_I, [_P, _P, _P, _L, _I, _P]),
+    't3d_group_sum': (_I, [_P, _I, _I, _I, _F, _P, _P]),
 }
 
 _lib = None

@@ -32,6 +32,12 @@ _DEFAULTS = dict(
     SEMI_ADV_TANH_FOR_LAST_LAYER_OF_G=True,
     SEMI_ADV_LEAKY_RELU=True,
     SEMI_TRAIN_BOXPC_MODEL=False,
+    SEMI_TRAIN_BOX_TRAIN_CLASS_AG_TNET=False,
+    SEMI_TRAIN_BOX_TRAIN_CLASS_AG_BOX=False,
+    SEMI_INTRACLSDIMS_ONLY_ON_2D_CLS=True,
+    WEAK_INACTIVE_VOL_ONLY_ON_2D_CLS=True,
+    TEST_CLS=['table', 'sofa', 'dresser', 'night_stand', 'bookshelf'],     # SUNRGBD_SEMI_TEST_CLS (config.py:193-194)
+    use_one_hot_boxpc=False,
     SEMI_BOXPC_MIN_FIT_LOSS_AFT_REFINE=False,
     SEMI_BOXPC_FIT_ONLY_ON_2D_CLS=False,
     SEMI_WEIGH_BOXPC_DELTA_DURING_TEST=False,

@@ -5,6 +5,7 @@
 #include "chain_max.cuh"
 #include "seg_stage2.cuh"
 #include "train_ops.cuh"
+#include "loss_ops.cuh"
 
 using namespace t3d;
 
@@ -373,12 +374,12 @@ extern "C" int t3d_gemm_f32(const float* A, long long sam, long long sak, const 
 }
 
 extern "C" int t3d_colstats(const float* X, const float* out, const float* y, const float* mean, const float* rstd, float* o0,
-                            float* o1, int M, int C, int mode, t3d_stream_t stream) {
+                            float* o1, int M, int C, int mode, int act, t3d_stream_t stream) {
   if (!X || !o0 || !o1 || (mode == 1 && (!y || !mean || !rstd))) return T3D_ERR_ARG;
-  if (M <= 0 || C <= 0 || (mode != 0 && mode != 1)) return T3D_ERR_SHAPE;
+  if (M <= 0 || C <= 0 || (mode != 0 && mode != 1) || act < 0 || act > 3) return T3D_ERR_SHAPE;
   T3D_CUDA(cudaMemsetAsync(o0, 0, sizeof(float) * C, S(stream)));
   T3D_CUDA(cudaMemsetAsync(o1, 0, sizeof(float) * C, S(stream)));
-  ColStatArgs a{X, out, y, mean, rstd, o0, o1, M, C, mode};
+  ColStatArgs a{X, out, y, mean, rstd, o0, o1, M, C, mode, act};
   int chunks = (M + 511) / 512;
   if (chunks > 1024) chunks = 1024;
   dim3 grid((C + 31) / 32, chunks);
@@ -387,10 +388,10 @@ extern "C" int t3d_colstats(const float* X, const float* out, const float* y, co
   return 0;
 }
 
-extern "C" int t3d_bn_finalize(const float* sum, const float* sumsq, int M, int C, float eps, float decay, float* mean,
-                               float* rstd, float* moving_mean, float* moving_var, t3d_stream_t stream) {
+extern "C" int t3d_bn_finalize(const float* sum, const float* sumsq, const float* shift, int M, int C, float eps, float decay,
+                               float* mean, float* rstd, float* moving_mean, float* moving_var, t3d_stream_t stream) {
   if (!sum || !sumsq || !mean || !rstd || ((moving_mean != nullptr) != (moving_var != nullptr))) return T3D_ERR_ARG;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, S(stream)>>>(sum, sumsq, M, C, eps, decay, mean, rstd, moving_mean, moving_var);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, S(stream)>>>(sum, sumsq, shift, M, C, eps, decay, mean, rstd, moving_mean, moving_var);
   T3D_CHECK_LAUNCH();
   return 0;
 }
@@ -398,6 +399,7 @@ extern "C" int t3d_bn_finalize(const float* sum, const float* sumsq, int M, int 
 extern "C" int t3d_bn_apply(const float* y, const float* mean, const float* rstd, const float* gamma, const float* beta,
                             float* out, int M, int C, int act, t3d_stream_t stream) {
   if (!y || !mean || !rstd || !gamma || !beta || !out) return T3D_ERR_ARG;
+  if (act < 0 || act > 3) return T3D_ERR_SHAPE;
   const size_t total = (size_t)M * C;
   bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(y, mean, rstd, gamma, beta, out, total, C, act);
   T3D_CHECK_LAUNCH();
@@ -405,10 +407,11 @@ extern "C" int t3d_bn_apply(const float* y, const float* mean, const float* rstd
 }
 
 extern "C" int t3d_bn_backward(float* dOut, const float* out, const float* y, const float* mean, const float* rstd,
-                               const float* gamma, const float* s1, const float* s2, int M, int C, t3d_stream_t stream) {
+                               const float* gamma, const float* s1, const float* s2, int M, int C, int act, t3d_stream_t stream) {
   if (!dOut || !y || !mean || !rstd || !gamma || !s1 || !s2) return T3D_ERR_ARG;
+  if (act < 0 || act > 3) return T3D_ERR_SHAPE;
   const size_t total = (size_t)M * C;
-  bn_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(dOut, out, y, mean, rstd, gamma, s1, s2, total, C, M);
+  bn_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(dOut, out, y, mean, rstd, gamma, s1, s2, total, C, M, act);
   T3D_CHECK_LAUNCH();
   return 0;
 }
@@ -450,6 +453,93 @@ extern "C" int t3d_adam(float* param, const float* grad, float* m, float* v, lon
                         float eps, float grad_scale, t3d_stream_t stream) {
   if (!param || !grad || !m || !v || n <= 0) return T3D_ERR_ARG;
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(param, grad, m, v, (size_t)n, lr_t, beta1, beta2, eps, grad_scale);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- semi-supervised step: losses and helpers
+extern "C" int t3d_seg_ce(const float* logits, const int* labels, int B, int N, float* out, t3d_stream_t stream) {
+  if (!logits || !labels || !out) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0) return T3D_ERR_SHAPE;
+  if ((uintptr_t)logits & 7) return T3D_ERR_ALIGN;
+  seg_ce_kernel<<<B, 256, 0, S(stream)>>>(logits, labels, N, out);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_class_dims_stats(const float* dims_reg, const float* one_hot, int B, int NC, float* cls_sum, float* cls_cnt,
+                                    t3d_stream_t stream) {
+  if (!dims_reg || !one_hot || !cls_sum || !cls_cnt) return T3D_ERR_ARG;
+  if (B <= 0 || NC <= 0 || NC > 32) return T3D_ERR_SHAPE;
+  T3D_CUDA(cudaMemsetAsync(cls_sum, 0, sizeof(float) * 3 * NC, S(stream)));
+  T3D_CUDA(cudaMemsetAsync(cls_cnt, 0, sizeof(float) * NC, S(stream)));
+  class_dims_stats_kernel<<<(B + 127) / 128, 128, 0, S(stream)>>>(dims_reg, one_hot, B, NC, cls_sum, cls_cnt);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_semi_loss(const t3d_semi_loss_args* p, t3d_stream_t stream) {
+  if (!p || !p->out || !p->stage1_center || !p->one_hot || !p->y_center || !p->y_orient_cls || !p->y_orient_reg || !p->y_dims_cls ||
+      !p->y_dims_reg || !p->is_data_2D || !p->mean_size || !p->dF || !p->ds1 || !p->g_reg || !p->total)
+    return T3D_ERR_ARG;
+  if (p->w_reproj != 0.f && (!p->Rtilt || !p->K || !p->rot_frust || !p->box2D || !p->img_dim)) return T3D_ERR_ARG;
+  if (p->B <= 0 || p->NH <= 0 || p->NH > kMaxNH || p->NS <= 0 || p->NS > kMaxNS || p->NC <= 0 || p->NC > 32) return T3D_ERR_SHAPE;
+  T3D_CUDA(cudaMemsetAsync(p->total, 0, sizeof(float) * 8, S(stream)));
+  SemiLossArgs a;
+  a.out = p->out; a.stage1_center = p->stage1_center; a.mask_losses = p->mask_losses; a.one_hot = p->one_hot;
+  a.y_center = p->y_center; a.y_orient_cls = p->y_orient_cls; a.y_orient_reg = p->y_orient_reg; a.y_dims_cls = p->y_dims_cls;
+  a.y_dims_reg = p->y_dims_reg; a.Rtilt = p->Rtilt; a.K = p->K; a.rot_frust = p->rot_frust; a.box2D = p->box2D; a.img_dim = p->img_dim;
+  a.is_data_2D = p->is_data_2D; a.fit_logits = p->fit_logits; a.mean_size = p->mean_size; a.cls_sum = p->cls_sum; a.cls_cnt = p->cls_cnt;
+  a.B = p->B; a.NH = p->NH; a.NS = p->NS; a.NC = p->NC; a.icv_train_mask = p->icv_train_mask;
+  a.w_ce = p->w_ce; a.box_mult = p->box_mult; a.w_center = p->w_center; a.w_ocls = p->w_ocls; a.w_dcls = p->w_dcls; a.w_oreg = p->w_oreg;
+  a.w_dreg = p->w_dreg; a.w_tnet = p->w_tnet; a.w_corner = p->w_corner; a.weak_mult = p->weak_mult; a.w_icv = p->w_icv;
+  a.w_reproj = p->w_reproj; a.w_fit = p->w_fit; a.reproj_only_2d = p->reproj_only_2d; a.fit_only_2d = p->fit_only_2d;
+  a.use_softmax_proj = p->use_softmax_proj; a.softmax_scale = p->softmax_scale; a.dilate = p->dilate; a.clip_lower_b = p->clip_lower_b;
+  a.clip_pred_box = p->clip_pred_box; a.reproj_mse = p->reproj_mse; a.icv_mse = p->icv_mse; a.train_box_mask = p->train_box_mask;
+  a.inv_n3d = p->inv_n3d; a.dF = p->dF; a.ds1 = p->ds1; a.g_reg = p->g_reg; a.dfit = p->dfit; a.per_sample = p->per_sample; a.total = p->total;
+  semi_loss_kernel<<<(p->B + 63) / 64, 64, 0, S(stream)>>>(a);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_box_reg_backward(const float* out, const float* g_reg, const float* mean_size, int B, int NH, int NS, float* dF,
+                                    float* ds1, t3d_stream_t stream) {
+  if (!out || !g_reg || !mean_size || !dF) return T3D_ERR_ARG;
+  if (B <= 0 || NH <= 0 || NS <= 0) return T3D_ERR_SHAPE;
+  box_reg_backward_kernel<<<(B + 127) / 128, 128, 0, S(stream)>>>(out, g_reg, mean_size, B, NH, NS, dF, ds1);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_boxpc_features_bwd(const float* pc, int B, int N, int C, const float* center, const float* orient, const float* g6,
+                                      float* g_box, t3d_stream_t stream) {
+  if (!pc || !center || !orient || !g6 || !g_box) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0 || C < 3) return T3D_ERR_SHAPE;
+  boxpc_features_bwd_kernel<<<B, 256, 0, S(stream)>>>(pc, N, C, center, orient, g6, g_box);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_act_bwd(float* dout, const float* out, long long n, int act, t3d_stream_t stream) {
+  if (!dout || !out || n <= 0) return T3D_ERR_ARG;
+  if (act < 0 || act > 3) return T3D_ERR_SHAPE;
+  act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(dout, out, (size_t)n, act);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_rowmask_mul(const float* x, const float* rowmask, float* out, long long M, int C, t3d_stream_t stream) {
+  if (!x || !rowmask || !out || M <= 0 || C <= 0) return T3D_ERR_ARG;
+  const size_t total = (size_t)M * C;
+  rowmask_mul_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(x, rowmask, out, total, C);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_group_sum(const float* x, int B, int N, int C, float scale, float* out, t3d_stream_t stream) {
+  if (!x || !out) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0 || C <= 0 || C > 8) return T3D_ERR_SHAPE;
+  group_sum_kernel<<<B, 256, 0, S(stream)>>>(x, N, C, scale, out);
   T3D_CHECK_LAUNCH();
   return 0;
 }

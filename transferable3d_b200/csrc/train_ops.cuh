@@ -89,10 +89,26 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs a) {
   }
 }
 
+// activation ids follow include/t3d_b200.h: 0 none, 1 relu, 2 leaky_relu(0.2), 3 tanh
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.0f);
+  if (act == 2) return v > 0.0f ? v : 0.2f * v;
+  if (act == 3) return tanhf(v);
+  return v;
+}
+// derivative expressed through the OUTPUT value (what the forward pass keeps)
+__device__ __forceinline__ float act_grad_from_out(float out, int act) {
+  if (act == 1) return out > 0.0f ? 1.0f : 0.0f;
+  if (act == 2) return out > 0.0f ? 1.0f : 0.2f;
+  if (act == 3) return 1.0f - out * out;
+  return 1.0f;
+}
+
 // ----------------------------------------------------------------------------- column statistics
 // out0[c] += sum_r f0, out1[c] += sum_r f1 over the rows of X[M,C] (zero-initialised outputs, atomics).
-//  mode 0: f0 = x,            f1 = x*x                      (BN forward: mean / variance)
-//  mode 1: f0 = dy,           f1 = dy * xhat                 (BN backward; dy = dOut * (out > 0) if out != null)
+//  mode 0: f0 = x - shift[c],  f1 = (x - shift[c])^2          (BN forward: mean / variance; shift = row 0 of X keeps
+//                                                            E[d^2] - E[d]^2 free of cancellation when |mean| >> std)
+//  mode 1: f0 = dy,           f1 = dy * xhat                 (BN backward; dy = dOut * act'(out) if out != null)
 //          xhat = (y - mean[c]) * rstd[c]
 struct ColStatArgs {
   const float* X;           // mode 0: x ; mode 1: dOut
@@ -100,7 +116,7 @@ struct ColStatArgs {
   const float* y;           // mode 1: pre-BN values
   const float* mean; const float* rstd;
   float* o0; float* o1;
-  int M, C, mode;
+  int M, C, mode, act;
 };
 __global__ void __launch_bounds__(256) colstats_kernel(const ColStatArgs a) {
   // block: 32 columns x 8 row-lanes; grid.x over column groups, grid.y over row chunks
@@ -111,12 +127,13 @@ __global__ void __launch_bounds__(256) colstats_kernel(const ColStatArgs a) {
   float s0 = 0.f, s1 = 0.f;
   if (c < a.C) {
     const float mu = a.mode == 1 ? a.mean[c] : 0.f, rs = a.mode == 1 ? a.rstd[c] : 0.f;
+    const float shift = (a.mode == 0 && a.y) ? a.y[c] : 0.f;
     for (int r = r0 + rl; r < r1; r += 8) {
       const size_t i = (size_t)r * a.C + c;
-      if (a.mode == 0) { const float x = a.X[i]; s0 += x; s1 = fmaf(x, x, s1); }
+      if (a.mode == 0) { const float x = a.X[i] - shift; s0 += x; s1 = fmaf(x, x, s1); }
       else {
         float dy = a.X[i];
-        if (a.out && !(a.out[i] > 0.0f)) dy = 0.0f;
+        if (a.out) dy *= act_grad_from_out(a.out[i], a.act);
         s0 += dy; s1 = fmaf(dy, (a.y[i] - mu) * rs, s1);
       }
     }
@@ -132,13 +149,14 @@ __global__ void __launch_bounds__(256) colstats_kernel(const ColStatArgs a) {
 
 // finalize BN statistics: mean, biased var -> rstd; moving <- decay*moving + (1-decay)*batch (unbiased var into
 // the moving variance, TF1 fused-BN behaviour)
-__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, int M, int C, float eps, float decay,
+__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const float* shift, int M, int C, float eps, float decay,
                                    float* mean, float* rstd, float* moving_mean, float* moving_var) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float mu = sum[c] / (float)M;
-  const float var = fmaxf(sumsq[c] / (float)M - mu * mu, 0.0f);
-  mean[c] = mu; rstd[c] = rsqrtf(var + eps);
+  const float md = sum[c] / (float)M;                       // mean of (x - shift)
+  const float var = fmaxf(sumsq[c] / (float)M - md * md, 0.0f);
+  const float mu = md + (shift ? shift[c] : 0.0f);
+  mean[c] = mu; rstd[c] = 1.0f / sqrtf(var + eps);
   if (moving_mean) {
     moving_mean[c] = decay * moving_mean[c] + (1.0f - decay) * mu;
     const float unb = var * ((float)M / (float)max(M - 1, 1));
@@ -146,7 +164,7 @@ __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, int M, 
   }
 }
 
-// out = act(gamma * (y - mean) * rstd + beta) ; act: 0 none, 1 relu
+// out = act(gamma * (y - mean) * rstd + beta)
 __global__ void bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
                                 size_t total, int C, int act) {
@@ -154,19 +172,18 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, const float* __rest
   if (i >= total) return;
   const int c = (int)(i % C);
   float v = gamma[c] * (y[i] - mean[c]) * rstd[c] + beta[c];
-  if (act == 1) v = fmaxf(v, 0.0f);
-  out[i] = v;
+  out[i] = act_apply(v, act);
 }
 
-// dY = gamma*rstd * (dy - s1/M - xhat*s2/M), dy = dOut*(out>0) ; written over dOut (in place)
+// dY = gamma*rstd * (dy - s1/M - xhat*s2/M), dy = dOut*act'(out) ; written over dOut (in place)
 __global__ void bn_backward_kernel(float* __restrict__ dOut, const float* __restrict__ out, const float* __restrict__ y,
                                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                   const float* __restrict__ s1, const float* __restrict__ s2, size_t total, int C, int M) {
+                                   const float* __restrict__ s1, const float* __restrict__ s2, size_t total, int C, int M, int act) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
   float dy = dOut[i];
-  if (out && !(out[i] > 0.0f)) dy = 0.0f;
+  if (out) dy *= act_grad_from_out(out[i], act);
   const float xh = (y[i] - mean[c]) * rstd[c];
   const float inv = 1.0f / (float)M;
   dOut[i] = gamma[c] * rstd[c] * (dy - s1[c] * inv - xh * s2[c] * inv);

@@ -17,6 +17,7 @@ from . import boxpc_sunrgbd
 from ._lib import ptr, stream, call, t3d_boxpc_loss_args
 from .constants import BN_EPS
 from .weights import net_table
+from .train_layers import TrainLayer, ACT_RELU, ACT_NONE
 
 BN_INIT_DECAY = 0.5
 BN_DECAY_DECAY_RATE = 0.5
@@ -32,82 +33,6 @@ def get_bn_decay(batch, batch_size, decay_step=800000):
     """train_boxpc.py:144-152."""
     bn_momentum = BN_INIT_DECAY * BN_DECAY_DECAY_RATE ** ((batch * batch_size) // int(decay_step))
     return min(BN_DECAY_CLIP, 1 - bn_momentum)
-
-
-def _gemm(A, sam, sak, Bm, sbk, sbn, M, N, K, bias=None, splitk=1):
-    C = torch.empty((M, N), dtype=torch.float32, device=A.device)
-    call('t3d_gemm_f32', ptr(A), sam, sak, ptr(Bm), sbk, sbn, ptr(C), N, M, N, K, splitk, ptr(bias), stream())
-    return C
-
-
-def _splitk(M, N, K):
-    tiles = ((M + 63) // 64) * ((N + 63) // 64)
-    return int(max(1, min(K // 512, (1200 + tiles - 1) // tiles)))
-
-
-class _Layer(object):
-    """One conv2d(1x1) / fully_connected layer in training mode: x.W + b -> BN(batch stats) -> ReLU."""
-
-    def __init__(self, g, name, kin, nout, bn, act):
-        self.g, self.name, self.K, self.N, self.bn, self.act = g, name, kin, nout, bn, act
-
-    def p(self, suffix):
-        return self.g.param[self.name + '/' + suffix]
-
-    def d(self, suffix):
-        return self.g.grad[self.name + '/' + suffix]
-
-    def forward(self, x, bn_decay):
-        M = x.shape[0]
-        self.x = x
-        W = self.p('weights').view(self.K, self.N)
-        y = _gemm(x, self.K, 1, W, self.N, 1, M, self.N, self.K, bias=self.p('biases'))
-        self.y = y
-        if not self.bn:
-            self.out = y
-            return y
-        dev = x.device
-        s0 = torch.empty(self.N, device=dev)
-        s1 = torch.empty(self.N, device=dev)
-        call('t3d_colstats', ptr(y), None, None, None, None, ptr(s0), ptr(s1), M, self.N, 0, stream())
-        self.mean = torch.empty(self.N, device=dev)
-        self.rstd = torch.empty(self.N, device=dev)
-        call('t3d_bn_finalize', ptr(s0), ptr(s1), M, self.N, BN_EPS, float(bn_decay), ptr(self.mean), ptr(self.rstd),
-             ptr(self.g.moving[self.name + '/bn/moving_mean']), ptr(self.g.moving[self.name + '/bn/moving_variance']), stream())
-        out = torch.empty_like(y)
-        call('t3d_bn_apply', ptr(y), ptr(self.mean), ptr(self.rstd), ptr(self.p('bn/gamma')), ptr(self.p('bn/beta')), ptr(out),
-             M, self.N, 1 if self.act else 0, stream())
-        self.out = out
-        return out
-
-    def backward(self, dout, need_dx=True):
-        """dout: gradient w.r.t. this layer's output (overwritten). Returns dX (or None)."""
-        M = self.x.shape[0]
-        dev = dout.device
-        if self.bn:
-            s1 = torch.empty(self.N, device=dev)
-            s2 = torch.empty(self.N, device=dev)
-            call('t3d_colstats', ptr(dout), ptr(self.out) if self.act else None, ptr(self.y), ptr(self.mean), ptr(self.rstd),
-                 ptr(s1), ptr(s2), M, self.N, 1, stream())
-            self.d('bn/beta').copy_(s1)
-            self.d('bn/gamma').copy_(s2)
-            call('t3d_bn_backward', ptr(dout), ptr(self.out) if self.act else None, ptr(self.y), ptr(self.mean), ptr(self.rstd),
-                 ptr(self.p('bn/gamma')), ptr(s1), ptr(s2), M, self.N, stream())
-        dy = dout
-        # bias gradient = column sum of dY
-        bs = torch.empty(self.N, device=dev)
-        junk = torch.empty(self.N, device=dev)
-        call('t3d_colstats', ptr(dy), None, None, None, None, ptr(bs), ptr(junk), M, self.N, 0, stream())
-        self.d('biases').copy_(bs)
-        # wgrad: dW[K,N] = X^T dY  (A(m=k_in, k=row) = X[row*K + k_in])
-        dW = self.d('weights').view(self.K, self.N)
-        call('t3d_gemm_f32', ptr(self.x), 1, self.K, ptr(dy), self.N, 1, ptr(dW), self.N, self.K, self.N, M,
-             _splitk(self.K, self.N, M), None, stream())
-        if not need_dx:
-            return None
-        # dgrad: dX[M,K] = dY W^T  (B(k=n_out, n=k_in) = W[k_in*N + n_out])
-        W = self.p('weights').view(self.K, self.N)
-        return _gemm(dy, self.N, 1, W, 1, self.N, M, self.K, self.N)
 
 
 class BoxPCTrainGraph(object):
@@ -149,7 +74,8 @@ class BoxPCTrainGraph(object):
                         np.asarray(variables['%s/%s/%s' % (scope, lname, suf)], dtype=np.float32)).to(self.device).contiguous()
         self.layers = []
         for i, (lname, kind, kw, cin, cout, bn) in enumerate(table):
-            self.layers.append(_Layer(self, lname, kw * cin if kind == 'conv' else cin, cout, bn, act=bn))
+            self.layers.append(TrainLayer(lname, kw * cin if kind == 'conv' else cin, cout, bn, ACT_RELU if bn else ACT_NONE,
+                                          self.param, self.moving, self.grad))
         self.global_step = 0
         self._store = rt.VariableStore({}, self.device)        # constants only (anchors)
 
