@@ -180,6 +180,7 @@ typedef struct {
   const float *Rtilt, *K, *rot_frust, *box2D, *img_dim;
   const int* is_data_2D;
   const float *fit_logits, *mean_size, *cls_sum, *cls_cnt;
+  const float* reg_in;   /* optional [B,7] (center, dims, orient): evaluate the weak losses on this box instead of the parsed one */
   int B, NH, NS, NC;
   unsigned icv_train_mask;
   float w_ce, box_mult, w_center, w_ocls, w_dcls, w_oreg, w_dreg, w_tnet, w_corner;

@@ -167,3 +167,49 @@ def test_semi_loss_kernel_vs_oracle(over, built_lib):
         s = err_stats(got, r64)
         floor = err_stats(r32, r64)
         assert s['max_abs'] <= 5 * floor['max_abs'] + 1e-4 * max(s['ref_scale'], 1e-6) + 1e-7, (name, s, floor)
+
+
+def test_reference_named_loss_wrappers(built_lib):
+    """semisup_v1_sunrgbd.get_semi_loss / get_strong_loss and weak_losses.get_reprojection_loss /
+    get_intraclass_variance_loss_v1 called with the reference's argument lists on the eval-mode graph's end points."""
+    from oracle import semisup_v1_sunrgbd as OM, weak_losses as owl, test_semisup as ots, train_semisup_adv as ot
+    from oracle.tf_layers import VarStore
+    from transferable3d_b200 import runtime as rt, test_semisup as ts, semisup_v1_sunrgbd as M, weak_losses as wl
+    B, N = 12, 256
+    v, feed, _, FLAGS = _setup(B, N)
+    vs = VarStore(v)
+    T = lambda a, dt=torch.float32: torch.as_tensor(np.asarray(a)).to(dt)
+    with torch.no_grad():
+        ologits, oep = ots.run_graph(vs, FLAGS, T(feed['pc']), T(feed['one_hot']))
+        oep['intraclsdims_train_classes'], oep['inactive_vol_train_classes'] = ot.class_lists(FLAGS)
+        I = torch.int64
+        olabels = (T(feed['labels'], I), T(feed['centers']), T(feed['y_orient_cls'], I), T(feed['y_orient_reg']), T(feed['y_dims_cls'], I),
+                   T(feed['y_dims_reg']), None, None, T(feed['Rtilt']), T(feed['K']), T(feed['rot_frust']), T(feed['box2D']),
+                   T(feed['img_dim']), T(feed['is_data_2D'], I))
+        opred = (ologits, None, tuple(oep['F_' + k] for k in ('center', 'size_scores', 'size_residuals', 'heading_scores', 'heading_residuals')))
+        ototal = OM.get_semi_loss(opred, olabels, oep, c=FLAGS)
+        omask_l, obox_l = OM.get_strong_loss((ologits, opred[2]), olabels[:6], oep, prefix='F_', reduce_loss=False, c=FLAGS)
+        orep = owl.get_reprojection_loss(oep['F_pred_box_reg'], olabels[11], olabels[8], olabels[9], olabels[12], olabels[10], False, 10., 1.5,
+                                         True, False, 'huber', [True, True, True], reduce_loss=False)
+        oicv = owl.get_intraclass_variance_loss_v1(oep['F_pred_box_reg'][1], oep['class_ids'], [True] * 10, 10, True, 0.2, 'huber')
+    store = rt.VariableStore(v, DEV)
+    rt.set_default_store(store)
+    D = lambda a, dt=torch.float32: torch.as_tensor(np.asarray(a)).to(device=DEV, dtype=dt).contiguous()
+    with rt.precision('fp32'), torch.no_grad():
+        logits, ep = ts.build_graph(FLAGS, D(feed['pc']), D(feed['one_hot']))
+    i32 = torch.int32
+    labels = (D(feed['labels'], i32), D(feed['centers']), D(feed['y_orient_cls'], i32), D(feed['y_orient_reg']), D(feed['y_dims_cls'], i32),
+              D(feed['y_dims_reg']), None, None, D(feed['Rtilt']), D(feed['K']), D(feed['rot_frust']), D(feed['box2D']), D(feed['img_dim']),
+              D(feed['is_data_2D'], i32))
+    pred = (logits, None, None)
+    total = M.get_semi_loss(pred, labels, ep, c=FLAGS)
+    mask_l, box_l = M.get_strong_loss(pred, labels[:6], ep, prefix='F_', reduce_loss=False, c=FLAGS)
+    rep = wl.get_reprojection_loss(ep['F_pred_box_reg'], labels[11], labels[8], labels[9], labels[12], labels[10], False, 10., 1.5, True, False,
+                                   'huber', [True, True, True], reduce_loss=False)
+    icv = wl.get_intraclass_variance_loss_v1(ep['F_pred_box_reg'][1], ep['class_ids'], [True] * 10, 10, True, 0.2, 'huber')
+    torch.cuda.synchronize()
+    assert abs(float(total) - float(ototal)) <= 1e-3 * max(1.0, abs(float(ototal))), (float(total), float(ototal))
+    for name, got, ref in (('mask_losses', mask_l, omask_l), ('box_losses', box_l, obox_l), ('reproj', rep, orep)):
+        s = err_stats(got.cpu().numpy(), ref.numpy())
+        assert s['max_abs'] <= 1e-3 * max(s['ref_scale'], 1.0), (name, s)
+    assert abs(float(icv) - float(oicv)) <= 1e-4 * max(1.0, float(oicv))

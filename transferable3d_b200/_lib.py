@@ -42,7 +42,7 @@ class t3d_boxpc_loss_args(_c.Structure):
 class t3d_semi_loss_args(_c.Structure):
     _fields_ = ([(n, _P) for n in ('out', 'stage1_center', 'mask_losses', 'one_hot', 'y_center', 'y_orient_cls', 'y_orient_reg',
                                    'y_dims_cls', 'y_dims_reg', 'Rtilt', 'K', 'rot_frust', 'box2D', 'img_dim', 'is_data_2D',
-                                   'fit_logits', 'mean_size', 'cls_sum', 'cls_cnt')] +
+                                   'fit_logits', 'mean_size', 'cls_sum', 'cls_cnt', 'reg_in')] +
                 [(n, _I) for n in ('B', 'NH', 'NS', 'NC')] + [('icv_train_mask', _c.c_uint)] +
                 [(n, _c.c_float) for n in ('w_ce', 'box_mult', 'w_center', 'w_ocls', 'w_dcls', 'w_oreg', 'w_dreg', 'w_tnet',
                                            'w_corner', 'weak_mult', 'w_icv', 'w_reproj', 'w_fit')] +

@@ -123,6 +123,7 @@ struct SemiLossArgs {
   const float* fit_logits;     // [B,2] BoxPC fit logits of F_pred_box_reg, or null
   const float* mean_size;      // [NS,3]
   const float* cls_sum; const float* cls_cnt;    // class_dims_stats_kernel output (intra-class variance), or null
+  const float* reg_in;         // [B,7] optional: evaluate the weak losses on this regression-format box instead of the one parsed from `out`
   int B, NH, NS, NC;
   unsigned icv_train_mask;     // bit c: class c is in intraclsdims_train_classes
   float w_ce, box_mult, w_center, w_ocls, w_dcls, w_oreg, w_dreg, w_tnet, w_corner;     // STRONG_*
@@ -282,7 +283,13 @@ __global__ void __launch_bounds__(64) semi_loss_kernel(const SemiLossArgs a) {
       const float v = m + o[base_sr + istar * 3 + k] * m;
       dims_live[k] = v >= 1e-5f; dims[k] = fmaxf(v, 1e-5f);
     }
-    const float orient = binw * (float)jstar + o[base_hr + jstar] * hscale;
+    float orient = binw * (float)jstar + o[base_hr + jstar] * hscale;
+    float rc[3] = {Fc[0], Fc[1], Fc[2]};
+    if (a.reg_in) {
+      const float* r = a.reg_in + (size_t)b * 7;
+      for (int k = 0; k < 3; ++k) { rc[k] = r[k]; dims[k] = r[3 + k]; dims_live[k] = true; }
+      orient = r[6];
+    }
 
     // ---------------- intra-class variance of dims_reg (weak_losses.py:267-291); group means are stop-gradient
     int cid = 0;
@@ -304,7 +311,7 @@ __global__ void __launch_bounds__(64) semi_loss_kernel(const SemiLossArgs a) {
     float l_reproj = 0.f;
     if (a.w_reproj != 0.f) {
       typedef Dual<7> D;
-      D cx = D::var(Fc[0], 0), cy = D::var(Fc[1], 1), cz = D::var(Fc[2], 2);
+      D cx = D::var(rc[0], 0), cy = D::var(rc[1], 1), cz = D::var(rc[2], 2);
       D dl = D::var(dims[0], 3), dw = D::var(dims[1], 4), dh = D::var(dims[2], 5), th = D::var(orient, 6);
       if (!(a.train_box_mask & 1)) { cx.d[0] = 0.f; cy.d[1] = 0.f; cz.d[2] = 0.f; }
       if (!(a.train_box_mask & 2)) { dl.d[3] = 0.f; dw.d[4] = 0.f; dh.d[5] = 0.f; }

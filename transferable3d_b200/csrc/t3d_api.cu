@@ -489,7 +489,7 @@ extern "C" int t3d_semi_loss(const t3d_semi_loss_args* p, t3d_stream_t stream) {
   a.out = p->out; a.stage1_center = p->stage1_center; a.mask_losses = p->mask_losses; a.one_hot = p->one_hot;
   a.y_center = p->y_center; a.y_orient_cls = p->y_orient_cls; a.y_orient_reg = p->y_orient_reg; a.y_dims_cls = p->y_dims_cls;
   a.y_dims_reg = p->y_dims_reg; a.Rtilt = p->Rtilt; a.K = p->K; a.rot_frust = p->rot_frust; a.box2D = p->box2D; a.img_dim = p->img_dim;
-  a.is_data_2D = p->is_data_2D; a.fit_logits = p->fit_logits; a.mean_size = p->mean_size; a.cls_sum = p->cls_sum; a.cls_cnt = p->cls_cnt;
+  a.is_data_2D = p->is_data_2D; a.fit_logits = p->fit_logits; a.mean_size = p->mean_size; a.cls_sum = p->cls_sum; a.cls_cnt = p->cls_cnt; a.reg_in = p->reg_in;
   a.B = p->B; a.NH = p->NH; a.NS = p->NS; a.NC = p->NC; a.icv_train_mask = p->icv_train_mask;
   a.w_ce = p->w_ce; a.box_mult = p->box_mult; a.w_center = p->w_center; a.w_ocls = p->w_ocls; a.w_dcls = p->w_dcls; a.w_oreg = p->w_oreg;
   a.w_dreg = p->w_dreg; a.w_tnet = p->w_tnet; a.w_corner = p->w_corner; a.weak_mult = p->weak_mult; a.w_icv = p->w_icv;

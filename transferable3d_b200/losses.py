@@ -29,7 +29,7 @@ def _consts(dev):
 
 
 def semi_loss(FLAGS, F_output, stage1_center, one_hot, feed, dev, logits=None, mask_losses=None, fit_logits=None, F_reg=None,
-              icv_mask=None, finish=True, mean_size=None, orient_anchors=None):
+              icv_mask=None, finish=True, mean_size=None, orient_anchors=None, reg_in=None):
     """Runs t3d_seg_ce (if `logits` is given), t3d_class_dims_stats and t3d_semi_loss.
     feed: dict with LABEL_KEYS (+ 'labels' when logits is given).  finish=True also folds g_reg into dF / ds1
     (t3d_box_reg_backward); the training graph passes finish=False, adds the BoxPC input gradient to g_reg and calls
@@ -51,7 +51,8 @@ def semi_loss(FLAGS, F_output, stage1_center, one_hot, feed, dev, logits=None, m
         mask_losses = E(B)
         call('t3d_seg_ce', ptr(logits), ptr(y_seg), B, N, ptr(mask_losses), stream())
     cls_sum, cls_cnt = E(NUM_CLASS, 3), E(NUM_CLASS)
-    call('t3d_class_dims_stats', ptr(F_reg[1]), ptr(one_hot), B, NUM_CLASS, ptr(cls_sum), ptr(cls_cnt), stream())
+    stat_dims = F_reg[1] if reg_in is None else reg_in[:, 3:6].contiguous()
+    call('t3d_class_dims_stats', ptr(stat_dims), ptr(one_hot), B, NUM_CLASS, ptr(cls_sum), ptr(cls_cnt), stream())
     is2d = feed['is_data_2D']
     is2d_host = is2d.cpu().numpy() if torch.is_tensor(is2d) else np.asarray(is2d)
     inv_n3d = 1.0 / (float((1 - is2d_host.astype(np.int64)).sum()) + 1e-3)
@@ -65,7 +66,7 @@ def semi_loss(FLAGS, F_output, stage1_center, one_hot, feed, dev, logits=None, m
     a = t3d_semi_loss_args()
     keep = dict(out=F_output, stage1_center=stage1_center, mask_losses=mask_losses, one_hot=one_hot, fit_logits=fit_logits,
                 mean_size=mean_size, cls_sum=cls_sum, cls_cnt=cls_cnt, dF=dF, ds1=ds1, g_reg=g_reg, dfit=dfit,
-                per_sample=per_sample, total=total, **lab)
+                per_sample=per_sample, total=total, reg_in=reg_in, **lab)
     for k, v in keep.items():
         setattr(a, k, ptr(v))
     a.B, a.NH, a.NS, a.NC = B, NH, NS, NUM_CLASS

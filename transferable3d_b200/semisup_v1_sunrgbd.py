@@ -1,7 +1,8 @@
 """Mirror of sunrgbd/sunrgbd_detection/semisup_v1_sunrgbd.py model definitions
 (placeholder_inputs :37-67, get_semi_model :69-79, get_semi_model_backbone :81-130,
 get_semi_model_final :132-230) on the B200 path; same returned tuples and end_points keys.
-Losses (:236-553) are evaluated by the oracle only in this round (SURVEY 8a a23-a26 'next').
+get_semi_loss / get_semi_loss_final (:248-254, 323-421) and get_strong_loss (:423-553) evaluate the fused loss kernel
+(csrc/loss_ops.cuh); get_iou_summary (:236-246, metrics-only tf.py_func around the missing box_util) is not built.
 """
 import numpy as np
 import torch
@@ -111,3 +112,68 @@ def get_semi_model_final(pc, bg_pc, img, one_hot_vec, is_training, use_one_hot, 
     end_points['F_pred_box_reg'] = F_reg
     pred = (logits, W_pred_box, F_pred_box)
     return pred, end_points
+
+
+# ------------------------------------------------------------------------------------------ losses
+def _label_feed(labels):
+    (y_seg, y_center, y_orient_cls, y_orient_reg, y_dims_cls, y_dims_reg, R0_rect, P, Rtilt, K, rot_frust, box2D, img_dim,
+     is_data_2D) = labels
+    return dict(labels=y_seg, centers=y_center, y_orient_cls=y_orient_cls, y_orient_reg=y_orient_reg, y_dims_cls=y_dims_cls,
+                y_dims_reg=y_dims_reg, Rtilt=Rtilt, K=K, rot_frust=rot_frust, box2D=box2D, img_dim=img_dim, is_data_2D=is_data_2D)
+
+
+def _fit_logits(end_points):
+    if 'boxpc_fit_logits' in end_points:
+        return rt.f32(end_points['boxpc_fit_logits'])
+    p = rt.f32(end_points['boxpc_fit_prob'])
+    return torch.stack([torch.log1p(-p), torch.log(p)], dim=1).contiguous()       # softmax of these is (1-p, p)
+
+
+def get_semi_loss_final(pred, labels, end_points, reduce_loss=True, c=None):
+    """semisup_v1_sunrgbd.py:323-421 -> scalar total loss; the terms land in end_points['semi_loss_terms'] =
+    [total, mask_loss, box_loss, intraclass_var, weak_loss, fit_loss, reproj mean] and the gradients w.r.t. F_output /
+    stage1_center / fit logits in end_points['semi_loss_grads']."""
+    from . import losses
+    if not reduce_loss:
+        raise Exception('Not implemented')
+    pred_seg = rt.f32(pred[0])
+    F_output = rt.f32(end_points['F_output'])
+    fit = _fit_logits(end_points) if c.SEMI_WEIGHT_BOXPC_FIT_LOSS != 0 else None
+    res = losses.semi_loss(c, F_output, rt.f32(end_points['stage1_center']), rt.f32(end_points['class_one_hot']), _label_feed(labels),
+                           F_output.device, logits=pred_seg, fit_logits=fit)
+    end_points['semi_loss_terms'] = res['total']
+    end_points['semi_loss_grads'] = {'F_output': res['dF'], 'stage1_center': res['ds1'], 'boxpc_fit_logits': res['dfit']}
+    end_points['reproj_loss'] = res['per_sample'][:, 2]
+    return res['total'][0]
+
+
+def get_semi_loss(pred, labels, end_points, reduce_loss=True, c=None):
+    """semisup_v1_sunrgbd.py:248-254."""
+    if c.SEMI_MODEL == 'F':
+        return get_semi_loss_final(pred, labels, end_points, reduce_loss, c)
+    raise Exception('Not implemented SEMI_MODEL: %s' % c.SEMI_MODEL)
+
+
+def get_strong_loss(pred, labels, end_points, prefix='', reduce_loss=True, c=None):
+    """semisup_v1_sunrgbd.py:423-553 -> per-sample (mask_losses, box_losses), both (B,) (their means if reduce_loss).
+    The head output is read from end_points['F_output'] (prefix 'F_') or end_points['box_params'] (prefix '')."""
+    from . import losses
+    from .config import cfg as _cfg
+    pred_seg = rt.f32(pred[0])
+    out = rt.f32(end_points['F_output' if prefix == 'F_' else prefix + 'box_params'])
+    y_seg, y_center, y_orient_cls, y_orient_reg, y_dims_cls, y_dims_reg = labels
+    B, dev = out.shape[0], out.device
+    z = lambda *s_, dt=torch.float32: torch.zeros(s_, dtype=dt, device=dev)
+    feed = dict(labels=y_seg, centers=y_center, y_orient_cls=y_orient_cls, y_orient_reg=y_orient_reg, y_dims_cls=y_dims_cls,
+                y_dims_reg=y_dims_reg, Rtilt=z(B, 3, 3), K=z(B, 3, 3), rot_frust=z(B), box2D=z(B, 4), img_dim=z(B, 2),
+                is_data_2D=z(B, dt=torch.int32))
+    cc = _cfg(**{k: getattr(c, k) for k in ('STRONG_WEIGHT_CROSS_ENTROPY', 'STRONG_BOX_MULTIPLER', 'STRONG_WEIGHT_CENTER',
+                                             'STRONG_WEIGHT_ORIENT_CLS', 'STRONG_WEIGHT_ORIENT_REG', 'STRONG_WEIGHT_DIMS_CLS',
+                                             'STRONG_WEIGHT_DIMS_REG', 'STRONG_WEIGHT_TNET_CENTER', 'STRONG_WEIGHT_CORNER')},
+              WEAK_WEIGHT_REPROJECTION=0., WEAK_WEIGHT_INTRACLASSVAR=0., SEMI_WEIGHT_BOXPC_FIT_LOSS=0.)
+    res = losses.semi_loss(cc, out, rt.f32(end_points['stage1_center']), rt.f32(end_points['class_one_hot']), feed, dev, logits=pred_seg)
+    mask_losses = res['per_sample'][:, 5].contiguous()
+    box_losses = res['per_sample'][:, 0].contiguous()
+    if reduce_loss:
+        return mask_losses.mean(), box_losses.mean()
+    return mask_losses, box_losses

@@ -159,11 +159,8 @@ class BoxPCTrainGraph(object):
 
     def apply_gradients(self):
         """Adam over every variable (optimizer.minimize(loss, global_step=batch), train_boxpc.py:249-256)."""
-        world = 1
-        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            world = torch.distributed.get_world_size(self.pg)
-            if world > 1:
-                torch.distributed.all_reduce(self.flat_grad, group=self.pg)        # one NCCL all-reduce of the flat arena
+        from .dist_util import allreduce_flat
+        world = allreduce_flat(self.flat_grad, self.pg)                              # one NCCL all-reduce of the flat arena
         lr = get_learning_rate(self.global_step, self.B, self.base_lr, self.decay_step, self.decay_rate)
         t = self.global_step + 1
         b1, b2 = 0.9, 0.999

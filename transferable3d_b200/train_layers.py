@@ -47,8 +47,8 @@ class ParamArena(object):
 
     def adam_step(self, lr, t, world=1, pg=None, beta1=0.9, beta2=0.999, eps=1e-8):
         """tf.train.AdamOptimizer update after one all-reduce of the flat gradient arena."""
-        if world > 1:
-            torch.distributed.all_reduce(self.flat_grad, group=pg)
+        from .dist_util import allreduce_flat
+        world = allreduce_flat(self.flat_grad, pg) if world > 1 else 1
         lr_t = lr * np.sqrt(1 - beta2 ** t) / (1 - beta1 ** t)
         call('t3d_adam', ptr(self.flat_param), ptr(self.flat_grad), ptr(self.adam_m), ptr(self.adam_v),
              self.flat_param.numel(), float(lr_t), beta1, beta2, eps, 1.0 / world, stream())
