@@ -1,0 +1,432 @@
+// Instance-segmentation stage 2, software-pipelined (v3): same arithmetic, arena and interface as
+// seg_stage2_kernel (seg_stage2.cuh; reference semisup_models.py:107-135 in eval mode, BN folded,
+// conv6's global half folded into gbias), but TWO 128-point tiles are in flight per CTA:
+//
+//   phase 1 of tile i    conv6' blocks (K=64) -> e6 (+gbias, ReLU, bf16) -> conv7 accumulation (K=512 in 4 slices)
+//   phase 2 of tile i-1  e7 -> conv8 -> e8 -> conv9 -> e9 + conv10 (fp32, CUDA cores) -> logits
+//
+// run concurrently: the single MMA-issuer thread interleaves both phases in a fixed order, and two
+// separate groups of 8 epilogue warps serve them (P1: the four e6 blocks, P2: e7 / e8 / e9), so the
+// serial conv7 -> conv8 -> conv9 -> conv10 tail of one tile hides behind the conv6'/conv7 work of the
+// next one.  Shared memory: conv6' activations pass to conv7 through two 16 KB K-block slots (64 channels each,
+// ping-pong), phase 2 owns one 64 KB buffer (conv7 activation = A of conv8, then the 32 KB conv8 activation = A of
+// conv9); what that saves over per-tile buffers deepens the weight ring to 6 x 16 KB (the ring depth, i.e. the
+// bytes in flight against the L2 -> smem multicast latency of ~1.1 k cycles, is what bounds this kernel).
+// TMEM: R6 = cols 0..127 (conv6' block), R89 = 128..255 (conv8, then conv9), R7 = 256..511 (conv7);
+// accumulators are released to the MMA thread as soon as the epilogue has them in registers.
+// Weights: the 26 chunk images of the arena stream through the ring in the issue order below.
+//   PAIR = false  cta_group::1: each CTA of the cluster fetches half of every chunk and multicasts it (as in v2), so
+//                 every SM still ingests all 416 KB of weights per tile -- measured L2 -> SM traffic of 7.8 TB/s is
+//                 what bounds that variant.
+//   PAIR = true   cta_group::2: the two CTAs of the cluster form one UMMA pair (M = 256 = their two tiles); the B
+//                 operand (weights) is split between the two shared memories, so each SM ingests only ITS half of
+//                 every chunk (64 of the 128 rows, 8 KB) and the ring holds 12 chunks.  The leader CTA (rank 0)
+//                 issues every MMA and commit (multicast to both CTAs' barriers); the peer's epilogue warps arrive
+//                 remotely on the leader's barriers, and two forwarder lanes in the peer relay its TMA completions.
+#pragma once
+#include "common.cuh"
+#include "chain_max.cuh"
+#include "seg_stage2.cuh"
+
+namespace t3d {
+
+template <bool PAIR>
+struct Seg2PSmem {
+  static constexpr int STAGES = PAIR ? 12 : 6;
+  static constexpr int STAGE_BYTES = PAIR ? kChunkBytes / 2 : kChunkBytes;
+  static constexpr int IN = 0;                        // [128 x 64] bf16 point_feat tile, 16 KB
+  static constexpr int A6 = 16384;                    // 2 K-block slots [128 x 64] bf16 of the conv6' activation, 16 KB each
+  static constexpr int P2 = A6 + 2 * 16384;           // phase-2 buffer: conv7 activation [128 x 256] (4 K-blocks), then conv8's [128 x 128]
+  static constexpr int RING = P2 + 65536;             // STAGES x STAGE_BYTES
+  static constexpr int GB = RING + STAGES * STAGE_BYTES;   // 2 x 512 fp32 gbias
+  static constexpr int FL = GB + 2 * 512 * 4;         // b7,b8,b9,W10,b10
+  static constexpr int LX = FL + ((kSeg2Floats * 4 + 15) / 16) * 16;   // [128][2] fp32 partial logits of column half 1
+  static constexpr int BARS = LX + 128 * 8;
+  // ring_full[S] ring_empty[S] in_ready in_free r6_full r6_empty a6_ready[2] a6_free[2] r7_full r7_empty a7_ready a8_ready r89_full r89_empty
+  static constexpr int NBARS = 2 * STAGES + 14;
+  static constexpr int TMEM_SLOT = BARS + 8 * NBARS;
+  static constexpr int TOTAL = TMEM_SLOT + 16;
+};
+static_assert(Seg2PSmem<false>::TOTAL + 1024 <= 232448 && Seg2PSmem<true>::TOTAL + 1024 <= 232448, "seg_stage2_pipe: shared memory budget");
+
+constexpr int kSeg2PThreads = 640;   // warp 0 weight producer, 1 MMA, 2 TMEM alloc, 3 input producer, 4-11 P1 epilogue, 12-19 P2 epilogue
+
+// Weight-chunk issue order of one iteration (arena chunk ids: c6(0)=0 c6(1)=1 c7(0)=2..5 c6(2)=6 c6(3)=7 c7(1)=8..11
+// c7(2)=12..15 c7(3)=16..19 conv8=20..23 conv9=24..25); +32 marks the phase-2 chunks (tile i-1).
+__device__ __constant__ uint8_t kSeg2POrder[kSeg2Chunks] = {
+    0, 1, 2, 3, 4, 5, 6, 32 + 20, 32 + 21, 32 + 22, 32 + 23, 8, 9, 10, 11, 7, 32 + 24, 32 + 25, 12, 13, 14, 15, 16, 17, 18, 19};
+
+template <bool PAIR>
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2PThreads, 1) seg_stage2_pipe_kernel(const Seg2Args args) {
+  using L = Seg2PSmem<PAIR>;
+  constexpr int kSeg2PStages = L::STAGES;
+  constexpr uint32_t kStageBytes = L::STAGE_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  constexpr uint16_t kAllCtas = (1u << kClusterSize) - 1;
+
+  const uint32_t bar0 = sbase + L::BARS;
+  auto ring_full = [&](int s) { return bar0 + 8u * s; };
+  auto ring_empty = [&](int s) { return bar0 + 8u * (kSeg2PStages + s); };
+  constexpr int B0 = 2 * kSeg2PStages;
+  const uint32_t in_ready = bar0 + 8u * (B0 + 0), in_free = bar0 + 8u * (B0 + 1);
+  const uint32_t r6_full = bar0 + 8u * (B0 + 2), r6_empty = bar0 + 8u * (B0 + 3);
+  auto a6_ready = [&](int b) { return bar0 + 8u * (B0 + 4 + b); };
+  auto a6_free = [&](int b) { return bar0 + 8u * (B0 + 6 + b); };
+  const uint32_t r7_full = bar0 + 8u * (B0 + 8), r7_empty = bar0 + 8u * (B0 + 9);
+  const uint32_t a7_ready = bar0 + 8u * (B0 + 10), a8_ready = bar0 + 8u * (B0 + 11);
+  const uint32_t r89_full = bar0 + 8u * (B0 + 12), r89_empty = bar0 + 8u * (B0 + 13);
+  constexpr uint32_t kR6 = 0, kR89 = 128, kR7 = 256;
+  const bool leader = !PAIR || crank == 0;
+  // epilogue -> MMA-thread signals: in PAIR mode the MMA thread lives in the leader CTA only
+  auto arrive_mma = [&](uint32_t bar) { if (leader) mbar_arrive(bar); else mbar_arrive_remote(bar, 0); };
+  auto wait_mma = [&](uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
+  // MMA-thread -> everybody signals (both CTAs of the pair in PAIR mode)
+  auto commit_all = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar, kAllCtas); else umma_commit(bar); };
+  auto commit_ring = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar, kAllCtas); else umma_commit_mc(bar, kAllCtas); };
+  auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+    if (PAIR) umma_bf16_pair(d, ad, bd, idesc, acc); else umma_bf16(d, ad, bd, idesc, acc);
+  };
+
+  const int tiles_per_frustum = (args.N + 127) / 128;
+  const int tiles256_per_frustum = (args.N + 255) / 256;
+  const int num_tiles = args.B * tiles_per_frustum;
+  const int ncl = gridDim.x / kClusterSize, cl = blockIdx.x / kClusterSize;
+  const int cbegin = (int)(((long long)num_tiles * cl) / ncl);
+  const int cend = (int)(((long long)num_tiles * (cl + 1)) / ncl);
+  const int iters = (cend - cbegin + kClusterSize - 1) / kClusterSize;
+  auto tile_of = [&](int i) { return min(cbegin + i * kClusterSize + (int)crank, cend - 1); };
+
+  if (threadIdx.x == 0) {
+    // PAIR: the leader's ring_full / in_ready also count the peer's forwarded completion; its epilogue-side barriers
+    // count the 8 warps of both CTAs; ring_empty gets one (pair-multicast) commit
+    const uint32_t fwd = (PAIR && crank == 0) ? 2 : 1, nepi = PAIR ? 16 : 8;
+    for (int s = 0; s < kSeg2PStages; ++s) { mbar_init(ring_full(s), fwd); mbar_init(ring_empty(s), PAIR ? 1 : kClusterSize); }
+    mbar_init(in_ready, fwd); mbar_init(in_free, 1);
+    mbar_init(r6_full, 1); mbar_init(r6_empty, nepi);
+    for (int b = 0; b < 2; ++b) { mbar_init(a6_ready(b), nepi); mbar_init(a6_free(b), 1); }
+    mbar_init(r7_full, 1); mbar_init(r7_empty, nepi);
+    mbar_init(a7_ready, nepi); mbar_init(a8_ready, nepi);
+    mbar_init(r89_full, 1); mbar_init(r89_empty, nepi);
+    fence_barrier_init();
+  }
+  if (warp == 2) { if (PAIR) tmem_alloc_pair<512>(sbase + L::TMEM_SLOT); else tmem_alloc<512>(sbase + L::TMEM_SLOT); }
+  {
+    const float* fsrc = reinterpret_cast<const float*>(args.arena + (size_t)kSeg2Chunks * kChunkBytes);
+    float* fdst = reinterpret_cast<float*>(smem + L::FL);
+    for (int i = threadIdx.x; i < kSeg2Floats; i += blockDim.x) fdst[i] = fsrc[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_SLOT);
+
+  if (warp == 0) {
+    // ================================================================ weight producer
+    // cta_group::1: half of every chunk, multicast to both CTAs; PAIR: this CTA's 64 rows of every chunk, kept local
+    if (lane == 0) {
+      constexpr uint32_t kHalf = kChunkBytes / kClusterSize;
+      uint32_t it = 0;
+      for (int i = 0; i <= iters; ++i)
+        for (int j = 0; j < kSeg2Chunks; ++j) {
+          const int e = kSeg2POrder[j];
+          if ((e & 32) ? (i == 0) : (i == iters)) continue;
+          const int c = e & 31;
+          const int s = it % kSeg2PStages;
+          mbar_wait(ring_empty(s), ((it / kSeg2PStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(ring_full(s), kStageBytes);
+          if (PAIR)
+            bulk_g2s(sbase + L::RING + s * kStageBytes, args.arena + (size_t)c * kChunkBytes + crank * kHalf, kHalf, ring_full(s));
+          else
+            bulk_g2s_mc(sbase + L::RING + s * kStageBytes + crank * kHalf, args.arena + (size_t)c * kChunkBytes + crank * kHalf,
+                        kHalf, ring_full(s), kAllCtas);
+          ++it;
+        }
+    }
+  } else if (PAIR && !leader && warp == 1) {
+    // ================================================================ peer: relay the ring's TMA completions to the leader's MMA thread
+    if (lane == 0) {
+      const uint32_t total = (uint32_t)iters * kSeg2Chunks;
+      for (uint32_t it = 0; it < total; ++it) {
+        const int s = it % kSeg2PStages;
+        mbar_wait(ring_full(s), (it / kSeg2PStages) & 1);
+        mbar_arrive_remote(ring_full(s), 0);
+      }
+    }
+  } else if (PAIR && !leader && warp == 2) {
+    // ================================================================ peer: relay "input tile landed" to the leader's MMA thread
+    if (lane == 0) {
+      for (int i = 0; i < iters; ++i) {
+        mbar_wait(in_ready, i & 1);
+        mbar_arrive_remote(in_ready, 0);
+      }
+    }
+  } else if (warp == 3) {
+    // ================================================================ input producer: point_feat tile + gbias of the frustum
+    if (lane == 0) {
+      for (int i = 0; i < iters; ++i) {
+        const int t = tile_of(i);
+        const int fr = t / tiles_per_frustum, j = t % tiles_per_frustum;
+        if (i > 0) mbar_wait(in_free, (i - 1) & 1);
+        mbar_arrive_expect_tx(in_ready, 16384 + 2048);
+        const size_t row0 = ((size_t)fr * tiles256_per_frustum + (j >> 1)) * 256 + (j & 1) * 128;
+        bulk_g2s(sbase + L::IN, reinterpret_cast<const uint8_t*>(args.point_feat) + row0 * 128, 16384, in_ready);
+        bulk_g2s(sbase + L::GB + (i & 1) * 2048, args.gbias + (size_t)fr * 512, 2048, in_ready);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (PAIR: leader CTA only, one instruction drives both SMs)
+    if (lane == 0) {
+      uint32_t it = 0, n_r6 = 0, n_r89 = 0, n_a6[2] = {0, 0};
+      constexpr int kM = PAIR ? 256 : 128;
+      const uint32_t idesc128 = make_idesc_bf16(kM, 128), idesc256 = make_idesc_bf16(kM, 256);
+      const uint32_t p2buf = sbase + L::P2;
+      Tracer tr; tr.init(args.trace, 1);
+      // one weight chunk (N=128 rows x K=64): D (+)= A[kM x 64] . chunk^T
+      auto mma_chunk = [&](uint32_t a_addr, uint32_t d, bool acc_first) {
+        const int s = it % kSeg2PStages;
+        wait_mma(ring_full(s), (it / kSeg2PStages) & 1);
+        tc_fence_after();
+        const uint32_t b_addr = sbase + L::RING + s * kStageBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          mma(d, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32), idesc128, (acc_first || k > 0) ? 1u : 0u);
+        commit_ring(ring_empty(s));
+        ++it;
+      };
+      for (int i = 0; i <= iters; ++i) {
+        const bool p1 = i < iters, p2 = i > 0;
+        auto c6 = [&](int nb) {
+          wait_mma(r6_empty, (n_r6 & 1) ^ 1);
+          tc_fence_after();
+          tr.mark(0x20 + nb);
+          mma_chunk(sbase + L::IN, tmem_base + kR6, false);
+          commit_all(r6_full); n_r6++;
+          if (nb == 3) commit_all(in_free);
+          tr.mark(0x28 + nb);
+        };
+        // conv7 slice nb = two K-blocks of 64 (the two A6 slots); per K-block the 256 weight rows are two consecutive
+        // chunks (rows 0-127 | rows 128-255): one N=256 instruction when the two ring stages are adjacent whole chunks
+        // (cta_group::1), else two N=128 instructions
+        auto c7 = [&](int nb) {
+          tr.mark(0x30 + nb);
+          for (int kb = 0; kb < 2; ++kb) {
+            wait_mma(a6_ready(kb), n_a6[kb] & 1); n_a6[kb]++;
+            if (nb == 0 && kb == 0) wait_mma(r7_empty, (i & 1) ^ 1);
+            const int s = it % kSeg2PStages, s2 = (it + 1) % kSeg2PStages;
+            wait_mma(ring_full(s), (it / kSeg2PStages) & 1);
+            wait_mma(ring_full(s2), ((it + 1) / kSeg2PStages) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = sbase + L::A6 + kb * 16384;
+            const uint32_t b_addr = sbase + L::RING + s * kStageBytes, b_addr2 = sbase + L::RING + s2 * kStageBytes;
+            if (!PAIR && s2 == s + 1) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                mma(tmem_base + kR7, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32), idesc256,
+                    (nb | kb | k) != 0 ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                mma(tmem_base + kR7, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32), idesc128,
+                    (nb | kb | k) != 0 ? 1u : 0u);
+                mma(tmem_base + kR7 + 128, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr2 + k * 32), idesc128,
+                    (nb | kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            commit_ring(ring_empty(s));
+            commit_ring(ring_empty(s2));
+            commit_all(a6_free(kb));
+            it += 2;
+          }
+          if (nb == 3) commit_all(r7_full);
+          tr.mark(0x38 + nb);
+        };
+        if (p1) { wait_mma(in_ready, i & 1); tc_fence_after(); }
+        tr.mark(0x10);
+        if (p1) { c6(0); c6(1); c7(0); c6(2); }
+        if (p2) {   // conv8 of tile i-1: A = conv7 activation (4 K-blocks) -> R89
+          wait_mma(a7_ready, (i - 1) & 1);
+          wait_mma(r89_empty, (n_r89 & 1) ^ 1);
+          tr.mark(0x40);
+          tc_fence_after();
+          for (int kb = 0; kb < 4; ++kb) mma_chunk(p2buf + kb * 16384, tmem_base + kR89, kb != 0);
+          commit_all(r89_full); n_r89++;
+          tr.mark(0x41);
+        }
+        if (p1) { c7(1); c6(3); }
+        if (p2) {   // conv9 of tile i-1: A = conv8 activation (2 K-blocks) -> R89
+          wait_mma(a8_ready, (i - 1) & 1);
+          wait_mma(r89_empty, (n_r89 & 1) ^ 1);
+          tr.mark(0x50);
+          tc_fence_after();
+          for (int kb = 0; kb < 2; ++kb) mma_chunk(p2buf + kb * 16384, tmem_base + kR89, kb != 0);
+          commit_all(r89_full); n_r89++;
+          tr.mark(0x51);
+        }
+        if (p1) { c7(2); c7(3); }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================ epilogue warps: lane quarter = warp&3, column half per group
+    const bool is_p1 = warp < 12;
+    const int q = warp & 3;
+    const int half = ((warp - 4) & 7) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const uint32_t fl = sbase + L::FL;     // byte addresses of the fp32 constants in smem
+    const uint32_t b7 = fl, b8 = fl + 4 * 256, b9 = fl + 4 * 384, w10 = fl + 4 * 512, b10 = fl + 4 * 768;
+    const uint32_t lx = sbase + L::LX;
+    Tracer tr; tr.init(((warp == 4 || warp == 12) && lane == 0) ? args.trace : nullptr, is_p1 ? 2 : 3);
+
+    // 64 accumulator columns [c0, c0+64) of TMEM region `rcol` into registers
+    auto load64 = [&](uint32_t rcol, int c0, uint32_t (&va)[32], uint32_t (&vb)[32]) {
+      tmem_ld32(tmem_base + lane_sel + rcol + c0, va);
+      tmem_ld32(tmem_base + lane_sel + rcol + c0 + 32, vb);
+      tmem_ld_wait();
+    };
+    // the accumulator region is free again as soon as this warp's values are in registers
+    auto release_acc = [&](uint32_t empty_bar) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive_mma(empty_bar);
+    };
+    // 32 columns [cg, cg+32) of a layer's output: +bias, ReLU, bf16, stored into the K-major SW128 operand whose K-block
+    // kb = cg / 64 lives at obuf + kb * 16 KB
+    auto store32 = [&](const uint32_t (&v)[32], int cg, uint32_t bias, uint32_t obuf) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = ld_shared_f4(bias + 4u * (cg + 4 * j));
+        pk[2 * j] = pack_bf16_relu(__uint_as_float(v[4 * j]) + b4.x, __uint_as_float(v[4 * j + 1]) + b4.y);
+        pk[2 * j + 1] = pack_bf16_relu(__uint_as_float(v[4 * j + 2]) + b4.z, __uint_as_float(v[4 * j + 3]) + b4.w);
+      }
+      const int kb = cg >> 6, j0 = (cg & 63) >> 3;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        st_shared_v4(obuf + kb * 16384 + sw128_offset(row, j0 + jj), pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+    };
+    auto store64 = [&](const uint32_t (&va)[32], const uint32_t (&vb)[32], int c0, uint32_t bias, uint32_t obuf) {
+      store32(va, c0, bias, obuf);
+      store32(vb, c0 + 32, bias, obuf);
+    };
+    auto publish = [&](uint32_t ready_bar) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) arrive_mma(ready_bar);
+    };
+
+    if (is_p1) {
+      // ---------------------------------------------------------------- P1: the four conv6' blocks of every tile
+      // each conv6' block of 128 channels leaves as two K-blocks of 64 (slot = K-block parity); this warp owns the
+      // 32 columns [half*32, +32) of either K-block
+      uint32_t n6 = 0, n_slot = 0;
+      for (int i = 0; i < iters; ++i) {
+        const uint32_t gb = sbase + L::GB + (i & 1) * 2048;
+        mbar_wait(in_ready, i & 1);                    // gbias of this tile has landed in smem
+        tr.mark(0x10);
+        for (int nb = 0; nb < 4; ++nb, ++n_slot) {
+          uint32_t va[32], vb[32];
+          mbar_wait(r6_full, n6 & 1); n6++;
+          tc_fence_after();
+          tr.mark(0x20 + nb);
+          tmem_ld32(tmem_base + lane_sel + kR6 + half * 32, va);
+          tmem_ld32(tmem_base + lane_sel + kR6 + 64 + half * 32, vb);
+          tmem_ld_wait();
+          release_acc(r6_empty);
+          // slot use number n_slot waits for the conv7 K-block that read use n_slot-1
+          mbar_wait(a6_free(0), (n_slot & 1) ^ 1);
+          store32(va, half * 32, gb + 4u * (nb * 128), sbase + L::A6);
+          publish(a6_ready(0));
+          mbar_wait(a6_free(1), (n_slot & 1) ^ 1);
+          store32(vb, half * 32, gb + 4u * (nb * 128 + 64), sbase + L::A6 + 16384);
+          publish(a6_ready(1));
+          tr.mark(0x28 + nb);
+        }
+      }
+    } else {
+      // ---------------------------------------------------------------- P2: e7, e8, e9 + conv10 of every tile
+      uint32_t n89 = 0;
+      for (int i = 0; i < iters; ++i) {
+        const int t = tile_of(i);
+        const int fr = t / tiles_per_frustum;
+        const int start = (t % tiles_per_frustum) * 128;
+        const int npts = min(128, args.N - start);
+        const uint32_t tb = sbase + L::P2;
+        tr.mark(0x10);
+        mbar_wait(r7_full, i & 1);
+        tc_fence_after();
+        tr.mark(0x30);
+        {
+          uint32_t va[32], vb[32];
+          load64(kR7, half * 128, va, vb);
+          store64(va, vb, half * 128, b7, tb);
+          load64(kR7, half * 128 + 64, va, vb);
+          release_acc(r7_empty);
+          store64(va, vb, half * 128 + 64, b7, tb);
+        }
+        publish(a7_ready);
+        tr.mark(0x31);
+        mbar_wait(r89_full, n89 & 1); n89++;
+        tc_fence_after();
+        tr.mark(0x40);
+        {
+          uint32_t va[32], vb[32];
+          load64(kR89, half * 64, va, vb);
+          release_acc(r89_empty);
+          store64(va, vb, half * 64, b8, tb);          // conv8 activation reuses the first 32 KB of the phase-2 buffer
+        }
+        publish(a8_ready);
+        tr.mark(0x41);
+        mbar_wait(r89_full, n89 & 1); n89++;
+        tc_fence_after();
+        tr.mark(0x50);
+        // conv9 epilogue + conv10 (128 -> 2) in fp32: each column half reduces its 64 channels
+        float l0 = 0.f, l1 = 0.f;
+        {
+          uint32_t va[32], vb[32];
+          const int c0 = half * 64;
+          load64(kR89, c0, va, vb);
+          release_acc(r89_empty);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const uint32_t (&v)[32] = g == 0 ? va : vb;
+            const int cg = c0 + g * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = ld_shared_f4(b9 + 4u * (cg + j));
+              const float4 w01 = ld_shared_f4(w10 + 8u * (cg + j)), w23 = ld_shared_f4(w10 + 8u * (cg + j + 2));
+              const float a0 = fmaxf(__uint_as_float(v[j]) + bb.x, 0.0f), a1 = fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.0f);
+              const float a2 = fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.0f), a3 = fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.0f);
+              l0 = fmaf(a0, w01.x, l0); l1 = fmaf(a0, w01.y, l1);
+              l0 = fmaf(a1, w01.z, l0); l1 = fmaf(a1, w01.w, l1);
+              l0 = fmaf(a2, w23.x, l0); l1 = fmaf(a2, w23.y, l1);
+              l0 = fmaf(a3, w23.z, l0); l1 = fmaf(a3, w23.w, l1);
+            }
+          }
+        }
+        if (half == 1) st_shared_f2(lx + 8u * row, l0, l1);
+        named_bar_sync(1 + q, 64);                     // the two P2 warps of this lane quarter
+        if (half == 0) {
+          const float2 o = ld_shared_f2(lx + 8u * row), bz = ld_shared_f2(b10);
+          if (row < npts)
+            *reinterpret_cast<float2*>(args.logits + ((size_t)fr * args.N + start + row) * 2) =
+                make_float2(l0 + o.x + bz.x, l1 + o.y + bz.y);
+        }
+        named_bar_sync(1 + q, 64);                     // lx may be overwritten by the next tile only after it was read
+        tr.mark(0x51);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) { if (PAIR) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base); }
+}
+
+}  // namespace t3d

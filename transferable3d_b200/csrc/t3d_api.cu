@@ -4,6 +4,7 @@
 #include "simt_ops.cuh"
 #include "chain_max.cuh"
 #include "seg_stage2.cuh"
+#include "seg_stage2_pipe.cuh"
 #include "train_ops.cuh"
 #include "loss_ops.cuh"
 
@@ -342,19 +343,26 @@ extern "C" int t3d_seg_stage2_bf16(const void* point_feat, const float* gbias, c
   if (B <= 0 || N <= 0) return T3D_ERR_SHAPE;
   if (((uintptr_t)point_feat & 15) || ((uintptr_t)gbias & 15) || ((uintptr_t)logits & 7) || ((uintptr_t)arena & 15))
     return T3D_ERR_ALIGN;
-  static int sms = 0;
+  static int sms = 0, variant = 3;
   if (sms == 0) {
     int dev = 0;
     T3D_CUDA(cudaGetDevice(&dev));
     T3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     T3D_CUDA(cudaFuncSetAttribute(seg_stage2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2Smem::TOTAL + 1024));
+    T3D_CUDA(cudaFuncSetAttribute(seg_stage2_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2PSmem<false>::TOTAL + 1024));
+    T3D_CUDA(cudaFuncSetAttribute(seg_stage2_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2PSmem<true>::TOTAL + 1024));
+    // A/B measurements: T3D_SEG2=v2 one tile at a time, v3 (default) two tiles in flight, v4 = v3 as a cta_group::2 CTA pair
+    const char* e = getenv("T3D_SEG2");
+    if (e != nullptr && e[0] == 'v' && e[1] >= '2' && e[1] <= '4') variant = e[1] - '0';
   }
   Seg2Args a{reinterpret_cast<const __nv_bfloat16*>(point_feat), gbias, reinterpret_cast<const uint8_t*>(arena), logits, B, N, g_trace};
   const int nt = B * ((N + 127) / 128);
   int grid = sms - (sms % kClusterSize);
   const int need = ((nt + kClusterSize - 1) / kClusterSize) * kClusterSize;
   if (need < grid) grid = need;
-  seg_stage2_kernel<<<grid, kSeg2Threads, Seg2Smem::TOTAL + 1024, S(stream)>>>(a);
+  if (variant == 2) seg_stage2_kernel<<<grid, kSeg2Threads, Seg2Smem::TOTAL + 1024, S(stream)>>>(a);
+  else if (variant == 4) seg_stage2_pipe_kernel<true><<<grid, kSeg2PThreads, Seg2PSmem<true>::TOTAL + 1024, S(stream)>>>(a);
+  else seg_stage2_pipe_kernel<false><<<grid, kSeg2PThreads, Seg2PSmem<false>::TOTAL + 1024, S(stream)>>>(a);
   T3D_CHECK_LAUNCH();
   return 0;
 }
