@@ -220,64 +220,90 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
   o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
-// One CTA (1024 threads) per frustum; supports count <= 2048 and npoints <= 2048.
+// One CTA per frustum; supports count <= 2048 and npoints <= 2048.
 // mode 0 ('philox'): see oracle/model_util.py philox_choice -- random ordered subset when count > npoints,
 // identity ++ uniform refill then a random shuffle otherwise; selection = stable sort by 64-bit key.
 // mode 1 ('choice'): rank-space choice array supplied by the host (numpy_legacy stream).
 // indices[b,t] = {b, point}; object_pc[b,t,:] = (xyz - mean, features) of that point.
-__global__ void __launch_bounds__(1024) resample_kernel(const int* __restrict__ idx, const int* __restrict__ count, int N, int npoints,
+//
+// The sort is a one-pass bucket sort: the keys are uniform 64-bit randoms, so their top 9 bits spread the <= 2048
+// elements over 512 buckets of ~4; an element's final rank is its bucket's start (histogram + scan) plus the number of
+// bucket mates that order before it under the (key, element id) comparison, i.e. exactly the stable-argsort position.
+// Only ranks < npoints are materialised.  ~12 shared-memory accesses per element and 5 block barriers instead of the
+// 66 compare-exchange stages of a 2048-wide bitonic network.
+constexpr int kResampleThreads = 512;
+constexpr int kResampleBuckets = 512;
+__global__ void __launch_bounds__(kResampleThreads) resample_kernel(const int* __restrict__ idx, const int* __restrict__ count, int N, int npoints,
                                                         int mode, unsigned long long seed, const int* __restrict__ choice,
                                                         int* __restrict__ indices, const float* __restrict__ pc, int C,
                                                         const float* __restrict__ mean, int c_out, float* __restrict__ object_pc) {
   __shared__ unsigned long long keys[2048];
-  __shared__ unsigned short pay[2048];
   __shared__ unsigned short lst[2048];
+  __shared__ unsigned short order[2048];     // element ids grouped by bucket
+  __shared__ unsigned short sel[2048];       // sel[rank] = element id, rank < npoints
+  __shared__ int start[kResampleBuckets + 1];
+  __shared__ int cursor[kResampleBuckets];
+  __shared__ int warp_tot[kResampleThreads / 32];
   const int b = blockIdx.x, tid = threadIdx.x;
   const int n = count[b];
   const uint32_t k0 = (uint32_t)(seed & 0xFFFFFFFFull), k1 = (uint32_t)(seed >> 32);
   if (n > 0 && mode == 0) {
     const bool sub = n > npoints;
     const int len = sub ? n : npoints;
-    int P = 512;                         // sort size: smallest power of two >= len
-    while (P < len) P <<= 1;
-    for (int t = tid; t < P; t += 1024) {
-      unsigned long long key = ~0ull;
-      if (t < len) {
-        uint32_t o[4];
-        philox4x32_10((uint32_t)t, sub ? 0u : 2u, (uint32_t)b, 0u, k0, k1, o);
-        key = ((unsigned long long)o[0] << 32) | o[1];
-        if (!sub) {
-          uint32_t r[4];
-          philox4x32_10((uint32_t)t, 1u, (uint32_t)b, 0u, k0, k1, r);
-          lst[t] = (unsigned short)(t < n ? t : (r[2] % (uint32_t)n));
-        }
+    for (int t = tid; t < kResampleBuckets; t += kResampleThreads) cursor[t] = 0;
+    __syncthreads();
+    for (int t = tid; t < len; t += kResampleThreads) {
+      uint32_t o[4];
+      philox4x32_10((uint32_t)t, sub ? 0u : 2u, (uint32_t)b, 0u, k0, k1, o);
+      const unsigned long long key = ((unsigned long long)o[0] << 32) | o[1];
+      if (!sub) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)t, 1u, (uint32_t)b, 0u, k0, k1, r);
+        lst[t] = (unsigned short)(t < n ? t : (r[2] % (uint32_t)n));
       }
       keys[t] = key;
-      pay[t] = (unsigned short)t;
+      atomicAdd(&cursor[(int)(key >> 55)], 1);
     }
     __syncthreads();
-    // bitonic sort of (key, payload) ascending, ties by payload (== numpy stable argsort)
-    for (int k = 2; k <= P; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int t = tid; t < P; t += 1024) {
-          const int ixj = t ^ j;
-          if (ixj > t) {
-            const unsigned long long ka = keys[t], kb = keys[ixj];
-            const unsigned short pa = pay[t], pb = pay[ixj];
-            const bool gt = (ka > kb) || (ka == kb && pa > pb);
-            const bool up = (t & k) == 0;
-            if (gt == up) { keys[t] = kb; keys[ixj] = ka; pay[t] = pb; pay[ixj] = pa; }
-          }
-        }
-        __syncthreads();
-      }
+    {   // exclusive scan of the bucket counts (one bucket per thread)
+      const int c = cursor[tid];
+      int v = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, d); if ((tid & 31) >= d) v += u; }
+      if ((tid & 31) == 31) warp_tot[tid >> 5] = v;
+      __syncthreads();
+      int base = 0;
+      for (int w = 0; w < (tid >> 5); ++w) base += warp_tot[w];
+      start[tid] = base + v - c;
+      if (tid == kResampleThreads - 1) start[kResampleBuckets] = base + v;
+      cursor[tid] = base + v - c;
     }
+    __syncthreads();
+    for (int t = tid; t < len; t += kResampleThreads) {
+      const int pos = atomicAdd(&cursor[(int)(keys[t] >> 55)], 1);
+      order[pos] = (unsigned short)t;
+    }
+    __syncthreads();
+    for (int t = tid; t < len; t += kResampleThreads) {
+      const unsigned long long key = keys[t];
+      const int bk = (int)(key >> 55);
+      const int s = start[bk], e = start[bk + 1];
+      if (s >= npoints) continue;                    // the whole bucket ranks beyond what is kept
+      int r = s;
+      for (int u = s; u < e; ++u) {
+        const int v = order[u];
+        const unsigned long long kv = keys[v];
+        r += (kv < key) || (kv == key && v < t);     // ties by element id (== numpy stable argsort)
+      }
+      if (r < npoints) sel[r] = (unsigned short)t;
+    }
+    __syncthreads();
   }
-  for (int t = tid; t < npoints; t += 1024) {
+  for (int t = tid; t < npoints; t += kResampleThreads) {
     int point = 0;
     if (n > 0) {
       int rank;
-      if (mode == 0) rank = (n > npoints) ? pay[t] : lst[pay[t]];
+      if (mode == 0) rank = (n > npoints) ? sel[t] : lst[sel[t]];
       else rank = choice[(size_t)b * npoints + t];
       point = idx[(size_t)b * N + rank];
     }

@@ -68,7 +68,7 @@ extern "C" int t3d_resample(const int* idx, const int* count, int B, int N, int 
   if (mode == 1 && !choice) return T3D_ERR_ARG;
   if (object_pc && (!pc || !mean || c_out < 3 || c_out > C)) return T3D_ERR_ARG;
   if (B <= 0 || N <= 0 || N > 2048 || npoints <= 0 || npoints > 2048) return T3D_ERR_SHAPE;
-  resample_kernel<<<B, 1024, 0, S(stream)>>>(idx, count, N, npoints, mode, (unsigned long long)seed, choice, indices, pc, C,
+  resample_kernel<<<B, kResampleThreads, 0, S(stream)>>>(idx, count, N, npoints, mode, (unsigned long long)seed, choice, indices, pc, C,
                                              mean, c_out, object_pc);
   T3D_CHECK_LAUNCH();
   return 0;
