@@ -192,7 +192,8 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kChainThr
   __syncthreads();
   cluster_sync_all();              // peer barriers are initialised before any multicast reaches them
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_SLOT);
+  const uint32_t tmem_base_v = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_SLOT);
+  const uint32_t tmem_base = tmem_base_v;
 
   if (warp == 0) {
     // ================================================================ weight producer (half of every chunk, multicast)
@@ -213,11 +214,13 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kChainThr
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer
-    if (lane == 0) {
+    // ================================================================ MMA issuer: the whole warp runs this loop converged,
+    // one elected lane issues (umma_*_w, common.cuh); every value below is warp-uniform
+    {
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_v, 0);
       uint32_t it = 0;                       // ring iteration of the first chunk of the current layer
       uint32_t acc_cnt[3] = {0, 0, 0};       // uses of each TMEM region so far
-      Tracer tr; tr.init(args.trace, 1);
+      Tracer tr; tr.init(lane == 0 ? args.trace : nullptr, 1);
       for (int i = 0; i < iters; ++i) {
         const uint32_t tpar = i & 1;
         int fr, start, npts;
@@ -229,14 +232,15 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kChainThr
           const int nbn = (S::HN(l) + 127) / 128, kbn = S::HK(l) / 64;
           for (int sub = 0; sub < NSUB; ++sub) {
             const int r = hidden_region(sub);
-            mbar_wait(act_ready(l, sub), tpar);
+            mbar_wait_w(act_ready(l, sub), tpar);
             tr.mark(0x20 + l * 2 + sub);
             if (S::EMIT_LAYER >= 0 && l == S::EMIT_LAYER + 1 && args.emit != nullptr) {
               // point_feat of this sub-tile: the swizzled [128 x 64] bf16 operand image goes to HBM as is
               const size_t trow = ((size_t)fr * tiles_per_frustum + start / TILE) * TILE + sub * 128;
-              bulk_s2g(reinterpret_cast<uint8_t*>(args.emit) + trow * 128, a_buf + sub * (128 * 128), 128 * 128);
+              if (lane == 0) bulk_s2g(reinterpret_cast<uint8_t*>(args.emit) + trow * 128, a_buf + sub * (128 * 128), 128 * 128);
+              __syncwarp();
             }
-            mbar_wait(acc_empty(r), (acc_cnt[r] & 1) ^ 1);
+            mbar_wait_w(acc_empty(r), (acc_cnt[r] & 1) ^ 1);
             tc_fence_after();
             for (int nb = 0; nb < nbn; ++nb) {
               const int ncols = min(128, S::HN(l) - nb * 128);
@@ -244,56 +248,56 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kChainThr
               for (int kb = 0; kb < kbn; ++kb) {
                 const uint32_t itc = it + nb * kbn + kb;
                 const int s = itc % kRingStages;
-                if (sub == 0) { mbar_wait(ring_full(s), (itc / kRingStages) & 1); tc_fence_after(); }
+                if (sub == 0) { mbar_wait_w(ring_full(s), (itc / kRingStages) & 1); tc_fence_after(); }
                 const uint32_t b_addr = sbase + L::RING + s * kChunkBytes;
                 const uint32_t a_addr = a_buf + kb * (TILE * 128) + sub * (128 * 128);
                 const uint32_t d = tmem_base + region_col(r) + nb * 128;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16(d, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32), idesc, (kb | k) != 0);
-                if (sub == NSUB - 1) umma_commit_mc(ring_empty(s), kAllCtas);
+                  umma_bf16_w(d, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32), idesc, (kb | k) != 0);
+                if (sub == NSUB - 1) umma_commit_mc_w(ring_empty(s), kAllCtas);
               }
             }
-            umma_commit(acc_full(r));
+            umma_commit_w(acc_full(r));
             acc_cnt[r]++;
             tr.mark(0x30 + l * 2 + sub);
           }
           it += nbn * kbn;
           if (l == S::FRONT_FREE_LAYER) {
-            if (S::EMIT_LAYER >= 0 && args.emit != nullptr) bulk_wait_read_all();   // emit has left the smem buffer
-            umma_commit(front_free);
+            if (S::EMIT_LAYER >= 0 && args.emit != nullptr) { if (lane == 0) bulk_wait_read_all(); __syncwarp(); }   // emit has left the smem buffer
+            umma_commit_w(front_free);
           }
         }
         // final layer: channels on M, points on N
-        for (int sub = 0; sub < NSUB; ++sub) mbar_wait(act_ready(S::NH, sub), tpar);
+        for (int sub = 0; sub < NSUB; ++sub) mbar_wait_w(act_ready(S::NH, sub), tpar);
         tr.mark(0x40);
         tc_fence_after();
         const uint32_t b_buf = sbase + L::buf_off(S::ACT_BUF(S::NH));
         const uint32_t idesc_f = make_idesc_bf16(128, TILE);
         for (int mt = 0; mt < NMT; ++mt) {
           const int r = mt & 1;
-          mbar_wait(acc_empty(r), (acc_cnt[r] & 1) ^ 1);
+          mbar_wait_w(acc_empty(r), (acc_cnt[r] & 1) ^ 1);
           tr.mark(0x50 + mt);
           tc_fence_after();
           const uint32_t d = tmem_base + region_col(r);
           for (int kb = 0; kb < S::FK / 64; ++kb, ++it) {
             const int s = it % kRingStages;
-            mbar_wait(ring_full(s), (it / kRingStages) & 1);
+            mbar_wait_w(ring_full(s), (it / kRingStages) & 1);
             tc_fence_after();
             const uint32_t a_addr = sbase + L::RING + s * kChunkBytes;
             const uint32_t b_addr = b_buf + kb * (TILE * 128);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(d, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32), idesc_f, (kb | k) != 0);
-            umma_commit_mc(ring_empty(s), kAllCtas);
+              umma_bf16_w(d, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32), idesc_f, (kb | k) != 0);
+            umma_commit_mc_w(ring_empty(s), kAllCtas);
           }
-          umma_commit(acc_full(r));
+          umma_commit_w(acc_full(r));
           acc_cnt[r]++;
           tr.mark(0x60 + mt);
         }
-        if (S::NH == 0) umma_commit(front_free);
+        if (S::NH == 0) umma_commit_w(front_free);
       }
-      if (S::EMIT_LAYER >= 0 && args.emit != nullptr) bulk_wait_all();
+      if (S::EMIT_LAYER >= 0 && args.emit != nullptr && lane == 0) bulk_wait_all();
     }
   } else if (warp >= 4 && warp < 12) {
     // ================================================================ epilogue warps: TMEM lane quarter = warp&3, column half = (warp-4)>>2

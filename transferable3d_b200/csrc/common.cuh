@@ -131,6 +131,39 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) 
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ----------------------------------------------------------------------------- warp-convergent issue
+// The MMA warp runs its whole loop with all 32 lanes converged and every operand warp-uniform, so ptxas keeps
+// descriptors / addresses in uniform registers and emits one UTCHMMA per instruction; issuing from inside an
+// `if (lane == 0)` region instead costs a vector->uniform "waterfall" loop (ELECT / R2UR.BROADCAST / BRA.U.ANY) and
+// ~85 cycles per MMA (measured: profiles/r01_trace_v3.txt).  elect.sync picks the same lane every time for a converged
+// full-mask warp, which tcgen05.commit requires (it tracks the MMAs of the executing thread).
+__device__ __forceinline__ void umma_bf16_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_w(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"(cta_mask) : "memory");
+}
+// whole-warp wait on an mbarrier phase (every lane polls; the warp reconverges behind the loop)
+__device__ __forceinline__ void mbar_wait_w(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) { }
+  __syncwarp();
+}
+
 // ----------------------------------------------------------------------------- CTA pair (cta_group::2)
 // Both CTAs of the pair allocate (one warp each); the leader (cluster rank 0) issues every MMA and commit.
 template <int COLS>

@@ -15,14 +15,11 @@
 // TMEM: R6 = cols 0..127 (conv6' block), R89 = 128..255 (conv8, then conv9), R7 = 256..511 (conv7);
 // accumulators are released to the MMA thread as soon as the epilogue has them in registers.
 // Weights: the 26 chunk images of the arena stream through the ring in the issue order below.
-//   PAIR = false  cta_group::1: each CTA of the cluster fetches half of every chunk and multicasts it (as in v2), so
-//                 every SM still ingests all 416 KB of weights per tile -- measured L2 -> SM traffic of 7.8 TB/s is
-//                 what bounds that variant.
-//   PAIR = true   cta_group::2: the two CTAs of the cluster form one UMMA pair (M = 256 = their two tiles); the B
-//                 operand (weights) is split between the two shared memories, so each SM ingests only ITS half of
-//                 every chunk (64 of the 128 rows, 8 KB) and the ring holds 12 chunks.  The leader CTA (rank 0)
-//                 issues every MMA and commit (multicast to both CTAs' barriers); the peer's epilogue warps arrive
-//                 remotely on the leader's barriers, and two forwarder lanes in the peer relay its TMA completions.
+// Each CTA of the 2-CTA cluster fetches half of every chunk and multicasts it.
+// (A cta_group::2 CTA-pair variant of this kernel -- weights split between the two shared memories -- was built and
+// measured at commit d57f045: parity-green, 7.9 ms against 6.9 ms for this one; see DESIGN.md.)
+// The MMA warp issues warp-convergently (common.cuh): with 64-cycle N=128 instructions the issue path, not the tensor
+// pipe, was the bottleneck of the first version of this kernel.
 #pragma once
 #include "common.cuh"
 #include "chain_max.cuh"
@@ -30,10 +27,9 @@
 
 namespace t3d {
 
-template <bool PAIR>
 struct Seg2PSmem {
-  static constexpr int STAGES = PAIR ? 12 : 6;
-  static constexpr int STAGE_BYTES = PAIR ? kChunkBytes / 2 : kChunkBytes;
+  static constexpr int STAGES = 6;
+  static constexpr int STAGE_BYTES = kChunkBytes;
   static constexpr int IN = 0;                        // [128 x 64] bf16 point_feat tile, 16 KB
   static constexpr int A6 = 16384;                    // 2 K-block slots [128 x 64] bf16 of the conv6' activation, 16 KB each
   static constexpr int P2 = A6 + 2 * 16384;           // phase-2 buffer: conv7 activation [128 x 256] (4 K-blocks), then conv8's [128 x 128]
@@ -47,7 +43,7 @@ struct Seg2PSmem {
   static constexpr int TMEM_SLOT = BARS + 8 * NBARS;
   static constexpr int TOTAL = TMEM_SLOT + 16;
 };
-static_assert(Seg2PSmem<false>::TOTAL + 1024 <= 232448 && Seg2PSmem<true>::TOTAL + 1024 <= 232448, "seg_stage2_pipe: shared memory budget");
+static_assert(Seg2PSmem::TOTAL + 1024 <= 232448, "seg_stage2_pipe: shared memory budget");
 
 constexpr int kSeg2PThreads = 640;   // warp 0 weight producer, 1 MMA, 2 TMEM alloc, 3 input producer, 4-11 P1 epilogue, 12-19 P2 epilogue
 
@@ -56,9 +52,8 @@ constexpr int kSeg2PThreads = 640;   // warp 0 weight producer, 1 MMA, 2 TMEM al
 __device__ __constant__ uint8_t kSeg2POrder[kSeg2Chunks] = {
     0, 1, 2, 3, 4, 5, 6, 32 + 20, 32 + 21, 32 + 22, 32 + 23, 8, 9, 10, 11, 7, 32 + 24, 32 + 25, 12, 13, 14, 15, 16, 17, 18, 19};
 
-template <bool PAIR>
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2PThreads, 1) seg_stage2_pipe_kernel(const Seg2Args args) {
-  using L = Seg2PSmem<PAIR>;
+  using L = Seg2PSmem;
   constexpr int kSeg2PStages = L::STAGES;
   constexpr uint32_t kStageBytes = L::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -81,17 +76,6 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2PThr
   const uint32_t a7_ready = bar0 + 8u * (B0 + 10), a8_ready = bar0 + 8u * (B0 + 11);
   const uint32_t r89_full = bar0 + 8u * (B0 + 12), r89_empty = bar0 + 8u * (B0 + 13);
   constexpr uint32_t kR6 = 0, kR89 = 128, kR7 = 256;
-  const bool leader = !PAIR || crank == 0;
-  // epilogue -> MMA-thread signals: in PAIR mode the MMA thread lives in the leader CTA only
-  auto arrive_mma = [&](uint32_t bar) { if (leader) mbar_arrive(bar); else mbar_arrive_remote(bar, 0); };
-  auto wait_mma = [&](uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); };
-  // MMA-thread -> everybody signals (both CTAs of the pair in PAIR mode)
-  auto commit_all = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar, kAllCtas); else umma_commit(bar); };
-  auto commit_ring = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar, kAllCtas); else umma_commit_mc(bar, kAllCtas); };
-  auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
-    if (PAIR) umma_bf16_pair(d, ad, bd, idesc, acc); else umma_bf16(d, ad, bd, idesc, acc);
-  };
-
   const int tiles_per_frustum = (args.N + 127) / 128;
   const int tiles256_per_frustum = (args.N + 255) / 256;
   const int num_tiles = args.B * tiles_per_frustum;
@@ -102,19 +86,16 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2PThr
   auto tile_of = [&](int i) { return min(cbegin + i * kClusterSize + (int)crank, cend - 1); };
 
   if (threadIdx.x == 0) {
-    // PAIR: the leader's ring_full / in_ready also count the peer's forwarded completion; its epilogue-side barriers
-    // count the 8 warps of both CTAs; ring_empty gets one (pair-multicast) commit
-    const uint32_t fwd = (PAIR && crank == 0) ? 2 : 1, nepi = PAIR ? 16 : 8;
-    for (int s = 0; s < kSeg2PStages; ++s) { mbar_init(ring_full(s), fwd); mbar_init(ring_empty(s), PAIR ? 1 : kClusterSize); }
-    mbar_init(in_ready, fwd); mbar_init(in_free, 1);
-    mbar_init(r6_full, 1); mbar_init(r6_empty, nepi);
-    for (int b = 0; b < 2; ++b) { mbar_init(a6_ready(b), nepi); mbar_init(a6_free(b), 1); }
-    mbar_init(r7_full, 1); mbar_init(r7_empty, nepi);
-    mbar_init(a7_ready, nepi); mbar_init(a8_ready, nepi);
-    mbar_init(r89_full, 1); mbar_init(r89_empty, nepi);
+    for (int s = 0; s < kSeg2PStages; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), kClusterSize); }
+    mbar_init(in_ready, 1); mbar_init(in_free, 1);
+    mbar_init(r6_full, 1); mbar_init(r6_empty, 8);
+    for (int b = 0; b < 2; ++b) { mbar_init(a6_ready(b), 8); mbar_init(a6_free(b), 1); }
+    mbar_init(r7_full, 1); mbar_init(r7_empty, 8);
+    mbar_init(a7_ready, 8); mbar_init(a8_ready, 8);
+    mbar_init(r89_full, 1); mbar_init(r89_empty, 8);
     fence_barrier_init();
   }
-  if (warp == 2) { if (PAIR) tmem_alloc_pair<512>(sbase + L::TMEM_SLOT); else tmem_alloc<512>(sbase + L::TMEM_SLOT); }
+  if (warp == 2) tmem_alloc<512>(sbase + L::TMEM_SLOT);
   {
     const float* fsrc = reinterpret_cast<const float*>(args.arena + (size_t)kSeg2Chunks * kChunkBytes);
     float* fdst = reinterpret_cast<float*>(smem + L::FL);
@@ -127,8 +108,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2PThr
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_SLOT);
 
   if (warp == 0) {
-    // ================================================================ weight producer
-    // cta_group::1: half of every chunk, multicast to both CTAs; PAIR: this CTA's 64 rows of every chunk, kept local
+    // ================================================================ weight producer (half of every chunk, multicast)
     if (lane == 0) {
       constexpr uint32_t kHalf = kChunkBytes / kClusterSize;
       uint32_t it = 0;
@@ -140,31 +120,10 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2PThr
           const int s = it % kSeg2PStages;
           mbar_wait(ring_empty(s), ((it / kSeg2PStages) & 1) ^ 1);
           mbar_arrive_expect_tx(ring_full(s), kStageBytes);
-          if (PAIR)
-            bulk_g2s(sbase + L::RING + s * kStageBytes, args.arena + (size_t)c * kChunkBytes + crank * kHalf, kHalf, ring_full(s));
-          else
-            bulk_g2s_mc(sbase + L::RING + s * kStageBytes + crank * kHalf, args.arena + (size_t)c * kChunkBytes + crank * kHalf,
-                        kHalf, ring_full(s), kAllCtas);
+          bulk_g2s_mc(sbase + L::RING + s * kStageBytes + crank * kHalf, args.arena + (size_t)c * kChunkBytes + crank * kHalf,
+                      kHalf, ring_full(s), kAllCtas);
           ++it;
         }
-    }
-  } else if (PAIR && !leader && warp == 1) {
-    // ================================================================ peer: relay the ring's TMA completions to the leader's MMA thread
-    if (lane == 0) {
-      const uint32_t total = (uint32_t)iters * kSeg2Chunks;
-      for (uint32_t it = 0; it < total; ++it) {
-        const int s = it % kSeg2PStages;
-        mbar_wait(ring_full(s), (it / kSeg2PStages) & 1);
-        mbar_arrive_remote(ring_full(s), 0);
-      }
-    }
-  } else if (PAIR && !leader && warp == 2) {
-    // ================================================================ peer: relay "input tile landed" to the leader's MMA thread
-    if (lane == 0) {
-      for (int i = 0; i < iters; ++i) {
-        mbar_wait(in_ready, i & 1);
-        mbar_arrive_remote(in_ready, 0);
-      }
     }
   } else if (warp == 3) {
     // ================================================================ input producer: point_feat tile + gbias of the frustum
@@ -180,92 +139,89 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2PThr
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (PAIR: leader CTA only, one instruction drives both SMs)
-    if (lane == 0) {
-      uint32_t it = 0, n_r6 = 0, n_r89 = 0, n_a6[2] = {0, 0};
-      constexpr int kM = PAIR ? 256 : 128;
-      const uint32_t idesc128 = make_idesc_bf16(kM, 128), idesc256 = make_idesc_bf16(kM, 256);
+    // ================================================================ MMA issuer: the whole warp runs this loop converged,
+    // one elected lane issues (umma_*_w); every value below is warp-uniform
+    {
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      uint32_t it = 0, n_r6 = 0, n_r89 = 0, n_a60 = 0, n_a61 = 0;
+      const uint32_t idesc128 = make_idesc_bf16(128, 128), idesc256 = make_idesc_bf16(128, 256);
       const uint32_t p2buf = sbase + L::P2;
-      Tracer tr; tr.init(args.trace, 1);
-      // one weight chunk (N=128 rows x K=64): D (+)= A[kM x 64] . chunk^T
+      Tracer tr; tr.init(lane == 0 ? args.trace : nullptr, 1);
+      // one weight chunk (N=128 rows x K=64): D (+)= A[128 x 64] . chunk^T
       auto mma_chunk = [&](uint32_t a_addr, uint32_t d, bool acc_first) {
-        const int s = it % kSeg2PStages;
-        wait_mma(ring_full(s), (it / kSeg2PStages) & 1);
+        const uint32_t s = it % kSeg2PStages;
+        mbar_wait_w(ring_full(s), (it / kSeg2PStages) & 1);
         tc_fence_after();
-        const uint32_t b_addr = sbase + L::RING + s * kStageBytes;
+        const uint64_t ad = make_sdesc_k128(a_addr), bd = make_sdesc_k128(sbase + L::RING + s * kStageBytes);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          mma(d, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32), idesc128, (acc_first || k > 0) ? 1u : 0u);
-        commit_ring(ring_empty(s));
+          umma_bf16_w(d, ad + 2u * k, bd + 2u * k, idesc128, (acc_first || k > 0) ? 1u : 0u);   // +32 B per K step (>>4)
+        umma_commit_mc_w(ring_empty(s), kAllCtas);
         ++it;
       };
       for (int i = 0; i <= iters; ++i) {
         const bool p1 = i < iters, p2 = i > 0;
         auto c6 = [&](int nb) {
-          wait_mma(r6_empty, (n_r6 & 1) ^ 1);
+          mbar_wait_w(r6_empty, (n_r6 & 1) ^ 1);
           tc_fence_after();
           tr.mark(0x20 + nb);
-          mma_chunk(sbase + L::IN, tmem_base + kR6, false);
-          commit_all(r6_full); n_r6++;
-          if (nb == 3) commit_all(in_free);
+          mma_chunk(sbase + L::IN, tm + kR6, false);
+          umma_commit_w(r6_full); n_r6++;
+          if (nb == 3) umma_commit_w(in_free);
           tr.mark(0x28 + nb);
         };
         // conv7 slice nb = two K-blocks of 64 (the two A6 slots); per K-block the 256 weight rows are two consecutive
-        // chunks (rows 0-127 | rows 128-255): one N=256 instruction when the two ring stages are adjacent whole chunks
-        // (cta_group::1), else two N=128 instructions
+        // chunks (rows 0-127 | rows 128-255): one N=256 instruction when the two ring stages are adjacent, else two N=128
         auto c7 = [&](int nb) {
           tr.mark(0x30 + nb);
-          for (int kb = 0; kb < 2; ++kb) {
-            wait_mma(a6_ready(kb), n_a6[kb] & 1); n_a6[kb]++;
-            if (nb == 0 && kb == 0) wait_mma(r7_empty, (i & 1) ^ 1);
-            const int s = it % kSeg2PStages, s2 = (it + 1) % kSeg2PStages;
-            wait_mma(ring_full(s), (it / kSeg2PStages) & 1);
-            wait_mma(ring_full(s2), ((it + 1) / kSeg2PStages) & 1);
-            tc_fence_after();
-            const uint32_t a_addr = sbase + L::A6 + kb * 16384;
-            const uint32_t b_addr = sbase + L::RING + s * kStageBytes, b_addr2 = sbase + L::RING + s2 * kStageBytes;
-            if (!PAIR && s2 == s + 1) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                mma(tmem_base + kR7, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32), idesc256,
-                    (nb | kb | k) != 0 ? 1u : 0u);
+          for (int kb = 0; kb < 2; ++kb) {
+            if (kb == 0) { mbar_wait_w(a6_ready(0), n_a60 & 1); n_a60++; } else { mbar_wait_w(a6_ready(1), n_a61 & 1); n_a61++; }
+            if (nb == 0 && kb == 0) mbar_wait_w(r7_empty, (i & 1) ^ 1);
+            const uint32_t s = it % kSeg2PStages, s2 = (it + 1) % kSeg2PStages;
+            mbar_wait_w(ring_full(s), (it / kSeg2PStages) & 1);
+            mbar_wait_w(ring_full(s2), ((it + 1) / kSeg2PStages) & 1);
+            tc_fence_after();
+            const uint64_t ad = make_sdesc_k128(sbase + L::A6 + kb * 16384);
+            const uint64_t bd = make_sdesc_k128(sbase + L::RING + s * kStageBytes), bd2 = make_sdesc_k128(sbase + L::RING + s2 * kStageBytes);
+            if (s2 == s + 1) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16_w(tm + kR7, ad + 2u * k, bd + 2u * k, idesc256, (nb | kb | k) != 0 ? 1u : 0u);
             } else {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                mma(tmem_base + kR7, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr + k * 32), idesc128,
-                    (nb | kb | k) != 0 ? 1u : 0u);
-                mma(tmem_base + kR7 + 128, make_sdesc_k128(a_addr + k * 32), make_sdesc_k128(b_addr2 + k * 32), idesc128,
-                    (nb | kb | k) != 0 ? 1u : 0u);
+                umma_bf16_w(tm + kR7, ad + 2u * k, bd + 2u * k, idesc128, (nb | kb | k) != 0 ? 1u : 0u);
+                umma_bf16_w(tm + kR7 + 128, ad + 2u * k, bd2 + 2u * k, idesc128, (nb | kb | k) != 0 ? 1u : 0u);
               }
             }
-            commit_ring(ring_empty(s));
-            commit_ring(ring_empty(s2));
-            commit_all(a6_free(kb));
+            umma_commit_mc_w(ring_empty(s), kAllCtas);
+            umma_commit_mc_w(ring_empty(s2), kAllCtas);
+            umma_commit_w(a6_free(kb));
             it += 2;
           }
-          if (nb == 3) commit_all(r7_full);
+          if (nb == 3) umma_commit_w(r7_full);
           tr.mark(0x38 + nb);
         };
-        if (p1) { wait_mma(in_ready, i & 1); tc_fence_after(); }
+        if (p1) { mbar_wait_w(in_ready, i & 1); tc_fence_after(); }
         tr.mark(0x10);
         if (p1) { c6(0); c6(1); c7(0); c6(2); }
         if (p2) {   // conv8 of tile i-1: A = conv7 activation (4 K-blocks) -> R89
-          wait_mma(a7_ready, (i - 1) & 1);
-          wait_mma(r89_empty, (n_r89 & 1) ^ 1);
+          mbar_wait_w(a7_ready, (i - 1) & 1);
+          mbar_wait_w(r89_empty, (n_r89 & 1) ^ 1);
           tr.mark(0x40);
           tc_fence_after();
-          for (int kb = 0; kb < 4; ++kb) mma_chunk(p2buf + kb * 16384, tmem_base + kR89, kb != 0);
-          commit_all(r89_full); n_r89++;
+          for (int kb = 0; kb < 4; ++kb) mma_chunk(p2buf + kb * 16384, tm + kR89, kb != 0);
+          umma_commit_w(r89_full); n_r89++;
           tr.mark(0x41);
         }
         if (p1) { c7(1); c6(3); }
         if (p2) {   // conv9 of tile i-1: A = conv8 activation (2 K-blocks) -> R89
-          wait_mma(a8_ready, (i - 1) & 1);
-          wait_mma(r89_empty, (n_r89 & 1) ^ 1);
+          mbar_wait_w(a8_ready, (i - 1) & 1);
+          mbar_wait_w(r89_empty, (n_r89 & 1) ^ 1);
           tr.mark(0x50);
           tc_fence_after();
-          for (int kb = 0; kb < 2; ++kb) mma_chunk(p2buf + kb * 16384, tmem_base + kR89, kb != 0);
-          commit_all(r89_full); n_r89++;
+          for (int kb = 0; kb < 2; ++kb) mma_chunk(p2buf + kb * 16384, tm + kR89, kb != 0);
+          umma_commit_w(r89_full); n_r89++;
           tr.mark(0x51);
         }
         if (p1) { c7(2); c7(3); }
@@ -293,7 +249,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2PThr
     auto release_acc = [&](uint32_t empty_bar) {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) arrive_mma(empty_bar);
+      if (lane == 0) mbar_arrive(empty_bar);
     };
     // 32 columns [cg, cg+32) of a layer's output: +bias, ReLU, bf16, stored into the K-major SW128 operand whose K-block
     // kb = cg / 64 lives at obuf + kb * 16 KB
@@ -317,7 +273,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2PThr
     auto publish = [&](uint32_t ready_bar) {
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) arrive_mma(ready_bar);
+      if (lane == 0) mbar_arrive(ready_bar);
     };
 
     if (is_p1) {
@@ -426,7 +382,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2PThr
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 2) { if (PAIR) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<512>(tmem_base); }
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace t3d

@@ -349,11 +349,10 @@ extern "C" int t3d_seg_stage2_bf16(const void* point_feat, const float* gbias, c
     T3D_CUDA(cudaGetDevice(&dev));
     T3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     T3D_CUDA(cudaFuncSetAttribute(seg_stage2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2Smem::TOTAL + 1024));
-    T3D_CUDA(cudaFuncSetAttribute(seg_stage2_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2PSmem<false>::TOTAL + 1024));
-    T3D_CUDA(cudaFuncSetAttribute(seg_stage2_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2PSmem<true>::TOTAL + 1024));
-    // A/B measurements: T3D_SEG2=v2 one tile at a time, v3 (default) two tiles in flight, v4 = v3 as a cta_group::2 CTA pair
+    T3D_CUDA(cudaFuncSetAttribute(seg_stage2_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2PSmem::TOTAL + 1024));
+    // A/B measurements: T3D_SEG2=v2 one tile at a time, v3 (default) two tiles in flight
     const char* e = getenv("T3D_SEG2");
-    if (e != nullptr && e[0] == 'v' && e[1] >= '2' && e[1] <= '4') variant = e[1] - '0';
+    if (e != nullptr && e[0] == 'v' && e[1] >= '2' && e[1] <= '3') variant = e[1] - '0';
   }
   Seg2Args a{reinterpret_cast<const __nv_bfloat16*>(point_feat), gbias, reinterpret_cast<const uint8_t*>(arena), logits, B, N, g_trace};
   const int nt = B * ((N + 127) / 128);
@@ -361,8 +360,7 @@ extern "C" int t3d_seg_stage2_bf16(const void* point_feat, const float* gbias, c
   const int need = ((nt + kClusterSize - 1) / kClusterSize) * kClusterSize;
   if (need < grid) grid = need;
   if (variant == 2) seg_stage2_kernel<<<grid, kSeg2Threads, Seg2Smem::TOTAL + 1024, S(stream)>>>(a);
-  else if (variant == 4) seg_stage2_pipe_kernel<true><<<grid, kSeg2PThreads, Seg2PSmem<true>::TOTAL + 1024, S(stream)>>>(a);
-  else seg_stage2_pipe_kernel<false><<<grid, kSeg2PThreads, Seg2PSmem<false>::TOTAL + 1024, S(stream)>>>(a);
+  else seg_stage2_pipe_kernel<<<grid, kSeg2PThreads, Seg2PSmem::TOTAL + 1024, S(stream)>>>(a);
   T3D_CHECK_LAUNCH();
   return 0;
 }
