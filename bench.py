@@ -37,6 +37,10 @@ FLOP_SEG2_PT = 426496
 FLOP_SEG_GLOBAL_FR = 2 * (1024 + 10) * 512
 FLOP_TNET_PT, FLOP_BOX_PT = 99072, 361216
 FLOP_FC_FR = 2 * (98688 + 2560 + 410368 + 5120)
+# DRAM bytes per frustum (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at 8192 frustums per
+# launch, profiles/r01_ncu_full_v3_kernels.csv); algorithmic: stage 2 reads point_feat 262 144 B + gbias 2 048 B and writes
+# logits 16 384 B, stage 1 reads the points 49 152 B and writes point_feat 262 144 B + gfeat 4 096 B
+NCU_DRAM_BYTES_FR = {'seg2': (2.169102e9 + 0.134332e9) / 8192, 'seg1': (0.436980e9 + 2.125062e9) / 8192}
 
 
 def peaks():
@@ -453,8 +457,10 @@ def main():
         avg = float(np.mean(dom_ms))
         flops = FLOP_SEG2_PT * rchunk * N_POINTS
         ach = flops / (avg * 1e-3) / 1e12
-        roof = {'kernel': 'seg_stage2_kernel (conv6..conv10, tcgen05)', 'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16'],
-                'unit': 'TFLOP/s', 'frac': ach / pk['bf16'], 'traffic': None, 'avg_launch_ms': avg,
+        roof = {'kernel': 'seg_stage2_pipe_kernel (conv6..conv10, tcgen05)', 'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16'],
+                'unit': 'TFLOP/s', 'frac': ach / pk['bf16'], 'frac_of_burst_peak': ach / pk['bf16_burst'],
+                'traffic': NCU_DRAM_BYTES_FR['seg2'] * rchunk, 'traffic_algorithmic': (262144 + 2048 + 16384) * rchunk,
+                'traffic_source': 'ncu --set full, profiles/r01_ncu_full_v3_kernels.csv, scaled per frustum', 'avg_launch_ms': avg,
                 'algorithmic_flops_per_launch': flops, 'peak_source': '%s, sustained bf16 (kernel timed inside a long step)' % pk['src']}
     roof_mp = None
     mp_ms = [a.elapsed_time(b) for a, b in dom['events_mp'][-(args.steps * (n_local // rchunk)):]]
@@ -464,6 +470,7 @@ def main():
         ach = flops / (avg * 1e-3) / 1e12
         roof_mp = {'kernel': 'chain_max_kernel<SEG1> (conv1..conv5 + max-pool fused, tcgen05)', 'bound': 'tensor', 'achieved': ach,
                    'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': ach / pk['bf16'], 'frac_of_burst_peak': ach / pk['bf16_burst'],
+                   'traffic': NCU_DRAM_BYTES_FR['seg1'] * rchunk, 'traffic_algorithmic': (49152 + 262144 + 4096) * rchunk,
                    'avg_launch_ms': avg, 'algorithmic_flops_per_launch': flops}
     if workload == 'cfg3':
         flops_fr = (FLOP_SEG1_PT + FLOP_SEG2_PT) * N_POINTS + FLOP_SEG_GLOBAL_FR + (FLOP_TNET_PT + FLOP_BOX_PT) * 512 + FLOP_FC_FR
