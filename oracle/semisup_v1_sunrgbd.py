@@ -218,8 +218,30 @@ def get_semi_loss_final(pred, labels, end_points, reduce_loss=True, c=None):
     raise Exception('Not implemented')
 
 
+def get_semi_loss_backbone(pred, labels, end_points, reduce_loss=True, c=None):
+    """semisup_v1_sunrgbd.py:256-321 (model A) with the surface term switched off: weak_losses.get_surface_loss and the
+    tf_distance_to_* family it needs are not restated yet (SURVEY 8(f) "next"), so WEAK_WEIGHT_SURFACE must be 0."""
+    from . import weak_losses
+    assert float(c.WEAK_WEIGHT_SURFACE) == 0.0, 'surface loss not restated'
+    pred_seg, pred_box = pred
+    (y_seg, y_center, y_orient_cls, y_orient_reg, y_dims_cls, y_dims_reg, R0_rect, P, Rtilt, K, rot_frust, box2D, img_dim,
+     is_data_2D) = labels
+    reproj = weak_losses.get_reprojection_loss(
+        end_points['S_pred_box_reg'], box2D, Rtilt, K, img_dim, rot_frust, c.WEAK_REPROJECTION_USE_SOFTMAX_PROJ,
+        c.WEAK_REPROJECTION_SOFTMAX_SCALE, c.WEAK_REPROJECTION_DILATE_FACTOR, c.WEAK_REPROJECTION_CLIP_LOWERB_LOSS,
+        c.WEAK_REPROJECTION_CLIP_PRED_BOX, c.WEAK_REPROJECTION_LOSS_TYPE, c.WEAK_TRAIN_BOX_W_REPROJECTION, reduce_loss=False)
+    weak_loss_fns = c.WEAK_WEIGHT_REPROJECTION * reproj
+    mask_losses, strong_losses = get_strong_loss((pred_seg, pred_box), (y_seg, y_center, y_orient_cls, y_orient_reg, y_dims_cls,
+                                                                         y_dims_reg), end_points, reduce_loss=False, c=c)
+    is2d = is_data_2D.to(pred_seg.dtype)
+    total_losses = (1 - is2d) * (mask_losses + strong_losses) + is2d * (weak_loss_fns * c.SEMI_MULTIPLIER_FOR_WEAK_LOSS)
+    return total_losses.mean() if reduce_loss else total_losses
+
+
 def get_semi_loss(pred, labels, end_points, reduce_loss=True, c=None):
     """semisup_v1_sunrgbd.py:248-254."""
+    if c.SEMI_MODEL == 'A':
+        return get_semi_loss_backbone(pred, labels, end_points, reduce_loss, c)
     if c.SEMI_MODEL == 'F':
         return get_semi_loss_final(pred, labels, end_points, reduce_loss, c)
     raise Exception('Not implemented SEMI_MODEL: %s' % c.SEMI_MODEL)

@@ -213,3 +213,66 @@ def test_reference_named_loss_wrappers(built_lib):
         s = err_stats(got.cpu().numpy(), ref.numpy())
         assert s['max_abs'] <= 1e-3 * max(s['ref_scale'], 1.0), (name, s)
     assert abs(float(icv) - float(oicv)) <= 1e-4 * max(1.0, float(oicv))
+
+
+def test_boxpc_reference_named_losses(built_lib):
+    """boxpc_sunrgbd.get_loss / get_boxpc_cls_loss / get_boxpc_delta_loss with the reference's argument lists vs the oracle."""
+    from oracle import boxpc_sunrgbd as OB
+    from transferable3d_b200 import boxpc_sunrgbd as GB
+    B = 64
+    rng = np.random.RandomState(5)
+    A = lambda *s: rng.randn(*s).astype(np.float32)
+    logits, dc, ds, da = A(B, 2) * 2, A(B, 3) * 0.5, A(B, 3) * 0.3, A(B) * 1.5
+    iou = rng.uniform(0, 1, B).astype(np.float32)
+    yc, ys, ya = A(B, 3) * 0.5, A(B, 3) * 0.3, A(B) * 1.5            # |error| on both sides of the huber knee
+    T = torch.as_tensor
+    D = lambda a: torch.as_tensor(a).to(DEV)
+    for kind in ('huber', 'mse'):
+        c = config.cfg(BOXPC_WEIGHT_DELTA=4., BOXPC_DELTA_LOSS_TYPE=kind)
+        opred, olab = (T(logits), (T(dc), T(ds), T(da))), (T(iou), (T(yc), T(ys), T(ya)))
+        pred, lab = (D(logits), (D(dc), D(ds), D(da))), (D(iou), (D(yc), D(ys), D(ya)))
+        ep = {}
+        got = (GB.get_boxpc_cls_loss(pred[0], lab[0], ep, reduce_loss=False, c=c), GB.get_boxpc_delta_loss(pred, lab, ep, reduce_loss=False, c=c),
+               GB.get_loss(pred, lab, ep, reduce_loss=False, c=c))
+        ref = (OB.get_boxpc_cls_loss(opred[0], olab[0], {}, reduce_loss=False, c=c), OB.get_boxpc_delta_loss(opred, olab, {}, reduce_loss=False, c=c),
+               OB.get_loss(opred, olab, {}, reduce_loss=False, c=c))
+        for g, r in zip(got, ref):
+            assert np.allclose(g.cpu().numpy(), r.numpy(), rtol=1e-5, atol=1e-6), kind
+        assert abs(float(GB.get_loss(pred, lab, ep, c=c)) - float(OB.get_loss(opred, olab, {}, c=c))) <= 1e-5 * max(1.0, float(ref[2].mean()))
+        assert ep['boxpc_loss_grad'].shape == (B, 9)
+
+
+def test_semi_loss_backbone_model_A(built_lib):
+    """semisup_v1_sunrgbd.get_semi_loss with SEMI_MODEL 'A' (get_semi_loss_backbone, surface weight 0) on the eval-mode
+    model-A graph vs the oracle."""
+    from oracle import semisup_v1_sunrgbd as OM
+    from oracle.tf_layers import VarStore
+    from transferable3d_b200 import runtime as rt, semisup_v1_sunrgbd as M
+    B, N = 12, 256
+    v = weights.make_weights_model_A()
+    feed = synth.make_batch(B, N, 6, seed=21, is_data_2D=(np.arange(B) % 2))
+    FLAGS = config.cfg(SEMI_MODEL='A', WEAK_WEIGHT_SURFACE=0., WEAK_WEIGHT_REPROJECTION=0.01, SEMI_MULTIPLIER_FOR_WEAK_LOSS=0.05)
+    T = lambda a, dt=torch.float32: torch.as_tensor(np.asarray(a)).to(dt)
+    I = torch.int64
+    with torch.no_grad():
+        opred, oep = OM.get_semi_model(T(feed['pc']), None, None, T(feed['one_hot']), False, True, VarStore(v), c=FLAGS)
+        olabels = (T(feed['labels'], I), T(feed['centers']), T(feed['y_orient_cls'], I), T(feed['y_orient_reg']), T(feed['y_dims_cls'], I),
+                   T(feed['y_dims_reg']), None, None, T(feed['Rtilt']), T(feed['K']), T(feed['rot_frust']), T(feed['box2D']),
+                   T(feed['img_dim']), T(feed['is_data_2D'], I))
+        oper = OM.get_semi_loss(opred, olabels, oep, reduce_loss=False, c=FLAGS)
+    rt.set_default_store(rt.VariableStore(v, DEV))
+    D = lambda a, dt=torch.float32: torch.as_tensor(np.asarray(a)).to(device=DEV, dtype=dt).contiguous()
+    i32 = torch.int32
+    with rt.precision('fp32'), torch.no_grad():
+        pred, ep = M.get_semi_model(D(feed['pc']), None, None, D(feed['one_hot']), False, True, c=FLAGS)
+    labels = (D(feed['labels'], i32), D(feed['centers']), D(feed['y_orient_cls'], i32), D(feed['y_orient_reg']), D(feed['y_dims_cls'], i32),
+              D(feed['y_dims_reg']), None, None, D(feed['Rtilt']), D(feed['K']), D(feed['rot_frust']), D(feed['box2D']), D(feed['img_dim']),
+              D(feed['is_data_2D'], i32))
+    per = M.get_semi_loss(pred, labels, ep, reduce_loss=False, c=FLAGS)
+    total = M.get_semi_loss(pred, labels, ep, c=FLAGS)
+    torch.cuda.synchronize()
+    s = err_stats(per.cpu().numpy(), oper.numpy())
+    assert s['max_abs'] <= 1e-3 * max(s['ref_scale'], 1.0), s
+    assert abs(float(total) - float(oper.mean())) <= 1e-3 * max(1.0, abs(float(oper.mean())))
+    with pytest.raises(NotImplementedError):
+        M.get_semi_loss(pred, labels, ep, c=config.cfg(SEMI_MODEL='A'))      # default WEAK_WEIGHT_SURFACE = 1: surface loss is 'next'

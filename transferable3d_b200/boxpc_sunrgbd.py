@@ -1,5 +1,5 @@
-"""Mirror of sunrgbd/sunrgbd_detection/boxpc_sunrgbd.py model definitions (placeholder_inputs :33-54,
-get_model :56-100, convert_raw_y_box_to_reg_format :206-229) on the B200 path."""
+"""Mirror of sunrgbd/sunrgbd_detection/boxpc_sunrgbd.py on the B200 path: placeholder_inputs :33-54, get_model :56-100,
+get_loss / get_boxpc_cls_loss / get_boxpc_delta_loss :106-193, convert_raw_y_box_to_reg_format :206-229."""
 import ctypes
 
 import numpy as np
@@ -7,7 +7,7 @@ import torch
 
 from . import runtime as rt
 from . import tf_util, semisup_models
-from ._lib import ptr, stream, call, t3d_refine_args
+from ._lib import ptr, stream, call, t3d_refine_args, t3d_boxpc_loss_args
 from .constants import NUM_HEADING_BIN, NUM_SIZE_CLUSTER, NUM_CLASS, MEAN_DIMS_ARR, ORIENT_ANCHORS
 
 
@@ -78,3 +78,48 @@ def convert_raw_y_box_to_reg_format(y_box, one_hot_vec):
     orient_reg = tf_util.tf_expand_tile(rt.f32(y_orient_reg), axis=1, tile=[1, NUM_HEADING_BIN]).contiguous()
     box = (y_centers, dims_cls, dims_reg, orient_cls, orient_reg)
     return tf_util.tf_convert_box_params_from_anchor_to_reg_format_multi(box, class_ids, dims_anchors, orient_anchors)
+
+
+def _boxpc_losses(pred, labels, end_points, c):
+    """One launch of the fused BoxPC loss kernel (csrc/train_ops.cuh, t3d_boxpc_loss): per-sample classification and delta
+    losses, the scalar total of get_loss and d total / d (delta_center, delta_size, delta_angle, fit logits)."""
+    logits, (d_center, d_size, d_angle) = pred
+    y_box_iou, (y_center, y_size, y_angle) = labels
+    if c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_CONF or c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_GT:
+        raise NotImplementedError('BOXPC_WEIGH_DELTA_LOSS_BY_CLS_* are not on the recipe path (scripts/train_semisup_bed.sh)')
+    B, dev = logits.shape[0], logits.device
+    out9 = torch.cat([rt.f32(d_center).reshape(B, 3), rt.f32(d_size).reshape(B, 3), rt.f32(d_angle).reshape(B, 1),
+                      rt.f32(logits).reshape(B, 2)], dim=1).contiguous()
+    y_iou, y_dc, y_ds, y_da = rt.f32(y_box_iou), rt.f32(y_center), rt.f32(y_size), rt.f32(y_angle)
+    E = lambda *s_: torch.empty(s_, dtype=torch.float32, device=dev)
+    cls_l, del_l, total, g9 = E(B), E(B), E(1), E(B, 9)
+    a = t3d_boxpc_loss_args(ptr(out9), ptr(y_iou), ptr(y_dc), ptr(y_ds), ptr(y_da), B, float(c.BOXPC_FIT_BOUNDS[0]),
+                            float(c.BOXPC_WEIGHT_CLS), float(c.BOXPC_WEIGHT_DELTA), float(c.BOXPC_WEIGHT_DELTA_CENTER_PERCENT),
+                            float(c.BOXPC_WEIGHT_DELTA_SIZE_PERCENT), float(c.BOXPC_WEIGHT_DELTA_ANGLE_PERCENT),
+                            1 if c.BOXPC_DELTA_LOSS_TYPE == 'huber' else 0, ptr(cls_l), ptr(del_l), ptr(total), ptr(g9))
+    call('t3d_boxpc_loss', ctypes.byref(a), stream())
+    if end_points is not None:
+        end_points['boxpc_loss_grad'] = g9        # columns: delta_center 0:3, delta_size 3:6, delta_angle 6, fit logits 7:9
+    return cls_l, del_l, total
+
+
+def get_boxpc_cls_loss(logits, y_box_iou, end_points, reduce_loss=True, c=None):
+    """boxpc_sunrgbd.py:130-141: softmax cross-entropy against (iou > BOXPC_FIT_BOUNDS[0]) -> (B,) (mean if reduce_loss)."""
+    B, dev = logits.shape[0], logits.device
+    z = lambda *s_: torch.zeros(s_, dtype=torch.float32, device=dev)
+    cls_l, _, _ = _boxpc_losses((logits, (z(B, 3), z(B, 3), z(B))), (y_box_iou, (z(B, 3), z(B, 3), z(B))), None, c)
+    return cls_l.mean() if reduce_loss else cls_l
+
+
+def get_boxpc_delta_loss(pred, labels, end_points, reduce_loss=True, c=None):
+    """boxpc_sunrgbd.py:143-193: weighted huber / mse of the three box deltas -> (B,) (mean if reduce_loss)."""
+    _, del_l, _ = _boxpc_losses(pred, labels, None, c)
+    return del_l.mean() if reduce_loss else del_l
+
+
+def get_loss(pred, labels, end_points, reduce_loss=True, c=None):
+    """boxpc_sunrgbd.py:106-128: BOXPC_WEIGHT_CLS * cls + BOXPC_WEIGHT_DELTA * delta -> scalar mean (or (B,))."""
+    cls_l, del_l, total = _boxpc_losses(pred, labels, end_points, c)
+    if reduce_loss:
+        return total[0]
+    return float(c.BOXPC_WEIGHT_CLS) * cls_l + float(c.BOXPC_WEIGHT_DELTA) * del_l

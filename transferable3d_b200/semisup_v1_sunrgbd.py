@@ -147,8 +147,34 @@ def get_semi_loss_final(pred, labels, end_points, reduce_loss=True, c=None):
     return res['total'][0]
 
 
+def get_semi_loss_backbone(pred, labels, end_points, reduce_loss=True, c=None):
+    """semisup_v1_sunrgbd.py:256-321 (model A): mean_B[(1 - is2D) * (mask + strong) + is2D * (W_r * reprojection +
+    W_s * surface) * SEMI_MULTIPLIER_FOR_WEAK_LOSS].  Forward values from the fused loss kernel (two launches: strong terms
+    on the parsed head output, reprojection on S_pred_box_reg).  The surface loss is SURVEY 8(f) "next": a non-zero
+    WEAK_WEIGHT_SURFACE raises.  get_iou_summary (metrics-only py_func) is not evaluated."""
+    from . import weak_losses
+    if float(c.WEAK_WEIGHT_SURFACE) != 0.0:
+        raise NotImplementedError('get_surface_loss (WEAK_WEIGHT_SURFACE != 0): SURVEY 8(f) next')
+    (y_seg, y_center, y_orient_cls, y_orient_reg, y_dims_cls, y_dims_reg, R0_rect, P, Rtilt, K, rot_frust, box2D, img_dim,
+     is_data_2D) = labels
+    reproj = weak_losses.get_reprojection_loss(
+        end_points['S_pred_box_reg'], box2D, Rtilt, K, img_dim, rot_frust,
+        use_softmax_projection=c.WEAK_REPROJECTION_USE_SOFTMAX_PROJ, softmax_scale_factor=c.WEAK_REPROJECTION_SOFTMAX_SCALE,
+        dilate_factor=c.WEAK_REPROJECTION_DILATE_FACTOR, clip_lower_b_loss=c.WEAK_REPROJECTION_CLIP_LOWERB_LOSS,
+        clip_pred_box=c.WEAK_REPROJECTION_CLIP_PRED_BOX, loss_type=c.WEAK_REPROJECTION_LOSS_TYPE,
+        train_box=c.WEAK_TRAIN_BOX_W_REPROJECTION, end_points=end_points, reduce_loss=False, scope='reprojection_loss')
+    mask_losses, strong_losses = get_strong_loss(pred, (y_seg, y_center, y_orient_cls, y_orient_reg, y_dims_cls, y_dims_reg),
+                                                 end_points, reduce_loss=False, c=c)
+    is2d = is_data_2D.to(torch.float32)
+    total_losses = (1.0 - is2d) * (mask_losses + strong_losses) + \
+        is2d * (float(c.WEAK_WEIGHT_REPROJECTION) * reproj * float(c.SEMI_MULTIPLIER_FOR_WEAK_LOSS))
+    return total_losses.mean() if reduce_loss else total_losses
+
+
 def get_semi_loss(pred, labels, end_points, reduce_loss=True, c=None):
     """semisup_v1_sunrgbd.py:248-254."""
+    if c.SEMI_MODEL == 'A':
+        return get_semi_loss_backbone(pred, labels, end_points, reduce_loss, c)
     if c.SEMI_MODEL == 'F':
         return get_semi_loss_final(pred, labels, end_points, reduce_loss, c)
     raise Exception('Not implemented SEMI_MODEL: %s' % c.SEMI_MODEL)
