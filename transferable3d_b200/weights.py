@@ -208,15 +208,15 @@ def calibrate_seg_logits(variables, scope, pc, one_hot=None, target_frac=0.4, ma
     return v, float(k), float(-k * thr)
 
 
-def standard_model_F(seed=42, num_channel=6, calib_frustums=4, calib_seed=999):
+def standard_model_F(seed=42, num_channel=6, calib_frustums=4, calib_seed=999, margin_std=2.0):
     """The synthetic model-F weight set used by tests and bench: Xavier weights (seed) with the
     seg logits calibrated on `calib_frustums` synthetic frustums (target 40 % masked-in,
     margin std 2.0)."""
     from . import synth
     v = make_weights_model_F(seed, num_channel)
     pc = synth.make_batch(calib_frustums, 2048, num_channel, seed=calib_seed)['pc']
-    v, k, shift = calibrate_seg_logits(v, 'class_agnostic/inst_seg', pc)
-    return v, {'margin_k': k, 'margin_shift': shift, 'target_frac': 0.4, 'margin_std': 2.0}
+    v, k, shift = calibrate_seg_logits(v, 'class_agnostic/inst_seg', pc, margin_std=margin_std)
+    return v, {'margin_k': k, 'margin_shift': shift, 'target_frac': 0.4, 'margin_std': margin_std}
 
 
 def standard_model_A(seed=42, num_channel=6, use_one_hot=True, calib_frustums=4, calib_seed=999):
