@@ -28,7 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TOTAL_FRUSTUMS = {'cfg3': 8192, 'cfg2': 1024}
+TOTAL_FRUSTUMS = {'cfg3': 8192, 'cfg2': 1024, 'cfg1': 32}
 N_POINTS, N_CH = 2048, 6
 UNIQUE = 512            # unique synthetic frustums generated on the host, tiled to the workload size
 # algorithmic FLOPs (2*MAC) per point, SURVEY 8(d) / DESIGN.md
@@ -166,7 +166,7 @@ def run_reference(args):
         return
     workload = args.workload
     variables, _ = standard_variables(workload)
-    sample = args.ref_sample
+    sample = 32 if workload == 'cfg1' else args.ref_sample
     pc, oh = make_host_data(workload, sample, 1234 + (3 if workload == 'cfg3' else 2))
     torch.set_num_threads(os.cpu_count() or 1)
     vs = VarStore(variables)
@@ -177,6 +177,10 @@ def run_reference(args):
         with torch.no_grad():
             if workload == 'cfg3':
                 oracle_cfg3(vs, pc_t, oh_t)
+            elif workload == 'cfg1':
+                from oracle import test_semisup as ots
+                from transferable3d_b200 import config
+                ots.run_graph(vs, config.cfg(), pc_t, oh_t)
             else:
                 from oracle import semisup_models as osm
                 with vs.variable_scope('class_agnostic'):
@@ -228,7 +232,8 @@ def workload_config(workload, args, sample_note=None):
     c = {'workload': ('cfg3: Frustum PointNet v1 pipeline inference (seg -> mask/centroid/resample 512 -> T-Net -> '
                       'box-est NH=12 NS=10), 8192 frustums x 2048 pts x 6 ch + one-hot %s, frustums sharded over the GPUs, '
                       'no collective' % ('per GPU' if args.scaling == 'weak' else 'in total'))
-         if workload == 'cfg3' else 'cfg2: instance-seg per-point MLP chain alone, 1024 frustums x 2048 pts x 6 ch per GPU',
+         if workload == 'cfg3' else ('cfg1: semisup_v1_sunrgbd model F + 1 BoxPC refine, eval, batch 32 x 2048 pts x 6 ch' if workload == 'cfg1'
+                                     else 'cfg2: instance-seg per-point MLP chain alone, 1024 frustums x 2048 pts x 6 ch per GPU'),
          'global_frustums': TOTAL_FRUSTUMS[workload] * (1 if (workload == 'cfg3' and args.scaling == 'strong') else args.gpus),
          'frustums_per_gpu': TOTAL_FRUSTUMS[workload] // (args.gpus if (workload == 'cfg3' and args.scaling == 'strong') else 1),
          'num_point': N_POINTS, 'num_channel': N_CH, 'chunk_frustums': args.resident_chunk, 'e2e_chunk_frustums': args.chunk, 'parallelism': 'shard%d' % args.gpus,
@@ -240,6 +245,77 @@ def workload_config(workload, args, sample_note=None):
     return c
 
 
+# ------------------------------------------------------------------------------------------ cfg1 (the reference's own batch-32 case)
+
+def run_cfg1(args):
+    """BASELINE cfg1: semisup_v1_sunrgbd model F + one BoxPC refine, eval mode, batch 32, through test_semisup.get_model /
+    sess.run with the fetch list of test_semisup.inference (test_semisup.py:210-226).  A step = one batch of 32 frustums.
+    value: inputs resident on the device, CUDA-graph replay; e2e: numpy feed in, fetched tensors back on the host."""
+    import torch
+    from transferable3d_b200 import weights, config, runtime as rt, test_semisup as ts
+    assert args.gpus == 1 and int(os.environ.get('WORLD_SIZE', '1')) == 1, 'cfg1 is a single-GPU latency case'
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+    B = TOTAL_FRUSTUMS['cfg1']
+    variables, _ = weights.standard_model_F()
+    FLAGS = config.cfg()
+    rt.set_precision('bf16')
+    pc_h, oh_h = make_host_data('cfg1', B, 1235)
+    fetch = ['logits', 'F2_center', 'F2_heading_scores', 'F2_heading_residuals', 'F2_size_scores', 'F2_size_residuals', 'boxpc_fit_prob']
+    res = {}
+    for name, graph in (('graph', True), ('eager', False)):
+        sess, ops = ts.get_model(B, N_POINTS, N_CH, FLAGS, variables, device=dev, cuda_graph=graph)
+        pc_d, oh_d = torch.as_tensor(pc_h).to(dev), torch.as_tensor(oh_h).to(dev)
+        feed_d = {ops['pc_pl']: pc_d, ops['one_hot_vec_pl']: oh_d, ops['is_training_pl']: False}
+        feed_h = {ops['pc_pl']: pc_h, ops['one_hot_vec_pl']: oh_h, ops['is_training_pl']: False}
+
+        def timed(fn):
+            for _ in range(max(args.warmup, 3)):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(args.steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
+        ms = timed(lambda: sess.run(fetch, feed_d))
+        ms_e2e = timed(lambda: [t.cpu() for t in sess.run(fetch, feed_h)])
+        res[name] = (ms, ms_e2e)
+    ms, ms_e2e = res['graph']
+    d2h = sum(int(np.prod(s_)) * 4 for s_ in ((B, N_POINTS, 2), (B, 3), (B, 12), (B, 12), (B, 10), (B, 10, 3), (B,)))
+    flops_fr = (FLOP_SEG1_PT + FLOP_SEG2_PT + FLOP_TNET_PT + FLOP_BOX_PT + 363520) * N_POINTS   # dense upper bound: masked stacks run compacted
+    line = {'metric': 'frustums_per_sec', 'value': B / ms * 1e3, 'unit': 'frustums/s', 'n_gpus': 1, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'cfg1: semisup_v1_sunrgbd model F + 1 BoxPC refine, eval, batch 32 x 2048 pts x 6 ch, '
+                                   'test_semisup.get_model / sess.run, CUDA-graph replay', 'batch': B, 'num_point': N_POINTS,
+                       'l2': 'latency case: 1.5 MB of inputs per step, L2-resident by nature'},
+            'e2e': {'value': B / ms_e2e * 1e3, 'unit': 'frustums/s', 'h2d_bytes_per_step': pc_h.nbytes + oh_h.nbytes,
+                    'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e},
+            'eager_launch_path': {'ms_per_step': res['eager'][0], 'e2e_ms_per_step': res['eager'][1]},
+            'gpu_launches': None, 'roofline': None, 'dense_tflops_upper_bound': B / ms * 1e3 * flops_fr / 1e12}
+    if not args.no_cpu_baseline:
+        from oracle.tf_layers import VarStore
+        from oracle import test_semisup as ots
+        torch.set_num_threads(os.cpu_count() or 1)
+        vs = VarStore(variables)
+        vs.literal = True
+        pc_t, oh_t = torch.as_tensor(pc_h), torch.as_tensor(oh_h)
+        with torch.no_grad():
+            ots.run_graph(vs, FLAGS, pc_t, oh_t)
+            t0, reps = time.perf_counter(), 0
+            while reps < 3 or time.perf_counter() - t0 < 10.0:
+                ots.run_graph(vs, FLAGS, pc_t, oh_t)
+                reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        line['cpu_baseline'] = {'value': B / dt, 'unit': 'frustums/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                'sample': '%d batches of 32, oracle restatement of the TF1 graph (literal conv6) on PyTorch-CPU' % reps}
+    print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------ B200 arm
 
 def main():
@@ -248,7 +324,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='t3d', choices=['t3d', 'reference'])
-    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg2'])
+    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg2', 'cfg1'])
     ap.add_argument('--chunk', type=int, default=2048, help='frustums per chunk of the e2e (H2D/compute/D2H) pipeline')
     ap.add_argument('--resident-chunk', type=int, default=8192, help='frustums per pass when inputs are resident in HBM')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
@@ -263,6 +339,9 @@ def main():
         args.warmup = 3
     if args.impl == 'reference':
         run_reference(args)
+        return
+    if args.workload == 'cfg1':
+        run_cfg1(args)
         return
 
     import torch

@@ -266,6 +266,27 @@ def test_inference_runner_matches_oracle_runner(built_lib, setup):
         assert_close(res[6], ores[6], 1e-3, 1e-3, 'scores')
 
 
+@pytest.mark.parametrize('mode', ['bf16', 'fp32'])
+def test_session_cuda_graph_replay_equals_eager(built_lib, setup, mode):
+    """test_semisup.get_model builds a static-shape session like the TF graph it replaces; its CUDA-graph replay returns
+    exactly what the eager launch sequence returns, for successive feeds."""
+    b, FLAGS = setup['batch'], setup['FLAGS']
+    fetch = ['logits', 'F2_center', 'F2_heading_scores', 'F2_heading_residuals', 'F2_size_scores', 'F2_size_residuals', 'boxpc_fit_prob']
+    with rt.precision(mode):
+        sess_g, ops = ts.get_model(4, 2048, 6, FLAGS, setup['store'], cuda_graph=True)
+        sess_e, _ = ts.get_model(4, 2048, 6, FLAGS, setup['store'], cuda_graph=False)
+        for rep in range(3):
+            pc = np.roll(b['pc'], rep, axis=0)
+            oh = np.roll(b['one_hot'], rep, axis=0)
+            feed = {ops['pc_pl']: pc, ops['one_hot_vec_pl']: oh, ops['is_training_pl']: False}
+            got = sess_g.run(fetch, feed)
+            ref = sess_e.run(fetch, feed)
+            torch.cuda.synchronize()
+            assert sess_g._graph is not None
+            for k, g, r in zip(fetch, got, ref):
+                assert torch.equal(g, r), (mode, rep, k)
+
+
 def test_size_independent_properties_bf16(built_lib, setup):
     """Properties that hold at any size: the max-pool is invariant to the order of the points and to
     duplicated points, frustums are independent of their batch neighbours, empty mask -> zero features."""

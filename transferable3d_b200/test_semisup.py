@@ -11,7 +11,7 @@ import torch
 from . import runtime as rt
 from . import tf_util, semisup_v1_sunrgbd as MODEL, boxpc_sunrgbd
 from ._lib import ptr, stream, call
-from .constants import NUM_HEADING_BIN, NUM_SIZE_CLUSTER
+from .constants import NUM_HEADING_BIN, NUM_SIZE_CLUSTER, NUM_CLASS
 
 
 def build_graph(FLAGS, pc, one_hot_vec, box2D=None, img_dim=None, oracle_mask=None, is_training=False):
@@ -60,10 +60,35 @@ def build_graph(FLAGS, pc, one_hot_vec, box2D=None, img_dim=None, oracle_mask=No
 
 
 class Session(object):
-    """Stands in for the tf.Session of test_semisup.get_model: run(fetches, feed_dict)."""
+    """Stands in for the tf.Session of test_semisup.get_model: run(fetches, feed_dict).
 
-    def __init__(self, FLAGS, store, use_oracle_mask=False):
+    Like the TF1 graph it replaces, a session is built for one static (batch_size, num_point, num_channel)
+    (test_semisup.py:61-66): with cuda_graph=True the whole eval-mode forward (~40 kernel launches, launch-latency bound
+    at the reference's batch of 32, SURVEY 7) is captured once into a CUDA graph on first use and replayed per run();
+    feeds of any other shape take the eager launch path."""
+
+    def __init__(self, FLAGS, store, use_oracle_mask=False, batch_size=None, num_point=None, num_channel=None, cuda_graph=True):
         self.FLAGS, self.store, self.use_oracle_mask = FLAGS, store, use_oracle_mask
+        self.shape = (batch_size, num_point, num_channel)
+        self.cuda_graph = bool(cuda_graph) and None not in self.shape
+        self._graph = None
+
+    def _capture(self, with_mask):
+        dev = self.store.device
+        B, N, C = self.shape
+        self._pc = torch.zeros((B, N, C), dtype=torch.float32, device=dev)
+        self._oh = torch.zeros((B, NUM_CLASS), dtype=torch.float32, device=dev)
+        self._om = torch.zeros((B, N), dtype=torch.float32, device=dev) if with_mask else None
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():       # warm-up: weight packing, function attributes, allocator pools
+            for _ in range(2):
+                build_graph(self.FLAGS, self._pc, self._oh, oracle_mask=self._om)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g), torch.no_grad():
+            logits, ep = build_graph(self.FLAGS, self._pc, self._oh, oracle_mask=self._om)
+        self._graph, self._ep, self._with_mask = g, ep, with_mask
 
     def run(self, fetches, feed_dict):
         dev = self.store.device
@@ -75,6 +100,17 @@ class Session(object):
         one_hot = T(feed_dict['one_hot_vec_pl'])
         om = T(feed_dict['y_seg_pl']) if (self.use_oracle_mask and 'y_seg_pl' in feed_dict) else None
         rt.set_default_store(self.store)
+        if self.cuda_graph and tuple(pc.shape) == self.shape and rt.get_precision() == getattr(self, '_prec', rt.get_precision()):
+            if self._graph is None or self._with_mask != (om is not None):
+                self._prec = rt.get_precision()
+                self._capture(om is not None)
+            self._pc.copy_(pc)
+            self._oh.copy_(one_hot)
+            if om is not None:
+                self._om.copy_(om)
+            self._graph.replay()
+            # the graph's outputs are static buffers, overwritten by the next run(): hand out copies (sess.run returns values)
+            return [self._ep[f].clone() if isinstance(f, str) else f for f in fetches]
         with torch.no_grad():
             logits, ep = build_graph(self.FLAGS, pc, one_hot, oracle_mask=om)
         out = []
@@ -83,11 +119,11 @@ class Session(object):
         return out
 
 
-def get_model(batch_size, num_point, num_channel, FLAGS, variables, use_oracle_mask=False, device='cuda'):
+def get_model(batch_size, num_point, num_channel, FLAGS, variables, use_oracle_mask=False, device='cuda', cuda_graph=True):
     """test_semisup.get_model (test_semisup.py:61-179) -> (sess, ops). `variables` = {TF name: array}
     (what saver.restore would load, :158-159)."""
     store = variables if isinstance(variables, rt.VariableStore) else rt.VariableStore(variables, device)
-    sess = Session(FLAGS, store, use_oracle_mask)
+    sess = Session(FLAGS, store, use_oracle_mask, batch_size, num_point, num_channel, cuda_graph)
     ops = {k: k for k in ('pc_pl', 'one_hot_vec_pl', 'y_seg_pl', 'y_centers_pl', 'y_orient_cls_pl', 'y_orient_reg_pl',
                           'y_dims_cls_pl', 'y_dims_reg_pl', 'R0_rect_pl', 'P_pl', 'Rtilt_pl', 'K_pl', 'rot_frust_pl',
                           'box2D_pl', 'img_dim_pl', 'is_training_pl')}
