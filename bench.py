@@ -28,7 +28,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-TOTAL_FRUSTUMS = {'cfg3': 8192, 'cfg2': 1024, 'cfg1': 32}
+TOTAL_FRUSTUMS = {'cfg3': 8192, 'cfg2': 1024, 'cfg1': 32, 'cfg4': 256, 'cfg5': 256}
 N_POINTS, N_CH = 2048, 6
 UNIQUE = 512            # unique synthetic frustums generated on the host, tiled to the workload size
 # algorithmic FLOPs (2*MAC) per point, SURVEY 8(d) / DESIGN.md
@@ -165,26 +165,35 @@ def run_reference(args):
     if rank != 0:
         return
     workload = args.workload
-    variables, _ = standard_variables(workload)
-    sample = 32 if workload == 'cfg1' else args.ref_sample
-    pc, oh = make_host_data(workload, sample, 1234 + (3 if workload == 'cfg3' else 2))
     torch.set_num_threads(os.cpu_count() or 1)
-    vs = VarStore(variables)
-    vs.literal = True
-    pc_t, oh_t = torch.as_tensor(pc), torch.as_tensor(oh)
+    if workload in ('cfg4', 'cfg5'):
+        from oracle import train_boxpc as otb, train_semisup_adv as ota
+        sample = 8
+        v2, feed2, masks2, FLAGS2 = train_setup(workload, sample, N_POINTS, 77)
+        fn = otb.loss_and_grads if workload == 'cfg4' else ota.loss_and_grads
 
-    def step():
-        with torch.no_grad():
-            if workload == 'cfg3':
-                oracle_cfg3(vs, pc_t, oh_t)
-            elif workload == 'cfg1':
-                from oracle import test_semisup as ots
-                from transferable3d_b200 import config
-                ots.run_graph(vs, config.cfg(), pc_t, oh_t)
-            else:
-                from oracle import semisup_models as osm
-                with vs.variable_scope('class_agnostic'):
-                    osm.v1_inst_seg(pc_t, None, None, {}, False, vs, scope='inst_seg')
+        def step():
+            fn(v2, FLAGS2, feed2, masks2)
+    else:
+        variables, _ = standard_variables(workload)
+        sample = 32 if workload == 'cfg1' else args.ref_sample
+        pc, oh = make_host_data(workload, sample, 1234 + (3 if workload == 'cfg3' else 2))
+        vs = VarStore(variables)
+        vs.literal = True
+        pc_t, oh_t = torch.as_tensor(pc), torch.as_tensor(oh)
+
+        def step():
+            with torch.no_grad():
+                if workload == 'cfg3':
+                    oracle_cfg3(vs, pc_t, oh_t)
+                elif workload == 'cfg1':
+                    from oracle import test_semisup as ots
+                    from transferable3d_b200 import config
+                    ots.run_graph(vs, config.cfg(), pc_t, oh_t)
+                else:
+                    from oracle import semisup_models as osm
+                    with vs.variable_scope('class_agnostic'):
+                        osm.v1_inst_seg(pc_t, None, None, {}, False, vs, scope='inst_seg')
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -232,8 +241,10 @@ def workload_config(workload, args, sample_note=None):
     c = {'workload': ('cfg3: Frustum PointNet v1 pipeline inference (seg -> mask/centroid/resample 512 -> T-Net -> '
                       'box-est NH=12 NS=10), 8192 frustums x 2048 pts x 6 ch + one-hot %s, frustums sharded over the GPUs, '
                       'no collective' % ('per GPU' if args.scaling == 'weak' else 'in total'))
-         if workload == 'cfg3' else ('cfg1: semisup_v1_sunrgbd model F + 1 BoxPC refine, eval, batch 32 x 2048 pts x 6 ch' if workload == 'cfg1'
-                                     else 'cfg2: instance-seg per-point MLP chain alone, 1024 frustums x 2048 pts x 6 ch per GPU'),
+         if workload == 'cfg3' else {'cfg1': 'cfg1: semisup_v1_sunrgbd model F + 1 BoxPC refine, eval, batch 32 x 2048 pts x 6 ch',
+                                     'cfg2': 'cfg2: instance-seg per-point MLP chain alone, 1024 frustums x 2048 pts x 6 ch per GPU',
+                                     'cfg4': 'cfg4: train_boxpc BoxPC-Fit forward + backward, batch 256 x 2048 pts per GPU',
+                                     'cfg5': 'cfg5: train_semisup_adv model F training step, batch 256 x 2048 pts per GPU'}[workload],
          'global_frustums': TOTAL_FRUSTUMS[workload] * (1 if (workload == 'cfg3' and args.scaling == 'strong') else args.gpus),
          'frustums_per_gpu': TOTAL_FRUSTUMS[workload] // (args.gpus if (workload == 'cfg3' and args.scaling == 'strong') else 1),
          'num_point': N_POINTS, 'num_channel': N_CH, 'chunk_frustums': args.resident_chunk, 'e2e_chunk_frustums': args.chunk, 'parallelism': 'shard%d' % args.gpus,
@@ -316,6 +327,127 @@ def run_cfg1(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ cfg4 / cfg5 (training steps)
+
+CFG5_FLAGS = dict(SEMI_TRAIN_BOX_TRAIN_CLASS_AG_TNET=True, SEMI_TRAIN_BOX_TRAIN_CLASS_AG_BOX=True, SEMI_BOXPC_MIN_FIT_LOSS_AFT_REFINE=True,
+                  WEAK_WEIGHT_INTRACLASSVAR=2., WEAK_WEIGHT_REPROJECTION=0.01, WEAK_REPROJECTION_ONLY_ON_2D_CLS=True,
+                  SEMI_MULTIPLIER_FOR_WEAK_LOSS=0.05, SEMI_WEIGHT_BOXPC_FIT_LOSS=1.)
+
+
+def train_setup(workload, B, N, seed):
+    from transferable3d_b200 import weights, synth, config
+    rng = np.random.RandomState(seed)
+    if workload == 'cfg4':
+        v = weights.make_weights_boxpc()
+        feed = synth.make_boxpc_batch(B, N, N_CH, seed=seed)
+        masks = {'dp1': (rng.rand(B, 512) < 0.7).astype(np.float32), 'dp2': (rng.rand(B, 256) < 0.7).astype(np.float32)}
+        return v, feed, masks, config.cfg(BOXPC_WEIGHT_DELTA=4.)
+    v = weights.make_weights_model_F()
+    feed = synth.make_batch(B, N, N_CH, seed=seed, is_data_2D=(np.arange(B) % 2))
+    masks = {'class_agnostic/inst_seg/dp1': (rng.rand(B, N, 128) < 0.5).astype(np.float32),
+             'class_dependent/box_refine/dp0': (rng.rand(B, 512) < 0.5).astype(np.float32),
+             'class_dependent/box_refine/dp1': (rng.rand(B, 256) < 0.5).astype(np.float32)}
+    return v, feed, masks, config.cfg(**CFG5_FLAGS)
+
+
+def run_train(args):
+    """BASELINE cfg4 (train_boxpc: BoxPC-Fit forward + backward + Adam) / cfg5 (train_semisup_adv: model F training step with
+    the frozen BoxPC branch and the strong + reprojection + intra-class-variance + fit losses), batch 256 per GPU, data
+    parallel with ONE NCCL all-reduce of the flat gradient arena per step (weak scaling).  A step = one training step;
+    value = frustums/s with the batch resident on the device; e2e = numpy batch in (H2D inside) and the loss read back."""
+    import torch
+    import torch.distributed as dist
+    from transferable3d_b200 import train_boxpc as tb, train_semisup_adv as tsa
+    rank, world, local = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == args.gpus
+    workload, B, N = args.workload, TOTAL_FRUSTUMS[args.workload], N_POINTS
+    v, feed, masks, FLAGS = train_setup(workload, B, N, 1234 + (4 if workload == 'cfg4' else 5) + 100 * rank)
+    g = tb.BoxPCTrainGraph(v, FLAGS, B, N, N_CH, dev) if workload == 'cfg4' else tsa.SemiAdvTrainGraph(v, FLAGS, B, N, N_CH, dev)
+    if world > 1:      # identical replicas to start from
+        from transferable3d_b200.dist_util import broadcast_params
+        broadcast_params(g.flat_param if workload == 'cfg4' else g.arena.flat_param)
+    D = lambda a: torch.as_tensor(np.asarray(a)).to(dev)
+    feed_d = {k: D(a) for k, a in feed.items()}
+    masks_d = {k: D(a) for k, a in masks.items()}
+    loss_key = 'loss' if workload == 'cfg4' else 'semi_loss'
+    losses = []
+
+    def step_resident():
+        out = g.step(feed_d, masks_d)
+        losses.append(out[loss_key])
+
+    def step_e2e():
+        out = g.step(feed, masks_d)                 # numpy batch -> device inside the step; dropout masks are device RNG state
+        losses.append(float(out[loss_key].reshape(-1)[0]))
+
+    def timed(fn, sample_clocks=False):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks
+    ms, clocks = timed(step_resident, True)
+    first, last = float(losses[0].reshape(-1)[0]), float(losses[-1].reshape(-1)[0])
+    ms_e2e, _ = timed(step_e2e)
+    h2d = sum(np.asarray(a).nbytes for a in feed.values())
+    nparam = int((g.flat_param if workload == 'cfg4' else g.arena.flat_param).numel())
+    line = {'metric': 'frustums_per_sec', 'value': B * world / ms * 1e3, 'unit': 'frustums/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': ('cfg4: train_boxpc BoxPC-Fit (rep A) forward + backward + Adam' if workload == 'cfg4' else
+                                    'cfg5: train_semisup_adv model F step (reprojection + intra-class-variance + fit losses, frozen BoxPC)') +
+                       ', batch %d x %d pts per GPU, data parallel, one NCCL all-reduce of the flat fp32 gradient arena per step' % (B, N),
+                       'global_batch': B * world, 'allreduce_bytes': 4 * nparam, 'parallelism': 'dp%d' % world,
+                       'precision': 'fp32 CUDA-core kernels (parity-first training path)',
+                       'l2': 'activations of one step (> 2 GB) exceed the 126 MB L2'},
+            'clocks': clocks, 'e2e': {'value': B * world / ms_e2e * 1e3, 'unit': 'frustums/s', 'h2d_bytes_per_step': h2d,
+                                      'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e},
+            'loss_first_step': first, 'loss_last_step': last, 'gpu_launches': None, 'roofline': None}
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import train_boxpc as otb, train_semisup_adv as ota
+            torch.set_num_threads(os.cpu_count() or 1)
+            Bs = 8
+            v2, feed2, masks2, FLAGS2 = train_setup(workload, Bs, N, 77)
+            fn = otb.loss_and_grads if workload == 'cfg4' else ota.loss_and_grads
+            fn(v2, FLAGS2, feed2, masks2)
+            t0, reps = time.perf_counter(), 0
+            while reps < 2 or time.perf_counter() - t0 < 10.0:
+                fn(v2, FLAGS2, feed2, masks2)
+                reps += 1
+            dt = (time.perf_counter() - t0) / reps
+            line['cpu_baseline'] = {'value': Bs / dt, 'unit': 'frustums/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                    'sample': '%d steps of batch %d (forward + autograd backward, no optimizer), oracle restatement on PyTorch-CPU' % (reps, Bs)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------ B200 arm
 
 def main():
@@ -324,7 +456,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='t3d', choices=['t3d', 'reference'])
-    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg2', 'cfg1'])
+    ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg2', 'cfg1', 'cfg4', 'cfg5'])
     ap.add_argument('--chunk', type=int, default=2048, help='frustums per chunk of the e2e (H2D/compute/D2H) pipeline')
     ap.add_argument('--resident-chunk', type=int, default=8192, help='frustums per pass when inputs are resident in HBM')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
@@ -342,6 +474,9 @@ def main():
         return
     if args.workload == 'cfg1':
         run_cfg1(args)
+        return
+    if args.workload in ('cfg4', 'cfg5'):
+        run_train(args)
         return
 
     import torch
