@@ -104,6 +104,39 @@ int t3d_box3d_corners_helper(const float* centers, const float* headings, const 
 int t3d_box3d_corners_all(const float* center, const float* heading_res, const float* size_res, const float* mean_size,
                           const float* orient_anchors, int B, int NH, int NS, float* out, t3d_stream_t stream);
 
+/* ---- oriented 3D box IoU and the BoxPC perturbation sampler ------------------------------------------------------
+ * The reference calls box_util.box3d_iou (roi_seg_box3d_dataset.py:15,133; box_pc_fit_dataset.py:17,38-42), a module that is
+ * absent from its tree: it is train/box_util.py of charlesq34/frustum-pointnets (Sutherland-Hodgman clip of the
+ * bird's-eye-view rectangles, polygon area, overlap of the y extents); restated in oracle/box_util.py.
+ * get_3d_box (roi_seg_box3d_dataset.py:84-100): size (l,w,h), heading about y, center -> corners [B,8,3]. */
+int t3d_get_3d_box(const float* size, const float* heading, const float* center, int B, float* corners, t3d_stream_t stream);
+/* box3d_iou on corner sets [B,8,3] x [B,8,3] -> iou3d [B], iou2d [B] (either may be NULL) */
+int t3d_box3d_iou(const float* corners1, const float* corners2, int B, float* iou3d, float* iou2d, t3d_stream_t stream);
+/* roi_seg_box3d_dataset.compute_box3d_iou (:102-139), the py_func behind semisup_v1_sunrgbd.get_iou_summary (:232-246):
+ * argmax-select, class2angle / class2size, get_3d_box on prediction and label, box3d_iou -> iou2ds, iou3ds [B] */
+typedef struct {
+  const float *center_pred, *heading_logits, *heading_residuals, *size_logits, *size_residuals;
+  const float* center_label; const int* heading_class_label; const float* heading_residual_label;
+  const int* size_class_label; const float* size_residual_label;
+  const float* mean_size;      /* [NS,3] */
+  int B, NH, NS;
+  float *iou2ds, *iou3ds;
+} t3d_compute_iou_args;
+int t3d_compute_box3d_iou(const t3d_compute_iou_args* args /* host */, t3d_stream_t stream);
+/* BoxPCFitDataset.perturb_box_to_diff_ious (box_pc_fit_dataset.py:211-244): per box, draw (center, size, angle) perturbations
+ * scaled by 1 - mean(band) until the 3D IoU with the original lies strictly inside bounds[b] = (lo, hi).  Randomness:
+ * Philox4x32-10 keyed by seed with counter (attempt, 0|1, box, 0) -- see oracle/box_pc_fit_dataset.py.  attempts[b] = number
+ * of draws used, or -1 if max_attempts draws all missed the band (the reference would loop for ever). */
+typedef struct {
+  const float *center, *size, *heading, *bounds;    /* [B,3], [B,3], [B], [B,2] */
+  int B, max_attempts;
+  float center_perturbation, size_perturbation, angle_perturbation;
+  uint64_t seed;
+  float *new_center, *new_size, *new_heading, *iou3d, *d_center, *d_size, *d_angle;
+  int* attempts;
+} t3d_perturb_args;
+int t3d_perturb_boxes(const t3d_perturb_args* args /* host */, t3d_stream_t stream);
+
 /* ---- tcgen05 (bf16 in / fp32 accumulate) fused per-point MLP chains ------------------------------------
  * kind: 0 inst_seg conv1-5 + max (semisup_models.py:76-97), 1 tnet convs + max (:172-189, model_util.py:300-316),
  *       2 box_est convs + max (:224-245), 3 box_pc_mask_model convs + max with the BoxPC features computed

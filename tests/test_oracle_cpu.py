@@ -223,3 +223,64 @@ def test_golden_model_F_fixture():
     assert np.allclose(logits.numpy(), z['logits'], atol=2e-5)
     for k in ('F2_center', 'F_size_residuals', 'F_heading_scores', 'boxpc_fit_prob', 'stage1_center'):
         assert np.allclose(ep[k].numpy(), z[k], atol=2e-5), k
+
+
+# ---------------------------------------------------------------------------------------------- box_util (3D IoU) oracle
+def _obox(c, s, h):
+    from oracle import box_util as bu
+    return bu.get_3d_box(np.array(s, dtype=np.float64), h, np.array(c, dtype=np.float64))
+
+
+def test_box3d_iou_closed_forms():
+    """oracle/box_util.py restates the un-shipped box_util of the reference's upstream; pinned by closed forms."""
+    from oracle import box_util as bu
+    a = _obox([0, 0, 0], [2, 1, 1], 0.3)
+    assert np.allclose(bu.box3d_iou(a, a), (1.0, 1.0))
+    # shifted by half the length along x: intersection 1 of volume 2 + 2 - 1
+    assert np.allclose(bu.box3d_iou(_obox([0, 0, 0], [2, 1, 1], 0.0), _obox([1, 0, 0], [2, 1, 1], 0.0)), (1 / 3, 1 / 3))
+    # the 2 x 1 footprint rotated by 90 degrees: BEV intersection 1 x 1
+    assert np.allclose(bu.box3d_iou(_obox([0, 0, 0], [2, 1, 1], 0.0), _obox([0, 0, 0], [2, 1, 1], np.pi / 2)), (1 / 3, 1 / 3))
+    assert np.allclose(bu.box3d_iou(_obox([0, 0, 0], [2, 1, 1], 0.0), _obox([5, 0, 0], [2, 1, 1], 0.0)), (0.0, 0.0))
+    # half-height shift along y leaves the BEV IoU at 1
+    assert np.allclose(bu.box3d_iou(_obox([0, 0, 0], [2, 1, 1], 0.0), _obox([0, 0.5, 0], [2, 1, 1], 0.0)), (1 / 3, 1.0))
+    # containment: small box inside a big one -> vol_small / vol_big
+    assert np.allclose(bu.box3d_iou(_obox([0, 0, 0], [4, 4, 4], 0.7), _obox([0.2, 0.1, -0.3], [1, 1, 1], 0.7))[0], 1 / 64)
+
+
+def test_box3d_iou_symmetry_and_monte_carlo():
+    from oracle import box_util as bu
+    rng = np.random.RandomState(0)
+    for _ in range(4):
+        c1, s1, h1 = rng.uniform(-0.3, 0.3, 3), rng.uniform(0.5, 2, 3), rng.uniform(-3, 3)
+        c2, s2, h2 = rng.uniform(-0.3, 0.3, 3), rng.uniform(0.5, 2, 3), rng.uniform(-3, 3)
+        i3, i2 = bu.box3d_iou(_obox(c1, s1, h1), _obox(c2, s2, h2))
+        j3, j2 = bu.box3d_iou(_obox(c2, s2, h2), _obox(c1, s1, h1))
+        assert abs(i3 - j3) < 1e-12 and abs(i2 - j2) < 1e-12
+        P = rng.uniform(-2.2, 2.2, (200000, 3))
+
+        def inside(c, s, h):
+            d = P - c
+            co, si = np.cos(h), np.sin(h)
+            x, z = co * d[:, 0] - si * d[:, 2], si * d[:, 0] + co * d[:, 2]           # inverse of roty
+            return (np.abs(x) <= s[0] / 2) & (np.abs(d[:, 1]) <= s[2] / 2) & (np.abs(z) <= s[1] / 2)
+        a, b = inside(c1, s1, h1), inside(c2, s2, h2)
+        assert abs(i3 - (a & b).sum() / max((a | b).sum(), 1)) < 0.02
+
+
+def test_perturb_box_to_diff_ious_bands_and_streams():
+    """box_pc_fit_dataset.py:211-244: accepted IoUs lie strictly inside the band; the philox stream is reproducible and
+    the numpy_legacy mode consumes numpy's global-style stream (7 uniforms per attempt)."""
+    from oracle import box_pc_fit_dataset as od
+    c, s, h = np.array([0.1, 0.2, 3.0]), np.array([1.9, 1.2, 0.9]), 0.4
+    for band in ([0.7, 1.0], [0.01, 0.25]):
+        r = od.perturb_box_to_diff_ious(c, s, h, band, rng_mode='philox', seed=9, box_index=3)
+        assert band[0] < r[3] < band[1] and r[7] >= 1
+        r2 = od.perturb_box_to_diff_ious(c, s, h, band, rng_mode='philox', seed=9, box_index=3)
+        assert np.array_equal(r[0], r2[0]) and r[7] == r2[7]
+        rng = np.random.RandomState(5)
+        r3 = od.perturb_box_to_diff_ious(c, s, h, band, rng_mode='numpy_legacy', rng=rng)
+        assert band[0] < r3[3] < band[1]
+        ref = np.random.RandomState(5)
+        ref.uniform(size=7 * r3[7])
+        assert rng.uniform() == ref.uniform()                     # exactly 7 draws per attempt were consumed
+        assert np.allclose(r3[0], c + r3[4]) and np.allclose(r3[1], s + r3[5]) and np.isclose(r3[2], h + r3[6])

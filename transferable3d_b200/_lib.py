@@ -53,6 +53,18 @@ class t3d_semi_loss_args(_c.Structure):
                 [(n, _P) for n in ('dF', 'ds1', 'g_reg', 'dfit', 'per_sample', 'total')])
 
 
+class t3d_compute_iou_args(_c.Structure):
+    _fields_ = ([(n, _P) for n in ('center_pred', 'heading_logits', 'heading_residuals', 'size_logits', 'size_residuals', 'center_label',
+                                   'heading_class_label', 'heading_residual_label', 'size_class_label', 'size_residual_label', 'mean_size')] +
+                [('B', _I), ('NH', _I), ('NS', _I), ('iou2ds', _P), ('iou3ds', _P)])
+
+
+class t3d_perturb_args(_c.Structure):
+    _fields_ = ([(n, _P) for n in ('center', 'size', 'heading', 'bounds')] + [('B', _I), ('max_attempts', _I)] +
+                [(n, _c.c_float) for n in ('center_perturbation', 'size_perturbation', 'angle_perturbation')] + [('seed', _c.c_uint64)] +
+                [(n, _P) for n in ('new_center', 'new_size', 'new_heading', 'iou3d', 'd_center', 'd_size', 'd_angle', 'attempts')])
+
+
 _L = _c.c_longlong
 _F = _c.c_float
 
@@ -100,6 +112,10 @@ SIGNATURES = {
     't3d_act_bwd': (_I, [_P, _P, _L, _I, _P]),
     't3d_rowmask_mul': (_I, [_P, _P, _P, _L, _I, _P]),
     't3d_group_sum': (_I, [_P, _I, _I, _I, _F, _P, _P]),
+    't3d_get_3d_box': (_I, [_P, _P, _P, _I, _P, _P]),
+    't3d_box3d_iou': (_I, [_P, _P, _I, _P, _P, _P]),
+    't3d_compute_box3d_iou': (_I, [_c.POINTER(t3d_compute_iou_args), _P]),
+    't3d_perturb_boxes': (_I, [_c.POINTER(t3d_perturb_args), _P]),
 }
 
 _lib = None

@@ -7,6 +7,7 @@
 #include "seg_stage2_pipe.cuh"
 #include "train_ops.cuh"
 #include "loss_ops.cuh"
+#include "box_ops.cuh"
 
 using namespace t3d;
 
@@ -162,6 +163,50 @@ extern "C" int t3d_box3d_corners_all(const float* center, const float* heading_r
   const int n = B * NH * NS;
   box3d_corners_all_kernel<<<(n + 127) / 128, 128, 0, S(stream)>>>(center, heading_res, size_res, mean_size, orient_anchors, B,
                                                                    NH, NS, out);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- oriented 3D IoU / BoxPC perturbation
+extern "C" int t3d_get_3d_box(const float* size, const float* heading, const float* center, int B, float* corners, t3d_stream_t stream) {
+  if (!size || !heading || !center || !corners) return T3D_ERR_ARG;
+  if (B <= 0) return T3D_ERR_SHAPE;
+  get_3d_box_kernel<<<(B + 127) / 128, 128, 0, S(stream)>>>(size, heading, center, B, corners);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_box3d_iou(const float* corners1, const float* corners2, int B, float* iou3d, float* iou2d, t3d_stream_t stream) {
+  if (!corners1 || !corners2 || (!iou3d && !iou2d)) return T3D_ERR_ARG;
+  if (B <= 0) return T3D_ERR_SHAPE;
+  box3d_iou_kernel<<<(B + 127) / 128, 128, 0, S(stream)>>>(corners1, corners2, B, iou3d, iou2d);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_compute_box3d_iou(const t3d_compute_iou_args* a, t3d_stream_t stream) {
+  if (!a || !a->center_pred || !a->heading_logits || !a->heading_residuals || !a->size_logits || !a->size_residuals ||
+      !a->center_label || !a->heading_class_label || !a->heading_residual_label || !a->size_class_label ||
+      !a->size_residual_label || !a->mean_size || !a->iou2ds || !a->iou3ds)
+    return T3D_ERR_ARG;
+  if (a->B <= 0 || a->NH <= 0 || a->NS <= 0) return T3D_ERR_SHAPE;
+  ComputeIouArgs k{a->center_pred, a->heading_logits, a->heading_residuals, a->size_logits, a->size_residuals, a->center_label,
+                   a->heading_class_label, a->heading_residual_label, a->size_class_label, a->size_residual_label, a->mean_size,
+                   a->B, a->NH, a->NS, a->iou2ds, a->iou3ds};
+  compute_box3d_iou_kernel<<<(a->B + 127) / 128, 128, 0, S(stream)>>>(k);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_perturb_boxes(const t3d_perturb_args* a, t3d_stream_t stream) {
+  if (!a || !a->center || !a->size || !a->heading || !a->bounds || !a->new_center || !a->new_size || !a->new_heading ||
+      !a->iou3d || !a->d_center || !a->d_size || !a->d_angle || !a->attempts)
+    return T3D_ERR_ARG;
+  if (a->B <= 0 || a->max_attempts <= 0) return T3D_ERR_SHAPE;
+  PerturbArgs k{a->center, a->size, a->heading, a->bounds, a->B, a->max_attempts, a->center_perturbation, a->size_perturbation,
+                a->angle_perturbation, (unsigned long long)a->seed, a->new_center, a->new_size, a->new_heading, a->iou3d,
+                a->d_center, a->d_size, a->d_angle, a->attempts};
+  perturb_boxes_kernel<<<(a->B + 63) / 64, 64, 0, S(stream)>>>(k);
   T3D_CHECK_LAUNCH();
   return 0;
 }

@@ -147,11 +147,26 @@ def get_semi_loss_final(pred, labels, end_points, reduce_loss=True, c=None):
     return res['total'][0]
 
 
+def get_iou_summary(pred_box, y_box, end_points, name_prefix=''):
+    """semisup_v1_sunrgbd.py:236-246: the tf.py_func around roi_seg_box3d_dataset.compute_box3d_iou, here one GPU kernel
+    (box_util.compute_box3d_iou); sets end_points[name_prefix + 'iou2ds' / 'iou3ds'] (B,).
+    pred_box = (center, dims_cls scores, dims_reg (B,NS,3), orient_cls scores, orient_reg (B,NH));
+    y_box = (center, dims_cls, dims_reg, orient_cls, orient_reg) labels."""
+    from . import box_util
+    pred_center, pred_dims_cls, pred_dims_reg, pred_orient_cls, pred_orient_reg = pred_box
+    y_center, y_dims_cls, y_dims_reg, y_orient_cls, y_orient_reg = y_box
+    iou2ds, iou3ds = box_util.compute_box3d_iou(pred_center, pred_orient_cls, pred_orient_reg, pred_dims_cls, pred_dims_reg,
+                                                y_center, y_orient_cls, y_orient_reg, y_dims_cls, y_dims_reg)
+    end_points[name_prefix + 'iou2ds'] = iou2ds
+    end_points[name_prefix + 'iou3ds'] = iou3ds
+    return iou2ds, iou3ds
+
+
 def get_semi_loss_backbone(pred, labels, end_points, reduce_loss=True, c=None):
     """semisup_v1_sunrgbd.py:256-321 (model A): mean_B[(1 - is2D) * (mask + strong) + is2D * (W_r * reprojection +
     W_s * surface) * SEMI_MULTIPLIER_FOR_WEAK_LOSS].  Forward values from the fused loss kernel (two launches: strong terms
     on the parsed head output, reprojection on S_pred_box_reg).  The surface loss is SURVEY 8(f) "next": a non-zero
-    WEAK_WEIGHT_SURFACE raises.  get_iou_summary (metrics-only py_func) is not evaluated."""
+    WEAK_WEIGHT_SURFACE raises.  The metrics-only get_iou_summary of :316 is available separately (get_iou_summary)."""
     from . import weak_losses
     if float(c.WEAK_WEIGHT_SURFACE) != 0.0:
         raise NotImplementedError('get_surface_loss (WEAK_WEIGHT_SURFACE != 0): SURVEY 8(f) next')
