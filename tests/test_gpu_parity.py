@@ -266,6 +266,14 @@ def test_inference_runner_matches_oracle_runner(built_lib, setup):
         assert_close(res[6], ores[6], 1e-3, 1e-3, 'scores')
 
 
+def test_tf_util_max_pool2d(built_lib):
+    x = torch.randn(3, 257, 70, device=DEV)
+    got = tu.max_pool2d(x, [257, 1], scope='maxpool')
+    assert got.shape == (3, 1, 70) and torch.equal(got[:, 0], x.max(dim=1).values)
+    with pytest.raises(ValueError):
+        tu.max_pool2d(x, [2, 2])
+
+
 @pytest.mark.parametrize('mode', ['bf16', 'fp32'])
 def test_session_cuda_graph_replay_equals_eager(built_lib, setup, mode):
     """test_semisup.get_model builds a static-shape session like the TF graph it replaces; its CUDA-graph replay returns

@@ -51,6 +51,19 @@ def fully_connected(inputs, num_outputs, scope, bn=False, bn_decay=None, is_trai
     return y
 
 
+def max_pool2d(inputs, kernel_size, scope=None, stride=[2, 2], padding='VALID'):
+    """tf_util.max_pool2d (tf_util.py:1501-1524) as the hot path uses it: kernel [num_point, 1] over the point axis.
+    inputs (B,N,C) -> (B,1,C).  (Inside the fused chains the max is taken in the last layer's epilogue instead.)"""
+    B, N, C = inputs.shape
+    if int(kernel_size[0]) != N or int(kernel_size[1]) != 1:
+        raise ValueError('max_pool2d: only the [num_point, 1] pooling of the PointNet stacks is on the hot path')
+    x = rt.f32(inputs).reshape(B * N, C)
+    pooled = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    arg = torch.empty((B, C), dtype=torch.int32, device=x.device)
+    call('t3d_maxpool_fwd', ptr(x), B, N, C, ptr(pooled), ptr(arg), stream())
+    return pooled.reshape(B, 1, C)
+
+
 def dropout(inputs, is_training, scope, keep_prob=0.5, noise_shape=None):
     """tf_util.dropout (tf_util.py:1720-1741): identity when not training."""
     rt.require_eval(is_training)
