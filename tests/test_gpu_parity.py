@@ -54,9 +54,12 @@ def test_linear_f32(M, K, N, act, built_lib):
     assert_close(y.cpu().numpy(), ref.numpy(), 1e-5, 1e-5, 'linear')
 
 
-def test_linear_f32_group_bias_mask_and_max(built_lib):
+@pytest.mark.parametrize('n,K,N', [(192, 70, 130), (256, 64, 256), (48, 40, 70)])
+def test_linear_f32_group_bias_mask_and_max(n, K, N, built_lib):
+    """both tile sizes (sgemm.cuh 128 x 128 / simt_ops.cuh 64 x 64), group max by per-element atomics and by the per-tile
+    reduction (rows_per_group a multiple of the tile height)"""
     g = torch.Generator().manual_seed(3)
-    B, n, K, N = 5, 192, 70, 130
+    B = 5
     x = torch.randn(B * n, K, generator=g)
     w = torch.randn(K, N, generator=g) / np.sqrt(K)
     b = torch.randn(N, generator=g)

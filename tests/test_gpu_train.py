@@ -24,7 +24,12 @@ def _setup(B, N, seed=3):
 
 
 @pytest.mark.parametrize('M,N,K,ta,tb_,splitk', [(70, 130, 50, False, False, 1), (64, 64, 5000, True, False, 7),
-                                                   (300, 12, 128, False, True, 1), (33, 65, 1000, True, True, 4)])
+                                                   (300, 12, 128, False, True, 1), (33, 65, 1000, True, True, 4),
+                                                   # the 128 x 128-tile kernels (sgemm.cuh): all four stride variants, ragged
+                                                   # edges, unaligned leading strides (scalar loads), split-K
+                                                   (300, 200, 77, False, False, 1), (257, 129, 1030, True, False, 3),
+                                                   (128, 96, 4096, False, True, 5), (1000, 130, 513, True, True, 1),
+                                                   (256, 256, 256, False, False, 1)])
 def test_gemm_f32_strided(M, N, K, ta, tb_, splitk, built_lib):
     g = torch.Generator().manual_seed(M * 7 + K)
     A = torch.randn(M, K, generator=g)

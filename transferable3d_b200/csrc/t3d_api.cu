@@ -8,6 +8,8 @@
 #include "train_ops.cuh"
 #include "loss_ops.cuh"
 #include "box_ops.cuh"
+#define T3D_SGEMM_WITH_EPILOGUES
+#include "sgemm.cuh"
 
 using namespace t3d;
 
@@ -45,6 +47,13 @@ extern "C" int t3d_linear_f32(const float* X, int ldx, const float* W, int ldw, 
   if (M <= 0 || K <= 0 || N <= 0 || act < 0 || act > 3) return T3D_ERR_SHAPE;
   if ((gbias || gmax) && rows_per_group <= 0) return T3D_ERR_SHAPE;
   LinearArgs a{X, ldx, W, ldw, bias, gbias, rows_per_group, Y, ldy, M, K, N, act, rowmask, gmax};
+  if (M >= 128 && N >= 96 && K >= 16) {      // 128 x 128 tiles (sgemm.cuh)
+    SgemmOperands o{X, ldx, 1, W, ldw, 1, M, N, K, (K + kSgBK - 1) / kSgBK * kSgBK, sg_aligned16(X, ldx) ? 1 : 0, sg_aligned16(W, ldw) ? 1 : 0};
+    dim3 grid((M + kSgBM - 1) / kSgBM, (N + kSgBN - 1) / kSgBN);
+    linear128_kernel<<<grid, 256, 0, S(stream)>>>(a, o);
+    T3D_CHECK_LAUNCH();
+    return 0;
+  }
   dim3 grid((M + 63) / 64, (N + 63) / 64);
   linear_f32_kernel<<<grid, 256, 0, S(stream)>>>(a);
   T3D_CHECK_LAUNCH();
@@ -418,6 +427,18 @@ extern "C" int t3d_gemm_f32(const float* A, long long sam, long long sak, const 
   if ((sam != 1 && sak != 1) || (sbk != 1 && sbn != 1)) return T3D_ERR_SHAPE;
   if (splitk > 1) T3D_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, S(stream)));
   GemmArgs a{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias};
+  if (M >= 128 && N >= 96 && K >= 16) {      // 128 x 128 tiles (sgemm.cuh)
+    const int kchunk = ((K + splitk - 1) / splitk + kSgBK - 1) / kSgBK * kSgBK;
+    const bool ak = (sak == 1), bk = (sbk == 1 && sbn != 1);
+    SgemmOperands o{A, sam, sak, B, sbk, sbn, M, N, K, kchunk, sg_aligned16(A, ak ? sam : sak) ? 1 : 0, sg_aligned16(B, bk ? sbn : sbk) ? 1 : 0};
+    dim3 grid((M + kSgBM - 1) / kSgBM, (N + kSgBN - 1) / kSgBN, splitk);
+    if (ak && bk) gemm128_kernel<true, true><<<grid, 256, 0, S(stream)>>>(a, o);
+    else if (ak) gemm128_kernel<true, false><<<grid, 256, 0, S(stream)>>>(a, o);
+    else if (bk) gemm128_kernel<false, true><<<grid, 256, 0, S(stream)>>>(a, o);
+    else gemm128_kernel<false, false><<<grid, 256, 0, S(stream)>>>(a, o);
+    T3D_CHECK_LAUNCH();
+    return 0;
+  }
   dim3 grid((M + 63) / 64, (N + 63) / 64, splitk);
   gemm_f32_kernel<<<grid, 256, 0, S(stream)>>>(a);
   T3D_CHECK_LAUNCH();
