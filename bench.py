@@ -457,7 +457,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='t3d', choices=['t3d', 'reference'])
     ap.add_argument('--workload', default='cfg3', choices=['cfg3', 'cfg2', 'cfg1', 'cfg4', 'cfg5'])
-    ap.add_argument('--chunk', type=int, default=2048, help='frustums per chunk of the e2e (H2D/compute/D2H) pipeline')
+    ap.add_argument('--chunk', type=int, default=4096, help='frustums per chunk of the e2e (H2D/compute/D2H) pipeline')
     ap.add_argument('--resident-chunk', type=int, default=8192, help='frustums per pass when inputs are resident in HBM')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: every GPU processes the full cfg3 batch of 8192 frustums (no data-path collective); '
@@ -571,7 +571,8 @@ def main():
     in_bufs = [(torch.empty((chunk, N_POINTS, N_CH), device=dev), torch.empty((chunk, 10), device=dev)) for _ in range(2)]
     stage_out, host_out = [{}, {}], [{}, {}]
     bytes_io = {'h2d': 0, 'd2h': 0}
-    carry = {'ready0': None, 'consumed': [None, None]}     # the next step's first H2D is issued under this step's last chunk
+    # the next step's first H2D is issued under this step's last chunk; D2H copies drain under the next step's compute
+    carry = {'ready0': None, 'consumed': [None, None], 'drained': [None, None]}
 
     def step_e2e():
         comp = torch.cuda.current_stream()
@@ -579,8 +580,7 @@ def main():
         nchunks = n_local // chunk
         ready = [None, None]
         consumed = carry['consumed']
-        drained = [None, None]          # the D2H of the staging set has finished
-        outs_done = []
+        drained = carry['drained']      # the D2H of the staging set has finished
 
         def issue_copy(i):
             s = i % 2
@@ -632,11 +632,15 @@ def main():
                     e3 = torch.cuda.Event()
                     e3.record(back_s)
                     drained[s] = e3
-                    outs_done.append(e3)
-        for e in outs_done[-2:]:
-            comp.wait_event(e)
 
-    def timed(fn, steps, warmup, sample_clocks=False):
+    def e2e_finish():
+        """before the closing timestamp: every result of every timed step is on the host"""
+        comp = torch.cuda.current_stream()
+        for e in carry['drained']:
+            if e is not None:
+                comp.wait_event(e)
+
+    def timed(fn, steps, warmup, sample_clocks=False, finish=None):
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
@@ -651,6 +655,8 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -668,7 +674,7 @@ def main():
     ms, n_launch, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
     dom['on'] = False
     dom_ms = [a.elapsed_time(b) for a, b in dom['events'][-(args.steps * (n_local // rchunk)):]]
-    ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup, finish=e2e_finish)
 
     if args.breakdown and rank == 0:
         bd['on'] = True
