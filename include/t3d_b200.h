@@ -173,6 +173,13 @@ int t3d_seg_stage2_bf16(const void* point_feat /* bf16 [B*N,64] */, const float*
  * splitk > 1 accumulates partial sums atomically (C is zeroed by the call). */
 int t3d_gemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
                  int ldc, int M, int N, int K, int splitk, const float* bias, t3d_stream_t stream);
+/* Engine behind t3d_linear_f32 / t3d_gemm_f32 for problems with M >= 128, N >= 64, K >= 32 (process-wide setting):
+ *   1 (default) = tcgen05 tensor cores with every fp32 operand split exactly into three bf16 pieces and the six leading
+ *                 partial products accumulated in fp32 (csrc/xgemm.cuh): fp32-level accuracy at 1/6 of the bf16 rate;
+ *   0           = CUDA-core SGEMM (csrc/sgemm.cuh).
+ * The reference computes these layers with tf.nn.conv2d / tf.matmul in fp32 (models/tf_util.py:1308,1489). */
+int t3d_set_f32_engine(int engine);
+int t3d_get_f32_engine(void);
 /* mode 0: o0 = sum_r d, o1 = sum_r d^2 with d = x - y[c] when y != NULL (a per-column shift, e.g. row 0 of X: keeps the
  * variance E[d^2] - E[d]^2 free of cancellation), else d = x; mode 1: o0 = sum_r dy, o1 = sum_r dy*xhat with dy = X*act'(out), xhat=(y-mean)*rstd
  * (act = the T3D_ACT_* the forward applied after the batch norm) */

@@ -1,0 +1,154 @@
+"""-m gpu: the tcgen05 "bf16 x 3" fp32 GEMM (csrc/xgemm.cuh) behind t3d_gemm_f32 / t3d_linear_f32, through the C ABI.
+
+The checker is a float64 matmul of the same fp32 inputs (test infrastructure only).  Bars:
+  * error of the tensor-core engine <= a few fp32 ulps of the row's |a|.|b| scale -- the same bar the CUDA-core SGEMM
+    is held to, and both engines are measured side by side;
+  * every operand layout of the training step (forward: A unit-k / B unit-n, dgrad: both unit-k, wgrad: both unit-row
+    with split-K), ragged M / N / K, the K tail, bias, split-K reductions;
+  * t3d_linear_f32 epilogues: bias, per-group bias, activations, row mask, group max with and without Y.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rt():
+    from transferable3d_b200 import runtime as rt
+    return rt
+
+
+def _gemm(A, sam, sak, Bm, sbk, sbn, M, N, K, bias=None, splitk=1):
+    from transferable3d_b200.train_layers import gemm
+    return gemm(A, sam, sak, Bm, sbk, sbn, M, N, K, bias=bias, splitk=splitk)
+
+
+def _operands(M, N, K, a_unit_k, b_unit_k, seed):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    # wide dynamic range inside every dot product: exercises all three bf16 pieces
+    a = torch.randn(M, K, generator=g, device='cuda') * torch.exp(2.0 * torch.randn(M, K, generator=g, device='cuda'))
+    b = torch.randn(K, N, generator=g, device='cuda') * torch.exp(2.0 * torch.randn(K, N, generator=g, device='cuda'))
+    A = a.contiguous() if a_unit_k else a.t().contiguous()            # [M,K] or [K,M]
+    Bm = b.t().contiguous() if b_unit_k else b.contiguous()           # [N,K] or [K,N]
+    sam, sak = (K, 1) if a_unit_k else (1, M)
+    sbk, sbn = (1, K) if b_unit_k else (N, 1)
+    return a, b, A, sam, sak, Bm, sbk, sbn
+
+
+def _ulp_err(C, a, b):
+    ref = a.double() @ b.double()
+    scale = a.double().abs() @ b.double().abs()          # sum_k |a||b|: the natural error scale of a dot product
+    return float(((C.double() - ref).abs() / scale).max()) / 2.0 ** -24
+
+
+SHAPES = [(256, 128, 128), (384, 256, 96), (1000, 200, 333), (128, 64, 32), (130, 515, 70), (4096, 512, 256)]
+
+
+@pytest.mark.parametrize('a_unit_k,b_unit_k', [(True, False), (True, True), (False, False), (False, True)])
+@pytest.mark.parametrize('M,N,K', SHAPES)
+def test_gemm_layouts_fp32_accurate(M, N, K, a_unit_k, b_unit_k):
+    rt = _rt()
+    a, b, A, sam, sak, Bm, sbk, sbn = _operands(M, N, K, a_unit_k, b_unit_k, seed=M + N + K)
+    bias = torch.randn(N, device='cuda')
+    with rt.f32_engine('tc'):
+        C = _gemm(A, sam, sak, Bm, sbk, sbn, M, N, K)
+        Cb = _gemm(A, sam, sak, Bm, sbk, sbn, M, N, K, bias=bias)
+    with rt.f32_engine('simt'):
+        C0 = _gemm(A, sam, sak, Bm, sbk, sbn, M, N, K)
+    torch.cuda.synchronize()
+    e_tc, e_simt = _ulp_err(C, a, b), _ulp_err(C0, a, b)
+    # the bar is the CUDA-core fp32 SGEMM itself (K sequential roundings): measured 12.8 ulp of sum|a||b| at K = 128 on the
+    # worst of 32768 outputs, against 13.7 for the split
+    assert e_tc < max(4.0, 1.5 * e_simt), 'tcgen05 bf16x3: %.2f ulp of sum|a||b| (CUDA-core SGEMM: %.2f)' % (e_tc, e_simt)
+    assert torch.equal(Cb, C + bias)
+
+
+@pytest.mark.parametrize('splitk', [2, 7, 33])
+def test_wgrad_splitk(splitk):
+    rt = _rt()
+    M, N, K = 128, 256, 20000         # dW[Cin,Cout] = X^T dY over 20000 rows
+    a, b, A, sam, sak, Bm, sbk, sbn = _operands(M, N, K, False, False, seed=splitk)
+    with rt.f32_engine('tc'):
+        C = _gemm(A, sam, sak, Bm, sbk, sbn, M, N, K, splitk=splitk)
+        C1 = _gemm(A, sam, sak, Bm, sbk, sbn, M, N, K, splitk=1)
+    torch.cuda.synchronize()
+    e, e1 = _ulp_err(C, a, b), _ulp_err(C1, a, b)
+    assert e < 64.0 and e1 < 64.0, (e, e1)
+
+
+def test_exact_on_bf16_representable_inputs():
+    """Inputs with <= 8 significant bits and small integer values: every partial product and sum is exact."""
+    rt = _rt()
+    g = torch.Generator(device='cuda').manual_seed(3)
+    a = torch.randint(-8, 9, (512, 192), generator=g, device='cuda').float()
+    b = torch.randint(-8, 9, (192, 128), generator=g, device='cuda').float()
+    with rt.f32_engine('tc'):
+        C = _gemm(a.contiguous(), 192, 1, b.contiguous(), 128, 1, 512, 128, 192)
+    assert torch.equal(C, a @ b)
+
+
+def test_split_is_exact_for_full_mantissas():
+    """24-bit mantissas times a power of two: the product needs all three pieces of a."""
+    rt = _rt()
+    g = torch.Generator(device='cuda').manual_seed(4)
+    a = (torch.randint(2 ** 23, 2 ** 24, (256, 64), generator=g, device='cuda').float()) * 2.0 ** -20
+    b = torch.zeros(64, 128, device='cuda')
+    b[torch.arange(64), torch.arange(64)] = 4.0          # C[:, j] = 4 a[:, j] for j < 64
+    with rt.f32_engine('tc'):
+        C = _gemm(a.contiguous(), 64, 1, b.contiguous(), 128, 1, 256, 128, 64)
+    assert torch.equal(C[:, :64], 4.0 * a) and float(C[:, 64:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('act', [None, 'relu', 'leaky_relu', 'tanh'])
+def test_linear_epilogues(act):
+    rt = _rt()
+    G, R, K, N = 6, 256, 128, 200                     # 6 groups of 256 rows
+    M = G * R
+    g = torch.Generator(device='cuda').manual_seed(11)
+    x = torch.randn(M, K, generator=g, device='cuda')
+    w = torch.randn(K, N, generator=g, device='cuda') * 0.1
+    b = torch.randn(N, generator=g, device='cuda')
+    gb = torch.randn(G, N, generator=g, device='cuda')
+    rm = (torch.rand(M, generator=g, device='cuda') < 0.5).float()
+    pre = (x.double() @ w.double() + b.double()).view(G, R, N) + gb.double()[:, None, :]
+    f = {None: lambda v: v, 'relu': torch.relu, 'leaky_relu': lambda v: torch.where(v > 0, v, 0.2 * v), 'tanh': torch.tanh}[act]
+    ref = (f(pre) * rm.double().view(G, R, 1)).view(M, N)
+    with rt.f32_engine('tc'):
+        y, _ = rt.linear(x, w, b, act, gbias=gb, rows_per_group=R, rowmask=rm)
+    assert float((y.double() - ref).abs().max()) < 2e-5
+    if act == 'relu':
+        with rt.f32_engine('tc'):
+            y2, gmax = rt.linear(x, w, b, act, gbias=gb, rows_per_group=R, rowmask=rm, gmax_groups=G)
+            _, gmax_only = rt.linear(x, w, b, act, gbias=gb, rows_per_group=R, rowmask=rm, gmax_groups=G, want_y=False)
+            # groups that do not align with the 128-row tiles take the per-element path
+            _, gmax_ragged = rt.linear(x[:5 * 300], w, b, act, rows_per_group=300, gmax_groups=5, want_y=False)
+        assert torch.equal(y2, y)
+        assert torch.equal(gmax, y.view(G, R, N).max(dim=1).values.clamp_min(0.0))
+        assert torch.equal(gmax_only, gmax)
+        ref_r = torch.relu(x[:1500].double() @ w.double() + b.double()).view(5, 300, N).max(dim=1).values
+        assert float((gmax_ragged.double() - ref_r).abs().max()) < 2e-5
+
+
+def test_engines_agree_on_a_training_layer():
+    """forward / dgrad / wgrad of one 128 -> 256 layer over 32768 rows: tensor-core engine vs CUDA-core engine."""
+    rt = _rt()
+    M, K, N = 32768, 128, 256
+    g = torch.Generator(device='cuda').manual_seed(5)
+    x = torch.randn(M, K, generator=g, device='cuda')
+    w = torch.randn(K, N, generator=g, device='cuda') * 0.1
+    dy = torch.randn(M, N, generator=g, device='cuda')
+    out = {}
+    for eng in ('tc', 'simt'):
+        with rt.f32_engine(eng):
+            y = _gemm(x, K, 1, w, N, 1, M, N, K)
+            dx = _gemm(dy, N, 1, w, 1, N, M, K, N)
+            dw = _gemm(x, 1, K, dy, N, 1, K, N, M, splitk=37)
+        out[eng] = (y, dx, dw)
+    ref = (x.double() @ w.double(), dy.double() @ w.double().t(), x.double().t() @ dy.double())
+    for i, name in enumerate(('forward', 'dgrad', 'wgrad')):
+        scale = float(ref[i].abs().mean())
+        e_tc = float((out['tc'][i].double() - ref[i]).abs().max()) / scale
+        e_simt = float((out['simt'][i].double() - ref[i]).abs().max()) / scale
+        assert e_tc < 5e-6, '%s: tcgen05 engine %.3g of scale (CUDA cores %.3g)' % (name, e_tc, e_simt)
+        assert e_tc < 4.0 * e_simt + 1e-6, '%s: tcgen05 engine %.3g vs CUDA cores %.3g' % (name, e_tc, e_simt)

@@ -95,6 +95,8 @@ SIGNATURES = {
     't3d_seg_stage2_bf16': (_I, [_P, _P, _P, _P, _I, _I, _P]),
     't3d_set_trace_buffer': (_I, [_P]),
     't3d_gemm_f32': (_I, [_P, _L, _L, _P, _L, _L, _P, _I, _I, _I, _I, _I, _P, _P]),
+    't3d_set_f32_engine': (_I, [_I]),
+    't3d_get_f32_engine': (_I, []),
     't3d_colstats': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     't3d_bn_finalize': (_I, [_P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P]),
     't3d_bn_apply': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
@@ -137,6 +139,11 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        engine = os.environ.get('T3D_F32_ENGINE')       # 'simt' = CUDA-core SGEMM, 'tc' = tcgen05 bf16 x 3 (default)
+        if engine is not None:
+            if engine not in ('simt', 'tc'):
+                raise T3DError("T3D_F32_ENGINE must be 'simt' or 'tc'")
+            lib.t3d_set_f32_engine(1 if engine == 'tc' else 0)
         _lib = lib
     return _lib
 

@@ -10,6 +10,8 @@
 #include "box_ops.cuh"
 #define T3D_SGEMM_WITH_EPILOGUES
 #include "sgemm.cuh"
+#define T3D_XGEMM_WITH_EPILOGUES
+#include "xgemm.cuh"
 
 using namespace t3d;
 
@@ -40,6 +42,24 @@ extern "C" const char* t3d_error_string(int code) {
   return "t3d: unknown error";
 }
 
+// fp32 GEMM engine for tile-sized problems: 1 = tcgen05 "bf16 x 3" split (xgemm.cuh, fp32-accurate, default),
+// 0 = CUDA-core SGEMM (sgemm.cuh).  Process-wide configuration, not per-call state.
+static int g_f32_engine = 1;
+extern "C" int t3d_set_f32_engine(int engine) {
+  if (engine != 0 && engine != 1) return T3D_ERR_ARG;
+  g_f32_engine = engine;
+  return 0;
+}
+extern "C" int t3d_get_f32_engine(void) { return g_f32_engine; }
+
+template <typename Kern>
+static int xg_prepare(Kern kern) {      // opt in to 97 KB of dynamic shared memory (2 CTAs / SM)
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXgSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  return (int)e;
+}
+static inline bool xg_fits(int M, int N, int K) { return g_f32_engine == 1 && M >= 128 && N >= 64 && K >= 32; }
+
 extern "C" int t3d_linear_f32(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* gbias,
                               int rows_per_group, float* Y, int ldy, int M, int K, int N, int act, const float* rowmask,
                               float* gmax, t3d_stream_t stream) {
@@ -47,6 +67,15 @@ extern "C" int t3d_linear_f32(const float* X, int ldx, const float* W, int ldw, 
   if (M <= 0 || K <= 0 || N <= 0 || act < 0 || act > 3) return T3D_ERR_SHAPE;
   if ((gbias || gmax) && rows_per_group <= 0) return T3D_ERR_SHAPE;
   LinearArgs a{X, ldx, W, ldw, bias, gbias, rows_per_group, Y, ldy, M, K, N, act, rowmask, gmax};
+  if (xg_fits(M, N, K)) {                    // tensor cores, bf16 x 3 split (xgemm.cuh)
+    static int prepared = xg_prepare(xlinear_kernel);
+    if (prepared != 0) return prepared;
+    const int ntm = (M + kXgBM - 1) / kXgBM, ntn = (N + kXgBN - 1) / kXgBN;
+    XgOperands o{X, ldx, W, ldw, M, N, K, (K + kXgBK - 1) / kXgBK * kXgBK, xg_aligned16(X, ldx) ? 1 : 0, 0, ntn};
+    xlinear_kernel<<<dim3((unsigned)ntm * ntn, 1), kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+    T3D_CHECK_LAUNCH();
+    return 0;
+  }
   if (M >= 128 && N >= 96 && K >= 16) {      // 128 x 128 tiles (sgemm.cuh)
     SgemmOperands o{X, ldx, 1, W, ldw, 1, M, N, K, (K + kSgBK - 1) / kSgBK * kSgBK, sg_aligned16(X, ldx) ? 1 : 0, sg_aligned16(W, ldw) ? 1 : 0};
     dim3 grid((M + kSgBM - 1) / kSgBM, (N + kSgBN - 1) / kSgBN);
@@ -427,6 +456,31 @@ extern "C" int t3d_gemm_f32(const float* A, long long sam, long long sak, const 
   if ((sam != 1 && sak != 1) || (sbk != 1 && sbn != 1)) return T3D_ERR_SHAPE;
   if (splitk > 1) T3D_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, S(stream)));
   GemmArgs a{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias};
+  if (xg_fits(M, N, K)) {                    // tensor cores, bf16 x 3 split (xgemm.cuh)
+    static int prepared = xg_prepare(xgemm_kernel<true, true>) | xg_prepare(xgemm_kernel<true, false>) |
+                          xg_prepare(xgemm_kernel<false, true>) | xg_prepare(xgemm_kernel<false, false>);
+    if (prepared != 0) return prepared;
+    // The tensor core adds each 16-deep partial sum into the fp32 accumulator with truncation, a bias of ~0.5 ulp per
+    // step (measured: 700 ulp of sum|a||b| after K = 20000, 25 after K = 600); K chunks are kept <= 2048 so that long
+    // reductions (wgrad over B*N rows) are summed across chunks by round-to-nearest fp32 reductions instead.
+    int sk = splitk;
+    if ((K + sk - 1) / sk > kXgMaxKChunk) sk = (K + kXgMaxKChunk - 1) / kXgMaxKChunk;
+    if (sk > 1 && splitk == 1) T3D_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, S(stream)));
+    a.splitk = sk;
+    const int kchunk = ((K + sk - 1) / sk + kXgBK - 1) / kXgBK * kXgBK;
+    const int nz = (K + kchunk - 1) / kchunk;            // every K chunk non-empty
+    const bool ak = (sak == 1), bk = (sbk == 1 && sbn != 1);
+    const int ntm = (M + kXgBM - 1) / kXgBM, ntn = (N + kXgBN - 1) / kXgBN;
+    const long long lda = ak ? sam : sak, ldb = bk ? sbn : sbk;
+    XgOperands o{A, lda, B, ldb, M, N, K, kchunk, (ak && xg_aligned16(A, lda)) ? 1 : 0, (bk && xg_aligned16(B, ldb)) ? 1 : 0, ntn};
+    const dim3 grid((unsigned)ntm * ntn, nz);
+    if (ak && bk) xgemm_kernel<true, true><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+    else if (ak) xgemm_kernel<true, false><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+    else if (bk) xgemm_kernel<false, true><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+    else xgemm_kernel<false, false><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+    T3D_CHECK_LAUNCH();
+    return 0;
+  }
   if (M >= 128 && N >= 96 && K >= 16) {      // 128 x 128 tiles (sgemm.cuh)
     const int kchunk = ((K + splitk - 1) / splitk + kSgBK - 1) / kSgBK * kSgBK;
     const bool ak = (sak == 1), bk = (sbk == 1 && sbn != 1);

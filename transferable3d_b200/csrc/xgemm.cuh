@@ -1,0 +1,386 @@
+// fp32-accurate GEMM on the tcgen05 tensor cores ("bf16 x 3"): the core behind t3d_linear_f32 (fp32-mode layers) and
+// t3d_gemm_f32 (training-step forward / dgrad / wgrad) for every problem large enough to fill 128 x 128 tiles.
+//
+//   C[M,N] = sum_k A(m,k) B(k,n),  fp32 operands in HBM with element strides (one stride of each operand is 1).
+//
+// Each fp32 operand value x is split exactly into three bf16 pieces x = x1 + x2 + x3 (8 + 8 + 8 significant bits, by
+// truncation: x1 = top 16 bits of x, x2 = top 16 bits of x - x1, x3 = x - x1 - x2; every subtraction is exact), and the
+// product is evaluated as the six partial products whose weight is >= 2^-16 of the leading one:
+//     a1 b1                                 -> TMEM accumulator "main"
+//     a1 b2 + a2 b1 + a1 b3 + a2 b2 + a3 b1 -> TMEM accumulator "small" (2^-8 of main, so its rounding is invisible)
+// The dropped terms (a2 b3, a3 b2, a3 b3) are <= 2^-24 relative, i.e. below fp32 round-off; bf16 x bf16 products are
+// exact in the fp32 accumulator.  Cost: 6 tensor-core passes per fp32 FMA = 1/6 of the bf16 rate (~230 TFLOP/s of
+// fp32-equivalent work against ~35 TFLOP/s for the CUDA-core SGEMM of sgemm.cuh) at fp32-level accuracy.
+//
+// Structure (one 128 x 128 output tile per CTA, 2 CTAs per SM so one CTA's epilogue hides under the other's main loop):
+//   warps 0-3  load the A tile (128 rows x 32 k per stage), split it in registers, store the three bf16 images
+//   warps 4-7  same for the B tile (128 output columns x 32 k)
+//   warp  8    TMEM allocation + MMA issue (one elected lane): 2 k-steps x 6 tcgen05.mma per stage
+//   warps 0-7  epilogue after the main loop: tcgen05.ld of both accumulators, main + small, bias / activation / mask /
+//              group max / split-K atomics, 128-byte row segments straight to global memory
+// Operand images are K-major SWIZZLE_128B blocks [128 rows x 64 k] (the layout of common.cuh's descriptors); a stage is
+// one half (32 k = 16-byte chunks 4s..4s+3 of every row) of the block, so the two-stage ring costs no extra shared memory:
+// 6 images x 16 KB = 96 KB per CTA.
+#pragma once
+#include "common.cuh"
+
+namespace t3d {
+
+constexpr int kXgBM = 128, kXgBN = 128, kXgBK = 32;
+constexpr int kXgThreads = 288;
+constexpr int kXgMaxKChunk = 2048;                            // longest K range accumulated in TMEM by one CTA
+constexpr uint32_t kXgImage = 128 * 128;                       // bytes of one [128 x 64] bf16 image
+constexpr uint32_t kXgBars = 6 * kXgImage;                     // barrier block offset
+constexpr uint32_t kXgSmemBytes = 6 * kXgImage + 64 + 1024;    // + barriers / TMEM slot + 1024-byte alignment slack
+
+struct XgOperands {
+  const float* A; long long lda;      // UNIT_K: A(m,k) = A[m*lda + k];  else A(m,k) = A[k*lda + m]
+  const float* B; long long ldb;      // UNIT_K: B(k,n) = B[n*ldb + k];  else B(k,n) = B[k*ldb + n]
+  int M, N, K;
+  int kchunk;                         // K range of blockIdx.y: [y*kchunk, min(K, (y+1)*kchunk)), multiple of 32
+  int vecA, vecB;                     // 128-bit loads allowed for a UNIT_K operand (16-byte aligned base and ld % 4 == 0)
+  int ntn;                            // number of column tiles; blockIdx.x = m_tile * ntn + n_tile
+};
+
+// row of the tile handled by (warp w of the operand's 4, iteration i, lane) in the UNIT_K mapping: a warp-wide 128-bit
+// load covers 4 rows x 128 B (coalesced), and the 4 rows are r, r+4 (lanes 0-15) and r+1, r+5 (lanes 16-31) of an 8-row
+// swizzle atom: the 64-bit shared stores are issued per half-warp, and rows r / r+4 land in opposite 64-byte halves of
+// the 128-byte bank span (ncu: 37-52 % of the store wavefronts were bank conflicts with rows r, r+1 in one half-warp).
+__device__ __forceinline__ int xg_row_unit_k(int w, int i, int lane) {
+  const int rsub = lane >> 3;
+  return w * 32 + (i >> 1) * 8 + (i & 1) * 2 + (rsub & 1) * 4 + (rsub >> 1);
+}
+
+// One stage (128 rows x 32 k) of an operand tile into registers.  `p` is this thread's pointer for the stage:
+//   UNIT_K  : &P[(row0 + xg_row_unit_k(w, 0, lane)) * ld + k0 + 4 * (lane & 7)]; the 8 rows of the thread are
+//             +0, +2, +8, +10, +16, +18, +24, +26 rows from there (128-bit loads, a warp covers 4 rows x 128 B)
+//   !UNIT_K : &P[k0 * ld + row0 + w * 32 + lane]; 32 consecutive k (a warp reads 32 consecutive floats of one k)
+// `full` = every row and k of the stage is in range and (UNIT_K) 128-bit loads are allowed: no predicates.
+template <bool UNIT_K>
+__device__ __forceinline__ void xg_load(const float* __restrict__ p, long long ld, bool full, int row, int nrows, int k, int kend,
+                                        float (&r)[32]) {
+  if (UNIT_K) {
+    if (full) {
+      const long long ld2 = 2 * ld, ld6 = 6 * ld;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        p += (i & 1) ? ld6 : ld2;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int ro = (i >> 1) * 8 + (i & 1) * 2;
+        const float* q = p + (long long)ro * ld;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[4 * i + e] = (row + ro < nrows && k + e < kend) ? __ldg(q + e) : 0.0f;
+      }
+    }
+  } else {
+    if (full) {
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) { r[kk] = __ldg(p); p += ld; }
+    } else {
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) r[kk] = (row < nrows && k + kk < kend) ? __ldg(p + (long long)kk * ld) : 0.0f;
+    }
+  }
+}
+
+// x = h + m + l exactly, each piece a bf16 held in the top half of a 32-bit word
+__device__ __forceinline__ void xg_split(float x, uint32_t& h, uint32_t& m, uint32_t& l) {
+  h = __float_as_uint(x) & 0xffff0000u;
+  const float r = x - __uint_as_float(h);
+  m = __float_as_uint(r) & 0xffff0000u;
+  l = __float_as_uint(r - __uint_as_float(m));
+}
+__device__ __forceinline__ uint32_t xg_pack(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x7632); }   // top halves
+
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+// registers of xg_load -> the three bf16 images of stage s (img = shared address of image 1; 2 and 3 follow)
+template <bool UNIT_K>
+__device__ __forceinline__ void xg_split_store(uint32_t img, int s, int w, int lane, const float (&r)[32]) {
+  if (UNIT_K) {
+    const int c = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t h[4], m[4], l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) xg_split(r[4 * i + e], h[e], m[e], l[e]);
+      const uint32_t addr = img + sw128_offset((uint32_t)xg_row_unit_k(w, i, lane), (uint32_t)(4 * s + (c >> 1))) + (uint32_t)(c & 1) * 8u;
+      st_shared_v2(addr, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]));
+      st_shared_v2(addr + kXgImage, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]));
+      st_shared_v2(addr + 2 * kXgImage, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]));
+    }
+  } else {
+    const uint32_t row = (uint32_t)(w * 32 + lane);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t h[8], m[8], l[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) xg_split(r[8 * j + e], h[e], m[e], l[e]);
+      const uint32_t addr = img + sw128_offset(row, (uint32_t)(4 * s + j));
+      st_shared_v4(addr, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]), xg_pack(h[4], h[5]), xg_pack(h[6], h[7]));
+      st_shared_v4(addr + kXgImage, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]), xg_pack(m[4], m[5]), xg_pack(m[6], m[7]));
+      st_shared_v4(addr + 2 * kXgImage, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]), xg_pack(l[4], l[5]), xg_pack(l[6], l[7]));
+    }
+  }
+}
+
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {     // many threads poll: yield issue slots
+  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+}
+
+// One operand's loader warp: stage it+1 is in flight in registers while stage it is split and stored (two register
+// sets, ping-pong).  full0 / empty0 = the stage-0 barriers (stage 1 follows at +8 bytes).
+template <bool UNIT_K>
+__device__ __forceinline__ void xg_loader(const float* __restrict__ P, long long ld, int row0, int nrows, int kbeg, int kend, bool vec,
+                                          uint32_t img, int w, int lane, int nst, uint32_t full0, uint32_t empty0) {
+  const int row = row0 + (UNIT_K ? xg_row_unit_k(w, 0, lane) : w * 32 + lane);      // first (or only) row of this thread
+  const int kofs = UNIT_K ? 4 * (lane & 7) : 0;
+  const float* p = UNIT_K ? P + (long long)row * ld + kbeg + kofs : P + (long long)kbeg * ld + row;
+  const long long pstep = UNIT_K ? (long long)kXgBK : (long long)kXgBK * ld;
+  const bool rows_full = (row0 + w * 32 + 32 <= nrows) && (UNIT_K ? vec : true);
+  auto load = [&](int it, float (&r)[32]) {
+    const int k0 = kbeg + it * kXgBK;
+    xg_load<UNIT_K>(p + (long long)it * pstep, ld, rows_full && (k0 + kXgBK <= kend), row, nrows, k0 + kofs, kend, r);
+  };
+  auto emit = [&](int it, const float (&r)[32]) {
+    const int s = it & 1;
+    mbar_wait_backoff(empty0 + 8u * s, ((it >> 1) & 1) ^ 1);
+    xg_split_store<UNIT_K>(img, s, w, lane, r);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(full0 + 8u * s);
+  };
+  float ra[32], rb[32];
+  load(0, ra);
+  int it = 0;
+  for (; it + 1 < nst; it += 2) {
+    load(it + 1, rb);
+    emit(it, ra);
+    if (it + 2 < nst) load(it + 2, ra);
+    emit(it + 1, rb);
+  }
+  if (it < nst) emit(it, ra);
+}
+
+struct XgTile {
+  uint32_t sbase, tmem_base;
+  int m0, n0, warp, lane;
+};
+
+// Runs the main loop of one tile.  Returns in the 8 loader warps once both accumulators are complete in TMEM
+// (main: columns [0,128), small: [128,256) of the allocation; lane = tile row); warp 8 returns immediately after its
+// last commit.  Every thread must then call xg_finish().
+template <bool A_UNIT_K, bool B_UNIT_K>
+__device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_raw, XgTile& t) {
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = sbase + kXgBars;
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (2 + s); };
+  const uint32_t acc_full = bar0 + 32u;
+  const uint32_t tmem_slot = bar0 + 40u;
+  const int m0 = (int)(blockIdx.x / o.ntn) * kXgBM, n0 = (int)(blockIdx.x % o.ntn) * kXgBN;
+  const int kbeg = blockIdx.y * o.kchunk, kend = min(o.K, kbeg + o.kchunk);
+  const int nst = (kend - kbeg + kXgBK - 1) / kXgBK;
+
+  if (threadIdx.x == 0) {
+    mbar_init(full(0), 8); mbar_init(full(1), 8);
+    mbar_init(empty(0), 1); mbar_init(empty(1), 1);
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kXgBars + 40);
+  t.sbase = sbase; t.tmem_base = tmem_base; t.m0 = m0; t.n0 = n0; t.warp = warp; t.lane = lane;
+
+  if (warp < 8) {
+    // ---------------------------------------------------------------- loaders: global fp32 -> registers -> 3 bf16 images
+    if (warp < 4) xg_loader<A_UNIT_K>(o.A, o.lda, m0, o.M, kbeg, kend, o.vecA != 0, sbase, warp & 3, lane, nst, full(0), empty(0));
+    else xg_loader<B_UNIT_K>(o.B, o.ldb, n0, o.N, kbeg, kend, o.vecB != 0, sbase + 3u * kXgImage, warp & 3, lane, nst, full(0), empty(0));
+    mbar_wait_backoff(acc_full, 0);
+    tc_fence_after();
+  } else {
+    // ---------------------------------------------------------------- MMA issue (warp-convergent, one elected lane)
+    const int ncols = min(kXgBN, ((o.N - n0) + 15) & ~15);
+    const uint32_t idesc = make_idesc_bf16(128, ncols);
+    const uint32_t d_main = tmem_base, d_small = tmem_base + 128;
+    const uint32_t a_img = sbase, b_img = sbase + 3 * kXgImage;
+    for (int it = 0; it < nst; ++it) {
+      const int s = it & 1;
+      mbar_wait_w(full(s), (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t off = (uint32_t)(2 * s + ks) * 32u;
+        const uint64_t a1 = make_sdesc_k128(a_img + off), a2 = make_sdesc_k128(a_img + kXgImage + off),
+                       a3 = make_sdesc_k128(a_img + 2 * kXgImage + off);
+        const uint64_t b1 = make_sdesc_k128(b_img + off), b2 = make_sdesc_k128(b_img + kXgImage + off),
+                       b3 = make_sdesc_k128(b_img + 2 * kXgImage + off);
+        const uint32_t first = (it | ks) != 0;
+        umma_bf16_w(d_small, a3, b1, idesc, first);
+        umma_bf16_w(d_small, a1, b3, idesc, 1);
+        umma_bf16_w(d_small, a2, b2, idesc, 1);
+        umma_bf16_w(d_small, a2, b1, idesc, 1);
+        umma_bf16_w(d_small, a1, b2, idesc, 1);
+        umma_bf16_w(d_main, a1, b1, idesc, first);
+      }
+      umma_commit_w(empty(s));
+    }
+    umma_commit_w(acc_full);
+  }
+}
+
+// 32 accumulator columns [c0, c0+32) of this thread's row: main + small
+__device__ __forceinline__ void xg_acc32(const XgTile& t, int c0, float (&v)[32]) {
+  const uint32_t taddr = t.tmem_base + ((uint32_t)((t.warp & 3) * 32) << 16) + (uint32_t)c0;
+  uint32_t va[32], vb[32];
+  tmem_ld32(taddr, va);
+  tmem_ld32(taddr + 128, vb);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(va[j]) + __uint_as_float(vb[j]);
+}
+
+__device__ __forceinline__ void xg_finish(const XgTile& t) {
+  tc_fence_before();
+  __syncthreads();
+  if (t.warp == 8) tmem_dealloc<256>(t.tmem_base);
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+#ifdef T3D_XGEMM_WITH_EPILOGUES
+// ---- t3d_gemm_f32 (same contract as gemm_f32_kernel, train_ops.cuh): C = A.B (+ bias by split 0); split-K partial tiles
+// are added into a zero-initialised C with vector reductions.
+template <bool A_UNIT_K, bool B_UNIT_K>
+__global__ void __launch_bounds__(kXgThreads, 2) xgemm_kernel(const GemmArgs a, const XgOperands o) {
+  extern __shared__ uint8_t xg_smem[];
+  XgTile t;
+  xg_mainloop<A_UNIT_K, B_UNIT_K>(o, xg_smem, t);
+  if (t.warp < 8) {
+    const int gm = t.m0 + (t.warp & 3) * 32 + t.lane;
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      const int c0 = (t.warp >> 2) * 64 + ch * 32;
+      float v[32];
+      xg_acc32(t, c0, v);
+      if (gm < a.M) {
+        float* crow = a.C + (size_t)gm * a.ldc;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int gn = t.n0 + c0 + j;
+          if (gn >= a.N) break;
+          if (a.bias && blockIdx.y == 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (gn + e < a.N) v[j + e] += a.bias[gn + e];
+          }
+          float* c = crow + gn;
+          if (gn + 4 <= a.N && (((uintptr_t)c) & 15) == 0) {
+            if (a.splitk > 1) red_add_v4(c, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            else *reinterpret_cast<float4*>(c) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (gn + e < a.N) {
+                if (a.splitk > 1) atomicAdd(c + e, v[j + e]);
+                else c[e] = v[j + e];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  xg_finish(t);
+}
+
+// ---- t3d_linear_f32 (same contract as linear_f32_kernel, simt_ops.cuh): Y = act(X.W + bias + gbias[row / rows_per_group])
+// * rowmask, optional max over the rows of each group.
+__global__ void __launch_bounds__(kXgThreads, 2) xlinear_kernel(const LinearArgs a, const XgOperands o) {
+  extern __shared__ uint8_t xg_smem[];
+  XgTile t;
+  xg_mainloop<true, false>(o, xg_smem, t);
+  if (t.warp < 8) {
+    const int gm = t.m0 + (t.warp & 3) * 32 + t.lane;
+    const bool row_ok = gm < a.M;
+    const int g = (a.rows_per_group > 0 && row_ok) ? gm / a.rows_per_group : 0;
+    const float rm = (a.rowmask && row_ok) ? a.rowmask[gm] : 1.0f;
+    // the tile's 128 rows belong to one group: reduce over the warp's 32 rows in registers before the atomics
+    const bool one_group = a.gmax && (a.rows_per_group % kXgBM == 0) && (t.m0 + kXgBM <= a.M);
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      const int c0 = (t.warp >> 2) * 64 + ch * 32;
+      float v[32];
+      xg_acc32(t, c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int gn = t.n0 + c0 + j;
+        float x = v[j];
+        if (gn < a.N) {
+          if (a.bias) x += a.bias[gn];
+          if (a.gbias && row_ok) x += a.gbias[(size_t)g * a.N + gn];
+          x = apply_act(x, a.act) * rm;
+        } else {
+          x = 0.0f;
+        }
+        v[j] = x;
+      }
+      if (a.Y && row_ok) {
+        float* yrow = a.Y + (size_t)gm * a.ldy;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int gn = t.n0 + c0 + j;
+          if (gn >= a.N) break;
+          float* y = yrow + gn;
+          if (gn + 4 <= a.N && (((uintptr_t)y) & 15) == 0) {
+            *reinterpret_cast<float4*>(y) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (gn + e < a.N) y[e] = v[j + e];
+          }
+        }
+      }
+      if (a.gmax) {
+        if (one_group) {      // values are >= 0 here (ReLU / mask); lane c ends up with the max of column c0 + c
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (t.lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; ++j) {
+              const float send = upper ? v[j] : v[j + off];
+              const float keep = upper ? v[j + off] : v[j];
+              v[j] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+            }
+          }
+          const int gn = t.n0 + c0 + t.lane;
+          if (gn < a.N) atomic_max_f32(a.gmax + (size_t)(t.m0 / a.rows_per_group) * a.N + gn, v[0]);
+        } else if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gn = t.n0 + c0 + j;
+            if (gn < a.N) atomic_max_f32(a.gmax + (size_t)g * a.N + gn, v[j]);
+          }
+        }
+      }
+    }
+  }
+  xg_finish(t);
+}
+#endif
+
+inline bool xg_aligned16(const void* p, long long ld) { return (((uintptr_t)p & 15) == 0) && (ld % 4 == 0); }
+
+}  // namespace t3d

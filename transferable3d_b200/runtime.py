@@ -32,6 +32,28 @@ def get_precision():
     return _state['precision']
 
 
+def set_f32_engine(engine):
+    """Engine of the fp32 GEMMs (fp32-mode layers, training steps): 'tc' = tcgen05 bf16 x 3 split (fp32-accurate,
+    default), 'simt' = CUDA-core SGEMM.  See include/t3d_b200.h: t3d_set_f32_engine."""
+    if engine not in ('tc', 'simt'):
+        raise ValueError(engine)
+    _lib.check(_lib.load().t3d_set_f32_engine(1 if engine == 'tc' else 0))
+
+
+def get_f32_engine():
+    return 'tc' if _lib.load().t3d_get_f32_engine() == 1 else 'simt'
+
+
+@contextlib.contextmanager
+def f32_engine(engine):
+    old = get_f32_engine()
+    set_f32_engine(engine)
+    try:
+        yield
+    finally:
+        set_f32_engine(old)
+
+
 @contextlib.contextmanager
 def precision(mode):
     old = _state['precision']
