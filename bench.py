@@ -365,6 +365,8 @@ def run_train(args):
         dist.init_process_group('nccl', device_id=dev)
     assert world == args.gpus
     workload, B, N = args.workload, TOTAL_FRUSTUMS[args.workload], N_POINTS
+    from transferable3d_b200 import runtime as rt
+    rt.set_f32_engine(args.f32_engine)
     v, feed, masks, FLAGS = train_setup(workload, B, N, 1234 + (4 if workload == 'cfg4' else 5) + 100 * rank)
     g = tb.BoxPCTrainGraph(v, FLAGS, B, N, N_CH, dev) if workload == 'cfg4' else tsa.SemiAdvTrainGraph(v, FLAGS, B, N, N_CH, dev)
     if world > 1:      # identical replicas to start from
@@ -422,7 +424,12 @@ def run_train(args):
                                     'cfg5: train_semisup_adv model F step (reprojection + intra-class-variance + fit losses, frozen BoxPC)') +
                        ', batch %d x %d pts per GPU, data parallel, one NCCL all-reduce of the flat fp32 gradient arena per step' % (B, N),
                        'global_batch': B * world, 'allreduce_bytes': 4 * nparam, 'parallelism': 'dp%d' % world,
-                       'precision': 'fp32 CUDA-core kernels (parity-first training path)',
+                       'precision': {'tc': 'fp32 in HBM; GEMMs on tcgen05 with every operand split into 3 bf16 pieces, 6 partial products, '
+                                           'fp32 accumulate (fp32-accurate); BN / loss / Adam kernels fp32 on CUDA cores',
+                                     'simt': 'fp32 CUDA-core kernels throughout',
+                                     'bf16': 'fp32 in HBM; GEMM operands rounded to bf16, one tcgen05 pass, fp32 accumulate; '
+                                             'BN / loss / Adam kernels fp32'}[args.f32_engine],
+                       'f32_engine': args.f32_engine,
                        'l2': 'activations of one step (> 2 GB) exceed the 126 MB L2'},
             'clocks': clocks, 'e2e': {'value': B * world / ms_e2e * 1e3, 'unit': 'frustums/s', 'h2d_bytes_per_step': h2d,
                                       'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e},
@@ -462,6 +469,9 @@ def main():
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: every GPU processes the full cfg3 batch of 8192 frustums (no data-path collective); '
                          'strong: one global batch of 8192 split over the GPUs')
+    ap.add_argument('--f32-engine', default='tc', choices=['tc', 'simt', 'bf16'],
+                    help='GEMM engine of the training workloads (cfg4 / cfg5): tc = tcgen05 bf16 x 3 split (fp32-accurate), '
+                         'simt = CUDA-core SGEMM, bf16 = one tcgen05 pass on bf16-rounded operands')
     ap.add_argument('--ref-sample', type=int, default=8)
     ap.add_argument('--cpu-sample', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -176,7 +176,9 @@ int t3d_gemm_f32(const float* A, long long sam, long long sak, const float* B, l
 /* Engine behind t3d_linear_f32 / t3d_gemm_f32 for problems with M >= 128, N >= 64, K >= 32 (process-wide setting):
  *   1 (default) = tcgen05 tensor cores with every fp32 operand split exactly into three bf16 pieces and the six leading
  *                 partial products accumulated in fp32 (csrc/xgemm.cuh): fp32-level accuracy at 1/6 of the bf16 rate;
- *   0           = CUDA-core SGEMM (csrc/sgemm.cuh).
+ *   0           = CUDA-core SGEMM (csrc/sgemm.cuh);
+ *   2           = tcgen05 with the operands rounded once to bf16 (round to nearest) and fp32 accumulation: the bf16 mode
+ *                 of the training steps (rel 1e-2 class accuracy), one tensor-core pass instead of six.
  * The reference computes these layers with tf.nn.conv2d / tf.matmul in fp32 (models/tf_util.py:1308,1489). */
 int t3d_set_f32_engine(int engine);
 int t3d_get_f32_engine(void);

@@ -36,7 +36,7 @@ def main():
         dw = torch.empty(K, N, device='cuda')
         sk = splitk_for(K, N, M)
         flops = 2.0 * M * K * N
-        for eng in ('tc', 'simt'):
+        for eng in os.environ.get('ENGINES', 'tc,simt,bf16').split(','):
             with rt.f32_engine(eng):
                 t_f = timed(lambda: gemm(x, K, 1, w, N, 1, M, N, K, out=y))
                 t_d = timed(lambda: gemm(dy, N, 1, w, 1, N, M, K, N, out=dx))

@@ -139,11 +139,11 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        engine = os.environ.get('T3D_F32_ENGINE')       # 'simt' = CUDA-core SGEMM, 'tc' = tcgen05 bf16 x 3 (default)
+        engine = os.environ.get('T3D_F32_ENGINE')       # 'simt' = CUDA-core SGEMM, 'tc' = tcgen05 bf16 x 3 (default), 'bf16' = one pass
         if engine is not None:
-            if engine not in ('simt', 'tc'):
-                raise T3DError("T3D_F32_ENGINE must be 'simt' or 'tc'")
-            lib.t3d_set_f32_engine(1 if engine == 'tc' else 0)
+            if engine not in ('simt', 'tc', 'bf16'):
+                raise T3DError("T3D_F32_ENGINE must be 'simt', 'tc' or 'bf16'")
+            lib.t3d_set_f32_engine({'simt': 0, 'tc': 1, 'bf16': 2}[engine])
         _lib = lib
     return _lib
 

@@ -46,7 +46,7 @@ extern "C" const char* t3d_error_string(int code) {
 // 0 = CUDA-core SGEMM (sgemm.cuh).  Process-wide configuration, not per-call state.
 static int g_f32_engine = 1;
 extern "C" int t3d_set_f32_engine(int engine) {
-  if (engine != 0 && engine != 1) return T3D_ERR_ARG;
+  if (engine < 0 || engine > 2) return T3D_ERR_ARG;
   g_f32_engine = engine;
   return 0;
 }
@@ -58,7 +58,7 @@ static int xg_prepare(Kern kern) {      // opt in to 97 KB of dynamic shared mem
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return (int)e;
 }
-static inline bool xg_fits(int M, int N, int K) { return g_f32_engine == 1 && M >= 128 && N >= 64 && K >= 32; }
+static inline bool xg_fits(int M, int N, int K) { return g_f32_engine != 0 && M >= 128 && N >= 64 && K >= 32; }
 
 extern "C" int t3d_linear_f32(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* gbias,
                               int rows_per_group, float* Y, int ldy, int M, int K, int N, int act, const float* rowmask,
@@ -68,11 +68,12 @@ extern "C" int t3d_linear_f32(const float* X, int ldx, const float* W, int ldw, 
   if ((gbias || gmax) && rows_per_group <= 0) return T3D_ERR_SHAPE;
   LinearArgs a{X, ldx, W, ldw, bias, gbias, rows_per_group, Y, ldy, M, K, N, act, rowmask, gmax};
   if (xg_fits(M, N, K)) {                    // tensor cores, bf16 x 3 split (xgemm.cuh)
-    static int prepared = xg_prepare(xlinear_kernel);
+    static int prepared = xg_prepare(xlinear_kernel<3>) | xg_prepare(xlinear_kernel<1>);
     if (prepared != 0) return prepared;
     const int ntm = (M + kXgBM - 1) / kXgBM, ntn = (N + kXgBN - 1) / kXgBN;
     XgOperands o{X, ldx, W, ldw, M, N, K, (K + kXgBK - 1) / kXgBK * kXgBK, xg_aligned16(X, ldx) ? 1 : 0, 0, ntn};
-    xlinear_kernel<<<dim3((unsigned)ntm * ntn, 1), kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+    if (g_f32_engine == 1) xlinear_kernel<3><<<dim3((unsigned)ntm * ntn, 1), kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+    else xlinear_kernel<1><<<dim3((unsigned)ntm * ntn, 1), kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
     T3D_CHECK_LAUNCH();
     return 0;
   }
@@ -457,8 +458,10 @@ extern "C" int t3d_gemm_f32(const float* A, long long sam, long long sak, const 
   if (splitk > 1) T3D_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, S(stream)));
   GemmArgs a{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias};
   if (xg_fits(M, N, K)) {                    // tensor cores, bf16 x 3 split (xgemm.cuh)
-    static int prepared = xg_prepare(xgemm_kernel<true, true>) | xg_prepare(xgemm_kernel<true, false>) |
-                          xg_prepare(xgemm_kernel<false, true>) | xg_prepare(xgemm_kernel<false, false>);
+    static int prepared = xg_prepare(xgemm_kernel<true, true, 3>) | xg_prepare(xgemm_kernel<true, false, 3>) |
+                          xg_prepare(xgemm_kernel<false, true, 3>) | xg_prepare(xgemm_kernel<false, false, 3>) |
+                          xg_prepare(xgemm_kernel<true, true, 1>) | xg_prepare(xgemm_kernel<true, false, 1>) |
+                          xg_prepare(xgemm_kernel<false, true, 1>) | xg_prepare(xgemm_kernel<false, false, 1>);
     if (prepared != 0) return prepared;
     // The tensor core adds each 16-deep partial sum into the fp32 accumulator with truncation, a bias of ~0.5 ulp per
     // step (measured: 700 ulp of sum|a||b| after K = 20000, 25 after K = 600); K chunks are kept <= 2048 so that long
@@ -474,10 +477,16 @@ extern "C" int t3d_gemm_f32(const float* A, long long sam, long long sak, const 
     const long long lda = ak ? sam : sak, ldb = bk ? sbn : sbk;
     XgOperands o{A, lda, B, ldb, M, N, K, kchunk, (ak && xg_aligned16(A, lda)) ? 1 : 0, (bk && xg_aligned16(B, ldb)) ? 1 : 0, ntn};
     const dim3 grid((unsigned)ntm * ntn, nz);
-    if (ak && bk) xgemm_kernel<true, true><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
-    else if (ak) xgemm_kernel<true, false><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
-    else if (bk) xgemm_kernel<false, true><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
-    else xgemm_kernel<false, false><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+#define XG_LAUNCH(P)                                                                                     \
+  do {                                                                                                   \
+    if (ak && bk) xgemm_kernel<true, true, P><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);        \
+    else if (ak) xgemm_kernel<true, false, P><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);        \
+    else if (bk) xgemm_kernel<false, true, P><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);        \
+    else xgemm_kernel<false, false, P><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);               \
+  } while (0)
+    if (g_f32_engine == 1) XG_LAUNCH(3);
+    else XG_LAUNCH(1);
+#undef XG_LAUNCH
     T3D_CHECK_LAUNCH();
     return 0;
   }

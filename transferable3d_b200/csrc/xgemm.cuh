@@ -102,31 +102,46 @@ __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t
 }
 
 // registers of xg_load -> the three bf16 images of stage s (img = shared address of image 1; 2 and 3 follow)
-template <bool UNIT_K>
+__device__ __forceinline__ uint32_t xg_pack_rn(float lo, float hi) {      // round-to-nearest bf16x2 (lo in the low half)
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <bool UNIT_K, int PARTS>
 __device__ __forceinline__ void xg_split_store(uint32_t img, int s, int w, int lane, const float (&r)[32]) {
   if (UNIT_K) {
     const int c = lane & 7;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      uint32_t h[4], m[4], l[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) xg_split(r[4 * i + e], h[e], m[e], l[e]);
       const uint32_t addr = img + sw128_offset((uint32_t)xg_row_unit_k(w, i, lane), (uint32_t)(4 * s + (c >> 1))) + (uint32_t)(c & 1) * 8u;
-      st_shared_v2(addr, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]));
-      st_shared_v2(addr + kXgImage, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]));
-      st_shared_v2(addr + 2 * kXgImage, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]));
+      if (PARTS == 1) {
+        st_shared_v2(addr, xg_pack_rn(r[4 * i], r[4 * i + 1]), xg_pack_rn(r[4 * i + 2], r[4 * i + 3]));
+      } else {
+        uint32_t h[4], m[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) xg_split(r[4 * i + e], h[e], m[e], l[e]);
+        st_shared_v2(addr, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]));
+        st_shared_v2(addr + kXgImage, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]));
+        st_shared_v2(addr + 2 * kXgImage, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]));
+      }
     }
   } else {
     const uint32_t row = (uint32_t)(w * 32 + lane);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint32_t h[8], m[8], l[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) xg_split(r[8 * j + e], h[e], m[e], l[e]);
       const uint32_t addr = img + sw128_offset(row, (uint32_t)(4 * s + j));
-      st_shared_v4(addr, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]), xg_pack(h[4], h[5]), xg_pack(h[6], h[7]));
-      st_shared_v4(addr + kXgImage, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]), xg_pack(m[4], m[5]), xg_pack(m[6], m[7]));
-      st_shared_v4(addr + 2 * kXgImage, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]), xg_pack(l[4], l[5]), xg_pack(l[6], l[7]));
+      if (PARTS == 1) {
+        st_shared_v4(addr, xg_pack_rn(r[8 * j], r[8 * j + 1]), xg_pack_rn(r[8 * j + 2], r[8 * j + 3]),
+                     xg_pack_rn(r[8 * j + 4], r[8 * j + 5]), xg_pack_rn(r[8 * j + 6], r[8 * j + 7]));
+      } else {
+        uint32_t h[8], m[8], l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) xg_split(r[8 * j + e], h[e], m[e], l[e]);
+        st_shared_v4(addr, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]), xg_pack(h[4], h[5]), xg_pack(h[6], h[7]));
+        st_shared_v4(addr + kXgImage, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]), xg_pack(m[4], m[5]), xg_pack(m[6], m[7]));
+        st_shared_v4(addr + 2 * kXgImage, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]), xg_pack(l[4], l[5]), xg_pack(l[6], l[7]));
+      }
     }
   }
 }
@@ -137,7 +152,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
 
 // One operand's loader warp: stage it+1 is in flight in registers while stage it is split and stored (two register
 // sets, ping-pong).  full0 / empty0 = the stage-0 barriers (stage 1 follows at +8 bytes).
-template <bool UNIT_K>
+template <bool UNIT_K, int PARTS>
 __device__ __forceinline__ void xg_loader(const float* __restrict__ P, long long ld, int row0, int nrows, int kbeg, int kend, bool vec,
                                           uint32_t img, int w, int lane, int nst, uint32_t full0, uint32_t empty0) {
   const int row = row0 + (UNIT_K ? xg_row_unit_k(w, 0, lane) : w * 32 + lane);      // first (or only) row of this thread
@@ -152,7 +167,7 @@ __device__ __forceinline__ void xg_loader(const float* __restrict__ P, long long
   auto emit = [&](int it, const float (&r)[32]) {
     const int s = it & 1;
     mbar_wait_backoff(empty0 + 8u * s, ((it >> 1) & 1) ^ 1);
-    xg_split_store<UNIT_K>(img, s, w, lane, r);
+    xg_split_store<UNIT_K, PARTS>(img, s, w, lane, r);
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(full0 + 8u * s);
@@ -177,7 +192,7 @@ struct XgTile {
 // Runs the main loop of one tile.  Returns in the 8 loader warps once both accumulators are complete in TMEM
 // (main: columns [0,128), small: [128,256) of the allocation; lane = tile row); warp 8 returns immediately after its
 // last commit.  Every thread must then call xg_finish().
-template <bool A_UNIT_K, bool B_UNIT_K>
+template <bool A_UNIT_K, bool B_UNIT_K, int PARTS>
 __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_raw, XgTile& t) {
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -206,8 +221,8 @@ __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_r
 
   if (warp < 8) {
     // ---------------------------------------------------------------- loaders: global fp32 -> registers -> 3 bf16 images
-    if (warp < 4) xg_loader<A_UNIT_K>(o.A, o.lda, m0, o.M, kbeg, kend, o.vecA != 0, sbase, warp & 3, lane, nst, full(0), empty(0));
-    else xg_loader<B_UNIT_K>(o.B, o.ldb, n0, o.N, kbeg, kend, o.vecB != 0, sbase + 3u * kXgImage, warp & 3, lane, nst, full(0), empty(0));
+    if (warp < 4) xg_loader<A_UNIT_K, PARTS>(o.A, o.lda, m0, o.M, kbeg, kend, o.vecA != 0, sbase, warp & 3, lane, nst, full(0), empty(0));
+    else xg_loader<B_UNIT_K, PARTS>(o.B, o.ldb, n0, o.N, kbeg, kend, o.vecB != 0, sbase + 3u * kXgImage, warp & 3, lane, nst, full(0), empty(0));
     mbar_wait_backoff(acc_full, 0);
     tc_fence_after();
   } else {
@@ -228,11 +243,13 @@ __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_r
         const uint64_t b1 = make_sdesc_k128(b_img + off), b2 = make_sdesc_k128(b_img + kXgImage + off),
                        b3 = make_sdesc_k128(b_img + 2 * kXgImage + off);
         const uint32_t first = (it | ks) != 0;
-        umma_bf16_w(d_small, a3, b1, idesc, first);
-        umma_bf16_w(d_small, a1, b3, idesc, 1);
-        umma_bf16_w(d_small, a2, b2, idesc, 1);
-        umma_bf16_w(d_small, a2, b1, idesc, 1);
-        umma_bf16_w(d_small, a1, b2, idesc, 1);
+        if (PARTS == 3) {
+          umma_bf16_w(d_small, a3, b1, idesc, first);
+          umma_bf16_w(d_small, a1, b3, idesc, 1);
+          umma_bf16_w(d_small, a2, b2, idesc, 1);
+          umma_bf16_w(d_small, a2, b1, idesc, 1);
+          umma_bf16_w(d_small, a1, b2, idesc, 1);
+        }
         umma_bf16_w(d_main, a1, b1, idesc, first);
       }
       umma_commit_w(empty(s));
@@ -242,14 +259,22 @@ __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_r
 }
 
 // 32 accumulator columns [c0, c0+32) of this thread's row: main + small
+template <int PARTS>
 __device__ __forceinline__ void xg_acc32(const XgTile& t, int c0, float (&v)[32]) {
   const uint32_t taddr = t.tmem_base + ((uint32_t)((t.warp & 3) * 32) << 16) + (uint32_t)c0;
-  uint32_t va[32], vb[32];
+  uint32_t va[32];
   tmem_ld32(taddr, va);
-  tmem_ld32(taddr + 128, vb);
-  tmem_ld_wait();
+  if (PARTS == 3) {
+    uint32_t vb[32];
+    tmem_ld32(taddr + 128, vb);
+    tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(va[j]) + __uint_as_float(vb[j]);
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(va[j]) + __uint_as_float(vb[j]);
+  } else {
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(va[j]);
+  }
 }
 
 __device__ __forceinline__ void xg_finish(const XgTile& t) {
@@ -265,18 +290,18 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 #ifdef T3D_XGEMM_WITH_EPILOGUES
 // ---- t3d_gemm_f32 (same contract as gemm_f32_kernel, train_ops.cuh): C = A.B (+ bias by split 0); split-K partial tiles
 // are added into a zero-initialised C with vector reductions.
-template <bool A_UNIT_K, bool B_UNIT_K>
+template <bool A_UNIT_K, bool B_UNIT_K, int PARTS>
 __global__ void __launch_bounds__(kXgThreads, 2) xgemm_kernel(const GemmArgs a, const XgOperands o) {
   extern __shared__ uint8_t xg_smem[];
   XgTile t;
-  xg_mainloop<A_UNIT_K, B_UNIT_K>(o, xg_smem, t);
+  xg_mainloop<A_UNIT_K, B_UNIT_K, PARTS>(o, xg_smem, t);
   if (t.warp < 8) {
     const int gm = t.m0 + (t.warp & 3) * 32 + t.lane;
 #pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {
       const int c0 = (t.warp >> 2) * 64 + ch * 32;
       float v[32];
-      xg_acc32(t, c0, v);
+      xg_acc32<PARTS>(t, c0, v);
       if (gm < a.M) {
         float* crow = a.C + (size_t)gm * a.ldc;
 #pragma unroll
@@ -309,10 +334,11 @@ __global__ void __launch_bounds__(kXgThreads, 2) xgemm_kernel(const GemmArgs a, 
 
 // ---- t3d_linear_f32 (same contract as linear_f32_kernel, simt_ops.cuh): Y = act(X.W + bias + gbias[row / rows_per_group])
 // * rowmask, optional max over the rows of each group.
+template <int PARTS>
 __global__ void __launch_bounds__(kXgThreads, 2) xlinear_kernel(const LinearArgs a, const XgOperands o) {
   extern __shared__ uint8_t xg_smem[];
   XgTile t;
-  xg_mainloop<true, false>(o, xg_smem, t);
+  xg_mainloop<true, false, PARTS>(o, xg_smem, t);
   if (t.warp < 8) {
     const int gm = t.m0 + (t.warp & 3) * 32 + t.lane;
     const bool row_ok = gm < a.M;
@@ -324,7 +350,7 @@ __global__ void __launch_bounds__(kXgThreads, 2) xlinear_kernel(const LinearArgs
     for (int ch = 0; ch < 2; ++ch) {
       const int c0 = (t.warp >> 2) * 64 + ch * 32;
       float v[32];
-      xg_acc32(t, c0, v);
+      xg_acc32<PARTS>(t, c0, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int gn = t.n0 + c0 + j;

@@ -34,14 +34,19 @@ def get_precision():
 
 def set_f32_engine(engine):
     """Engine of the fp32 GEMMs (fp32-mode layers, training steps): 'tc' = tcgen05 bf16 x 3 split (fp32-accurate,
-    default), 'simt' = CUDA-core SGEMM.  See include/t3d_b200.h: t3d_set_f32_engine."""
-    if engine not in ('tc', 'simt'):
+    default), 'simt' = CUDA-core SGEMM, 'bf16' = tcgen05 with operands rounded to bf16 (one pass, fp32 accumulate).
+    See include/t3d_b200.h: t3d_set_f32_engine."""
+    if engine not in F32_ENGINES:
         raise ValueError(engine)
-    _lib.check(_lib.load().t3d_set_f32_engine(1 if engine == 'tc' else 0))
+    _lib.check(_lib.load().t3d_set_f32_engine(F32_ENGINES[engine]))
+
+
+F32_ENGINES = {'simt': 0, 'tc': 1, 'bf16': 2}
 
 
 def get_f32_engine():
-    return 'tc' if _lib.load().t3d_get_f32_engine() == 1 else 'simt'
+    code = _lib.load().t3d_get_f32_engine()
+    return [k for k, v in F32_ENGINES.items() if v == code][0]
 
 
 @contextlib.contextmanager
