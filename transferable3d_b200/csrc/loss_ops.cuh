@@ -10,6 +10,7 @@
 // numbers over the 7 box parameters they depend on, so the forward code is written once and the
 // sub-gradient choices (min / max pick one corner, clamp, huber) follow the values exactly as autograd's do.
 #pragma once
+#include <initializer_list>
 #include "common.cuh"
 
 namespace t3d {
@@ -532,6 +533,99 @@ __global__ void rowmask_mul_kernel(const float* __restrict__ x, const float* __r
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) out[i] = x[i] * rowmask[i / C];
 }
+
+// ----------------------------------------------------------------------------- 128-bit variants of the streaming kernels
+// The training step is half HBM-bound element-wise passes (ncu launch list, profiles/r01_launches_bench_cfg5_tc.csv); the
+// scalar kernels above ran at ~2.4 TB/s (one element per thread, a 64-bit modulo per element).  These move float4s, four
+// per thread with all loads issued before the first use, and take the channel from a 32-bit modulo on the float4 index.
+// Same arithmetic expressions as the scalar kernels (bit-identical results); used when C % 4 == 0 and the pointers are
+// 16-byte aligned.
+constexpr int kEw4 = 4;      // float4s per thread
+#define T3D_EW4_LOOP(q) for (int u = 0; u < kEw4; ++u) if (const unsigned q = blockIdx.x * (256u * kEw4) + u * 256u + threadIdx.x; q < n4)
+
+__global__ void __launch_bounds__(256) bn_apply4_kernel(const float4* __restrict__ y, const float4* __restrict__ mean, const float4* __restrict__ rstd,
+                                                       const float4* __restrict__ gamma, const float4* __restrict__ beta, float4* __restrict__ out,
+                                                       unsigned n4, unsigned C4, int act) {
+  float4 v[kEw4];
+#pragma unroll
+  T3D_EW4_LOOP(q) v[u] = y[q];
+#pragma unroll
+  T3D_EW4_LOOP(q) {
+    const unsigned c = q % C4;
+    const float4 m = __ldg(mean + c), r = __ldg(rstd + c), g = __ldg(gamma + c), b = __ldg(beta + c);
+    float4 o;
+    o.x = act_apply(g.x * (v[u].x - m.x) * r.x + b.x, act);
+    o.y = act_apply(g.y * (v[u].y - m.y) * r.y + b.y, act);
+    o.z = act_apply(g.z * (v[u].z - m.z) * r.z + b.z, act);
+    o.w = act_apply(g.w * (v[u].w - m.w) * r.w + b.w, act);
+    out[q] = o;
+  }
+}
+
+__device__ __forceinline__ float bn_bwd_one(float dy, float o, bool has_out, float y, float m, float r, float g, float s1, float s2, float inv, int act) {
+  if (has_out) dy *= act_grad_from_out(o, act);
+  const float xh = (y - m) * r;
+  return g * r * (dy - s1 * inv - xh * s2 * inv);
+}
+__global__ void __launch_bounds__(256) bn_backward4_kernel(float4* __restrict__ dOut, const float4* __restrict__ out, const float4* __restrict__ y,
+                                                          const float4* __restrict__ mean, const float4* __restrict__ rstd,
+                                                          const float4* __restrict__ gamma, const float4* __restrict__ s1,
+                                                          const float4* __restrict__ s2, unsigned n4, unsigned C4, int M, int act) {
+  float4 d[kEw4], o[kEw4], yy[kEw4];
+  const bool has_out = out != nullptr;
+#pragma unroll
+  T3D_EW4_LOOP(q) { d[u] = dOut[q]; yy[u] = y[q]; o[u] = has_out ? out[q] : make_float4(0.f, 0.f, 0.f, 0.f); }
+  const float inv = 1.0f / (float)M;
+#pragma unroll
+  T3D_EW4_LOOP(q) {
+    const unsigned c = q % C4;
+    const float4 m = __ldg(mean + c), r = __ldg(rstd + c), g = __ldg(gamma + c), a1 = __ldg(s1 + c), a2 = __ldg(s2 + c);
+    float4 w;
+    w.x = bn_bwd_one(d[u].x, o[u].x, has_out, yy[u].x, m.x, r.x, g.x, a1.x, a2.x, inv, act);
+    w.y = bn_bwd_one(d[u].y, o[u].y, has_out, yy[u].y, m.y, r.y, g.y, a1.y, a2.y, inv, act);
+    w.z = bn_bwd_one(d[u].z, o[u].z, has_out, yy[u].z, m.z, r.z, g.z, a1.z, a2.z, inv, act);
+    w.w = bn_bwd_one(d[u].w, o[u].w, has_out, yy[u].w, m.w, r.w, g.w, a1.w, a2.w, inv, act);
+    dOut[q] = w;
+  }
+}
+
+__global__ void __launch_bounds__(256) act_bwd4_kernel(float4* __restrict__ dout, const float4* __restrict__ out, unsigned n4, int act) {
+  float4 d[kEw4], o[kEw4];
+#pragma unroll
+  T3D_EW4_LOOP(q) { d[u] = dout[q]; o[u] = out[q]; }
+#pragma unroll
+  T3D_EW4_LOOP(q) {
+    float4 w = d[u];
+    w.x *= act_grad_from_out(o[u].x, act); w.y *= act_grad_from_out(o[u].y, act);
+    w.z *= act_grad_from_out(o[u].z, act); w.w *= act_grad_from_out(o[u].w, act);
+    dout[q] = w;
+  }
+}
+
+__global__ void __launch_bounds__(256) rowmask_mul4_kernel(const float4* __restrict__ x, const float* __restrict__ rowmask, float4* __restrict__ out,
+                                                          unsigned n4, unsigned C4) {
+  float4 v[kEw4]; float rm[kEw4];
+#pragma unroll
+  T3D_EW4_LOOP(q) { v[u] = x[q]; rm[u] = __ldg(rowmask + q / C4); }
+#pragma unroll
+  T3D_EW4_LOOP(q) out[q] = make_float4(v[u].x * rm[u], v[u].y * rm[u], v[u].z * rm[u], v[u].w * rm[u]);
+}
+
+__global__ void __launch_bounds__(256) scale_mask4_kernel(const float4* __restrict__ x, const float4* __restrict__ mask, float scale,
+                                                         float4* __restrict__ out, unsigned n4) {
+  float4 v[kEw4], m[kEw4];
+#pragma unroll
+  T3D_EW4_LOOP(q) { v[u] = x[q]; m[u] = mask[q]; }
+#pragma unroll
+  T3D_EW4_LOOP(q) out[q] = make_float4(v[u].x * m[u].x * scale, v[u].y * m[u].y * scale, v[u].z * m[u].z * scale, v[u].w * m[u].w * scale);
+}
+#undef T3D_EW4_LOOP
+inline bool ew4_ok(size_t total, int C, std::initializer_list<const void*> ptrs) {
+  if (C % 4 != 0 || total % 4 != 0 || total / 4 >= 0xffffffffull) return false;
+  for (const void* p : ptrs) if (p && ((uintptr_t)p & 15)) return false;
+  return true;
+}
+inline unsigned ew4_grid(size_t total) { return (unsigned)((total / 4 + 256 * kEw4 - 1) / (256 * kEw4)); }
 
 // out[b, c] = scale * sum_n x[b, n, c]   (C <= 8; e.g. d stage1_center = -sum_n d(xyz - stage1_center), semisup_models.py:204-209)
 __global__ void __launch_bounds__(256) group_sum_kernel(const float* __restrict__ x, int N, int C, float scale, float* __restrict__ out) {

@@ -536,7 +536,13 @@ extern "C" int t3d_bn_apply(const float* y, const float* mean, const float* rstd
   if (!y || !mean || !rstd || !gamma || !beta || !out) return T3D_ERR_ARG;
   if (act < 0 || act > 3) return T3D_ERR_SHAPE;
   const size_t total = (size_t)M * C;
-  bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(y, mean, rstd, gamma, beta, out, total, C, act);
+  if (ew4_ok(total, C, {y, mean, rstd, gamma, beta, out})) {
+    using F4 = const float4*;
+    bn_apply4_kernel<<<ew4_grid(total), 256, 0, S(stream)>>>((F4)y, (F4)mean, (F4)rstd, (F4)gamma, (F4)beta, (float4*)out,
+                                                             (unsigned)(total / 4), (unsigned)(C / 4), act);
+  } else {
+    bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(y, mean, rstd, gamma, beta, out, total, C, act);
+  }
   T3D_CHECK_LAUNCH();
   return 0;
 }
@@ -546,7 +552,13 @@ extern "C" int t3d_bn_backward(float* dOut, const float* out, const float* y, co
   if (!dOut || !y || !mean || !rstd || !gamma || !s1 || !s2) return T3D_ERR_ARG;
   if (act < 0 || act > 3) return T3D_ERR_SHAPE;
   const size_t total = (size_t)M * C;
-  bn_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(dOut, out, y, mean, rstd, gamma, s1, s2, total, C, M, act);
+  if (ew4_ok(total, C, {dOut, out, y, mean, rstd, gamma, s1, s2})) {
+    using F4 = const float4*;
+    bn_backward4_kernel<<<ew4_grid(total), 256, 0, S(stream)>>>((float4*)dOut, (F4)out, (F4)y, (F4)mean, (F4)rstd, (F4)gamma, (F4)s1, (F4)s2,
+                                                                (unsigned)(total / 4), (unsigned)(C / 4), M, act);
+  } else {
+    bn_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(dOut, out, y, mean, rstd, gamma, s1, s2, total, C, M, act);
+  }
   T3D_CHECK_LAUNCH();
   return 0;
 }
@@ -568,7 +580,11 @@ extern "C" int t3d_maxpool_bwd(const float* dout, const int* arg, int B, int N, 
 
 extern "C" int t3d_scale_mask(const float* x, const float* mask, float scale, float* out, long long n, t3d_stream_t stream) {
   if (!x || !mask || !out || n <= 0) return T3D_ERR_ARG;
-  scale_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(x, mask, scale, out, (size_t)n);
+  if (ew4_ok((size_t)n, 4, {x, mask, out})) {
+    scale_mask4_kernel<<<ew4_grid((size_t)n), 256, 0, S(stream)>>>((const float4*)x, (const float4*)mask, scale, (float4*)out, (unsigned)(n / 4));
+  } else {
+    scale_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(x, mask, scale, out, (size_t)n);
+  }
   T3D_CHECK_LAUNCH();
   return 0;
 }
@@ -658,7 +674,11 @@ extern "C" int t3d_boxpc_features_bwd(const float* pc, int B, int N, int C, cons
 extern "C" int t3d_act_bwd(float* dout, const float* out, long long n, int act, t3d_stream_t stream) {
   if (!dout || !out || n <= 0) return T3D_ERR_ARG;
   if (act < 0 || act > 3) return T3D_ERR_SHAPE;
-  act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(dout, out, (size_t)n, act);
+  if (ew4_ok((size_t)n, 4, {dout, out})) {
+    act_bwd4_kernel<<<ew4_grid((size_t)n), 256, 0, S(stream)>>>((float4*)dout, (const float4*)out, (unsigned)(n / 4), act);
+  } else {
+    act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(dout, out, (size_t)n, act);
+  }
   T3D_CHECK_LAUNCH();
   return 0;
 }
@@ -666,7 +686,11 @@ extern "C" int t3d_act_bwd(float* dout, const float* out, long long n, int act, 
 extern "C" int t3d_rowmask_mul(const float* x, const float* rowmask, float* out, long long M, int C, t3d_stream_t stream) {
   if (!x || !rowmask || !out || M <= 0 || C <= 0) return T3D_ERR_ARG;
   const size_t total = (size_t)M * C;
-  rowmask_mul_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(x, rowmask, out, total, C);
+  if (ew4_ok(total, C, {x, out})) {
+    rowmask_mul4_kernel<<<ew4_grid(total), 256, 0, S(stream)>>>((const float4*)x, rowmask, (float4*)out, (unsigned)(total / 4), (unsigned)(C / 4));
+  } else {
+    rowmask_mul_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(x, rowmask, out, total, C);
+  }
   T3D_CHECK_LAUNCH();
   return 0;
 }
