@@ -543,8 +543,13 @@ __global__ void rowmask_mul_kernel(const float* __restrict__ x, const float* __r
 constexpr int kEw4 = 4;      // float4s per thread
 #define T3D_EW4_LOOP(q) for (int u = 0; u < kEw4; ++u) if (const unsigned q = blockIdx.x * (256u * kEw4) + u * 256u + threadIdx.x; q < n4)
 
-__global__ void __launch_bounds__(256) bn_apply4_kernel(const float4* __restrict__ y, const float4* __restrict__ mean, const float4* __restrict__ rstd,
-                                                       const float4* __restrict__ gamma, const float4* __restrict__ beta, float4* __restrict__ out,
+// per-channel parameters live at arbitrary offsets of the flat parameter arena: scalar loads (L1 hits), no alignment demand
+__device__ __forceinline__ float4 ldg4(const float* __restrict__ p, unsigned c4) {
+  const float* q = p + 4u * c4;
+  return make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+}
+__global__ void __launch_bounds__(256) bn_apply4_kernel(const float4* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta, float4* __restrict__ out,
                                                        unsigned n4, unsigned C4, int act) {
   float4 v[kEw4];
 #pragma unroll
@@ -552,7 +557,7 @@ __global__ void __launch_bounds__(256) bn_apply4_kernel(const float4* __restrict
 #pragma unroll
   T3D_EW4_LOOP(q) {
     const unsigned c = q % C4;
-    const float4 m = __ldg(mean + c), r = __ldg(rstd + c), g = __ldg(gamma + c), b = __ldg(beta + c);
+    const float4 m = ldg4(mean, c), r = ldg4(rstd, c), g = ldg4(gamma, c), b = ldg4(beta, c);
     float4 o;
     o.x = act_apply(g.x * (v[u].x - m.x) * r.x + b.x, act);
     o.y = act_apply(g.y * (v[u].y - m.y) * r.y + b.y, act);
@@ -568,9 +573,9 @@ __device__ __forceinline__ float bn_bwd_one(float dy, float o, bool has_out, flo
   return g * r * (dy - s1 * inv - xh * s2 * inv);
 }
 __global__ void __launch_bounds__(256) bn_backward4_kernel(float4* __restrict__ dOut, const float4* __restrict__ out, const float4* __restrict__ y,
-                                                          const float4* __restrict__ mean, const float4* __restrict__ rstd,
-                                                          const float4* __restrict__ gamma, const float4* __restrict__ s1,
-                                                          const float4* __restrict__ s2, unsigned n4, unsigned C4, int M, int act) {
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          const float* __restrict__ gamma, const float* __restrict__ s1,
+                                                          const float* __restrict__ s2, unsigned n4, unsigned C4, int M, int act) {
   float4 d[kEw4], o[kEw4], yy[kEw4];
   const bool has_out = out != nullptr;
 #pragma unroll
@@ -579,7 +584,7 @@ __global__ void __launch_bounds__(256) bn_backward4_kernel(float4* __restrict__ 
 #pragma unroll
   T3D_EW4_LOOP(q) {
     const unsigned c = q % C4;
-    const float4 m = __ldg(mean + c), r = __ldg(rstd + c), g = __ldg(gamma + c), a1 = __ldg(s1 + c), a2 = __ldg(s2 + c);
+    const float4 m = ldg4(mean, c), r = ldg4(rstd, c), g = ldg4(gamma, c), a1 = ldg4(s1, c), a2 = ldg4(s2, c);
     float4 w;
     w.x = bn_bwd_one(d[u].x, o[u].x, has_out, yy[u].x, m.x, r.x, g.x, a1.x, a2.x, inv, act);
     w.y = bn_bwd_one(d[u].y, o[u].y, has_out, yy[u].y, m.y, r.y, g.y, a1.y, a2.y, inv, act);

@@ -71,7 +71,7 @@ extern "C" int t3d_linear_f32(const float* X, int ldx, const float* W, int ldw, 
     static int prepared = xg_prepare(xlinear_kernel<3>) | xg_prepare(xlinear_kernel<1>);
     if (prepared != 0) return prepared;
     const int ntm = (M + kXgBM - 1) / kXgBM, ntn = (N + kXgBN - 1) / kXgBN;
-    XgOperands o{X, ldx, W, ldw, M, N, K, (K + kXgBK - 1) / kXgBK * kXgBK, xg_aligned16(X, ldx) ? 1 : 0, 0, ntn};
+    XgOperands o{X, ldx, W, ldw, M, N, K, (K + kXgBK - 1) / kXgBK * kXgBK, xg_aligned16(X, ldx) ? 1 : 0, 0, ntn, g_trace};
     if (g_f32_engine == 1) xlinear_kernel<3><<<dim3((unsigned)ntm * ntn, 1), kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
     else xlinear_kernel<1><<<dim3((unsigned)ntm * ntn, 1), kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
     T3D_CHECK_LAUNCH();
@@ -475,7 +475,7 @@ extern "C" int t3d_gemm_f32(const float* A, long long sam, long long sak, const 
     const bool ak = (sak == 1), bk = (sbk == 1 && sbn != 1);
     const int ntm = (M + kXgBM - 1) / kXgBM, ntn = (N + kXgBN - 1) / kXgBN;
     const long long lda = ak ? sam : sak, ldb = bk ? sbn : sbk;
-    XgOperands o{A, lda, B, ldb, M, N, K, kchunk, (ak && xg_aligned16(A, lda)) ? 1 : 0, (bk && xg_aligned16(B, ldb)) ? 1 : 0, ntn};
+    XgOperands o{A, lda, B, ldb, M, N, K, kchunk, (ak && xg_aligned16(A, lda)) ? 1 : 0, (bk && xg_aligned16(B, ldb)) ? 1 : 0, ntn, g_trace};
     const dim3 grid((unsigned)ntm * ntn, nz);
 #define XG_LAUNCH(P)                                                                                     \
   do {                                                                                                   \
@@ -536,9 +536,9 @@ extern "C" int t3d_bn_apply(const float* y, const float* mean, const float* rstd
   if (!y || !mean || !rstd || !gamma || !beta || !out) return T3D_ERR_ARG;
   if (act < 0 || act > 3) return T3D_ERR_SHAPE;
   const size_t total = (size_t)M * C;
-  if (ew4_ok(total, C, {y, mean, rstd, gamma, beta, out})) {
+  if (ew4_ok(total, C, {y, out})) {
     using F4 = const float4*;
-    bn_apply4_kernel<<<ew4_grid(total), 256, 0, S(stream)>>>((F4)y, (F4)mean, (F4)rstd, (F4)gamma, (F4)beta, (float4*)out,
+    bn_apply4_kernel<<<ew4_grid(total), 256, 0, S(stream)>>>((F4)y, mean, rstd, gamma, beta, (float4*)out,
                                                              (unsigned)(total / 4), (unsigned)(C / 4), act);
   } else {
     bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(y, mean, rstd, gamma, beta, out, total, C, act);
@@ -552,9 +552,9 @@ extern "C" int t3d_bn_backward(float* dOut, const float* out, const float* y, co
   if (!dOut || !y || !mean || !rstd || !gamma || !s1 || !s2) return T3D_ERR_ARG;
   if (act < 0 || act > 3) return T3D_ERR_SHAPE;
   const size_t total = (size_t)M * C;
-  if (ew4_ok(total, C, {dOut, out, y, mean, rstd, gamma, s1, s2})) {
+  if (ew4_ok(total, C, {dOut, out, y})) {
     using F4 = const float4*;
-    bn_backward4_kernel<<<ew4_grid(total), 256, 0, S(stream)>>>((float4*)dOut, (F4)out, (F4)y, (F4)mean, (F4)rstd, (F4)gamma, (F4)s1, (F4)s2,
+    bn_backward4_kernel<<<ew4_grid(total), 256, 0, S(stream)>>>((float4*)dOut, (F4)out, (F4)y, mean, rstd, gamma, s1, s2,
                                                                 (unsigned)(total / 4), (unsigned)(C / 4), M, act);
   } else {
     bn_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(dOut, out, y, mean, rstd, gamma, s1, s2, total, C, M, act);

@@ -40,6 +40,7 @@ struct XgOperands {
   int kchunk;                         // K range of blockIdx.y: [y*kchunk, min(K, (y+1)*kchunk)), multiple of 32
   int vecA, vecB;                     // 128-bit loads allowed for a UNIT_K operand (16-byte aligned base and ld % 4 == 0)
   int ntn;                            // number of column tiles; blockIdx.x = m_tile * ntn + n_tile
+  unsigned long long* trace;          // debug: clock64 timeline of the middle CTA (t3d_set_trace_buffer) or null
 };
 
 // row of the tile handled by (warp w of the operand's 4, iteration i, lane) in the UNIT_K mapping: a warp-wide 128-bit
@@ -146,6 +147,16 @@ __device__ __forceinline__ void xg_split_store(uint32_t img, int s, int w, int l
   }
 }
 
+struct XgTracer {          // (clock64 << 8 | tag) per role, recorded by one thread of the middle CTA of the grid
+  unsigned long long* buf; int n;
+  __device__ __forceinline__ void init(unsigned long long* base, int role, bool who) {
+    buf = (base != nullptr && who && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0) ? base + (size_t)role * kTraceSlots : nullptr; n = 0;
+  }
+  __device__ __forceinline__ void mark(int tag) {
+    if (buf != nullptr && n < kTraceSlots) buf[n++] = ((unsigned long long)clock64() << 8) | (unsigned long long)(tag & 0xff);
+  }
+};
+
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {     // many threads poll: yield issue slots
   while (!mbar_try_wait(bar, parity)) __nanosleep(32);
 }
@@ -154,7 +165,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
 // sets, ping-pong).  full0 / empty0 = the stage-0 barriers (stage 1 follows at +8 bytes).
 template <bool UNIT_K, int PARTS>
 __device__ __forceinline__ void xg_loader(const float* __restrict__ P, long long ld, int row0, int nrows, int kbeg, int kend, bool vec,
-                                          uint32_t img, int w, int lane, int nst, uint32_t full0, uint32_t empty0) {
+                                          uint32_t img, int w, int lane, int nst, uint32_t full0, uint32_t empty0, XgTracer& tr) {
   const int row = row0 + (UNIT_K ? xg_row_unit_k(w, 0, lane) : w * 32 + lane);      // first (or only) row of this thread
   const int kofs = UNIT_K ? 4 * (lane & 7) : 0;
   const float* p = UNIT_K ? P + (long long)row * ld + kbeg + kofs : P + (long long)kbeg * ld + row;
@@ -167,18 +178,23 @@ __device__ __forceinline__ void xg_loader(const float* __restrict__ P, long long
   auto emit = [&](int it, const float (&r)[32]) {
     const int s = it & 1;
     mbar_wait_backoff(empty0 + 8u * s, ((it >> 1) & 1) ^ 1);
+    tr.mark(0x20);
     xg_split_store<UNIT_K, PARTS>(img, s, w, lane, r);
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) mbar_arrive(full0 + 8u * s);
+    tr.mark(0x30);
   };
   float ra[32], rb[32];
   load(0, ra);
+  tr.mark(0x10);
   int it = 0;
   for (; it + 1 < nst; it += 2) {
     load(it + 1, rb);
+    tr.mark(0x10);
     emit(it, ra);
     if (it + 2 < nst) load(it + 2, ra);
+    tr.mark(0x10);
     emit(it + 1, rb);
   }
   if (it < nst) emit(it, ra);
@@ -218,13 +234,17 @@ __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_r
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kXgBars + 40);
   t.sbase = sbase; t.tmem_base = tmem_base; t.m0 = m0; t.n0 = n0; t.warp = warp; t.lane = lane;
+  XgTracer tr;
+  tr.init(o.trace, warp == 0 ? 0 : (warp == 4 ? 1 : 2), lane == 0 && (warp == 0 || warp == 4 || warp == 8));
+  tr.mark(0x02);
 
   if (warp < 8) {
     // ---------------------------------------------------------------- loaders: global fp32 -> registers -> 3 bf16 images
-    if (warp < 4) xg_loader<A_UNIT_K, PARTS>(o.A, o.lda, m0, o.M, kbeg, kend, o.vecA != 0, sbase, warp & 3, lane, nst, full(0), empty(0));
-    else xg_loader<B_UNIT_K, PARTS>(o.B, o.ldb, n0, o.N, kbeg, kend, o.vecB != 0, sbase + 3u * kXgImage, warp & 3, lane, nst, full(0), empty(0));
+    if (warp < 4) xg_loader<A_UNIT_K, PARTS>(o.A, o.lda, m0, o.M, kbeg, kend, o.vecA != 0, sbase, warp & 3, lane, nst, full(0), empty(0), tr);
+    else xg_loader<B_UNIT_K, PARTS>(o.B, o.ldb, n0, o.N, kbeg, kend, o.vecB != 0, sbase + 3u * kXgImage, warp & 3, lane, nst, full(0), empty(0), tr);
     mbar_wait_backoff(acc_full, 0);
     tc_fence_after();
+    tr.mark(0x40);
   } else {
     // ---------------------------------------------------------------- MMA issue (warp-convergent, one elected lane)
     const int ncols = min(kXgBN, ((o.N - n0) + 15) & ~15);
@@ -235,6 +255,7 @@ __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_r
       const int s = it & 1;
       mbar_wait_w(full(s), (it >> 1) & 1);
       tc_fence_after();
+      tr.mark(0x10);
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
         const uint32_t off = (uint32_t)(2 * s + ks) * 32u;
@@ -253,6 +274,7 @@ __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_r
         umma_bf16_w(d_main, a1, b1, idesc, first);
       }
       umma_commit_w(empty(s));
+      tr.mark(0x20);
     }
     umma_commit_w(acc_full);
   }
