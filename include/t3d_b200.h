@@ -245,6 +245,30 @@ int t3d_rowmask_mul(const float* x, const float* rowmask, float* out, long long 
 /* out[b,c] = scale * sum_n x[b,n,c], C <= 8 */
 int t3d_group_sum(const float* x, int B, int N, int C, float scale, float* out, t3d_stream_t stream);
 
+/* ---- inference post-processing ------------------------------------------------------
+ * The numpy tail of test_semisup.inference (sunrgbd_detection/test_semisup.py:236-258) for one batch:
+ *   pred_seg = argmax(logits, 2); mask_mean_prob = sum(softmax(logits)[:,:,1] * pred_seg) / (sum(pred_seg) + 1);
+ *   score = log(mask_mean_prob + .01) + log(max softmax(heading_scores) + .01) + log(max softmax(size_scores) + .01)
+ *           [+ log(fit_prob + .01)]; heading_cls / size_cls = argmax of the scores and the residuals they select.
+ * pred_seg and mask_mean_prob may be NULL. */
+typedef struct {
+  const float *logits, *heading_scores, *heading_residuals, *size_scores, *size_residuals, *fit_prob;
+  int B, N, NH, NS;
+  unsigned char* pred_seg;
+  float* mask_mean_prob;
+  int* heading_cls;
+  float* heading_res;
+  int* size_cls;
+  float* size_res;
+  float* scores;
+} t3d_infer_score_args;
+int t3d_inference_scores(const t3d_infer_score_args* args /* host */, t3d_stream_t stream);
+/* roi_seg_box3d_dataset.from_prediction_to_label_format (roi_seg_box3d_dataset.py:461-466, with class2angle :64-71,
+ * class2size :79-82, rotate_pc_along_y :37-45) for a batch: out7[b] = (h, w, l, tx, ty, tz, ry). */
+int t3d_prediction_to_label(const float* center, const int* heading_cls, const float* heading_res, const int* size_cls,
+                            const float* size_res, const float* rot_angle, const float* mean_size /* [NS,3] (l,w,h) */,
+                            int B, int NH, float* out7, t3d_stream_t stream);
+
 /* Debug hook (not part of the reference-facing surface): install a device buffer of
  * 4 * 8192 uint64 into which CTA 0 of the tcgen05 kernels records (clock64 << 8 | tag) per role
  * (0 weight producer, 1 MMA issuer, 2 epilogue warp, 3 front warp); NULL switches tracing off. */

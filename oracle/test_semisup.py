@@ -113,3 +113,23 @@ def inference(vs, FLAGS, pc, one_hot_vec, batch_size, prefix='', use_boxpc_fit_p
     pred_orient_reg = np.array([heading_residuals[i, heading_cls[i]] for i in range(n)])
     pred_dims_reg = np.vstack([size_residuals[i, size_cls[i], :] for i in range(n)])
     return pred_seg, centers, heading_cls, pred_orient_reg, size_cls, pred_dims_reg, scores
+
+
+def inference_scores(logits, heading_scores, heading_residuals, size_scores, size_residuals, fit_prob=None):
+    """The per-batch numpy block of test_semisup.inference (test_semisup.py:236-258) on given fetches (float64):
+    -> pred_seg, mask_mean_prob, heading_cls, heading_res, size_cls, size_res, scores."""
+    logits = np.asarray(logits, dtype=np.float64)
+    hs, ss = np.asarray(heading_scores, dtype=np.float64), np.asarray(size_scores, dtype=np.float64)
+    seg_prob = softmax(logits)[:, :, 1]
+    seg_mask = np.argmax(logits, 2)
+    mask_mean_prob = np.sum(seg_prob * seg_mask, 1) / (np.sum(seg_mask, 1) + 1)
+    heading_prob = np.max(softmax(hs), 1)
+    size_prob = np.max(softmax(ss), 1)
+    scores = np.log(mask_mean_prob + 0.01) + np.log(heading_prob + 0.01) + np.log(size_prob + 0.01)
+    if fit_prob is not None:
+        scores = scores + np.log(np.asarray(fit_prob, dtype=np.float64) + 0.01)
+    heading_cls, size_cls = np.argmax(hs, 1), np.argmax(ss, 1)
+    n = logits.shape[0]
+    heading_res = np.array([heading_residuals[i, heading_cls[i]] for i in range(n)])
+    size_res = np.vstack([size_residuals[i, size_cls[i], :] for i in range(n)])
+    return seg_mask, mask_mean_prob, heading_cls, heading_res, size_cls, size_res, scores

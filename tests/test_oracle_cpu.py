@@ -284,3 +284,38 @@ def test_perturb_box_to_diff_ious_bands_and_streams():
         ref.uniform(size=7 * r3[7])
         assert rng.uniform() == ref.uniform()                     # exactly 7 draws per attempt were consumed
         assert np.allclose(r3[0], c + r3[4]) and np.allclose(r3[1], s + r3[5]) and np.isclose(r3[2], h + r3[6])
+
+
+# ----------------------------------------------------------------------------- inference post-processing
+def test_oracle_label_conversions_hand_cases():
+    from oracle import roi_seg_box3d_dataset as o
+    from transferable3d_b200.constants import type_mean_size
+    # class2angle: bin 9 of 12 = 270 deg -> wrapped to -90 deg; bin 3 + 0.1 stays
+    assert abs(o.class2angle(9, 0.0, 12) - (-np.pi / 2)) < 1e-12
+    assert abs(o.class2angle(3, 0.1, 12) - (np.pi / 2 + 0.1)) < 1e-12
+    assert abs(o.class2angle(9, 0.0, 12, to_label_format=False) - 1.5 * np.pi) < 1e-12
+    # rotate_pc_along_y by +90 deg: (x, z) = (1, 0) -> (0, 1)  [x' = c x - s z, z' = s x + c z]
+    p = o.rotate_pc_along_y(np.array([[1.0, 5.0, 0.0]]), np.pi / 2)
+    assert np.allclose(p, [[0.0, 5.0, 1.0]], atol=1e-12)
+    # from_prediction_to_label_format: chair (class 3), zero residuals, rot_angle = pi/2, centre (0, 1, 2):
+    # centre is rotated by -pi/2: (x, z) = (0, 2) -> (2, 0); ty = 1 + h/2; ry = bin 0 + rot
+    h, w, l, tx, ty, tz, ry = o.from_prediction_to_label_format(np.array([0.0, 1.0, 2.0]), 0, 0.0, 3, np.zeros(3), np.pi / 2)
+    ml, mw, mh = type_mean_size['chair']
+    assert (h, w, l) == (mh, mw, ml)
+    assert np.allclose([tx, ty, tz, ry], [2.0, 1.0 + mh / 2, 0.0, np.pi / 2], atol=1e-12)
+
+
+def test_oracle_inference_scores_hand_case():
+    from oracle import test_semisup as o
+    # 1 frustum, 3 points: logits (0,0) tie -> class 0; (0, ln 3) -> in, p1 = 3/4; (1, 0) -> out
+    logits = np.array([[[0.0, 0.0], [0.0, np.log(3.0)], [1.0, 0.0]]])
+    hs = np.zeros((1, 12)); hs[0, 5] = np.log(12.0)       # softmax max = 12 / (11 + 12)
+    ss = np.zeros((1, 10)); ss[0, 2] = np.log(10.0)       # 10 / 19
+    hr = np.arange(12.0)[None] * 0.1
+    sr = np.arange(30.0).reshape(1, 10, 3)
+    seg, mmp, hc, hres, sc, sres, score = o.inference_scores(logits, hs, hr, ss, sr, fit_prob=np.array([0.5]))
+    assert seg.tolist() == [[0, 1, 0]]
+    assert abs(mmp[0] - 0.75 / 2.0) < 1e-12                 # / (count + 1)
+    assert hc[0] == 5 and abs(hres[0] - 0.5) < 1e-12 and sc[0] == 2 and sres[0].tolist() == [6.0, 7.0, 8.0]
+    want = np.log(0.375 + 0.01) + np.log(12.0 / 23.0 + 0.01) + np.log(10.0 / 19.0 + 0.01) + np.log(0.51)
+    assert abs(score[0] - want) < 1e-12

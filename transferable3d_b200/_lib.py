@@ -65,6 +65,12 @@ class t3d_perturb_args(_c.Structure):
                 [(n, _P) for n in ('new_center', 'new_size', 'new_heading', 'iou3d', 'd_center', 'd_size', 'd_angle', 'attempts')])
 
 
+class t3d_infer_score_args(_c.Structure):
+    _fields_ = ([(n, _P) for n in ('logits', 'heading_scores', 'heading_residuals', 'size_scores', 'size_residuals', 'fit_prob')] +
+                [(n, _I) for n in ('B', 'N', 'NH', 'NS')] +
+                [(n, _P) for n in ('pred_seg', 'mask_mean_prob', 'heading_cls', 'heading_res', 'size_cls', 'size_res', 'scores')])
+
+
 _L = _c.c_longlong
 _F = _c.c_float
 
@@ -118,6 +124,8 @@ SIGNATURES = {
     't3d_box3d_iou': (_I, [_P, _P, _I, _P, _P, _P]),
     't3d_compute_box3d_iou': (_I, [_c.POINTER(t3d_compute_iou_args), _P]),
     't3d_perturb_boxes': (_I, [_c.POINTER(t3d_perturb_args), _P]),
+    't3d_inference_scores': (_I, [_c.POINTER(t3d_infer_score_args), _P]),
+    't3d_prediction_to_label': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
 }
 
 _lib = None

@@ -8,6 +8,7 @@
 #include "train_ops.cuh"
 #include "loss_ops.cuh"
 #include "box_ops.cuh"
+#include "post_ops.cuh"
 #define T3D_SGEMM_WITH_EPILOGUES
 #include "sgemm.cuh"
 #define T3D_XGEMM_WITH_EPILOGUES
@@ -246,6 +247,31 @@ extern "C" int t3d_perturb_boxes(const t3d_perturb_args* a, t3d_stream_t stream)
                 a->angle_perturbation, (unsigned long long)a->seed, a->new_center, a->new_size, a->new_heading, a->iou3d,
                 a->d_center, a->d_size, a->d_angle, a->attempts};
   perturb_boxes_kernel<<<(a->B + 63) / 64, 64, 0, S(stream)>>>(k);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- inference post-processing
+extern "C" int t3d_inference_scores(const t3d_infer_score_args* a, t3d_stream_t stream) {
+  if (!a || !a->logits || !a->heading_scores || !a->heading_residuals || !a->size_scores || !a->size_residuals || !a->heading_cls ||
+      !a->heading_res || !a->size_cls || !a->size_res || !a->scores)
+    return T3D_ERR_ARG;
+  if (a->B <= 0 || a->N <= 0 || a->NH <= 0 || a->NS <= 0) return T3D_ERR_SHAPE;
+  if ((uintptr_t)a->logits & 7) return T3D_ERR_ALIGN;
+  InferScoreArgs k{a->logits, a->heading_scores, a->heading_residuals, a->size_scores, a->size_residuals, a->fit_prob, a->B, a->N,
+                   a->NH, a->NS, a->pred_seg, a->mask_mean_prob, a->heading_cls, a->heading_res, a->size_cls, a->size_res, a->scores};
+  inference_scores_kernel<<<a->B, 256, 0, S(stream)>>>(k);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_prediction_to_label(const float* center, const int* heading_cls, const float* heading_res, const int* size_cls,
+                                       const float* size_res, const float* rot_angle, const float* mean_size, int B, int NH,
+                                       float* out7, t3d_stream_t stream) {
+  if (!center || !heading_cls || !heading_res || !size_cls || !size_res || !rot_angle || !mean_size || !out7) return T3D_ERR_ARG;
+  if (B <= 0 || NH <= 0) return T3D_ERR_SHAPE;
+  prediction_to_label_kernel<<<(B + 127) / 128, 128, 0, S(stream)>>>(center, heading_cls, heading_res, size_cls, size_res, rot_angle,
+                                                                     mean_size, B, NH, out7);
   T3D_CHECK_LAUNCH();
   return 0;
 }

@@ -32,6 +32,15 @@ def get_precision():
     return _state['precision']
 
 
+def default_device():
+    """Device of the default variable store, else the current CUDA device (raises without one: no CPU fallback)."""
+    if _state['store'] is not None:
+        return _state['store'].device
+    if not torch.cuda.is_available():
+        raise _lib.T3DError('t3d_b200 ops need a CUDA device (no CPU fallback)')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
 def set_f32_engine(engine):
     """Engine of the fp32 GEMMs (fp32-mode layers, training steps): 'tc' = tcgen05 bf16 x 3 split (fp32-accurate,
     default), 'simt' = CUDA-core SGEMM, 'bf16' = tcgen05 with operands rounded to bf16 (one pass, fp32 accumulate).

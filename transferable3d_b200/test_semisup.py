@@ -197,3 +197,102 @@ def inference(sess, ops, pc, one_hot_vec, batch_size, prefix='', use_boxpc_fit_p
     pred_orient_reg = np.array([heading_residuals[i, heading_cls[i]] for i in range(n)])
     pred_dims_reg = np.vstack([size_residuals[i, size_cls[i], :] for i in range(n)])
     return pred_seg, centers, heading_cls, pred_orient_reg, size_cls, pred_dims_reg, scores
+
+
+def inference_scores(logits, heading_scores, heading_residuals, size_scores, size_residuals, fit_prob=None):
+    """The numpy block of inference() (test_semisup.py:236-258) for one batch, on the device (t3d_inference_scores).
+    Device tensors in -> dict of device tensors: pred_seg (B,N) uint8, mask_mean_prob, heading_cls, heading_res, size_cls,
+    size_res (B,3), scores."""
+    from ._lib import t3d_infer_score_args, load, check, ptr, stream
+    import ctypes
+    f = rt.f32
+    logits, hs, hr, ss, sr = f(logits), f(heading_scores), f(heading_residuals), f(size_scores), f(size_residuals)
+    fp = f(fit_prob) if fit_prob is not None else None
+    B, N = logits.shape[0], logits.shape[1]
+    dev = logits.device
+    out = {'pred_seg': torch.empty((B, N), dtype=torch.uint8, device=dev),
+           'mask_mean_prob': torch.empty((B,), dtype=torch.float32, device=dev),
+           'heading_cls': torch.empty((B,), dtype=torch.int32, device=dev),
+           'heading_res': torch.empty((B,), dtype=torch.float32, device=dev),
+           'size_cls': torch.empty((B,), dtype=torch.int32, device=dev),
+           'size_res': torch.empty((B, 3), dtype=torch.float32, device=dev),
+           'scores': torch.empty((B,), dtype=torch.float32, device=dev)}
+    a = t3d_infer_score_args(ptr(logits), ptr(hs), ptr(hr), ptr(ss), ptr(sr), ptr(fp), B, N, hs.shape[1], ss.shape[1],
+                             ptr(out['pred_seg']), ptr(out['mask_mean_prob']), ptr(out['heading_cls']), ptr(out['heading_res']),
+                             ptr(out['size_cls']), ptr(out['size_res']), ptr(out['scores']))
+    check(load().t3d_inference_scores(ctypes.byref(a), stream()))
+    return out
+
+
+def inference_device(sess, ops, pc, one_hot_vec, batch_size, prefix='', use_boxpc_fit_prob=False, oracle_mask=None):
+    """inference() with the post-processing on the device: the same 7-tuple (numpy), but per frustum only the prediction
+    crosses PCIe (N bytes of pred_seg + 10 floats) instead of the raw fetches (2 N + 67 floats).  pred_seg is uint8."""
+    assert pc.shape[0] % batch_size == 0
+    n, ep = pc.shape[0], ops['end_points']
+    parts = []
+    for i in range(n // batch_size):
+        sl = slice(i * batch_size, (i + 1) * batch_size)
+        feed_dict = {ops['pc_pl']: pc[sl, ...], ops['one_hot_vec_pl']: one_hot_vec[sl, :], ops['is_training_pl']: False}
+        if oracle_mask is not None:
+            feed_dict.update({ops['y_seg_pl']: oracle_mask[sl]})
+        run_ops = [ops['logits'], ep[prefix + 'center'], ep[prefix + 'heading_scores'], ep[prefix + 'heading_residuals'],
+                   ep[prefix + 'size_scores'], ep[prefix + 'size_residuals']]
+        if use_boxpc_fit_prob:
+            run_ops.append(ep['boxpc_fit_prob'])
+        res = sess.run(run_ops, feed_dict=feed_dict)
+        out = inference_scores(res[0], res[2], res[3], res[4], res[5], res[6] if use_boxpc_fit_prob else None)
+        out['center'] = res[1]
+        parts.append(out)
+    cat = lambda k: torch.cat([p[k] for p in parts], 0).cpu().numpy()
+    return (cat('pred_seg'), cat('center').astype(np.float64), cat('heading_cls').astype(np.int64), cat('heading_res').astype(np.float64),
+            cat('size_cls').astype(np.int64), cat('size_res').astype(np.float64), cat('scores').astype(np.float64))
+
+
+def write_detection_results(result_dir, test_classes, id_list, type_list, box2d_list, center_list, heading_cls_list, heading_res_list,
+                            size_cls_list, size_res_list, rot_angle_list, score_list):
+    """test_semisup.py:262-294: one `<class>_pred.txt` per class, lines
+    `idx cls -1 -1 -10 x1 y1 x2 y2 h w l tx ty tz ry score` (%f); the label conversion runs as one batched kernel."""
+    import os
+    from .roi_seg_box3d_dataset import from_prediction_to_label_format_batch
+    assert result_dir is not None
+    if not os.path.exists(result_dir):
+        os.mkdir(result_dir)
+    cls_files = {c: open(os.path.join(result_dir, c + '_pred.txt'), 'w') for c in test_classes}
+    if len(center_list) > 0:
+        lab = from_prediction_to_label_format_batch(np.asarray(center_list), np.asarray(heading_cls_list), np.asarray(heading_res_list),
+                                                    np.asarray(size_cls_list), np.asarray(size_res_list), np.asarray(rot_angle_list))
+        lab = lab.cpu().numpy().astype(np.float64)
+    for i in range(len(center_list)):
+        box2d, cls_name = box2d_list[i], type_list[i]
+        h, w, l, tx, ty, tz, ry = lab[i]
+        cls_files[cls_name].write('%d %s -1 -1 -10 %f %f %f %f %f %f %f %f %f %f %f %f\n' % (
+            id_list[i], cls_name, box2d[0], box2d[1], box2d[2], box2d[3], h, w, l, tx, ty, tz, ry, score_list[i]))
+    for f in cls_files.values():
+        f.close()
+
+
+def write_gt_results(result_dir, test_classes, test_dataset):
+    """test_semisup.py:296-327: `<class>_gt.txt`, lines `idx cls -1 -1 -10 x1 y1 x2 y2 h w l tx ty tz heading`.
+    test_dataset needs idx_l, box2d_l, cls_type_l, size_l, heading_l and get_box3d_center(i)."""
+    import os
+    assert result_dir is not None
+    if not os.path.exists(result_dir):
+        os.mkdir(result_dir)
+    cls_files = {c: open(os.path.join(result_dir, c + '_gt.txt'), 'w') for c in test_classes}
+    for i in range(len(test_dataset)):
+        box2d, cls_name = test_dataset.box2d_l[i], test_dataset.cls_type_l[i]
+        l, w, h = test_dataset.size_l[i]
+        tx, ty, tz = test_dataset.get_box3d_center(i)
+        cls_files[cls_name].write('%d %s -1 -1 -10 %f %f %f %f %f %f %f %f %f %f %f\n' % (
+            test_dataset.idx_l[i], cls_name, box2d[0], box2d[1], box2d[2], box2d[3], h, w, l, tx, ty, tz, test_dataset.heading_l[i]))
+    for f in cls_files.values():
+        f.close()
+
+
+def fill_files(output_dir, to_fill_filename_list):
+    """test_semisup.py:329-334."""
+    import os
+    for filename in to_fill_filename_list:
+        filepath = os.path.join(output_dir, filename)
+        if not os.path.exists(filepath):
+            open(filepath, 'w').close()
