@@ -28,6 +28,14 @@ namespace t3d {
 
 constexpr int kXgBM = 128, kXgBN = 128, kXgBK = 32;
 constexpr int kXgThreads = 288;
+#ifndef XG_SETS
+#define XG_SETS 2
+#endif
+#ifndef XG_MINB
+#define XG_MINB 2
+#endif
+constexpr int kXgSets = XG_SETS;                               // register sets of the loaders (stages in flight + 1)
+constexpr int kXgMinBlocks = XG_MINB;                          // CTAs per SM the register budget is compiled for
 constexpr int kXgMaxKChunk = 2048;                            // longest K range accumulated in TMEM by one CTA
 constexpr uint32_t kXgImage = 128 * 128;                       // bytes of one [128 x 64] bf16 image
 constexpr uint32_t kXgBars = 6 * kXgImage;                     // barrier block offset
@@ -185,19 +193,22 @@ __device__ __forceinline__ void xg_loader(const float* __restrict__ P, long long
     if (lane == 0) mbar_arrive(full0 + 8u * s);
     tr.mark(0x30);
   };
-  float ra[32], rb[32];
-  load(0, ra);
+  // kXgSets register sets: stage `it` lives in set it % kXgSets; kXgSets - 1 stages are in flight while one is consumed
+  float r[kXgSets][32];
+#pragma unroll
+  for (int j = 0; j < kXgSets - 1; ++j) if (j < nst) load(j, r[j]);
   tr.mark(0x10);
-  int it = 0;
-  for (; it + 1 < nst; it += 2) {
-    load(it + 1, rb);
-    tr.mark(0x10);
-    emit(it, ra);
-    if (it + 2 < nst) load(it + 2, ra);
-    tr.mark(0x10);
-    emit(it + 1, rb);
+  for (int it0 = 0; it0 < nst; it0 += kXgSets) {
+#pragma unroll
+    for (int j = 0; j < kXgSets; ++j) {
+      const int it = it0 + j;
+      if (it < nst) {
+        if (it + kXgSets - 1 < nst) load(it + kXgSets - 1, r[(j + kXgSets - 1) % kXgSets]);
+        tr.mark(0x10);
+        emit(it, r[j]);
+      }
+    }
   }
-  if (it < nst) emit(it, ra);
 }
 
 struct XgTile {
@@ -313,7 +324,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // ---- t3d_gemm_f32 (same contract as gemm_f32_kernel, train_ops.cuh): C = A.B (+ bias by split 0); split-K partial tiles
 // are added into a zero-initialised C with vector reductions.
 template <bool A_UNIT_K, bool B_UNIT_K, int PARTS>
-__global__ void __launch_bounds__(kXgThreads, 2) xgemm_kernel(const GemmArgs a, const XgOperands o) {
+__global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xgemm_kernel(const GemmArgs a, const XgOperands o) {
   extern __shared__ uint8_t xg_smem[];
   XgTile t;
   xg_mainloop<A_UNIT_K, B_UNIT_K, PARTS>(o, xg_smem, t);
@@ -357,7 +368,7 @@ __global__ void __launch_bounds__(kXgThreads, 2) xgemm_kernel(const GemmArgs a, 
 // ---- t3d_linear_f32 (same contract as linear_f32_kernel, simt_ops.cuh): Y = act(X.W + bias + gbias[row / rows_per_group])
 // * rowmask, optional max over the rows of each group.
 template <int PARTS>
-__global__ void __launch_bounds__(kXgThreads, 2) xlinear_kernel(const LinearArgs a, const XgOperands o) {
+__global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xlinear_kernel(const LinearArgs a, const XgOperands o) {
   extern __shared__ uint8_t xg_smem[];
   XgTile t;
   xg_mainloop<true, false, PARTS>(o, xg_smem, t);
