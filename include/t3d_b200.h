@@ -181,6 +181,15 @@ int t3d_gemm_f32(const float* A, long long sam, long long sak, const float* B, l
  *                 of the training steps (rel 1e-2 class accuracy), one tensor-core pass instead of six.
  * The reference computes these layers with tf.nn.conv2d / tf.matmul in fp32 (models/tf_util.py:1308,1489). */
 int t3d_set_f32_engine(int engine);
+/* Same calls with a caller-owned device workspace (16-byte aligned, >= t3d_gemm_ws_bytes(N, K) bytes, private to the stream):
+ * when A / X is k-contiguous, M >= 4096 and K <= 2048 the tensor-core engines split the small operand once per call into
+ * the workspace instead of once per row tile.  ws == NULL is the plain call. */
+size_t t3d_gemm_ws_bytes(int N, int K);
+int t3d_gemm_f32_ws(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
+                    int ldc, int M, int N, int K, int splitk, const float* bias, void* ws, size_t ws_bytes, t3d_stream_t stream);
+int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* gbias,
+                      int rows_per_group, float* Y, int ldy, int M, int K, int N, int act, const float* rowmask,
+                      float* gmax, void* ws, size_t ws_bytes, t3d_stream_t stream);
 int t3d_get_f32_engine(void);
 /* mode 0: o0 = sum_r d, o1 = sum_r d^2 with d = x - y[c] when y != NULL (a per-column shift, e.g. row 0 of X: keeps the
  * variance E[d^2] - E[d]^2 free of cancellation), else d = x; mode 1: o0 = sum_r dy, o1 = sum_r dy*xhat with dy = X*act'(out), xhat=(y-mean)*rstd

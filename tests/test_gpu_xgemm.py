@@ -42,7 +42,7 @@ def _ulp_err(C, a, b):
     return float(((C.double() - ref).abs() / scale).max()) / 2.0 ** -24
 
 
-SHAPES = [(256, 128, 128), (384, 256, 96), (1000, 200, 333), (128, 64, 32), (130, 515, 70), (4096, 512, 256)]
+SHAPES = [(256, 128, 128), (384, 256, 96), (1000, 200, 333), (128, 64, 32), (130, 515, 70), (4096, 512, 256), (4500, 200, 333)]
 
 
 @pytest.mark.parametrize('a_unit_k,b_unit_k', [(True, False), (True, True), (False, False), (False, True)])
@@ -103,10 +103,11 @@ def test_split_is_exact_for_full_mantissas():
     assert torch.equal(C[:, :64], 4.0 * a) and float(C[:, 64:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('G', [6, 20])                 # M = 1536: B split per tile; M = 5120: pre-split B (workspace path)
 @pytest.mark.parametrize('act', [None, 'relu', 'leaky_relu', 'tanh'])
-def test_linear_epilogues(act):
+def test_linear_epilogues(act, G):
     rt = _rt()
-    G, R, K, N = 6, 256, 128, 200                     # 6 groups of 256 rows
+    R, K, N = 256, 128, 200                           # G groups of 256 rows
     M = G * R
     g = torch.Generator(device='cuda').manual_seed(11)
     x = torch.randn(M, K, generator=g, device='cuda')
@@ -157,11 +158,12 @@ def test_engines_agree_on_a_training_layer():
         assert e_tc < 4.0 * e_simt + 1e-6, '%s: tcgen05 engine %.3g vs CUDA cores %.3g' % (name, e_tc, e_simt)
 
 
-def test_bf16_engine_is_a_bf16_gemm():
+@pytest.mark.parametrize('M', [1024, 8192])            # without / with the pre-split workspace path
+def test_bf16_engine_is_a_bf16_gemm(M):
     """Engine 'bf16': operands rounded to nearest bf16, fp32 accumulation -- equals a float64 matmul of the rounded inputs
     up to accumulation order."""
     rt = _rt()
-    M, K, N = 1024, 256, 384
+    K, N = 256, 384
     g = torch.Generator(device='cuda').manual_seed(9)
     x = torch.randn(M, K, generator=g, device='cuda')
     w = torch.randn(K, N, generator=g, device='cuda') * 0.1

@@ -101,6 +101,9 @@ SIGNATURES = {
     't3d_seg_stage2_bf16': (_I, [_P, _P, _P, _P, _I, _I, _P]),
     't3d_set_trace_buffer': (_I, [_P]),
     't3d_gemm_f32': (_I, [_P, _L, _L, _P, _L, _L, _P, _I, _I, _I, _I, _I, _P, _P]),
+    't3d_gemm_ws_bytes': (_c.c_size_t, [_I, _I]),
+    't3d_gemm_f32_ws': (_I, [_P, _L, _L, _P, _L, _L, _P, _I, _I, _I, _I, _I, _P, _P, _c.c_size_t, _P]),
+    't3d_linear_f32_ws': (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _c.c_size_t, _P]),
     't3d_set_f32_engine': (_I, [_I]),
     't3d_get_f32_engine': (_I, []),
     't3d_colstats': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
@@ -177,5 +180,24 @@ def stream():
     return _P(torch.cuda.current_stream().cuda_stream)
 
 
+_WS_CALLS = ('t3d_gemm_f32', 't3d_linear_f32')
+_WS_BYTES = 16 << 20          # >= t3d_gemm_ws_bytes(1152, 2048): every layer of the reference's networks
+_workspaces = {}
+
+
+def gemm_workspace():
+    """Per (device, stream) scratch for the pre-split operand of the tensor-core GEMMs (caller-owned: the library never
+    allocates)."""
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = _workspaces[key] = torch.empty(_WS_BYTES, dtype=torch.uint8, device='cuda')
+    return ws
+
+
 def call(name, *args):
+    if name in _WS_CALLS:
+        ws = gemm_workspace()
+        args = args[:-1] + (ptr(ws), ws.numel(), args[-1])
+        name += '_ws'
     check(getattr(load(), name)(*args))

@@ -61,20 +61,38 @@ static int xg_prepare(Kern kern) {      // opt in to 97 KB of dynamic shared mem
 }
 static inline bool xg_fits(int M, int N, int K) { return g_f32_engine != 0 && M >= 128 && N >= 64 && K >= 32; }
 
-extern "C" int t3d_linear_f32(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* gbias,
-                              int rows_per_group, float* Y, int ldy, int M, int K, int N, int act, const float* rowmask,
-                              float* gmax, t3d_stream_t stream) {
+// B_PRE path: forward / dgrad with the small operand pre-split once per call into the caller's workspace (xgemm.cuh)
+static inline bool xg_pre_ok(int M, int N, int K, const void* ws, size_t ws_bytes) {
+  return ws != nullptr && (((uintptr_t)ws) & 15) == 0 && M >= 4096 && K <= kXgMaxKChunk && ws_bytes >= xg_pre_bytes(N, K);
+}
+
+extern "C" size_t t3d_gemm_ws_bytes(int N, int K) { return (N > 0 && K > 0) ? xg_pre_bytes(N, K) : 0; }
+
+extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* gbias,
+                                 int rows_per_group, float* Y, int ldy, int M, int K, int N, int act, const float* rowmask,
+                                 float* gmax, void* ws, size_t ws_bytes, t3d_stream_t stream) {
   if (!X || !W || (!Y && !gmax)) return T3D_ERR_ARG;
   if (M <= 0 || K <= 0 || N <= 0 || act < 0 || act > 3) return T3D_ERR_SHAPE;
   if ((gbias || gmax) && rows_per_group <= 0) return T3D_ERR_SHAPE;
   LinearArgs a{X, ldx, W, ldw, bias, gbias, rows_per_group, Y, ldy, M, K, N, act, rowmask, gmax};
   if (xg_fits(M, N, K)) {                    // tensor cores, bf16 x 3 split (xgemm.cuh)
-    static int prepared = xg_prepare(xlinear_kernel<3>) | xg_prepare(xlinear_kernel<1>);
+    static int prepared = xg_prepare(xlinear_kernel<3>) | xg_prepare(xlinear_kernel<1>) | xg_prepare(xlinear_pre_kernel<3>) |
+                          xg_prepare(xlinear_pre_kernel<1>);
     if (prepared != 0) return prepared;
     const int ntm = (M + kXgBM - 1) / kXgBM, ntn = (N + kXgBN - 1) / kXgBN;
-    XgOperands o{X, ldx, W, ldw, M, N, K, (K + kXgBK - 1) / kXgBK * kXgBK, xg_aligned16(X, ldx) ? 1 : 0, 0, ntn, g_trace};
-    if (g_f32_engine == 1) xlinear_kernel<3><<<dim3((unsigned)ntm * ntn, 1), kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
-    else xlinear_kernel<1><<<dim3((unsigned)ntm * ntn, 1), kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+    const int parts = g_f32_engine == 1 ? 3 : 1;
+    XgOperands o{X, ldx, W, ldw, M, N, K, (K + kXgBK - 1) / kXgBK * kXgBK, xg_aligned16(X, ldx) ? 1 : 0, 0, ntn, g_trace, nullptr, 0};
+    const dim3 grid((unsigned)ntm * ntn, 1);
+    if (xg_pre_ok(M, N, K, ws, ws_bytes)) {
+      o.bpre = reinterpret_cast<const uint8_t*>(ws);
+      o.nkb = (K + 63) / 64;
+      xg_presplit_kernel<<<dim3(o.nkb, ntn), 256, 0, S(stream)>>>(W, ldw, 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
+      if (parts == 3) xlinear_pre_kernel<3><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+      else xlinear_pre_kernel<1><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+    } else {
+      if (parts == 3) xlinear_kernel<3><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+      else xlinear_kernel<1><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+    }
     T3D_CHECK_LAUNCH();
     return 0;
   }
@@ -89,6 +107,12 @@ extern "C" int t3d_linear_f32(const float* X, int ldx, const float* W, int ldw, 
   linear_f32_kernel<<<grid, 256, 0, S(stream)>>>(a);
   T3D_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int t3d_linear_f32(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* gbias,
+                              int rows_per_group, float* Y, int ldy, int M, int K, int N, int act, const float* rowmask,
+                              float* gmax, t3d_stream_t stream) {
+  return t3d_linear_f32_ws(X, ldx, W, ldw, bias, gbias, rows_per_group, Y, ldy, M, K, N, act, rowmask, gmax, nullptr, 0, stream);
 }
 
 extern "C" int t3d_mask_centroid(const float* logits, const float* pc, int B, int N, int C, float* mask, int* count,
@@ -476,8 +500,9 @@ extern "C" int t3d_seg_stage2_bf16(const void* point_feat, const float* gbias, c
 }
 
 // ----------------------------------------------------------------------------- training-step kernels
-extern "C" int t3d_gemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
-                            int ldc, int M, int N, int K, int splitk, const float* bias, t3d_stream_t stream) {
+extern "C" int t3d_gemm_f32_ws(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
+                               int ldc, int M, int N, int K, int splitk, const float* bias, void* ws, size_t ws_bytes,
+                               t3d_stream_t stream) {
   if (!A || !B || !C) return T3D_ERR_ARG;
   if (M <= 0 || N <= 0 || K <= 0 || splitk <= 0 || ldc < N) return T3D_ERR_SHAPE;
   if ((sam != 1 && sak != 1) || (sbk != 1 && sbn != 1)) return T3D_ERR_SHAPE;
@@ -487,7 +512,8 @@ extern "C" int t3d_gemm_f32(const float* A, long long sam, long long sak, const 
     static int prepared = xg_prepare(xgemm_kernel<true, true, 3>) | xg_prepare(xgemm_kernel<true, false, 3>) |
                           xg_prepare(xgemm_kernel<false, true, 3>) | xg_prepare(xgemm_kernel<false, false, 3>) |
                           xg_prepare(xgemm_kernel<true, true, 1>) | xg_prepare(xgemm_kernel<true, false, 1>) |
-                          xg_prepare(xgemm_kernel<false, true, 1>) | xg_prepare(xgemm_kernel<false, false, 1>);
+                          xg_prepare(xgemm_kernel<false, true, 1>) | xg_prepare(xgemm_kernel<false, false, 1>) |
+                          xg_prepare(xgemm_pre_kernel<3>) | xg_prepare(xgemm_pre_kernel<1>);
     if (prepared != 0) return prepared;
     // The tensor core adds each 16-deep partial sum into the fp32 accumulator with truncation, a bias of ~0.5 ulp per
     // step (measured: 700 ulp of sum|a||b| after K = 20000, 25 after K = 600); K chunks are kept <= 2048 so that long
@@ -501,8 +527,18 @@ extern "C" int t3d_gemm_f32(const float* A, long long sam, long long sak, const 
     const bool ak = (sak == 1), bk = (sbk == 1 && sbn != 1);
     const int ntm = (M + kXgBM - 1) / kXgBM, ntn = (N + kXgBN - 1) / kXgBN;
     const long long lda = ak ? sam : sak, ldb = bk ? sbn : sbk;
-    XgOperands o{A, lda, B, ldb, M, N, K, kchunk, (ak && xg_aligned16(A, lda)) ? 1 : 0, (bk && xg_aligned16(B, ldb)) ? 1 : 0, ntn, g_trace};
+    XgOperands o{A, lda, B, ldb, M, N, K, kchunk, (ak && xg_aligned16(A, lda)) ? 1 : 0, (bk && xg_aligned16(B, ldb)) ? 1 : 0, ntn, g_trace, nullptr, 0};
     const dim3 grid((unsigned)ntm * ntn, nz);
+    if (ak && nz == 1 && sk == 1 && xg_pre_ok(M, N, K, ws, ws_bytes)) {     // forward / dgrad: pre-split B
+      o.bpre = reinterpret_cast<const uint8_t*>(ws);
+      o.nkb = (K + 63) / 64;
+      const int parts = g_f32_engine == 1 ? 3 : 1;
+      xg_presplit_kernel<<<dim3(o.nkb, ntn), 256, 0, S(stream)>>>(B, ldb, bk ? 1 : 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
+      if (parts == 3) xgemm_pre_kernel<3><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+      else xgemm_pre_kernel<1><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+      T3D_CHECK_LAUNCH();
+      return 0;
+    }
 #define XG_LAUNCH(P)                                                                                     \
   do {                                                                                                   \
     if (ak && bk) xgemm_kernel<true, true, P><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);        \
@@ -532,6 +568,11 @@ extern "C" int t3d_gemm_f32(const float* A, long long sam, long long sak, const 
   gemm_f32_kernel<<<grid, 256, 0, S(stream)>>>(a);
   T3D_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int t3d_gemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
+                            int ldc, int M, int N, int K, int splitk, const float* bias, t3d_stream_t stream) {
+  return t3d_gemm_f32_ws(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias, nullptr, 0, stream);
 }
 
 extern "C" int t3d_colstats(const float* X, const float* out, const float* y, const float* mean, const float* rstd, float* o0,

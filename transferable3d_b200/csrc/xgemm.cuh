@@ -34,6 +34,13 @@ constexpr int kXgThreads = 288;
 #ifndef XG_MINB
 #define XG_MINB 2
 #endif
+#ifndef XG_PRE_SETS
+#define XG_PRE_SETS 3
+#endif
+constexpr int kXgPreSets = XG_PRE_SETS;                        // register sets (16 values each) of the pre-split-B loaders
+#ifndef XG_DBG
+#define XG_DBG 0      // measurement only: 1 = no global loads (A), 2 = no image stores, 4 = no MMAs, 8 = no B copy, 16 = no epilogue
+#endif
 constexpr int kXgSets = XG_SETS;                               // register sets of the loaders (stages in flight + 1)
 constexpr int kXgMinBlocks = XG_MINB;                          // CTAs per SM the register budget is compiled for
 constexpr int kXgMaxKChunk = 2048;                            // longest K range accumulated in TMEM by one CTA
@@ -49,6 +56,8 @@ struct XgOperands {
   int vecA, vecB;                     // 128-bit loads allowed for a UNIT_K operand (16-byte aligned base and ld % 4 == 0)
   int ntn;                            // number of column tiles; blockIdx.x = m_tile * ntn + n_tile
   unsigned long long* trace;          // debug: clock64 timeline of the middle CTA (t3d_set_trace_buffer) or null
+  const uint8_t* bpre;                // B_PRE kernels: pre-split images of B, [n_tile][k_block of 64][part][16 KB], else null
+  int nkb;                            // k blocks per n tile in bpre
 };
 
 // row of the tile handled by (warp w of the operand's 4, iteration i, lane) in the UNIT_K mapping: a warp-wide 128-bit
@@ -211,6 +220,132 @@ __device__ __forceinline__ void xg_loader(const float* __restrict__ P, long long
   }
 }
 
+// ---- pre-split B (forward / dgrad: B is the small weight matrix, the same for every row tile) -------------------------
+// A pre-pass splits B once per call into the exact shared-memory images ([128 rows x 64 k] SW128 blocks, 3 parts) in a
+// caller-provided workspace; the main kernel then brings its B stage in with 16-byte cp.async copies (no registers, no
+// split arithmetic, no per-CTA re-splitting of the same weights) and all 8 loader warps split A, 16 values per thread
+// and stage instead of 32.
+constexpr size_t kXgPreBlockBytes = 3 * (size_t)kXgImage;       // one (n tile, k block): 3 parts x 16 KB
+inline size_t xg_pre_bytes(int N, int K) { return (size_t)((N + kXgBN - 1) / kXgBN) * ((K + 63) / 64) * kXgPreBlockBytes; }
+
+__global__ void __launch_bounds__(256) xg_presplit_kernel(const float* __restrict__ B, long long ldb, int unit_k, int N, int K,
+                                                         int parts, uint8_t* __restrict__ ws) {
+  const int kb = blockIdx.x, nt = blockIdx.y;
+  uint8_t* dst = ws + ((size_t)nt * gridDim.x + kb) * kXgPreBlockBytes;
+  for (int e = threadIdx.x; e < 128 * 64; e += 256) {
+    const int r = unit_k ? (e >> 6) : (e & 127), kk = unit_k ? (e & 63) : (e >> 7);
+    const int n = nt * kXgBN + r, k = kb * 64 + kk;
+    float v = 0.0f;
+    if (n < N && k < K) v = unit_k ? B[(long long)n * ldb + k] : B[(long long)k * ldb + n];
+    const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)(kk >> 3)) + (uint32_t)(kk & 7) * 2u;
+    if (parts == 1) {
+      *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16_rn(v);
+    } else {
+      uint32_t h, m, l;
+      xg_split(v, h, m, l);
+      *reinterpret_cast<uint16_t*>(dst + off) = (uint16_t)(h >> 16);
+      *reinterpret_cast<uint16_t*>(dst + kXgImage + off) = (uint16_t)(m >> 16);
+      *reinterpret_cast<uint16_t*>(dst + 2 * kXgImage + off) = (uint16_t)(l >> 16);
+    }
+  }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// loader warp w of 8 (k-contiguous A, pre-split B): rows w*16 .. w*16+15 of the A tile + 1/8 of the B stage copy
+template <int PARTS>
+__device__ __forceinline__ void xg_loader_pre(const float* __restrict__ P, long long ld, int row0, int nrows, int kend, bool vec,
+                                              uint32_t a_img, uint32_t b_img, const uint8_t* __restrict__ bsrc, int w, int lane, int nst,
+                                              uint32_t full0, uint32_t empty0, XgTracer& tr) {
+  const int rsub = lane >> 3, c = lane & 7;
+  auto rowof = [&](int i) { return w * 16 + (i >> 1) * 8 + (i & 1) * 2 + (rsub & 1) * 4 + (rsub >> 1); };
+  const int row = row0 + rowof(0), kofs = 4 * c;
+  const float* p = P + (long long)row * ld + kofs;
+  const bool rows_full = (row0 + w * 16 + 16 <= nrows) && vec;
+  const long long ld2 = 2 * ld, ld6 = 6 * ld;
+  auto load = [&](int it, float (&r)[16]) {
+    const int k0 = it * kXgBK;
+    const float* q = p + k0;
+    if (XG_DBG & 1) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) r[e] = (float)(it + e);
+    } else if (rows_full && k0 + kXgBK <= kend) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(q));
+        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        q += (i & 1) ? ld6 : ld2;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ro = (i >> 1) * 8 + (i & 1) * 2;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) r[4 * i + e] = (row + ro < nrows && k0 + kofs + e < kend) ? __ldg(q + (long long)ro * ld + e) : 0.0f;
+      }
+    }
+  };
+  const int tid = w * 32 + lane;
+  auto emit = [&](int it, const float (&r)[16]) {
+    const int s = it & 1;
+    mbar_wait_backoff(empty0 + 8u * s, ((it >> 1) & 1) ^ 1);
+    tr.mark(0x20);
+    {   // B stage: PARTS x 128 rows x 4 chunks of 16 B, same swizzled offsets in the workspace block and in shared memory
+      const uint8_t* blk = bsrc + (size_t)(it >> 1) * kXgPreBlockBytes;
+#pragma unroll
+      for (int j = 0; j < ((XG_DBG & 8) ? 0 : PARTS * 2); ++j) {
+        const int id = tid + 256 * j, part = id >> 9, rem = id & 511;
+        const uint32_t off = (uint32_t)part * kXgImage + sw128_offset((uint32_t)(rem >> 2), (uint32_t)(4 * s + (rem & 3)));
+        cp_async16(b_img + off, blk + off);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < ((XG_DBG & 2) ? 0 : 4); ++i) {
+      const uint32_t addr = a_img + sw128_offset((uint32_t)rowof(i), (uint32_t)(4 * s + (c >> 1))) + (uint32_t)(c & 1) * 8u;
+      if (PARTS == 1) {
+        st_shared_v2(addr, xg_pack_rn(r[4 * i], r[4 * i + 1]), xg_pack_rn(r[4 * i + 2], r[4 * i + 3]));
+      } else {
+        uint32_t h[4], m[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) xg_split(r[4 * i + e], h[e], m[e], l[e]);
+        st_shared_v2(addr, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]));
+        st_shared_v2(addr + kXgImage, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]));
+        st_shared_v2(addr + 2 * kXgImage, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]));
+      }
+    }
+    if (XG_DBG & 2) {      // keep the loads alive without the stores
+      uint32_t x = 0;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) x ^= __float_as_uint(r[e]);
+      if (x == 0xdeadbeefu) st_shared_v2(a_img, x, x);
+    }
+    cp_async_wait_all();
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(full0 + 8u * s);
+    tr.mark(0x30);
+  };
+  float r[kXgPreSets][16];
+#pragma unroll
+  for (int j = 0; j < kXgPreSets - 1; ++j) if (j < nst) load(j, r[j]);
+  for (int it0 = 0; it0 < nst; it0 += kXgPreSets) {
+#pragma unroll
+    for (int j = 0; j < kXgPreSets; ++j) {
+      const int it = it0 + j;
+      if (it < nst) {
+        if (it + kXgPreSets - 1 < nst) load(it + kXgPreSets - 1, r[(j + kXgPreSets - 1) % kXgPreSets]);
+        emit(it, r[j]);
+      }
+    }
+  }
+}
+
 struct XgTile {
   uint32_t sbase, tmem_base;
   int m0, n0, warp, lane;
@@ -219,7 +354,7 @@ struct XgTile {
 // Runs the main loop of one tile.  Returns in the 8 loader warps once both accumulators are complete in TMEM
 // (main: columns [0,128), small: [128,256) of the allocation; lane = tile row); warp 8 returns immediately after its
 // last commit.  Every thread must then call xg_finish().
-template <bool A_UNIT_K, bool B_UNIT_K, int PARTS>
+template <bool A_UNIT_K, bool B_UNIT_K, int PARTS, bool B_PRE = false>
 __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_raw, XgTile& t) {
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
@@ -251,7 +386,9 @@ __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_r
 
   if (warp < 8) {
     // ---------------------------------------------------------------- loaders: global fp32 -> registers -> 3 bf16 images
-    if (warp < 4) xg_loader<A_UNIT_K, PARTS>(o.A, o.lda, m0, o.M, kbeg, kend, o.vecA != 0, sbase, warp & 3, lane, nst, full(0), empty(0), tr);
+    if (B_PRE) xg_loader_pre<PARTS>(o.A, o.lda, m0, o.M, kend, o.vecA != 0, sbase, sbase + 3u * kXgImage,
+                                    o.bpre + (size_t)(blockIdx.x % o.ntn) * o.nkb * kXgPreBlockBytes, warp, lane, nst, full(0), empty(0), tr);
+    else if (warp < 4) xg_loader<A_UNIT_K, PARTS>(o.A, o.lda, m0, o.M, kbeg, kend, o.vecA != 0, sbase, warp & 3, lane, nst, full(0), empty(0), tr);
     else xg_loader<B_UNIT_K, PARTS>(o.B, o.ldb, n0, o.N, kbeg, kend, o.vecB != 0, sbase + 3u * kXgImage, warp & 3, lane, nst, full(0), empty(0), tr);
     mbar_wait_backoff(acc_full, 0);
     tc_fence_after();
@@ -275,6 +412,7 @@ __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_r
         const uint64_t b1 = make_sdesc_k128(b_img + off), b2 = make_sdesc_k128(b_img + kXgImage + off),
                        b3 = make_sdesc_k128(b_img + 2 * kXgImage + off);
         const uint32_t first = (it | ks) != 0;
+        if (XG_DBG & 4) continue;
         if (PARTS == 3) {
           umma_bf16_w(d_small, a3, b1, idesc, first);
           umma_bf16_w(d_small, a1, b3, idesc, 1);
@@ -320,59 +458,91 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// The warp's 32 x 32 chunk (thread = row, v = 32 consecutive columns) goes through a warp-private shared-memory patch
+// (the operand images are dead once acc_full has fired) and leaves as full 128-byte row segments: 8 lanes per row, 4 rows
+// per store instruction.  Storing straight from the accumulator layout (a 16-byte piece of 32 different lines per
+// instruction) cost 20 - 47 % of the kernel on the output-heavy forward layers (measured by removing the epilogue).
+// Patch rows are 144 bytes apart, so both the 128-bit writes (thread = row) and reads (8 lanes = one row) are
+// conflict-free.
+constexpr uint32_t kXgPatchRow = 144, kXgPatchBytes = 32 * kXgPatchRow;
+template <bool ATOMIC>
+__device__ __forceinline__ void xg_store_chunk(const XgTile& t, float* __restrict__ C, long long ldc, int M, int N, int row0, int col0,
+                                               const float (&v)[32]) {
+  const uint32_t patch = t.sbase + (uint32_t)t.warp * kXgPatchBytes;
+  __syncwarp();                                          // the previous chunk's reads are done
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    st_shared_v4(patch + (uint32_t)t.lane * kXgPatchRow + 16u * j, __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                 __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+  __syncwarp();
+  const int cq = (t.lane & 7) * 4, gn = col0 + cq;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = (t.lane >> 3) + 4 * i, gm = row0 + r;
+    const float4 x = ld_shared_f4(patch + (uint32_t)r * kXgPatchRow + 4u * cq);
+    if (gm >= M || gn >= N) continue;
+    float* c = C + (long long)gm * ldc + gn;
+    if (gn + 4 <= N && (((uintptr_t)c) & 15) == 0) {
+      if (ATOMIC) red_add_v4(c, x.x, x.y, x.z, x.w);
+      else *reinterpret_cast<float4*>(c) = x;
+    } else {
+      const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (gn + e < N) {
+          if (ATOMIC) atomicAdd(c + e, xs[e]);
+          else c[e] = xs[e];
+        }
+      }
+    }
+  }
+}
+
 #ifdef T3D_XGEMM_WITH_EPILOGUES
 // ---- t3d_gemm_f32 (same contract as gemm_f32_kernel, train_ops.cuh): C = A.B (+ bias by split 0); split-K partial tiles
 // are added into a zero-initialised C with vector reductions.
-template <bool A_UNIT_K, bool B_UNIT_K, int PARTS>
-__global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xgemm_kernel(const GemmArgs a, const XgOperands o) {
-  extern __shared__ uint8_t xg_smem[];
-  XgTile t;
-  xg_mainloop<A_UNIT_K, B_UNIT_K, PARTS>(o, xg_smem, t);
-  if (t.warp < 8) {
-    const int gm = t.m0 + (t.warp & 3) * 32 + t.lane;
+template <int PARTS>
+__device__ __forceinline__ void xg_epilogue_gemm(const GemmArgs& a, const XgTile& t) {
+  if (t.warp < 8 && !(XG_DBG & 16)) {
+    const int row0 = t.m0 + (t.warp & 3) * 32;
 #pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {
       const int c0 = (t.warp >> 2) * 64 + ch * 32;
       float v[32];
       xg_acc32<PARTS>(t, c0, v);
-      if (gm < a.M) {
-        float* crow = a.C + (size_t)gm * a.ldc;
+      if (a.bias && blockIdx.y == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int gn = t.n0 + c0 + j;
-          if (gn >= a.N) break;
-          if (a.bias && blockIdx.y == 0) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) if (gn + e < a.N) v[j + e] += a.bias[gn + e];
-          }
-          float* c = crow + gn;
-          if (gn + 4 <= a.N && (((uintptr_t)c) & 15) == 0) {
-            if (a.splitk > 1) red_add_v4(c, v[j], v[j + 1], v[j + 2], v[j + 3]);
-            else *reinterpret_cast<float4*>(c) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (gn + e < a.N) {
-                if (a.splitk > 1) atomicAdd(c + e, v[j + e]);
-                else c[e] = v[j + e];
-              }
-            }
-          }
-        }
+        for (int j = 0; j < 32; ++j) if (t.n0 + c0 + j < a.N) v[j] += a.bias[t.n0 + c0 + j];
       }
+      if (a.splitk > 1) xg_store_chunk<true>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v);
+      else xg_store_chunk<false>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v);
     }
   }
+}
+
+template <bool A_UNIT_K, bool B_UNIT_K, int PARTS>
+__global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xgemm_kernel(const GemmArgs a, const XgOperands o) {
+  extern __shared__ uint8_t xg_smem[];
+  XgTile t;
+  xg_mainloop<A_UNIT_K, B_UNIT_K, PARTS>(o, xg_smem, t);
+  xg_epilogue_gemm<PARTS>(a, t);
+  xg_finish(t);
+}
+// k-contiguous A, pre-split B (forward: B = W; dgrad: B = W^T)
+template <int PARTS>
+__global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xgemm_pre_kernel(const GemmArgs a, const XgOperands o) {
+  extern __shared__ uint8_t xg_smem[];
+  XgTile t;
+  xg_mainloop<true, false, PARTS, true>(o, xg_smem, t);
+  xg_epilogue_gemm<PARTS>(a, t);
   xg_finish(t);
 }
 
 // ---- t3d_linear_f32 (same contract as linear_f32_kernel, simt_ops.cuh): Y = act(X.W + bias + gbias[row / rows_per_group])
 // * rowmask, optional max over the rows of each group.
 template <int PARTS>
-__global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xlinear_kernel(const LinearArgs a, const XgOperands o) {
-  extern __shared__ uint8_t xg_smem[];
-  XgTile t;
-  xg_mainloop<true, false, PARTS>(o, xg_smem, t);
-  if (t.warp < 8) {
+__device__ __forceinline__ void xg_epilogue_linear(const LinearArgs& a, const XgTile& t) {
+  if (t.warp < 8 && !(XG_DBG & 16)) {
     const int gm = t.m0 + (t.warp & 3) * 32 + t.lane;
     const bool row_ok = gm < a.M;
     const int g = (a.rows_per_group > 0 && row_ok) ? gm / a.rows_per_group : 0;
@@ -397,21 +567,7 @@ __global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xlinear_kernel(const
         }
         v[j] = x;
       }
-      if (a.Y && row_ok) {
-        float* yrow = a.Y + (size_t)gm * a.ldy;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int gn = t.n0 + c0 + j;
-          if (gn >= a.N) break;
-          float* y = yrow + gn;
-          if (gn + 4 <= a.N && (((uintptr_t)y) & 15) == 0) {
-            *reinterpret_cast<float4*>(y) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) if (gn + e < a.N) y[e] = v[j + e];
-          }
-        }
-      }
+      if (a.Y) xg_store_chunk<false>(t, a.Y, a.ldy, a.M, a.N, t.m0 + (t.warp & 3) * 32, t.n0 + c0, v);
       if (a.gmax) {
         if (one_group) {      // values are >= 0 here (ReLU / mask); lane c ends up with the max of column c0 + c
 #pragma unroll
@@ -436,6 +592,22 @@ __global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xlinear_kernel(const
       }
     }
   }
+}
+
+template <int PARTS>
+__global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xlinear_kernel(const LinearArgs a, const XgOperands o) {
+  extern __shared__ uint8_t xg_smem[];
+  XgTile t;
+  xg_mainloop<true, false, PARTS>(o, xg_smem, t);
+  xg_epilogue_linear<PARTS>(a, t);
+  xg_finish(t);
+}
+template <int PARTS>
+__global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xlinear_pre_kernel(const LinearArgs a, const XgOperands o) {
+  extern __shared__ uint8_t xg_smem[];
+  XgTile t;
+  xg_mainloop<true, false, PARTS, true>(o, xg_smem, t);
+  xg_epilogue_linear<PARTS>(a, t);
   xg_finish(t);
 }
 #endif
