@@ -278,6 +278,25 @@ int t3d_prediction_to_label(const float* center, const int* heading_cls, const f
                             const float* size_res, const float* rot_angle, const float* mean_size /* [NS,3] (l,w,h) */,
                             int B, int NH, float* out7, t3d_stream_t stream);
 
+/* ---- detection evaluation ------------------------------------------------------------
+ * The matching loop of eval_det.eval_det_cls (sunrgbd_detection/eval_det.py:118-145) for one class: detections sorted by
+ * descending score, 3D IoU (box_util.box3d_iou, the get_iou hook of eval_det.py:63-69) against the ground-truth boxes of
+ * the same image, first-maximum / first-claim greedy matching -> tp, fp per detection (+ optional ovmax, jmax).
+ * Detections and boxes are grouped by image through CSR offsets; gt_det is ng bytes of scratch. */
+typedef struct {
+  const float* det_corners;  /* [nd,8,3] */
+  const int* img_det_off;    /* [nimg+1] */
+  const int* img_det_idx;    /* [nd] positions in the sorted order, ascending inside an image */
+  const float* gt_corners;   /* [ng,8,3] */
+  const int* img_gt_off;     /* [nimg+1] */
+  int nimg, nd, ng;
+  float ovthresh;
+  float *tp, *fp, *ovmax;
+  int* jmax;
+  unsigned char* gt_det;
+} t3d_det_match_args;
+int t3d_det_match(const t3d_det_match_args* args /* host */, t3d_stream_t stream);
+
 /* Debug hook (not part of the reference-facing surface): install a device buffer of
  * 4 * 8192 uint64 into which CTA 0 of the tcgen05 kernels records (clock64 << 8 | tag) per role
  * (0 weight producer, 1 MMA issuer, 2 epilogue warp, 3 front warp); NULL switches tracing off. */

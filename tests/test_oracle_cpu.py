@@ -319,3 +319,23 @@ def test_oracle_inference_scores_hand_case():
     assert hc[0] == 5 and abs(hres[0] - 0.5) < 1e-12 and sc[0] == 2 and sres[0].tolist() == [6.0, 7.0, 8.0]
     want = np.log(0.375 + 0.01) + np.log(12.0 / 23.0 + 0.01) + np.log(10.0 / 19.0 + 0.01) + np.log(0.51)
     assert abs(score[0] - want) < 1e-12
+
+
+# ----------------------------------------------------------------------------- detection evaluation
+def test_oracle_voc_ap_and_matching_hand_cases():
+    from oracle import eval_det as o, box_util as ob
+    # voc_ap: PR points (rec, prec) = (0.5, 1.0), (0.5, 0.5), (1.0, 2/3) -> envelope 1.0 on [0, .5], 2/3 on (.5, 1]
+    rec, prec = np.array([0.5, 0.5, 1.0]), np.array([1.0, 0.5, 2.0 / 3.0])
+    assert abs(o.voc_ap(rec, prec) - (0.5 * 1.0 + 0.5 * 2.0 / 3.0)) < 1e-12
+    # 11-point: recall thresholds 0..0.5 -> 1.0 (6 points), 0.6..1.0 -> 2/3 (5 points)
+    assert abs(o.voc_ap(rec, prec, use_07_metric=True) - (6 * 1.0 + 5 * 2.0 / 3.0) / 11.0) < 1e-12
+    # one image, two unit GT boxes 10 apart; detections: exact hit on box 0 (score .9), duplicate of box 0 (score .8,
+    # false positive: already claimed), half-shifted box on box 1 (score .7, IoU 1/3 > .25: true positive), far miss (.6)
+    box = lambda x: ob.get_3d_box((1.0, 1.0, 1.0), 0.0, (x, 0.0, 0.0))
+    gt = {7: [box(0.0), box(10.0)]}
+    pred = {7: [(box(0.0), 0.9), (box(0.05), 0.8), (box(10.5), 0.7), (box(50.0), 0.6)]}
+    rec, prec, ap, (tp, fp, ov) = o.eval_det_cls(pred, gt, 0.25, return_match=True)
+    assert tp.tolist() == [1, 0, 1, 0] and fp.tolist() == [0, 1, 0, 1]
+    assert abs(ov[2] - 1.0 / 3.0) < 1e-9 and ov[3] == 0.0
+    assert np.allclose(rec, [0.5, 0.5, 1.0, 1.0]) and np.allclose(prec, [1.0, 0.5, 2.0 / 3.0, 0.5])
+    assert abs(ap - (0.5 + 0.5 * 2.0 / 3.0)) < 1e-12

@@ -9,6 +9,7 @@
 #include "loss_ops.cuh"
 #include "box_ops.cuh"
 #include "post_ops.cuh"
+#include "eval_ops.cuh"
 #define T3D_SGEMM_WITH_EPILOGUES
 #include "sgemm.cuh"
 #define T3D_XGEMM_WITH_EPILOGUES
@@ -296,6 +297,17 @@ extern "C" int t3d_prediction_to_label(const float* center, const int* heading_c
   if (B <= 0 || NH <= 0) return T3D_ERR_SHAPE;
   prediction_to_label_kernel<<<(B + 127) / 128, 128, 0, S(stream)>>>(center, heading_cls, heading_res, size_cls, size_res, rot_angle,
                                                                      mean_size, B, NH, out7);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_det_match(const t3d_det_match_args* a, t3d_stream_t stream) {
+  if (!a || !a->det_corners || !a->img_det_off || !a->img_det_idx || !a->img_gt_off || !a->tp || !a->fp || !a->gt_det) return T3D_ERR_ARG;
+  if (a->nimg <= 0 || a->nd <= 0 || a->ng < 0 || (a->ng > 0 && !a->gt_corners)) return T3D_ERR_SHAPE;
+  T3D_CUDA(cudaMemsetAsync(a->gt_det, 0, (size_t)(a->ng > 0 ? a->ng : 1), S(stream)));
+  DetMatchArgs k{a->det_corners, a->img_det_off, a->img_det_idx, a->gt_corners, a->img_gt_off, a->nimg, a->ovthresh, a->tp, a->fp,
+                 a->ovmax, a->jmax, a->gt_det};
+  det_match_kernel<<<(a->nimg + 63) / 64, 64, 0, S(stream)>>>(k);
   T3D_CHECK_LAUNCH();
   return 0;
 }
