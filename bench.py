@@ -534,6 +534,8 @@ def main():
 
     def counting_call(name, *a):
         launches['n'] += KERNELS_PER_CALL.get(name, 0)
+        if name == 't3d_linear_f32' and a[9] >= 4096 and a[11] >= 64 and 32 <= a[10] <= 2048 and rt.get_f32_engine() != 'simt':
+            launches['n'] += 1          # the weight pre-split pass of the tensor-core GEMM (xg_presplit_kernel)
         if bd['on']:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
