@@ -17,7 +17,7 @@ def dump(buf, title):
     b = buf.cpu().numpy().reshape(4, SLOTS)
     print('=== %s' % title)
     t0 = None
-    for role, name in enumerate(('loaderA', 'loaderB', 'mma')):
+    for role, name in enumerate(('loaderA', 'loaderB/mma(pp)', 'mma/epi(pp)')):
         ev = b[role]
         ev = ev[ev != 0]
         if len(ev) == 0:
@@ -26,7 +26,7 @@ def dump(buf, title):
         tag = (ev & 0xff).astype(np.int64)
         if t0 is None:
             t0 = t[0]
-        print('  %-8s ' % name + ' '.join('%02x@%d' % (tg, r) for tg, r in zip(tag[:40], (t - t0)[:40])))
+        print('  %-8s ' % name + ' '.join('%02x@%d' % (tg, r) for tg, r in zip(tag[:int(os.environ.get('NEV', 40))], (t - t0)[:int(os.environ.get('NEV', 40))])))
 
 
 def main():

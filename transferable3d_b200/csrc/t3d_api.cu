@@ -1,4 +1,5 @@
 // extern "C" entry points of libt3d_b200.so (declared in include/t3d_b200.h).
+#include <cstdlib>
 #include "../../include/t3d_b200.h"
 #include "common.cuh"
 #include "simt_ops.cuh"
@@ -67,6 +68,23 @@ static inline bool xg_pre_ok(int M, int N, int K, const void* ws, size_t ws_byte
   return ws != nullptr && (((uintptr_t)ws) & 15) == 0 && M >= 4096 && K <= kXgMaxKChunk && ws_bytes >= xg_pre_bytes(N, K);
 }
 
+// Persistent forward / dgrad kernel (xg_pp_kernel) for K <= 128: with 4 stages or fewer per tile the per-CTA overheads and
+// the epilogue dominate the one-tile kernel (measured: 98 / 117 / 140 against 86 / 103 / 121 TFLOP/s on the 128 -> 128 /
+// 256 / 1024 forward layers); for longer K the two co-resident one-tile CTAs win (176 against 158 on dgrad 256 <- 512).
+// T3D_XG_PP=0 / 1 in the environment forces one or the other.
+static bool xg_use_pp(int K) {
+  static const int v = [] { const char* e = getenv("T3D_XG_PP"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
+  return v < 0 ? K <= 128 : v != 0;
+}
+static int xg_num_sms() {
+  static const int n = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
+  return n;
+}
+template <typename Kern>
+static int xg_prepare_pp(Kern kern) {
+  return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXgPPSmemBytes);
+}
+
 extern "C" size_t t3d_gemm_ws_bytes(int N, int K) { return (N > 0 && K > 0) ? xg_pre_bytes(N, K) : 0; }
 
 extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ldw, const float* bias, const float* gbias,
@@ -88,7 +106,13 @@ extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ld
       o.bpre = reinterpret_cast<const uint8_t*>(ws);
       o.nkb = (K + 63) / 64;
       xg_presplit_kernel<<<dim3(o.nkb, ntn), 256, 0, S(stream)>>>(W, ldw, 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
-      if (parts == 3) xlinear_pre_kernel<3><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+      if (xg_use_pp(K)) {
+        static int prepared_pp = xg_prepare_pp(xg_pp_kernel<3, true>) | xg_prepare_pp(xg_pp_kernel<1, true>);
+        if (prepared_pp != 0) return prepared_pp;
+        const int g = ntm * ntn < xg_num_sms() ? ntm * ntn : xg_num_sms();
+        if (parts == 3) xg_pp_kernel<3, true><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(GemmArgs{}, a, o);
+        else xg_pp_kernel<1, true><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(GemmArgs{}, a, o);
+      } else if (parts == 3) xlinear_pre_kernel<3><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
       else xlinear_pre_kernel<1><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
     } else {
       if (parts == 3) xlinear_kernel<3><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
@@ -546,7 +570,13 @@ extern "C" int t3d_gemm_f32_ws(const float* A, long long sam, long long sak, con
       o.nkb = (K + 63) / 64;
       const int parts = g_f32_engine == 1 ? 3 : 1;
       xg_presplit_kernel<<<dim3(o.nkb, ntn), 256, 0, S(stream)>>>(B, ldb, bk ? 1 : 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
-      if (parts == 3) xgemm_pre_kernel<3><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+      if (xg_use_pp(K)) {
+        static int prepared_pp = xg_prepare_pp(xg_pp_kernel<3, false>) | xg_prepare_pp(xg_pp_kernel<1, false>);
+        if (prepared_pp != 0) return prepared_pp;
+        const int g = ntm * ntn < xg_num_sms() ? ntm * ntn : xg_num_sms();
+        if (parts == 3) xg_pp_kernel<3, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o);
+        else xg_pp_kernel<1, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o);
+      } else if (parts == 3) xgemm_pre_kernel<3><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
       else xgemm_pre_kernel<1><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
       T3D_CHECK_LAUNCH();
       return 0;

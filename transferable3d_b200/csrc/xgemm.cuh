@@ -250,6 +250,9 @@ __global__ void __launch_bounds__(256) xg_presplit_kernel(const float* __restric
   }
 }
 
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {      // contiguous range -> L2 (16-byte granularity)
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
@@ -501,16 +504,18 @@ __device__ __forceinline__ void xg_store_chunk(const XgTile& t, float* __restric
 #ifdef T3D_XGEMM_WITH_EPILOGUES
 // ---- t3d_gemm_f32 (same contract as gemm_f32_kernel, train_ops.cuh): C = A.B (+ bias by split 0); split-K partial tiles
 // are added into a zero-initialised C with vector reductions.
+// t.warp: 0-7 in the one-tile kernels (lane quarter = warp & 3, column half = warp >> 2, 2 chunks), 0-3 in the persistent
+// kernel (4 chunks: the whole row)
 template <int PARTS>
-__device__ __forceinline__ void xg_epilogue_gemm(const GemmArgs& a, const XgTile& t) {
+__device__ __forceinline__ void xg_epilogue_gemm(const GemmArgs& a, const XgTile& t, int nchunks = 2, bool first_split = true) {
   if (t.warp < 8 && !(XG_DBG & 16)) {
     const int row0 = t.m0 + (t.warp & 3) * 32;
 #pragma unroll 1
-    for (int ch = 0; ch < 2; ++ch) {
-      const int c0 = (t.warp >> 2) * 64 + ch * 32;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int c0 = (nchunks == 2 ? (t.warp >> 2) * 64 : 0) + ch * 32;
       float v[32];
       xg_acc32<PARTS>(t, c0, v);
-      if (a.bias && blockIdx.y == 0) {
+      if (a.bias && first_split) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (t.n0 + c0 + j < a.N) v[j] += a.bias[t.n0 + c0 + j];
       }
@@ -525,7 +530,7 @@ __global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xgemm_kernel(const G
   extern __shared__ uint8_t xg_smem[];
   XgTile t;
   xg_mainloop<A_UNIT_K, B_UNIT_K, PARTS>(o, xg_smem, t);
-  xg_epilogue_gemm<PARTS>(a, t);
+  xg_epilogue_gemm<PARTS>(a, t, 2, blockIdx.y == 0);
   xg_finish(t);
 }
 // k-contiguous A, pre-split B (forward: B = W; dgrad: B = W^T)
@@ -534,14 +539,14 @@ __global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xgemm_pre_kernel(con
   extern __shared__ uint8_t xg_smem[];
   XgTile t;
   xg_mainloop<true, false, PARTS, true>(o, xg_smem, t);
-  xg_epilogue_gemm<PARTS>(a, t);
+  xg_epilogue_gemm<PARTS>(a, t, 2, blockIdx.y == 0);
   xg_finish(t);
 }
 
 // ---- t3d_linear_f32 (same contract as linear_f32_kernel, simt_ops.cuh): Y = act(X.W + bias + gbias[row / rows_per_group])
 // * rowmask, optional max over the rows of each group.
 template <int PARTS>
-__device__ __forceinline__ void xg_epilogue_linear(const LinearArgs& a, const XgTile& t) {
+__device__ __forceinline__ void xg_epilogue_linear(const LinearArgs& a, const XgTile& t, int nchunks = 2) {
   if (t.warp < 8 && !(XG_DBG & 16)) {
     const int gm = t.m0 + (t.warp & 3) * 32 + t.lane;
     const bool row_ok = gm < a.M;
@@ -550,8 +555,8 @@ __device__ __forceinline__ void xg_epilogue_linear(const LinearArgs& a, const Xg
     // the tile's 128 rows belong to one group: reduce over the warp's 32 rows in registers before the atomics
     const bool one_group = a.gmax && (a.rows_per_group % kXgBM == 0) && (t.m0 + kXgBM <= a.M);
 #pragma unroll 1
-    for (int ch = 0; ch < 2; ++ch) {
-      const int c0 = (t.warp >> 2) * 64 + ch * 32;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      const int c0 = (nchunks == 2 ? (t.warp >> 2) * 64 : 0) + ch * 32;
       float v[32];
       xg_acc32<PARTS>(t, c0, v);
 #pragma unroll
@@ -609,6 +614,221 @@ __global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xlinear_pre_kernel(c
   xg_mainloop<true, false, PARTS, true>(o, xg_smem, t);
   xg_epilogue_linear<PARTS>(a, t);
   xg_finish(t);
+}
+// ---- persistent variant for forward / dgrad (k-contiguous A, pre-split B) ------------------------------------------------
+// One CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The per-tile costs of the one-tile kernel that the
+// ablation exposed -- the epilogue (20 - 47 % of the forward layers) and the CTA skeleton (launch, TMEM allocation, barrier
+// set-up: ~17 %) -- are taken off the critical path:
+//   warps 0-7   loaders: A split (16 values per thread and stage), B stage by cp.async issued one stage ahead; 4-slot ring
+//   warps 8-11  epilogue: drain accumulator set (tile & 1) while the MMAs of the next tile fill the other set
+//   warp  12    MMA issue
+// Shared memory: 4 stages x 6 images x 8 KB = 192 KB + 4 epilogue patches; TMEM: 2 x (main + small) = 512 columns.
+#ifndef XG_PP_LOADERS
+#define XG_PP_LOADERS 8
+#endif
+constexpr int kXgPPLoaders = XG_PP_LOADERS;                     // loader warps: 8 (16 rows each) or 16 (8 rows each)
+constexpr int kXgPPThreads = (kXgPPLoaders + 5) * 32;           // + 4 epilogue warps + the MMA warp
+constexpr int kXgPPBAhead = 2;                                  // stages the B copies run ahead of the A split (<= 2 with 4 slots)
+constexpr int kXgPPVals = 128 / kXgPPLoaders;                   // A values per thread and stage (16 or 8)
+constexpr int kXgPPSlots = 4;
+constexpr uint32_t kXgPPImages = 12 * kXgImage;                                  // A: 3 parts x 2 blocks, then B the same
+constexpr uint32_t kXgPPPatch = kXgPPImages;                                    // 4 x kXgPatchBytes
+constexpr uint32_t kXgPPBars = kXgPPPatch + 4 * kXgPatchBytes;
+constexpr uint32_t kXgPPSmemBytes = kXgPPBars + 128 + 1024;
+
+// shared address of (part p, ring slot s) of an operand whose images start at `base`: block s >> 1 of image p; the
+// stage is half s & 1 of that block
+__device__ __forceinline__ uint32_t xg_pp_block(uint32_t base, int p, int s) { return base + (uint32_t)(p * 2 + (s >> 1)) * kXgImage; }
+
+template <int PARTS, bool LINEAR>
+__global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs ga, const LinearArgs la, const XgOperands o) {
+  extern __shared__ uint8_t xg_smem[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)xg_smem + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = sbase + kXgPPBars;
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto acc_full = [&](int b) { return bar0 + 8u * (8 + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (10 + b); };
+  const uint32_t tmem_slot = bar0 + 96u;
+  const int ntm = (o.M + kXgBM - 1) / kXgBM, ntiles = ntm * o.ntn;
+  const int nst = (o.K + kXgBK - 1) / kXgBK;
+  const uint32_t a_img = sbase, b_img = sbase + 6u * kXgImage;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kXgPPSlots; ++s) { mbar_init(full(s), kXgPPLoaders); mbar_init(empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
+    fence_barrier_init();
+  }
+  if (warp == kXgPPLoaders + 4) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kXgPPBars + 96);
+  XgTracer tr;      // roles: 0 loader warp 0, 1 MMA warp, 2 epilogue warp 0
+  tr.init(o.trace, warp == 0 ? 0 : (warp == kXgPPLoaders + 4 ? 1 : 2), lane == 0 && (warp == 0 || warp == kXgPPLoaders + 4 || warp == kXgPPLoaders));
+  tr.mark(0x02);
+
+  if (warp < kXgPPLoaders) {
+    // ------------------------------------------------------------------------------------------------ loaders
+    const int rsub = lane >> 3, c = lane & 7, tid = threadIdx.x;
+    constexpr int RW = 128 / kXgPPLoaders, NI = RW / 4;      // rows per warp, 128-bit loads per thread and stage
+    auto rowof = [&](int i) { return warp * RW + (i >> 1) * 8 + (i & 1) * 2 + (rsub & 1) * 4 + (rsub >> 1); };
+    const long long ld = o.lda, ld2 = 2 * ld, ld6 = 6 * ld;
+    const int kofs = 4 * c;
+    // work item g = (tile, stage), numbered consecutively over this CTA's tiles: slot g & 3, ring phase (g >> 2) & 1
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = my_tiles * nst;
+    // Both streams (A loads, B copies) visit the work items in order: (tile, stage) advance by counters -- an integer
+    // division is a ~100-cycle dependent chain, and three of them per call made up half of the stage time (clock64 trace).
+    int l_it = 0, l_row0 = ((int)blockIdx.x / o.ntn) * kXgBM, l_tile = blockIdx.x;
+    int c_it = 0, c_nt = (int)blockIdx.x % o.ntn, c_tile = blockIdx.x;
+    auto load = [&](int g, float (&r)[kXgPPVals]) {
+      const int it = l_it, row0 = l_row0, k0 = it * kXgBK;
+      if (++l_it == nst) { l_it = 0; l_tile += gridDim.x; l_row0 = (l_tile / o.ntn) * kXgBM; }
+      const int row = row0 + rowof(0);
+      const float* q = o.A + (long long)row * ld + k0 + kofs;
+      if (o.vecA && row0 + warp * RW + RW <= o.M && k0 + kXgBK <= o.K) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(q));
+          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+          q += (i & 1) ? ld6 : ld2;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int ro = (i >> 1) * 8 + (i & 1) * 2;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) r[4 * i + e] = (row + ro < o.M && k0 + kofs + e < o.K) ? __ldg(q + (long long)ro * ld + e) : 0.0f;
+        }
+      }
+    };
+    // B stage of work item g: PARTS x 128 rows x 4 chunks of 16 B from the pre-split workspace into slot g & 3
+    auto copy_b = [&](int g) {
+      const int it = c_it, nt = c_nt, s = g & 3;
+      if (++c_it == nst) { c_it = 0; c_tile += gridDim.x; c_nt = c_tile % o.ntn; }
+      mbar_wait_backoff(empty(s), ((g >> 2) & 1) ^ 1);
+      const uint8_t* blk = o.bpre + ((size_t)nt * o.nkb + (it >> 1)) * kXgPreBlockBytes;
+#pragma unroll
+      for (int j = 0; j < PARTS * 512 / (kXgPPLoaders * 32); ++j) {
+        const int id = tid + kXgPPLoaders * 32 * j, part = id >> 9, rem = id & 511;
+        const uint32_t row = (uint32_t)(rem >> 2), ch = (uint32_t)(rem & 3);
+        cp_async16(xg_pp_block(b_img, part, s) + sw128_offset(row, 4u * (s & 1) + ch),
+                   blk + (size_t)part * kXgImage + sw128_offset(row, 4u * (it & 1) + ch));
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto emit = [&](int g, const float (&r)[kXgPPVals]) {
+      const int s = g & 3;
+      // B runs kXgPPBAhead stages ahead (an L2 round trip is ~2 k cycles, longer than a stage): one commit group per stage
+      if (g + kXgPPBAhead < total) copy_b(g + kXgPPBAhead);
+      else asm volatile("cp.async.commit_group;" ::: "memory");
+      tr.mark(0x18);
+      // slot s is free: copy_b(g) waited for it kXgPPBAhead steps earlier (or in the prologue below)
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const uint32_t off = sw128_offset((uint32_t)rowof(i), (uint32_t)(4 * (s & 1) + (c >> 1))) + (uint32_t)(c & 1) * 8u;
+        if (PARTS == 1) {
+          st_shared_v2(xg_pp_block(a_img, 0, s) + off, xg_pack_rn(r[4 * i], r[4 * i + 1]), xg_pack_rn(r[4 * i + 2], r[4 * i + 3]));
+        } else {
+          uint32_t h[4], m[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) xg_split(r[4 * i + e], h[e], m[e], l[e]);
+          st_shared_v2(xg_pp_block(a_img, 0, s) + off, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]));
+          st_shared_v2(xg_pp_block(a_img, 1, s) + off, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]));
+          st_shared_v2(xg_pp_block(a_img, 2, s) + off, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]));
+        }
+      }
+      tr.mark(0x28);
+      asm volatile("cp.async.wait_group %0;" ::"n"(kXgPPBAhead) : "memory");      // all but the newest groups: this stage's B has landed
+      tr.mark(0x2c);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full(s));
+      tr.mark(0x30);
+    };
+    if (total > 0) {
+      float r[kXgPreSets][kXgPPVals];
+#pragma unroll
+      for (int j = 0; j < kXgPreSets - 1; ++j) if (j < total) load(j, r[j]);
+#pragma unroll
+      for (int j = 0; j < kXgPPBAhead; ++j) {
+        if (j < total) copy_b(j);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      for (int g0 = 0; g0 < total; g0 += kXgPreSets) {
+#pragma unroll
+        for (int j = 0; j < kXgPreSets; ++j) {
+          const int g = g0 + j;
+          if (g < total) {
+            if (g + kXgPreSets - 1 < total) load(g + kXgPreSets - 1, r[(j + kXgPreSets - 1) % kXgPreSets]);
+            tr.mark(0x10);
+            emit(g, r[j]);
+          }
+        }
+      }
+    }
+  } else if (warp == kXgPPLoaders + 4) {
+    // ------------------------------------------------------------------------------------------------ MMA issue
+    int g = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+      const int n0 = (tile % o.ntn) * kXgBN, ab = lt & 1;
+      const int ncols = min(kXgBN, ((o.N - n0) + 15) & ~15);
+      const uint32_t idesc = make_idesc_bf16(128, ncols);
+      const uint32_t d_main = tmem_base + (uint32_t)ab * 256u, d_small = d_main + 128u;
+      mbar_wait_w(acc_empty(ab), ((lt >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int it = 0; it < nst; ++it, ++g) {
+        const int s = g & 3;
+        mbar_wait_w(full(s), (g >> 2) & 1);
+        tc_fence_after();
+        tr.mark(0x10);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint32_t off = (uint32_t)(2 * (s & 1) + ks) * 32u;
+          const uint64_t a1 = make_sdesc_k128(xg_pp_block(a_img, 0, s) + off), a2 = make_sdesc_k128(xg_pp_block(a_img, 1, s) + off),
+                         a3 = make_sdesc_k128(xg_pp_block(a_img, 2, s) + off);
+          const uint64_t b1 = make_sdesc_k128(xg_pp_block(b_img, 0, s) + off), b2 = make_sdesc_k128(xg_pp_block(b_img, 1, s) + off),
+                         b3 = make_sdesc_k128(xg_pp_block(b_img, 2, s) + off);
+          const uint32_t first = (it | ks) != 0;
+          if (PARTS == 3) {
+            umma_bf16_w(d_small, a3, b1, idesc, first);
+            umma_bf16_w(d_small, a1, b3, idesc, 1);
+            umma_bf16_w(d_small, a2, b2, idesc, 1);
+            umma_bf16_w(d_small, a2, b1, idesc, 1);
+            umma_bf16_w(d_small, a1, b2, idesc, 1);
+          }
+          umma_bf16_w(d_main, a1, b1, idesc, first);
+        }
+        umma_commit_w(empty(s));
+        tr.mark(0x20);
+      }
+      umma_commit_w(acc_full(ab));
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------------ epilogue (warps 8-11)
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
+      const int ab = lt & 1;
+      XgTile t;
+      t.sbase = sbase + kXgPPPatch; t.tmem_base = tmem_base + (uint32_t)ab * 256u;
+      t.m0 = (tile / o.ntn) * kXgBM; t.n0 = (tile % o.ntn) * kXgBN; t.warp = warp - kXgPPLoaders; t.lane = lane;
+      mbar_wait_backoff(acc_full(ab), (lt >> 1) & 1);
+      tc_fence_after();
+      tr.mark(0x40);
+      if (LINEAR) xg_epilogue_linear<PARTS>(la, t, 4);
+      else xg_epilogue_gemm<PARTS>(ga, t, 4, true);
+      tc_fence_before();                                  // the tcgen05.ld of this tile are complete (wait::ld inside)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty(ab));
+      tr.mark(0x50);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kXgPPLoaders + 4) tmem_dealloc<512>(tmem_base);
 }
 #endif
 
