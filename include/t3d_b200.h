@@ -278,6 +278,24 @@ int t3d_prediction_to_label(const float* center, const int* heading_cls, const f
                             const float* size_res, const float* rot_angle, const float* mean_size /* [NS,3] (l,w,h) */,
                             int B, int NH, float* out7, t3d_stream_t stream);
 
+/* ---- surface loss (first item) ----------------------------------------------------------
+ * weak_losses.get_surface_loss (models/weak_losses.py:240-265) with tf_distance_to_closest_3D_box_surface_multi
+ * (models/tf_util.py:610-720): loss[b] = mean_n max(0, d(p_bn, box_b) - margin) * soft_mask[b,n], d = the minimum of the six
+ * (uncleaned, as the reference returns them) point-to-surface distances of the box (center, dims * scale_dims, orient).
+ * With upstream != NULL (d total / d loss[b]) the same pass writes g_box [B,7] = d total / d (center, dims, orient) -- groups
+ * gated by the train_* flags (WEAK_TRAIN_BOX_W_SURFACE) -- and g_mask [B,N] = d total / d soft_mask. */
+typedef struct {
+  const float* pc; int C;
+  const float* soft_mask;
+  const float *center, *dims, *orient;
+  int B, N;
+  float margin, scale_dims;
+  int train_center, train_dims, train_orient;
+  const float* upstream;
+  float *loss, *g_box, *g_mask;
+} t3d_surface_loss_args;
+int t3d_surface_loss(const t3d_surface_loss_args* args /* host */, t3d_stream_t stream);
+
 /* ---- detection evaluation ------------------------------------------------------------
  * The matching loop of eval_det.eval_det_cls (sunrgbd_detection/eval_det.py:118-145) for one class: detections sorted by
  * descending score, 3D IoU (box_util.box3d_iou, the get_iou hook of eval_det.py:63-69) against the ground-truth boxes of

@@ -219,10 +219,8 @@ def get_semi_loss_final(pred, labels, end_points, reduce_loss=True, c=None):
 
 
 def get_semi_loss_backbone(pred, labels, end_points, reduce_loss=True, c=None):
-    """semisup_v1_sunrgbd.py:256-321 (model A) with the surface term switched off: weak_losses.get_surface_loss and the
-    tf_distance_to_* family it needs are not restated yet (SURVEY 8(f) "next"), so WEAK_WEIGHT_SURFACE must be 0."""
+    """semisup_v1_sunrgbd.py:256-321 (model A), surface term :284-291 included."""
     from . import weak_losses
-    assert float(c.WEAK_WEIGHT_SURFACE) == 0.0, 'surface loss not restated'
     pred_seg, pred_box = pred
     (y_seg, y_center, y_orient_cls, y_orient_reg, y_dims_cls, y_dims_reg, R0_rect, P, Rtilt, K, rot_frust, box2D, img_dim,
      is_data_2D) = labels
@@ -231,6 +229,12 @@ def get_semi_loss_backbone(pred, labels, end_points, reduce_loss=True, c=None):
         c.WEAK_REPROJECTION_SOFTMAX_SCALE, c.WEAK_REPROJECTION_DILATE_FACTOR, c.WEAK_REPROJECTION_CLIP_LOWERB_LOSS,
         c.WEAK_REPROJECTION_CLIP_PRED_BOX, c.WEAK_REPROJECTION_LOSS_TYPE, c.WEAK_TRAIN_BOX_W_REPROJECTION, reduce_loss=False)
     weak_loss_fns = c.WEAK_WEIGHT_REPROJECTION * reproj
+    if float(c.WEAK_WEIGHT_SURFACE) != 0.0:
+        surface = weak_losses.get_surface_loss(
+            end_points['S_pred_box_reg'], end_points['point_cloud'][:, :, 0:3], end_points['soft_mask'], c.WEAK_SURFACE_MARGIN,
+            c.WEAK_SURFACE_LOSS_SCALE_DIMS, c.WEAK_SURFACE_LOSS_WT_FOR_INNER_PTS, c.WEAK_TRAIN_SEG_W_SURFACE,
+            c.WEAK_TRAIN_BOX_W_SURFACE, reduce_loss=False)
+        weak_loss_fns = weak_loss_fns + c.WEAK_WEIGHT_SURFACE * surface
     mask_losses, strong_losses = get_strong_loss((pred_seg, pred_box), (y_seg, y_center, y_orient_cls, y_orient_reg, y_dims_cls,
                                                                          y_dims_reg), end_points, reduce_loss=False, c=c)
     is2d = is_data_2D.to(pred_seg.dtype)

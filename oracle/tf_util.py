@@ -146,6 +146,30 @@ def tf_create_3D_box_by_surface_centers_multi(box_params, apply_translation=Fals
     return center, rsp, rsn
 
 
+def tf_distance_to_box_surfaces_multi(point_clouds, box_params):
+    """tf_util.py:610-677 batched over frustums (the reference maps the single-box function over the batch, :711-720):
+    (B,N,3), (center (B,3), dims (B,3), orient (B,)) -> dist_points_to_surfaces (B,N,6).  Literal restatement: surface
+    points / normals from tf_create_3D_box_by_surface_centers(apply_translation=True, use_base=False)."""
+    center, surface_pts, surface_norms = tf_create_3D_box_by_surface_centers_multi(box_params, apply_translation=True)
+    ray = point_clouds - center.unsqueeze(1)                                    # (B,N,3)
+    perp = torch.einsum('bnc,bsc->bns', ray, surface_norms)                     # l . n
+    p0l0n = ((surface_pts - center.unsqueeze(1)) * surface_norms).sum(dim=2)    # (B,6)
+    norm = torch.sqrt((ray * ray).sum(dim=2))                                   # (B,N)
+    dcs = p0l0n.unsqueeze(1) / (perp + 1e-5)
+    dcs = norm.unsqueeze(2) * dcs
+    l, w, h = box_params[1][:, 0], box_params[1][:, 1], box_params[1][:, 2]
+    half = torch.stack([l / 2, l / 2, h / 2, h / 2, w / 2, w / 2], dim=1)       # (B,6)
+    at_centre = (ray.abs().sum(dim=2) == 0).unsqueeze(2)
+    dcs = torch.where(at_centre, half.unsqueeze(1).expand_as(dcs), dcs)
+    return (norm.unsqueeze(2) - dcs).abs()
+
+
+def tf_distance_to_closest_3D_box_surface_multi(point_clouds, box_params):
+    """tf_util.py:679-720: the reference cleans the distances (NaN / intersection outside the box -> 1e8) and then takes
+    the minimum of the UNCLEANED tensor (:707) -- replicated."""
+    return tf_distance_to_box_surfaces_multi(point_clouds, box_params).min(dim=2).values
+
+
 def tf_get_box_pc_representation(box_reg, pc):
     """tf_util.py:764-795: original pc (all channels, untranslated) ++ 6 signed plane distances."""
     center, dims_reg, orient_reg = box_reg

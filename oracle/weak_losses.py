@@ -48,6 +48,22 @@ def get_inactive_volume_loss_v1(dims_reg, y_class, inactive_vol_train_classes, n
     return torch.stack(group_losses).mean()
 
 
+def get_surface_loss(pred_box_reg, pc_xyz, soft_mask, margin, scale_dims_factor, weight_for_points_within, train_seg, train_box,
+                     reduce_loss=True):
+    """weak_losses.py:240-265.  `mask` (the stop-gradient copy) is computed and not used by the reference: the product is
+    taken with soft_mask itself (:257), so the mask gradient flows whatever train_seg says; weight_for_points_within only
+    appears in the commented-out variant.  Both replicated."""
+    center_reg, dims_reg, orient_reg = pred_box_reg
+    center_reg = center_reg if train_box[0] else center_reg.detach()
+    dims_reg = dims_reg if train_box[1] else dims_reg.detach()
+    orient_reg = orient_reg if train_box[2] else orient_reg.detach()
+    box = (center_reg, dims_reg * scale_dims_factor, orient_reg)
+    d = tf_util.tf_distance_to_closest_3D_box_surface_multi(pc_xyz, box)       # (B,N)
+    loss = torch.clamp(d - margin, min=0.) * soft_mask
+    loss = loss.mean(dim=1)
+    return loss.mean() if reduce_loss else loss
+
+
 def get_reprojection_loss(pred_box_reg, box2D, Rtilts, Ks, img_dims, rot_frust, use_softmax_projection,
                           softmax_scale_factor, dilate_factor, clip_lower_b_loss, clip_pred_box, loss_type,
                           train_box, reduce_loss=True, scope=None, end_points=None):

@@ -242,16 +242,17 @@ def test_boxpc_reference_named_losses(built_lib):
         assert ep['boxpc_loss_grad'].shape == (B, 9)
 
 
-def test_semi_loss_backbone_model_A(built_lib):
-    """semisup_v1_sunrgbd.get_semi_loss with SEMI_MODEL 'A' (get_semi_loss_backbone, surface weight 0) on the eval-mode
-    model-A graph vs the oracle."""
+@pytest.mark.parametrize('w_surface', [0., 1.])
+def test_semi_loss_backbone_model_A(built_lib, w_surface):
+    """semisup_v1_sunrgbd.get_semi_loss with SEMI_MODEL 'A' (get_semi_loss_backbone, without and with the surface loss of
+    :284-291 at the config default weight) on the eval-mode model-A graph vs the oracle."""
     from oracle import semisup_v1_sunrgbd as OM
     from oracle.tf_layers import VarStore
     from transferable3d_b200 import runtime as rt, semisup_v1_sunrgbd as M
     B, N = 12, 256
     v = weights.make_weights_model_A()
     feed = synth.make_batch(B, N, 6, seed=21, is_data_2D=(np.arange(B) % 2))
-    FLAGS = config.cfg(SEMI_MODEL='A', WEAK_WEIGHT_SURFACE=0., WEAK_WEIGHT_REPROJECTION=0.01, SEMI_MULTIPLIER_FOR_WEAK_LOSS=0.05)
+    FLAGS = config.cfg(SEMI_MODEL='A', WEAK_WEIGHT_SURFACE=w_surface, WEAK_WEIGHT_REPROJECTION=0.01, SEMI_MULTIPLIER_FOR_WEAK_LOSS=0.05)
     T = lambda a, dt=torch.float32: torch.as_tensor(np.asarray(a)).to(dt)
     I = torch.int64
     with torch.no_grad():
@@ -274,5 +275,3 @@ def test_semi_loss_backbone_model_A(built_lib):
     s = err_stats(per.cpu().numpy(), oper.numpy())
     assert s['max_abs'] <= 1e-3 * max(s['ref_scale'], 1.0), s
     assert abs(float(total) - float(oper.mean())) <= 1e-3 * max(1.0, abs(float(oper.mean())))
-    with pytest.raises(NotImplementedError):
-        M.get_semi_loss(pred, labels, ep, c=config.cfg(SEMI_MODEL='A'))      # default WEAK_WEIGHT_SURFACE = 1: surface loss is 'next'

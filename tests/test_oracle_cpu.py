@@ -339,3 +339,24 @@ def test_oracle_voc_ap_and_matching_hand_cases():
     assert abs(ov[2] - 1.0 / 3.0) < 1e-9 and ov[3] == 0.0
     assert np.allclose(rec, [0.5, 0.5, 1.0, 1.0]) and np.allclose(prec, [1.0, 0.5, 2.0 / 3.0, 0.5])
     assert abs(ap - (0.5 + 0.5 * 2.0 / 3.0)) < 1e-12
+
+
+# ----------------------------------------------------------------------------- surface loss
+def test_oracle_surface_distance_closed_forms():
+    """Axis-aligned unit box at the origin: a point on the ray through the +x face at (a, 0, 0), a > 0, is |a - 0.5| from
+    that face along the ray; the uncleaned minimum also sees the opposite face (distance a + 0.5) and the side faces
+    (ray parallel: |r - r * 0.5 / 1e-5|, huge) -- so d = |a - 0.5|; rotating box and point together changes nothing."""
+    from oracle import tf_util as OT
+    for theta in (0.0, 0.7):
+        c, s = np.cos(theta), np.sin(theta)
+        box = (torch.zeros(1, 3, dtype=torch.float64), torch.ones(1, 3, dtype=torch.float64), torch.tensor([theta], dtype=torch.float64))
+        for a in (0.2, 0.5, 1.3):
+            # box-frame point (a,0,0) -> world: R (a,0,0) = (c a, 0, -s a)
+            p = torch.tensor([[[c * a, 0.0, -s * a]]], dtype=torch.float64)
+            d = OT.tf_distance_to_closest_3D_box_surface_multi(p, box)
+            assert abs(float(d) - abs(a - 0.5)) < 1e-4, (theta, a, float(d))
+    # dims order (l, w, h): x uses l, y uses h, z uses w
+    box = (torch.zeros(1, 3, dtype=torch.float64), torch.tensor([[2.0, 4.0, 6.0]], dtype=torch.float64), torch.zeros(1, dtype=torch.float64))
+    pts = torch.tensor([[[1.5, 0, 0], [0, 3.5, 0], [0, 0, 2.5]]], dtype=torch.float64)
+    d = OT.tf_distance_to_closest_3D_box_surface_multi(pts, box)[0]
+    assert np.allclose(d.numpy(), [0.5, 0.5, 0.5], atol=1e-4)

@@ -71,6 +71,12 @@ class t3d_infer_score_args(_c.Structure):
                 [(n, _P) for n in ('pred_seg', 'mask_mean_prob', 'heading_cls', 'heading_res', 'size_cls', 'size_res', 'scores')])
 
 
+class t3d_surface_loss_args(_c.Structure):
+    _fields_ = [('pc', _P), ('C', _I), ('soft_mask', _P), ('center', _P), ('dims', _P), ('orient', _P), ('B', _I), ('N', _I),
+                ('margin', _c.c_float), ('scale_dims', _c.c_float), ('train_center', _I), ('train_dims', _I), ('train_orient', _I),
+                ('upstream', _P), ('loss', _P), ('g_box', _P), ('g_mask', _P)]
+
+
 class t3d_det_match_args(_c.Structure):
     _fields_ = ([(n, _P) for n in ('det_corners', 'img_det_off', 'img_det_idx', 'gt_corners', 'img_gt_off')] +
                 [(n, _I) for n in ('nimg', 'nd', 'ng')] + [('ovthresh', _c.c_float)] +
@@ -133,6 +139,7 @@ SIGNATURES = {
     't3d_box3d_iou': (_I, [_P, _P, _I, _P, _P, _P]),
     't3d_compute_box3d_iou': (_I, [_c.POINTER(t3d_compute_iou_args), _P]),
     't3d_perturb_boxes': (_I, [_c.POINTER(t3d_perturb_args), _P]),
+    't3d_surface_loss': (_I, [_c.POINTER(t3d_surface_loss_args), _P]),
     't3d_det_match': (_I, [_c.POINTER(t3d_det_match_args), _P]),
     't3d_inference_scores': (_I, [_c.POINTER(t3d_infer_score_args), _P]),
     't3d_prediction_to_label': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),

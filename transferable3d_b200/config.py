@@ -47,6 +47,11 @@ _DEFAULTS = dict(
     WEAK_WEIGHT_INACTIVE_VOLUME=0,
     WEAK_WEIGHT_REPROJECTION=0.01,
     WEAK_WEIGHT_SURFACE=1.,
+    WEAK_TRAIN_SEG_W_SURFACE=False,
+    WEAK_TRAIN_BOX_W_SURFACE=[True, False, True],
+    WEAK_SURFACE_MARGIN=0,
+    WEAK_SURFACE_LOSS_WT_FOR_INNER_PTS=0.8,
+    WEAK_SURFACE_LOSS_SCALE_DIMS=0.9,
     WEAK_WEIGHT_INTRACLASSVAR=0,
     WEAK_TRAIN_BOX_W_REPROJECTION=[True, True, True],
     WEAK_REPROJECTION_USE_SOFTMAX_PROJ=False,

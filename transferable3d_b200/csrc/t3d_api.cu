@@ -11,6 +11,7 @@
 #include "box_ops.cuh"
 #include "post_ops.cuh"
 #include "eval_ops.cuh"
+#include "surface_ops.cuh"
 #define T3D_SGEMM_WITH_EPILOGUES
 #include "sgemm.cuh"
 #define T3D_XGEMM_WITH_EPILOGUES
@@ -72,9 +73,11 @@ static inline bool xg_pre_ok(int M, int N, int K, const void* ws, size_t ws_byte
 // the epilogue dominate the one-tile kernel (measured: 98 / 117 / 140 against 86 / 103 / 121 TFLOP/s on the 128 -> 128 /
 // 256 / 1024 forward layers); for longer K the two co-resident one-tile CTAs win (176 against 158 on dgrad 256 <- 512).
 // T3D_XG_PP=0 / 1 in the environment forces one or the other.
-static bool xg_use_pp(int K) {
+// The t3d_linear_f32 epilogue (group bias, activation, row mask, group max) is too heavy for the persistent kernel's 4
+// epilogue warps -- the fp32-mode pipeline dropped from 43.6 k to 24.8 k frustums/s with it -- so only t3d_gemm_f32 uses it.
+static bool xg_use_pp(int K, bool linear = false) {
   static const int v = [] { const char* e = getenv("T3D_XG_PP"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
-  return v < 0 ? K <= 128 : v != 0;
+  return v < 0 ? (K <= 128 && !linear) : v != 0;
 }
 static int xg_num_sms() {
   static const int n = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
@@ -106,7 +109,7 @@ extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ld
       o.bpre = reinterpret_cast<const uint8_t*>(ws);
       o.nkb = (K + 63) / 64;
       xg_presplit_kernel<<<dim3(o.nkb, ntn), 256, 0, S(stream)>>>(W, ldw, 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
-      if (xg_use_pp(K)) {
+      if (xg_use_pp(K, true)) {
         static int prepared_pp = xg_prepare_pp(xg_pp_kernel<3, true>) | xg_prepare_pp(xg_pp_kernel<1, true>);
         if (prepared_pp != 0) return prepared_pp;
         const int g = ntm * ntn < xg_num_sms() ? ntm * ntn : xg_num_sms();
@@ -321,6 +324,16 @@ extern "C" int t3d_prediction_to_label(const float* center, const int* heading_c
   if (B <= 0 || NH <= 0) return T3D_ERR_SHAPE;
   prediction_to_label_kernel<<<(B + 127) / 128, 128, 0, S(stream)>>>(center, heading_cls, heading_res, size_cls, size_res, rot_angle,
                                                                      mean_size, B, NH, out7);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_surface_loss(const t3d_surface_loss_args* a, t3d_stream_t stream) {
+  if (!a || !a->pc || !a->soft_mask || !a->center || !a->dims || !a->orient || !a->loss) return T3D_ERR_ARG;
+  if (a->B <= 0 || a->N <= 0 || a->C < 3) return T3D_ERR_SHAPE;
+  SurfaceLossArgs k{a->pc, a->C, a->soft_mask, a->center, a->dims, a->orient, a->B, a->N, a->margin, a->scale_dims, a->train_center,
+                    a->train_dims, a->train_orient, a->upstream, a->loss, a->g_box, a->g_mask};
+  surface_loss_kernel<<<a->B, 256, 0, S(stream)>>>(k);
   T3D_CHECK_LAUNCH();
   return 0;
 }

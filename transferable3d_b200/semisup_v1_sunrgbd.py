@@ -165,11 +165,10 @@ def get_iou_summary(pred_box, y_box, end_points, name_prefix=''):
 def get_semi_loss_backbone(pred, labels, end_points, reduce_loss=True, c=None):
     """semisup_v1_sunrgbd.py:256-321 (model A): mean_B[(1 - is2D) * (mask + strong) + is2D * (W_r * reprojection +
     W_s * surface) * SEMI_MULTIPLIER_FOR_WEAK_LOSS].  Forward values from the fused loss kernel (two launches: strong terms
-    on the parsed head output, reprojection on S_pred_box_reg).  The surface loss is SURVEY 8(f) "next": a non-zero
-    WEAK_WEIGHT_SURFACE raises.  The metrics-only get_iou_summary of :316 is available separately (get_iou_summary)."""
+    on the parsed head output, reprojection on S_pred_box_reg) and, when WEAK_WEIGHT_SURFACE != 0, the surface-loss kernel on
+    (S_pred_box_reg, point_cloud xyz, soft_mask) (:284-291).  The metrics-only get_iou_summary of :316 is available
+    separately (get_iou_summary)."""
     from . import weak_losses
-    if float(c.WEAK_WEIGHT_SURFACE) != 0.0:
-        raise NotImplementedError('get_surface_loss (WEAK_WEIGHT_SURFACE != 0): SURVEY 8(f) next')
     (y_seg, y_center, y_orient_cls, y_orient_reg, y_dims_cls, y_dims_reg, R0_rect, P, Rtilt, K, rot_frust, box2D, img_dim,
      is_data_2D) = labels
     reproj = weak_losses.get_reprojection_loss(
@@ -181,8 +180,15 @@ def get_semi_loss_backbone(pred, labels, end_points, reduce_loss=True, c=None):
     mask_losses, strong_losses = get_strong_loss(pred, (y_seg, y_center, y_orient_cls, y_orient_reg, y_dims_cls, y_dims_reg),
                                                  end_points, reduce_loss=False, c=c)
     is2d = is_data_2D.to(torch.float32)
-    total_losses = (1.0 - is2d) * (mask_losses + strong_losses) + \
-        is2d * (float(c.WEAK_WEIGHT_REPROJECTION) * reproj * float(c.SEMI_MULTIPLIER_FOR_WEAK_LOSS))
+    weak = float(c.WEAK_WEIGHT_REPROJECTION) * reproj
+    if float(c.WEAK_WEIGHT_SURFACE) != 0.0:
+        surface = weak_losses.get_surface_loss(
+            end_points['S_pred_box_reg'], end_points['point_cloud'][:, :, 0:3].contiguous(), end_points['soft_mask'],
+            margin=c.WEAK_SURFACE_MARGIN, scale_dims_factor=c.WEAK_SURFACE_LOSS_SCALE_DIMS,
+            weight_for_points_within=c.WEAK_SURFACE_LOSS_WT_FOR_INNER_PTS, train_seg=c.WEAK_TRAIN_SEG_W_SURFACE,
+            train_box=c.WEAK_TRAIN_BOX_W_SURFACE, end_points=end_points, reduce_loss=False, scope='surface_loss')
+        weak = weak + float(c.WEAK_WEIGHT_SURFACE) * surface
+    total_losses = (1.0 - is2d) * (mask_losses + strong_losses) + is2d * (weak * float(c.SEMI_MULTIPLIER_FOR_WEAK_LOSS))
     return total_losses.mean() if reduce_loss else total_losses
 
 

@@ -2,7 +2,8 @@
 get_intraclass_variance_loss_v1 (:267-291) with the reference's argument lists, evaluated by the fused loss kernel
 (csrc/loss_ops.cuh, t3d_semi_loss) with every other term switched off.  Forward values; the gradients of these terms
 inside a training step are produced by the same kernel through train_semisup_adv.SemiAdvTrainGraph.
-get_inactive_volume_loss_v1 / get_surface_loss / get_D_loss / get_G_loss: SURVEY 8(f) "next"."""
+get_surface_loss (:240-265) has its own kernel (csrc/surface_ops.cuh, t3d_surface_loss: forward and backward in one pass
+over the points).  get_inactive_volume_loss_v1 / get_D_loss / get_G_loss: SURVEY 8(f) "next"."""
 import numpy as np
 import torch
 
@@ -57,3 +58,33 @@ def get_intraclass_variance_loss_v1(dims_reg, y_class, intraclsdims_train_classe
     reg = torch.cat([torch.zeros((B, 3), device=dev), dims_reg.to(torch.float32), torch.zeros((B, 1), device=dev)], dim=1).contiguous()
     res = losses.semi_loss(c, out0, s0, oh, feed, dev, reg_in=reg, icv_mask=mask, finish=False)
     return res['total'][3]
+
+
+def get_surface_loss(pred_box_reg, pc_xyz, soft_mask, margin, scale_dims_factor, weight_for_points_within, train_seg, train_box,
+                     reduce_loss=True, scope=None, end_points=None, upstream=None):
+    """weak_losses.py:240-265: pred_box_reg = (center (B,3), dims (B,3), orient (B,)), pc_xyz (B,N,>=3), soft_mask (B,N) ->
+    (B,) losses (scalar mean if reduce_loss).  weight_for_points_within and train_seg do not enter the reference's result
+    (see csrc/surface_ops.cuh).  With `upstream` (B,) = d total / d loss_b the same launch also returns the gradients:
+    end_points['surface_grad_box_reg'] (B,7) w.r.t. (center, dims, orient), gated by train_box, and
+    end_points['surface_grad_soft_mask'] (B,N)."""
+    import ctypes
+    from . import runtime as rt
+    from ._lib import t3d_surface_loss_args, load, check, ptr, stream
+    center, dims, orient = (rt.f32(t) for t in pred_box_reg)
+    pc, sm = rt.f32(pc_xyz), rt.f32(soft_mask)
+    B, N, C = pc.shape
+    dev = pc.device
+    loss = torch.empty((B,), dtype=torch.float32, device=dev)
+    up = rt.f32(upstream) if upstream is not None else None
+    g_box = torch.zeros((B, 7), dtype=torch.float32, device=dev) if up is not None else None
+    g_mask = torch.empty((B, N), dtype=torch.float32, device=dev) if up is not None else None
+    a = t3d_surface_loss_args(ptr(pc), C, ptr(sm), ptr(center), ptr(dims), ptr(orient.reshape(B).contiguous()), B, N, float(margin),
+                              float(scale_dims_factor), int(bool(train_box[0])), int(bool(train_box[1])), int(bool(train_box[2])),
+                              ptr(up), ptr(loss), ptr(g_box), ptr(g_mask))
+    check(load().t3d_surface_loss(ctypes.byref(a), stream()))
+    if end_points is not None:
+        end_points['surface_loss'] = loss
+        if up is not None:
+            end_points['surface_grad_box_reg'] = g_box
+            end_points['surface_grad_soft_mask'] = g_mask
+    return loss.mean() if reduce_loss else loss
