@@ -296,6 +296,13 @@ typedef struct {
 } t3d_surface_loss_args;
 int t3d_surface_loss(const t3d_surface_loss_args* args /* host */, t3d_stream_t stream);
 
+/* weak_losses.get_inactive_volume_loss_v1 (models/weak_losses.py:38-67) -> out[0]; with total / g_reg (the buffers of
+ * t3d_semi_loss) the term is also folded in as get_semi_loss_final does (semisup_v1_sunrgbd.py:348-360):
+ * total[4] += w iv, total[0] += mult w iv, g_reg[:,3:6] += mult w d iv / d dims.  Launch after t3d_semi_loss, same stream. */
+int t3d_inactive_volume_loss(const float* dims, const float* one_hot, const float* margins, int B, int NC,
+                             unsigned train_mask, float w, float mult, float* out, float* total, float* g_reg,
+                             t3d_stream_t stream);
+
 /* ---- detection evaluation ------------------------------------------------------------
  * The matching loop of eval_det.eval_det_cls (sunrgbd_detection/eval_det.py:118-145) for one class: detections sorted by
  * descending score, 3D IoU (box_util.box3d_iou, the get_iou hook of eval_det.py:63-69) against the ground-truth boxes of

@@ -117,6 +117,9 @@ def test_semisup_adv_training_reduces_loss(built_lib):
     dict(WEAK_REPROJECTION_LOSS_TYPE='mse', WEAK_DIMS_LOSS_TYPE='mse', WEAK_REPROJECTION_ONLY_ON_2D_CLS=False),
     dict(WEAK_REPROJECTION_USE_SOFTMAX_PROJ=True, WEAK_TRAIN_BOX_W_REPROJECTION=[True, False, True]),
     dict(SEMI_BOXPC_FIT_ONLY_ON_2D_CLS=True, SEMI_INTRACLSDIMS_ONLY_ON_2D_CLS=False, WEAK_WEIGHT_REPROJECTION=1.0),
+    # inactive-volume loss (weak_losses.py:38-67) folded in as semisup_v1_sunrgbd.py:348-360 does; margins around the class volumes
+    dict(WEAK_WEIGHT_INACTIVE_VOLUME=1.5, WEAK_INACTIVE_VOL_ONLY_ON_2D_CLS=False,
+         WEAK_INACTIVE_VOL_LOSS_MARGINS=[4.0, 1.5, 2.0, 0.4, 0.3, 1.0, 0.8, 0.3, 1.0, 0.6]),
 ])
 def test_semi_loss_kernel_vs_oracle(over, built_lib):
     """get_semi_loss_final value + gradients w.r.t. F_output, stage1_center and the BoxPC fit logits."""

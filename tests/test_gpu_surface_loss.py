@@ -66,3 +66,21 @@ def test_surface_loss_is_zero_on_the_surface_and_grows_with_distance():
         loss = W.get_surface_loss(box, torch.as_tensor(pts).cuda(), ones, 0.0, 1.0, 0.8, False, (True, False, True), reduce_loss=False)
         want = np.linalg.norm(pts[0], axis=1) * (1 - 1 / (1 + 2 * t))
         assert abs(float(loss[0]) - float(want.mean())) < 2e-4, (t, float(loss[0]), float(want.mean()))
+
+
+def test_inactive_volume_loss_vs_oracle():
+    """weak_losses.get_inactive_volume_loss_v1 (weak_losses.py:38-67): class-grouped mean violations, empty and untrained
+    classes, all-satisfied margins."""
+    from transferable3d_b200 import weak_losses as W
+    from oracle import weak_losses as OW
+    rng = np.random.RandomState(2)
+    B = 300
+    dims = rng.uniform(0.3, 2.0, (B, 3)).astype(np.float32)
+    cls = rng.randint(0, 10, B)
+    cls[cls == 7] = 6                                  # class 7 empty
+    margins = np.array([4.0, 1.5, 2.0, 0.4, 0.3, 1.0, 0.8, 0.3, 1.0, 0.0], np.float32)      # class 9: never violated
+    for train in ([True] * 10, [i % 2 == 0 for i in range(10)], [False] * 9 + [True]):
+        want = OW.get_inactive_volume_loss_v1(torch.as_tensor(dims, dtype=torch.float64), torch.as_tensor(cls), train, 10,
+                                              torch.as_tensor(margins, dtype=torch.float64))
+        got = W.get_inactive_volume_loss_v1(torch.as_tensor(dims).cuda(), torch.as_tensor(cls).cuda(), train, 10, margins)
+        assert abs(float(got) - float(want)) <= 1e-5 * max(1.0, abs(float(want))), (train, float(got), float(want))

@@ -139,6 +139,7 @@ SIGNATURES = {
     't3d_box3d_iou': (_I, [_P, _P, _I, _P, _P, _P]),
     't3d_compute_box3d_iou': (_I, [_c.POINTER(t3d_compute_iou_args), _P]),
     't3d_perturb_boxes': (_I, [_c.POINTER(t3d_perturb_args), _P]),
+    't3d_inactive_volume_loss': (_I, [_P, _P, _P, _I, _I, _c.c_uint, _F, _F, _P, _P, _P, _P]),
     't3d_surface_loss': (_I, [_c.POINTER(t3d_surface_loss_args), _P]),
     't3d_det_match': (_I, [_c.POINTER(t3d_det_match_args), _P]),
     't3d_inference_scores': (_I, [_c.POINTER(t3d_infer_score_args), _P]),

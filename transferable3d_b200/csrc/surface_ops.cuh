@@ -106,4 +106,61 @@ __global__ void __launch_bounds__(256) surface_loss_kernel(const SurfaceLossArgs
   }
 }
 
+// weak_losses.get_inactive_volume_loss_v1 (models/weak_losses.py:38-67): per trained class the mean over its samples of
+// max(0, margin_c - l w h) (0 for an empty group), then the mean over the trained classes.  One CTA; class id = argmax of
+// the one-hot row.  The value is written to out[0]; with w != 0 it is also accumulated the way get_semi_loss_final combines
+// it (semisup_v1_sunrgbd.py:348-360, :393-398): total[4] (weak_loss) += w * iv, total[0] += mult * w * iv, and
+// g_reg[b, 3:6] += mult * w * d iv / d dims_b.
+struct InactiveVolArgs {
+  const float* dims;        // [B,3] regression-format dims (l, w, h)
+  const float* one_hot;     // [B,NC]
+  const float* margins;     // [NC]
+  int B, NC;
+  unsigned train_mask;      // bit c: class c is in inactive_vol_train_classes
+  float w, mult;
+  float* out;               // [1]
+  float* total;             // [8] of t3d_semi_loss, or null
+  float* g_reg;             // [B,7] of t3d_semi_loss, or null
+};
+__global__ void __launch_bounds__(256) inactive_volume_kernel(const InactiveVolArgs a) {
+  __shared__ float viol[32], cnt[32];
+  if (threadIdx.x < 32) { viol[threadIdx.x] = 0.f; cnt[threadIdx.x] = 0.f; }
+  __syncthreads();
+  auto cls_of = [&](int b) {
+    int cid = 0; float best = a.one_hot[(size_t)b * a.NC];
+    for (int c = 1; c < a.NC; ++c) { const float v = a.one_hot[(size_t)b * a.NC + c]; if (v > best) { best = v; cid = c; } }
+    return cid;
+  };
+  for (int b = threadIdx.x; b < a.B; b += 256) {
+    const int c = cls_of(b);
+    if (!((a.train_mask >> c) & 1u)) continue;
+    const float vol = a.dims[b * 3] * a.dims[b * 3 + 1] * a.dims[b * 3 + 2];
+    atomicAdd(&cnt[c], 1.0f);
+    atomicAdd(&viol[c], fmaxf(0.0f, a.margins[c] - vol));
+  }
+  __syncthreads();
+  const int ntrain = __popc(a.train_mask & ((a.NC >= 32) ? 0xffffffffu : ((1u << a.NC) - 1u)));
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int c = 0; c < a.NC; ++c) if (((a.train_mask >> c) & 1u) && cnt[c] > 0.f) s += viol[c] / cnt[c];
+    const float iv = ntrain > 0 ? s / (float)ntrain : 0.f;
+    a.out[0] = iv;
+    if (a.total) { a.total[4] += a.w * iv; a.total[0] += a.mult * a.w * iv; }
+  }
+  __syncthreads();
+  if (a.g_reg && a.w != 0.f && ntrain > 0) {
+    for (int b = threadIdx.x; b < a.B; b += 256) {
+      const int c = cls_of(b);
+      if (!((a.train_mask >> c) & 1u)) continue;
+      const float l = a.dims[b * 3], w = a.dims[b * 3 + 1], h = a.dims[b * 3 + 2];
+      if (a.margins[c] - l * w * h > 0.0f) {
+        const float g = -a.mult * a.w / (cnt[c] * (float)ntrain);
+        a.g_reg[(size_t)b * 7 + 3] += g * w * h;
+        a.g_reg[(size_t)b * 7 + 4] += g * l * h;
+        a.g_reg[(size_t)b * 7 + 5] += g * l * w;
+      }
+    }
+  }
+}
+
 }  // namespace t3d

@@ -338,6 +338,17 @@ extern "C" int t3d_surface_loss(const t3d_surface_loss_args* a, t3d_stream_t str
   return 0;
 }
 
+extern "C" int t3d_inactive_volume_loss(const float* dims, const float* one_hot, const float* margins, int B, int NC,
+                                        unsigned train_mask, float w, float mult, float* out, float* total, float* g_reg,
+                                        t3d_stream_t stream) {
+  if (!dims || !one_hot || !margins || !out) return T3D_ERR_ARG;
+  if (B <= 0 || NC <= 0 || NC > 32) return T3D_ERR_SHAPE;
+  InactiveVolArgs k{dims, one_hot, margins, B, NC, train_mask, w, mult, out, total, g_reg};
+  inactive_volume_kernel<<<1, 256, 0, S(stream)>>>(k);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int t3d_det_match(const t3d_det_match_args* a, t3d_stream_t stream) {
   if (!a || !a->det_corners || !a->img_det_off || !a->img_det_idx || !a->img_gt_off || !a->tp || !a->fp || !a->gt_det) return T3D_ERR_ARG;
   if (a->nimg <= 0 || a->nd <= 0 || a->ng < 0 || (a->ng > 0 && !a->gt_corners)) return T3D_ERR_SHAPE;

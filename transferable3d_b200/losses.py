@@ -23,6 +23,13 @@ def icv_train_mask(FLAGS):
     return sum(1 << i for i, t in enumerate(icv) if t)
 
 
+def inactive_vol_train_mask(FLAGS):
+    """inactive_vol_train_classes of train_semisup_adv.py:322-323 as a bit mask over ALL_CLASSES."""
+    test_cls = getattr(FLAGS, 'TEST_CLS', None) or []
+    iv = [(cls in test_cls) for cls in ALL_CLASSES] if FLAGS.WEAK_INACTIVE_VOL_ONLY_ON_2D_CLS else [True] * len(ALL_CLASSES)
+    return sum(1 << i for i, t in enumerate(iv) if t)
+
+
 def _consts(dev):
     D = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32)).to(dev).contiguous()
     return D(MEAN_DIMS_ARR), D(np.arange(0, 2 * np.pi, 2 * np.pi / NUM_HEADING_BIN))
@@ -35,8 +42,6 @@ def semi_loss(FLAGS, F_output, stage1_center, one_hot, feed, dev, logits=None, m
     (t3d_box_reg_backward); the training graph passes finish=False, adds the BoxPC input gradient to g_reg and calls
     finish_box_reg itself.  Returns dict(total[8], dF, ds1, g_reg, dfit, per_sample[B,6], mask_losses)."""
     c = FLAGS
-    if c.WEAK_WEIGHT_INACTIVE_VOLUME != 0:
-        raise NotImplementedError('inactive-volume loss (SURVEY 8f next)')
     T = lambda v, dt=torch.float32: (v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v))).to(device=dev, dtype=dt).contiguous()
     B = F_output.shape[0]
     NH, NS = NUM_HEADING_BIN, NUM_SIZE_CLUSTER
@@ -86,7 +91,14 @@ def semi_loss(FLAGS, F_output, stage1_center, one_hot, feed, dev, logits=None, m
     a.train_box_mask = (1 if tb[0] else 0) | (2 if tb[1] else 0) | (4 if tb[2] else 0)
     a.inv_n3d = inv_n3d
     call('t3d_semi_loss', ctypes.byref(a), stream())
-    res = dict(total=total, dF=dF, ds1=ds1, g_reg=g_reg, dfit=dfit, per_sample=per_sample, mask_losses=mask_losses, F_reg=F_reg,
+    iv_out = None
+    if c.WEAK_WEIGHT_INACTIVE_VOLUME != 0:           # semisup_v1_sunrgbd.py:348-360: folded into total / weak_loss / g_reg
+        assert len(c.WEAK_INACTIVE_VOL_LOSS_MARGINS) == NUM_CLASS
+        margins = T(np.asarray(c.WEAK_INACTIVE_VOL_LOSS_MARGINS, dtype=np.float32))
+        iv_out = E(1)
+        call('t3d_inactive_volume_loss', ptr(stat_dims), ptr(one_hot), ptr(margins), B, NUM_CLASS, inactive_vol_train_mask(c),
+             float(c.WEAK_WEIGHT_INACTIVE_VOLUME), float(c.SEMI_MULTIPLIER_FOR_WEAK_LOSS), ptr(iv_out), ptr(total), ptr(g_reg), stream())
+    res = dict(inactive_vol=iv_out, total=total, dF=dF, ds1=ds1, g_reg=g_reg, dfit=dfit, per_sample=per_sample, mask_losses=mask_losses, F_reg=F_reg,
                _mean_size=mean_size, _F_output=F_output)
     if finish:
         finish_box_reg(res)

@@ -56,8 +56,6 @@ class SemiAdvTrainGraph(object):
             raise NotImplementedError('SEMI_REFINE_USING_BOXPC_DELTA_NUM != 1')
         if c.USE_NORMALIZED_BOX2D_AS_FEATS:
             raise NotImplementedError('USE_NORMALIZED_BOX2D_AS_FEATS in the training graph')
-        if c.WEAK_WEIGHT_INACTIVE_VOLUME != 0:
-            raise NotImplementedError('inactive-volume loss (SURVEY 8f next)')
         self.FLAGS, self.B, self.Npt, self.C = FLAGS, batch_size, num_point, num_channels
         self.device = dev = torch.device(device)
         self.base_lr, self.decay_step, self.decay_rate = base_learning_rate, decay_step, decay_rate

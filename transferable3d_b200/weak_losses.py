@@ -3,7 +3,8 @@ get_intraclass_variance_loss_v1 (:267-291) with the reference's argument lists, 
 (csrc/loss_ops.cuh, t3d_semi_loss) with every other term switched off.  Forward values; the gradients of these terms
 inside a training step are produced by the same kernel through train_semisup_adv.SemiAdvTrainGraph.
 get_surface_loss (:240-265) has its own kernel (csrc/surface_ops.cuh, t3d_surface_loss: forward and backward in one pass
-over the points).  get_inactive_volume_loss_v1 / get_D_loss / get_G_loss: SURVEY 8(f) "next"."""
+over the points); get_inactive_volume_loss_v1 (:38-67) is a one-CTA kernel (t3d_inactive_volume_loss).  get_D_loss /
+get_G_loss belong to the dead discriminator branches and are not built."""
 import numpy as np
 import torch
 
@@ -88,3 +89,19 @@ def get_surface_loss(pred_box_reg, pc_xyz, soft_mask, margin, scale_dims_factor,
             end_points['surface_grad_box_reg'] = g_box
             end_points['surface_grad_soft_mask'] = g_mask
     return loss.mean() if reduce_loss else loss
+
+
+def get_inactive_volume_loss_v1(dims_reg, y_class, inactive_vol_train_classes, num_classes, inactive_vol_loss_margins, scope=None):
+    """weak_losses.py:38-67: dims_reg (B,3), y_class (B,), train flags and margins per class -> scalar."""
+    from . import runtime as rt
+    from ._lib import call, ptr, stream
+    dims = rt.f32(dims_reg)
+    dev, B = dims.device, dims.shape[0]
+    margins = rt.f32(torch.as_tensor(np.asarray(inactive_vol_loss_margins.cpu() if torch.is_tensor(inactive_vol_loss_margins)
+                                                else inactive_vol_loss_margins, dtype=np.float32)).to(dev))
+    assert margins.shape[0] == num_classes == len(inactive_vol_train_classes)
+    oh = torch.nn.functional.one_hot(y_class.long(), num_classes).to(torch.float32).contiguous()
+    mask = sum(1 << i for i, t in enumerate(inactive_vol_train_classes) if t)
+    out = torch.empty((1,), dtype=torch.float32, device=dev)
+    call('t3d_inactive_volume_loss', ptr(dims), ptr(oh), ptr(margins), B, int(num_classes), mask, 0.0, 0.0, ptr(out), None, None, stream())
+    return out[0]
