@@ -303,6 +303,31 @@ int t3d_inactive_volume_loss(const float* dims, const float* one_hot, const floa
                              unsigned train_mask, float w, float mult, float* out, float* total, float* g_reg,
                              t3d_stream_t stream);
 
+/* ---- frustum batch assembly (input side) ------------------------------------------------
+ * ROISegBoxDataset.__getitem__ + get_batch (sunrgbd_detection/roi_seg_box3d_dataset.py:259-345, 370-417) for a batch:
+ * resample every selected frustum to N points with the given choice indices, rotate to the centre view
+ * (rot_angle = pi/2 + frustum_angle, rotate_pc_along_y), optional flip / shift augmentation, and -- when box3d != NULL --
+ * the label encoding (box centre, angle2class, size2class).  The dataset is one flat device array of points + offsets. */
+typedef struct {
+  const float* points; int C_src;
+  const int* labels;
+  const long long* pt_off;
+  const int *sel, *choice;
+  const float *frustum_angle, *box3d, *heading, *size;
+  const int* cls;
+  const float* mean_size;
+  const unsigned char* flip;
+  const float *shift_z, *shift_y;
+  int B, N, C_out, rotate_to_center, NH;
+  float* batch_data;
+  int* batch_label;
+  float* center;
+  int* heading_class; float* heading_residual;
+  int* size_class; float* size_residual;
+  float* rot_angle;
+} t3d_assemble_args;
+int t3d_assemble_frustum_batch(const t3d_assemble_args* args /* host */, t3d_stream_t stream);
+
 /* ---- detection evaluation ------------------------------------------------------------
  * The matching loop of eval_det.eval_det_cls (sunrgbd_detection/eval_det.py:118-145) for one class: detections sorted by
  * descending score, 3D IoU (box_util.box3d_iou, the get_iou hook of eval_det.py:63-69) against the ground-truth boxes of

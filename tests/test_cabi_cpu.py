@@ -51,3 +51,16 @@ def test_product_path_fails_loudly_without_gpu(built_lib):
     from transferable3d_b200 import runtime as rt, _lib
     with pytest.raises(_lib.T3DError):
         rt.linear(torch.zeros(4, 4), torch.zeros(4, 4))
+
+
+def test_zipped_pickle_roundtrip_protocol2(tmp_path):
+    """utils.save_zipped_pickle / load_zipped_pickle (sunrgbd_data/utils.py:341-348): protocol-2 gz pickle (what Python 2's
+    cPickle wrote), numpy arrays and str survive the latin1 load."""
+    import numpy as np
+    from transferable3d_b200 import utils
+    obj = [[1, 2], [np.arange(6.0).reshape(2, 3), np.ones((0, 3))], ['bed', 'night_stand']]
+    p = os.path.join(str(tmp_path), 'x.zip.pickle')
+    utils.save_zipped_pickle(obj, p)
+    back = utils.load_zipped_pickle(p)
+    assert back[0] == [1, 2] and back[2] == ['bed', 'night_stand']
+    assert np.array_equal(back[1][0], obj[1][0]) and back[1][1].shape == (0, 3)

@@ -1,0 +1,89 @@
+"""-m gpu: frustum batch assembly (input side): ROISegBoxDataset.get_batch on the device
+(t3d_assemble_frustum_batch) against the literal numpy restatement of __getitem__ + get_batch under the same numpy seed,
+through a gz-pickle file in the reference's 13-list (and 7-list) layout."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CLASSES = ['bed', 'table', 'sofa', 'chair', 'toilet', 'desk', 'dresser', 'night_stand', 'bookshelf', 'bathtub']
+
+
+def _lists(F, seed, with_extra_class=True):
+    from oracle import box_util as ob
+    from transferable3d_b200.constants import type_mean_size
+    rng = np.random.RandomState(seed)
+    L = [[] for _ in range(13)]
+    for i in range(F):
+        cls = CLASSES[rng.randint(10)] if not (with_extra_class and i % 9 == 4) else 'lamp'      # filtered out by `classes`
+        n = rng.randint(40, 700)
+        size = type_mean_size.get(cls, np.ones(3)) * rng.uniform(0.8, 1.2, 3)
+        heading = rng.uniform(-np.pi, np.pi) + 0.013                      # keep clear of the angle-bin boundaries
+        center = np.array([rng.uniform(-2, 2), rng.uniform(-0.5, 0.5), rng.uniform(1.5, 5)])
+        pts = np.concatenate([center + rng.randn(n, 3) * 0.5, rng.rand(n, 3)], axis=1)
+        rec = [1000 + i, rng.rand(4) * 400, ob.get_3d_box(size, heading, center), None, pts, rng.randint(0, 2, n).astype(np.int64), cls,
+               heading, size, np.eye(3) + rng.randn(3, 3) * 0.01, np.diag([520.0, 520.0, 1.0]) + rng.rand(3, 3), rng.uniform(-0.6, 0.6),
+               np.array([640.0, 480.0])]
+        for l, v in zip(L, rec):
+            l.append(v)
+    return L
+
+
+@pytest.mark.parametrize('rotate,flip,shift,one_hot', [(True, False, False, True), (False, False, False, False), (True, True, True, True)])
+def test_get_batch_vs_oracle(tmp_path, rotate, flip, shift, one_hot):
+    from transferable3d_b200 import roi_seg_box3d_dataset as D, utils
+    from oracle import roi_seg_box3d_dataset as OD
+    lists = _lists(60, seed=3)
+    path = os.path.join(str(tmp_path), 'frustums.zip.pickle')
+    utils.save_zipped_pickle(lists, path)
+    ds = D.ROISegBoxDataset(CLASSES, 512, 'val', random_flip=flip, random_shift=shift, rotate_to_center=rotate,
+                            overwritten_data_path=path, one_hot=one_hot)
+    keep = [i for i, c in enumerate(lists[6]) if c in CLASSES]
+    assert len(ds) == len(keep) < 60 and ds.idx_l == [lists[0][i] for i in keep]
+    ods = OD.ROISegBoxDataset([[l[i] for i in keep] for l in lists], 512, random_flip=flip, random_shift=shift,
+                              rotate_to_center=rotate, one_hot=one_hot)
+    idxs = np.random.RandomState(1).permutation(len(ds))
+    np.random.seed(77)
+    got = ds.get_batch(idxs, 4, 36, 512, 6)
+    np.random.seed(77)
+    want = ods.get_batch(idxs, 4, 36, 512, 6)
+    assert len(got) == len(want) == (14 if one_hot else 13) and got[1] is None
+    G = lambda t: t.cpu().numpy()
+    assert np.abs(G(got[0]) - want[0]).max() < 2e-5                       # fp32 rotation vs float64 numpy, coordinates up to ~6 m
+    if not (rotate or flip or shift):
+        assert np.array_equal(G(got[0]), want[0].astype(np.float32))      # pure gather: bit-exact
+    assert np.array_equal(G(got[2]), want[2])                             # seg labels
+    assert np.abs(G(got[3]) - want[3]).max() < 2e-6 * 6 + 1e-6            # box centre
+    assert np.array_equal(G(got[4]), want[4]) and np.abs(G(got[5]) - want[5]).max() < 1e-5      # heading class / residual
+    assert np.array_equal(G(got[6]), want[6]) and np.abs(G(got[7]) - want[7]).max() < 1e-6      # size class / residual
+    for k in (8, 9, 10, 12):
+        assert np.allclose(G(got[k]), want[k], rtol=1e-6, atol=1e-6)
+    assert np.abs(G(got[11]) - want[11]).max() < 1e-6                     # rot_angle
+    if one_hot:
+        assert np.array_equal(G(got[13]), want[13])
+
+
+def test_rgb_detection_layout_and_pickle_roundtrip(tmp_path):
+    from transferable3d_b200 import roi_seg_box3d_dataset as D, utils
+    L13 = _lists(20, seed=5, with_extra_class=False)
+    rng = np.random.RandomState(0)
+    L7 = [L13[0], L13[1], L13[3], L13[4], L13[6], L13[11], list(rng.rand(20))]
+    path = os.path.join(str(tmp_path), 'rgb_det.zip.pickle')
+    utils.save_zipped_pickle(L7, path)
+    back = utils.load_zipped_pickle(path)
+    assert len(back) == 7 and back[4] == L7[4] and np.array_equal(back[3][7], L7[3][7])
+    ds = D.ROISegBoxDataset(CLASSES, 256, 'val', rotate_to_center=True, overwritten_data_path=path, from_rgb_detection=True, one_hot=True)
+    np.random.seed(5)
+    data, img, rot, prob, one_hot, y_seg = ds.get_batch(np.arange(20), 0, 8, 256, 6, from_rgb_detection=True)
+    np.random.seed(5)
+    for i in range(8):
+        choice = np.random.choice(L7[3][i].shape[0], 256, replace=True)
+        want = D.rotate_pc_along_y(np.copy(L7[3][i]), np.pi / 2 + L7[5][i])[choice]
+        assert np.abs(data[i].cpu().numpy() - want).max() < 2e-5
+        assert abs(float(rot[i]) - (np.pi / 2 + L7[5][i])) < 1e-6 and abs(float(prob[i]) - L7[6][i]) < 1e-6
+    assert img is None and one_hot.shape == (8, 10) and float(y_seg.abs().max()) == 0.0
+    with pytest.raises(AssertionError):
+        D.ROISegBoxDataset(CLASSES, 256, 'val', overwritten_data_path=path)           # 7 lists where 13 are expected

@@ -77,6 +77,14 @@ class t3d_surface_loss_args(_c.Structure):
                 ('upstream', _P), ('loss', _P), ('g_box', _P), ('g_mask', _P)]
 
 
+class t3d_assemble_args(_c.Structure):
+    _fields_ = [('points', _P), ('C_src', _I), ('labels', _P), ('pt_off', _P), ('sel', _P), ('choice', _P), ('frustum_angle', _P),
+                ('box3d', _P), ('heading', _P), ('size', _P), ('cls', _P), ('mean_size', _P), ('flip', _P), ('shift_z', _P),
+                ('shift_y', _P), ('B', _I), ('N', _I), ('C_out', _I), ('rotate_to_center', _I), ('NH', _I), ('batch_data', _P),
+                ('batch_label', _P), ('center', _P), ('heading_class', _P), ('heading_residual', _P), ('size_class', _P),
+                ('size_residual', _P), ('rot_angle', _P)]
+
+
 class t3d_det_match_args(_c.Structure):
     _fields_ = ([(n, _P) for n in ('det_corners', 'img_det_off', 'img_det_idx', 'gt_corners', 'img_gt_off')] +
                 [(n, _I) for n in ('nimg', 'nd', 'ng')] + [('ovthresh', _c.c_float)] +
@@ -141,6 +149,7 @@ SIGNATURES = {
     't3d_perturb_boxes': (_I, [_c.POINTER(t3d_perturb_args), _P]),
     't3d_inactive_volume_loss': (_I, [_P, _P, _P, _I, _I, _c.c_uint, _F, _F, _P, _P, _P, _P]),
     't3d_surface_loss': (_I, [_c.POINTER(t3d_surface_loss_args), _P]),
+    't3d_assemble_frustum_batch': (_I, [_c.POINTER(t3d_assemble_args), _P]),
     't3d_det_match': (_I, [_c.POINTER(t3d_det_match_args), _P]),
     't3d_inference_scores': (_I, [_c.POINTER(t3d_infer_score_args), _P]),
     't3d_prediction_to_label': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),

@@ -12,6 +12,7 @@
 #include "post_ops.cuh"
 #include "eval_ops.cuh"
 #include "surface_ops.cuh"
+#include "data_ops.cuh"
 #define T3D_SGEMM_WITH_EPILOGUES
 #include "sgemm.cuh"
 #define T3D_XGEMM_WITH_EPILOGUES
@@ -345,6 +346,20 @@ extern "C" int t3d_inactive_volume_loss(const float* dims, const float* one_hot,
   if (B <= 0 || NC <= 0 || NC > 32) return T3D_ERR_SHAPE;
   InactiveVolArgs k{dims, one_hot, margins, B, NC, train_mask, w, mult, out, total, g_reg};
   inactive_volume_kernel<<<1, 256, 0, S(stream)>>>(k);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_assemble_frustum_batch(const t3d_assemble_args* a, t3d_stream_t stream) {
+  if (!a || !a->points || !a->pt_off || !a->sel || !a->choice || !a->frustum_angle || !a->batch_data || !a->rot_angle) return T3D_ERR_ARG;
+  if (a->box3d && (!a->heading || !a->size || !a->cls || !a->mean_size || !a->center || !a->heading_class || !a->heading_residual ||
+                   !a->size_class || !a->size_residual))
+    return T3D_ERR_ARG;
+  if (a->B <= 0 || a->N <= 0 || a->C_src < 3 || a->C_out < 3 || a->C_out > a->C_src || a->NH <= 0) return T3D_ERR_SHAPE;
+  AssembleArgs k{a->points, a->C_src, a->labels, a->pt_off, a->sel, a->choice, a->frustum_angle, a->box3d, a->heading, a->size, a->cls,
+                 a->mean_size, a->flip, a->shift_z, a->shift_y, a->B, a->N, a->C_out, a->rotate_to_center, a->NH, a->batch_data,
+                 a->batch_label, a->center, a->heading_class, a->heading_residual, a->size_class, a->size_residual, a->rot_angle};
+  assemble_batch_kernel<<<a->B, 256, 0, S(stream)>>>(k);
   T3D_CHECK_LAUNCH();
   return 0;
 }
