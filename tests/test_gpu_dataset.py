@@ -87,3 +87,50 @@ def test_rgb_detection_layout_and_pickle_roundtrip(tmp_path):
     assert img is None and one_hot.shape == (8, 10) and float(y_seg.abs().max()) == 0.0
     with pytest.raises(AssertionError):
         D.ROISegBoxDataset(CLASSES, 256, 'val', overwritten_data_path=path)           # 7 lists where 13 are expected
+
+
+def test_main_batch_end_to_end(tmp_path):
+    """Frustum file -> ROISegBoxDataset.get_batch -> model F + BoxPC refine (sess.run) -> device post-processing ->
+    predictions / result files -> 3D AP: the reference's test flow (test_semisup.main_batch, evaluate_predictions) end to
+    end on the device pieces.  Checked against the literal host inference() on the same batches."""
+    from transferable3d_b200 import roi_seg_box3d_dataset as D, utils, test_semisup as ts, eval_det as ed, weights, config, runtime as rt
+    from transferable3d_b200.constants import class2type
+    lists = _lists(45, seed=9, with_extra_class=False)
+    path = os.path.join(str(tmp_path), 'val.zip.pickle')
+    utils.save_zipped_pickle(lists, path)
+    ds = D.ROISegBoxDataset(CLASSES, 1024, 'val', rotate_to_center=True, overwritten_data_path=path, one_hot=True)
+    variables, _ = weights.standard_model_F()
+    FLAGS = config.cfg()
+    out_pickle, result_dir = os.path.join(str(tmp_path), 'pred.zip.pickle'), os.path.join(str(tmp_path), 'results')
+    with rt.precision('fp32'):
+        sess_ops = ts.get_model(32, 1024, 6, FLAGS, variables, cuda_graph=False)
+        np.random.seed(3)
+        pred = ts.main_batch(ds, CLASSES, 10, 1024, 6, prefix='F2_', use_boxpc_fit_prob=True, sess_ops=sess_ops,
+                             output_filename=out_pickle, result_dir=result_dir)
+        # the same batches through the literal host post-processing
+        np.random.seed(3)
+        sess, ops = sess_ops
+        ref_scores, ref_seg = [], []
+        for s in range(0, 45, 32):
+            e = min(45, s + 32)
+            b = ds.get_batch(np.arange(45), s, e, 1024, 6)
+            r = ts.inference(sess, ops, ts._pad_batch(b[0], 32).cpu().numpy(), ts._pad_batch(b[13], 32).cpu().numpy(), 32, prefix='F2_',
+                             use_boxpc_fit_prob=True)
+            ref_scores += list(r[6][:e - s])
+            ref_seg += list(r[0][:e - s])
+    assert len(pred) == 14 and all(len(l) == 45 for l in pred)
+    assert np.allclose(np.array(pred[9]), np.array(ref_scores), rtol=1e-5, atol=1e-5)
+    assert all(np.array_equal(a, b) for a, b in zip(pred[2], ref_seg))
+    assert pred[11] == ds.idx_l and pred[0][0].shape == (1024, 6)
+    back = utils.load_zipped_pickle(out_pickle)
+    assert len(back) == 14 and np.array_equal(back[3][7], pred[3][7])
+    n_lines = sum(len(open(os.path.join(result_dir, c + '_pred.txt')).read().splitlines()) for c in CLASSES)
+    assert n_lines == 45
+    # predictions -> boxes -> AP (evaluate.py:53-72); with random weights the AP is just a number in [0, 1]
+    corners = ed.prediction_corners(pred[3], pred[4], pred[5], pred[6], pred[7], pred[8])
+    pred_all, gt_all = {}, {}
+    for i in range(45):
+        pred_all.setdefault(pred[11][i], []).append((class2type[pred[10][i]], corners[i], pred[9][i]))
+        gt_all.setdefault(ds.idx_l[i], []).append((ds.cls_type_l[i], ds.box3d_l[i]))
+    rec, prec, ap = ed.eval_det(pred_all, gt_all, 0.25)
+    assert set(ap) == set(ds.cls_type_l) and all(0.0 <= v <= 1.0 for v in ap.values())

@@ -296,3 +296,95 @@ def fill_files(output_dir, to_fill_filename_list):
         filepath = os.path.join(output_dir, filename)
         if not os.path.exists(filepath):
             open(filepath, 'w').close()
+
+
+def _pad_batch(t, batch_size):
+    """The reference feeds a fixed-size batch (static TF graph) and leaves the unused tail rows zero (:470-471)."""
+    if t.shape[0] == batch_size:
+        return t
+    out = torch.zeros((batch_size,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    out[:t.shape[0]] = t
+    return out
+
+
+def main_batch(test_dataset, test_classes, num_class, num_point, num_channel, prefix='', semi_type=None, use_boxpc_fit_prob=False,
+               sess_ops=None, output_filename=None, result_dir=None, verbose=False, batch_size=32, FLAGS=None, variables=None):
+    """test_semisup.py:430-520: batches of 32 through get_batch -> inference -> the 14-list `predictions`
+    [ps, seg_gt, seg_pred, center, heading_cls, heading_res, size_cls, size_res, rot_angle, score, cls, file_num, box2d, box3d],
+    optional gz pickle and per-class result files.  test_dataset is roi_seg_box3d_dataset.ROISegBoxDataset (device batches);
+    the post-processing runs on the device (inference_device).  sess_ops=None builds the session from (FLAGS, variables)."""
+    from .utils import save_zipped_pickle
+    lists = [[] for _ in range(14)]
+    test_idxs = np.arange(0, len(test_dataset))
+    num_batches = int((len(test_dataset) + batch_size - 1) / batch_size)
+    sess, ops = sess_ops if sess_ops is not None else get_model(batch_size, num_point, num_channel, FLAGS, variables)
+    idx, iou_sum = 0, 0.0
+    for batch_idx in range(num_batches):
+        start_idx, end_idx = batch_idx * batch_size, min(len(test_dataset), (batch_idx + 1) * batch_size)
+        cur = end_idx - start_idx
+        b = test_dataset.get_batch(test_idxs, start_idx, end_idx, num_point, num_channel)
+        batch_data, batch_label, batch_rot_angle, batch_one_hot_vec = b[0], b[2], b[11], b[13]
+        out = inference_device(sess, ops, _pad_batch(batch_data, batch_size), _pad_batch(batch_one_hot_vec, batch_size), batch_size,
+                               prefix=prefix, use_boxpc_fit_prob=use_boxpc_fit_prob)
+        batch_output, center_pred, hclass_pred, hres_pred, sclass_pred, sres_pred, scores = out
+        data_h, label_h, rot_h, oh_h = (t.cpu().numpy() for t in (batch_data, batch_label, batch_rot_angle, batch_one_hot_vec))
+        for i in range(cur):                                  # segmentation IoU on the un-duplicated points (:479-490)
+            _, unique_idx = np.unique(data_h[i], axis=0, return_index=True)
+            y_pred, y_true = batch_output[i][unique_idx].astype(np.int64), label_h[i][unique_idx].astype(np.int64)
+            iou_sum += float(np.sum(y_pred & y_true)) / (np.sum(y_pred | y_true) + 1)
+        for i in range(cur):
+            vals = (data_h[i], label_h[i], batch_output[i], center_pred[i], hclass_pred[i], hres_pred[i], sclass_pred[i], sres_pred[i],
+                    rot_h[i], scores[i], int(np.argmax(oh_h[i])), test_dataset.idx_l[idx], test_dataset.box2d_l[idx],
+                    test_dataset.box3d_l[idx])
+            for l, v in zip(lists, vals):
+                l.append(v)
+            idx += 1
+    if verbose:
+        print('Mean segmentation IOU: %f' % (iou_sum / max(len(test_dataset.idx_l), 1)))
+    predictions = lists
+    if output_filename is not None:
+        save_zipped_pickle(predictions, output_filename)
+    if result_dir is not None:
+        write_detection_results(result_dir, test_classes, test_dataset.idx_l, test_dataset.cls_type_l, test_dataset.box2d_l,
+                                lists[3], lists[4], lists[5], lists[6], lists[7], lists[8], lists[9])
+    return predictions
+
+
+def main_batch_from_rgb_detection(test_dataset, test_classes, num_class, num_point, num_channel, prefix='', semi_type=None,
+                                  use_boxpc_fit_prob=False, use_oracle_mask=False, sess_ops=None, output_filename=None, result_dir=None,
+                                  verbose=False, batch_size=32, FLAGS=None, variables=None):
+    """test_semisup.py:336-428: the 7-list (rgb detection) flow; the score kept is the 2D detector's probability (:401) and
+    predictions = [ps, None, seg_pred, center, heading_cls, heading_res, size_cls, size_res, rot_angle, score, cls, file_num,
+    box2d, None]."""
+    from .utils import save_zipped_pickle
+    lists = [[] for _ in range(14)]
+    lists[1] = lists[13] = None
+    test_idxs = np.arange(0, len(test_dataset))
+    num_batches = int((len(test_dataset) + batch_size - 1) / batch_size)
+    sess, ops = sess_ops if sess_ops is not None else get_model(batch_size, num_point, num_channel, FLAGS, variables,
+                                                                 use_oracle_mask=use_oracle_mask)
+    idx = 0
+    for batch_idx in range(num_batches):
+        start_idx, end_idx = batch_idx * batch_size, min(len(test_dataset), (batch_idx + 1) * batch_size)
+        cur = end_idx - start_idx
+        batch_data, _, batch_rot_angle, batch_rgb_prob, batch_one_hot_vec, batch_oracle_y_seg = \
+            test_dataset.get_batch(test_idxs, start_idx, end_idx, num_point, num_channel, from_rgb_detection=True)
+        om = _pad_batch(batch_oracle_y_seg, batch_size) if use_oracle_mask else None
+        out = inference_device(sess, ops, _pad_batch(batch_data, batch_size), _pad_batch(batch_one_hot_vec, batch_size), batch_size,
+                               prefix=prefix, use_boxpc_fit_prob=use_boxpc_fit_prob, oracle_mask=om)
+        batch_output, center_pred, hclass_pred, hres_pred, sclass_pred, sres_pred, _ = out
+        data_h, rot_h, prob_h, oh_h = (t.cpu().numpy() for t in (batch_data, batch_rot_angle, batch_rgb_prob, batch_one_hot_vec))
+        for i in range(cur):
+            vals = {0: data_h[i], 2: batch_output[i], 3: center_pred[i], 4: hclass_pred[i], 5: hres_pred[i], 6: sclass_pred[i],
+                    7: sres_pred[i], 8: rot_h[i], 9: prob_h[i], 10: int(np.argmax(oh_h[i])), 11: test_dataset.idx_l[idx],
+                    12: test_dataset.box2d_l[idx]}
+            for k, v in vals.items():
+                lists[k].append(v)
+            idx += 1
+    predictions = lists
+    if output_filename is not None:
+        save_zipped_pickle(predictions, output_filename)
+    if result_dir is not None:
+        write_detection_results(result_dir, test_classes, test_dataset.idx_l, test_dataset.cls_type_l, test_dataset.box2d_l,
+                                lists[3], lists[4], lists[5], lists[6], lists[7], lists[8], lists[9])
+    return predictions
