@@ -109,7 +109,7 @@ extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ld
     if (xg_pre_ok(M, N, K, ws, ws_bytes)) {
       o.bpre = reinterpret_cast<const uint8_t*>(ws);
       o.nkb = (K + 63) / 64;
-      xg_presplit_kernel<<<dim3(o.nkb, ntn), 256, 0, S(stream)>>>(W, ldw, 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
+      xg_presplit_kernel<<<dim3(o.nkb, ntn, 4), 256, 0, S(stream)>>>(W, ldw, 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
       if (xg_use_pp(K, true)) {
         static int prepared_pp = xg_prepare_pp(xg_pp_kernel<3, true>) | xg_prepare_pp(xg_pp_kernel<1, true>);
         if (prepared_pp != 0) return prepared_pp;
@@ -608,7 +608,7 @@ extern "C" int t3d_gemm_f32_ws(const float* A, long long sam, long long sak, con
       o.bpre = reinterpret_cast<const uint8_t*>(ws);
       o.nkb = (K + 63) / 64;
       const int parts = g_f32_engine == 1 ? 3 : 1;
-      xg_presplit_kernel<<<dim3(o.nkb, ntn), 256, 0, S(stream)>>>(B, ldb, bk ? 1 : 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
+      xg_presplit_kernel<<<dim3(o.nkb, ntn, 4), 256, 0, S(stream)>>>(B, ldb, bk ? 1 : 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
       if (xg_use_pp(K)) {
         static int prepared_pp = xg_prepare_pp(xg_pp_kernel<3, false>) | xg_prepare_pp(xg_pp_kernel<1, false>);
         if (prepared_pp != 0) return prepared_pp;

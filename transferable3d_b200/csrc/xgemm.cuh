@@ -228,25 +228,31 @@ __device__ __forceinline__ void xg_loader(const float* __restrict__ P, long long
 constexpr size_t kXgPreBlockBytes = 3 * (size_t)kXgImage;       // one (n tile, k block): 3 parts x 16 KB
 inline size_t xg_pre_bytes(int N, int K) { return (size_t)((N + kXgBN - 1) / kXgBN) * ((K + 63) / 64) * kXgPreBlockBytes; }
 
+// grid (k blocks, n tiles, 4): block z handles k groups z*2, z*2+1 (8 k each) of the 64-wide block; a thread owns one
+// row and 8 consecutive k, i.e. one 16-byte chunk of each image.  (The first version wrote 2 bytes per store from 64 blocks
+// and took as long as the FC-head GEMMs it served: 29 us per call in the cfg3 launch list.)
 __global__ void __launch_bounds__(256) xg_presplit_kernel(const float* __restrict__ B, long long ldb, int unit_k, int N, int K,
                                                          int parts, uint8_t* __restrict__ ws) {
   const int kb = blockIdx.x, nt = blockIdx.y;
   uint8_t* dst = ws + ((size_t)nt * gridDim.x + kb) * kXgPreBlockBytes;
-  for (int e = threadIdx.x; e < 128 * 64; e += 256) {
-    const int r = unit_k ? (e >> 6) : (e & 127), kk = unit_k ? (e & 63) : (e >> 7);
-    const int n = nt * kXgBN + r, k = kb * 64 + kk;
-    float v = 0.0f;
-    if (n < N && k < K) v = unit_k ? B[(long long)n * ldb + k] : B[(long long)k * ldb + n];
-    const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)(kk >> 3)) + (uint32_t)(kk & 7) * 2u;
-    if (parts == 1) {
-      *reinterpret_cast<__nv_bfloat16*>(dst + off) = __float2bfloat16_rn(v);
-    } else {
-      uint32_t h, m, l;
-      xg_split(v, h, m, l);
-      *reinterpret_cast<uint16_t*>(dst + off) = (uint16_t)(h >> 16);
-      *reinterpret_cast<uint16_t*>(dst + kXgImage + off) = (uint16_t)(m >> 16);
-      *reinterpret_cast<uint16_t*>(dst + 2 * kXgImage + off) = (uint16_t)(l >> 16);
-    }
+  const int r = threadIdx.x & 127, kg = blockIdx.z * 2 + (threadIdx.x >> 7);       // row, 8-k group (= 16-byte chunk)
+  const int n = nt * kXgBN + r, k0 = kb * 64 + kg * 8;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = k0 + e;
+    v[e] = (n < N && k < K) ? (unit_k ? B[(long long)n * ldb + k] : B[(long long)k * ldb + n]) : 0.0f;
+  }
+  const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)kg);
+  if (parts == 1) {
+    *reinterpret_cast<uint4*>(dst + off) = make_uint4(xg_pack_rn(v[0], v[1]), xg_pack_rn(v[2], v[3]), xg_pack_rn(v[4], v[5]), xg_pack_rn(v[6], v[7]));
+  } else {
+    uint32_t h[8], m[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xg_split(v[e], h[e], m[e], l[e]);
+    *reinterpret_cast<uint4*>(dst + off) = make_uint4(xg_pack(h[0], h[1]), xg_pack(h[2], h[3]), xg_pack(h[4], h[5]), xg_pack(h[6], h[7]));
+    *reinterpret_cast<uint4*>(dst + kXgImage + off) = make_uint4(xg_pack(m[0], m[1]), xg_pack(m[2], m[3]), xg_pack(m[4], m[5]), xg_pack(m[6], m[7]));
+    *reinterpret_cast<uint4*>(dst + 2 * kXgImage + off) = make_uint4(xg_pack(l[0], l[1]), xg_pack(l[2], l[3]), xg_pack(l[4], l[5]), xg_pack(l[6], l[7]));
   }
 }
 
