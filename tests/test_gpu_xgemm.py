@@ -176,3 +176,26 @@ def test_bf16_engine_is_a_bf16_gemm(M):
     full = x.double() @ w.double()
     assert float((y.double() - full).abs().max()) / float(full.abs().mean()) < 5e-2       # bf16-class accuracy
     assert rt.get_f32_engine() == 'tc'
+
+
+@pytest.mark.parametrize('Kin', [3, 12])
+def test_skinny_first_layer_shapes(Kin):
+    """skinny_gemm.cuh: forward with K = 3 / 12, input gradient with N = 3 / 12, weight gradient with M = 3 / 12 over
+    B*N rows -- the HBM-bound first-layer shapes of the point networks -- against a float64 matmul."""
+    rt = _rt()
+    rows, N = 70000, 128
+    g = torch.Generator(device='cuda').manual_seed(Kin)
+    x = torch.randn(rows, Kin, generator=g, device='cuda')
+    w = torch.randn(Kin, N, generator=g, device='cuda') * 0.3
+    b = torch.randn(N, generator=g, device='cuda')
+    dy = torch.randn(rows, N, generator=g, device='cuda')
+    y = _gemm(x, Kin, 1, w, N, 1, rows, N, Kin, bias=b)                       # forward
+    dx = _gemm(dy, N, 1, w, 1, N, rows, Kin, N)                               # dgrad: dY W^T
+    dw = _gemm(x, 1, Kin, dy, N, 1, Kin, N, rows, splitk=64)                  # wgrad: X^T dY
+    dw1 = _gemm(x, 1, Kin, dy, N, 1, Kin, N, rows, splitk=1)
+    torch.cuda.synchronize()
+    assert float((y.double() - (x.double() @ w.double() + b.double())).abs().max()) < 1e-5
+    assert float((dx.double() - dy.double() @ w.double().t()).abs().max()) < 2e-5
+    ref = x.double().t() @ dy.double()
+    assert float((dw.double() - ref).abs().max()) < 2e-4 * float(ref.abs().max())
+    assert float((dw1.double() - ref).abs().max()) < 2e-4 * float(ref.abs().max())

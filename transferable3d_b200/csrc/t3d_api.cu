@@ -13,6 +13,7 @@
 #include "eval_ops.cuh"
 #include "surface_ops.cuh"
 #include "data_ops.cuh"
+#include "skinny_gemm.cuh"
 #define T3D_SGEMM_WITH_EPILOGUES
 #include "sgemm.cuh"
 #define T3D_XGEMM_WITH_EPILOGUES
@@ -583,6 +584,29 @@ extern "C" int t3d_gemm_f32_ws(const float* A, long long sam, long long sak, con
   if ((sam != 1 && sak != 1) || (sbk != 1 && sbn != 1)) return T3D_ERR_SHAPE;
   if (splitk > 1) T3D_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, S(stream)));
   GemmArgs a{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias};
+  {   // HBM-bound first-layer shapes (skinny_gemm.cuh); 128-bit accesses need aligned bases and leading dimensions
+    auto al16 = [](const void* p) { return (((uintptr_t)p) & 15) == 0; };
+    const int sms = xg_num_sms();
+    static const int skinny = [] { const char* e = getenv("T3D_SKINNY"); return e ? atoi(e) : 7; }();      // bit 0 k, 1 n, 2 m
+    if ((skinny & 1) && M >= 4096 && K <= kSkinnyMax && sak == 1 && sbn == 1 && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && al16(C) && ldc % 4 == 0) {
+      if (splitk > 1) { /* C was zeroed above; a single pass writes every element */ }
+      skinny_k_kernel<<<sms * 8, 256, sizeof(float) * (size_t)(K * N + N), S(stream)>>>(A, sam, B, sbk, bias, C, ldc, M, N, K);
+      T3D_CHECK_LAUNCH();
+      return 0;
+    }
+    if ((skinny & 2) && M >= 4096 && N <= kSkinnyMax && sak == 1 && sbk == 1 && sbn != 1 && K % 4 == 0 && K <= 1024 && al16(A) && sam % 4 == 0) {
+      skinny_n_kernel<<<sms * 8, 256, sizeof(float) * (size_t)N * K, S(stream)>>>(A, sam, B, sbn, bias, C, ldc, M, N, K);
+      T3D_CHECK_LAUNCH();
+      return 0;
+    }
+    if ((skinny & 4) && K >= 4096 && M <= kSkinnyMax && sam == 1 && sbn == 1 && !bias && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && al16(B) &&
+        sbk % 4 == 0 && (size_t)M * N * sizeof(float) <= 48 * 1024) {
+      if (splitk <= 1) T3D_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, S(stream)));
+      skinny_m_kernel<<<sms * 4, 256, sizeof(float) * (size_t)M * N, S(stream)>>>(A, sak, B, sbk, C, ldc, M, N, K);
+      T3D_CHECK_LAUNCH();
+      return 0;
+    }
+  }
   if (xg_fits(M, N, K)) {                    // tensor cores, bf16 x 3 split (xgemm.cuh)
     static int prepared = xg_prepare(xgemm_kernel<true, true, 3>) | xg_prepare(xgemm_kernel<true, false, 3>) |
                           xg_prepare(xgemm_kernel<false, true, 3>) | xg_prepare(xgemm_kernel<false, false, 3>) |

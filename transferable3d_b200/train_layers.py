@@ -115,10 +115,15 @@ class TrainLayer(object):
             call('t3d_bn_backward', ptr(dout), outp, ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(self.p('bn/gamma')),
                  ptr(s1), ptr(s2), M, self.N, self.act, stream())
         dy = dout
-        bs = torch.empty(self.N, device=dev)
-        junk = torch.empty(self.N, device=dev)
-        call('t3d_colstats', ptr(dy), None, None, None, None, ptr(bs), ptr(junk), M, self.N, 0, 0, stream())
-        g[self.name + '/biases'].copy_(bs)
+        if self.bn:
+            # a bias in front of a batch norm cancels in (y - mean): its gradient, the column sum of the BN input gradient,
+            # is analytically zero (what TF accumulates there is rounding noise) -- no pass over dY for it
+            g[self.name + '/biases'].zero_()
+        else:
+            bs = torch.empty(self.N, device=dev)
+            junk = torch.empty(self.N, device=dev)
+            call('t3d_colstats', ptr(dy), None, None, None, None, ptr(bs), ptr(junk), M, self.N, 0, 0, stream())
+            g[self.name + '/biases'].copy_(bs)
         # wgrad: dW[K,N] = X^T dY
         dW = g[self.name + '/weights'].view(self.K, self.N)
         call('t3d_gemm_f32', ptr(self.x), 1, self.K, ptr(dy), self.N, 1, ptr(dW), self.N, self.K, self.N, M,
