@@ -548,22 +548,36 @@ __device__ __forceinline__ float4 ldg4(const float* __restrict__ p, unsigned c4)
   const float* q = p + 4u * c4;
   return make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
 }
+// Per-channel parameters are staged once per block in shared memory (as float4s, 16 scalar loads per data float4 otherwise)
+// and a block streams kBnIter x 1024 float4s (64 KB) to amortise the staging.
+constexpr int kBnIter = 4;
 __global__ void __launch_bounds__(256) bn_apply4_kernel(const float4* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float4* __restrict__ out,
                                                        unsigned n4, unsigned C4, int act) {
-  float4 v[kEw4];
+  extern __shared__ float4 bn_sp[];                  // [4][C4]: mean, rstd, gamma, beta
+  for (unsigned i = threadIdx.x; i < C4; i += 256) {
+    bn_sp[i] = ldg4(mean, i); bn_sp[C4 + i] = ldg4(rstd, i); bn_sp[2 * C4 + i] = ldg4(gamma, i); bn_sp[3 * C4 + i] = ldg4(beta, i);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int it = 0; it < kBnIter; ++it) {
+    const unsigned base = (blockIdx.x * kBnIter + it) * (256u * kEw4) + threadIdx.x;
+    float4 v[kEw4];
 #pragma unroll
-  T3D_EW4_LOOP(q) v[u] = y[q];
+    for (int u = 0; u < kEw4; ++u) if (base + u * 256u < n4) v[u] = y[base + u * 256u];
 #pragma unroll
-  T3D_EW4_LOOP(q) {
-    const unsigned c = q % C4;
-    const float4 m = ldg4(mean, c), r = ldg4(rstd, c), g = ldg4(gamma, c), b = ldg4(beta, c);
-    float4 o;
-    o.x = act_apply(g.x * (v[u].x - m.x) * r.x + b.x, act);
-    o.y = act_apply(g.y * (v[u].y - m.y) * r.y + b.y, act);
-    o.z = act_apply(g.z * (v[u].z - m.z) * r.z + b.z, act);
-    o.w = act_apply(g.w * (v[u].w - m.w) * r.w + b.w, act);
-    out[q] = o;
+    for (int u = 0; u < kEw4; ++u) {
+      const unsigned q = base + u * 256u;
+      if (q >= n4) continue;
+      const unsigned c = q % C4;
+      const float4 m = bn_sp[c], r = bn_sp[C4 + c], g = bn_sp[2 * C4 + c], b = bn_sp[3 * C4 + c];
+      float4 o;
+      o.x = act_apply(g.x * (v[u].x - m.x) * r.x + b.x, act);
+      o.y = act_apply(g.y * (v[u].y - m.y) * r.y + b.y, act);
+      o.z = act_apply(g.z * (v[u].z - m.z) * r.z + b.z, act);
+      o.w = act_apply(g.w * (v[u].w - m.w) * r.w + b.w, act);
+      out[q] = o;
+    }
   }
 }
 
@@ -576,21 +590,36 @@ __global__ void __launch_bounds__(256) bn_backward4_kernel(float4* __restrict__ 
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ gamma, const float* __restrict__ s1,
                                                           const float* __restrict__ s2, unsigned n4, unsigned C4, int M, int act) {
-  float4 d[kEw4], o[kEw4], yy[kEw4];
+  extern __shared__ float4 bn_sp[];                  // [5][C4]: mean, rstd, gamma, s1, s2
+  for (unsigned i = threadIdx.x; i < C4; i += 256) {
+    bn_sp[i] = ldg4(mean, i); bn_sp[C4 + i] = ldg4(rstd, i); bn_sp[2 * C4 + i] = ldg4(gamma, i);
+    bn_sp[3 * C4 + i] = ldg4(s1, i); bn_sp[4 * C4 + i] = ldg4(s2, i);
+  }
+  __syncthreads();
   const bool has_out = out != nullptr;
-#pragma unroll
-  T3D_EW4_LOOP(q) { d[u] = dOut[q]; yy[u] = y[q]; o[u] = has_out ? out[q] : make_float4(0.f, 0.f, 0.f, 0.f); }
   const float inv = 1.0f / (float)M;
+#pragma unroll 1
+  for (int it = 0; it < kBnIter; ++it) {
+    const unsigned base = (blockIdx.x * kBnIter + it) * (256u * kEw4) + threadIdx.x;
+    float4 d[kEw4], o[kEw4], yy[kEw4];
 #pragma unroll
-  T3D_EW4_LOOP(q) {
-    const unsigned c = q % C4;
-    const float4 m = ldg4(mean, c), r = ldg4(rstd, c), g = ldg4(gamma, c), a1 = ldg4(s1, c), a2 = ldg4(s2, c);
-    float4 w;
-    w.x = bn_bwd_one(d[u].x, o[u].x, has_out, yy[u].x, m.x, r.x, g.x, a1.x, a2.x, inv, act);
-    w.y = bn_bwd_one(d[u].y, o[u].y, has_out, yy[u].y, m.y, r.y, g.y, a1.y, a2.y, inv, act);
-    w.z = bn_bwd_one(d[u].z, o[u].z, has_out, yy[u].z, m.z, r.z, g.z, a1.z, a2.z, inv, act);
-    w.w = bn_bwd_one(d[u].w, o[u].w, has_out, yy[u].w, m.w, r.w, g.w, a1.w, a2.w, inv, act);
-    dOut[q] = w;
+    for (int u = 0; u < kEw4; ++u) {
+      const unsigned q = base + u * 256u;
+      if (q < n4) { d[u] = dOut[q]; yy[u] = y[q]; o[u] = has_out ? out[q] : make_float4(0.f, 0.f, 0.f, 0.f); }
+    }
+#pragma unroll
+    for (int u = 0; u < kEw4; ++u) {
+      const unsigned q = base + u * 256u;
+      if (q >= n4) continue;
+      const unsigned c = q % C4;
+      const float4 m = bn_sp[c], r = bn_sp[C4 + c], g = bn_sp[2 * C4 + c], a1 = bn_sp[3 * C4 + c], a2 = bn_sp[4 * C4 + c];
+      float4 w;
+      w.x = bn_bwd_one(d[u].x, o[u].x, has_out, yy[u].x, m.x, r.x, g.x, a1.x, a2.x, inv, act);
+      w.y = bn_bwd_one(d[u].y, o[u].y, has_out, yy[u].y, m.y, r.y, g.y, a1.y, a2.y, inv, act);
+      w.z = bn_bwd_one(d[u].z, o[u].z, has_out, yy[u].z, m.z, r.z, g.z, a1.z, a2.z, inv, act);
+      w.w = bn_bwd_one(d[u].w, o[u].w, has_out, yy[u].w, m.w, r.w, g.w, a1.w, a2.w, inv, act);
+      dOut[q] = w;
+    }
   }
 }
 

@@ -708,9 +708,9 @@ extern "C" int t3d_bn_apply(const float* y, const float* mean, const float* rstd
   if (!y || !mean || !rstd || !gamma || !beta || !out) return T3D_ERR_ARG;
   if (act < 0 || act > 3) return T3D_ERR_SHAPE;
   const size_t total = (size_t)M * C;
-  if (ew4_ok(total, C, {y, out})) {
+  if (ew4_ok(total, C, {y, out}) && C <= 2048) {
     using F4 = const float4*;
-    bn_apply4_kernel<<<ew4_grid(total), 256, 0, S(stream)>>>((F4)y, mean, rstd, gamma, beta, (float4*)out,
+    bn_apply4_kernel<<<(ew4_grid(total) + kBnIter - 1) / kBnIter, 256, sizeof(float) * 4 * (size_t)C, S(stream)>>>((F4)y, mean, rstd, gamma, beta, (float4*)out,
                                                              (unsigned)(total / 4), (unsigned)(C / 4), act);
   } else {
     bn_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(y, mean, rstd, gamma, beta, out, total, C, act);
@@ -724,9 +724,9 @@ extern "C" int t3d_bn_backward(float* dOut, const float* out, const float* y, co
   if (!dOut || !y || !mean || !rstd || !gamma || !s1 || !s2) return T3D_ERR_ARG;
   if (act < 0 || act > 3) return T3D_ERR_SHAPE;
   const size_t total = (size_t)M * C;
-  if (ew4_ok(total, C, {dOut, out, y})) {
+  if (ew4_ok(total, C, {dOut, out, y}) && C <= 2048) {
     using F4 = const float4*;
-    bn_backward4_kernel<<<ew4_grid(total), 256, 0, S(stream)>>>((float4*)dOut, (F4)out, (F4)y, mean, rstd, gamma, s1, s2,
+    bn_backward4_kernel<<<(ew4_grid(total) + kBnIter - 1) / kBnIter, 256, sizeof(float) * 5 * (size_t)C, S(stream)>>>((float4*)dOut, (F4)out, (F4)y, mean, rstd, gamma, s1, s2,
                                                                 (unsigned)(total / 4), (unsigned)(C / 4), M, act);
   } else {
     bn_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(dOut, out, y, mean, rstd, gamma, s1, s2, total, C, M, act);
