@@ -205,6 +205,11 @@ int t3d_bn_backward(float* dOut, const float* out, const float* y, const float* 
                     const float* s1, const float* s2, int M, int C, int act, t3d_stream_t stream);
 int t3d_maxpool_fwd(const float* x, int B, int N, int C, float* out, int* arg, t3d_stream_t stream);
 int t3d_maxpool_bwd(const float* dout, const int* arg, int B, int N, int C, float* dx, t3d_stream_t stream);
+/* the same with the `net * mask` of the masked stacks (semisup_models.py:184-185, 240-241) folded in: pools x * rowmask[row]
+ * without materialising the product; the backward scales the routed gradient by the mask of the arg-max row */
+int t3d_maxpool_masked_fwd(const float* x, const float* rowmask, int B, int N, int C, float* out, int* arg, t3d_stream_t stream);
+int t3d_maxpool_masked_bwd(const float* dout, const int* arg, const float* rowmask, int B, int N, int C, float* dx,
+                           t3d_stream_t stream);
 int t3d_scale_mask(const float* x, const float* mask, float scale, float* out, long long n, t3d_stream_t stream);
 typedef struct {
   const float *out9, *y_iou, *y_dc, *y_ds, *y_da;

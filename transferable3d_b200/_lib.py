@@ -132,6 +132,8 @@ SIGNATURES = {
     't3d_bn_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     't3d_maxpool_fwd': (_I, [_P, _I, _I, _I, _P, _P, _P]),
     't3d_maxpool_bwd': (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    't3d_maxpool_masked_fwd': (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    't3d_maxpool_masked_bwd': (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     't3d_scale_mask': (_I, [_P, _P, _F, _P, _L, _P]),
     't3d_boxpc_loss': (_I, [_c.POINTER(t3d_boxpc_loss_args), _P]),
     't3d_adam': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _P]),

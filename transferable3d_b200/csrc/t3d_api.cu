@@ -735,19 +735,27 @@ extern "C" int t3d_bn_backward(float* dOut, const float* out, const float* y, co
   return 0;
 }
 
-extern "C" int t3d_maxpool_fwd(const float* x, int B, int N, int C, float* out, int* arg, t3d_stream_t stream) {
+extern "C" int t3d_maxpool_masked_fwd(const float* x, const float* rowmask, int B, int N, int C, float* out, int* arg,
+                                      t3d_stream_t stream) {
   if (!x || !out || !arg) return T3D_ERR_ARG;
-  maxpool_fwd_kernel<<<(B * C + 255) / 256, 256, 0, S(stream)>>>(x, B, N, C, out, arg);
+  maxpool_fwd_kernel<<<(B * C + 255) / 256, 256, 0, S(stream)>>>(x, rowmask, B, N, C, out, arg);
   T3D_CHECK_LAUNCH();
   return 0;
 }
+extern "C" int t3d_maxpool_fwd(const float* x, int B, int N, int C, float* out, int* arg, t3d_stream_t stream) {
+  return t3d_maxpool_masked_fwd(x, nullptr, B, N, C, out, arg, stream);
+}
 
-extern "C" int t3d_maxpool_bwd(const float* dout, const int* arg, int B, int N, int C, float* dx, t3d_stream_t stream) {
+extern "C" int t3d_maxpool_masked_bwd(const float* dout, const int* arg, const float* rowmask, int B, int N, int C, float* dx,
+                                      t3d_stream_t stream) {
   if (!dout || !arg || !dx) return T3D_ERR_ARG;
   T3D_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * N * C, S(stream)));
-  maxpool_bwd_kernel<<<(B * C + 255) / 256, 256, 0, S(stream)>>>(dout, arg, B, N, C, dx);
+  maxpool_bwd_kernel<<<(B * C + 255) / 256, 256, 0, S(stream)>>>(dout, arg, rowmask, B, N, C, dx);
   T3D_CHECK_LAUNCH();
   return 0;
+}
+extern "C" int t3d_maxpool_bwd(const float* dout, const int* arg, int B, int N, int C, float* dx, t3d_stream_t stream) {
+  return t3d_maxpool_masked_bwd(dout, arg, nullptr, B, N, C, dx, stream);
 }
 
 extern "C" int t3d_scale_mask(const float* x, const float* mask, float scale, float* out, long long n, t3d_stream_t stream) {

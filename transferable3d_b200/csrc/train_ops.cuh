@@ -190,20 +190,43 @@ __global__ void bn_backward_kernel(float* __restrict__ dOut, const float* __rest
 }
 
 // ----------------------------------------------------------------------------- max-pool over points with argmax
-__global__ void maxpool_fwd_kernel(const float* __restrict__ x, int B, int N, int C, float* __restrict__ out, int* __restrict__ arg) {
+// rowmask != null: the pooled tensor is x * rowmask[row] (the `net * mask` in front of the max-pool of the masked stacks,
+// semisup_models.py:184-185, 240-241) without materialising the product; its backward scales the routed gradient by the
+// mask of the arg-max row -- identical to multiplying afterwards, two passes over the activation fewer each way.
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ rowmask, int B, int N, int C,
+                                   float* __restrict__ out, int* __restrict__ arg) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;        // over B*C
   if (i >= B * C) return;
   const int b = i / C, c = i % C;
   const float* p = x + (size_t)b * N * C + c;
-  float m = p[0]; int am = 0;
-  for (int n = 1; n < N; ++n) { const float v = p[(size_t)n * C]; if (v > m) { m = v; am = n; } }    // first max wins
+  const float* rm = rowmask ? rowmask + (size_t)b * N : nullptr;
+  float m = rm ? p[0] * rm[0] : p[0]; int am = 0;
+  int n = 1;
+  for (; n + 8 <= N; n += 8) {                                  // 8 rows in flight; compared in order: first max wins
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = p[(size_t)(n + j) * C];
+    if (rm) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= rm[n + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (v[j] > m) { m = v[j]; am = n + j; }
+  }
+  for (; n < N; ++n) {
+    float v = p[(size_t)n * C];
+    if (rm) v *= rm[n];
+    if (v > m) { m = v; am = n; }
+  }
   out[i] = m; arg[i] = am;
 }
-__global__ void maxpool_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ arg, int B, int N, int C, float* __restrict__ dx) {
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ arg, const float* __restrict__ rowmask,
+                                   int B, int N, int C, float* __restrict__ dx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i % C;
-  dx[((size_t)b * N + arg[i]) * C + c] = dout[i];             // dx is zero-initialised by the caller
+  const size_t row = (size_t)b * N + arg[i];
+  dx[row * C + c] = rowmask ? dout[i] * rowmask[row] : dout[i];       // dx is zero-initialised by the caller
 }
 
 // out = x * mask * scale  (tf.nn.dropout forward and backward with the same keep mask, scale = 1/keep_prob)

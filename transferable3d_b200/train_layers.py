@@ -163,16 +163,17 @@ class EvalLayer(object):
         return gemm(dout, self.N, 1, Wsub, 1, self.N, M, k_hi - k_lo, self.N)
 
 
-def maxpool(x, B, N, C):
+def maxpool(x, B, N, C, rowmask=None):
+    """max over the N rows of each group (+ arg-max); rowmask: pool x * rowmask[row] without materialising it."""
     pooled = torch.empty((B, C), dtype=torch.float32, device=x.device)
     arg = torch.empty((B, C), dtype=torch.int32, device=x.device)
-    call('t3d_maxpool_fwd', ptr(x), B, N, C, ptr(pooled), ptr(arg), stream())
+    call('t3d_maxpool_masked_fwd', ptr(x), ptr(rowmask), B, N, C, ptr(pooled), ptr(arg), stream())
     return pooled, arg
 
 
-def maxpool_bwd(g, arg, B, N, C):
+def maxpool_bwd(g, arg, B, N, C, rowmask=None):
     dx = torch.empty((B * N, C), dtype=torch.float32, device=g.device)
-    call('t3d_maxpool_bwd', ptr(g), ptr(arg), B, N, C, ptr(dx), stream())
+    call('t3d_maxpool_masked_bwd', ptr(g), ptr(arg), ptr(rowmask), B, N, C, ptr(dx), stream())
     return dx
 
 

@@ -168,9 +168,7 @@ class SemiAdvTrainGraph(object):
         x = xyz1.reshape(B * N, 3)
         for l in Tn[:3]:
             x = l.forward(x, bn_decay)
-        xm = rowmask_mul(x, rowmask)
-        t_pool, t_arg = maxpool(xm, B, N, 256)
-        del xm
+        t_pool, t_arg = maxpool(x, B, N, 256, rowmask)          # max(net * mask) without the product in HBM
         h = Tn[3].forward(t_pool, bn_decay)
         h = Tn[4].forward(h, bn_decay)
         t_out = Tn[5].forward(h, bn_decay)
@@ -184,9 +182,7 @@ class SemiAdvTrainGraph(object):
         x = xin.reshape(B * N, 3)
         for l in Bx[:4]:
             x = l.forward(x, bn_decay)
-        xm = rowmask_mul(x, rowmask)
-        feats_lv1, b_arg = maxpool(xm, B, N, 512)
-        del xm
+        feats_lv1, b_arg = maxpool(x, B, N, 512, rowmask)
         ep['feats_lv1'] = feats_lv1
         h = Bx[4].forward(feats_lv1, bn_decay, keep=False)
         ep['feats_lv2'] = h
@@ -278,8 +274,7 @@ class SemiAdvTrainGraph(object):
         train_box = 'class_agnostic/box_est/conv-reg1/weights' in self.grad
         train_tnet = 'class_agnostic/tnet/fc3-stage1/weights' in self.grad
         if train_box:
-            g = maxpool_bwd(g_lv1, b_arg, B, N, 512)
-            rowmask_mul(g, rowmask, inplace=True)
+            g = maxpool_bwd(g_lv1, b_arg, B, N, 512, rowmask)
             g = Bx[3].backward(g)
             g = Bx[2].backward(g)
             g = Bx[1].backward(g)
@@ -295,8 +290,7 @@ class SemiAdvTrainGraph(object):
             g = Tn[5].backward(ds1.contiguous().clone())
             g = Tn[4].backward(g)
             g = Tn[3].backward(g)
-            g = maxpool_bwd(g, t_arg, B, N, 256)
-            rowmask_mul(g, rowmask, inplace=True)
+            g = maxpool_bwd(g, t_arg, B, N, 256, rowmask)
             g = Tn[2].backward(g)
             g = Tn[1].backward(g)
             Tn[0].backward(g, need_dx=False)
