@@ -199,3 +199,20 @@ def test_skinny_first_layer_shapes(Kin):
     ref = x.double().t() @ dy.double()
     assert float((dw.double() - ref).abs().max()) < 2e-4 * float(ref.abs().max())
     assert float((dw1.double() - ref).abs().max()) < 2e-4 * float(ref.abs().max())
+
+
+def test_skinny_linear_first_and_last_layers():
+    """t3d_linear_f32 on the HBM-bound layers of the fp32-mode pipeline: conv1 (K = 6 / 3 inputs, bias + ReLU) and conv10
+    (N = 2 outputs, bias only), M >= 4096 rows."""
+    rt = _rt()
+    g = torch.Generator(device='cuda').manual_seed(21)
+    M = 9000
+    for K, N, act in ((6, 64, 'relu'), (3, 128, 'relu'), (12, 128, None), (128, 2, None), (256, 12, None)):
+        x = torch.randn(M, K, generator=g, device='cuda')
+        w = torch.randn(K, N, generator=g, device='cuda') * 0.2
+        b = torch.randn(N, generator=g, device='cuda')
+        y, _ = rt.linear(x, w, b, act)
+        ref = x.double() @ w.double() + b.double()
+        if act == 'relu':
+            ref = torch.relu(ref)
+        assert float((y.double() - ref).abs().max()) < 2e-5, (K, N, act)

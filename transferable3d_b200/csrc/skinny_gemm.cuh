@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "simt_ops.cuh"     // apply_act
 
 namespace t3d {
 
@@ -15,7 +16,7 @@ constexpr int kSkinnyMax = 16;
 //     thread = 4 consecutive columns of one row; a block covers 256 * 4 / N rows per step.
 __global__ void __launch_bounds__(256) skinny_k_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B,
                                                       long long ldb, const float* __restrict__ bias, float* __restrict__ C,
-                                                      long long ldc, int M, int N, int K) {
+                                                      long long ldc, int M, int N, int K, int act = 0) {
   extern __shared__ float sB[];                      // [K][N] + bias [N]
   for (int i = threadIdx.x; i < K * N; i += 256) sB[i] = B[(long long)(i / N) * ldb + (i % N)];
   for (int i = threadIdx.x; i < N; i += 256) sB[K * N + i] = bias ? bias[i] : 0.0f;
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(256) skinny_k_kernel(const float* __restrict__
       const float4 w = *reinterpret_cast<const float4*>(&sB[k * N + cq]);
       acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
     }
+    if (act != 0) { acc.x = apply_act(acc.x, act); acc.y = apply_act(acc.y, act); acc.z = apply_act(acc.z, act); acc.w = apply_act(acc.w, act); }
     *reinterpret_cast<float4*>(C + m * ldc + cq) = acc;
   }
 }
@@ -39,10 +41,10 @@ __global__ void __launch_bounds__(256) skinny_k_kernel(const float* __restrict__
 //     one warp per row: lanes stride over K with 128-bit loads, N warp reductions.  (A 4-rows-per-warp / 8-lanes-per-row
 //     mapping with 3 shuffle steps per output was measured slower: 426 against 305 us at N = 12.)
 __global__ void __launch_bounds__(256) skinny_n_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B,
-                                                      long long ldb, const float* __restrict__ bias, float* __restrict__ C,
-                                                      long long ldc, int M, int N, int K) {
-  extern __shared__ float sB[];                      // [N][K]
-  for (int i = threadIdx.x; i < N * K; i += 256) sB[i] = B[(long long)(i / K) * ldb + (i % K)];
+                                                      long long sbn, const float* __restrict__ bias, float* __restrict__ C,
+                                                      long long ldc, int M, int N, int K, long long sbk = 1) {
+  extern __shared__ float sB[];                      // [N][K]; B(k,n) = B[k*sbk + n*sbn]
+  for (int i = threadIdx.x; i < N * K; i += 256) sB[i] = B[(long long)(i % K) * sbk + (long long)(i / K) * sbn];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long m = (long long)blockIdx.x * 8 + warp; m < M; m += (long long)gridDim.x * 8) {

@@ -99,6 +99,19 @@ extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ld
   if (M <= 0 || K <= 0 || N <= 0 || act < 0 || act > 3) return T3D_ERR_SHAPE;
   if ((gbias || gmax) && rows_per_group <= 0) return T3D_ERR_SHAPE;
   LinearArgs a{X, ldx, W, ldw, bias, gbias, rows_per_group, Y, ldy, M, K, N, act, rowmask, gmax};
+  if (M >= 4096 && Y && !gbias && !rowmask && !gmax) {       // HBM-bound first / last layers (skinny_gemm.cuh)
+    auto al16 = [](const void* p) { return (((uintptr_t)p) & 15) == 0; };
+    if (K <= kSkinnyMax && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && al16(Y) && ldy % 4 == 0) {
+      skinny_k_kernel<<<xg_num_sms() * 8, 256, sizeof(float) * (size_t)(K * N + N), S(stream)>>>(X, ldx, W, ldw, bias, Y, ldy, M, N, K, act);
+      T3D_CHECK_LAUNCH();
+      return 0;
+    }
+    if (N <= kSkinnyMax && act == 0 && K % 4 == 0 && K <= 1024 && al16(X) && ldx % 4 == 0) {
+      skinny_n_kernel<<<xg_num_sms() * 8, 256, sizeof(float) * (size_t)N * K, S(stream)>>>(X, ldx, W, 1, bias, Y, ldy, M, N, K, ldw);
+      T3D_CHECK_LAUNCH();
+      return 0;
+    }
+  }
   if (xg_fits(M, N, K)) {                    // tensor cores, bf16 x 3 split (xgemm.cuh)
     static int prepared = xg_prepare(xlinear_kernel<3>) | xg_prepare(xlinear_kernel<1>) | xg_prepare(xlinear_pre_kernel<3>) |
                           xg_prepare(xlinear_pre_kernel<1>);
