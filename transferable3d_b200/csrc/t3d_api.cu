@@ -75,11 +75,16 @@ static inline bool xg_pre_ok(int M, int N, int K, const void* ws, size_t ws_byte
 // the epilogue dominate the one-tile kernel (measured: 98 / 117 / 140 against 86 / 103 / 121 TFLOP/s on the 128 -> 128 /
 // 256 / 1024 forward layers); for longer K the two co-resident one-tile CTAs win (176 against 158 on dgrad 256 <- 512).
 // T3D_XG_PP=0 / 1 in the environment forces one or the other.
-// The t3d_linear_f32 epilogue (group bias, activation, row mask, group max) is too heavy for the persistent kernel's 4
-// epilogue warps -- the fp32-mode pipeline dropped from 43.6 k to 24.8 k frustums/s with it -- so only t3d_gemm_f32 uses it.
-static bool xg_use_pp(int K, bool linear = false) {
+// t3d_linear_f32: with an output to store, the epilogue is too heavy for the persistent kernel's 4 epilogue warps (the
+// fp32-mode pipeline dropped from 43.6 k to 24.8 k frustums/s with it everywhere; restricted to the max-only layers -- conv5 +
+// max-pool, no Y to store -- it still lost: 32.7 k against 45.9 k; with the K <= 64 layers added 26.9 k).  Off by default;
+// T3D_XG_PP_LINEAR=1|3 switches those two sets on for measurement.
+static bool xg_use_pp(int K, bool linear = false, bool has_y = true) {
   static const int v = [] { const char* e = getenv("T3D_XG_PP"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
-  return v < 0 ? (K <= 128 && !linear) : v != 0;
+  static const int lin = [] { const char* e = getenv("T3D_XG_PP_LINEAR"); return e ? atoi(e) : 0; }();     // bit 0: max-only layers, bit 1: K <= 64
+  if (v >= 0) return v != 0;
+  if (!linear) return K <= 128;
+  return ((lin & 1) && !has_y && K <= 128) || ((lin & 2) && K <= 64);
 }
 static int xg_num_sms() {
   static const int n = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
@@ -124,7 +129,7 @@ extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ld
       o.bpre = reinterpret_cast<const uint8_t*>(ws);
       o.nkb = (K + 63) / 64;
       xg_presplit_kernel<<<dim3(o.nkb, ntn, 4), 256, 0, S(stream)>>>(W, ldw, 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
-      if (xg_use_pp(K, true)) {
+      if (xg_use_pp(K, true, Y != nullptr)) {
         static int prepared_pp = xg_prepare_pp(xg_pp_kernel<3, true>) | xg_prepare_pp(xg_pp_kernel<1, true>);
         if (prepared_pp != 0) return prepared_pp;
         const int g = ntm * ntn < xg_num_sms() ? ntm * ntn : xg_num_sms();
