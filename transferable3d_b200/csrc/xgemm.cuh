@@ -522,8 +522,11 @@ __device__ __forceinline__ void xg_epilogue_gemm(const GemmArgs& a, const XgTile
       float v[32];
       xg_acc32<PARTS>(t, c0, v);
       if (a.bias && first_split) {
+        float q[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (t.n0 + c0 + j < a.N) v[j] += a.bias[t.n0 + c0 + j];
+        for (int j = 0; j < 32; ++j) q[j] = (t.n0 + c0 + j < a.N) ? __ldg(a.bias + t.n0 + c0 + j) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += q[j];
       }
       if (a.splitk > 1) xg_store_chunk<true>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v);
       else xg_store_chunk<false>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v);
@@ -565,18 +568,39 @@ __device__ __forceinline__ void xg_epilogue_linear(const LinearArgs& a, const Xg
       const int c0 = (nchunks == 2 ? (t.warp >> 2) * 64 : 0) + ch * 32;
       float v[32];
       xg_acc32<PARTS>(t, c0, v);
+      // bias, then the per-group bias: 32 consecutive floats each, fetched as eight independent 128-bit loads before the
+      // first use.  (One guarded scalar load per element left 32 dependent L2 round trips per chunk in the persistent
+      // kernel, whose loaders keep L1 cold: its epilogue took 31 k cycles per tile in the clock64 trace.)
+      const int gn0 = t.n0 + c0;
+      const bool full = gn0 + 32 <= a.N;
+      auto add_vec32 = [&](const float* __restrict__ p) {
+        if (full && (((uintptr_t)p) & 15) == 0) {
+          float4 q[8];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int gn = t.n0 + c0 + j;
-        float x = v[j];
-        if (gn < a.N) {
-          if (a.bias) x += a.bias[gn];
-          if (a.gbias && row_ok) x += a.gbias[(size_t)g * a.N + gn];
-          x = apply_act(x, a.act) * rm;
+          for (int i = 0; i < 8; ++i) q[i] = __ldg(reinterpret_cast<const float4*>(p) + i);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { v[4 * i] += q[i].x; v[4 * i + 1] += q[i].y; v[4 * i + 2] += q[i].z; v[4 * i + 3] += q[i].w; }
         } else {
-          x = 0.0f;
+          float q[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) q[j] = (gn0 + j < a.N) ? __ldg(p + j) : 0.0f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += q[j];
         }
-        v[j] = x;
+      };
+      if (a.bias) add_vec32(a.bias + gn0);
+      if (a.gbias && row_ok) add_vec32(a.gbias + (size_t)g * a.N + gn0);
+      // the activation switch is hoisted out of the element loop: inside it the compiler evaluates every branch (tanhf
+      // included) per element -- 28 k cycles per tile for the 4 epilogue warps of the persistent kernel (clock64 trace)
+      if (a.act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (gn0 + j < a.N) ? fmaxf(v[j], 0.0f) * rm : 0.0f;
+      } else if (a.act == ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (gn0 + j < a.N) ? v[j] * rm : 0.0f;
+      } else {        // leaky ReLU / tanh (the refinement head); fully unrolled so that v[] stays in registers
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (gn0 + j < a.N) ? apply_act(v[j], a.act) * rm : 0.0f;
       }
       if (a.Y) xg_store_chunk<false>(t, a.Y, a.ldy, a.M, a.N, t.m0 + (t.warp & 3) * 32, t.n0 + c0, v);
       if (a.gmax) {
