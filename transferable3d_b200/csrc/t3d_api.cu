@@ -86,6 +86,15 @@ static bool xg_use_pp(int K, bool linear = false, bool has_y = true) {
   if (!linear) return K <= 128;
   return ((lin & 1) && !has_y && K <= 128) || ((lin & 2) && K <= 64);
 }
+// A-stationary kernel (xg_as_kernel): K <= 128 and at least four column tiles; for t3d_linear_f32 only the max-only layers
+// (no Y to store: its 4 epilogue warps are the limit when every tile writes 64 KB).  T3D_XG_AS: 0 off, 1 default, 2 every
+// layer with at least two column tiles (measurement).
+static bool xg_use_as(int K, int ntn, bool linear = false, bool has_y = true) {
+  static const int v = [] { const char* e = getenv("T3D_XG_AS"); return e ? atoi(e) : 1; }();
+  if (v == 0 || K > 128) return false;
+  if (v == 2) return ntn >= 2;
+  return ntn >= 4 && !(linear && has_y);
+}
 static int xg_num_sms() {
   static const int n = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
   return n;
@@ -129,7 +138,13 @@ extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ld
       o.bpre = reinterpret_cast<const uint8_t*>(ws);
       o.nkb = (K + 63) / 64;
       xg_presplit_kernel<<<dim3(o.nkb, ntn, 4), 256, 0, S(stream)>>>(W, ldw, 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
-      if (xg_use_pp(K, true, Y != nullptr)) {
+      if (xg_use_as(K, ntn, true, Y != nullptr)) {
+        static int prepared_as = xg_prepare_pp(xg_as_kernel<3, true>) | xg_prepare_pp(xg_as_kernel<1, true>);
+        if (prepared_as != 0) return prepared_as;
+        const int g = ntm < xg_num_sms() ? ntm : xg_num_sms();
+        if (parts == 3) xg_as_kernel<3, true><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(GemmArgs{}, a, o);
+        else xg_as_kernel<1, true><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(GemmArgs{}, a, o);
+      } else if (xg_use_pp(K, true, Y != nullptr)) {
         static int prepared_pp = xg_prepare_pp(xg_pp_kernel<3, true>) | xg_prepare_pp(xg_pp_kernel<1, true>);
         if (prepared_pp != 0) return prepared_pp;
         const int g = ntm * ntn < xg_num_sms() ? ntm * ntn : xg_num_sms();
@@ -651,7 +666,13 @@ extern "C" int t3d_gemm_f32_ws(const float* A, long long sam, long long sak, con
       o.nkb = (K + 63) / 64;
       const int parts = g_f32_engine == 1 ? 3 : 1;
       xg_presplit_kernel<<<dim3(o.nkb, ntn, 4), 256, 0, S(stream)>>>(B, ldb, bk ? 1 : 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
-      if (xg_use_pp(K)) {
+      if (xg_use_as(K, ntn)) {
+        static int prepared_as = xg_prepare_pp(xg_as_kernel<3, false>) | xg_prepare_pp(xg_as_kernel<1, false>);
+        if (prepared_as != 0) return prepared_as;
+        const int g = ntm < xg_num_sms() ? ntm : xg_num_sms();
+        if (parts == 3) xg_as_kernel<3, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o);
+        else xg_as_kernel<1, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o);
+      } else if (xg_use_pp(K)) {
         static int prepared_pp = xg_prepare_pp(xg_pp_kernel<3, false>) | xg_prepare_pp(xg_pp_kernel<1, false>);
         if (prepared_pp != 0) return prepared_pp;
         const int g = ntm * ntn < xg_num_sms() ? ntm * ntn : xg_num_sms();

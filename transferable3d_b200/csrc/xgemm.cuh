@@ -860,6 +860,205 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs g
   __syncthreads();
   if (warp == kXgPPLoaders + 4) tmem_dealloc<512>(tmem_base);
 }
+// ---- A-stationary variant for K <= 128 and several column tiles -----------------------------------------------------------
+// Same roles and shared-memory map as xg_pp_kernel, but a CTA owns ROW tiles: the split images of its A block (at most 4
+// stages) are written once and stay resident while the CTA walks all N / 128 column tiles, streaming only the pre-split B
+// stages through the 4-slot ring.  A is loaded and split once per row tile instead of once per (row, column) tile, and the
+// per-tile skeleton of the one-tile kernel is paid once per row tile.  The next row tile's A values are already in
+// registers while the current one is multiplied; the images are rewritten once the last MMA of the row tile has retired
+// (a_free), which costs a short bubble per row tile.
+template <int PARTS, bool LINEAR>
+__global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs ga, const LinearArgs la, const XgOperands o) {
+  extern __shared__ uint8_t xg_smem[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)xg_smem + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = sbase + kXgPPBars;
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto acc_full = [&](int b) { return bar0 + 8u * (8 + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (10 + b); };
+  const uint32_t a_ready = bar0 + 8u * 13, a_free = bar0 + 8u * 14;
+  const uint32_t tmem_slot = bar0 + 96u;
+  const int ntm = (o.M + kXgBM - 1) / kXgBM, ntn = o.ntn;
+  const int nst = (o.K + kXgBK - 1) / kXgBK;                       // <= 4
+  const uint32_t a_img = sbase, b_img = sbase + 6u * kXgImage;
+  const int my_mt = (ntm - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // row tiles of this CTA
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kXgPPSlots; ++s) { mbar_init(full(s), kXgPPLoaders); mbar_init(empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
+    mbar_init(a_ready, kXgPPLoaders); mbar_init(a_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == kXgPPLoaders + 4) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kXgPPBars + 96);
+
+  if (warp < kXgPPLoaders) {
+    // ------------------------------------------------------------------------------------------------ loaders
+    const int rsub = lane >> 3, c = lane & 7, tid = threadIdx.x;
+    constexpr int RW = 128 / kXgPPLoaders, NI = RW / 4;
+    auto rowof = [&](int i) { return warp * RW + (i >> 1) * 8 + (i & 1) * 2 + (rsub & 1) * 4 + (rsub >> 1); };
+    const long long ld = o.lda, ld2 = 2 * ld, ld6 = 6 * ld;
+    const int kofs = 4 * c;
+    float rA[4][kXgPPVals];
+    auto load_a = [&](int mt) {                                     // all stages of row tile mt -> registers
+      const int row0 = mt * kXgBM, row = row0 + rowof(0);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        if (it < nst) {
+          const int k0 = it * kXgBK;
+          const float* q = o.A + (long long)row * ld + k0 + kofs;
+          if (o.vecA && row0 + warp * RW + RW <= o.M && k0 + kXgBK <= o.K) {
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+              const float4 v = __ldg(reinterpret_cast<const float4*>(q));
+              rA[it][4 * i] = v.x; rA[it][4 * i + 1] = v.y; rA[it][4 * i + 2] = v.z; rA[it][4 * i + 3] = v.w;
+              q += (i & 1) ? ld6 : ld2;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+              const int ro = (i >> 1) * 8 + (i & 1) * 2;
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                rA[it][4 * i + e] = (row + ro < o.M && k0 + kofs + e < o.K) ? __ldg(q + (long long)ro * ld + e) : 0.0f;
+            }
+          }
+        }
+      }
+    };
+    auto store_a = [&]() {                                          // registers -> resident images, stage it in slot it
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        if (it < nst) {
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            const uint32_t off = sw128_offset((uint32_t)rowof(i), (uint32_t)(4 * (it & 1) + (c >> 1))) + (uint32_t)(c & 1) * 8u;
+            const float* r = &rA[it][4 * i];
+            if (PARTS == 1) {
+              st_shared_v2(xg_pp_block(a_img, 0, it) + off, xg_pack_rn(r[0], r[1]), xg_pack_rn(r[2], r[3]));
+            } else {
+              uint32_t h[4], m[4], l[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) xg_split(r[e], h[e], m[e], l[e]);
+              st_shared_v2(xg_pp_block(a_img, 0, it) + off, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]));
+              st_shared_v2(xg_pp_block(a_img, 1, it) + off, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]));
+              st_shared_v2(xg_pp_block(a_img, 2, it) + off, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]));
+            }
+          }
+        }
+      }
+    };
+    // B stream: work item g = ((row tile, column tile), stage) in order; slot g & 3
+    const int per_mt = ntn * nst, total = my_mt * per_mt;
+    int c_it = 0, c_nt = 0;
+    auto copy_b = [&](int g) {
+      const int it = c_it, nt = c_nt, s = g & 3;
+      if (++c_it == nst) { c_it = 0; if (++c_nt == ntn) c_nt = 0; }
+      mbar_wait_backoff(empty(s), ((g >> 2) & 1) ^ 1);
+      const uint8_t* blk = o.bpre + ((size_t)nt * o.nkb + (it >> 1)) * kXgPreBlockBytes;
+#pragma unroll
+      for (int j = 0; j < PARTS * 512 / (kXgPPLoaders * 32); ++j) {
+        const int id = tid + kXgPPLoaders * 32 * j, part = id >> 9, rem = id & 511;
+        const uint32_t row = (uint32_t)(rem >> 2), ch = (uint32_t)(rem & 3);
+        cp_async16(xg_pp_block(b_img, part, s) + sw128_offset(row, 4u * (s & 1) + ch),
+                   blk + (size_t)part * kXgImage + sw128_offset(row, 4u * (it & 1) + ch));
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (my_mt > 0) {
+      load_a(blockIdx.x);
+#pragma unroll
+      for (int j = 0; j < kXgPPBAhead; ++j) {
+        if (j < total) copy_b(j);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      int g = 0;
+      for (int i = 0; i < my_mt; ++i) {
+        mbar_wait_backoff(a_free, (i & 1) ^ 1);                     // every MMA of the previous row tile has retired
+        store_a();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready);
+        if (i + 1 < my_mt) load_a((int)blockIdx.x + (i + 1) * (int)gridDim.x);      // in flight during this row tile's B stream
+        for (int q = 0; q < per_mt; ++q, ++g) {
+          if (g + kXgPPBAhead < total) copy_b(g + kXgPPBAhead);
+          else asm volatile("cp.async.commit_group;" ::: "memory");
+          asm volatile("cp.async.wait_group %0;" ::"n"(kXgPPBAhead) : "memory");
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full(g & 3));
+        }
+      }
+    }
+  } else if (warp == kXgPPLoaders + 4) {
+    // ------------------------------------------------------------------------------------------------ MMA issue
+    int g = 0, lt = 0;
+    for (int i = 0; i < my_mt; ++i) {
+      mbar_wait_w(a_ready, i & 1);
+      tc_fence_after();
+      for (int nt = 0; nt < ntn; ++nt, ++lt) {
+        const int n0 = nt * kXgBN, ab = lt & 1;
+        const int ncols = min(kXgBN, ((o.N - n0) + 15) & ~15);
+        const uint32_t idesc = make_idesc_bf16(128, ncols);
+        const uint32_t d_main = tmem_base + (uint32_t)ab * 256u, d_small = d_main + 128u;
+        mbar_wait_w(acc_empty(ab), ((lt >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int it = 0; it < nst; ++it, ++g) {
+          const int s = g & 3;
+          mbar_wait_w(full(s), (g >> 2) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t offa = (uint32_t)(2 * (it & 1) + ks) * 32u, offb = (uint32_t)(2 * (s & 1) + ks) * 32u;
+            const uint64_t a1 = make_sdesc_k128(xg_pp_block(a_img, 0, it) + offa), a2 = make_sdesc_k128(xg_pp_block(a_img, 1, it) + offa),
+                           a3 = make_sdesc_k128(xg_pp_block(a_img, 2, it) + offa);
+            const uint64_t b1 = make_sdesc_k128(xg_pp_block(b_img, 0, s) + offb), b2 = make_sdesc_k128(xg_pp_block(b_img, 1, s) + offb),
+                           b3 = make_sdesc_k128(xg_pp_block(b_img, 2, s) + offb);
+            const uint32_t accum = (it | ks) != 0;
+            if (PARTS == 3) {
+              umma_bf16_w(d_small, a3, b1, idesc, accum);
+              umma_bf16_w(d_small, a1, b3, idesc, 1);
+              umma_bf16_w(d_small, a2, b2, idesc, 1);
+              umma_bf16_w(d_small, a2, b1, idesc, 1);
+              umma_bf16_w(d_small, a1, b2, idesc, 1);
+            }
+            umma_bf16_w(d_main, a1, b1, idesc, accum);
+          }
+          umma_commit_w(empty(s));
+        }
+        umma_commit_w(acc_full(ab));
+      }
+      umma_commit_w(a_free);                                        // the resident A images may be rewritten
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------------ epilogue (4 warps)
+    int lt = 0;
+    for (int i = 0; i < my_mt; ++i) {
+      const int mt = (int)blockIdx.x + i * (int)gridDim.x;
+      for (int nt = 0; nt < ntn; ++nt, ++lt) {
+        const int ab = lt & 1;
+        XgTile t;
+        t.sbase = sbase + kXgPPPatch; t.tmem_base = tmem_base + (uint32_t)ab * 256u;
+        t.m0 = mt * kXgBM; t.n0 = nt * kXgBN; t.warp = warp - kXgPPLoaders; t.lane = lane;
+        mbar_wait_backoff(acc_full(ab), (lt >> 1) & 1);
+        tc_fence_after();
+        if (LINEAR) xg_epilogue_linear<PARTS>(la, t, 4);
+        else xg_epilogue_gemm<PARTS>(ga, t, 4, true);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(ab));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kXgPPLoaders + 4) tmem_dealloc<512>(tmem_base);
+}
 #endif
 
 inline bool xg_aligned16(const void* p, long long ld) { return (((uintptr_t)p & 15) == 0) && (ld % 4 == 0); }
