@@ -1,0 +1,104 @@
+"""-m "not gpu": transferable3d_b200.tf_checkpoint -- TensorFlow V2 checkpoint reader without TensorFlow.
+Pinned by: the CRC-32C known-answer vector, the byte layout of a hand-assembled BundleEntryProto and footer, and a
+round trip through the writer (multi-block index with prefix-compressed keys, several dtypes, scalars).  No
+TensorFlow-written file is available here: the on-disk format is restated from the published sources, see the module
+docstring."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from transferable3d_b200 import tf_checkpoint as ck
+
+
+def test_crc32c_known_answers():
+    assert ck.crc32c(b'123456789') == 0xE3069283                    # the standard CRC-32C check value
+    assert ck.crc32c(b'') == 0
+    assert ck.crc32c(bytes(32)) == 0x8A9136AA                       # 32 zero bytes (RFC 3720 B.4)
+    c = ck.crc32c(b'123456789')
+    assert ck.masked_crc(b'123456789') == ((((c >> 15) | (c << 17)) + 0xa282ead8) & 0xffffffff)
+
+
+def test_entry_and_footer_byte_layout(tmp_path):
+    v = {'w': np.arange(6, dtype=np.float32).reshape(2, 3)}
+    prefix = os.path.join(str(tmp_path), 'm.ckpt')
+    ck.save_checkpoint(prefix, v)
+    idx = open(prefix + '.index', 'rb').read()
+    assert struct.unpack('<Q', idx[-8:])[0] == 0xdb4775248b80fb57 and len(idx) >= 48
+    # BundleEntryProto of 'w': dtype DT_FLOAT (08 01), shape {dim{size 2} dim{size 3}} (12 08 12 02 08 02 12 02 08 03),
+    # offset 0 (20 00), size 24 (28 18), crc32c fixed32 (35 ....)
+    want = bytes([0x08, 0x01, 0x12, 0x08, 0x12, 0x02, 0x08, 0x02, 0x12, 0x02, 0x08, 0x03, 0x20, 0x00, 0x28, 0x18, 0x35])
+    assert want in idx
+    raw = open(prefix + '.data-00000-of-00001', 'rb').read()
+    assert raw == v['w'].tobytes()
+    header, entries = ck.read_index(prefix)
+    assert header == dict(num_shards=1, endianness=0)
+    assert entries['w']['shape'] == [2, 3] and entries['w']['crc32c'] == ck.masked_crc(raw)
+
+
+def test_round_trip_many_variables(tmp_path):
+    rng = np.random.RandomState(0)
+    v = {}
+    for net in ('class_agnostic/inst_seg', 'class_agnostic/tnet', 'class_agnostic/box_est', 'class_dependent/box_refine'):
+        for i in range(1, 12):
+            cin, cout = rng.randint(3, 40), rng.randint(3, 40)
+            v['%s/conv%d/weights' % (net, i)] = rng.randn(1, 1, cin, cout).astype(np.float32)
+            v['%s/conv%d/biases' % (net, i)] = rng.randn(cout).astype(np.float32)
+            for s in ('beta', 'gamma', 'moving_mean', 'moving_variance'):
+                v['%s/conv%d/bn/%s' % (net, i, s)] = rng.randn(cout).astype(np.float32)
+    v['global_step'] = np.array(1234, dtype=np.int64)               # scalar
+    v['flags'] = np.array([True, False, True])
+    v['half'] = rng.randn(5).astype(np.float16)
+    v['beta1_power'] = np.array(0.9, dtype=np.float32)
+    v['class_agnostic/tnet/conv1/weights/Adam'] = np.zeros((1, 1, 3, 4), np.float32)
+    prefix = os.path.join(str(tmp_path), 'sub', 'model.ckpt')
+    ck.save_checkpoint(prefix, v, block_size=512)                   # many data blocks
+    back = ck.load_checkpoint(prefix, verify_data=True)
+    assert set(back) == set(v)
+    for k in v:
+        assert back[k].dtype == np.asarray(v[k]).dtype and back[k].shape == np.asarray(v[k]).shape and np.array_equal(back[k], v[k]), k
+    names = ck.list_variables(prefix)
+    assert [n for n, _ in names] == sorted(v) and dict(names)['global_step'] == []
+    some = ck.load_checkpoint(prefix, names=['flags', 'half'])
+    assert set(some) == {'flags', 'half'}
+    with pytest.raises(KeyError):
+        ck.load_checkpoint(prefix, names=['nope'])
+    # scope remap of the reference's restore maps; optimizer slots dropped
+    r = ck.remap_scope({k: a for k, a in back.items() if not k.startswith('class_dependent')}, 'D_boxpc_branch/',
+                       only=lambda n: 'tnet' in n)
+    assert all(k.startswith('D_boxpc_branch/class_agnostic/tnet') for k in r) and not any(k.endswith('/Adam') for k in r)
+    assert 'D_boxpc_branch/class_agnostic/tnet/conv1/weights' in r
+
+
+def test_corruption_is_detected(tmp_path):
+    prefix = os.path.join(str(tmp_path), 'm.ckpt')
+    ck.save_checkpoint(prefix, {'a': np.arange(10, dtype=np.float32), 'b': np.ones((3, 3), np.float32)})
+    idx = bytearray(open(prefix + '.index', 'rb').read())
+    bad = bytearray(idx)
+    bad[-1] ^= 0xff                                                 # magic
+    open(prefix + '.index', 'wb').write(bytes(bad))
+    with pytest.raises(ValueError):
+        ck.load_checkpoint(prefix)
+    bad = bytearray(idx)
+    bad[3] ^= 0x01                                                  # a byte inside the first data block
+    open(prefix + '.index', 'wb').write(bytes(bad))
+    with pytest.raises(ValueError):
+        ck.load_checkpoint(prefix)
+    open(prefix + '.index', 'wb').write(bytes(idx))
+    data = bytearray(open(prefix + '.data-00000-of-00001', 'rb').read())
+    data[5] ^= 0x10
+    open(prefix + '.data-00000-of-00001', 'wb').write(bytes(data))
+    ck.load_checkpoint(prefix)                                      # data checksums are opt-in (pure-python CRC is slow)
+    with pytest.raises(ValueError):
+        ck.load_checkpoint(prefix, verify_data=True)
+
+
+def test_checkpoint_feeds_the_variable_store(tmp_path):
+    """weights -> checkpoint -> load_checkpoint gives back the dict runtime.VariableStore / the oracle take."""
+    from transferable3d_b200 import weights
+    v = weights.make_weights_boxpc()
+    prefix = os.path.join(str(tmp_path), 'boxpc.ckpt')
+    ck.save_checkpoint(prefix, {k: np.asarray(a) for k, a in v.items()})
+    back = ck.load_checkpoint(prefix)
+    assert set(back) == set(v) and all(np.array_equal(back[k], np.asarray(v[k])) for k in v)
