@@ -134,3 +134,22 @@ def test_main_batch_end_to_end(tmp_path):
         gt_all.setdefault(ds.idx_l[i], []).append((ds.cls_type_l[i], ds.box3d_l[i]))
     rec, prec, ap = ed.eval_det(pred_all, gt_all, 0.25)
     assert set(ap) == set(ds.cls_type_l) and all(0.0 <= v <= 1.0 for v in ap.values())
+
+
+def test_checkpoint_to_session(tmp_path):
+    """tf_checkpoint.load_checkpoint -> get_model / sess.run: the loaded dict drives the model exactly like the dict it was
+    written from (the path saver.restore takes in the reference, test_semisup.py:158-159)."""
+    from transferable3d_b200 import tf_checkpoint as ck, test_semisup as ts, weights, synth, config, runtime as rt
+    variables, _ = weights.standard_model_F()
+    prefix = os.path.join(str(tmp_path), 'model.ckpt')
+    ck.save_checkpoint(prefix, {k: np.asarray(v) for k, v in variables.items()})
+    loaded = ck.load_checkpoint(prefix)
+    b = synth.make_batch(4, 1024, 6, seed=2)
+    FLAGS = config.cfg()
+    outs = []
+    for v in (variables, loaded):
+        with rt.precision('fp32'):
+            sess, ops = ts.get_model(4, 1024, 6, FLAGS, v, cuda_graph=False)
+            outs.append(sess.run([ops['logits'], ops['end_points']['F2_center']],
+                                 {ops['pc_pl']: b['pc'], ops['one_hot_vec_pl']: b['one_hot'], ops['is_training_pl']: False}))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
