@@ -164,6 +164,33 @@ int t3d_pack_seg2(const float* W6p /* [64,512] */, const float* W7 /* [512,256] 
 int t3d_seg_stage2_bf16(const void* point_feat /* bf16 [B*N,64] */, const float* gbias, const void* arena,
                         float* logits, int B, int N, t3d_stream_t stream);
 
+/* ---- split-precision ("f16x2") variants of the same fused chains: fp32-accurate on the tensor cores --------------
+ * Same reference functions, arguments and outputs as t3d_chain_max_bf16 / t3d_seg_stage2_bf16.  Every operand is a pair
+ * of fp16 images x = hi + lo (22+ significant bits); a layer issues three tcgen05 products (hi.lo, lo.hi, hi.hi) into one
+ * fp32 accumulator (csrc/chain_x2.cuh, csrc/seg_stage2_x2.cuh).  Tile = 128 points for every kind.
+ * wscale (HOST array of powers of two, one per tensor-core layer: hidden..., final) scales the weights into the fp16
+ * normal range; the arena stores the inverse.  emit (seg1) = per 128-point tile [hi image 16 KB][lo image 16 KB] of
+ * conv3's output (32 KB x B x ceil(N/128)); gbias of the stage-2 call must be multiplied by 16 (the activation scale:
+ * pass 16*W6[64:], 16*b6 to t3d_linear_f32).
+ * t3d_set_x2_debias: per-accumulation-step correction of the tensor core's round-toward-zero accumulation folded into
+ * the packed epilogue scales (applies to arenas packed afterwards; default 2.1e-8, 0 = off). */
+size_t t3d_chain_arena_bytes_x2(int kind);
+int t3d_pack_chain_x2(int kind, const float* const* W /* host array of device ptrs */,
+                      const float* const* bias /* host array of device ptrs */, const float* wscale /* host */,
+                      void* arena, t3d_stream_t stream);
+int t3d_chain_max_x2(int kind, const float* pc, int B, int N, int C, const float* center, const int* idx,
+                     int idx_stride, const int* count, const void* tiles, const int* num_tiles,
+                     const float* box_center, const float* box_dims, const float* box_orient,
+                     const void* arena, float* out, void* emit, t3d_stream_t stream);
+size_t t3d_seg2_arena_bytes_x2(void);
+int t3d_pack_seg2_x2(const float* W6p, const float* W7, const float* W8, const float* W9, const float* b7, const float* b8,
+                     const float* b9, const float* W10, const float* b10, const float* wscale /* host[4]: conv6' 7 8 9 */,
+                     void* arena, t3d_stream_t stream);
+int t3d_seg_stage2_x2(const void* point_feat, const float* gbias /* x16 */, const void* arena, float* logits, int B, int N,
+                      t3d_stream_t stream);
+int t3d_set_x2_debias(float per_step);
+float t3d_get_x2_debias(void);
+
 /* ---- training-step kernels (fp32, CUDA cores) ---------------------------------------------------------
  * The TF ops behind train_boxpc.train (train_boxpc.py:219-300) and the trainable part of train_semisup_adv.train:
  * conv2d / fully_connected forward, dgrad and wgrad as one strided GEMM, training-mode batch norm

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import model_F_setup, oracle_model_F, assert_close, err_stats
+from util import model_F_setup, oracle_model_F, oracle_cfg3_from_logits, assert_close, err_stats
 
 pytestmark = pytest.mark.gpu
 
@@ -229,23 +229,9 @@ def test_cfg3_pipeline_fp32_vs_oracle(built_lib):
         ep = fpn.get_model(pc_c.to(DEV), oh_c.to(DEV), False)
     scale_close(ep['mask_logits'], ologits, 1e-4, 'cfg3 logits')
     # continue the oracle from the GPU logits so the masks are identical, then everything must agree
-    with torch.no_grad():
-        glog = ep['mask_logits'].cpu()
-        obj, omean, oep = omu.point_cloud_masking(pc_c, glog, oep, rng_mode='philox', seed=5)
-        assert np.array_equal(ep['object_pc_indices'].cpu().numpy(), oep['object_pc_indices'])
-        with vs.variable_scope('tnet'):
-            delta, _ = omu.get_center_regression_net(obj, oh_c, False, None, oep, vs)
-        s1 = delta + omean
-        from oracle.tf_layers import conv2d, fully_connected, max_pool_points
-        with vs.variable_scope('box_est'):
-            net = obj - delta.unsqueeze(1)
-            for nm, c in (('conv-reg1', 128), ('conv-reg2', 128), ('conv-reg3', 256), ('conv-reg4', 512)):
-                net = conv2d(net, c, [1, 1], vs, nm, True, False)
-            net = torch.cat([max_pool_points(net), oh_c], dim=1)
-            net = fully_connected(net, 512, vs, 'fc1', True, False)
-            net = fully_connected(net, 256, vs, 'fc2', True, False)
-            out = fully_connected(net, 67, vs, 'fc3', activation_fn=None)
-        oep = omu.parse_output_to_tensors(out, oep, 12, MEAN_DIMS_ARR)
+    oep = oracle_cfg3_from_logits(variables, b['pc'], b['one_hot'], ep['mask_logits'].cpu(), seed=5)
+    assert np.array_equal(ep['object_pc_indices'].cpu().numpy(), oep['object_pc_indices'])
+    s1 = oep['stage1_center']
     scale_close(ep['stage1_center'], s1, 2e-4, 'cfg3 stage1_center')
     scale_close(ep['center'], oep['center_boxnet'] + s1, 2e-4, 'cfg3 center')
     scale_close(ep['size_residuals'], oep['size_residuals'], 2e-4, 'cfg3 size residuals')

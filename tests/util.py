@@ -14,15 +14,77 @@ def model_F_setup(B, N=2048, seed=1234, margin=True):
     return variables, batch, config.cfg(), info
 
 
-def oracle_model_F(variables, batch, FLAGS, dtype=torch.float32, literal=True):
+def oracle_model_F(variables, batch, FLAGS, dtype=torch.float32, literal=True, oracle_mask=None):
+    """Oracle run of the test graph.  oracle_mask (B,N) 0/1: continue the oracle from a GIVEN mask (the reference's own
+    oracle_mask input, semisup_v1_sunrgbd.py:161-162) -- used to compare everything downstream of the strict logit
+    compare on identical masks; the returned logits are then the stacked mask, the seg logits stay in
+    ep['_oracle_seg_logits'] when computed separately."""
     from oracle.tf_layers import VarStore
     from oracle import test_semisup
     vs = VarStore(variables, dtype=dtype)
     vs.literal = literal
+    om = None if oracle_mask is None else torch.as_tensor(np.asarray(oracle_mask)).to(dtype)
     with torch.no_grad():
         logits, ep = test_semisup.run_graph(vs, FLAGS, torch.as_tensor(batch['pc']).to(dtype),
-                                            torch.as_tensor(batch['one_hot']).to(dtype))
+                                            torch.as_tensor(batch['one_hot']).to(dtype), oracle_mask=om)
     return logits, ep
+
+
+def oracle_seg_logits(variables, pc, one_hot=None, scope='class_agnostic/inst_seg', chunk=64, dtype=torch.float32):
+    """Oracle mask logits of many frustums in chunks (folded conv6: algebraically identical, a third of the memory)."""
+    from oracle.tf_layers import VarStore
+    from oracle import semisup_models as osm
+    vs = VarStore(variables, dtype=dtype)
+    vs.literal = False
+    out = []
+    with torch.no_grad():
+        for i in range(0, pc.shape[0], chunk):
+            oh = None if one_hot is None else torch.as_tensor(one_hot[i:i + chunk]).to(dtype)
+            parts = scope.split('/')
+            ctx = [vs.variable_scope(p) for p in parts[:-1]]
+            for c in ctx:
+                c.__enter__()
+            try:
+                out.append(osm.v1_inst_seg(torch.as_tensor(pc[i:i + chunk]).to(dtype), None, oh, {}, False, vs, scope=parts[-1]))
+            finally:
+                for c in reversed(ctx):
+                    c.__exit__(None, None, None)
+    return torch.cat(out)
+
+
+def oracle_cfg3_from_logits(variables, pc, one_hot, logits, seed, dtype=torch.float32):
+    """F-PointNet v1 pipeline downstream of GIVEN mask logits (models/model_util.py:241-325, box-estimation net of
+    semisup_models.py:224-261 on the 512 gathered points): the oracle continued from the GPU's own logits, so that masks
+    and resampled indices are identical and every later output is comparable."""
+    from oracle.tf_layers import VarStore, conv2d, fully_connected, max_pool_points
+    from oracle import model_util as omu
+    from transferable3d_b200.constants import MEAN_DIMS_ARR
+    vs = VarStore(variables, dtype=dtype)
+    pc_c, oh_c = torch.as_tensor(pc).to(dtype), torch.as_tensor(one_hot).to(dtype)
+    with torch.no_grad():
+        oep = {}
+        obj, omean, oep = omu.point_cloud_masking(pc_c, torch.as_tensor(logits).to(dtype), oep, rng_mode='philox', seed=seed)
+        with vs.variable_scope('tnet'):
+            delta, _ = omu.get_center_regression_net(obj, oh_c, False, None, oep, vs)
+        s1 = delta + omean
+        with vs.variable_scope('box_est'):
+            net = obj - delta.unsqueeze(1)
+            for nm, c in (('conv-reg1', 128), ('conv-reg2', 128), ('conv-reg3', 256), ('conv-reg4', 512)):
+                net = conv2d(net, c, [1, 1], vs, nm, True, False)
+            net = torch.cat([max_pool_points(net), oh_c], dim=1)
+            net = fully_connected(net, 512, vs, 'fc1', True, False)
+            net = fully_connected(net, 256, vs, 'fc2', True, False)
+            out = fully_connected(net, 67, vs, 'fc3', activation_fn=None)
+        oep = omu.parse_output_to_tensors(out, oep, 12, MEAN_DIMS_ARR)
+    oep['stage1_center'] = s1
+    oep['center'] = oep['center_boxnet'] + s1
+    return oep
+
+
+def frac_within(a, b, rel, abs_):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float((np.abs(a - b) <= abs_ + rel * np.abs(b)).mean())
 
 
 def err_stats(a, b):

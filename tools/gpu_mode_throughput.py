@@ -1,4 +1,4 @@
-"""Not a test: frustums/s of the cfg3 pipeline and of model F (+ BoxPC refine) in both precision modes, inputs resident.
+"""Not a test: frustums/s of the cfg3 pipeline and of model F (+ BoxPC refine) in every precision mode, inputs resident.
 Run under gpurun."""
 import os
 import sys
@@ -27,7 +27,7 @@ def timed(fn, n=3):
 
 def main():
     dev = 'cuda:0'
-    B = 1024
+    B = int(os.environ.get('T3D_TP_B', '1024'))
     b = synth.make_batch(64, 2048, 6, seed=3)
     pc = torch.as_tensor(np.tile(b['pc'], (B // 64, 1, 1))).to(dev)
     oh = torch.as_tensor(np.tile(b['one_hot'], (B // 64, 1))).to(dev)
@@ -37,7 +37,7 @@ def main():
                               ('model F + 1 BoxPC refine', weights.standard_model_F, lambda: ts.build_graph(FLAGS, pc, oh))):
         v, _ = vars_fn()
         rt.set_default_store(rt.VariableStore(v, dev))
-        for mode in ('bf16', 'fp32'):
+        for mode in ('bf16', 'f16x2', 'fp32'):
             with rt.precision(mode), torch.no_grad():
                 ms = timed(fn)
             print(json.dumps({'graph': name, 'mode': mode, 'frustums': B, 'ms': ms, 'frustums_per_s': B / ms * 1e3}), flush=True)

@@ -1,5 +1,5 @@
 """Run under torchrun on >= 2 GPUs (not collected by pytest):
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_train.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_train.py
 Checks the data-parallel training steps (cfg4 BoxPC, cfg5 semi-supervised): every rank runs forward/backward on its own
 micro-batch, ONE NCCL all-reduce of the flat gradient arena, fused Adam with 1/world scaling.  After the step the
 parameters are identical on all ranks and equal to a single-process Adam update with the mean of the per-rank gradients."""

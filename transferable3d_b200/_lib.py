@@ -119,6 +119,14 @@ SIGNATURES = {
     't3d_seg2_arena_bytes': (_c.c_size_t, []),
     't3d_pack_seg2': (_I, [_P] * 10 + [_P]),
     't3d_seg_stage2_bf16': (_I, [_P, _P, _P, _P, _I, _I, _P]),
+    't3d_chain_arena_bytes_x2': (_c.c_size_t, [_I]),
+    't3d_pack_chain_x2': (_I, [_I, _c.POINTER(_P), _c.POINTER(_P), _c.POINTER(_F), _P, _P]),
+    't3d_chain_max_x2': (_I, [_I, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    't3d_seg2_arena_bytes_x2': (_c.c_size_t, []),
+    't3d_pack_seg2_x2': (_I, [_P] * 9 + [_c.POINTER(_F), _P, _P]),
+    't3d_seg_stage2_x2': (_I, [_P, _P, _P, _P, _I, _I, _P]),
+    't3d_set_x2_debias': (_I, [_F]),
+    't3d_get_x2_debias': (_F, []),
     't3d_set_trace_buffer': (_I, [_P]),
     't3d_gemm_f32': (_I, [_P, _L, _L, _P, _L, _L, _P, _I, _I, _I, _I, _I, _P, _P]),
     't3d_gemm_ws_bytes': (_c.c_size_t, [_I, _I]),

@@ -124,6 +124,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
 }
+// 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
 // same commit, delivered to the barrier at this CTA-relative offset in every CTA of cta_mask
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -226,6 +235,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// same with A = B = fp16 (format code 0): the operands of the f16x2 split-precision kernels
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // byte offset of the 16-byte chunk j (8 bf16 along K) of row r inside a [rows x 64] K-major SW128 block
 __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t j) {
   return r * 128u + ((j ^ (r & 7u)) << 4);
@@ -235,6 +249,15 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {   // ma
   uint32_t r;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+// f16x2 split of two fp32 values with ReLU: hi = x truncated to 11 significant bits (exactly an fp16 when x is in the fp16
+// normal range), lo = fp16(x - hi) >= 0, so hi + lo carries 22+ bits of x.  Negative x gives hi = lo = 0 (both converts clamp).
+// Two LOP + two FADD on the ALU / FMA pipes and two F2FP on the conversion pipe per pair.
+__device__ __forceinline__ void split_f16x2_relu(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+  const float h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(h1), "f"(h0));
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;

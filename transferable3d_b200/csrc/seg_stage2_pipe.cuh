@@ -1,6 +1,14 @@
-// Instance-segmentation stage 2, software-pipelined (v3): same arithmetic, arena and interface as
-// seg_stage2_kernel (seg_stage2.cuh; reference semisup_models.py:107-135 in eval mode, BN folded,
-// conv6's global half folded into gbias), but TWO 128-point tiles are in flight per CTA:
+// Instance-segmentation stage 2 on tcgen05/TMEM: point_feat(64) -> conv6'(512) -> conv7(256) -> conv8(128) -> conv9(128)
+// -> conv10(2) = mask logits (sunrgbd_detection/semisup_models.py:107-135, eval mode, BN folded).
+//
+// The reference tiles the 1024(+10)-wide global feature to every point and runs conv6 on the 1088-wide concat; here the
+// global half of conv6 is folded into a per-frustum bias gbias[b] = b6 + [gfeat_b, one_hot_b] . W6[64:], so conv6' is a
+// K=64 GEMM.  Per 128-point tile (points on the UMMA M dimension, channels on N) conv6' is produced in 4
+// blocks of 128 channels; each block's epilogue (+gbias, ReLU, bf16) becomes a K=128 slice of conv7's A operand, so the
+// 512-wide activation never exists as a whole; conv7 accumulates its 256 outputs in TMEM across the 4 slices; conv10
+// (128 -> 2) is evaluated on CUDA cores from the fp32 conv9 epilogue registers.
+//
+// Software-pipelined: TWO 128-point tiles are in flight per CTA:
 //
 //   phase 1 of tile i    conv6' blocks (K=64) -> e6 (+gbias, ReLU, bf16) -> conv7 accumulation (K=512 in 4 slices)
 //   phase 2 of tile i-1  e7 -> conv8 -> e8 -> conv9 -> e9 + conv10 (fp32, CUDA cores) -> logits
@@ -16,16 +24,29 @@
 // accumulators are released to the MMA thread as soon as the epilogue has them in registers.
 // Weights: the 26 chunk images of the arena stream through the ring in the issue order below.
 // Each CTA of the 2-CTA cluster fetches half of every chunk and multicasts it.
-// (A cta_group::2 CTA-pair variant of this kernel -- weights split between the two shared memories -- was built and
-// measured at commit d57f045: parity-green, 7.9 ms against 6.9 ms for this one; see DESIGN.md.)
+// (Measured and dropped, see DESIGN.md: a one-tile-at-a-time version, 6.95 ms against 5.33 ms per 8192 frustums; a
+// cta_group::2 CTA-pair variant with the weights split between the two shared memories, 7.9 ms against 6.9 ms.)
 // The MMA warp issues warp-convergently (common.cuh): with 64-cycle N=128 instructions the issue path, not the tensor
 // pipe, was the bottleneck of the first version of this kernel.
 #pragma once
 #include "common.cuh"
 #include "chain_max.cuh"
-#include "seg_stage2.cuh"
 
 namespace t3d {
+
+constexpr int kSeg2Chunks = 26;   // per tile: 4 (W6') + 16 (W7) + 4 (W8) + 2 (W9), consumption order in t3d_pack_seg2
+// arena = [26 chunk images][b7 256][b8 128][b9 128][W10 128x2][b10 2] fp32
+constexpr int kSeg2Floats = 256 + 128 + 128 + 256 + 2;
+constexpr size_t kSeg2ArenaBytes = (size_t)kSeg2Chunks * kChunkBytes + sizeof(float) * kSeg2Floats;
+
+struct Seg2Args {
+  const __nv_bfloat16* point_feat;   // stage-1 emit: per 256-point tile a [256 x 64] bf16 K-major SW128 image
+  const float* gbias;                // [B, 512] fp32 per-frustum conv6 bias (global half + b6, BN folded)
+  const uint8_t* arena;
+  float* logits;                     // [B, N, 2]
+  int B, N;
+  unsigned long long* trace;
+};
 
 struct Seg2PSmem {
   static constexpr int STAGES = 6;

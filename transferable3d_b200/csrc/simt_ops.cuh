@@ -496,6 +496,8 @@ __global__ void box3d_corners_all_kernel(const float* center, const float* headi
 // ----------------------------------------------------------------------------- weight packing for tcgen05
 // chunk image: [128 rows x 64 K] bf16, K-major SWIZZLE_128B; row r = output channel row0+r, K = k0..k0+63 of
 // W[K_total, Nout] (row-major, TF layout).  Rows >= nrows and k >= K_total are zero.
-struct PackDesc { const float* W; int ldw; int k_total; int k0; int row0; int nrows; };
+// one 16 KB weight chunk image: rows [row0, row0+nrows) x K [k0, k0+64) of W[k_total, ldw]; part 0 = bf16,
+// 1 / 2 = fp16 hi / lo image of W * scale (f16x2 kernels)
+struct PackDesc { const float* W; int ldw; int k_total; int k0; int row0; int nrows; int part; float scale; };
 
 }  // namespace t3d

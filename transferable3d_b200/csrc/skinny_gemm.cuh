@@ -11,6 +11,7 @@
 namespace t3d {
 
 constexpr int kSkinnyMax = 16;
+constexpr size_t kSkinnySmemMax = 48 * 1024;   // dynamic shared memory without an opt-in; larger problems take the tiled GEMMs
 
 // (a) C[M,N] = A[M,K] . B[K,N] (+ bias), K <= 16, N % 4 == 0, A row-major (lda), B row-major (ldb), C row-major (ldc).
 //     thread = 4 consecutive columns of one row; a block covers 256 * 4 / N rows per step.

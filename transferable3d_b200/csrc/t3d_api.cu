@@ -1,11 +1,13 @@
 // extern "C" entry points of libt3d_b200.so (declared in include/t3d_b200.h).
+#include <cmath>
 #include <cstdlib>
 #include "../../include/t3d_b200.h"
 #include "common.cuh"
 #include "simt_ops.cuh"
 #include "chain_max.cuh"
-#include "seg_stage2.cuh"
 #include "seg_stage2_pipe.cuh"
+#include "chain_x2.cuh"
+#include "seg_stage2_x2.cuh"
 #include "train_ops.cuh"
 #include "loss_ops.cuh"
 #include "box_ops.cuh"
@@ -74,30 +76,27 @@ static inline bool xg_pre_ok(int M, int N, int K, const void* ws, size_t ws_byte
 // Persistent forward / dgrad kernel (xg_pp_kernel) for K <= 128: with 4 stages or fewer per tile the per-CTA overheads and
 // the epilogue dominate the one-tile kernel (measured: 98 / 117 / 140 against 86 / 103 / 121 TFLOP/s on the 128 -> 128 /
 // 256 / 1024 forward layers); for longer K the two co-resident one-tile CTAs win (176 against 158 on dgrad 256 <- 512).
-// T3D_XG_PP=0 / 1 in the environment forces one or the other.
-// t3d_linear_f32: with an output to store, the epilogue is too heavy for the persistent kernel's 4 epilogue warps (the
-// fp32-mode pipeline dropped from 43.6 k to 24.8 k frustums/s with it everywhere; restricted to the max-only layers -- conv5 +
-// max-pool, no Y to store -- it still lost: 32.7 k against 45.9 k; with the K <= 64 layers added 26.9 k).  Off by default;
-// T3D_XG_PP_LINEAR=1|3 switches those two sets on for measurement.
-static bool xg_use_pp(int K, bool linear = false, bool has_y = true) {
-  static const int v = [] { const char* e = getenv("T3D_XG_PP"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
-  static const int lin = [] { const char* e = getenv("T3D_XG_PP_LINEAR"); return e ? atoi(e) : 0; }();     // bit 0: max-only layers, bit 1: K <= 64
-  if (v >= 0) return v != 0;
-  if (!linear) return K <= 128;
-  return ((lin & 1) && !has_y && K <= 128) || ((lin & 2) && K <= 64);
-}
+// t3d_linear_f32 never uses it: with an output to store its 4 epilogue warps are the limit (fp32-mode pipeline 43.6 k ->
+// 24.8 k frustums/s with it everywhere, 32.7 k on the max-only layers alone).
+static bool xg_use_pp(int K) { return K <= 128; }
 // A-stationary kernel (xg_as_kernel): K <= 128 and at least four column tiles; for t3d_linear_f32 only the max-only layers
-// (no Y to store: its 4 epilogue warps are the limit when every tile writes 64 KB).  T3D_XG_AS: 0 off, 1 default, 2 every
-// layer with at least two column tiles (measurement).
-static bool xg_use_as(int K, int ntn, bool linear = false, bool has_y = true) {
-  static const int v = [] { const char* e = getenv("T3D_XG_AS"); return e ? atoi(e) : 1; }();
-  if (v == 0 || K > 128) return false;
-  if (v == 2) return ntn >= 2;
-  return ntn >= 4 && !(linear && has_y);
-}
+// (no Y to store: its 4 epilogue warps are the limit when every tile writes 64 KB).
+static bool xg_use_as(int K, int ntn, bool linear = false, bool has_y = true) { return K <= 128 && ntn >= 4 && !(linear && has_y); }
+// Function attributes (dynamic shared memory opt-in) and the SM count are per DEVICE: caches are keyed by the current one.
+constexpr int kMaxDevices = 64;
+static int cur_device() { int dev = 0; cudaGetDevice(&dev); return (dev >= 0 && dev < kMaxDevices) ? dev : 0; }
 static int xg_num_sms() {
-  static const int n = [] { int dev = 0, v = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); return v; }();
-  return n;
+  static int n[kMaxDevices] = {0};
+  const int dev = cur_device();
+  if (n[dev] == 0) { int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); n[dev] = v; }
+  return n[dev];
+}
+// runs `prep` once per device; returns its error code (0 = prepared)
+template <typename F>
+static int once_per_device(int (&state)[kMaxDevices], F prep) {
+  const int dev = cur_device();
+  if (state[dev] == 0) { const int e = prep(); if (e != 0) return e; state[dev] = 1; }
+  return 0;
 }
 template <typename Kern>
 static int xg_prepare_pp(Kern kern) {
@@ -115,21 +114,26 @@ extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ld
   LinearArgs a{X, ldx, W, ldw, bias, gbias, rows_per_group, Y, ldy, M, K, N, act, rowmask, gmax};
   if (M >= 4096 && Y && !gbias && !rowmask && !gmax) {       // HBM-bound first / last layers (skinny_gemm.cuh)
     auto al16 = [](const void* p) { return (((uintptr_t)p) & 15) == 0; };
-    if (K <= kSkinnyMax && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && al16(Y) && ldy % 4 == 0) {
+    if (K <= kSkinnyMax && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && al16(Y) && ldy % 4 == 0 &&
+        sizeof(float) * (size_t)(K * N + N) <= kSkinnySmemMax) {
       skinny_k_kernel<<<xg_num_sms() * 8, 256, sizeof(float) * (size_t)(K * N + N), S(stream)>>>(X, ldx, W, ldw, bias, Y, ldy, M, N, K, act);
       T3D_CHECK_LAUNCH();
       return 0;
     }
-    if (N <= kSkinnyMax && act == 0 && K % 4 == 0 && K <= 1024 && al16(X) && ldx % 4 == 0) {
+    if (N <= kSkinnyMax && act == 0 && K % 4 == 0 && K <= 1024 && al16(X) && ldx % 4 == 0 &&
+        sizeof(float) * (size_t)N * K <= kSkinnySmemMax) {
       skinny_n_kernel<<<xg_num_sms() * 8, 256, sizeof(float) * (size_t)N * K, S(stream)>>>(X, ldx, W, 1, bias, Y, ldy, M, N, K, ldw);
       T3D_CHECK_LAUNCH();
       return 0;
     }
   }
   if (xg_fits(M, N, K)) {                    // tensor cores, bf16 x 3 split (xgemm.cuh)
-    static int prepared = xg_prepare(xlinear_kernel<3>) | xg_prepare(xlinear_kernel<1>) | xg_prepare(xlinear_pre_kernel<3>) |
-                          xg_prepare(xlinear_pre_kernel<1>);
-    if (prepared != 0) return prepared;
+    static int prepared[kMaxDevices] = {0};
+    if (int e = once_per_device(prepared, [] {
+          return xg_prepare(xlinear_kernel<3>) | xg_prepare(xlinear_kernel<1>) | xg_prepare(xlinear_pre_kernel<3>) |
+                 xg_prepare(xlinear_pre_kernel<1>) | xg_prepare_pp(xg_as_kernel<3, true>) | xg_prepare_pp(xg_as_kernel<1, true>);
+        }))
+      return e;
     const int ntm = (M + kXgBM - 1) / kXgBM, ntn = (N + kXgBN - 1) / kXgBN;
     const int parts = g_f32_engine == 1 ? 3 : 1;
     XgOperands o{X, ldx, W, ldw, M, N, K, (K + kXgBK - 1) / kXgBK * kXgBK, xg_aligned16(X, ldx) ? 1 : 0, 0, ntn, g_trace, nullptr, 0};
@@ -139,17 +143,9 @@ extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ld
       o.nkb = (K + 63) / 64;
       xg_presplit_kernel<<<dim3(o.nkb, ntn, 4), 256, 0, S(stream)>>>(W, ldw, 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
       if (xg_use_as(K, ntn, true, Y != nullptr)) {
-        static int prepared_as = xg_prepare_pp(xg_as_kernel<3, true>) | xg_prepare_pp(xg_as_kernel<1, true>);
-        if (prepared_as != 0) return prepared_as;
         const int g = ntm < xg_num_sms() ? ntm : xg_num_sms();
         if (parts == 3) xg_as_kernel<3, true><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(GemmArgs{}, a, o);
         else xg_as_kernel<1, true><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(GemmArgs{}, a, o);
-      } else if (xg_use_pp(K, true, Y != nullptr)) {
-        static int prepared_pp = xg_prepare_pp(xg_pp_kernel<3, true>) | xg_prepare_pp(xg_pp_kernel<1, true>);
-        if (prepared_pp != 0) return prepared_pp;
-        const int g = ntm * ntn < xg_num_sms() ? ntm * ntn : xg_num_sms();
-        if (parts == 3) xg_pp_kernel<3, true><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(GemmArgs{}, a, o);
-        else xg_pp_kernel<1, true><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(GemmArgs{}, a, o);
       } else if (parts == 3) xlinear_pre_kernel<3><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
       else xlinear_pre_kernel<1><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
     } else {
@@ -410,7 +406,8 @@ extern "C" int t3d_det_match(const t3d_det_match_args* a, t3d_stream_t stream) {
 }
 
 // ----------------------------------------------------------------------------- tcgen05 chains
-struct PackTable { PackDesc d[32]; };
+constexpr int kPackMax = 64;
+struct PackTable { PackDesc d[kPackMax]; };
 __global__ void __launch_bounds__(256) pack_table_kernel(const PackTable tab, uint8_t* arena) {
   const PackDesc d = tab.d[blockIdx.x];
   uint8_t* dst = arena + (size_t)blockIdx.x * kChunkBytes;
@@ -418,8 +415,25 @@ __global__ void __launch_bounds__(256) pack_table_kernel(const PackTable tab, ui
     const int r = e >> 6, kk = e & 63;
     float v = 0.0f;
     if (r < d.nrows && d.k0 + kk < d.k_total) v = d.W[(size_t)(d.k0 + kk) * d.ldw + d.row0 + r];
-    *reinterpret_cast<__nv_bfloat16*>(dst + sw128_offset(r, kk >> 3) + (kk & 7) * 2) = __float2bfloat16_rn(v);
+    uint8_t* o = dst + sw128_offset(r, kk >> 3) + (kk & 7) * 2;
+    if (d.part == 0) {
+      *reinterpret_cast<__nv_bfloat16*>(o) = __float2bfloat16_rn(v);
+    } else {                                   // fp16 hi / lo images of W * scale (round to nearest both)
+      v *= d.scale;
+      const __half hi = __float2half_rn(v);
+      *reinterpret_cast<__half*>(o) = d.part == 1 ? hi : __float2half_rn(v - __half2float(hi));
+    }
   }
+}
+__global__ void scale_copy_kernel(float* dst, const float* src, int n, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * scale;
+}
+__global__ void write4_kernel(float* dst, float a, float b, float c, float d) { dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d; }
+static int scale_copy(float* dst, const float* src, int n, float scale, cudaStream_t st) {
+  scale_copy_kernel<<<(n + 255) / 256, 256, 0, st>>>(dst, src, n, scale);
+  T3D_CHECK_LAUNCH();
+  return 0;
 }
 
 template <int KIND>
@@ -434,7 +448,7 @@ static int pack_chain_impl(const float* const* W, const float* const* bias, uint
   for (int mt = 0; mt < Sp::FC / 128; ++mt)
     for (int kb = 0; kb < Sp::FK / 64; ++kb)
       tab.d[n++] = PackDesc{W[1 + Sp::NH], Sp::FC, Sp::FK, kb * 64, mt * 128, 128};
-  if (n != chain_num_chunks<Sp>() || n > 32) return T3D_ERR_SHAPE;
+  if (n != chain_num_chunks<Sp>() || n > kPackMax) return T3D_ERR_SHAPE;
   pack_table_kernel<<<n, 256, 0, st>>>(tab, arena);
   T3D_CHECK_LAUNCH();
   float* f = reinterpret_cast<float*>(arena + (size_t)n * kChunkBytes);
@@ -454,13 +468,12 @@ template <int KIND>
 static int chain_launch(const ChainArgs& a, int out_elems, cudaStream_t st) {
   using Sp = ChainSpec<KIND>;
   using L = ChainSmem<Sp>;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    T3D_CUDA(cudaGetDevice(&dev));
-    T3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    T3D_CUDA(cudaFuncSetAttribute(chain_max_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL + 1024));
-  }
+  static int prepared[kMaxDevices] = {0};
+  if (int e = once_per_device(prepared, [] {
+        return (int)cudaFuncSetAttribute(chain_max_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL + 1024);
+      }))
+    return e;
+  const int sms = xg_num_sms();
   T3D_CUDA(cudaMemsetAsync(a.out, 0, sizeof(float) * (size_t)out_elems, st));
   int grid = sms - (sms % kClusterSize);
   if (!a.tiles) {
@@ -562,7 +575,7 @@ extern "C" int t3d_pack_seg2(const float* W6p, const float* W7, const float* W8,
     for (int kb = 0; kb < 2; ++kb)
       for (int nh = 0; nh < 2; ++nh) tab.d[n++] = PackDesc{W7, 256, 512, nb * 128 + kb * 64, nh * 128, 128};
   };
-  // consumption order of seg_stage2_kernel: j6(0) j6(1) j7(0) j6(2) j6(3) j7(1) j7(2) j7(3) conv8 conv9
+  // arena order (seg_stage2_pipe.cuh indexes it through kSeg2POrder): c6(0) c6(1) c7(0) c6(2) c6(3) c7(1) c7(2) c7(3) conv8 conv9
   // (every conv7 chunk pair starts at an even position of the chunk stream = even ring stage)
   c6(0); c6(1); c7(0); c6(2); c6(3); c7(1); c7(2); c7(3);
   for (int kb = 0; kb < 4; ++kb) tab.d[n++] = PackDesc{W8, 128, 256, kb * 64, 0, 128};
@@ -586,24 +599,203 @@ extern "C" int t3d_seg_stage2_bf16(const void* point_feat, const float* gbias, c
   if (B <= 0 || N <= 0) return T3D_ERR_SHAPE;
   if (((uintptr_t)point_feat & 15) || ((uintptr_t)gbias & 15) || ((uintptr_t)logits & 7) || ((uintptr_t)arena & 15))
     return T3D_ERR_ALIGN;
-  static int sms = 0, variant = 3;
-  if (sms == 0) {
-    int dev = 0;
-    T3D_CUDA(cudaGetDevice(&dev));
-    T3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    T3D_CUDA(cudaFuncSetAttribute(seg_stage2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2Smem::TOTAL + 1024));
-    T3D_CUDA(cudaFuncSetAttribute(seg_stage2_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2PSmem::TOTAL + 1024));
-    // A/B measurements: T3D_SEG2=v2 one tile at a time, v3 (default) two tiles in flight
-    const char* e = getenv("T3D_SEG2");
-    if (e != nullptr && e[0] == 'v' && e[1] >= '2' && e[1] <= '3') variant = e[1] - '0';
-  }
+  static int prepared[kMaxDevices] = {0};
+  if (int e = once_per_device(prepared, [] {
+        return (int)cudaFuncSetAttribute(seg_stage2_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2PSmem::TOTAL + 1024);
+      }))
+    return e;
+  const int sms = xg_num_sms();
   Seg2Args a{reinterpret_cast<const __nv_bfloat16*>(point_feat), gbias, reinterpret_cast<const uint8_t*>(arena), logits, B, N, g_trace};
   const int nt = B * ((N + 127) / 128);
   int grid = sms - (sms % kClusterSize);
   const int need = ((nt + kClusterSize - 1) / kClusterSize) * kClusterSize;
   if (need < grid) grid = need;
-  if (variant == 2) seg_stage2_kernel<<<grid, kSeg2Threads, Seg2Smem::TOTAL + 1024, S(stream)>>>(a);
-  else seg_stage2_pipe_kernel<<<grid, kSeg2PThreads, Seg2PSmem::TOTAL + 1024, S(stream)>>>(a);
+  seg_stage2_pipe_kernel<<<grid, kSeg2PThreads, Seg2PSmem::TOTAL + 1024, S(stream)>>>(a);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- f16x2 split-precision chains
+// First-order correction of the tensor core's round-toward-zero accumulation: every K=16 step that adds into a non-empty
+// accumulator loses ~0.36 ulp of it on average, so the epilogue scale of a layer with n such steps carries (1 + c n).
+// c is calibrated against the float64 oracle (tests/gpu_mask_exactness.py; emulated in tests/numerics_split_study.py).
+static float g_x2_debias = 2.1e-8f;
+extern "C" int t3d_set_x2_debias(float c) {
+  if (!(c >= 0.0f && c < 1e-6f)) return T3D_ERR_ARG;
+  g_x2_debias = c;
+  return 0;
+}
+extern "C" float t3d_get_x2_debias(void) { return g_x2_debias; }
+// epilogue scale of a layer whose accumulator holds (s * true value): kbn K-blocks issued in groups of `group`
+static float x2_inv(float s, int kbn, int group) {
+  const int neff = 12 * kbn - 8 * (group < kbn ? group : kbn);      // steps after the first group's small products
+  return (1.0f / s) * (1.0f + g_x2_debias * (float)neff);
+}
+static bool is_pow2(float x) { int e; return x > 0.0f && std::frexp(x, &e) == 0.5f; }
+
+template <int KIND>
+static int pack_chain_x2_impl(const float* const* W, const float* const* bias, const float* wscale, uint8_t* arena, cudaStream_t st) {
+  using Sp = ChainSpec<KIND>;
+  PackTable tab;
+  int n = 0;
+  // chunk order = consumption order of chain_max_x2_kernel: per output block, per group of K-blocks: lo images, then hi images
+  auto block = [&](const float* Wl, int ldw, int ktot, int row0, int nrows, float sc) {
+    const int kbn = ktot / 64;
+    for (int g0 = 0; g0 < kbn; g0 += kX2Group) {
+      const int gn = kbn - g0 < kX2Group ? kbn - g0 : kX2Group;
+      for (int part = 2; part >= 1; --part)
+        for (int j = 0; j < gn; ++j)
+          if (n < kPackMax) tab.d[n++] = PackDesc{Wl, ldw, ktot, (g0 + j) * 64, row0, nrows, part, sc};
+    }
+  };
+  for (int l = 0; l <= Sp::NH; ++l)
+    if (!is_pow2(wscale[l])) return T3D_ERR_ARG;
+  for (int l = 0; l < Sp::NH; ++l)
+    for (int nb = 0; nb < (Sp::HN(l) + 127) / 128; ++nb)
+      block(W[1 + l], Sp::HN(l), Sp::HK(l), nb * 128, Sp::HN(l) - nb * 128 < 128 ? Sp::HN(l) - nb * 128 : 128, wscale[l]);
+  for (int mt = 0; mt < Sp::FC / 128; ++mt) block(W[1 + Sp::NH], Sp::FC, Sp::FK, mt * 128, 128, wscale[Sp::NH]);
+  if (n != x2_num_chunks<Sp>()) return T3D_ERR_SHAPE;
+  pack_table_kernel<<<n, 256, 0, st>>>(tab, arena);
+  T3D_CHECK_LAUNCH();
+  float* f = reinterpret_cast<float*>(arena + (size_t)n * kChunkBytes);
+  int e;
+  if ((e = scale_copy(f, W[0], Sp::CIN * Sp::C1, kX2ActScale, st)) != 0) return e;
+  f += Sp::CIN * Sp::C1;
+  if ((e = scale_copy(f, bias[0], Sp::C1, kX2ActScale, st)) != 0) return e;
+  f += Sp::C1;
+  for (int l = 0; l < Sp::NH; ++l) {
+    if ((e = scale_copy(f, bias[1 + l], Sp::HN(l), kX2ActScale, st)) != 0) return e;
+    f += Sp::HN(l);
+  }
+  if ((e = scale_copy(f, bias[1 + Sp::NH], Sp::FC, 1.0f, st)) != 0) return e;
+  f += Sp::FC;
+  float inv[4] = {0, 0, 0, 0};
+  for (int l = 0; l < Sp::NH; ++l) inv[l] = x2_inv(wscale[l], Sp::HK(l) / 64, kX2Group);
+  inv[Sp::NH] = x2_inv(wscale[Sp::NH] * kX2ActScale, Sp::FK / 64, kX2Group);
+  write4_kernel<<<1, 1, 0, st>>>(f, inv[0], inv[1], inv[2], inv[3]);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+template <int KIND>
+static int chain_launch_x2(const ChainArgs& a, int out_elems, cudaStream_t st) {
+  using Sp = ChainSpec<KIND>;
+  using L = X2Smem<Sp>;
+  static int prepared[kMaxDevices] = {0};
+  if (int e = once_per_device(prepared, [] {
+        return (int)cudaFuncSetAttribute(chain_max_x2_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL + 1024);
+      }))
+    return e;
+  const int sms = xg_num_sms();
+  T3D_CUDA(cudaMemsetAsync(a.out, 0, sizeof(float) * (size_t)out_elems, st));
+  int grid = sms - (sms % kClusterSize);
+  if (!a.tiles) {
+    const int nt = a.B * ((a.N + 127) / 128);
+    const int need = ((nt + kClusterSize - 1) / kClusterSize) * kClusterSize;
+    if (need < grid) grid = need;
+  }
+  chain_max_x2_kernel<KIND><<<grid, kChainThreads, L::TOTAL + 1024, st>>>(a);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" size_t t3d_chain_arena_bytes_x2(int kind) {
+  switch (kind) {
+    case CHAIN_SEG1: return x2_arena_bytes<ChainSpec<CHAIN_SEG1>>();
+    case CHAIN_TNET: return x2_arena_bytes<ChainSpec<CHAIN_TNET>>();
+    case CHAIN_BOX: return x2_arena_bytes<ChainSpec<CHAIN_BOX>>();
+    case CHAIN_BOXPC: return x2_arena_bytes<ChainSpec<CHAIN_BOXPC>>();
+    default: return 0;
+  }
+}
+
+extern "C" int t3d_pack_chain_x2(int kind, const float* const* W, const float* const* bias, const float* wscale, void* arena,
+                                 t3d_stream_t stream) {
+  if (!W || !bias || !wscale || !arena) return T3D_ERR_ARG;
+  if ((uintptr_t)arena & 1023) return T3D_ERR_ALIGN;
+  CHAIN_SWITCH(kind, return pack_chain_x2_impl<K_>(W, bias, wscale, reinterpret_cast<uint8_t*>(arena), S(stream)));
+  return 0;
+}
+
+extern "C" int t3d_chain_max_x2(int kind, const float* pc, int B, int N, int C, const float* center, const int* idx,
+                                int idx_stride, const int* count, const void* tiles, const int* num_tiles,
+                                const float* box_center, const float* box_dims, const float* box_orient, const void* arena,
+                                float* out, void* emit, t3d_stream_t stream) {
+  if (!pc || !arena || !out) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0) return T3D_ERR_SHAPE;
+  if ((uintptr_t)arena & 15) return T3D_ERR_ALIGN;
+  if ((tiles != nullptr) != (num_tiles != nullptr)) return T3D_ERR_ARG;
+  if (idx && idx_stride <= 0) return T3D_ERR_SHAPE;
+  if (kind == CHAIN_BOXPC && (!box_center || !box_dims || !box_orient)) return T3D_ERR_ARG;
+  if (kind == CHAIN_BOXPC ? C != 6 : (kind == CHAIN_SEG1 ? C != 6 : C < 3)) return T3D_ERR_SHAPE;
+  if (emit && (kind != CHAIN_SEG1 || ((uintptr_t)emit & 15))) return T3D_ERR_ARG;
+  ChainArgs a{pc, B, N, C, center, idx, idx_stride, count, reinterpret_cast<const int4*>(tiles), num_tiles,
+              box_center, box_dims, box_orient, reinterpret_cast<const uint8_t*>(arena), out,
+              reinterpret_cast<__nv_bfloat16*>(emit), g_trace};
+  CHAIN_SWITCH(kind, return chain_launch_x2<K_>(a, B * ChainSpec<K_>::FC, S(stream)));
+  return 0;
+}
+
+extern "C" size_t t3d_seg2_arena_bytes_x2(void) { return kSeg2XArenaBytes; }
+
+extern "C" int t3d_pack_seg2_x2(const float* W6p, const float* W7, const float* W8, const float* W9, const float* b7,
+                                const float* b8, const float* b9, const float* W10, const float* b10, const float* wscale,
+                                void* arena, t3d_stream_t stream) {
+  if (!W6p || !W7 || !W8 || !W9 || !b7 || !b8 || !b9 || !W10 || !b10 || !wscale || !arena) return T3D_ERR_ARG;
+  if ((uintptr_t)arena & 1023) return T3D_ERR_ALIGN;
+  for (int l = 0; l < 4; ++l)
+    if (!is_pow2(wscale[l])) return T3D_ERR_ARG;
+  cudaStream_t st = S(stream);
+  PackTable tab;
+  int n = 0;
+  auto c6 = [&](int nb) {
+    for (int part = 2; part >= 1; --part) tab.d[n++] = PackDesc{W6p, 512, 64, 0, nb * 128, 128, part, wscale[0]};
+  };
+  auto c7 = [&](int kbg) {      // [lo rows 0-127][lo rows 128-255][hi rows 0-127][hi rows 128-255]
+    for (int part = 2; part >= 1; --part)
+      for (int nh = 0; nh < 2; ++nh) tab.d[n++] = PackDesc{W7, 256, 512, kbg * 64, nh * 128, 128, part, wscale[1]};
+  };
+  // consumption order of seg_stage2_x2_kernel
+  c6(0); c6(1); c7(0); c7(1); c6(2); c7(2); c7(3); c6(3); c7(4); c7(5); c7(6); c7(7);
+  for (int kb = 0; kb < 4; ++kb)
+    for (int part = 2; part >= 1; --part) tab.d[n++] = PackDesc{W8, 128, 256, kb * 64, 0, 128, part, wscale[2]};
+  for (int part = 2; part >= 1; --part)
+    for (int kb = 0; kb < 2; ++kb) tab.d[n++] = PackDesc{W9, 128, 128, kb * 64, 0, 128, part, wscale[3]};
+  if (n != kSeg2XChunks) return T3D_ERR_SHAPE;
+  uint8_t* ar = reinterpret_cast<uint8_t*>(arena);
+  pack_table_kernel<<<n, 256, 0, st>>>(tab, ar);
+  T3D_CHECK_LAUNCH();
+  float* f = reinterpret_cast<float*>(ar + (size_t)n * kChunkBytes);
+  int e;
+  if ((e = scale_copy(f, b7, 256, kX2ActScale, st)) != 0) return e;
+  if ((e = scale_copy(f + 256, b8, 128, kX2ActScale, st)) != 0) return e;
+  if ((e = scale_copy(f + 384, b9, 128, kX2ActScale, st)) != 0) return e;
+  if ((e = scale_copy(f + 512, W10, 256, 1.0f / kX2ActScale, st)) != 0) return e;
+  if ((e = scale_copy(f + 768, b10, 2, 1.0f, st)) != 0) return e;
+  write4_kernel<<<1, 1, 0, st>>>(f + 770, x2_inv(wscale[0], 1, 1), x2_inv(wscale[1], 8, 1), x2_inv(wscale[2], 4, 1),
+                                 x2_inv(wscale[3], 2, 2));
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int t3d_seg_stage2_x2(const void* point_feat, const float* gbias, const void* arena, float* logits, int B, int N,
+                                 t3d_stream_t stream) {
+  if (!point_feat || !gbias || !arena || !logits) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0) return T3D_ERR_SHAPE;
+  if (((uintptr_t)point_feat & 15) || ((uintptr_t)gbias & 15) || ((uintptr_t)logits & 7) || ((uintptr_t)arena & 15))
+    return T3D_ERR_ALIGN;
+  static int prepared[kMaxDevices] = {0};
+  if (int e = once_per_device(prepared, [] {
+        return (int)cudaFuncSetAttribute(seg_stage2_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2XSmem::TOTAL + 1024);
+      }))
+    return e;
+  const int sms = xg_num_sms();
+  Seg2XArgs a{reinterpret_cast<const uint8_t*>(point_feat), gbias, reinterpret_cast<const uint8_t*>(arena), logits, B, N, g_trace};
+  const int nt = B * ((N + 127) / 128);
+  int grid = sms - (sms % kClusterSize);
+  const int need = ((nt + kClusterSize - 1) / kClusterSize) * kClusterSize;
+  if (need < grid) grid = need;
+  seg_stage2_x2_kernel<<<grid, kSeg2XThreads, Seg2XSmem::TOTAL + 1024, S(stream)>>>(a);
   T3D_CHECK_LAUNCH();
   return 0;
 }
@@ -620,20 +812,21 @@ extern "C" int t3d_gemm_f32_ws(const float* A, long long sam, long long sak, con
   {   // HBM-bound first-layer shapes (skinny_gemm.cuh); 128-bit accesses need aligned bases and leading dimensions
     auto al16 = [](const void* p) { return (((uintptr_t)p) & 15) == 0; };
     const int sms = xg_num_sms();
-    static const int skinny = [] { const char* e = getenv("T3D_SKINNY"); return e ? atoi(e) : 7; }();      // bit 0 k, 1 n, 2 m
-    if ((skinny & 1) && M >= 4096 && K <= kSkinnyMax && sak == 1 && sbn == 1 && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && al16(C) && ldc % 4 == 0) {
+    if (M >= 4096 && K <= kSkinnyMax && sak == 1 && sbn == 1 && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && al16(C) && ldc % 4 == 0 &&
+        sizeof(float) * (size_t)(K * N + N) <= kSkinnySmemMax) {
       if (splitk > 1) { /* C was zeroed above; a single pass writes every element */ }
       skinny_k_kernel<<<sms * 8, 256, sizeof(float) * (size_t)(K * N + N), S(stream)>>>(A, sam, B, sbk, bias, C, ldc, M, N, K);
       T3D_CHECK_LAUNCH();
       return 0;
     }
-    if ((skinny & 2) && M >= 4096 && N <= kSkinnyMax && sak == 1 && sbk == 1 && sbn != 1 && K % 4 == 0 && K <= 1024 && al16(A) && sam % 4 == 0) {
+    if (M >= 4096 && N <= kSkinnyMax && sak == 1 && sbk == 1 && sbn != 1 && K % 4 == 0 && K <= 1024 && al16(A) && sam % 4 == 0 &&
+        sizeof(float) * (size_t)N * K <= kSkinnySmemMax) {
       skinny_n_kernel<<<sms * 8, 256, sizeof(float) * (size_t)N * K, S(stream)>>>(A, sam, B, sbn, bias, C, ldc, M, N, K);
       T3D_CHECK_LAUNCH();
       return 0;
     }
-    if ((skinny & 4) && K >= 4096 && M <= kSkinnyMax && sam == 1 && sbn == 1 && !bias && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && al16(B) &&
-        sbk % 4 == 0 && (size_t)M * N * sizeof(float) <= 48 * 1024) {
+    if (K >= 4096 && M <= kSkinnyMax && sam == 1 && sbn == 1 && !bias && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && al16(B) &&
+        sbk % 4 == 0 && (size_t)M * N * sizeof(float) <= kSkinnySmemMax) {
       if (splitk <= 1) T3D_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, S(stream)));
       skinny_m_kernel<<<sms * 4, 256, sizeof(float) * (size_t)M * N, S(stream)>>>(A, sak, B, sbk, C, ldc, M, N, K);
       T3D_CHECK_LAUNCH();
@@ -641,12 +834,17 @@ extern "C" int t3d_gemm_f32_ws(const float* A, long long sam, long long sak, con
     }
   }
   if (xg_fits(M, N, K)) {                    // tensor cores, bf16 x 3 split (xgemm.cuh)
-    static int prepared = xg_prepare(xgemm_kernel<true, true, 3>) | xg_prepare(xgemm_kernel<true, false, 3>) |
-                          xg_prepare(xgemm_kernel<false, true, 3>) | xg_prepare(xgemm_kernel<false, false, 3>) |
-                          xg_prepare(xgemm_kernel<true, true, 1>) | xg_prepare(xgemm_kernel<true, false, 1>) |
-                          xg_prepare(xgemm_kernel<false, true, 1>) | xg_prepare(xgemm_kernel<false, false, 1>) |
-                          xg_prepare(xgemm_pre_kernel<3>) | xg_prepare(xgemm_pre_kernel<1>);
-    if (prepared != 0) return prepared;
+    static int prepared[kMaxDevices] = {0};
+    if (int e = once_per_device(prepared, [] {
+          return xg_prepare(xgemm_kernel<true, true, 3>) | xg_prepare(xgemm_kernel<true, false, 3>) |
+                 xg_prepare(xgemm_kernel<false, true, 3>) | xg_prepare(xgemm_kernel<false, false, 3>) |
+                 xg_prepare(xgemm_kernel<true, true, 1>) | xg_prepare(xgemm_kernel<true, false, 1>) |
+                 xg_prepare(xgemm_kernel<false, true, 1>) | xg_prepare(xgemm_kernel<false, false, 1>) |
+                 xg_prepare(xgemm_pre_kernel<3>) | xg_prepare(xgemm_pre_kernel<1>) |
+                 xg_prepare_pp(xg_as_kernel<3, false>) | xg_prepare_pp(xg_as_kernel<1, false>) |
+                 xg_prepare_pp(xg_pp_kernel<3, false>) | xg_prepare_pp(xg_pp_kernel<1, false>);
+        }))
+      return e;
     // The tensor core adds each 16-deep partial sum into the fp32 accumulator with truncation, a bias of ~0.5 ulp per
     // step (measured: 700 ulp of sum|a||b| after K = 20000, 25 after K = 600); K chunks are kept <= 2048 so that long
     // reductions (wgrad over B*N rows) are summed across chunks by round-to-nearest fp32 reductions instead.
@@ -667,14 +865,10 @@ extern "C" int t3d_gemm_f32_ws(const float* A, long long sam, long long sak, con
       const int parts = g_f32_engine == 1 ? 3 : 1;
       xg_presplit_kernel<<<dim3(o.nkb, ntn, 4), 256, 0, S(stream)>>>(B, ldb, bk ? 1 : 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
       if (xg_use_as(K, ntn)) {
-        static int prepared_as = xg_prepare_pp(xg_as_kernel<3, false>) | xg_prepare_pp(xg_as_kernel<1, false>);
-        if (prepared_as != 0) return prepared_as;
         const int g = ntm < xg_num_sms() ? ntm : xg_num_sms();
         if (parts == 3) xg_as_kernel<3, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o);
         else xg_as_kernel<1, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o);
       } else if (xg_use_pp(K)) {
-        static int prepared_pp = xg_prepare_pp(xg_pp_kernel<3, false>) | xg_prepare_pp(xg_pp_kernel<1, false>);
-        if (prepared_pp != 0) return prepared_pp;
         const int g = ntm * ntn < xg_num_sms() ? ntm * ntn : xg_num_sms();
         if (parts == 3) xg_pp_kernel<3, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o);
         else xg_pp_kernel<1, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o);

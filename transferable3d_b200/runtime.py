@@ -2,9 +2,12 @@
 collection + tf.variable_scope, models/tf_util.py:1151-1190), BN folding / weight packing caches,
 the precision switch, and thin wrappers over the C ABI.
 
-Precision modes (BASELINE north_star): 'bf16' = tcgen05 kernels, bf16 operands / fp32 accumulate;
-'fp32' = CUDA-core fp32 kernels layer by layer (1e-4 parity mode).  FC heads are fp32 in both.
-Only eval-mode graphs (is_training=False) are implemented on the GPU path in this round.
+Precision modes (BASELINE north_star):
+  'bf16'   fused tcgen05 kernels, bf16 operands / fp32 accumulate (the throughput mode);
+  'f16x2'  the same fused kernels in split precision: every operand is an fp16 hi + lo pair, three tensor-core products
+           per layer, fp32-accurate (the mode that meets the mask-exactness target; csrc/chain_x2.cuh);
+  'fp32'   layer-by-layer fp32 GEMMs with the literal mask multiply (1e-4 parity mode, every activation through HBM).
+FC heads are fp32 in all three.  Eval-mode graphs only; training graphs live in train_boxpc / train_semisup_adv.
 """
 import contextlib
 import ctypes
@@ -19,17 +22,43 @@ from .weights import fold_bn
 ACT = {'none': 0, None: 0, 'relu': 1, 'leaky_relu': 2, 'tanh': 3}
 CHAIN_SEG1, CHAIN_TNET, CHAIN_BOX, CHAIN_BOXPC = 0, 1, 2, 3
 
+PRECISIONS = ('bf16', 'f16x2', 'fp32')
+FUSED = ('bf16', 'f16x2')          # modes that run the fused tcgen05 chains
+X2_ACT_SCALE = 16.0               # csrc/chain_x2.cuh: kX2ActScale
+
 _state = {'store': None, 'precision': 'bf16'}
 
 
 def set_precision(mode):
-    if mode not in ('bf16', 'fp32'):
+    if mode not in PRECISIONS:
         raise ValueError(mode)
     _state['precision'] = mode
 
 
 def get_precision():
     return _state['precision']
+
+
+def is_x2():
+    return _state['precision'] == 'f16x2'
+
+
+def set_x2_debias(per_step):
+    """Correction of the tensor core's truncating accumulation folded into the f16x2 epilogue scales (include/t3d_b200.h:
+    t3d_set_x2_debias).  Arenas are cached per value."""
+    _lib.check(_lib.load().t3d_set_x2_debias(float(per_step)))
+
+
+def get_x2_debias():
+    return float(_lib.load().t3d_get_x2_debias())
+
+
+def _pow2_scale(w):
+    """Power of two s with max|w| * s in [2^9, 2^10): keeps the fp16 lo image of the weights in the normal range."""
+    m = float(w.abs().max())
+    if not np.isfinite(m) or m <= 0.0:
+        return 1.0
+    return float(2.0 ** (9 - int(np.floor(np.log2(m)))))
 
 
 def default_device():
@@ -119,16 +148,22 @@ class VariableStore(object):
             self._consts[name] = torch.as_tensor(np.asarray(array, dtype=np.float32)).to(self.device).contiguous()
         return self._consts[name]
 
+    def cached(self, key, make):
+        """Device-side value derived from the variables, built once (`make()` returns tensors on self.device)."""
+        if key not in self._consts:
+            self._consts[key] = make()
+        return self._consts[key]
+
     def _new_arena(self, nbytes):
         # 1024-byte aligned base (torch allocations are 512-byte aligned)
         raw = torch.empty(nbytes + 1024, dtype=torch.uint8, device=self.device)
         off = (-raw.data_ptr()) % 1024
         return raw[off:off + nbytes]
 
-    def chain_arena(self, scope, kind, layers, w1_rows=None):
+    def chain_arena(self, scope, kind, layers, x2=False):
         """Packed tcgen05 weights of one per-point chain. `layers` = TF layer names under `scope`:
-        [layer1, hidden..., final]."""
-        key = ('chain', scope, kind)
+        [layer1, hidden..., final].  x2: fp16 hi / lo images for the f16x2 kernels."""
+        key = ('chain', scope, kind, get_x2_debias() if x2 else None)
         if key not in self._arenas:
             lib = _lib.load()
             assert lib.t3d_chain_num_layers(kind) == len(layers)
@@ -137,15 +172,36 @@ class VariableStore(object):
                 w, b = self.folded('%s/%s' % (scope, name))
                 ws.append(w.contiguous())
                 bs.append(b.contiguous())
-            arena = self._new_arena(lib.t3d_chain_arena_bytes(kind))
             PA = ctypes.c_void_p * len(layers)
-            call('t3d_pack_chain', kind, PA(*[w.data_ptr() for w in ws]), PA(*[b.data_ptr() for b in bs]),
-                 ptr(arena), stream())
+            if x2:
+                arena = self._new_arena(lib.t3d_chain_arena_bytes_x2(kind))
+                scales = (ctypes.c_float * (len(layers) - 1))(*[_pow2_scale(w) for w in ws[1:]])
+                call('t3d_pack_chain_x2', kind, PA(*[w.data_ptr() for w in ws]), PA(*[b.data_ptr() for b in bs]), scales,
+                     ptr(arena), stream())
+            else:
+                arena = self._new_arena(lib.t3d_chain_arena_bytes(kind))
+                call('t3d_pack_chain', kind, PA(*[w.data_ptr() for w in ws]), PA(*[b.data_ptr() for b in bs]),
+                     ptr(arena), stream())
             torch.cuda.current_stream().synchronize()       # ws/bs may be freed after this
             self._arenas[key] = arena
         return self._arenas[key]
 
-    def seg2_arena(self, scope):
+    def seg2_arena(self, scope, x2=False):
+        if x2:
+            key = ('seg2x', scope, get_x2_debias())
+            if key not in self._arenas:
+                lib = _lib.load()
+                w6, _ = self.folded(scope + '/conv6')
+                w6p = w6[:64].contiguous()
+                (w7, b7), (w8, b8), (w9, b9) = [self.folded(scope + '/conv%d' % i) for i in (7, 8, 9)]
+                w10, b10 = self.folded(scope + '/conv10')
+                scales = (ctypes.c_float * 4)(*[_pow2_scale(w) for w in (w6p, w7, w8, w9)])
+                arena = self._new_arena(lib.t3d_seg2_arena_bytes_x2())
+                call('t3d_pack_seg2_x2', ptr(w6p), ptr(w7), ptr(w8), ptr(w9), ptr(b7), ptr(b8), ptr(b9), ptr(w10), ptr(b10),
+                     scales, ptr(arena), stream())
+                torch.cuda.current_stream().synchronize()
+                self._arenas[key] = arena
+            return self._arenas[key]
         key = ('seg2', scope)
         if key not in self._arenas:
             lib = _lib.load()
@@ -227,8 +283,8 @@ def build_tiles(count, tile_pts, max_per_frustum):
     return tiles, num
 
 
-def chain_max(kind, pc, arena, center=None, idx=None, count=None, box=None, emit=None):
-    """Fused per-point chain + max on tcgen05. Returns (B, FC) fp32."""
+def chain_max(kind, pc, arena, center=None, idx=None, count=None, box=None, emit=None, x2=False):
+    """Fused per-point chain + max on tcgen05. Returns (B, FC) fp32.  x2: the f16x2 kernel (arena packed with x2=True)."""
     lib = _lib.load()
     B, N, C = pc.shape
     fc = lib.t3d_chain_out_channels(kind)
@@ -239,16 +295,16 @@ def chain_max(kind, pc, arena, center=None, idx=None, count=None, box=None, emit
         idx_stride = idx.shape[1]
         if count is None:
             count = torch.full((B,), idx_stride, dtype=torch.int32, device=pc.device)
-        tiles, num = build_tiles(count, lib.t3d_chain_tile_points(kind), idx_stride)
+        tiles, num = build_tiles(count, 128 if x2 else lib.t3d_chain_tile_points(kind), idx_stride)
     bc = bd = bo = None
     if box is not None:
         bc, bd, bo = [f32(t) for t in box]
-    call('t3d_chain_max_bf16', kind, ptr(pc), B, N, C, ptr(center), ptr(idx), idx_stride, ptr(count), ptr(tiles), ptr(num),
+    call('t3d_chain_max_x2' if x2 else 't3d_chain_max_bf16', kind, ptr(pc), B, N, C, ptr(center), ptr(idx), idx_stride, ptr(count), ptr(tiles), ptr(num),
          ptr(bc), ptr(bd), ptr(bo), ptr(arena), ptr(out), ptr(emit), stream())
     return out
 
 
-def seg_stage2(point_feat, gbias, arena, B, N):
+def seg_stage2(point_feat, gbias, arena, B, N, x2=False):
     logits = torch.empty((B, N, 2), dtype=torch.float32, device=gbias.device)
-    call('t3d_seg_stage2_bf16', ptr(point_feat), ptr(gbias), ptr(arena), ptr(logits), B, N, stream())
+    call('t3d_seg_stage2_x2' if x2 else 't3d_seg_stage2_bf16', ptr(point_feat), ptr(gbias), ptr(arena), ptr(logits), B, N, stream())
     return logits

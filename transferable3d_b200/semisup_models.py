@@ -1,10 +1,11 @@
 """Mirror of sunrgbd/sunrgbd_detection/semisup_models.py (same function names, argument order and
 end_points keys), evaluated on the B200.
 
-bf16 mode: every per-point conv stack + max-pool is ONE fused tcgen05 kernel (csrc/chain_max.cuh,
-csrc/seg_stage2.cuh); the masked stacks (tnet, box_est) run on the compacted masked-in points, which
-equals the reference's max(net*mask) because post-ReLU activations are >= 0.
-fp32 mode: layer-by-layer CUDA-core kernels (t3d_linear_f32) with the literal mask multiply.
+bf16 / f16x2 modes: every per-point conv stack + max-pool is ONE fused tcgen05 kernel (csrc/chain_max.cuh,
+csrc/seg_stage2_pipe.cuh; split-precision twins csrc/chain_x2.cuh, csrc/seg_stage2_x2.cuh); the masked stacks (tnet,
+box_est) run on the compacted masked-in points, which equals the reference's max(net*mask) because post-ReLU
+activations are >= 0.
+fp32 mode: layer-by-layer fp32 GEMMs (t3d_linear_f32) with the literal mask multiply.
 Variables are resolved by TF name through runtime.variable_scope (checkpoint contract).
 """
 import numpy as np
@@ -81,17 +82,25 @@ def v1_inst_seg(point_cloud, img_feats, one_hot_vec, end_points, is_training, bn
     with rt.variable_scope(scope):
         full = st.scope_name()
         w6, b6 = st.folded(full + '/conv6')
-        if rt.get_precision() == 'bf16':
+        if rt.get_precision() in rt.FUSED:
             if D != 6:
                 raise ValueError('the tcgen05 inst_seg kernel is built for 6-channel frustums (got %d)' % D)
-            arena1 = st.chain_arena(full, rt.CHAIN_SEG1, ['conv1', 'conv2', 'conv3', 'conv4', 'conv5'])
-            arena2 = st.seg2_arena(full)
-            # stage 1 emits conv3's output as the swizzled operand images of stage 2 (one [256 x 64] image per tile)
-            point_feat = torch.empty((B * ((N + 255) // 256) * 256, 64), dtype=torch.bfloat16, device=pc.device)
-            gfeat = rt.chain_max(rt.CHAIN_SEG1, pc, arena1, emit=point_feat)                 # (B,1024)
+            x2 = rt.is_x2()
+            arena1 = st.chain_arena(full, rt.CHAIN_SEG1, ['conv1', 'conv2', 'conv3', 'conv4', 'conv5'], x2=x2)
+            arena2 = st.seg2_arena(full, x2=x2)
+            # stage 1 emits conv3's output as the swizzled operand images of stage 2 (bf16: one [256 x 64] image per
+            # 256-point tile; f16x2: a hi and a lo fp16 [128 x 64] image per 128-point tile)
+            if x2:
+                point_feat = torch.empty((B * ((N + 127) // 128), 32768), dtype=torch.uint8, device=pc.device)
+                w6g, b6g = st.cached(full + '/conv6/x2_global', lambda: ((w6[64:] * rt.X2_ACT_SCALE).contiguous(),
+                                                                         (b6 * rt.X2_ACT_SCALE).contiguous()))
+            else:
+                point_feat = torch.empty((B * ((N + 255) // 256) * 256, 64), dtype=torch.bfloat16, device=pc.device)
+                w6g, b6g = st.cached(full + '/conv6/global', lambda: (w6[64:].contiguous(), b6))
+            gfeat = rt.chain_max(rt.CHAIN_SEG1, pc, arena1, emit=point_feat, x2=x2)          # (B,1024)
             g = _cat([gfeat, one_hot_vec])
-            gbias, _ = rt.linear(g, w6[64:].contiguous(), b6)                               # conv6 global half
-            logits = rt.seg_stage2(point_feat, gbias, arena2, B, N)
+            gbias, _ = rt.linear(g, w6g, b6g)                                               # conv6 global half
+            logits = rt.seg_stage2(point_feat, gbias, arena2, B, N, x2=x2)
         else:
             x = pc.reshape(B * N, D)
             for name in ('conv1', 'conv2', 'conv3'):
@@ -129,12 +138,13 @@ def _masked_chain(kind, view, mask, layer_names, scope_full):
     st = rt.store()
     pc = view.pc
     B, N, _ = pc.shape
-    if rt.get_precision() == 'bf16':
-        arena = st.chain_arena(scope_full, kind, layer_names)
+    if rt.get_precision() in rt.FUSED:
+        x2 = rt.is_x2()
+        arena = st.chain_arena(scope_full, kind, layer_names, x2=x2)
         if mask is None:
-            return rt.chain_max(kind, pc, arena, center=view.center)
+            return rt.chain_max(kind, pc, arena, center=view.center, x2=x2)
         idx, count = _compaction_of(mask, pc)
-        return rt.chain_max(kind, pc, arena, center=view.center, idx=idx, count=count)
+        return rt.chain_max(kind, pc, arena, center=view.center, idx=idx, count=count, x2=x2)
     x = view.tensor().reshape(B * N, 3)
     rowmask = None if mask is None else rt.f32(mask.reshape(B * N))
     for name in layer_names[:-1]:
@@ -229,9 +239,9 @@ def combined_box_pc_mask_features_model(box_reg, pc, mask, num_outputs, is_train
     names = ['conv-reg1', 'conv-reg2', 'conv-reg3', 'conv-reg4']
     with rt.variable_scope(scope):
         full = st.scope_name()
-        if rt.get_precision() == 'bf16':
-            arena = st.chain_arena(full, rt.CHAIN_BOXPC, names)
-            net = rt.chain_max(rt.CHAIN_BOXPC, pc, arena, box=box_reg)
+        if rt.get_precision() in rt.FUSED:
+            arena = st.chain_arena(full, rt.CHAIN_BOXPC, names, x2=rt.is_x2())
+            net = rt.chain_max(rt.CHAIN_BOXPC, pc, arena, box=box_reg, x2=rt.is_x2())
         else:
             x = tf_util.tf_get_box_pc_representation(box_reg, pc).reshape(B * N, C + 6)
             for name in names[:-1]:
