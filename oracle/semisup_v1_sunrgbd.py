@@ -114,7 +114,7 @@ def huber_loss(error, delta, reduce_loss=True):
     return losses.mean() if reduce_loss else losses
 
 
-def get_strong_loss(pred, labels, end_points, prefix='', reduce_loss=True, c=None):
+def get_strong_loss(pred, labels, end_points, prefix='', reg_weight=0.001, reduce_loss=True, c=None):
     """semisup_v1_sunrgbd.py:423-553: returns per-sample (mask_losses, box_losses), both (B,)."""
     Fn = torch.nn.functional
     pred_seg, pred_box = pred

@@ -34,8 +34,9 @@ def run_graph(vs, FLAGS, pc, one_hot_vec, box2D=None, img_dim=None, oracle_mask=
         with vs.variable_scope('D_boxpc_branch'):
             _, ep = boxpc_sunrgbd.get_model(fake_box_pc, False, one_hot_vec, vs, use_one_hot_vec=False, c=FLAGS)
         boxpc_fit_prob = torch.softmax(ep['boxpc_fit_logits'], dim=1)[:, 1]
-        weight = (1 - ep['logits_for_weigh']) if FLAGS.SEMI_WEIGH_BOXPC_DELTA_DURING_TEST \
-            else torch.ones_like(ep['logits_for_weigh'])
+        # test_semisup.py:86 sets FLAGS.SEMI_WEIGH_BOXPC_DELTA_DURING_TEST = False before building the graph, so the
+        # `1 - logits_for_weigh` branch (:117-119) is never taken at test time
+        weight = torch.ones_like(ep['logits_for_weigh'])
         delta_center = ep['boxpc_delta_center'] * weight.unsqueeze(1)
         delta_angle = ep['boxpc_delta_angle'] * weight
         delta_size = ep['boxpc_delta_size'] * weight.unsqueeze(1)

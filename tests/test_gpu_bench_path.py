@@ -9,7 +9,10 @@ sess.run at batch 32, and cfg2 (seg chain alone, batch 1024).  Checks:
   * the big batch equals, bit for bit, the same frustums run as four batches of 256 (other tile -> CTA assignment, other
     ring phases, other flush points).
 Tolerances: f16x2 = the fp32-mode bar (1e-4 of the tensor scale).  bf16 = the north star's rel 1e-2 / abs 1e-3 applied to
-raw values; the fraction of elements inside is asserted at the level measured on B200 (README states the numbers).
+raw values for everything downstream of the mask: >= 99 % of the elements of every output inside (measured on B200:
+99.7 - 100 %, largest error 2.7e-3; profiles/r02_parity_stats_bench_path.json).  The bf16 seg logits themselves carry
+0.5 % of the logit scale of rounding noise (mean) and are held to that, not to abs 1e-3: each is a difference of two
+large terms with the synthetic calibrated weights (README, parity table).
 """
 import json
 import os
@@ -93,13 +96,17 @@ def test_cfg3_pipeline_big_batch(mode, built_lib, big):
             s = err_stats(glog, big['ologits'])
             assert s['mean_abs'] <= 0.008 * s['ref_scale'] and s['max_abs'] <= 0.05 * s['ref_scale'], s
             assert ((glog[..., 0] < glog[..., 1]) == (big['ologits'][..., 0] < big['ologits'][..., 1])).mean() > 0.96
-        # (2) downstream of the GPU's own logits: identical masks -> identical resampled indices, outputs within tolerance
-        oep = oracle_cfg3_from_logits(big['variables'], big['batch']['pc'][sel], big['batch']['one_hot'][sel], glog, seed=11)
-        # the Philox key of a frustum is (seed, frustum index in the batch): re-run the sample as its own batch on the GPU
+        # (2) downstream of the GPU's own logits: identical masks -> identical resampled indices, outputs within tolerance.
+        # The Philox key of a frustum is (seed, frustum index in the batch), so the sample is re-run as its own batch on the
+        # GPU and the oracle continues from THAT run's logits (its gbias GEMM has 48 rows -> another kernel than the big
+        # batch's, i.e. logits equal to ~1e-7 relative, not bit for bit).
         eps = fpn.get_model(big['pc'][sel].contiguous(), big['oh'][sel].contiguous(), False)
+        slog = eps['mask_logits'].cpu().numpy()
+        assert float(np.abs(slog - glog).max()) <= (2e-4 if mode == 'f16x2' else 5e-2) * float(np.abs(glog).mean())
+        oep = oracle_cfg3_from_logits(big['variables'], big['batch']['pc'][sel], big['batch']['one_hot'][sel], slog, seed=11)
         assert np.array_equal(eps['object_pc_indices'].cpu().numpy(), oep['object_pc_indices'])
         for k in ('stage1_center', 'center', 'heading_scores', 'heading_residuals', 'size_scores', 'size_residuals'):
-            check_mode(mode, eps[k], oep[k], 'cfg3 ' + k, bf16_frac=0.97)
+            check_mode(mode, eps[k], oep[k], 'cfg3 ' + k, bf16_frac=0.99)
         # (3) the big batch against four batches of 256: bit for bit on everything the fused kernels produce
         for q in range(4):
             sl = slice(q * 256, (q + 1) * 256)
@@ -179,5 +186,5 @@ def test_cfg1_session_batch_32(mode, built_lib):
     gmask = (gl[..., 0] < gl[..., 1]).astype(np.float32)
     _, oep = oracle_model_F(variables, batch, FLAGS, oracle_mask=gmask)
     for k in fetch[1:]:
-        check_mode(mode, got[k], oep[k], 'cfg1 ' + k, bf16_frac=0.97)
+        check_mode(mode, got[k], oep[k], 'cfg1 ' + k, bf16_frac=0.99)
     rt.set_default_store(None)

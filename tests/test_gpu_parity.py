@@ -148,6 +148,36 @@ def test_head_kernels_vs_oracle(built_lib, setup):
     assert_close(rep.cpu().numpy(), orep.numpy(), 1e-5, 1e-5, 'boxpc rep')
 
 
+def test_box3d_corners_helper_vs_oracle(built_lib):
+    """a21 model_util.get_box3d_corners_helper (model_util.py:94-119) on the GPU against the oracle and a closed form"""
+    from oracle import model_util as omu
+    g = torch.Generator().manual_seed(21)
+    n = 301
+    centers = torch.randn(n, 3, generator=g) * 3
+    headings = (torch.rand(n, generator=g) * 2 - 1) * 3.14159
+    sizes = torch.rand(n, 3, generator=g) * 2 + 0.1
+    headings[0] = 0.0
+    got = mu.get_box3d_corners_helper(centers.to(DEV), headings.to(DEV), sizes.to(DEV)).cpu()
+    ref = omu.get_box3d_corners_helper(centers.double(), headings.double(), sizes.double())
+    assert got.shape == (n, 8, 3)
+    assert_close(got.numpy(), ref.numpy(), 1e-5, 1e-5, 'corners helper')
+    # heading 0: corner 0 = centre + (l/2, h/2, w/2), corner 6 = centre - (l/2, h/2, w/2)   (sizes are (l, w, h))
+    l, w, h = sizes[0]
+    assert_close(got[0, 0].numpy(), (centers[0] + torch.stack([l / 2, h / 2, w / 2])).numpy(), 1e-6, 1e-6, 'corner 0')
+    assert_close(got[0, 6].numpy(), (centers[0] - torch.stack([l / 2, h / 2, w / 2])).numpy(), 1e-6, 1e-6, 'corner 6')
+
+
+def test_tf_normalize_2D_bboxes(built_lib):
+    """a31 tf_util.tf_normalize_2D_bboxes (tf_util.py:466-484): [l/cols, t/rows, r/cols, b/rows], img_dim = (rows, cols)"""
+    from oracle import tf_util as otu
+    box = torch.tensor([[64., 48., 320., 240.], [0., 0., 730., 530.], [10.5, 20.25, 30.75, 40.]])
+    dim = torch.tensor([[480., 640.], [530., 730.], [427., 561.]])
+    got = tu.tf_normalize_2D_bboxes(box.to(DEV), dim.to(DEV)).cpu()
+    assert torch.equal(got, otu.tf_normalize_2D_bboxes(box, dim))
+    assert torch.equal(got[0], torch.tensor([0.1, 0.1, 0.5, 0.5]))
+    assert torch.equal(got[1], torch.tensor([0., 0., 1., 1.]))
+
+
 # ------------------------------------------------------------------------------------------ model F
 
 def test_model_F_fp32_mode_vs_oracle(built_lib, setup):
@@ -155,12 +185,14 @@ def test_model_F_fp32_mode_vs_oracle(built_lib, setup):
         logits, ep = ts.build_graph(setup['FLAGS'], setup['pc'], setup['oh'])
     scale_close(logits, setup['ologits'], 1e-4, 'logits')
     # the mask is a strict compare of two fp32 logits: allow the rare 1-ulp flip, then compare downstream
-    agree = ((logits[..., 0] < logits[..., 1]).cpu() == (setup['ologits'][..., 0] < setup['ologits'][..., 1])).float().mean()
+    gmask = (logits[..., 0] < logits[..., 1]).float().cpu()
+    agree = (gmask == (setup['ologits'][..., 0] < setup['ologits'][..., 1]).float()).float().mean()
     assert agree > 0.9995
-    if agree == 1.0:
-        for k in ('stage1_center', 'feats_lv1', 'F_center', 'F_heading_scores', 'F_heading_residuals', 'F_size_scores',
-                  'F_size_residuals', 'F2_center', 'F2_heading_residuals', 'F2_size_residuals', 'boxpc_fit_prob'):
-            scale_close(ep[k], setup['oep'][k], 2e-4, k)
+    # everything downstream against the oracle continued from the GPU's own mask (the reference's oracle_mask input)
+    _, oep = oracle_model_F(setup['variables'], setup['batch'], setup['FLAGS'], oracle_mask=gmask.numpy())
+    for k in ('stage1_center', 'feats_lv1', 'F_center', 'F_heading_scores', 'F_heading_residuals', 'F_size_scores',
+              'F_size_residuals', 'F2_center', 'F2_heading_residuals', 'F2_size_residuals', 'boxpc_fit_prob'):
+        scale_close(ep[k], oep[k], 2e-4, k)
 
 
 @pytest.mark.parametrize('mode,tol', [('fp32', 2e-4), ('bf16', None)])
@@ -250,9 +282,14 @@ def test_inference_runner_matches_oracle_runner(built_lib, setup):
     ores = ots.inference(VarStore(setup['variables']), FLAGS, b['pc'], b['one_hot'], 2, prefix='F2_', use_boxpc_fit_prob=True)
     assert (res[0] == ores[0]).mean() > 0.9995                      # pred_seg
     assert np.array_equal(res[2], ores[2]) and np.array_equal(res[4], ores[4])
-    if (res[0] == ores[0]).all():
-        assert_close(res[1], ores[1], 1e-3, 1e-3, 'centers')
-        assert_close(res[6], ores[6], 1e-3, 1e-3, 'scores')
+    # frustums whose mask equals the oracle's bit for bit (a 1-ulp logit tie may flip a point in the others): at least 3
+    # of the 4, and on those everything the runner returns agrees
+    ok = (res[0] == ores[0]).all(axis=1)
+    assert ok.sum() >= 3, ok
+    assert_close(res[1][ok], ores[1][ok], 1e-3, 1e-3, 'centers')
+    assert_close(res[3][ok], ores[3][ok], 1e-3, 1e-3, 'orient_reg')
+    assert_close(res[5][ok], ores[5][ok], 1e-3, 1e-3, 'dims_reg')
+    assert_close(res[6][ok], ores[6][ok], 1e-3, 1e-3, 'scores')
 
 
 def test_tf_util_max_pool2d(built_lib):

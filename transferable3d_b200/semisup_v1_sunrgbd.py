@@ -201,9 +201,10 @@ def get_semi_loss(pred, labels, end_points, reduce_loss=True, c=None):
     raise Exception('Not implemented SEMI_MODEL: %s' % c.SEMI_MODEL)
 
 
-def get_strong_loss(pred, labels, end_points, prefix='', reduce_loss=True, c=None):
+def get_strong_loss(pred, labels, end_points, prefix='', reg_weight=0.001, reduce_loss=True, c=None):
     """semisup_v1_sunrgbd.py:423-553 -> per-sample (mask_losses, box_losses), both (B,) (their means if reduce_loss).
-    The head output is read from end_points['F_output'] (prefix 'F_') or end_points['box_params'] (prefix '')."""
+    The head output is read from end_points['F_output'] (prefix 'F_') or end_points['box_params'] (prefix '').
+    `reg_weight` keeps the reference's positional signature; the reference body never reads it either."""
     from . import losses
     from .config import cfg as _cfg
     pred_seg = rt.f32(pred[0])

@@ -39,8 +39,9 @@ def build_graph(FLAGS, pc, one_hot_vec, box2D=None, img_dim=None, oracle_mask=No
         with rt.variable_scope('D_boxpc_branch'):
             _, ep = boxpc_sunrgbd.get_model((box_in, fake_pc), False, one_hot_vec=one_hot_vec, use_one_hot_vec=False,
                                             c=FLAGS,
-                                            _refine=dict(curr_box=curr_box, totals=totals,
-                                                         weigh_during_test=FLAGS.SEMI_WEIGH_BOXPC_DELTA_DURING_TEST))
+                                            # the test graph forces SEMI_WEIGH_BOXPC_DELTA_DURING_TEST = False whatever the
+                                            # training configuration says (reference test_semisup.py:86)
+                                            _refine=dict(curr_box=curr_box, totals=totals, weigh_during_test=False))
         boxpc_fit_prob = ep['logits_for_weigh']
         for k in ('boxpc_delta_center', 'boxpc_delta_size', 'boxpc_delta_angle', 'boxpc_feats_dict', 'pred_boxpc_fit',
                   'boxpc_fit_logits'):
@@ -110,13 +111,25 @@ class Session(object):
                 self._om.copy_(om)
             self._graph.replay()
             # the graph's outputs are static buffers, overwritten by the next run(): hand out copies (sess.run returns values)
-            return [self._ep[f].clone() if isinstance(f, str) else f for f in fetches]
+            return [_clone_value(self._ep[f]) if isinstance(f, str) else f for f in fetches]
         with torch.no_grad():
             logits, ep = build_graph(self.FLAGS, pc, one_hot, oracle_mask=om)
         out = []
         for f in fetches:
             out.append(ep[f] if isinstance(f, str) else f)
         return out
+
+
+def _clone_value(v):
+    """Copy of an end point out of the graph's static buffers: tensors, and the tuple / dict / None end points
+    ('F_pred_box_reg', 'boxpc_feats_dict', 'boxpc_fit_prob' with refine = 0) the eager path returns as they are."""
+    if torch.is_tensor(v):
+        return v.clone()
+    if isinstance(v, (tuple, list)):
+        return type(v)(_clone_value(x) for x in v)
+    if isinstance(v, dict):
+        return {k: _clone_value(x) for k, x in v.items()}
+    return v
 
 
 def get_model(batch_size, num_point, num_channel, FLAGS, variables, use_oracle_mask=False, device='cuda', cuda_graph=True):
