@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 TOTAL_FRUSTUMS = {'cfg3': 8192, 'cfg2': 1024, 'cfg1': 32, 'cfg4': 256, 'cfg5': 256}
 N_POINTS, N_CH = 2048, 6
-UNIQUE = 512            # unique synthetic frustums generated on the host, tiled to the workload size
+UNIQUE = 8192           # unique synthetic frustums generated on the host, tiled to the workload size
 # algorithmic FLOPs (2*MAC) per point, SURVEY 8(d) / DESIGN.md
 FLOP_SEG1_PT = 295680
 FLOP_SEG2_PT = 426496
@@ -136,14 +136,22 @@ class ClockSampler(object):
                 'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi -lms 200'}
 
 
-def make_host_data(workload, n_local, seed):
+def make_host_data(workload, n_local, seed, wire=False):
+    """Synthetic frustums of the workload.  Colours are quantised to 8 bits, rgb = float32(k) / 255 -- what im2double of an
+    8-bit image gives in the prepared SUN-RGBD frustums -- so that the e2e wire format (xyz fp32 + rgb uint8) and the
+    fp32 (B,N,6) placeholder hold bit-identical values.  wire=True also returns (xyz [n,N,3] fp32, rgb [n,N,3] uint8)."""
     from transferable3d_b200 import synth
     u = min(UNIQUE, n_local)
     b = synth.make_batch(u, N_POINTS, N_CH, seed=seed)
+    k = np.clip(np.rint(b['pc'][:, :, 3:6] * 255.0), 0, 255).astype(np.uint8)
+    pc_u = b['pc'].copy()
+    pc_u[:, :, 3:6] = k.astype(np.float32) / np.float32(255)
     reps = (n_local + u - 1) // u
-    pc = np.tile(b['pc'], (reps, 1, 1))[:n_local]
-    oh = np.tile(b['one_hot'], (reps, 1))[:n_local]
-    return np.ascontiguousarray(pc), np.ascontiguousarray(oh)
+    pc = np.ascontiguousarray(np.tile(pc_u, (reps, 1, 1))[:n_local])
+    oh = np.ascontiguousarray(np.tile(b['one_hot'], (reps, 1))[:n_local])
+    if not wire:
+        return pc, oh
+    return pc, oh, np.ascontiguousarray(pc[:, :, 0:3]), np.ascontiguousarray(np.tile(k, (reps, 1, 1))[:n_local])
 
 
 def standard_variables(workload):
@@ -170,6 +178,7 @@ def run_reference(args):
         from oracle import train_boxpc as otb, train_semisup_adv as ota
         sample = 8
         v2, feed2, masks2, FLAGS2 = train_setup(workload, sample, N_POINTS, 77)
+        feed2 = {k: a for k, a in feed2.items() if k != '_2d'}
         fn = otb.loss_and_grads if workload == 'cfg4' else ota.loss_and_grads
 
         def step():
@@ -212,29 +221,9 @@ def run_reference(args):
 
 
 def oracle_cfg3(vs, pc_t, oh_t, seed=5):
-    """SURVEY 3.2 pipeline on the oracle (model-A variable names)."""
-    import torch
-    from oracle import semisup_models as osm, model_util as omu
-    from oracle.tf_layers import conv2d, fully_connected, max_pool_points
-    from transferable3d_b200.constants import MEAN_DIMS_ARR
-    ep = {}
-    logits = osm.v1_inst_seg(pc_t, None, oh_t, ep, False, vs, scope='inst_seg')
-    obj, mean, ep = omu.point_cloud_masking(pc_t, logits, ep, rng_mode='philox', seed=seed)
-    with vs.variable_scope('tnet'):
-        delta, _ = omu.get_center_regression_net(obj, oh_t, False, None, ep, vs)
-    s1 = delta + mean
-    with vs.variable_scope('box_est'):
-        net = obj - delta.unsqueeze(1)
-        for nm, c in (('conv-reg1', 128), ('conv-reg2', 128), ('conv-reg3', 256), ('conv-reg4', 512)):
-            net = conv2d(net, c, [1, 1], vs, nm, True, False)
-        net = torch.cat([max_pool_points(net), oh_t], dim=1)
-        net = fully_connected(net, 512, vs, 'fc1', True, False)
-        net = fully_connected(net, 256, vs, 'fc2', True, False)
-        out = fully_connected(net, 67, vs, 'fc3', activation_fn=None)
-    ep = omu.parse_output_to_tensors(out, ep, 12, MEAN_DIMS_ARR)
-    ep['center'] = ep['center_boxnet'] + s1
-    ep['mask_logits'] = logits
-    return ep
+    """SURVEY 3.2 pipeline on the oracle (model-A variable names): oracle/frustum_pointnets_v1.py."""
+    from oracle import frustum_pointnets_v1 as ofpn
+    return ofpn.get_model(vs, pc_t, oh_t, seed=seed)
 
 
 def workload_config(workload, args, sample_note=None):
@@ -248,8 +237,10 @@ def workload_config(workload, args, sample_note=None):
          'global_frustums': TOTAL_FRUSTUMS[workload] * (1 if (workload == 'cfg3' and args.scaling == 'strong') else args.gpus),
          'frustums_per_gpu': TOTAL_FRUSTUMS[workload] // (args.gpus if (workload == 'cfg3' and args.scaling == 'strong') else 1),
          'num_point': N_POINTS, 'num_channel': N_CH, 'chunk_frustums': args.resident_chunk, 'e2e_chunk_frustums': args.chunk, 'parallelism': 'shard%d' % args.gpus,
-         'precision': 'bf16 operands / fp32 accumulate (tcgen05), fp32 heads',
+         'precision': {'bf16': 'bf16 operands / fp32 accumulate (tcgen05), fp32 heads',
+                       'f16x2': 'fp16 hi + lo operand pairs, 3 tcgen05 products per layer, fp32 accumulate (fp32-accurate), fp32 heads'}[getattr(args, 'precision', 'bf16')],
          'weights': 'synthetic Xavier (seed 42), seg logits calibrated (margin std 2.0, 40% masked-in)',
+         'frustums': '%d unique synthetic frustums per rank, colours quantised to 8 bit (k / 255)' % UNIQUE,
          'resample_rng': 'philox', 'l2': 'per-step inputs (>= 400 MB per GPU at N=1) exceed the 126 MB L2; no explicit flush'}
     if sample_note:
         c['sample'] = sample_note
@@ -343,7 +334,14 @@ def train_setup(workload, B, N, seed):
         masks = {'dp1': (rng.rand(B, 512) < 0.7).astype(np.float32), 'dp2': (rng.rand(B, 256) < 0.7).astype(np.float32)}
         return v, feed, masks, config.cfg(BOXPC_WEIGHT_DELTA=4.)
     v = weights.make_weights_model_F()
-    feed = synth.make_batch(B, N, N_CH, seed=seed, is_data_2D=(np.arange(B) % 2))
+    # pure batches alternating 3D-labelled / 2D-only (ALTERNATE_BATCH, train_semisup_adv.py:539-565); 2D batches
+    # carry all-zero 3D labels (roi_semi_dataset.py:452-454).  `feed` is the 3D batch, feed['_2d'] the 2D one.
+    feed = synth.make_batch(B, N, N_CH, seed=seed, is_data_2D=0)
+    feed2 = synth.make_batch(B, N, N_CH, seed=seed + 1, is_data_2D=1)
+    for k in ('labels', 'centers', 'y_orient_cls', 'y_orient_reg', 'y_dims_cls', 'y_dims_reg'):
+        if k in feed2:
+            feed2[k] = np.zeros_like(feed2[k])
+    feed['_2d'] = feed2
     masks = {'class_agnostic/inst_seg/dp1': (rng.rand(B, N, 128) < 0.5).astype(np.float32),
              'class_dependent/box_refine/dp0': (rng.rand(B, 512) < 0.5).astype(np.float32),
              'class_dependent/box_refine/dp1': (rng.rand(B, 256) < 0.5).astype(np.float32)}
@@ -373,17 +371,22 @@ def run_train(args):
         from transferable3d_b200.dist_util import broadcast_params
         broadcast_params(g.flat_param if workload == 'cfg4' else g.arena.flat_param)
     D = lambda a: torch.as_tensor(np.asarray(a)).to(dev)
-    feed_d = {k: D(a) for k, a in feed.items()}
+    feeds_h = [feed]
+    if '_2d' in feed:                              # cfg5: alternate the pure 3D batch and the pure 2D batch
+        feeds_h = [{k: a for k, a in feed.items() if k != '_2d'}, feed['_2d']]
+    feeds_d = [{k: D(a) for k, a in f.items()} for f in feeds_h]
     masks_d = {k: D(a) for k, a in masks.items()}
     loss_key = 'loss' if workload == 'cfg4' else 'semi_loss'
-    losses = []
+    losses, nstep = [], {'n': 0}
 
     def step_resident():
-        out = g.step(feed_d, masks_d)
+        out = g.step(feeds_d[nstep['n'] % len(feeds_d)], masks_d)
+        nstep['n'] += 1
         losses.append(out[loss_key])
 
     def step_e2e():
-        out = g.step(feed, masks_d)                 # numpy batch -> device inside the step; dropout masks are device RNG state
+        out = g.step(feeds_h[nstep['n'] % len(feeds_h)], masks_d)   # numpy batch -> device inside the step; dropout masks are device state
+        nstep['n'] += 1
         losses.append(float(out[loss_key].reshape(-1)[0]))
 
     def timed(fn, sample_clocks=False):
@@ -412,10 +415,48 @@ def run_train(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms, clocks
+    from transferable3d_b200 import _lib as _l, train_layers as _tl, losses as _ls
+    import transferable3d_b200.tf_util as _tu
+    launches = {'n': 0, 'on': False}
+    _orig = _l.call
+
+    def _counting(name, *a):
+        if launches['on']:
+            launches['n'] += 1
+        return _orig(name, *a)
+    for mod in (_l, _tl, _ls, _tu, tb, tsa, rt):
+        if hasattr(mod, 'call'):
+            mod.call = _counting
     ms, clocks = timed(step_resident, True)
+    launches['on'] = True
+    step_resident()                                   # C-ABI calls of one step (each launches >= 1 kernel of this library)
+    torch.cuda.synchronize()
+    launches['on'] = False
+    n_launch = launches['n']
     first, last = float(losses[0].reshape(-1)[0]), float(losses[-1].reshape(-1)[0])
     ms_e2e, _ = timed(step_e2e)
-    h2d = sum(np.asarray(a).nbytes for a in feed.values())
+    h2d = sum(np.asarray(a).nbytes for a in feeds_h[0].values())
+    # algorithmic FLOPs of one step (2 x MAC; SURVEY 8(d): dgrad = wgrad = forward MACs per trained layer, forward only for
+    # frozen layers, no dgrad into data).  Per-point / per-frustum MAC counts of the layer tables.
+    P = N
+    if workload == 'cfg4':      # BoxPC net: conv 12-128-128-256-512 + fc 512-512-256-9, all trained, no dgrad for conv1
+        macs_fr = 3 * (181760 * P + 395520) - 12 * 128 * P
+    else:                       # seg forward (frozen, conv6 folded) + T-Net and box convs trained (box FC head forward only)
+        seg = 361088 * P + 1024 * 512                                  # conv1-5, conv6' (K = 64), conv7-10 per point + global half
+        tnet = 3 * (49536 * P + 98688) - 3 * 128 * P                    # no dgrad into the points
+        box = 3 * (180608 * P) + 410368                                 # conv1 dgrad feeds stage1_center
+        refine = 3 * 415488
+        boxpc = 2 * (181760 * P + 395520)                               # frozen branch: forward + dgrad to the box
+        macs_fr = seg + tnet + box + refine + boxpc
+    step_flops = 2.0 * macs_fr * B
+    pk = peaks()
+    roof = {'kernel': 'whole training step (tcgen05 bf16 x 3 GEMMs + BN / pooling / loss / Adam kernels)', 'bound': 'tensor',
+            'achieved': step_flops / (ms * 1e-3) / 1e12, 'peak': pk['bf16_burst'], 'unit': 'TFLOP/s',
+            'frac': step_flops / (ms * 1e-3) / 1e12 / pk['bf16_burst'], 'traffic': None,
+            'algorithmic_flops_per_step': step_flops,
+            'note': 'fp32-accurate GEMMs issue 6 bf16 tensor-core products per MAC (engine tc); the step is bound by the fp32 '
+                    'activation traffic of the batch-norm passes, not by the tensor pipe (DESIGN.md section 5)',
+            'peak_source': '%s, burst bf16' % pk['src']}
     nparam = int((g.flat_param if workload == 'cfg4' else g.arena.flat_param).numel())
     line = {'metric': 'frustums_per_sec', 'value': B * world / ms * 1e3, 'unit': 'frustums/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -433,13 +474,14 @@ def run_train(args):
                        'l2': 'activations of one step (> 2 GB) exceed the 126 MB L2'},
             'clocks': clocks, 'e2e': {'value': B * world / ms_e2e * 1e3, 'unit': 'frustums/s', 'h2d_bytes_per_step': h2d,
                                       'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e},
-            'loss_first_step': first, 'loss_last_step': last, 'gpu_launches': None, 'roofline': None}
+            'loss_first_step': first, 'loss_last_step': last, 'gpu_launches': n_launch, 'roofline': roof}
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             from oracle import train_boxpc as otb, train_semisup_adv as ota
             torch.set_num_threads(os.cpu_count() or 1)
             Bs = 8
             v2, feed2, masks2, FLAGS2 = train_setup(workload, Bs, N, 77)
+            feed2 = {k: a for k, a in feed2.items() if k != '_2d'}
             fn = otb.loss_and_grads if workload == 'cfg4' else ota.loss_and_grads
             fn(v2, FLAGS2, feed2, masks2)
             t0, reps = time.perf_counter(), 0
@@ -472,7 +514,12 @@ def main():
     ap.add_argument('--f32-engine', default='tc', choices=['tc', 'simt', 'bf16'],
                     help='GEMM engine of the training workloads (cfg4 / cfg5): tc = tcgen05 bf16 x 3 split (fp32-accurate), '
                          'simt = CUDA-core SGEMM, bf16 = one tcgen05 pass on bf16-rounded operands')
-    ap.add_argument('--ref-sample', type=int, default=8)
+    ap.add_argument('--ref-sample', type=int, default=32, help='frustums per step of the reference (CPU) arm')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'f16x2'],
+                    help='mode of the headline line: bf16 = one tensor-core product per MAC; f16x2 = fp16 hi / lo split, three products, '
+                         'fp32-accurate (the mode that meets the mask-exactness target); the other one is reported under exact_mode')
+    ap.add_argument('--no-exact-mode', action='store_true', help='skip the f16x2 leg of the line')
+    ap.add_argument('--no-parity', action='store_true', help='skip the oracle spot-check of the timed batch')
     ap.add_argument('--cpu-sample', type=int, default=8)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--breakdown', action='store_true', help='per-entry-point CUDA-event times of the resident step (stderr)')
@@ -514,22 +561,20 @@ def main():
     variables, winfo = standard_variables(workload)
     store = rt.VariableStore(variables, dev)
     rt.set_default_store(store)
-    rt.set_precision('bf16')
+    rt.set_precision(args.precision)
     mu.set_resample_rng('philox', seed=5)
-    pc_h, oh_h = make_host_data(workload, n_local, 1234 + (3 if workload == 'cfg3' else 2))
-    pc_pin = torch.from_numpy(pc_h).pin_memory()
-    oh_pin = torch.from_numpy(oh_h).pin_memory()
-    pc_dev, oh_dev = pc_pin.to(dev), oh_pin.to(dev)
+    numa = bind_numa_local(local)
+    pc_h, oh_h, xyz_h, rgb_h = make_host_data(workload, n_local, 1234 + (3 if workload == 'cfg3' else 2), wire=True)
+    xyz_pin, rgb_pin, oh_pin = torch.from_numpy(xyz_h).pin_memory(), torch.from_numpy(rgb_h).pin_memory(), torch.from_numpy(oh_h).pin_memory()
+    pc_dev, oh_dev = torch.from_numpy(pc_h).to(dev), oh_pin.to(dev)
 
-    # launch counting + per-kernel timing of the dominant kernel (CUDA events on the launching stream)
+    # launch counting + per-kernel timing of the two dominant kernels (CUDA events on the launching stream)
     launches = {'n': 0}
-    KERNELS_PER_CALL = {'t3d_chain_max_bf16': 1, 't3d_seg_stage2_bf16': 1, 't3d_linear_f32': 1, 't3d_mask_centroid': 1,
-                        't3d_resample': 1, 't3d_build_tiles': 1, 't3d_parse_box': 1, 't3d_prepare_xyz': 1,
-                        't3d_boxpc_features': 1, 't3d_anchor_to_reg': 1, 't3d_boxpc_refine': 1, 't3d_f2': 1,
-                        't3d_box3d_corners_helper': 1, 't3d_box3d_corners_all': 1}
-    dom = {'events': [], 'events_mp': [], 'on': False}
+    KERNELS_PER_CALL = {'t3d_chain_max_bf16': 1, 't3d_seg_stage2_bf16': 1, 't3d_chain_max_x2': 1, 't3d_seg_stage2_x2': 1,
+                        't3d_linear_f32': 1, 't3d_mask_centroid': 1, 't3d_resample': 1, 't3d_build_tiles': 1, 't3d_parse_box': 1,
+                        't3d_prepare_xyz': 1, 't3d_assemble_points': 1}
+    dom = {'seg2': [], 'seg1': [], 'on': False}
     orig_call = _lib.call
-
     bd = {'on': False, 'ev': []}
 
     def counting_call(name, *a):
@@ -541,50 +586,58 @@ def main():
             e0.record()
             orig_call(name, *a)
             e1.record()
-            bd['ev'].append((name + (':%d' % a[0] if name == 't3d_chain_max_bf16' else ''), e0, e1))
+            bd['ev'].append((name + (':%d' % a[0] if name.startswith('t3d_chain_max') else ''), e0, e1))
             return
-        is_seg2 = name == 't3d_seg_stage2_bf16'
-        is_seg1 = name == 't3d_chain_max_bf16' and a[0] == 0
+        is_seg2 = name in ('t3d_seg_stage2_bf16', 't3d_seg_stage2_x2')
+        is_seg1 = name in ('t3d_chain_max_bf16', 't3d_chain_max_x2') and a[0] == 0
         if dom['on'] and (is_seg2 or is_seg1):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             orig_call(name, *a)
             e1.record()
-            dom['events' if is_seg2 else 'events_mp'].append((e0, e1))
+            dom['seg2' if is_seg2 else 'seg1'].append((e0, e1))
         else:
             orig_call(name, *a)
-    for mod in (rt, sm, mu, _lib):
-        if hasattr(mod, 'call'):
-            mod.call = counting_call
     import transferable3d_b200.tf_util as tu
     import transferable3d_b200.boxpc_sunrgbd as bp
     import transferable3d_b200.test_semisup as ts
-    for mod in (tu, bp, ts):
-        mod.call = counting_call
+    for mod in (rt, sm, mu, _lib, tu, bp, ts):
+        if hasattr(mod, 'call'):
+            mod.call = counting_call
 
     def pipeline(pc, oh):
         if workload == 'cfg3':
             return fpn.get_model(pc, oh, False)
         return {'mask_logits': sm.v1_inst_seg(pc, None, None, {}, False, scope='class_agnostic/inst_seg')}
 
-    OUT_KEYS = ('mask_logits', 'center', 'heading_scores', 'heading_residuals', 'size_scores', 'size_residuals') \
-        if workload == 'cfg3' else ('mask_logits',)
-
     def step_resident():
         with torch.no_grad():
             for c0 in range(0, n_local, rchunk):
                 pipeline(pc_dev[c0:c0 + rchunk], oh_dev[c0:c0 + rchunk])
 
-    # e2e: double-buffered H2D / compute / D2H.  Inputs land in two preallocated device buffers (copy stream), the
-    # pipeline runs on the compute stream, its results are packed into two preallocated device staging sets on the
-    # compute stream (D2D, ~0.05 ms) and leave for pinned host memory on a third stream -- no allocation and no
-    # record_stream inside the timed region.
+    # e2e through the public API a user calls: host wire format (xyz fp32 + rgb uint8 + one-hot, pinned) -> H2D ->
+    # model_util.assemble_point_cloud -> frustum_pointnets_v1.inference (pipeline + the reference's test-time
+    # post-processing on the device) -> D2H of the prediction (pred_seg bytes + 10 numbers per frustum).  Double-buffered:
+    # inputs land in two preallocated device buffer sets (copy stream), the pipeline runs on the compute stream, results are
+    # packed into two preallocated staging sets (D2D) and leave for pinned host memory on a third stream -- no allocation
+    # and no record_stream inside the timed region.  cfg2 (seg chain alone) returns the raw mask logits.
+    OUT_KEYS = ('pred_seg', 'center', 'heading_cls', 'heading_res', 'size_cls', 'size_res', 'scores') if workload == 'cfg3' else ('mask_logits',)
     copy_s, back_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    in_bufs = [(torch.empty((chunk, N_POINTS, N_CH), device=dev), torch.empty((chunk, 10), device=dev)) for _ in range(2)]
+    in_bufs = [(torch.empty((chunk, N_POINTS, 3), device=dev), torch.empty((chunk, N_POINTS, 3), dtype=torch.uint8, device=dev),
+                torch.empty((chunk, 10), device=dev), torch.empty((chunk, N_POINTS, N_CH), device=dev)) for _ in range(2)]
+    in_bytes = sum(t.numel() * t.element_size() for t in in_bufs[0][:3])
     stage_out, host_out = [{}, {}], [{}, {}]
     bytes_io = {'h2d': 0, 'd2h': 0}
     # the next step's first H2D is issued under this step's last chunk; D2H copies drain under the next step's compute
     carry = {'ready0': None, 'consumed': [None, None], 'drained': [None, None]}
+
+    def e2e_pipeline(s):
+        xyz, rgb, oh, pc6 = in_bufs[s]
+        mu.assemble_point_cloud(xyz, rgb, out=pc6)
+        if workload == 'cfg3':
+            launches['n'] += 1                      # t3d_inference_scores (bound outside _lib.call)
+            return fpn.inference(pc6, oh)
+        return pipeline(pc6, oh)
 
     def step_e2e():
         comp = torch.cuda.current_stream()
@@ -599,15 +652,17 @@ def main():
             with torch.cuda.stream(copy_s):
                 if consumed[s] is not None:
                     copy_s.wait_event(consumed[s])
-                in_bufs[s][0].copy_(pc_pin[i * chunk:(i + 1) * chunk], non_blocking=True)
-                in_bufs[s][1].copy_(oh_pin[i * chunk:(i + 1) * chunk], non_blocking=True)
+                sl = slice(i * chunk, (i + 1) * chunk)
+                in_bufs[s][0].copy_(xyz_pin[sl], non_blocking=True)
+                in_bufs[s][1].copy_(rgb_pin[sl], non_blocking=True)
+                in_bufs[s][2].copy_(oh_pin[sl], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_s)
                 ready[s] = ev
-            bytes_io['h2d'] += in_bufs[s][0].numel() * 4 + in_bufs[s][1].numel() * 4
+            bytes_io['h2d'] += in_bytes
         if carry['ready0'] is not None:
             ready[0] = carry['ready0']      # prefetched by the previous step (same rotation of input buffers)
-            bytes_io['h2d'] += in_bufs[0][0].numel() * 4 + in_bufs[0][1].numel() * 4
+            bytes_io['h2d'] += in_bytes
             carry['ready0'] = None
         else:
             issue_copy(0)
@@ -622,7 +677,7 @@ def main():
                     bytes_io['h2d'] = h2d
                     carry['ready0'] = ready[0]
                 comp.wait_event(ready[s])
-                ep = pipeline(in_bufs[s][0], in_bufs[s][1])
+                ep = e2e_pipeline(s)
                 ev = torch.cuda.Event()
                 ev.record(comp)
                 consumed[s] = ev
@@ -682,11 +737,57 @@ def main():
             ms = float(t.item())
         return ms, launches['n'], clocks
 
-    dom['on'] = True
-    ms, n_launch, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
-    dom['on'] = False
-    dom_ms = [a.elapsed_time(b) for a, b in dom['events'][-(args.steps * (n_local // rchunk)):]]
-    ms_e2e, _, _ = timed(step_e2e, args.steps, args.warmup, finish=e2e_finish)
+    pk = peaks()
+    n_calls = args.steps * (n_local // rchunk)
+
+    def measure_resident(precision):
+        """resident step in `precision`: ms per step, launches, clocks and the rooflines of the two dominant kernels"""
+        rt.set_precision(precision)
+        dom['seg2'], dom['seg1'], dom['on'] = [], [], True
+        ms, n_launch, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+        dom['on'] = False
+        region_s = ms * args.steps * 1e-3
+        # the driver-measured bf16 peak a kernel is held to: the burst figure when the timed region is shorter than the 4 s
+        # sustained-clock measurement window, as here (steps x ~12 ms); the sustained figure rides along
+        peak, peak_name = (pk['bf16_burst'], 'burst') if region_s < 1.0 else (pk['bf16'], 'sustained')
+        products = 3 if precision == 'f16x2' else 1
+        roofs = {}
+        for key, flop_pt, kname, traffic, traffic_alg in (
+                ('seg2', FLOP_SEG2_PT, 'seg_stage2_x2_kernel' if products == 3 else 'seg_stage2_pipe_kernel',
+                 NCU_DRAM_BYTES_FR['seg2'], 262144 + 2048 + 16384),
+                ('seg1', FLOP_SEG1_PT, 'chain_max_x2_kernel<SEG1>' if products == 3 else 'chain_max_kernel<SEG1>',
+                 NCU_DRAM_BYTES_FR['seg1'], 49152 + 262144 + 4096)):
+            t_ms = [a.elapsed_time(b) for a, b in dom[key][-n_calls:]]
+            if not t_ms:
+                continue
+            avg = float(np.mean(t_ms))
+            flops = flop_pt * rchunk * N_POINTS
+            ach = flops / (avg * 1e-3) / 1e12
+            r = {'kernel': kname + (' (conv6..conv10, tcgen05)' if key == 'seg2' else ' (conv1..conv5 + max-pool fused, tcgen05)'),
+                 'bound': 'tensor', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak,
+                 'frac_of_sustained_peak': ach / pk['bf16'], 'frac_of_burst_peak': ach / pk['bf16_burst'],
+                 'avg_launch_ms': avg, 'algorithmic_flops_per_launch': flops,
+                 'peak_source': '%s, %s bf16 (timed region %.2f s)' % (pk['src'], peak_name, region_s)}
+            if products == 1:
+                r.update({'traffic': traffic * rchunk, 'traffic_algorithmic': traffic_alg * rchunk,
+                          'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel at '
+                                            '8192 frustums per launch (profiles/), scaled per frustum; not re-measured in this run'})
+            else:
+                # three tensor-core products per algorithmic MAC (hi.lo + lo.hi + hi.hi): what the tensor pipe executes
+                r.update({'traffic': None, 'executed_tflops': 3 * ach, 'executed_frac_of_peak': 3 * ach / peak,
+                          'note': 'f16x2: fp32-accurate result from 3 fp16 tensor-core products per MAC; achieved / frac count the '
+                                  'algorithmic FLOPs once, executed_* count what the tensor pipe runs'})
+            roofs[key] = r
+        return ms, n_launch, clocks, roofs
+
+    ms, n_launch, clocks, roofs = measure_resident(args.precision)
+    ms_e2e, n_launch_e2e, _ = timed(step_e2e, args.steps, args.warmup, finish=e2e_finish)
+    exact = None
+    if args.precision != 'f16x2' and not args.no_exact_mode:
+        ms_x, _, clocks_x, roofs_x = measure_resident('f16x2')
+        exact = {'precision': 'f16x2', 'value': n_local * world / ms_x * 1e3, 'unit': 'frustums/s', 'ms_per_step': ms_x,
+                 'roofline': roofs_x.get('seg2'), 'roofline_fused_maxpool': roofs_x.get('seg1'), 'clocks': clocks_x}
+        rt.set_precision(args.precision)
 
     if args.breakdown and rank == 0:
         bd['on'] = True
@@ -704,47 +805,109 @@ def main():
     total_units = n_local * world
     value = total_units / ms * 1e3
     e2e_value = total_units / ms_e2e * 1e3
-    pk = peaks()
-    roof = None
-    if dom_ms:
-        avg = float(np.mean(dom_ms))
-        flops = FLOP_SEG2_PT * rchunk * N_POINTS
-        ach = flops / (avg * 1e-3) / 1e12
-        roof = {'kernel': 'seg_stage2_pipe_kernel (conv6..conv10, tcgen05)', 'bound': 'tensor', 'achieved': ach, 'peak': pk['bf16'],
-                'unit': 'TFLOP/s', 'frac': ach / pk['bf16'], 'frac_of_burst_peak': ach / pk['bf16_burst'],
-                'traffic': NCU_DRAM_BYTES_FR['seg2'] * rchunk, 'traffic_algorithmic': (262144 + 2048 + 16384) * rchunk,
-                'traffic_source': 'ncu --set full, profiles/r01_ncu_full_v3_kernels.csv, scaled per frustum', 'avg_launch_ms': avg,
-                'algorithmic_flops_per_launch': flops, 'peak_source': '%s, sustained bf16 (kernel timed inside a long step)' % pk['src']}
-    roof_mp = None
-    mp_ms = [a.elapsed_time(b) for a, b in dom['events_mp'][-(args.steps * (n_local // rchunk)):]]
-    if mp_ms:
-        avg = float(np.mean(mp_ms))
-        flops = FLOP_SEG1_PT * rchunk * N_POINTS
-        ach = flops / (avg * 1e-3) / 1e12
-        roof_mp = {'kernel': 'chain_max_kernel<SEG1> (conv1..conv5 + max-pool fused, tcgen05)', 'bound': 'tensor', 'achieved': ach,
-                   'peak': pk['bf16'], 'unit': 'TFLOP/s', 'frac': ach / pk['bf16'], 'frac_of_burst_peak': ach / pk['bf16_burst'],
-                   'traffic': NCU_DRAM_BYTES_FR['seg1'] * rchunk, 'traffic_algorithmic': (49152 + 262144 + 4096) * rchunk,
-                   'avg_launch_ms': avg, 'algorithmic_flops_per_launch': flops}
     if workload == 'cfg3':
         flops_fr = (FLOP_SEG1_PT + FLOP_SEG2_PT) * N_POINTS + FLOP_SEG_GLOBAL_FR + (FLOP_TNET_PT + FLOP_BOX_PT) * 512 + FLOP_FC_FR
     else:
         flops_fr = (FLOP_SEG1_PT + FLOP_SEG2_PT) * N_POINTS + 2 * 1024 * 512
     line = {'metric': 'frustums_per_sec', 'value': value, 'unit': 'frustums/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
-            'scaling': args.scaling if workload == 'cfg3' else 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'scaling': args.scaling if workload == 'cfg3' else 'weak', 'vs_baseline': None,
+            'dtype': {'bf16': 'bf16', 'f16x2': 'f16 x 2 (fp32-accurate)'}[args.precision], 'data': 'synthetic',
             'config': workload_config(workload, args), 'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'frustums/s', 'h2d_bytes_per_step': bytes_io['h2d'],
-                    'd2h_bytes_per_step': bytes_io['d2h'], 'ms_per_step': ms_e2e},
-            'gpu_launches': n_launch, 'roofline': roof, 'roofline_fused_maxpool': roof_mp,
-            'pipeline_tflops': value * flops_fr / 1e12, 'pipeline_frac_of_bf16_peak': value * flops_fr / 1e12 / (pk['bf16'] * world)}
+                    'd2h_bytes_per_step': bytes_io['d2h'], 'ms_per_step': ms_e2e, 'gpu_launches': n_launch_e2e,
+                    'host_gbps_all_ranks': (bytes_io['h2d'] + bytes_io['d2h']) * world / (ms_e2e * 1e-3) / 1e9,
+                    'wire_format': 'in: xyz fp32 + rgb uint8 + one-hot fp32 (pinned); out: pred_seg uint8 + centre / heading / size / score'
+                                   if workload == 'cfg3' else 'in: xyz fp32 + rgb uint8; out: raw mask logits fp32', 'numa': numa},
+            'gpu_launches': n_launch, 'roofline': roofs.get('seg2'), 'roofline_fused_maxpool': roofs.get('seg1'),
+            'pipeline_tflops': value * flops_fr / 1e12, 'pipeline_frac_of_bf16_peak': value * flops_fr / 1e12 / (pk['bf16_burst'] * world),
+            'exact_mode': exact}
 
     if rank == 0:
+        if not args.no_parity:
+            line['parity'] = {args.precision: parity_block(workload, variables, pc_h, oh_h, pc_dev, oh_dev, rchunk, args.precision)}
+            if exact is not None:
+                line['parity']['f16x2'] = parity_block(workload, variables, pc_h, oh_h, pc_dev, oh_dev, rchunk, 'f16x2')
         if not args.no_cpu_baseline and world == 1:
             line['cpu_baseline'] = cpu_baseline(workload, variables, args.cpu_sample)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bind_numa_local(local_rank):
+    """Pin this rank to the CPUs NVML reports as local to its GPU BEFORE the pinned host buffers are allocated (first touch
+    puts them on that NUMA node).  Returns what was done, for the bench line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = int(vis.split(',')[local_rank]) if vis and all(x.strip().isdigit() for x in vis.split(',')) else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        node = None
+        try:
+            node = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            pass
+        return {'gpu': phys, 'cpus_local_to_gpu': '%d-%d (%d)' % (min(allowed), max(allowed), len(allowed)) if allowed else None,
+                'numa_node': node}
+    except Exception as e:      # NVML missing: leave the affinity alone
+        return {'error': str(e)[:80]}
+
+
+def parity_block(workload, variables, pc_h, oh_h, pc_dev, oh_dev, rchunk, precision, n_sample=16):
+    """Checker leg (not timed): 16 frustums sampled from the timed batch against the oracle.  Seg logits and masks first;
+    then, with the oracle continued from the GPU's own logits (identical masks, identical resampled indices), every box
+    output.  The sample is re-run as its own batch (the Philox key of the resample is (seed, index in the batch)) and
+    tied to the timed batch by comparing its logits with the big batch's."""
+    import torch
+    from oracle.tf_layers import VarStore
+    from transferable3d_b200 import runtime as rt, frustum_pointnets_v1 as fpn, semisup_models as sm
+    sel = np.sort(np.random.RandomState(7).permutation(rchunk)[:n_sample])
+    torch.set_num_threads(os.cpu_count() or 1)
+    vs = VarStore(variables)
+    vs.literal = True
+    pc_t, oh_t = torch.as_tensor(pc_h[sel]), torch.as_tensor(oh_h[sel])
+    rt.set_precision(precision)
+    with torch.no_grad():
+        if workload == 'cfg3':
+            from oracle import frustum_pointnets_v1 as ofpn
+            big = fpn.get_model(pc_dev[:rchunk], oh_dev[:rchunk], False)['mask_logits'][torch.as_tensor(sel, device=pc_dev.device)].cpu().numpy()
+            ep = fpn.get_model(pc_dev[:rchunk][torch.as_tensor(sel, device=pc_dev.device)].contiguous(),
+                               oh_dev[:rchunk][torch.as_tensor(sel, device=pc_dev.device)].contiguous(), False)
+            g = ep['mask_logits'].cpu().numpy()
+            oep = ofpn.get_model(vs, pc_t, oh_t, seed=5)
+            ol = oep['mask_logits'].numpy()
+            cont = ofpn.get_model(vs, pc_t, oh_t, seed=5, logits=torch.as_tensor(g))
+        else:
+            from oracle import semisup_models as osm
+            big = sm.v1_inst_seg(pc_dev[:rchunk], None, None, {}, False, scope='class_agnostic/inst_seg')[torch.as_tensor(sel, device=pc_dev.device)].cpu().numpy()
+            g, ep, cont = big, None, None
+            with vs.variable_scope('class_agnostic'):
+                ol = osm.v1_inst_seg(pc_t, None, None, {}, False, vs, scope='inst_seg').numpy()
+    scale = float(np.abs(ol).mean())
+    agree = (g[..., 0] < g[..., 1]) == (ol[..., 0] < ol[..., 1])
+    out = {'precision': precision, 'frustums_checked': int(n_sample), 'oracle': 'PyTorch-CPU fp32 restatement of the TF1 graph (literal conv6)',
+           'seg_logit_err_max_of_scale': float(np.abs(g - ol).max() / scale), 'seg_logit_err_mean_of_scale': float(np.abs(g - ol).mean() / scale),
+           'mask_point_agreement': float(agree.mean()), 'mask_frustums_bit_exact': '%d / %d' % (int(agree.all(axis=1).sum()), n_sample),
+           'mask_exactness_1024_frustums': 'profiles/r02_mask_exactness.txt',
+           'timed_batch_vs_checked_batch_logit_diff_of_scale': float(np.abs(big - g).max() / scale)}
+    if cont is not None:
+        out['resampled_indices_bit_exact'] = bool(np.array_equal(ep['object_pc_indices'].cpu().numpy(), cont['object_pc_indices']))
+        worst, inside = 0.0, 1.0
+        for k in ('stage1_center', 'center', 'heading_scores', 'heading_residuals', 'size_scores', 'size_residuals'):
+            a, b = ep[k].float().cpu().numpy().astype(np.float64), cont[k].numpy().astype(np.float64)
+            worst = max(worst, float(np.abs(a - b).max()))
+            inside = min(inside, float((np.abs(a - b) <= 1e-3 + 1e-2 * np.abs(b)).mean()))
+        out['box_outputs_from_gpu_logits'] = {'max_abs_err': worst, 'min_fraction_within_rel1e-2_abs1e-3': inside}
+    return out
 
 
 def cpu_baseline(workload, variables, sample):

@@ -360,6 +360,11 @@ typedef struct {
 } t3d_assemble_args;
 int t3d_assemble_frustum_batch(const t3d_assemble_args* args /* host */, t3d_stream_t stream);
 
+/* Input wire format of the inference path: xyz fp32 [n,3] + rgb uint8 [n,3] (colours are k / 255 of 8-bit images in the
+ * prepared SUN-RGBD frustums) -> the fp32 [n,6] layout of the reference's pc placeholder (semisup_v1_sunrgbd.py:39),
+ * bit-identical to float32(k) / 255 on the host.  15 B instead of 24 B per point over PCIe. */
+int t3d_assemble_points(const float* xyz, const uint8_t* rgb, long long n_points, float* out, t3d_stream_t stream);
+
 /* ---- detection evaluation ------------------------------------------------------------
  * The matching loop of eval_det.eval_det_cls (sunrgbd_detection/eval_det.py:118-145) for one class: detections sorted by
  * descending score, 3D IoU (box_util.box3d_iou, the get_iou hook of eval_det.py:63-69) against the ground-truth boxes of

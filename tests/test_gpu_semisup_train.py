@@ -35,10 +35,13 @@ def _setup(B, N, seed=11, mixed=True, **over):
     return v, feed, masks, config.cfg(**kw)
 
 
-@pytest.mark.parametrize('B,N', [(8, 256), (16, 1024)])
-def test_semisup_adv_step_vs_oracle(B, N, built_lib):
+# third case: only the T-Net trains (box net frozen) -- the gradient still reaches stage1_center through the frozen box_est
+# convolutions (TF back-propagates through frozen variables to their inputs)
+@pytest.mark.parametrize('B,N,over', [(8, 256, {}), (16, 1024, {}), (8, 256, dict(SEMI_TRAIN_BOX_TRAIN_CLASS_AG_BOX=False)),
+                                      (8, 256, dict(SEMI_TRAIN_BOX_TRAIN_CLASS_AG_TNET=False))])
+def test_semisup_adv_step_vs_oracle(B, N, over, built_lib):
     from oracle import train_semisup_adv as ot
-    v, feed, masks, FLAGS = _setup(B, N)
+    v, feed, masks, FLAGS = _setup(B, N, **over)
     oloss, ograds, ovs, oep = ot.loss_and_grads(v, FLAGS, feed, masks, global_step=0)
     _, ograds64, _, oep64 = ot.loss_and_grads(v, FLAGS, feed, masks, global_step=0, dtype=torch.float64)
     g = tsa.SemiAdvTrainGraph(v, FLAGS, B, N, 6, DEV)

@@ -53,32 +53,14 @@ def oracle_seg_logits(variables, pc, one_hot=None, scope='class_agnostic/inst_se
 
 
 def oracle_cfg3_from_logits(variables, pc, one_hot, logits, seed, dtype=torch.float32):
-    """F-PointNet v1 pipeline downstream of GIVEN mask logits (models/model_util.py:241-325, box-estimation net of
-    semisup_models.py:224-261 on the 512 gathered points): the oracle continued from the GPU's own logits, so that masks
-    and resampled indices are identical and every later output is comparable."""
-    from oracle.tf_layers import VarStore, conv2d, fully_connected, max_pool_points
-    from oracle import model_util as omu
-    from transferable3d_b200.constants import MEAN_DIMS_ARR
+    """F-PointNet v1 pipeline downstream of GIVEN mask logits (oracle/frustum_pointnets_v1.py): the oracle continued from
+    the GPU's own logits, so that masks and resampled indices are identical and every later output is comparable."""
+    from oracle.tf_layers import VarStore
+    from oracle import frustum_pointnets_v1 as ofpn
     vs = VarStore(variables, dtype=dtype)
-    pc_c, oh_c = torch.as_tensor(pc).to(dtype), torch.as_tensor(one_hot).to(dtype)
     with torch.no_grad():
-        oep = {}
-        obj, omean, oep = omu.point_cloud_masking(pc_c, torch.as_tensor(logits).to(dtype), oep, rng_mode='philox', seed=seed)
-        with vs.variable_scope('tnet'):
-            delta, _ = omu.get_center_regression_net(obj, oh_c, False, None, oep, vs)
-        s1 = delta + omean
-        with vs.variable_scope('box_est'):
-            net = obj - delta.unsqueeze(1)
-            for nm, c in (('conv-reg1', 128), ('conv-reg2', 128), ('conv-reg3', 256), ('conv-reg4', 512)):
-                net = conv2d(net, c, [1, 1], vs, nm, True, False)
-            net = torch.cat([max_pool_points(net), oh_c], dim=1)
-            net = fully_connected(net, 512, vs, 'fc1', True, False)
-            net = fully_connected(net, 256, vs, 'fc2', True, False)
-            out = fully_connected(net, 67, vs, 'fc3', activation_fn=None)
-        oep = omu.parse_output_to_tensors(out, oep, 12, MEAN_DIMS_ARR)
-    oep['stage1_center'] = s1
-    oep['center'] = oep['center_boxnet'] + s1
-    return oep
+        return ofpn.get_model(vs, torch.as_tensor(pc).to(dtype), torch.as_tensor(one_hot).to(dtype), seed=seed,
+                              logits=torch.as_tensor(logits).to(dtype))
 
 
 def frac_within(a, b, rel, abs_):

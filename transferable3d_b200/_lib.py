@@ -161,6 +161,7 @@ SIGNATURES = {
     't3d_surface_loss': (_I, [_c.POINTER(t3d_surface_loss_args), _P]),
     't3d_assemble_frustum_batch': (_I, [_c.POINTER(t3d_assemble_args), _P]),
     't3d_det_match': (_I, [_c.POINTER(t3d_det_match_args), _P]),
+    't3d_assemble_points': (_I, [_P, _P, _L, _P, _P]),
     't3d_inference_scores': (_I, [_c.POINTER(t3d_infer_score_args), _P]),
     't3d_prediction_to_label': (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P]),
 }

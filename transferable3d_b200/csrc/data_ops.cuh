@@ -86,4 +86,30 @@ __global__ void __launch_bounds__(256) assemble_batch_kernel(const AssembleArgs 
   }
 }
 
+// Wire format -> placeholder layout: the frustum points cross PCIe as xyz fp32 [n,3] + rgb uint8 [n,3] (SUN-RGBD colours are
+// im2double of 8-bit images, sunrgbd_data: rgb = k / 255) = 15 B / point instead of the 24 B of the fp32 (B,N,6) placeholder
+// of semisup_v1_sunrgbd.py:39.  One thread per output float4 (stores fully coalesced, the reads hit L1): out[p][0:3] =
+// xyz[p], out[p][3:6] = (float)rgb[p] / 255 (IEEE division: bit-identical to numpy's float32 k / 255).
+__global__ void __launch_bounds__(256) assemble_points_kernel(const float* __restrict__ xyz, const uint8_t* __restrict__ rgb,
+                                                              long long n_points, float* __restrict__ out) {
+  const long long nq = (n_points * 6 + 3) / 4;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long e = q * 4 + j;
+      const long long p = e / 6;
+      const int c = (int)(e - p * 6);
+      v[j] = 0.0f;
+      if (p < n_points) v[j] = c < 3 ? __ldg(xyz + p * 3 + c) : __fdiv_rn((float)__ldg(rgb + p * 3 + (c - 3)), 255.0f);
+    }
+    if (q * 4 + 3 < n_points * 6) {
+      *reinterpret_cast<float4*>(out + q * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      for (int j = 0; j < 4; ++j)
+        if (q * 4 + j < n_points * 6) out[q * 4 + j] = v[j];
+    }
+  }
+}
+
 }  // namespace t3d

@@ -394,6 +394,15 @@ extern "C" int t3d_assemble_frustum_batch(const t3d_assemble_args* a, t3d_stream
   return 0;
 }
 
+extern "C" int t3d_assemble_points(const float* xyz, const uint8_t* rgb, long long n_points, float* out, t3d_stream_t stream) {
+  if (!xyz || !rgb || !out) return T3D_ERR_ARG;
+  if (n_points <= 0) return T3D_ERR_SHAPE;
+  if ((uintptr_t)out & 15) return T3D_ERR_ALIGN;
+  assemble_points_kernel<<<xg_num_sms() * 8, 256, 0, S(stream)>>>(xyz, rgb, n_points, out);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int t3d_det_match(const t3d_det_match_args* a, t3d_stream_t stream) {
   if (!a || !a->det_corners || !a->img_det_off || !a->img_det_idx || !a->img_gt_off || !a->tp || !a->fp || !a->gt_det) return T3D_ERR_ARG;
   if (a->nimg <= 0 || a->nd <= 0 || a->ng < 0 || (a->ng > 0 && !a->gt_corners)) return T3D_ERR_SHAPE;

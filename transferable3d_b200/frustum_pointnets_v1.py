@@ -38,3 +38,16 @@ def get_model(point_cloud, one_hot_vec, is_training, bn_decay=None, end_points=N
     end_points = model_util.parse_output_to_tensors(output, end_points, NUM_HEADING_BIN, MEAN_DIMS_ARR)
     end_points['center'] = end_points['center_boxnet'] + stage1_center
     return end_points
+
+
+def inference(point_cloud, one_hot_vec, end_points=None):
+    """get_model + the reference's test-time post-processing (test_semisup.inference, test_semisup.py:236-258: softmax over
+    the point logits, mask_mean_prob, log-score, argmax-selected residuals) on the device.  Returns the prediction the
+    reference's runner returns -- a dict of device tensors pred_seg (B,N) uint8, center (B,3), heading_cls, heading_res,
+    size_cls, size_res (B,3), scores -- i.e. N bytes + 10 numbers per frustum instead of the 2 N + 67 raw fetches."""
+    from .test_semisup import inference_scores
+    ep = get_model(point_cloud, one_hot_vec, False, end_points=end_points)
+    out = inference_scores(ep['mask_logits'], ep['heading_scores'], ep['heading_residuals'], ep['size_scores'], ep['size_residuals'])
+    out['center'] = ep['center']
+    out['end_points'] = ep
+    return out

@@ -100,21 +100,29 @@ class TrainLayer(object):
         return out
 
     def backward(self, dout, need_dx=True):
-        """dout: gradient w.r.t. this layer's output (overwritten in place).  Returns dX or None."""
+        """dout: gradient w.r.t. this layer's output (overwritten in place).  Returns dX or None.
+        A layer whose variables are not in the gradient arena (frozen, but still in the training-mode graph: batch
+        statistics) only propagates the input gradient -- TF back-propagates through frozen variables to their input."""
         M = self.y.shape[0]
         dev = dout.device
         g = self.grads
+        trainable = g is not None and (self.name + '/weights') in g
+        if not trainable and not need_dx:
+            return None
         if self.bn:
             s1 = torch.empty(self.N, device=dev)
             s2 = torch.empty(self.N, device=dev)
             outp = ptr(self.out) if self.act != ACT_NONE else None
             call('t3d_colstats', ptr(dout), outp, ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(s1), ptr(s2), M, self.N, 1,
                  self.act, stream())
-            g[self.name + '/bn/beta'].copy_(s1)
-            g[self.name + '/bn/gamma'].copy_(s2)
+            if trainable:
+                g[self.name + '/bn/beta'].copy_(s1)
+                g[self.name + '/bn/gamma'].copy_(s2)
             call('t3d_bn_backward', ptr(dout), outp, ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(self.p('bn/gamma')),
                  ptr(s1), ptr(s2), M, self.N, self.act, stream())
         dy = dout
+        if not trainable:
+            return gemm(dy, self.N, 1, self.W(), 1, self.N, M, self.K, self.N)
         if self.bn:
             # a bias in front of a batch norm cancels in (y - mean): its gradient, the column sum of the BN input gradient,
             # is analytically zero (what TF accumulates there is rounding noise) -- no pass over dY for it

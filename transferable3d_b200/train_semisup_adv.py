@@ -273,7 +273,9 @@ class SemiAdvTrainGraph(object):
         g_lv1 = g[:, :512].contiguous() if c.use_one_hot else g
         train_box = 'class_agnostic/box_est/conv-reg1/weights' in self.grad
         train_tnet = 'class_agnostic/tnet/fc3-stage1/weights' in self.grad
-        if train_box:
+        if train_box or train_tnet:
+            # with the box net frozen (SEMI_TRAIN_BOX_TRAIN_CLASS_AG_BOX = 0) its convolutions still carry the gradient to
+            # stage1_center: TrainLayer.backward is dgrad-only for layers outside the gradient arena
             g = maxpool_bwd(g_lv1, b_arg, B, N, 512, rowmask)
             g = Bx[3].backward(g)
             g = Bx[2].backward(g)
