@@ -11,10 +11,12 @@
 // kX2ActScale, each layer's weights carry 2^s chosen at pack time (max |W| 2^s in [2^9, 2^10)); the epilogue undoes the
 // weight scale with one FFMA (x = acc * inv + bias * kX2ActScale).  `inv` also carries a first-order correction of the
 // tensor core's round-toward-zero accumulation (t3d_api.cu: x2_debias; tests/numerics_split_study.py).
-// The tensor core truncates at every K=16 accumulation step, so the two small products of a group of K-blocks are
-// issued BEFORE its main products (the accumulator is still small when they are added): chunk stream per
-// (n-block, group of <= 2 K-blocks) = [lo(kb)...][hi(kb)...], MMAs = a_hi.w_lo (per lo chunk), then a_lo.w_hi for the
-// whole group, then a_hi.w_hi for the whole group.
+// The tensor core truncates at every K=16 accumulation step; per K-block the two small products are issued before the
+// main one (chunk stream per (n-block, K-block) = [lo][hi], MMAs = a_hi.w_lo, a_lo.w_hi, a_hi.w_hi), so every chunk leaves
+// the ring right after its last product.  (Issuing the small products of TWO K-blocks first -- kX2Group = 2 -- halves the
+// truncation steps at partial magnitude but holds the hi chunks in the ring twice as long: measured 97.6 - 98.5 % mask-exact
+// either way (profiles/r02_mask_exactness.txt: the de-bias factor removes the mean effect), and the ring stalls cost
+// ~5 k cycles per tile, so the streaming order won.)
 // One 128-point tile per iteration (the hi + lo images double every activation buffer); for the 256-wide box chains the
 // final-layer operand aliases the two hidden buffers.  bf16 counterpart: 62 % tensor-pipe active with one product;
 // here the pipe has three products per epilogue.
@@ -25,7 +27,8 @@
 namespace t3d {
 
 constexpr float kX2ActScale = 16.0f;
-constexpr int kX2Group = 2;               // K-blocks per small-first group (hi chunks of a group are resident together)
+constexpr int kX2Group = 1;               // K-blocks per small-first group (hi chunks of a group are resident together)
+constexpr int kX2Stages = 5;              // 16 KB weight-ring stages (131 KB of activation images leave room for five)
 
 template <typename S> __host__ __device__ constexpr int x2_buf_width(int b) { return S::BUF_BYTES(b) / (256 * S::NSUB); }
 template <typename S> __host__ __device__ constexpr int x2_num_chunks() { return 2 * chain_num_chunks<S>(); }
@@ -45,12 +48,12 @@ template <typename S> struct X2Smem {
   static constexpr int BUF2 = ALIAS2 ? 0 : BUF1 + 512 * W1w;
   static constexpr int ACT_END = ALIAS2 ? 512 * ((W0 + W1w) > W2 ? (W0 + W1w) : W2) : BUF2 + 512 * W2;
   static constexpr int RING = ACT_END;
-  static constexpr int W1 = RING + kRingStages * kChunkBytes;              // fp32 [CIN][C1]
+  static constexpr int W1 = RING + kX2Stages * kChunkBytes;              // fp32 [CIN][C1]
   static constexpr int B1 = W1 + 4 * S::CIN * S::C1;
   static constexpr int HB = B1 + 4 * S::C1;                                  // hidden biases
   static constexpr int BARS = (HB + 4 * chain_hidden_bias_count<S>() + 15) / 16 * 16;
   // barriers: ring_full[4], ring_empty[4], acc_full[3], acc_empty[3], act_ready[4], front_free
-  static constexpr int NBARS = 2 * kRingStages + 6 + 4 + 1;
+  static constexpr int NBARS = 2 * kX2Stages + 6 + 4 + 1;
   static constexpr int TMEM_SLOT = BARS + 8 * NBARS;
   static constexpr int TOTAL = TMEM_SLOT + 16;
   static constexpr int buf_off(int b) { return b == 0 ? BUF0 : (b == 1 ? BUF1 : BUF2); }
@@ -76,11 +79,11 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kChainThr
 
   const uint32_t bar0 = sbase + L::BARS;
   auto ring_full = [&](int s) { return bar0 + 8u * s; };
-  auto ring_empty = [&](int s) { return bar0 + 8u * (kRingStages + s); };
-  auto acc_full = [&](int r) { return bar0 + 8u * (2 * kRingStages + r); };
-  auto acc_empty = [&](int r) { return bar0 + 8u * (2 * kRingStages + 3 + r); };
-  auto act_ready = [&](int a) { return bar0 + 8u * (2 * kRingStages + 6 + a); };
-  const uint32_t front_free = bar0 + 8u * (2 * kRingStages + 10);
+  auto ring_empty = [&](int s) { return bar0 + 8u * (kX2Stages + s); };
+  auto acc_full = [&](int r) { return bar0 + 8u * (2 * kX2Stages + r); };
+  auto acc_empty = [&](int r) { return bar0 + 8u * (2 * kX2Stages + 3 + r); };
+  auto act_ready = [&](int a) { return bar0 + 8u * (2 * kX2Stages + 6 + a); };
+  const uint32_t front_free = bar0 + 8u * (2 * kX2Stages + 10);
   // TMEM regions: final R0 = cols 0..127, R1 = 128..255 (ping-pong over channel tiles), hidden R2 = 256..511
   auto region_col = [&](int r) -> uint32_t { return (uint32_t)(r * 128); };
 
@@ -99,7 +102,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kChainThr
 
   // ------------------------------------------------------------------ setup
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kRingStages; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), kClusterSize); }
+    for (int s = 0; s < kX2Stages; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), kClusterSize); }
     for (int r = 0; r < 3; ++r) { mbar_init(acc_full(r), 1); mbar_init(acc_empty(r), 8); }
     for (int a = 0; a < 4; ++a) mbar_init(act_ready(a), a == 0 ? 4 : 8);
     mbar_init(front_free, 1);
@@ -125,8 +128,8 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kChainThr
       uint32_t it = 0;
       for (int i = 0; i < iters; ++i) {
         for (int c = 0; c < NCH; ++c, ++it) {
-          const int s = it % kRingStages;
-          mbar_wait(ring_empty(s), ((it / kRingStages) & 1) ^ 1);
+          const int s = it % kX2Stages;
+          mbar_wait(ring_empty(s), ((it / kX2Stages) & 1) ^ 1);
           mbar_arrive_expect_tx(ring_full(s), kChunkBytes);
           bulk_g2s_mc(sbase + L::RING + s * kChunkBytes + crank * kHalf, args.arena + (size_t)c * kChunkBytes + crank * kHalf,
                       kHalf, ring_full(s), kAllCtas);
@@ -152,8 +155,8 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kChainThr
       for (int g0 = 0; g0 < kbn; g0 += kX2Group) {
         const int gn = min(kX2Group, kbn - g0);
         for (int j = 0; j < gn; ++j, ++it) {                       // lo chunks: a_hi . w_lo
-          const int s = it % kRingStages;
-          mbar_wait_w(ring_full(s), (it / kRingStages) & 1);
+          const int s = it % kX2Stages;
+          mbar_wait_w(ring_full(s), (it / kX2Stages) & 1);
           tc_fence_after();
           const uint32_t w = sbase + L::RING + s * kChunkBytes, a = act + (g0 + j) * 16384;
           if (swapped) mma4(d, w, a, idesc, first); else mma4(d, a, w, idesc, first);
@@ -161,14 +164,14 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kChainThr
           umma_commit_mc_w(ring_empty(s), kAllCtas);
         }
         for (int j = 0; j < gn; ++j) {                             // hi chunks of the group: a_lo . w_hi
-          const int s = (it + j) % kRingStages;
-          mbar_wait_w(ring_full(s), ((it + j) / kRingStages) & 1);
+          const int s = (it + j) % kX2Stages;
+          mbar_wait_w(ring_full(s), ((it + j) / kX2Stages) & 1);
           tc_fence_after();
           const uint32_t w = sbase + L::RING + s * kChunkBytes, a = act + lo_off + (g0 + j) * 16384;
           if (swapped) mma4(d, w, a, idesc, false); else mma4(d, a, w, idesc, false);
         }
         for (int j = 0; j < gn; ++j, ++it) {                       // main products: a_hi . w_hi
-          const int s = it % kRingStages;
+          const int s = it % kX2Stages;
           const uint32_t w = sbase + L::RING + s * kChunkBytes, a = act + (g0 + j) * 16384;
           if (swapped) mma4(d, w, a, idesc, false); else mma4(d, a, w, idesc, false);
           umma_commit_mc_w(ring_empty(s), kAllCtas);

@@ -8,7 +8,8 @@
 //   conv7 (256 channels)                    -> e7 -> 4 K-blocks streamed through the slots -> conv8
 //   conv8 (128 channels)                    -> e8 -> 2 K-blocks (both slots)              -> conv9 -> e9 + conv10 (fp32)
 // so the 512- and 256-wide activations never exist as a whole.  Three products per K-block (hi.lo, lo.hi, hi.hi) into
-// one fp32 accumulator, the two small ones first.  16 epilogue warps (4 lane quarters x 4 column quarters of a K-block).
+// one fp32 accumulator, the two small ones first; the first conv6' block of tile i+1 is issued under the e7 epilogue of
+// tile i.  16 epilogue warps (4 lane quarters x 4 column quarters of a K-block).
 // TMEM: R6 = cols 0..127 (conv6' block), R89 = 128..255 (conv8, conv9), R7 = 256..511 (conv7).
 // Weight chunks (fp16 hi / lo images, 16 KB) stream through a 5-stage ring, each CTA of the cluster fetching half of
 // every chunk and multicasting it; the input tile (stage 1's hi + lo point_feat images, 32 KB) and gbias are double-buffered.
@@ -161,17 +162,16 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
       it += 2;
     };
     auto slot_wait = [&](int b) { mbar_wait_w(sl_ready(b), n_sl[b] & 1); n_sl[b]++; tc_fence_after(); };
+    bool pre = false;              // conv6' block 0 of the current tile was already issued under the previous tile's tail
     for (int i = 0; i < iters; ++i) {
       const int ib = i & 1;
       const uint32_t in = sbase + L::IN + ib * 32768;
-      mbar_wait_w(in_ready(ib), (i >> 1) & 1);
-      tc_fence_after();
       tr.mark(0x10);
-      auto c6 = [&](int nb) {
+      auto c6 = [&](int nb, uint32_t in_addr) {
         mbar_wait_w(r6_empty, (n_r6 & 1) ^ 1);
         tc_fence_after();
         tr.mark(0x20 + nb);
-        kblock(tm + kR6, in, true);
+        kblock(tm + kR6, in_addr, true);
         umma_commit_w(r6_full); n_r6++;
       };
       // conv7 K-block kbg (slot kbg & 1): chunks [lo rows 0-127][lo rows 128-255][hi rows 0-127][hi rows 128-255]
@@ -190,15 +190,29 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
         const uint32_t wh0 = ring_wait(it + 2), wh1 = ring_wait(it + 3);
         tc_fence_after();
         mma4(tm + kR7, a + 16384, wh0, false);
-        mma4(tm + kR7 + 128, a + 16384, wh1, false);
         mma4(tm + kR7, a, wh0, false);
+        ring_release(it + 2);
+        mma4(tm + kR7 + 128, a + 16384, wh1, false);
         mma4(tm + kR7 + 128, a, wh1, false);
-        ring_release(it + 2); ring_release(it + 3);
+        ring_release(it + 3);
         it += 4;
         umma_commit_w(sl_free(b));
         if (kbg == 7) umma_commit_w(r7_full);
       };
-      c6(0); c6(1); c7(0); c7(1); c6(2); c7(2); c7(3); c6(3); c7(4); c7(5); c7(6); c7(7);
+      if (!pre) {
+        mbar_wait_w(in_ready(ib), (i >> 1) & 1);
+        tc_fence_after();
+        c6(0, in);
+      }
+      c6(1, in); c7(0); c7(1); c6(2, in); c7(2); c7(3); c6(3, in); c7(4); c7(5); c7(6); c7(7);
+      // the tensor pipe would idle while the epilogue works through e7: start the next tile's first conv6' block now
+      pre = false;
+      if (i + 1 < iters) {
+        mbar_wait_w(in_ready((i + 1) & 1), ((i + 1) >> 1) & 1);
+        tc_fence_after();
+        c6(0, sbase + L::IN + ((i + 1) & 1) * 32768);
+        pre = true;
+      }
       // conv8: the four K-blocks of the conv7 activation stream through the slots
       for (int kb = 0; kb < 4; ++kb) {
         const int b = kb & 1;
@@ -209,29 +223,16 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
         umma_commit_w(sl_free(b));
       }
       umma_commit_w(r89_full); n_r89++;
-      // conv9: both K-blocks of the conv8 activation are resident (slot kb): small products of both first
-      slot_wait(0); slot_wait(1);
+      // conv9: the two K-blocks of the conv8 activation sit in the two slots
+      slot_wait(0);
       mbar_wait_w(r89_empty, (n_r89 & 1) ^ 1);
       tc_fence_after();
       tr.mark(0x50);
-      {
-        const uint32_t a0 = sbase + L::SL, a1 = sbase + L::SL + 32768;
-        const uint32_t wl0 = ring_wait(it), wl1 = ring_wait(it + 1);
-        tc_fence_after();
-        mma4(tm + kR89, a0, wl0, true);
-        mma4(tm + kR89, a1, wl1, false);
-        ring_release(it); ring_release(it + 1);
-        const uint32_t wh0 = ring_wait(it + 2), wh1 = ring_wait(it + 3);
-        tc_fence_after();
-        mma4(tm + kR89, a0 + 16384, wh0, false);
-        mma4(tm + kR89, a1 + 16384, wh1, false);
-        mma4(tm + kR89, a0, wh0, false);
-        mma4(tm + kR89, a1, wh1, false);
-        ring_release(it + 2); ring_release(it + 3);
-        it += 4;
-      }
-      umma_commit_w(r89_full); n_r89++;
+      kblock(tm + kR89, sbase + L::SL, true);
       umma_commit_w(sl_free(0));
+      slot_wait(1);
+      kblock(tm + kR89, sbase + L::SL + 32768, false);
+      umma_commit_w(r89_full); n_r89++;
       umma_commit_w(sl_free(1));
       tr.mark(0x51);
     }

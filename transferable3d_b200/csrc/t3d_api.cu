@@ -768,8 +768,8 @@ extern "C" int t3d_pack_seg2_x2(const float* W6p, const float* W7, const float* 
   c6(0); c6(1); c7(0); c7(1); c6(2); c7(2); c7(3); c6(3); c7(4); c7(5); c7(6); c7(7);
   for (int kb = 0; kb < 4; ++kb)
     for (int part = 2; part >= 1; --part) tab.d[n++] = PackDesc{W8, 128, 256, kb * 64, 0, 128, part, wscale[2]};
-  for (int part = 2; part >= 1; --part)
-    for (int kb = 0; kb < 2; ++kb) tab.d[n++] = PackDesc{W9, 128, 128, kb * 64, 0, 128, part, wscale[3]};
+  for (int kb = 0; kb < 2; ++kb)
+    for (int part = 2; part >= 1; --part) tab.d[n++] = PackDesc{W9, 128, 128, kb * 64, 0, 128, part, wscale[3]};
   if (n != kSeg2XChunks) return T3D_ERR_SHAPE;
   uint8_t* ar = reinterpret_cast<uint8_t*>(arena);
   pack_table_kernel<<<n, 256, 0, st>>>(tab, ar);
@@ -782,7 +782,7 @@ extern "C" int t3d_pack_seg2_x2(const float* W6p, const float* W7, const float* 
   if ((e = scale_copy(f + 512, W10, 256, 1.0f / kX2ActScale, st)) != 0) return e;
   if ((e = scale_copy(f + 768, b10, 2, 1.0f, st)) != 0) return e;
   write4_kernel<<<1, 1, 0, st>>>(f + 770, x2_inv(wscale[0], 1, 1), x2_inv(wscale[1], 8, 1), x2_inv(wscale[2], 4, 1),
-                                 x2_inv(wscale[3], 2, 2));
+                                 x2_inv(wscale[3], 2, 1));
   T3D_CHECK_LAUNCH();
   return 0;
 }
