@@ -102,3 +102,53 @@ def test_checkpoint_feeds_the_variable_store(tmp_path):
     ck.save_checkpoint(prefix, {k: np.asarray(a) for k, a in v.items()})
     back = ck.load_checkpoint(prefix)
     assert set(back) == set(v) and all(np.array_equal(back[k], np.asarray(v[k])) for k in v)
+
+
+def test_handmade_fixture_not_produced_by_the_writer():
+    """tests/golden/tf_ckpt_handmade.* is assembled byte by byte by tests/golden/make_tf_ckpt_fixture.py (which does not
+    import the product module) in TensorFlow's own table layout: restart interval 16 with a mid-block restart, shortened
+    separator keys ("b", "t") in the index block, a DT_STRING entry, an empty shape message for the scalar, a bit-serial
+    CRC.  The reader must return exactly the arrays the script generated."""
+    import hashlib
+    import importlib.util
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    prefix = os.path.join(here, 'tf_ckpt_handmade')
+    idx = open(prefix + '.index', 'rb').read()
+    dat = open(prefix + '.data-00000-of-00001', 'rb').read()
+    assert hashlib.sha256(idx).hexdigest() == 'c8dcc03b2e5a34315d52d97b4e02cf0b6b3dad49e9e5188bc29acacf3fcc4580'
+    assert hashlib.sha256(dat).hexdigest() == 'a059084545405792ddb8dd83393fcfa165ce93d14737c24eeec24debd6d10a40'
+    spec = importlib.util.spec_from_file_location('make_tf_ckpt_fixture', os.path.join(here, 'make_tf_ckpt_fixture.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    index2, data2, arrays = mod.build()
+    assert index2 == idx and data2 == dat                           # the committed files are what the script builds
+    assert mod.crc32c_bitwise(b'123456789') == 0xE3069283           # the independent CRC agrees with the published check value
+    # structure the writer in the product never emits: two restart points in the first data block, separator keys
+    header, entries = ck.read_index(prefix)
+    assert header == dict(num_shards=1, endianness=0)
+    assert set(entries) == set(arrays) | {'save_counter_names'}
+    assert entries['global_step']['shape'] == [] and entries['global_step']['dtype'] == 9
+    assert entries['a/conv1/biases']['offset'] == 0 and entries['shape_probe']['shape'] == [2, 3, 4]
+    back = ck.load_checkpoint(prefix, verify_data=True)
+    assert set(back) == set(arrays)                                 # the string entry is skipped
+    for k, a in arrays.items():
+        assert back[k].dtype == a.dtype and back[k].shape == a.shape and np.array_equal(back[k], a), k
+    assert [n for n, _ in ck.list_variables(prefix)] == sorted(entries)
+    # a flipped byte in the second data block (reached only through the shortened separator key's handle) is detected
+    bad = bytearray(idx)
+    pos = idx.index(b'c/fc1/biases')
+    bad[pos + 20] ^= 0x40
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        p2 = os.path.join(d, 'x')
+        open(p2 + '.index', 'wb').write(bytes(bad))
+        open(p2 + '.data-00000-of-00001', 'wb').write(dat)
+        with pytest.raises(ValueError):
+            ck.load_checkpoint(p2)
+
+
+def test_v1_checkpoint_is_named_as_such(tmp_path):
+    p = os.path.join(str(tmp_path), 'model.ckpt')
+    open(p, 'wb').write(b'\x00' * 64)
+    with pytest.raises(ValueError, match='V1'):
+        ck.load_checkpoint(p)

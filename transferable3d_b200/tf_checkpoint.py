@@ -3,8 +3,10 @@ restores with `saver.restore(sess, path)` (sunrgbd_detection/test_semisup.py:158
 without TensorFlow: `load_checkpoint(prefix)` returns the `{variable name: ndarray}` dict `runtime.VariableStore` takes
 (SURVEY 8f rank 5).
 
-Format (restated from TensorFlow's published tensor_bundle / table sources; **unpinned**: no TensorFlow-written file exists
-in this environment, the tests round-trip through the writer below, which emits the same structures):
+Format (restated from TensorFlow's published tensor_bundle / table sources; no TensorFlow-written file exists in this
+environment, so the reader is pinned by (a) tests/golden/tf_ckpt_handmade.*, a fixture assembled byte by byte by an
+independent script in TensorFlow's own layout -- restart interval 16, shortened separator keys in the index block, a
+DT_STRING entry, bit-serial CRC -- and (b) round trips through the writer below):
 
 * `<prefix>.index` is a LevelDB-style sorted table.  Footer = last 48 bytes: metaindex BlockHandle, index BlockHandle
   (each two varint64: offset, size), zero padding to 40 bytes, 8-byte little-endian magic 0xdb4775248b80fb57.
@@ -139,6 +141,9 @@ def _block_entries(block):
 
 def read_index(prefix, verify=True):
     """-> (header dict, {name: entry dict(dtype, shape, shard_id, offset, size, crc32c)})"""
+    if not os.path.exists(prefix + '.index') and os.path.isfile(prefix):
+        raise ValueError('%s is a single-file (V1, tf.train.SaverDef.V1) checkpoint; only the V2 format (<prefix>.index + '
+                         '<prefix>.data-*) is read here -- re-save it with tf.train.Saver(write_version=V2)' % prefix)
     buf = open(prefix + '.index', 'rb').read()
     if len(buf) < 48 or struct.unpack_from('<Q', buf, len(buf) - 8)[0] != MAGIC:
         raise ValueError('%s.index is not a TensorFlow V2 checkpoint index (bad magic)' % prefix)
