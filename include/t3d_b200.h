@@ -238,6 +238,40 @@ int t3d_maxpool_masked_fwd(const float* x, const float* rowmask, int B, int N, i
 int t3d_maxpool_masked_bwd(const float* dout, const int* arg, const float* rowmask, int B, int N, int C, float* dx,
                            t3d_stream_t stream);
 int t3d_scale_mask(const float* x, const float* mask, float scale, float* out, long long n, t3d_stream_t stream);
+/* ---- lazy batch norm (training-mode layers with M = B*N rows; tf_util.conv2d :1258-1323 + batch_norm_template :1645-1664) ----
+ * The post-BN activation relu(gamma (y - mean) rstd + beta) of a layer is never written: consumers read the pre-BN tensor y
+ * and apply the folded map relu(a_scale[c] * y + a_shift[c]) (a_scale = gamma rstd, a_shift = beta - mean a_scale, produced by
+ * t3d_bn_finalize_affine) on the fly, and the batch statistics of y are accumulated by the GEMM that produces it.
+ * t3d_gemm_bn_f32 = t3d_gemm_f32_ws with (a) a_scale / a_shift != NULL: A := relu(a_scale[c] * A + a_shift[c]), c = k for a
+ * k-contiguous A (forward: needs the workspace path, K % 32 == 0, 16-byte aligned arrays), c = m for a row-contiguous A
+ * (wgrad); (b) st_sum / st_sq != NULL: column sums of (C - st_shift[n]) and of its square (splitk == 1), zeroed inside.
+ * Returns T3D_ERR_SHAPE when the problem does not reach a kernel that implements the extras; t3d_gemm_bn_supported says so
+ * beforehand (kind 0 forward: 1 = tensor-core path, 2 = first-layer kernel (statistics only), 0 = no; kind 1 wgrad). */
+int t3d_gemm_bn_supported(int M, int N, int K, int kind);
+int t3d_gemm_bn_f32(const float* A, long long sam, long long sak, const float* a_scale, const float* a_shift, const float* B,
+                    long long sbk, long long sbn, float* C, int ldc, int M, int N, int K, int splitk, const float* bias,
+                    float* st_sum, float* st_sq, const float* st_shift, void* ws, size_t ws_bytes, t3d_stream_t stream);
+/* y0[n] = sum_k a(k) W[k, n] + bias[n] for one row a (lazy BN applied when a_scale != NULL): the shift of the statistics */
+int t3d_row0(const float* a, const float* a_scale, const float* a_shift, const float* W, int ldw, const float* bias, int K, int N,
+             float* y0, t3d_stream_t stream);
+int t3d_bn_finalize_affine(const float* sum, const float* sumsq, const float* shift, int M, int C, float eps, float decay,
+                           const float* gamma, const float* beta, float* mean, float* rstd, float* a_scale, float* a_shift,
+                           float* moving_mean, float* moving_var, t3d_stream_t stream);
+/* t3d_colstats mode 1 / t3d_bn_backward of a lazy layer: the ReLU mask is a_scale * y + a_shift > 0 */
+int t3d_colstats_lazy(const float* dOut, const float* y, const float* mean, const float* rstd, const float* a_scale,
+                      const float* a_shift, float* s1, float* s2, int M, int C, t3d_stream_t stream);
+int t3d_bn_backward_lazy(float* dOut, const float* y, const float* mean, const float* rstd, const float* gamma,
+                         const float* a_scale, const float* a_shift, const float* s1, const float* s2, int M, int C,
+                         t3d_stream_t stream);
+int t3d_maxpool_lazy_fwd(const float* y, const float* a_scale, const float* a_shift, const float* rowmask, int B, int N, int C,
+                         float* out, int* arg, t3d_stream_t stream);
+/* backward of [BN -> ReLU -> (x rowmask) -> max-pool over the N rows of each group] from the pooled gradient g [B, C]: the BN
+ * reductions are O(B C) gathers at the arg-max elements, dY [B*N, C] is one dense pass + a B x C scatter; s1 = d beta,
+ * s2 = d gamma.  Replaces t3d_maxpool_masked_bwd + t3d_colstats + t3d_bn_backward (semisup_models.py:184-189, 240-245). */
+int t3d_pool_bn_backward(const float* g, const int* arg, const float* rowmask, const float* y, const float* mean,
+                         const float* rstd, const float* gamma, const float* a_scale, const float* a_shift, int B, int N, int C,
+                         float* s1, float* s2, float* dY, t3d_stream_t stream);
+
 typedef struct {
   const float *out9, *y_iou, *y_dc, *y_ds, *y_da;
   int B; float fit_bound, w_cls, w_delta, wc, ws, wa; int huber;

@@ -581,22 +581,27 @@ __global__ void __launch_bounds__(256) bn_apply4_kernel(const float4* __restrict
   }
 }
 
-__device__ __forceinline__ float bn_bwd_one(float dy, float o, bool has_out, float y, float m, float r, float g, float s1, float s2, float inv, int act) {
-  if (has_out) dy *= act_grad_from_out(o, act);
+// has_out == 2: lazy BN layer, o carries a_scale * y + a_shift (the forward ReLU argument) instead of the stored output
+__device__ __forceinline__ float bn_bwd_one(float dy, float o, int has_out, float y, float m, float r, float g, float s1, float s2, float inv, int act) {
+  if (has_out == 1) dy *= act_grad_from_out(o, act);
+  else if (has_out == 2) dy = o > 0.0f ? dy : 0.0f;
   const float xh = (y - m) * r;
   return g * r * (dy - s1 * inv - xh * s2 * inv);
 }
 __global__ void __launch_bounds__(256) bn_backward4_kernel(float4* __restrict__ dOut, const float4* __restrict__ out, const float4* __restrict__ y,
                                                           const float* __restrict__ mean, const float* __restrict__ rstd,
                                                           const float* __restrict__ gamma, const float* __restrict__ s1,
-                                                          const float* __restrict__ s2, unsigned n4, unsigned C4, int M, int act) {
-  extern __shared__ float4 bn_sp[];                  // [5][C4]: mean, rstd, gamma, s1, s2
+                                                          const float* __restrict__ s2, unsigned n4, unsigned C4, int M, int act,
+                                                          const float* __restrict__ a_scale = nullptr,
+                                                          const float* __restrict__ a_shift = nullptr) {
+  extern __shared__ float4 bn_sp[];                  // [5 or 7][C4]: mean, rstd, gamma, s1, s2 (, a_scale, a_shift)
+  const int has_out = out != nullptr ? 1 : (a_scale != nullptr ? 2 : 0);
   for (unsigned i = threadIdx.x; i < C4; i += 256) {
     bn_sp[i] = ldg4(mean, i); bn_sp[C4 + i] = ldg4(rstd, i); bn_sp[2 * C4 + i] = ldg4(gamma, i);
     bn_sp[3 * C4 + i] = ldg4(s1, i); bn_sp[4 * C4 + i] = ldg4(s2, i);
+    if (has_out == 2) { bn_sp[5 * C4 + i] = ldg4(a_scale, i); bn_sp[6 * C4 + i] = ldg4(a_shift, i); }
   }
   __syncthreads();
-  const bool has_out = out != nullptr;
   const float inv = 1.0f / (float)M;
 #pragma unroll 1
   for (int it = 0; it < kBnIter; ++it) {
@@ -605,7 +610,7 @@ __global__ void __launch_bounds__(256) bn_backward4_kernel(float4* __restrict__ 
 #pragma unroll
     for (int u = 0; u < kEw4; ++u) {
       const unsigned q = base + u * 256u;
-      if (q < n4) { d[u] = dOut[q]; yy[u] = y[q]; o[u] = has_out ? out[q] : make_float4(0.f, 0.f, 0.f, 0.f); }
+      if (q < n4) { d[u] = dOut[q]; yy[u] = y[q]; o[u] = has_out == 1 ? out[q] : make_float4(0.f, 0.f, 0.f, 0.f); }
     }
 #pragma unroll
     for (int u = 0; u < kEw4; ++u) {
@@ -613,6 +618,10 @@ __global__ void __launch_bounds__(256) bn_backward4_kernel(float4* __restrict__ 
       if (q >= n4) continue;
       const unsigned c = q % C4;
       const float4 m = bn_sp[c], r = bn_sp[C4 + c], g = bn_sp[2 * C4 + c], a1 = bn_sp[3 * C4 + c], a2 = bn_sp[4 * C4 + c];
+      if (has_out == 2) {
+        const float4 sc = bn_sp[5 * C4 + c], sh = bn_sp[6 * C4 + c];
+        o[u] = make_float4(fmaf(sc.x, yy[u].x, sh.x), fmaf(sc.y, yy[u].y, sh.y), fmaf(sc.z, yy[u].z, sh.z), fmaf(sc.w, yy[u].w, sh.w));
+      }
       float4 w;
       w.x = bn_bwd_one(d[u].x, o[u].x, has_out, yy[u].x, m.x, r.x, g.x, a1.x, a2.x, inv, act);
       w.y = bn_bwd_one(d[u].y, o[u].y, has_out, yy[u].y, m.y, r.y, g.y, a1.y, a2.y, inv, act);

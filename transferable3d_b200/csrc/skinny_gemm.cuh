@@ -17,25 +17,62 @@ constexpr size_t kSkinnySmemMax = 48 * 1024;   // dynamic shared memory without 
 //     thread = 4 consecutive columns of one row; a block covers 256 * 4 / N rows per step.
 __global__ void __launch_bounds__(256) skinny_k_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ B,
                                                       long long ldb, const float* __restrict__ bias, float* __restrict__ C,
-                                                      long long ldc, int M, int N, int K, int act = 0) {
-  extern __shared__ float sB[];                      // [K][N] + bias [N]
+                                                      long long ldc, int M, int N, int K, int act = 0, float* __restrict__ st_sum = nullptr,
+                                                      float* __restrict__ st_sq = nullptr, const float* __restrict__ st_shift = nullptr) {
+  extern __shared__ float sB[];                      // [K][N] + bias [N] (+ column sums / sums of squares [2][N] when st_sum)
   for (int i = threadIdx.x; i < K * N; i += 256) sB[i] = B[(long long)(i / N) * ldb + (i % N)];
   for (int i = threadIdx.x; i < N; i += 256) sB[K * N + i] = bias ? bias[i] : 0.0f;
+  const bool stats = st_sum != nullptr;
+  if (stats) for (int i = threadIdx.x; i < 2 * N; i += 256) sB[K * N + N + i] = 0.0f;
   __syncthreads();
   const int n4 = N / 4, rows_per_step = 256 / n4;
   const int cq = (threadIdx.x % n4) * 4, rl = threadIdx.x / n4;
-  if (rl >= rows_per_step) return;
-  for (long long m = (long long)blockIdx.x * rows_per_step + rl; m < M; m += (long long)gridDim.x * rows_per_step) {
-    const float* a = A + m * lda;
-    float4 acc = *reinterpret_cast<const float4*>(&sB[K * N + cq]);
-    for (int k = 0; k < K; ++k) {
-      const float x = __ldg(a + k);
-      const float4 w = *reinterpret_cast<const float4*>(&sB[k * N + cq]);
-      acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
+  if (rl < rows_per_step) {
+    // training-mode BN statistics of the output (fused): this thread's 4 columns over all its rows, in registers
+    float4 sf = make_float4(0.f, 0.f, 0.f, 0.f), s1 = sf, s2 = sf;
+    if (stats && st_shift) sf = make_float4(st_shift[cq], st_shift[cq + 1], st_shift[cq + 2], st_shift[cq + 3]);
+    for (long long m = (long long)blockIdx.x * rows_per_step + rl; m < M; m += (long long)gridDim.x * rows_per_step) {
+      const float* a = A + m * lda;
+      float4 acc = *reinterpret_cast<const float4*>(&sB[K * N + cq]);
+      for (int k = 0; k < K; ++k) {
+        const float x = __ldg(a + k);
+        const float4 w = *reinterpret_cast<const float4*>(&sB[k * N + cq]);
+        acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
+      }
+      if (act != 0) { acc.x = apply_act(acc.x, act); acc.y = apply_act(acc.y, act); acc.z = apply_act(acc.z, act); acc.w = apply_act(acc.w, act); }
+      *reinterpret_cast<float4*>(C + m * ldc + cq) = acc;
+      if (stats) {
+        const float d0 = acc.x - sf.x, d1 = acc.y - sf.y, d2 = acc.z - sf.z, d3 = acc.w - sf.w;
+        s1.x += d0; s1.y += d1; s1.z += d2; s1.w += d3;
+        s2.x = fmaf(d0, d0, s2.x); s2.y = fmaf(d1, d1, s2.y); s2.z = fmaf(d2, d2, s2.z); s2.w = fmaf(d3, d3, s2.w);
+      }
     }
-    if (act != 0) { acc.x = apply_act(acc.x, act); acc.y = apply_act(acc.y, act); acc.z = apply_act(acc.z, act); acc.w = apply_act(acc.w, act); }
-    *reinterpret_cast<float4*>(C + m * ldc + cq) = acc;
+    if (stats) {
+      float* q = &sB[K * N + N + cq];
+      atomicAdd(q, s1.x); atomicAdd(q + 1, s1.y); atomicAdd(q + 2, s1.z); atomicAdd(q + 3, s1.w);
+      q += N;
+      atomicAdd(q, s2.x); atomicAdd(q + 1, s2.y); atomicAdd(q + 2, s2.z); atomicAdd(q + 3, s2.w);
+    }
   }
+  if (stats) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += 256) { atomicAdd(st_sum + i, sB[K * N + N + i]); atomicAdd(st_sq + i, sB[K * N + 2 * N + i]); }
+  }
+}
+
+// y0[n] = sum_k a(k) B[k, n] + bias[n] for one row a, a(k) = relu(a_scale[k] * a[k] + a_shift[k]) when a_scale != null
+__global__ void __launch_bounds__(128) row0_kernel(const float* __restrict__ a, const float* __restrict__ a_scale,
+                                                  const float* __restrict__ a_shift, const float* __restrict__ B, int ldb,
+                                                  const float* __restrict__ bias, int K, int N, float* __restrict__ y0) {
+  const int n = blockIdx.x * 128 + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.0f;
+  for (int k = 0; k < K; ++k) {
+    float x = a[k];
+    if (a_scale) x = fmaxf(fmaf(a_scale[k], x, a_shift[k]), 0.0f);
+    acc = fmaf(x, B[(size_t)k * ldb + n], acc);
+  }
+  y0[n] = acc + (bias ? bias[n] : 0.0f);
 }
 
 // (b) C[M,N] = A[M,K] . B^T with B stored [N,K] row-major (B(k,n) = B[n*ldb + k]), N <= 16, K % 4 == 0, K <= 1024:

@@ -810,31 +810,44 @@ extern "C" int t3d_seg_stage2_x2(const void* point_feat, const float* gbias, con
 }
 
 // ----------------------------------------------------------------------------- training-step kernels
-extern "C" int t3d_gemm_f32_ws(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
-                               int ldc, int M, int N, int K, int splitk, const float* bias, void* ws, size_t ws_bytes,
-                               t3d_stream_t stream) {
+// Extras of the training-mode layers (t3d_gemm_bn_f32): lazy batch norm of the A operand and fused output statistics.
+struct GemmBnExtras {
+  const float* a_scale = nullptr; const float* a_shift = nullptr;      // A := relu(a_scale[c] * A + a_shift[c])
+  float* st_sum = nullptr; float* st_sq = nullptr; const float* st_shift = nullptr;
+  bool any() const { return a_scale != nullptr || st_sum != nullptr; }
+};
+
+static int gemm_f32_impl(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
+                         int ldc, int M, int N, int K, int splitk, const float* bias, void* ws, size_t ws_bytes,
+                         t3d_stream_t stream, const GemmBnExtras& x) {
   if (!A || !B || !C) return T3D_ERR_ARG;
   if (M <= 0 || N <= 0 || K <= 0 || splitk <= 0 || ldc < N) return T3D_ERR_SHAPE;
   if ((sam != 1 && sak != 1) || (sbk != 1 && sbn != 1)) return T3D_ERR_SHAPE;
   if (splitk > 1) T3D_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, S(stream)));
-  GemmArgs a{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias};
+  GemmArgs a{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias, x.st_sum, x.st_sq, x.st_shift};
+  if (x.st_sum != nullptr) {
+    T3D_CUDA(cudaMemsetAsync(x.st_sum, 0, sizeof(float) * N, S(stream)));
+    T3D_CUDA(cudaMemsetAsync(x.st_sq, 0, sizeof(float) * N, S(stream)));
+  }
   {   // HBM-bound first-layer shapes (skinny_gemm.cuh); 128-bit accesses need aligned bases and leading dimensions
     auto al16 = [](const void* p) { return (((uintptr_t)p) & 15) == 0; };
     const int sms = xg_num_sms();
     if (M >= 4096 && K <= kSkinnyMax && sak == 1 && sbn == 1 && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && al16(C) && ldc % 4 == 0 &&
-        sizeof(float) * (size_t)(K * N + N) <= kSkinnySmemMax) {
+        sizeof(float) * (size_t)(K * N + 3 * N) <= kSkinnySmemMax && x.a_scale == nullptr) {
       if (splitk > 1) { /* C was zeroed above; a single pass writes every element */ }
-      skinny_k_kernel<<<sms * 8, 256, sizeof(float) * (size_t)(K * N + N), S(stream)>>>(A, sam, B, sbk, bias, C, ldc, M, N, K);
+      skinny_k_kernel<<<sms * 8, 256, sizeof(float) * (size_t)(K * N + 3 * N), S(stream)>>>(A, sam, B, sbk, bias, C, ldc, M, N, K, 0,
+                                                                                             x.st_sum, x.st_sq, x.st_shift);
       T3D_CHECK_LAUNCH();
       return 0;
     }
-    if (M >= 4096 && N <= kSkinnyMax && sak == 1 && sbk == 1 && sbn != 1 && K % 4 == 0 && K <= 1024 && al16(A) && sam % 4 == 0 &&
+    if (x.any() && !xg_fits(M, N, K)) return T3D_ERR_SHAPE;      // the extras exist on the tensor-core path (and skinny_k) only
+    if (!x.any() && M >= 4096 && N <= kSkinnyMax && sak == 1 && sbk == 1 && sbn != 1 && K % 4 == 0 && K <= 1024 && al16(A) && sam % 4 == 0 &&
         sizeof(float) * (size_t)N * K <= kSkinnySmemMax) {
       skinny_n_kernel<<<sms * 8, 256, sizeof(float) * (size_t)N * K, S(stream)>>>(A, sam, B, sbn, bias, C, ldc, M, N, K);
       T3D_CHECK_LAUNCH();
       return 0;
     }
-    if (K >= 4096 && M <= kSkinnyMax && sam == 1 && sbn == 1 && !bias && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && al16(B) &&
+    if (!x.any() && K >= 4096 && M <= kSkinnyMax && sam == 1 && sbn == 1 && !bias && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 && al16(B) &&
         sbk % 4 == 0 && (size_t)M * N * sizeof(float) <= kSkinnySmemMax) {
       if (splitk <= 1) T3D_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, S(stream)));
       skinny_m_kernel<<<sms * 4, 256, sizeof(float) * (size_t)M * N, S(stream)>>>(A, sak, B, sbk, C, ldc, M, N, K);
@@ -866,9 +879,18 @@ extern "C" int t3d_gemm_f32_ws(const float* A, long long sam, long long sak, con
     const bool ak = (sak == 1), bk = (sbk == 1 && sbn != 1);
     const int ntm = (M + kXgBM - 1) / kXgBM, ntn = (N + kXgBN - 1) / kXgBN;
     const long long lda = ak ? sam : sak, ldb = bk ? sbn : sbk;
-    XgOperands o{A, lda, B, ldb, M, N, K, kchunk, (ak && xg_aligned16(A, lda)) ? 1 : 0, (bk && xg_aligned16(B, ldb)) ? 1 : 0, ntn, g_trace, nullptr, 0};
+    XgOperands o{A, lda, B, ldb, M, N, K, kchunk, (ak && xg_aligned16(A, lda)) ? 1 : 0, (bk && xg_aligned16(B, ldb)) ? 1 : 0, ntn, g_trace, nullptr, 0,
+                 x.a_scale, x.a_shift};
     const dim3 grid((unsigned)ntm * ntn, nz);
-    if (ak && nz == 1 && sk == 1 && xg_pre_ok(M, N, K, ws, ws_bytes)) {     // forward / dgrad: pre-split B
+    const bool pre = ak && nz == 1 && sk == 1 && xg_pre_ok(M, N, K, ws, ws_bytes);
+    if (x.any()) {
+      // lazy BN of a k-contiguous A lives in the pre-split-B loaders (128-bit parameter loads: K % 32 == 0, aligned arrays);
+      // of a row-contiguous A (wgrad) in the generic loader.  Statistics need the whole K range in one CTA.
+      if (x.a_scale && ak && (!pre || K % kXgBK != 0 || (((uintptr_t)x.a_scale | (uintptr_t)x.a_shift) & 15))) return T3D_ERR_SHAPE;
+      if (x.a_scale && !ak && pre) return T3D_ERR_SHAPE;
+      if (x.st_sum && sk != 1) return T3D_ERR_SHAPE;
+    }
+    if (pre) {     // forward / dgrad: pre-split B
       o.bpre = reinterpret_cast<const uint8_t*>(ws);
       o.nkb = (K + 63) / 64;
       const int parts = g_f32_engine == 1 ? 3 : 1;
@@ -917,24 +939,73 @@ extern "C" int t3d_gemm_f32_ws(const float* A, long long sam, long long sak, con
   return 0;
 }
 
+extern "C" int t3d_gemm_f32_ws(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
+                               int ldc, int M, int N, int K, int splitk, const float* bias, void* ws, size_t ws_bytes,
+                               t3d_stream_t stream) {
+  return gemm_f32_impl(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias, ws, ws_bytes, stream, GemmBnExtras{});
+}
+
+// Can t3d_gemm_bn_f32 serve this problem?  kind 0: forward (k-contiguous A, lazy BN by k and / or output statistics),
+// kind 1: wgrad (row-contiguous A, lazy BN by row).  Mirrors the dispatch of gemm_f32_impl.
+extern "C" int t3d_gemm_bn_supported(int M, int N, int K, int kind) {
+  if (kind == 0) {
+    if (M >= 4096 && K <= kSkinnyMax && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 &&
+        sizeof(float) * (size_t)(K * N + 3 * N) <= kSkinnySmemMax)
+      return 2;                                     // first-layer kernel: statistics only (its input is never a lazy BN)
+    return (xg_fits(M, N, K) && M >= 4096 && K <= kXgMaxKChunk && K % kXgBK == 0) ? 1 : 0;
+  }
+  if (kind == 1) return (xg_fits(M, N, K) && !(K >= 4096 && M <= kSkinnyMax)) ? 1 : 0;
+  return 0;
+}
+
+extern "C" int t3d_gemm_bn_f32(const float* A, long long sam, long long sak, const float* a_scale, const float* a_shift,
+                               const float* B, long long sbk, long long sbn, float* C, int ldc, int M, int N, int K, int splitk,
+                               const float* bias, float* st_sum, float* st_sq, const float* st_shift, void* ws, size_t ws_bytes,
+                               t3d_stream_t stream) {
+  if ((a_scale != nullptr) != (a_shift != nullptr) || (st_sum != nullptr) != (st_sq != nullptr)) return T3D_ERR_ARG;
+  GemmBnExtras x;
+  x.a_scale = a_scale; x.a_shift = a_shift; x.st_sum = st_sum; x.st_sq = st_sq; x.st_shift = st_shift;
+  return gemm_f32_impl(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias, ws, ws_bytes, stream, x);
+}
+
+// y0[n] = sum_k a(k) W[k, n] + bias[n] for ONE row a (lazy BN applied when a_scale != null): the shift of the fused statistics
+extern "C" int t3d_row0(const float* a, const float* a_scale, const float* a_shift, const float* W, int ldw, const float* bias,
+                        int K, int N, float* y0, t3d_stream_t stream) {
+  if (!a || !W || !y0 || K <= 0 || N <= 0) return T3D_ERR_ARG;
+  row0_kernel<<<(N + 127) / 128, 128, 0, S(stream)>>>(a, a_scale, a_shift, W, ldw, bias, K, N, y0);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int t3d_gemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
                             int ldc, int M, int N, int K, int splitk, const float* bias, t3d_stream_t stream) {
   return t3d_gemm_f32_ws(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias, nullptr, 0, stream);
 }
 
-extern "C" int t3d_colstats(const float* X, const float* out, const float* y, const float* mean, const float* rstd, float* o0,
-                            float* o1, int M, int C, int mode, int act, t3d_stream_t stream) {
+static int colstats_impl(const float* X, const float* out, const float* y, const float* mean, const float* rstd, float* o0,
+                         float* o1, int M, int C, int mode, int act, const float* a_scale, const float* a_shift, t3d_stream_t stream) {
   if (!X || !o0 || !o1 || (mode == 1 && (!y || !mean || !rstd))) return T3D_ERR_ARG;
   if (M <= 0 || C <= 0 || (mode != 0 && mode != 1) || act < 0 || act > 3) return T3D_ERR_SHAPE;
+  if ((a_scale != nullptr) != (a_shift != nullptr) || (a_scale && (out || mode != 1 || act != 1))) return T3D_ERR_ARG;
   T3D_CUDA(cudaMemsetAsync(o0, 0, sizeof(float) * C, S(stream)));
   T3D_CUDA(cudaMemsetAsync(o1, 0, sizeof(float) * C, S(stream)));
-  ColStatArgs a{X, out, y, mean, rstd, o0, o1, M, C, mode, act};
+  ColStatArgs a{X, out, y, mean, rstd, o0, o1, M, C, mode, act, a_scale, a_shift};
   int chunks = (M + 511) / 512;
   if (chunks > 1024) chunks = 1024;
   dim3 grid((C + 31) / 32, chunks);
   colstats_kernel<<<grid, 256, 0, S(stream)>>>(a);
   T3D_CHECK_LAUNCH();
   return 0;
+}
+extern "C" int t3d_colstats(const float* X, const float* out, const float* y, const float* mean, const float* rstd, float* o0,
+                            float* o1, int M, int C, int mode, int act, t3d_stream_t stream) {
+  return colstats_impl(X, out, y, mean, rstd, o0, o1, M, C, mode, act, nullptr, nullptr, stream);
+}
+// BN-backward reductions of a lazy BN layer (no stored output): ReLU mask = a_scale * y + a_shift > 0
+extern "C" int t3d_colstats_lazy(const float* dOut, const float* y, const float* mean, const float* rstd, const float* a_scale,
+                                 const float* a_shift, float* s1, float* s2, int M, int C, t3d_stream_t stream) {
+  if (!a_scale || !a_shift) return T3D_ERR_ARG;
+  return colstats_impl(dOut, nullptr, y, mean, rstd, s1, s2, M, C, 1, 1, a_scale, a_shift, stream);
 }
 
 extern "C" int t3d_bn_finalize(const float* sum, const float* sumsq, const float* shift, int M, int C, float eps, float decay,
@@ -961,18 +1032,68 @@ extern "C" int t3d_bn_apply(const float* y, const float* mean, const float* rstd
   return 0;
 }
 
-extern "C" int t3d_bn_backward(float* dOut, const float* out, const float* y, const float* mean, const float* rstd,
-                               const float* gamma, const float* s1, const float* s2, int M, int C, int act, t3d_stream_t stream) {
+static int bn_backward_impl(float* dOut, const float* out, const float* y, const float* mean, const float* rstd,
+                            const float* gamma, const float* s1, const float* s2, int M, int C, int act, const float* a_scale,
+                            const float* a_shift, t3d_stream_t stream) {
   if (!dOut || !y || !mean || !rstd || !gamma || !s1 || !s2) return T3D_ERR_ARG;
   if (act < 0 || act > 3) return T3D_ERR_SHAPE;
+  if ((a_scale != nullptr) != (a_shift != nullptr) || (a_scale && (out || act != 1))) return T3D_ERR_ARG;
   const size_t total = (size_t)M * C;
-  if (ew4_ok(total, C, {dOut, out, y}) && C <= 2048) {
+  if (ew4_ok(total, C, {dOut, out, y}) && C <= (a_scale ? 1536 : 2048)) {
     using F4 = const float4*;
-    bn_backward4_kernel<<<(ew4_grid(total) + kBnIter - 1) / kBnIter, 256, sizeof(float) * 5 * (size_t)C, S(stream)>>>((float4*)dOut, (F4)out, (F4)y, mean, rstd, gamma, s1, s2,
-                                                                (unsigned)(total / 4), (unsigned)(C / 4), M, act);
+    bn_backward4_kernel<<<(ew4_grid(total) + kBnIter - 1) / kBnIter, 256, sizeof(float) * (a_scale ? 7 : 5) * (size_t)C, S(stream)>>>((float4*)dOut, (F4)out, (F4)y, mean, rstd, gamma, s1, s2,
+                                                                (unsigned)(total / 4), (unsigned)(C / 4), M, act, a_scale, a_shift);
   } else {
-    bn_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(dOut, out, y, mean, rstd, gamma, s1, s2, total, C, M, act);
+    bn_backward_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(dOut, out, y, mean, rstd, gamma, s1, s2, total, C, M, act, a_scale, a_shift);
   }
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int t3d_bn_backward(float* dOut, const float* out, const float* y, const float* mean, const float* rstd,
+                               const float* gamma, const float* s1, const float* s2, int M, int C, int act, t3d_stream_t stream) {
+  return bn_backward_impl(dOut, out, y, mean, rstd, gamma, s1, s2, M, C, act, nullptr, nullptr, stream);
+}
+extern "C" int t3d_bn_backward_lazy(float* dOut, const float* y, const float* mean, const float* rstd, const float* gamma,
+                                    const float* a_scale, const float* a_shift, const float* s1, const float* s2, int M, int C,
+                                    t3d_stream_t stream) {
+  if (!a_scale || !a_shift) return T3D_ERR_ARG;
+  return bn_backward_impl(dOut, nullptr, y, mean, rstd, gamma, s1, s2, M, C, 1, a_scale, a_shift, stream);
+}
+
+extern "C" int t3d_bn_finalize_affine(const float* sum, const float* sumsq, const float* shift, int M, int C, float eps, float decay,
+                                      const float* gamma, const float* beta, float* mean, float* rstd, float* a_scale,
+                                      float* a_shift, float* moving_mean, float* moving_var, t3d_stream_t stream) {
+  if (!sum || !sumsq || !gamma || !beta || !mean || !rstd || !a_scale || !a_shift || ((moving_mean != nullptr) != (moving_var != nullptr)))
+    return T3D_ERR_ARG;
+  bn_finalize_affine_kernel<<<(C + 127) / 128, 128, 0, S(stream)>>>(sum, sumsq, shift, M, C, eps, decay, gamma, beta, mean, rstd, a_scale,
+                                                                  a_shift, moving_mean, moving_var);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
+// Backward of [BN -> ReLU -> (x rowmask) -> max over the N rows of each group] of a lazy BN layer (train_ops.cuh): writes the
+// BN input gradient dY [B*N, C] and s1 = d beta, s2 = d gamma from the pooled gradient g [B, C] and the arg-max rows.
+extern "C" int t3d_pool_bn_backward(const float* g, const int* arg, const float* rowmask, const float* y, const float* mean,
+                                    const float* rstd, const float* gamma, const float* a_scale, const float* a_shift, int B, int N,
+                                    int C, float* s1, float* s2, float* dY, t3d_stream_t stream) {
+  if (!g || !arg || !y || !mean || !rstd || !gamma || !a_scale || !a_shift || !s1 || !s2 || !dY) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0 || C <= 0) return T3D_ERR_SHAPE;
+  T3D_CUDA(cudaMemsetAsync(s1, 0, sizeof(float) * C, S(stream)));
+  T3D_CUDA(cudaMemsetAsync(s2, 0, sizeof(float) * C, S(stream)));
+  PoolBnBwdArgs a{g, arg, rowmask, y, mean, rstd, gamma, a_scale, a_shift, s1, s2, dY, B, N, C};
+  int chunks = (B + 7) / 8;
+  if (chunks > 64) chunks = 64;
+  pool_bn_stats_kernel<<<dim3((C + 31) / 32, chunks), dim3(32, 8), 0, S(stream)>>>(a);
+  const int M = B * N;
+  const size_t total = (size_t)M * C;
+  if (ew4_ok(total, C, {y, dY}) && C <= 2048) {
+    const unsigned n4 = (unsigned)(total / 4);
+    pool_bn_dense_kernel<<<(n4 + 4095) / 4096, 256, sizeof(float) * 3 * (size_t)C, S(stream)>>>((const float4*)y, mean, rstd, gamma, s1, s2,
+                                                                                             (float4*)dY, n4, (unsigned)(C / 4), M);
+  } else {
+    pool_bn_dense_scalar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, S(stream)>>>(y, mean, rstd, gamma, s1, s2, dY, total, C, M);
+  }
+  pool_bn_scatter_kernel<<<(B * C + 255) / 256, 256, 0, S(stream)>>>(a);
   T3D_CHECK_LAUNCH();
   return 0;
 }
@@ -981,6 +1102,14 @@ extern "C" int t3d_maxpool_masked_fwd(const float* x, const float* rowmask, int 
                                       t3d_stream_t stream) {
   if (!x || !out || !arg) return T3D_ERR_ARG;
   maxpool_fwd_kernel<<<(B * C + 255) / 256, 256, 0, S(stream)>>>(x, rowmask, B, N, C, out, arg);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+// pooled = max_n relu(a_scale[c] * y + a_shift[c]) (* rowmask): the max-pool reads the pre-BN tensor of a lazy BN layer
+extern "C" int t3d_maxpool_lazy_fwd(const float* y, const float* a_scale, const float* a_shift, const float* rowmask, int B, int N,
+                                    int C, float* out, int* arg, t3d_stream_t stream) {
+  if (!y || !a_scale || !a_shift || !out || !arg) return T3D_ERR_ARG;
+  maxpool_fwd_kernel<<<(B * C + 255) / 256, 256, 0, S(stream)>>>(y, rowmask, B, N, C, out, arg, a_scale, a_shift);
   T3D_CHECK_LAUNCH();
   return 0;
 }

@@ -17,6 +17,9 @@ struct GemmArgs {
   float* C; int ldc;
   int M, N, K, splitk;
   const float* bias;        // [N], added by split 0 (may be null)
+  // fused batch-norm statistics of C (tensor-core path, splitk == 1): st_sum[n] += sum_m (C - st_shift[n]),
+  // st_sq[n] += sum_m (C - st_shift[n])^2; zero-initialised by the caller.  null: off
+  float* st_sum; float* st_sq; const float* st_shift;
 };
 
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs a) {
@@ -117,6 +120,9 @@ struct ColStatArgs {
   const float* mean; const float* rstd;
   float* o0; float* o1;
   int M, C, mode, act;
+  // lazy BN layers keep no post-activation tensor: the ReLU mask is recomputed as a_scale[c] * y + a_shift[c] > 0, the
+  // expression the consumer's loader evaluated in the forward pass (out must be null then)
+  const float* a_scale; const float* a_shift;
 };
 __global__ void __launch_bounds__(256) colstats_kernel(const ColStatArgs a) {
   // block: 32 columns x 8 row-lanes; grid.x over column groups, grid.y over row chunks
@@ -128,13 +134,16 @@ __global__ void __launch_bounds__(256) colstats_kernel(const ColStatArgs a) {
   if (c < a.C) {
     const float mu = a.mode == 1 ? a.mean[c] : 0.f, rs = a.mode == 1 ? a.rstd[c] : 0.f;
     const float shift = (a.mode == 0 && a.y) ? a.y[c] : 0.f;
+    const float asc = a.a_scale ? a.a_scale[c] : 0.f, ash = a.a_scale ? a.a_shift[c] : 0.f;
     for (int r = r0 + rl; r < r1; r += 8) {
       const size_t i = (size_t)r * a.C + c;
       if (a.mode == 0) { const float x = a.X[i] - shift; s0 += x; s1 = fmaf(x, x, s1); }
       else {
         float dy = a.X[i];
+        const float yv = a.y[i];
         if (a.out) dy *= act_grad_from_out(a.out[i], a.act);
-        s0 += dy; s1 = fmaf(dy, (a.y[i] - mu) * rs, s1);
+        else if (a.a_scale) dy = fmaf(asc, yv, ash) > 0.0f ? dy : 0.0f;
+        s0 += dy; s1 = fmaf(dy, (yv - mu) * rs, s1);
       }
     }
   }
@@ -164,6 +173,26 @@ __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const f
   }
 }
 
+// same, plus the folded affine map of the lazy BN layers: scale = gamma * rstd, shift = beta - mean * scale
+__global__ void bn_finalize_affine_kernel(const float* sum, const float* sumsq, const float* shift, int M, int C, float eps, float decay,
+                                          const float* gamma, const float* beta, float* mean, float* rstd, float* a_scale,
+                                          float* a_shift, float* moving_mean, float* moving_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float md = sum[c] / (float)M;
+  const float var = fmaxf(sumsq[c] / (float)M - md * md, 0.0f);
+  const float mu = md + (shift ? shift[c] : 0.0f);
+  const float rs = 1.0f / sqrtf(var + eps);
+  mean[c] = mu; rstd[c] = rs;
+  const float sc = gamma[c] * rs;
+  a_scale[c] = sc; a_shift[c] = beta[c] - mu * sc;
+  if (moving_mean) {
+    moving_mean[c] = decay * moving_mean[c] + (1.0f - decay) * mu;
+    const float unb = var * ((float)M / (float)max(M - 1, 1));
+    moving_var[c] = decay * moving_var[c] + (1.0f - decay) * unb;
+  }
+}
+
 // out = act(gamma * (y - mean) * rstd + beta)
 __global__ void bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ out,
@@ -178,12 +207,14 @@ __global__ void bn_apply_kernel(const float* __restrict__ y, const float* __rest
 // dY = gamma*rstd * (dy - s1/M - xhat*s2/M), dy = dOut*act'(out) ; written over dOut (in place)
 __global__ void bn_backward_kernel(float* __restrict__ dOut, const float* __restrict__ out, const float* __restrict__ y,
                                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                   const float* __restrict__ s1, const float* __restrict__ s2, size_t total, int C, int M, int act) {
+                                   const float* __restrict__ s1, const float* __restrict__ s2, size_t total, int C, int M, int act,
+                                   const float* __restrict__ a_scale = nullptr, const float* __restrict__ a_shift = nullptr) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
   float dy = dOut[i];
   if (out) dy *= act_grad_from_out(out[i], act);
+  else if (a_scale) dy = fmaf(a_scale[c], y[i], a_shift[c]) > 0.0f ? dy : 0.0f;
   const float xh = (y[i] - mean[c]) * rstd[c];
   const float inv = 1.0f / (float)M;
   dOut[i] = gamma[c] * rstd[c] * (dy - s1[c] * inv - xh * s2[c] * inv);
@@ -193,19 +224,29 @@ __global__ void bn_backward_kernel(float* __restrict__ dOut, const float* __rest
 // rowmask != null: the pooled tensor is x * rowmask[row] (the `net * mask` in front of the max-pool of the masked stacks,
 // semisup_models.py:184-185, 240-241) without materialising the product; its backward scales the routed gradient by the
 // mask of the arg-max row -- identical to multiplying afterwards, two passes over the activation fewer each way.
+// a_scale != null: x is the pre-BN tensor of a lazy BN layer and the pooled value is relu(a_scale[c] * x + a_shift[c]).
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ rowmask, int B, int N, int C,
-                                   float* __restrict__ out, int* __restrict__ arg) {
+                                   float* __restrict__ out, int* __restrict__ arg, const float* __restrict__ a_scale = nullptr,
+                                   const float* __restrict__ a_shift = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;        // over B*C
   if (i >= B * C) return;
   const int b = i / C, c = i % C;
   const float* p = x + (size_t)b * N * C + c;
   const float* rm = rowmask ? rowmask + (size_t)b * N : nullptr;
-  float m = rm ? p[0] * rm[0] : p[0]; int am = 0;
+  const bool lazy = a_scale != nullptr;
+  const float sc = lazy ? a_scale[c] : 1.0f, sh = lazy ? a_shift[c] : 0.0f;
+  float m = lazy ? fmaxf(fmaf(sc, p[0], sh), 0.0f) : p[0];
+  if (rm) m *= rm[0];
+  int am = 0;
   int n = 1;
   for (; n + 8 <= N; n += 8) {                                  // 8 rows in flight; compared in order: first max wins
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = p[(size_t)(n + j) * C];
+    if (lazy) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(sc, v[j], sh), 0.0f);
+    }
     if (rm) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] *= rm[n + j];
@@ -215,10 +256,114 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, const float* __r
   }
   for (; n < N; ++n) {
     float v = p[(size_t)n * C];
+    if (lazy) v = fmaxf(fmaf(sc, v, sh), 0.0f);
     if (rm) v *= rm[n];
     if (v > m) { m = v; am = n; }
   }
   out[i] = m; arg[i] = am;
+}
+
+// ---- backward of [BN -> ReLU -> (row mask) -> max-pool] without the dense pooled-gradient tensor ------------------------
+// The gradient w.r.t. the BN output is non-zero only at the B x C arg-max elements, so the two batch-norm reductions
+// (s1 = sum dy, s2 = sum dy * xhat) are O(B C) gathers instead of two passes over the B N x C tensor, and the BN input
+// gradient  dY = gamma rstd (dy - s1 / M - xhat s2 / M)  is one dense pass that reads y and writes dY plus a B x C
+// scatter.  Replaces maxpool_bwd (memset + scatter) + colstats mode 1 + bn_backward: 8 passes over the widest
+// activation of every stack become 2.
+struct PoolBnBwdArgs {
+  const float* g;            // [B, C] gradient w.r.t. the pooled features
+  const int* arg;            // [B, C] arg-max rows
+  const float* rowmask;      // [B * N] or null
+  const float* y;            // [B * N, C] pre-BN values
+  const float* mean; const float* rstd; const float* gamma;
+  const float* a_scale; const float* a_shift;      // ReLU mask = a_scale * y + a_shift > 0
+  float* s1; float* s2;      // [C] zero-initialised (= d beta, d gamma)
+  float* dY;                 // [B * N, C]
+  int B, N, C;
+};
+__device__ __forceinline__ float pool_bn_dy(const PoolBnBwdArgs& a, int i, size_t& at) {
+  const int b = i / a.C, c = i % a.C;
+  const size_t row = (size_t)b * a.N + a.arg[i];
+  at = row * a.C + c;
+  const float yv = a.y[at];
+  float dy = fmaf(a.a_scale[c], yv, a.a_shift[c]) > 0.0f ? a.g[i] : 0.0f;
+  if (a.rowmask) dy *= a.rowmask[row];
+  return dy;
+}
+__global__ void __launch_bounds__(256) pool_bn_stats_kernel(const PoolBnBwdArgs a) {      // grid (C / 32.., B chunks), block (32, 8)
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float s1 = 0.f, s2 = 0.f;
+  if (c < a.C) {
+    const float mu = a.mean[c], rs = a.rstd[c];
+    for (int b = blockIdx.y * 8 + threadIdx.y; b < a.B; b += gridDim.y * 8) {
+      size_t at;
+      const float dy = pool_bn_dy(a, b * a.C + c, at);
+      s1 += dy; s2 = fmaf(dy, (a.y[at] - mu) * rs, s2);
+    }
+  }
+  __shared__ float sh[2][8][32];
+  sh[0][threadIdx.y][threadIdx.x] = s1; sh[1][threadIdx.y][threadIdx.x] = s2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < a.C) {
+    for (int k = 1; k < 8; ++k) { s1 += sh[0][k][threadIdx.x]; s2 += sh[1][k][threadIdx.x]; }
+    atomicAdd(a.s1 + c, s1); atomicAdd(a.s2 + c, s2);
+  }
+}
+// dense part: dY = -gamma rstd (s1 + xhat s2) / M     (float4 over [M, C], parameters staged per block)
+__global__ void __launch_bounds__(256) pool_bn_dense_kernel(const float4* __restrict__ y, const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ s1, const float* __restrict__ s2,
+                                                           float4* __restrict__ dY, unsigned n4, unsigned C4, int M) {
+  extern __shared__ float4 pb_sp[];                  // [3][C4]: mean, k1 = -gamma rstd s1 / M, k2 = -gamma rstd^2 s2 / M
+  const float inv = 1.0f / (float)M;
+  for (unsigned i = threadIdx.x; i < C4; i += 256) {
+    float m[4], k1[4], k2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned c = 4u * i + e;
+      const float gr = gamma[c] * rstd[c];
+      m[e] = mean[c]; k1[e] = -gr * s1[c] * inv; k2[e] = -gr * rstd[c] * s2[c] * inv;
+    }
+    pb_sp[i] = make_float4(m[0], m[1], m[2], m[3]); pb_sp[C4 + i] = make_float4(k1[0], k1[1], k1[2], k1[3]);
+    pb_sp[2 * C4 + i] = make_float4(k2[0], k2[1], k2[2], k2[3]);
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    const unsigned base = (blockIdx.x * 4 + it) * 1024u + threadIdx.x;
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (base + u * 256u < n4) v[u] = y[base + u * 256u];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned q = base + u * 256u;
+      if (q >= n4) continue;
+      const unsigned c = q % C4;
+      const float4 m = pb_sp[c], k1 = pb_sp[C4 + c], k2 = pb_sp[2 * C4 + c];
+      float4 o;
+      o.x = fmaf(v[u].x - m.x, k2.x, k1.x); o.y = fmaf(v[u].y - m.y, k2.y, k1.y);
+      o.z = fmaf(v[u].z - m.z, k2.z, k1.z); o.w = fmaf(v[u].w - m.w, k2.w, k1.w);
+      dY[q] = o;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) pool_bn_dense_scalar_kernel(const float* __restrict__ y, const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ s1, const float* __restrict__ s2,
+                                                                  float* __restrict__ dY, size_t total, int C, int M) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C);
+  const float inv = 1.0f / (float)M, gr = gamma[c] * rstd[c];
+  dY[i] = fmaf(y[i] - mean[c], -gr * rstd[c] * s2[c] * inv, -gr * s1[c] * inv);
+}
+// sparse part (after the dense pass): dY[arg-max element] += gamma rstd dy; an element can be the arg-max of one (b, c) only
+__global__ void __launch_bounds__(256) pool_bn_scatter_kernel(const PoolBnBwdArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.B * a.C) return;
+  size_t at;
+  const float dy = pool_bn_dy(a, i, at);
+  const int c = i % a.C;
+  a.dY[at] += a.gamma[c] * a.rstd[c] * dy;
 }
 __global__ void maxpool_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ arg, const float* __restrict__ rowmask,
                                    int B, int N, int C, float* __restrict__ dx) {

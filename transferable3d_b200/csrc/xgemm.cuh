@@ -58,7 +58,17 @@ struct XgOperands {
   unsigned long long* trace;          // debug: clock64 timeline of the middle CTA (t3d_set_trace_buffer) or null
   const uint8_t* bpre;                // B_PRE kernels: pre-split images of B, [n_tile][k_block of 64][part][16 KB], else null
   int nkb;                            // k blocks per n tile in bpre
+  // Lazy batch norm of the A operand (training forward / wgrad): the value multiplied is relu(a_scale[c] * A + a_shift[c])
+  // with c the CHANNEL of the stored pre-BN activation (its k index when A is k-contiguous, its row m otherwise), so the
+  // post-BN activation of the previous layer never exists in HBM.  null: A is used as stored.  K % 32 == 0 required.
+  const float* a_scale; const float* a_shift;
 };
+
+// relu(sc * x + sh) on 4 consecutive channels
+__device__ __forceinline__ void xg_bn4(float* r, const float4& sc, const float4& sh) {
+  r[0] = fmaxf(fmaf(sc.x, r[0], sh.x), 0.0f); r[1] = fmaxf(fmaf(sc.y, r[1], sh.y), 0.0f);
+  r[2] = fmaxf(fmaf(sc.z, r[2], sh.z), 0.0f); r[3] = fmaxf(fmaf(sc.w, r[3], sh.w), 0.0f);
+}
 
 // row of the tile handled by (warp w of the operand's 4, iteration i, lane) in the UNIT_K mapping: a warp-wide 128-bit
 // load covers 4 rows x 128 B (coalesced), and the 4 rows are r, r+4 (lanes 0-15) and r+1, r+5 (lanes 16-31) of an 8-row
@@ -182,7 +192,8 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
 // sets, ping-pong).  full0 / empty0 = the stage-0 barriers (stage 1 follows at +8 bytes).
 template <bool UNIT_K, int PARTS>
 __device__ __forceinline__ void xg_loader(const float* __restrict__ P, long long ld, int row0, int nrows, int kbeg, int kend, bool vec,
-                                          uint32_t img, int w, int lane, int nst, uint32_t full0, uint32_t empty0, XgTracer& tr) {
+                                          uint32_t img, int w, int lane, int nst, uint32_t full0, uint32_t empty0, XgTracer& tr,
+                                          const float* __restrict__ tsc = nullptr, const float* __restrict__ tsh = nullptr) {
   const int row = row0 + (UNIT_K ? xg_row_unit_k(w, 0, lane) : w * 32 + lane);      // first (or only) row of this thread
   const int kofs = UNIT_K ? 4 * (lane & 7) : 0;
   const float* p = UNIT_K ? P + (long long)row * ld + kbeg + kofs : P + (long long)kbeg * ld + row;
@@ -192,8 +203,17 @@ __device__ __forceinline__ void xg_loader(const float* __restrict__ P, long long
     const int k0 = kbeg + it * kXgBK;
     xg_load<UNIT_K>(p + (long long)it * pstep, ld, rows_full && (k0 + kXgBK <= kend), row, nrows, k0 + kofs, kend, r);
   };
-  auto emit = [&](int it, const float (&r)[32]) {
+  // lazy BN of a row-contiguous operand (wgrad: A = X^T, row = channel of X): one scale / shift pair per thread; k past the
+  // end of the range and rows past the operand stay zero
+  const bool bn = !UNIT_K && tsc != nullptr;
+  const float bsc = (bn && row < nrows) ? __ldg(tsc + row) : 0.0f, bsh = (bn && row < nrows) ? __ldg(tsh + row) : 0.0f;
+  auto emit = [&](int it, float (&r)[32]) {
     const int s = it & 1;
+    if (bn) {
+      const int k0 = kbeg + it * kXgBK;
+#pragma unroll
+      for (int kk = 0; kk < 32; ++kk) r[kk] = (row < nrows && k0 + kk < kend) ? fmaxf(fmaf(bsc, r[kk], bsh), 0.0f) : 0.0f;
+    }
     mbar_wait_backoff(empty0 + 8u * s, ((it >> 1) & 1) ^ 1);
     tr.mark(0x20);
     xg_split_store<UNIT_K, PARTS>(img, s, w, lane, r);
@@ -271,7 +291,8 @@ __device__ __forceinline__ void cp_async_wait_all() {
 template <int PARTS>
 __device__ __forceinline__ void xg_loader_pre(const float* __restrict__ P, long long ld, int row0, int nrows, int kend, bool vec,
                                               uint32_t a_img, uint32_t b_img, const uint8_t* __restrict__ bsrc, int w, int lane, int nst,
-                                              uint32_t full0, uint32_t empty0, XgTracer& tr) {
+                                              uint32_t full0, uint32_t empty0, XgTracer& tr,
+                                              const float* __restrict__ tsc = nullptr, const float* __restrict__ tsh = nullptr) {
   const int rsub = lane >> 3, c = lane & 7;
   auto rowof = [&](int i) { return w * 16 + (i >> 1) * 8 + (i & 1) * 2 + (rsub & 1) * 4 + (rsub >> 1); };
   const int row = row0 + rowof(0), kofs = 4 * c;
@@ -301,8 +322,14 @@ __device__ __forceinline__ void xg_loader_pre(const float* __restrict__ P, long 
     }
   };
   const int tid = w * 32 + lane;
-  auto emit = [&](int it, const float (&r)[16]) {
+  auto emit = [&](int it, float (&r)[16]) {
     const int s = it & 1;
+    if (tsc != nullptr) {      // lazy BN: this thread's 4 channels of the stage (issued before the slot wait)
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(tsc + it * kXgBK + kofs));
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(tsh + it * kXgBK + kofs));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xg_bn4(&r[4 * i], sc, sh);
+    }
     mbar_wait_backoff(empty0 + 8u * s, ((it >> 1) & 1) ^ 1);
     tr.mark(0x20);
     {   // B stage: PARTS x 128 rows x 4 chunks of 16 B, same swizzled offsets in the workspace block and in shared memory
@@ -396,8 +423,10 @@ __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_r
   if (warp < 8) {
     // ---------------------------------------------------------------- loaders: global fp32 -> registers -> 3 bf16 images
     if (B_PRE) xg_loader_pre<PARTS>(o.A, o.lda, m0, o.M, kend, o.vecA != 0, sbase, sbase + 3u * kXgImage,
-                                    o.bpre + (size_t)(blockIdx.x % o.ntn) * o.nkb * kXgPreBlockBytes, warp, lane, nst, full(0), empty(0), tr);
-    else if (warp < 4) xg_loader<A_UNIT_K, PARTS>(o.A, o.lda, m0, o.M, kbeg, kend, o.vecA != 0, sbase, warp & 3, lane, nst, full(0), empty(0), tr);
+                                    o.bpre + (size_t)(blockIdx.x % o.ntn) * o.nkb * kXgPreBlockBytes, warp, lane, nst, full(0), empty(0), tr,
+                                    o.a_scale, o.a_shift);
+    else if (warp < 4) xg_loader<A_UNIT_K, PARTS>(o.A, o.lda, m0, o.M, kbeg, kend, o.vecA != 0, sbase, warp & 3, lane, nst, full(0), empty(0), tr,
+                                                  o.a_scale, o.a_shift);
     else xg_loader<B_UNIT_K, PARTS>(o.B, o.ldb, n0, o.N, kbeg, kend, o.vecB != 0, sbase + 3u * kXgImage, warp & 3, lane, nst, full(0), empty(0), tr);
     mbar_wait_backoff(acc_full, 0);
     tc_fence_after();
@@ -474,9 +503,13 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // Patch rows are 144 bytes apart, so both the 128-bit writes (thread = row) and reads (8 lanes = one row) are
 // conflict-free.
 constexpr uint32_t kXgPatchRow = 144, kXgPatchBytes = 32 * kXgPatchRow;
-template <bool ATOMIC>
+// STATS: the column sums of (x - shift[col]) and of its square over the chunk's valid rows are added to st_sum / st_sq
+// (training-mode batch norm: the statistics pass over the layer output is fused here; shift = row 0 of the output keeps
+// E[d^2] - E[d]^2 well conditioned).  Each lane sums its 8 rows of 4 columns, two shuffles fold the 4 row groups.
+template <bool ATOMIC, bool STATS = false>
 __device__ __forceinline__ void xg_store_chunk(const XgTile& t, float* __restrict__ C, long long ldc, int M, int N, int row0, int col0,
-                                               const float (&v)[32]) {
+                                               const float (&v)[32], float* __restrict__ st_sum = nullptr,
+                                               float* __restrict__ st_sq = nullptr, const float* __restrict__ st_shift = nullptr) {
   const uint32_t patch = t.sbase + (uint32_t)t.warp * kXgPatchBytes;
   __syncwarp();                                          // the previous chunk's reads are done
 #pragma unroll
@@ -485,11 +518,21 @@ __device__ __forceinline__ void xg_store_chunk(const XgTile& t, float* __restric
                  __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
   __syncwarp();
   const int cq = (t.lane & 7) * 4, gn = col0 + cq;
+  float ss[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f}, sf[4] = {0.f, 0.f, 0.f, 0.f};
+  if (STATS && st_shift != nullptr) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sf[e] = (gn + e < N) ? __ldg(st_shift + gn + e) : 0.0f;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = (t.lane >> 3) + 4 * i, gm = row0 + r;
     const float4 x = ld_shared_f4(patch + (uint32_t)r * kXgPatchRow + 4u * cq);
     if (gm >= M || gn >= N) continue;
+    if (STATS) {
+      const float d0 = x.x - sf[0], d1 = x.y - sf[1], d2 = x.z - sf[2], d3 = x.w - sf[3];
+      ss[0] += d0; ss[1] += d1; ss[2] += d2; ss[3] += d3;
+      sq[0] = fmaf(d0, d0, sq[0]); sq[1] = fmaf(d1, d1, sq[1]); sq[2] = fmaf(d2, d2, sq[2]); sq[3] = fmaf(d3, d3, sq[3]);
+    }
     float* c = C + (long long)gm * ldc + gn;
     if (gn + 4 <= N && (((uintptr_t)c) & 15) == 0) {
       if (ATOMIC) red_add_v4(c, x.x, x.y, x.z, x.w);
@@ -502,6 +545,22 @@ __device__ __forceinline__ void xg_store_chunk(const XgTile& t, float* __restric
           if (ATOMIC) atomicAdd(c + e, xs[e]);
           else c[e] = xs[e];
         }
+      }
+    }
+  }
+  if (STATS) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ss[e] += __shfl_xor_sync(0xffffffffu, ss[e], 8); ss[e] += __shfl_xor_sync(0xffffffffu, ss[e], 16);
+      sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 8); sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 16);
+    }
+    if (t.lane < 8 && gn < N) {
+      if (gn + 4 <= N && ((((uintptr_t)(st_sum + gn)) | ((uintptr_t)(st_sq + gn))) & 15) == 0) {
+        red_add_v4(st_sum + gn, ss[0], ss[1], ss[2], ss[3]);
+        red_add_v4(st_sq + gn, sq[0], sq[1], sq[2], sq[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (gn + e < N) { atomicAdd(st_sum + gn + e, ss[e]); atomicAdd(st_sq + gn + e, sq[e]); }
       }
     }
   }
@@ -529,6 +588,7 @@ __device__ __forceinline__ void xg_epilogue_gemm(const GemmArgs& a, const XgTile
         for (int j = 0; j < 32; ++j) v[j] += q[j];
       }
       if (a.splitk > 1) xg_store_chunk<true>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v);
+      else if (a.st_sum != nullptr) xg_store_chunk<false, true>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v, a.st_sum, a.st_sq, a.st_shift);
       else xg_store_chunk<false>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v);
     }
   }
@@ -750,8 +810,16 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs g
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto emit = [&](int g, const float (&r)[kXgPPVals]) {
+    int e_it = 0;
+    auto emit = [&](int g, float (&r)[kXgPPVals]) {
       const int s = g & 3;
+      if (o.a_scale != nullptr) {      // lazy BN of A: the 4 channels of this thread in stage e_it
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(o.a_scale + e_it * kXgBK + kofs));
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(o.a_shift + e_it * kXgBK + kofs));
+#pragma unroll
+        for (int i = 0; i < NI; ++i) xg_bn4(&r[4 * i], sc, sh);
+      }
+      if (++e_it == nst) e_it = 0;
       // B runs kXgPPBAhead stages ahead (an L2 round trip is ~2 k cycles, longer than a stage): one commit group per stage
       if (g + kXgPPBAhead < total) copy_b(g + kXgPPBAhead);
       else asm volatile("cp.async.commit_group;" ::: "memory");
@@ -935,6 +1003,12 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs g
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         if (it < nst) {
+          if (o.a_scale != nullptr) {      // lazy BN of A
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(o.a_scale + it * kXgBK + kofs));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(o.a_shift + it * kXgBK + kofs));
+#pragma unroll
+            for (int i = 0; i < NI; ++i) xg_bn4(&rA[it][4 * i], sc, sh);
+          }
 #pragma unroll
           for (int i = 0; i < NI; ++i) {
             const uint32_t off = sw128_offset((uint32_t)rowof(i), (uint32_t)(4 * (it & 1) + (c >> 1))) + (uint32_t)(c & 1) * 8u;

@@ -17,7 +17,7 @@ from . import boxpc_sunrgbd
 from ._lib import ptr, stream, call, t3d_boxpc_loss_args
 from .constants import BN_EPS
 from .weights import net_table
-from .train_layers import TrainLayer, ACT_RELU, ACT_NONE
+from .train_layers import TrainLayer, ACT_RELU, ACT_NONE, maxpool
 
 BN_INIT_DECAY = 0.5
 BN_DECAY_DECAY_RATE = 0.5
@@ -107,10 +107,8 @@ class BoxPCTrainGraph(object):
         L = self.layers
         x = rep
         for l in L[:4]:
-            x = l.forward(x, bn_decay)
-        pooled = torch.empty((B, 512), device=dev)
-        self.arg = torch.empty((B, 512), dtype=torch.int32, device=dev)
-        call('t3d_maxpool_fwd', ptr(x), B, N, 512, ptr(pooled), ptr(self.arg), stream())
+            x = l.forward(x, bn_decay, lazy=True)       # lazy BN: statistics from the GEMM epilogue, BN map applied by the consumer
+        pooled, self.arg = maxpool(x, B, N, 512)
         feat = torch.cat([pooled, one_hot], dim=1).contiguous() if self.use_one_hot else pooled
         h1 = L[4].forward(feat, bn_decay)
         m1 = T(dropout_masks['dp1'])
@@ -146,9 +144,7 @@ class BoxPCTrainGraph(object):
         g = L[4].backward(gd)
         if self.use_one_hot:
             g = g[:, :512].contiguous()
-        dx = torch.empty((B * N, 512), device=dev)
-        call('t3d_maxpool_bwd', ptr(g), ptr(self.arg), B, N, 512, ptr(dx), stream())
-        g = L[3].backward(dx)
+        g = L[3].backward_pooled(g.contiguous(), self.arg, B, N)     # max-pool + BN backward without the dense pooled gradient
         g = L[2].backward(g)
         g = L[1].backward(g)
         L[0].backward(g, need_dx=False)

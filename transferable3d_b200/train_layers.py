@@ -7,7 +7,7 @@ All arithmetic runs in libt3d_b200.so kernels (fp32 CUDA-core path).
 import numpy as np
 import torch
 
-from ._lib import ptr, stream, call
+from ._lib import ptr, stream, call, gemm_workspace
 from .constants import BN_EPS
 from .weights import fold_bn
 
@@ -54,14 +54,49 @@ class ParamArena(object):
              self.flat_param.numel(), float(lr_t), beta1, beta2, eps, 1.0 / world, stream())
 
 
+class Lazy(object):
+    """Output of a lazy batch-norm layer: the pre-BN tensor y [M, C] plus the folded map of its batch norm; the value is
+    relu(scale[c] * y + shift[c]).  Consumers that can apply the map in their loaders (TrainLayer.forward / wgrad on the
+    tensor-core GEMM, maxpool) read y directly; anything else calls materialize() (one t3d_bn_apply pass, cached)."""
+
+    def __init__(self, layer):
+        self.layer, self.y, self.scale, self.shift = layer, layer.y, layer.a_scale, layer.a_shift
+        self.shape, self.device = self.y.shape, self.y.device
+        self._dense = None
+
+    def materialize(self):
+        if self._dense is None:
+            l = self.layer
+            out = torch.empty_like(self.y)
+            call('t3d_bn_apply', ptr(self.y), ptr(l.mean), ptr(l.rstd), ptr(l.p('bn/gamma')), ptr(l.p('bn/beta')), ptr(out),
+                 self.y.shape[0], self.y.shape[1], ACT_RELU, stream())
+            self._dense = out
+        return self._dense
+
+
+def dense(x):
+    return x.materialize() if isinstance(x, Lazy) else x
+
+
+def bn_supported(M, N, K, kind):
+    from ._lib import load
+    return int(load().t3d_gemm_bn_supported(int(M), int(N), int(K), int(kind)))
+
+
 class TrainLayer(object):
     """One layer in training mode.  `params`: dict name -> fp32 device tensor for '<layer>/weights', '/biases',
     '/bn/gamma', '/bn/beta'; `moving`: dict for '/bn/moving_mean', '/bn/moving_variance' (updated in the forward
-    pass, updates_collections=None); `grads`: dict of gradient views or None for a forward-only layer."""
+    pass, updates_collections=None); `grads`: dict of gradient views or None for a forward-only layer.
+
+    forward(..., lazy=True) (BN + ReLU layers) returns a Lazy instead of the activated tensor: the batch statistics come out
+    of the GEMM epilogue (t3d_gemm_bn_f32), the BN map is applied by whoever consumes the output, and the backward pass
+    recomputes the ReLU mask from y -- three of the five passes over each B*N x C activation of the forward pass and two of
+    the nine of the backward pass disappear."""
 
     def __init__(self, name, kin, nout, bn, act, params, moving, grads=None):
         self.name, self.K, self.N, self.bn, self.act = name, kin, nout, bn, act
         self.params, self.moving, self.grads = params, moving, grads
+        self.lazy_out = False
 
     def p(self, suffix):
         return self.params[self.name + '/' + suffix]
@@ -69,13 +104,32 @@ class TrainLayer(object):
     def W(self):
         return self.p('weights').view(self.K, self.N)
 
-    def forward(self, x, bn_decay, y=None, keep=True):
-        """x: (M,K) fp32.  `y`: pre-BN values computed by the caller (conv6 fold).  keep=False drops what only a
-        backward pass would need."""
+    def forward(self, x, bn_decay, y=None, keep=True, lazy=False):
+        """x: (M,K) fp32 tensor or Lazy.  `y`: pre-BN values computed by the caller (conv6 fold).  keep=False drops what only
+        a backward pass would need."""
         M = x.shape[0] if x is not None else y.shape[0]
         dev = (x if x is not None else y).device
+        lazy = bool(lazy and self.bn and self.act == ACT_RELU)
+        E = lambda: torch.empty(self.N, device=dev)
+        fused = False
         if y is None:
-            y = gemm(x, self.K, 1, self.W(), self.N, 1, M, self.N, self.K, bias=self.p('biases'))
+            kind = bn_supported(M, self.N, self.K, 0) if self.bn else 0
+            if isinstance(x, Lazy) and kind != 1:
+                x = x.materialize()
+            if kind:
+                # statistics in the GEMM epilogue, shifted by row 0 of the output (t3d_row0) as t3d_colstats does
+                xl = x if isinstance(x, Lazy) else None
+                xa = xl.y if xl is not None else x
+                sc, sh = (ptr(xl.scale), ptr(xl.shift)) if xl is not None else (None, None)
+                y0, s0, s1 = E(), E(), E()
+                call('t3d_row0', ptr(xa), sc, sh, ptr(self.W()), self.N, ptr(self.p('biases')), self.K, self.N, ptr(y0), stream())
+                y = torch.empty((M, self.N), dtype=torch.float32, device=dev)
+                ws = gemm_workspace()
+                call('t3d_gemm_bn_f32', ptr(xa), self.K, 1, sc, sh, ptr(self.W()), self.N, 1, ptr(y), self.N, M, self.N, self.K, 1,
+                     ptr(self.p('biases')), ptr(s0), ptr(s1), ptr(y0), ptr(ws), ws.numel(), stream())
+                fused = True
+            else:
+                y = gemm(x, self.K, 1, self.W(), self.N, 1, M, self.N, self.K, bias=self.p('biases'))
         if keep:
             self.x, self.y = x, y
         if not self.bn:
@@ -84,17 +138,29 @@ class TrainLayer(object):
                 raise NotImplementedError('activation without batch norm is not on the hot path')
             self.out = out if keep else None
             return out
-        s0 = torch.empty(self.N, device=dev)
-        s1 = torch.empty(self.N, device=dev)
-        # statistics of (y - row 0 of y): the per-column shift keeps the one-pass variance well conditioned
-        call('t3d_colstats', ptr(y), None, ptr(y), None, None, ptr(s0), ptr(s1), M, self.N, 0, 0, stream())
-        mean = torch.empty(self.N, device=dev)
-        rstd = torch.empty(self.N, device=dev)
-        call('t3d_bn_finalize', ptr(s0), ptr(s1), ptr(y), M, self.N, BN_EPS, float(bn_decay), ptr(mean), ptr(rstd),
-             ptr(self.moving[self.name + '/bn/moving_mean']), ptr(self.moving[self.name + '/bn/moving_variance']), stream())
+        if not fused:
+            s0, s1, y0 = E(), E(), y
+            # statistics of (y - row 0 of y): the per-column shift keeps the one-pass variance well conditioned
+            call('t3d_colstats', ptr(y), None, ptr(y), None, None, ptr(s0), ptr(s1), M, self.N, 0, 0, stream())
+        mean, rstd = E(), E()
+        mm, mv = self.moving[self.name + '/bn/moving_mean'], self.moving[self.name + '/bn/moving_variance']
+        if lazy:
+            a_scale, a_shift = E(), E()
+            call('t3d_bn_finalize_affine', ptr(s0), ptr(s1), ptr(y0), M, self.N, BN_EPS, float(bn_decay), ptr(self.p('bn/gamma')),
+                 ptr(self.p('bn/beta')), ptr(mean), ptr(rstd), ptr(a_scale), ptr(a_shift), ptr(mm), ptr(mv), stream())
+            self.y, self.mean, self.rstd, self.a_scale, self.a_shift = y, mean, rstd, a_scale, a_shift
+            res = Lazy(self)
+            self.lazy_out = True
+            self.out = None
+            if not keep:
+                self.y = None
+            return res
+        call('t3d_bn_finalize', ptr(s0), ptr(s1), ptr(y0), M, self.N, BN_EPS, float(bn_decay), ptr(mean), ptr(rstd), ptr(mm), ptr(mv),
+             stream())
         out = torch.empty_like(y)
         call('t3d_bn_apply', ptr(y), ptr(mean), ptr(rstd), ptr(self.p('bn/gamma')), ptr(self.p('bn/beta')), ptr(out),
              M, self.N, self.act, stream())
+        self.lazy_out = False
         if keep:
             self.mean, self.rstd, self.out = mean, rstd, out
         return out
@@ -112,15 +178,46 @@ class TrainLayer(object):
         if self.bn:
             s1 = torch.empty(self.N, device=dev)
             s2 = torch.empty(self.N, device=dev)
-            outp = ptr(self.out) if self.act != ACT_NONE else None
-            call('t3d_colstats', ptr(dout), outp, ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(s1), ptr(s2), M, self.N, 1,
-                 self.act, stream())
+            if self.lazy_out:
+                call('t3d_colstats_lazy', ptr(dout), ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(self.a_scale), ptr(self.a_shift),
+                     ptr(s1), ptr(s2), M, self.N, stream())
+                call('t3d_bn_backward_lazy', ptr(dout), ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(self.p('bn/gamma')),
+                     ptr(self.a_scale), ptr(self.a_shift), ptr(s1), ptr(s2), M, self.N, stream())
+            else:
+                outp = ptr(self.out) if self.act != ACT_NONE else None
+                call('t3d_colstats', ptr(dout), outp, ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(s1), ptr(s2), M, self.N, 1,
+                     self.act, stream())
+                call('t3d_bn_backward', ptr(dout), outp, ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(self.p('bn/gamma')),
+                     ptr(s1), ptr(s2), M, self.N, self.act, stream())
             if trainable:
                 g[self.name + '/bn/beta'].copy_(s1)
                 g[self.name + '/bn/gamma'].copy_(s2)
-            call('t3d_bn_backward', ptr(dout), outp, ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(self.p('bn/gamma')),
-                 ptr(s1), ptr(s2), M, self.N, self.act, stream())
-        dy = dout
+        return self._backward_gemms(dout, trainable, need_dx)
+
+    def backward_pooled(self, gpool, arg, B, N, rowmask=None, need_dx=True):
+        """Backward of this (lazy BN + ReLU) layer when its output only feeds a max-pool over the N rows of each group
+        (optionally through `* rowmask`): gpool [B, C] is the gradient w.r.t. the pooled features, `arg` the arg-max rows.
+        The pooled gradient is never scattered into a dense B*N x C tensor (t3d_pool_bn_backward)."""
+        assert self.bn and self.lazy_out
+        dev = gpool.device
+        g = self.grads
+        trainable = g is not None and (self.name + '/weights') in g
+        if not trainable and not need_dx:
+            return None
+        s1 = torch.empty(self.N, device=dev)
+        s2 = torch.empty(self.N, device=dev)
+        dY = torch.empty((B * N, self.N), dtype=torch.float32, device=dev)
+        call('t3d_pool_bn_backward', ptr(gpool), ptr(arg), ptr(rowmask), ptr(self.y), ptr(self.mean), ptr(self.rstd),
+             ptr(self.p('bn/gamma')), ptr(self.a_scale), ptr(self.a_shift), B, N, self.N, ptr(s1), ptr(s2), ptr(dY), stream())
+        if trainable:
+            g[self.name + '/bn/beta'].copy_(s1)
+            g[self.name + '/bn/gamma'].copy_(s2)
+        return self._backward_gemms(dY, trainable, need_dx)
+
+    def _backward_gemms(self, dy, trainable, need_dx):
+        M = dy.shape[0]
+        dev = dy.device
+        g = self.grads
         if not trainable:
             return gemm(dy, self.N, 1, self.W(), 1, self.N, M, self.K, self.N)
         if self.bn:
@@ -132,10 +229,17 @@ class TrainLayer(object):
             junk = torch.empty(self.N, device=dev)
             call('t3d_colstats', ptr(dy), None, None, None, None, ptr(bs), ptr(junk), M, self.N, 0, 0, stream())
             g[self.name + '/biases'].copy_(bs)
-        # wgrad: dW[K,N] = X^T dY
+        # wgrad: dW[K,N] = X^T dY   (X lazy: the BN map of the previous layer is applied by the loader, per row of X^T)
         dW = g[self.name + '/weights'].view(self.K, self.N)
-        call('t3d_gemm_f32', ptr(self.x), 1, self.K, ptr(dy), self.N, 1, ptr(dW), self.N, self.K, self.N, M,
-             splitk_for(self.K, self.N, M), None, stream())
+        x = self.x
+        sk = splitk_for(self.K, self.N, M)
+        if isinstance(x, Lazy) and bn_supported(self.K, self.N, M, 1):
+            ws = gemm_workspace()
+            call('t3d_gemm_bn_f32', ptr(x.y), 1, self.K, ptr(x.scale), ptr(x.shift), ptr(dy), self.N, 1, ptr(dW), self.N, self.K, self.N,
+                 M, sk, None, None, None, None, ptr(ws), ws.numel(), stream())
+        else:
+            x = dense(x)
+            call('t3d_gemm_f32', ptr(x), 1, self.K, ptr(dy), self.N, 1, ptr(dW), self.N, self.K, self.N, M, sk, None, stream())
         if not need_dx:
             return None
         # dgrad: dX[M,K] = dY W^T
@@ -172,10 +276,14 @@ class EvalLayer(object):
 
 
 def maxpool(x, B, N, C, rowmask=None):
-    """max over the N rows of each group (+ arg-max); rowmask: pool x * rowmask[row] without materialising it."""
+    """max over the N rows of each group (+ arg-max); rowmask: pool x * rowmask[row] without materialising it.
+    x may be a Lazy: the BN map + ReLU is applied while pooling."""
     pooled = torch.empty((B, C), dtype=torch.float32, device=x.device)
     arg = torch.empty((B, C), dtype=torch.int32, device=x.device)
-    call('t3d_maxpool_masked_fwd', ptr(x), ptr(rowmask), B, N, C, ptr(pooled), ptr(arg), stream())
+    if isinstance(x, Lazy):
+        call('t3d_maxpool_lazy_fwd', ptr(x.y), ptr(x.scale), ptr(x.shift), ptr(rowmask), B, N, C, ptr(pooled), ptr(arg), stream())
+    else:
+        call('t3d_maxpool_masked_fwd', ptr(x), ptr(rowmask), B, N, C, ptr(pooled), ptr(arg), stream())
     return pooled, arg
 
 

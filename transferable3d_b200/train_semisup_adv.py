@@ -31,7 +31,7 @@ from .constants import NUM_HEADING_BIN, NUM_SIZE_CLUSTER, NUM_CLASS, MEAN_DIMS_A
 from .weights import net_table
 from .train_boxpc import get_learning_rate, get_bn_decay          # same schedules (train_semisup_adv.py:135-153)
 from .train_layers import (ParamArena, TrainLayer, EvalLayer, ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH, maxpool, maxpool_bwd,
-                           rowmask_mul, dropout, gemm)
+                           rowmask_mul, dropout, gemm, dense)
 
 
 def train_var_prefixes(FLAGS):
@@ -137,22 +137,23 @@ class SemiAdvTrainGraph(object):
         # ---- inst_seg, training mode, forward only (semisup_models.py:69-139); conv6's global half is folded per frustum
         S = self.seg
         x = pc.reshape(B * N, C)
-        x = S[0].forward(x, bn_decay, keep=False)
-        x = S[1].forward(x, bn_decay, keep=False)
-        point_feat = S[2].forward(x, bn_decay, keep=False)
-        x = S[3].forward(point_feat, bn_decay, keep=False)
-        x = S[4].forward(x, bn_decay, keep=False)
+        x = S[0].forward(x, bn_decay, keep=False, lazy=True)
+        x = S[1].forward(x, bn_decay, keep=False, lazy=True)
+        pf_lazy = S[2].forward(x, bn_decay, keep=False, lazy=True)
+        x = S[3].forward(pf_lazy, bn_decay, keep=False, lazy=True)
+        x = S[4].forward(x, bn_decay, keep=False, lazy=True)
         gfeat, _ = maxpool(x, B, N, 1024)
         del x
+        point_feat = dense(pf_lazy)                                      # [B*N, 64]: the operand of the folded conv6
         W6 = S[5].W()                                                    # [64 + 1024, 512]
         gb = gemm(gfeat, 1024, 1, W6[64:], 512, 1, B, 512, 1024, bias=S[5].p('biases'))
         y6 = torch.empty((B * N, 512), device=dev)
         call('t3d_linear_f32', ptr(point_feat), 64, ptr(W6), 512, None, ptr(gb), N, ptr(y6), 512, B * N, 64, 512, 0, None, None,
              stream())
-        x = S[5].forward(None, bn_decay, y=y6, keep=False)
+        x = S[5].forward(None, bn_decay, y=y6, keep=False, lazy=True)
         del y6
-        x = S[6].forward(x, bn_decay, keep=False)
-        x = S[7].forward(x, bn_decay, keep=False)
+        x = S[6].forward(x, bn_decay, keep=False, lazy=True)
+        x = S[7].forward(x, bn_decay, keep=False, lazy=True)
         x = S[8].forward(x, bn_decay, keep=False)
         x = dropout(x, T(dropout_masks['class_agnostic/inst_seg/dp1']).reshape(B * N, 128), 0.5)
         logits = S[9].forward(x, bn_decay, keep=False).reshape(B, N, 2)
@@ -167,7 +168,7 @@ class SemiAdvTrainGraph(object):
         Tn = self.tnet
         x = xyz1.reshape(B * N, 3)
         for l in Tn[:3]:
-            x = l.forward(x, bn_decay)
+            x = l.forward(x, bn_decay, lazy=True)
         t_pool, t_arg = maxpool(x, B, N, 256, rowmask)          # max(net * mask) without the product in HBM
         h = Tn[3].forward(t_pool, bn_decay)
         h = Tn[4].forward(h, bn_decay)
@@ -181,7 +182,7 @@ class SemiAdvTrainGraph(object):
         call('t3d_prepare_xyz', ptr(pc), B, N, C, ptr(stage1_center), ptr(xin), stream())
         x = xin.reshape(B * N, 3)
         for l in Bx[:4]:
-            x = l.forward(x, bn_decay)
+            x = l.forward(x, bn_decay, lazy=True)
         feats_lv1, b_arg = maxpool(x, B, N, 512, rowmask)
         ep['feats_lv1'] = feats_lv1
         h = Bx[4].forward(feats_lv1, bn_decay, keep=False)
@@ -276,8 +277,7 @@ class SemiAdvTrainGraph(object):
         if train_box or train_tnet:
             # with the box net frozen (SEMI_TRAIN_BOX_TRAIN_CLASS_AG_BOX = 0) its convolutions still carry the gradient to
             # stage1_center: TrainLayer.backward is dgrad-only for layers outside the gradient arena
-            g = maxpool_bwd(g_lv1, b_arg, B, N, 512, rowmask)
-            g = Bx[3].backward(g)
+            g = Bx[3].backward_pooled(g_lv1.contiguous(), b_arg, B, N, rowmask)
             g = Bx[2].backward(g)
             g = Bx[1].backward(g)
             gx = Bx[0].backward(g, need_dx=train_tnet)
@@ -292,8 +292,7 @@ class SemiAdvTrainGraph(object):
             g = Tn[5].backward(ds1.contiguous().clone())
             g = Tn[4].backward(g)
             g = Tn[3].backward(g)
-            g = maxpool_bwd(g, t_arg, B, N, 256, rowmask)
-            g = Tn[2].backward(g)
+            g = Tn[2].backward_pooled(g.contiguous(), t_arg, B, N, rowmask)
             g = Tn[1].backward(g)
             Tn[0].backward(g, need_dx=False)
             del g
