@@ -265,6 +265,11 @@ int t3d_bn_backward_lazy(float* dOut, const float* y, const float* mean, const f
                          t3d_stream_t stream);
 int t3d_maxpool_lazy_fwd(const float* y, const float* a_scale, const float* a_shift, const float* rowmask, int B, int N, int C,
                          float* out, int* arg, t3d_stream_t stream);
+/* t3d_maxpool_masked_fwd / t3d_maxpool_lazy_fwd with a caller-owned scratch of 8 * B * C bytes (8-byte aligned): the N rows of a
+ * group are split across blocks and merged by a 64-bit atomic max (value, then smallest row) when B * C threads cannot fill
+ * the GPU; keys == NULL is the serial kernel. */
+int t3d_maxpool_fwd_ws(const float* x, const float* a_scale, const float* a_shift, const float* rowmask, int B, int N, int C,
+                       float* out, int* arg, void* keys, t3d_stream_t stream);
 /* backward of [BN -> ReLU -> (x rowmask) -> max-pool over the N rows of each group] from the pooled gradient g [B, C]: the BN
  * reductions are O(B C) gathers at the arg-max elements, dY [B*N, C] is one dense pass + a B x C scatter; s1 = d beta,
  * s2 = d gamma.  Replaces t3d_maxpool_masked_bwd + t3d_colstats + t3d_bn_backward (semisup_models.py:184-189, 240-245). */

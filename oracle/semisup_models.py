@@ -11,6 +11,31 @@ from .tf_layers import conv2d, fully_connected, max_pool_points, dropout
 from transferable3d_b200.constants import NUM_HEADING_BIN, NUM_SIZE_CLUSTER, MEAN_DIMS_ARR
 
 
+def mlps(input_feat, layers, is_training, vs, bn=True, bn_decay=None, c=None, scope=None):
+    """semisup_models.py:30-42: fully connected stack, the last layer without batch norm and without activation."""
+    with vs.variable_scope(scope):
+        net = input_feat
+        for i, layer_size in enumerate(layers):
+            if len(layers) - 1 == i:
+                net = fully_connected(net, layer_size, vs, 'fc%d' % i, bn=False, is_training=is_training, activation_fn=None,
+                                      bn_decay=bn_decay)
+            else:
+                net = fully_connected(net, layer_size, vs, 'fc%d' % i, bn=bn, is_training=is_training, bn_decay=bn_decay)
+    return net
+
+
+def _normalize_xyz(pc, normalize_method):
+    """semisup_models.py:335-343 / :413-421: xyz normalised, the remaining channels untouched."""
+    xyz, rest = pc[:, :, :3], pc[:, :, 3:]
+    if normalize_method == 'SD':
+        xyz = tf_util.tf_normalize_point_clouds_to_mean_zero_and_unit_var(xyz)
+    elif normalize_method == 'Spread':
+        xyz = tf_util.tf_normalize_point_clouds_to_01(xyz)
+    else:
+        raise Exception('Invalid normalization method')
+    return torch.cat([xyz, rest], dim=2)
+
+
 def mlps_with_dropout(input_feat, layers, activation_fns, keep_probs, is_training, vs, bn=True,
                       bn_decay=None, c=None, scope=None):
     """semisup_models.py:44-63."""
@@ -144,11 +169,15 @@ def v1_box_est(point_cloud_xyz_submean, stage1_center, mask, one_hot_vec, end_po
 def box_pc_mask_features_model(box, pc, logits, num_outputs, is_training, end_points, reuse, bn_for_output, vs,
                                normalize_pc=False, normalize_method='SD', one_hot_vec=None, norm_box2D=None,
                                bn_decay=None, c=None, scope=None):
-    """semisup_models.py:297-324 (representation A only; B is SURVEY 8f 'next')."""
+    """semisup_models.py:297-324."""
     if c.BOX_PC_MASK_REPRESENTATION == 'A':
         return combined_box_pc_mask_features_model(box, pc, logits, num_outputs, is_training, end_points, reuse,
                                                    False, vs, normalize_pc, normalize_method, one_hot_vec, None,
                                                    bn_decay, c, 'box_pc_mask_model')
+    if c.BOX_PC_MASK_REPRESENTATION == 'B':
+        return independent_box_pc_mask_features_model(box, pc, logits, num_outputs, is_training, end_points, reuse,
+                                                      False, vs, normalize_pc, normalize_method, one_hot_vec, None,
+                                                      bn_decay, c, 'box_pc_mask_model')
     raise Exception('Box pc mask representation not implemented: %s' % c.BOX_PC_MASK_REPRESENTATION)
 
 
@@ -159,7 +188,7 @@ def combined_box_pc_mask_features_model(box_reg, pc, mask, num_outputs, is_train
     with vs.variable_scope(scope):
         rep = tf_util.tf_get_box_pc_representation(box_reg, pc)               # (B,N,C+6)
         if normalize_pc:
-            raise NotImplementedError('NORMALIZE_PC options are SURVEY 8f next')
+            rep = _normalize_xyz(rep, normalize_method)
         if mask is not None:
             rep = torch.cat([rep, mask], dim=2)
         D = rep.shape[2]
@@ -182,6 +211,45 @@ def combined_box_pc_mask_features_model(box_reg, pc, mask, num_outputs, is_train
         features_lv3 = net
         net = dropout(net, vs, is_training, 'dp2', keep_prob=0.7)
         net = fully_connected(net, num_outputs, vs, 'fc3', bn=bn_for_output, is_training=is_training,
+                              activation_fn=None, bn_decay=bn_decay)
+        features = {'%s_feats_lv1' % scope: features_lv1, '%s_feats_lv2' % scope: features_lv2,
+                    '%s_feats_lv3' % scope: features_lv3}
+    return net, features
+
+
+def independent_box_pc_mask_features_model(box_reg, pc, mask, num_outputs, is_training, end_points, reuse,
+                                           bn_for_output, vs, normalize_pc=False, normalize_method='SD',
+                                           one_hot_vec=None, norm_box2D=None, bn_decay=None, c=None, scope=None):
+    """semisup_models.py:400-471 (representation B): box parameters (B,7) through an FC stack, the raw points through a
+    conv stack + max-pool, the two 512-vectors concatenated (box first; then norm_box2D, then the one-hot) into a 4-layer
+    FC head."""
+    with vs.variable_scope(scope):
+        box7 = torch.cat([box_reg[0], box_reg[1], box_reg[2].unsqueeze(1)], dim=1)
+        box_feat = mlps(box7, [128, 128, 256, 512], is_training, vs, bn=True, bn_decay=bn_decay, c=c, scope='extract_box_feats')
+        if normalize_pc:
+            pc = _normalize_xyz(pc, normalize_method)
+        D = pc.shape[2]
+        net = conv2d(pc, 128, [1, D], vs, 'conv-reg1', True, is_training, bn_decay=bn_decay)
+        net = conv2d(net, 128, [1, 1], vs, 'conv-reg2', True, is_training, bn_decay=bn_decay)
+        net = conv2d(net, 256, [1, 1], vs, 'conv-reg3', True, is_training, bn_decay=bn_decay)
+        net = conv2d(net, 512, [1, 1], vs, 'conv-reg4', True, is_training, bn_decay=bn_decay)
+        if mask is not None:
+            net = net * mask
+        net = max_pool_points(net)
+        net = torch.cat([box_feat, net], dim=1)
+        features_lv1 = net
+        if norm_box2D is not None:
+            net = torch.cat([net, norm_box2D], dim=1)
+        if one_hot_vec is not None:
+            net = torch.cat([net, one_hot_vec], dim=1)
+        net = fully_connected(net, 512, vs, 'fc1', True, is_training, bn_decay=bn_decay)
+        net = fully_connected(net, 512, vs, 'fc2', True, is_training, bn_decay=bn_decay)
+        features_lv2 = net
+        net = dropout(net, vs, is_training, 'dp2', keep_prob=0.7)
+        net = fully_connected(net, 256, vs, 'fc3', True, is_training, bn_decay=bn_decay)
+        features_lv3 = net
+        net = dropout(net, vs, is_training, 'dp3', keep_prob=0.7)
+        net = fully_connected(net, num_outputs, vs, 'fc4', bn=bn_for_output, is_training=is_training,
                               activation_fn=None, bn_decay=bn_decay)
         features = {'%s_feats_lv1' % scope: features_lv1, '%s_feats_lv2' % scope: features_lv2,
                     '%s_feats_lv3' % scope: features_lv3}

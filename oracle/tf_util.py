@@ -170,6 +170,25 @@ def tf_distance_to_closest_3D_box_surface_multi(point_clouds, box_params):
     return tf_distance_to_box_surfaces_multi(point_clouds, box_params).min(dim=2).values
 
 
+def tf_normalize_point_clouds_to_01(point_clouds):
+    """tf_util.py:134-155: subtract the per-cloud centroid, divide by the largest xyz extent (+1e-5); channels >= 3 are kept."""
+    centroids = point_clouds.mean(dim=1, keepdim=True)
+    translated = point_clouds - centroids
+    max_dims = translated.max(dim=1).values - translated.min(dim=1).values           # (B,D)
+    max_dims = max_dims[:, :3].max(dim=1).values.reshape(-1, 1, 1)
+    normalized = translated / (max_dims + 1e-5)
+    return torch.cat([normalized[:, :, :3], point_clouds[:, :, 3:]], dim=2)
+
+
+def tf_normalize_point_clouds_to_mean_zero_and_unit_var(point_clouds):
+    """tf_util.py:157-173: (x - mean) / (sqrt(var) + 1e-5) per cloud and channel (tf.nn.moments: biased variance); channels
+    >= 3 are kept."""
+    centroids = point_clouds.mean(dim=1, keepdim=True)
+    variances = ((point_clouds - centroids) ** 2).mean(dim=1, keepdim=True)
+    normalized = (point_clouds - centroids) / (variances.sqrt() + 1e-5)
+    return torch.cat([normalized[:, :, :3], point_clouds[:, :, 3:]], dim=2)
+
+
 def tf_get_box_pc_representation(box_reg, pc):
     """tf_util.py:764-795: original pc (all channels, untranslated) ++ 6 signed plane distances."""
     center, dims_reg, orient_reg = box_reg

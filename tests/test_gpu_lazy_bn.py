@@ -151,3 +151,33 @@ def test_pool_bn_backward_and_lazy_ops(B, N, C, masked, built_lib):
         assert torch.allclose(a, b_, rtol=1e-4, atol=1e-4)
     assert torch.allclose(dx, dx_lazy, **tol)
     assert torch.allclose(dx, dY, **tol)
+
+
+@pytest.mark.parametrize('B,N,C,lazy,masked', [(4, 2048, 512, True, True), (3, 1000, 300, False, False), (2, 4096, 64, False, True),
+                                               (8, 256, 1024, True, False)])
+def test_maxpool_row_split_equals_serial(B, N, C, lazy, masked, built_lib):
+    """t3d_maxpool_fwd_ws (rows split across blocks, 64-bit atomic max on (value, ~row)) == the serial kernel, including
+    ties (first row wins), negative values and all-masked groups."""
+    rng = np.random.RandomState(N + C)
+    x = np.round(rng.randn(B * N, C) * 2) / 2                       # many exact ties
+    x[:N, :7] = -3.0                                                # constant negative columns in the first group: row 0 wins
+    xd = _dev(x)
+    rm = rng.rand(B * N) < 0.5
+    rm[N:2 * N] = False                                             # one group fully masked
+    rowmask = _dev(rm) if masked else None
+    sc = _dev((rng.rand(C) + 0.5) * np.where(rng.rand(C) < 0.3, -1, 1)) if lazy else None
+    sh = _dev(rng.randn(C)) if lazy else None
+    p1, a1 = torch.empty(B, C, device=DEV), torch.empty(B, C, dtype=torch.int32, device=DEV)
+    p2, a2 = torch.empty(B, C, device=DEV), torch.empty(B, C, dtype=torch.int32, device=DEV)
+    keys = torch.empty(B, C, dtype=torch.int64, device=DEV)
+    call('t3d_maxpool_fwd_ws', ptr(xd), ptr(sc), ptr(sh), ptr(rowmask), B, N, C, ptr(p1), ptr(a1), None, stream())
+    call('t3d_maxpool_fwd_ws', ptr(xd), ptr(sc), ptr(sh), ptr(rowmask), B, N, C, ptr(p2), ptr(a2), ptr(keys), stream())
+    torch.cuda.synchronize()
+    assert torch.equal(p1, p2) and torch.equal(a1, a2)
+    # and against numpy
+    v = x.reshape(B, N, C).astype(np.float32)
+    if lazy:
+        v = np.maximum(np.float32(sc.cpu().numpy()) * v + np.float32(sh.cpu().numpy()), 0)
+    if masked:
+        v = v * rm.reshape(B, N, 1).astype(np.float32)
+    assert np.allclose(p2.cpu().numpy(), v.max(1), rtol=1e-6, atol=1e-6)

@@ -145,6 +145,7 @@ SIGNATURES = {
     't3d_colstats_lazy': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     't3d_bn_backward_lazy': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     't3d_maxpool_lazy_fwd': (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    't3d_maxpool_fwd_ws': (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     't3d_pool_bn_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     't3d_maxpool_fwd': (_I, [_P, _I, _I, _I, _P, _P, _P]),
     't3d_maxpool_bwd': (_I, [_P, _P, _I, _I, _I, _P, _P]),

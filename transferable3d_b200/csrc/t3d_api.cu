@@ -972,7 +972,7 @@ extern "C" int t3d_gemm_bn_f32(const float* A, long long sam, long long sak, con
 extern "C" int t3d_row0(const float* a, const float* a_scale, const float* a_shift, const float* W, int ldw, const float* bias,
                         int K, int N, float* y0, t3d_stream_t stream) {
   if (!a || !W || !y0 || K <= 0 || N <= 0) return T3D_ERR_ARG;
-  row0_kernel<<<(N + 127) / 128, 128, 0, S(stream)>>>(a, a_scale, a_shift, W, ldw, bias, K, N, y0);
+  row0_kernel<<<(N + 31) / 32, 256, 0, S(stream)>>>(a, a_scale, a_shift, W, ldw, bias, K, N, y0);
   T3D_CHECK_LAUNCH();
   return 0;
 }
@@ -1098,12 +1098,40 @@ extern "C" int t3d_pool_bn_backward(const float* g, const int* arg, const float*
   return 0;
 }
 
+// `keys`: caller-owned scratch of B * C 64-bit words for the row-split kernel (null: the serial kernel)
+static int maxpool_fwd_impl(const float* x, const float* rowmask, int B, int N, int C, float* out, int* arg, const float* a_scale,
+                            const float* a_shift, void* keys, t3d_stream_t stream) {
+  const int cblocks = (C + 255) / 256;
+  int split = 1;
+  if (keys != nullptr && (((uintptr_t)keys) & 7) == 0) {
+    split = (xg_num_sms() * 8 + cblocks * B - 1) / (cblocks * B);
+    if (split > N / 64) split = N / 64;
+  }
+  if (split <= 1) {
+    maxpool_fwd_kernel<<<(B * C + 255) / 256, 256, 0, S(stream)>>>(x, rowmask, B, N, C, out, arg, a_scale, a_shift);
+    T3D_CHECK_LAUNCH();
+    return 0;
+  }
+  const int rows = (N + split - 1) / split;
+  T3D_CUDA(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)B * C, S(stream)));
+  maxpool_split_kernel<<<dim3(cblocks, B, (N + rows - 1) / rows), 256, 0, S(stream)>>>(x, rowmask, B, N, C, rows,
+                                                                                     reinterpret_cast<unsigned long long*>(keys), a_scale, a_shift);
+  maxpool_split_finish_kernel<<<(B * C + 255) / 256, 256, 0, S(stream)>>>(reinterpret_cast<const unsigned long long*>(keys), B * C, out, arg);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
 extern "C" int t3d_maxpool_masked_fwd(const float* x, const float* rowmask, int B, int N, int C, float* out, int* arg,
                                       t3d_stream_t stream) {
   if (!x || !out || !arg) return T3D_ERR_ARG;
-  maxpool_fwd_kernel<<<(B * C + 255) / 256, 256, 0, S(stream)>>>(x, rowmask, B, N, C, out, arg);
-  T3D_CHECK_LAUNCH();
-  return 0;
+  return maxpool_fwd_impl(x, rowmask, B, N, C, out, arg, nullptr, nullptr, nullptr, stream);
+}
+// the same with a caller-owned scratch of 8 * B * C bytes: rows are split across blocks when B * C alone cannot fill the GPU;
+// a_scale / a_shift != NULL: x is the pre-BN tensor of a lazy BN layer (pooled = max relu(a_scale x + a_shift) * rowmask)
+extern "C" int t3d_maxpool_fwd_ws(const float* x, const float* a_scale, const float* a_shift, const float* rowmask, int B, int N, int C,
+                                  float* out, int* arg, void* keys, t3d_stream_t stream) {
+  if (!x || !out || !arg || (a_scale != nullptr) != (a_shift != nullptr)) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0 || C <= 0) return T3D_ERR_SHAPE;
+  return maxpool_fwd_impl(x, rowmask, B, N, C, out, arg, a_scale, a_shift, keys, stream);
 }
 // pooled = max_n relu(a_scale[c] * y + a_shift[c]) (* rowmask): the max-pool reads the pre-BN tensor of a lazy BN layer
 extern "C" int t3d_maxpool_lazy_fwd(const float* y, const float* a_scale, const float* a_shift, const float* rowmask, int B, int N,

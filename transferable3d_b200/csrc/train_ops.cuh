@@ -263,6 +263,53 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, const float* __r
   out[i] = m; arg[i] = am;
 }
 
+// Row-split variant: blockIdx.z owns a chunk of the N rows, so that enough loads are in flight to fill HBM when B * C / 256
+// blocks are too few (3.5 blocks per SM at B = 256, C = 512: 2.9 TB/s).  Chunks are merged by a 64-bit atomic max on
+// (order-preserving image of the value) << 32 | ~row: the largest value wins, the smallest row among equal values -- the
+// "first max wins" of the serial kernel.  maxpool_split_finish_kernel unpacks into (out, arg).
+__device__ __forceinline__ uint32_t f32_ordered(float f) {
+  const uint32_t u = __float_as_uint(f + 0.0f);                 // -0 -> +0
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unordered(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+__global__ void __launch_bounds__(256) maxpool_split_kernel(const float* __restrict__ x, const float* __restrict__ rowmask, int B, int N,
+                                                           int C, int rows_per_chunk, unsigned long long* __restrict__ keys,
+                                                           const float* __restrict__ a_scale, const float* __restrict__ a_shift) {
+  const int c = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+  if (c >= C) return;
+  const int n0 = blockIdx.z * rows_per_chunk, n1 = min(N, n0 + rows_per_chunk);
+  if (n0 >= n1) return;
+  const float* p = x + (size_t)b * N * C + c;
+  const float* rm = rowmask ? rowmask + (size_t)b * N : nullptr;
+  const bool lazy = a_scale != nullptr;
+  const float sc = lazy ? a_scale[c] : 1.0f, sh = lazy ? a_shift[c] : 0.0f;
+  auto val = [&](float v, int n) {
+    if (lazy) v = fmaxf(fmaf(sc, v, sh), 0.0f);
+    if (rm) v *= rm[n];
+    return v;
+  };
+  float m = val(p[(size_t)n0 * C], n0); int am = n0;
+  int n = n0 + 1;
+  for (; n + 8 <= n1; n += 8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = p[(size_t)(n + j) * C];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] = val(v[j], n + j); if (v[j] > m) { m = v[j]; am = n + j; } }
+  }
+  for (; n < n1; ++n) { const float v = val(p[(size_t)n * C], n); if (v > m) { m = v; am = n; } }
+  const unsigned long long key = ((unsigned long long)f32_ordered(m) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)am);
+  atomicMax(keys + (size_t)b * C + c, key);
+}
+__global__ void maxpool_split_finish_kernel(const unsigned long long* __restrict__ keys, int total, float* __restrict__ out,
+                                            int* __restrict__ arg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const unsigned long long k = keys[i];
+  out[i] = f32_unordered((uint32_t)(k >> 32));
+  arg[i] = (int)(0xffffffffu - (uint32_t)(k & 0xffffffffull));
+}
+
 // ---- backward of [BN -> ReLU -> (row mask) -> max-pool] without the dense pooled-gradient tensor ------------------------
 // The gradient w.r.t. the BN output is non-zero only at the B x C arg-max elements, so the two batch-norm reductions
 // (s1 = sum dy, s2 = sum dy * xhat) are O(B C) gathers instead of two passes over the B N x C tensor, and the BN input

@@ -280,10 +280,11 @@ def maxpool(x, B, N, C, rowmask=None):
     x may be a Lazy: the BN map + ReLU is applied while pooling."""
     pooled = torch.empty((B, C), dtype=torch.float32, device=x.device)
     arg = torch.empty((B, C), dtype=torch.int32, device=x.device)
+    keys = torch.empty((B, C), dtype=torch.int64, device=x.device)          # scratch of the row-split kernel
     if isinstance(x, Lazy):
-        call('t3d_maxpool_lazy_fwd', ptr(x.y), ptr(x.scale), ptr(x.shift), ptr(rowmask), B, N, C, ptr(pooled), ptr(arg), stream())
+        call('t3d_maxpool_fwd_ws', ptr(x.y), ptr(x.scale), ptr(x.shift), ptr(rowmask), B, N, C, ptr(pooled), ptr(arg), ptr(keys), stream())
     else:
-        call('t3d_maxpool_masked_fwd', ptr(x), ptr(rowmask), B, N, C, ptr(pooled), ptr(arg), stream())
+        call('t3d_maxpool_fwd_ws', ptr(x), None, None, ptr(rowmask), B, N, C, ptr(pooled), ptr(arg), ptr(keys), stream())
     return pooled, arg
 
 

@@ -62,6 +62,19 @@ def net_table(net, num_channel=6, one_hot=False, norm_box2d=False):
                 ('fc1', 'fc', 0, 512 + oh, 512, True),
                 ('fc2', 'fc', 0, 512, 256, True),
                 ('fc3', 'fc', 0, 256, BOXPC_OUT, False)]
+    if net == 'box_pc_mask_model_B':        # representation B (semisup_models.py:400-471): box FC stack + point conv stack
+        return [('extract_box_feats/fc0', 'fc', 0, 7, 128, True),
+                ('extract_box_feats/fc1', 'fc', 0, 128, 128, True),
+                ('extract_box_feats/fc2', 'fc', 0, 128, 256, True),
+                ('extract_box_feats/fc3', 'fc', 0, 256, 512, False),
+                ('conv-reg1', 'conv', num_channel, 1, 128, True),
+                ('conv-reg2', 'conv', 1, 128, 128, True),
+                ('conv-reg3', 'conv', 1, 128, 256, True),
+                ('conv-reg4', 'conv', 1, 256, 512, True),
+                ('fc1', 'fc', 0, 1024 + oh, 512, True),
+                ('fc2', 'fc', 0, 512, 512, True),
+                ('fc3', 'fc', 0, 512, 256, True),
+                ('fc4', 'fc', 0, 256, BOXPC_OUT, False)]
     raise KeyError(net)
 
 
@@ -121,11 +134,11 @@ def make_weights_model_A(seed=42, num_channel=6, use_one_hot=True, norm_box2d=Fa
     return v
 
 
-def make_weights_boxpc(seed=43, num_channel=6, use_one_hot=False):
-    """Variables of the standalone BoxPC graph (train_boxpc.py:252)."""
+def make_weights_boxpc(seed=43, num_channel=6, use_one_hot=False, rep='A', scope='box_pc_mask_model'):
+    """Variables of the standalone BoxPC graph (train_boxpc.py:252); rep = BOX_PC_MASK_REPRESENTATION ('A' or 'B')."""
     rng = np.random.Generator(np.random.PCG64(seed))
-    return init_net(rng, 'box_pc_mask_model',
-                    net_table('box_pc_mask_model', num_channel, one_hot=use_one_hot))
+    return init_net(rng, scope, net_table('box_pc_mask_model' if rep == 'A' else 'box_pc_mask_model_B', num_channel,
+                                          one_hot=use_one_hot))
 
 
 def apply_logit_margin(variables, scope, k):
