@@ -142,7 +142,8 @@ int t3d_perturb_boxes(const t3d_perturb_args* args /* host */, t3d_stream_t stre
  *       2 box_est convs + max (:224-245), 3 box_pc_mask_model convs + max with the BoxPC features computed
  *       in the first-layer prologue (:334-376).
  * Weights are packed once into a caller-owned arena (BN already folded; W[l] is [K,N] row-major fp32 on device). */
-enum { T3D_CHAIN_SEG1 = 0, T3D_CHAIN_TNET = 1, T3D_CHAIN_BOX = 2, T3D_CHAIN_BOXPC = 3 };
+enum { T3D_CHAIN_SEG1 = 0, T3D_CHAIN_TNET = 1, T3D_CHAIN_BOX = 2, T3D_CHAIN_BOXPC = 3,
+       T3D_CHAIN_BOXPCB = 4 /* BoxPC representation B: conv 6-128-128-256-512 + max on the raw points (semisup_models.py:423-443) */ };
 size_t t3d_chain_arena_bytes(int kind);
 int t3d_chain_num_layers(int kind);     /* layer 1 + hidden + final */
 int t3d_chain_tile_points(int kind);
@@ -237,6 +238,10 @@ int t3d_maxpool_bwd(const float* dout, const int* arg, int B, int N, int C, floa
 int t3d_maxpool_masked_fwd(const float* x, const float* rowmask, int B, int N, int C, float* out, int* arg, t3d_stream_t stream);
 int t3d_maxpool_masked_bwd(const float* dout, const int* arg, const float* rowmask, int B, int N, int C, float* dx,
                            t3d_stream_t stream);
+/* NORMALIZE_PC options of the BoxPC models (semisup_models.py:335-343, 413-421): pc [B,N,C] -> out [B,N,C] with xyz normalised
+ * per cloud, channels >= 3 copied.  mode 0 'SD' = tf_normalize_point_clouds_to_mean_zero_and_unit_var (models/tf_util.py:157-173),
+ * mode 1 'Spread' = tf_normalize_point_clouds_to_01 (:134-155). */
+int t3d_normalize_pc(const float* pc, int B, int N, int C, int mode, float* out, t3d_stream_t stream);
 int t3d_scale_mask(const float* x, const float* mask, float scale, float* out, long long n, t3d_stream_t stream);
 /* ---- lazy batch norm (training-mode layers with M = B*N rows; tf_util.conv2d :1258-1323 + batch_norm_template :1645-1664) ----
  * The post-BN activation relu(gamma (y - mean) rstd + beta) of a layer is never written: consumers read the pre-BN tensor y
@@ -281,6 +286,11 @@ typedef struct {
   const float *out9, *y_iou, *y_dc, *y_ds, *y_da;
   int B; float fit_bound, w_cls, w_delta, wc, ws, wa; int huber;
   float *cls_losses, *delta_losses, *total, *grad;
+  /* class-confidence weighting (boxpc_sunrgbd.py:76-91, 166-177), p1 = softmax(fit logits)[1]:
+   * pred_weigh 1: the deltas entering the loss are out9[0:7] * (1 - p1) (BOXPC_WEIGH_DELTA_PRED_BY_CLS_CONF; pass the RAW
+   * network output); loss_weigh 1: delta loss * (1 - p1) (BOXPC_WEIGH_DELTA_LOSS_BY_CLS_CONF), 2: * (1 - y_iou)
+   * (..._BY_CLS_GT); stop_grad 1: p1 is a constant in both (BOXPC_STOP_GRAD_OF_CLS_VIA_DELTA).  All 0: the plain loss. */
+  int pred_weigh, loss_weigh, stop_grad;
 } t3d_boxpc_loss_args;
 int t3d_boxpc_loss(const t3d_boxpc_loss_args* args /* host */, t3d_stream_t stream);
 /* theta -= lr_t * m / (sqrt(v) + eps), lr_t = lr*sqrt(1-b2^t)/(1-b1^t) supplied by the host (TF Adam) */

@@ -36,7 +36,8 @@ class t3d_boxpc_loss_args(_c.Structure):
     _fields_ = [('out9', _P), ('y_iou', _P), ('y_dc', _P), ('y_ds', _P), ('y_da', _P),
                 ('B', _I), ('fit_bound', _c.c_float), ('w_cls', _c.c_float), ('w_delta', _c.c_float),
                 ('wc', _c.c_float), ('ws', _c.c_float), ('wa', _c.c_float), ('huber', _I),
-                ('cls_losses', _P), ('delta_losses', _P), ('total', _P), ('grad', _P)]
+                ('cls_losses', _P), ('delta_losses', _P), ('total', _P), ('grad', _P),
+                ('pred_weigh', _I), ('loss_weigh', _I), ('stop_grad', _I)]
 
 
 class t3d_semi_loss_args(_c.Structure):
@@ -146,6 +147,7 @@ SIGNATURES = {
     't3d_bn_backward_lazy': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     't3d_maxpool_lazy_fwd': (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     't3d_maxpool_fwd_ws': (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    't3d_normalize_pc': (_I, [_P, _I, _I, _I, _I, _P, _P]),
     't3d_pool_bn_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     't3d_maxpool_fwd': (_I, [_P, _I, _I, _I, _P, _P, _P]),
     't3d_maxpool_bwd': (_I, [_P, _P, _I, _I, _I, _P, _P]),

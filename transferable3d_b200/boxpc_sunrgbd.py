@@ -85,8 +85,10 @@ def _boxpc_losses(pred, labels, end_points, c):
     losses, the scalar total of get_loss and d total / d (delta_center, delta_size, delta_angle, fit logits)."""
     logits, (d_center, d_size, d_angle) = pred
     y_box_iou, (y_center, y_size, y_angle) = labels
-    if c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_CONF or c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_GT:
-        raise NotImplementedError('BOXPC_WEIGH_DELTA_LOSS_BY_CLS_* are not on the recipe path (scripts/train_semisup_bed.sh)')
+    assert not (c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_CONF and c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_GT)
+    # the deltas in `pred` are what get_model returned (already scaled when BOXPC_WEIGH_DELTA_PRED_BY_CLS_CONF); the loss
+    # weight 1 - softmax(fit logits)[1] equals end_points['logits_for_weigh'] (boxpc_sunrgbd.py:166-177)
+    loss_weigh = 1 if c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_CONF else (2 if c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_GT else 0)
     B, dev = logits.shape[0], logits.device
     out9 = torch.cat([rt.f32(d_center).reshape(B, 3), rt.f32(d_size).reshape(B, 3), rt.f32(d_angle).reshape(B, 1),
                       rt.f32(logits).reshape(B, 2)], dim=1).contiguous()
@@ -96,7 +98,8 @@ def _boxpc_losses(pred, labels, end_points, c):
     a = t3d_boxpc_loss_args(ptr(out9), ptr(y_iou), ptr(y_dc), ptr(y_ds), ptr(y_da), B, float(c.BOXPC_FIT_BOUNDS[0]),
                             float(c.BOXPC_WEIGHT_CLS), float(c.BOXPC_WEIGHT_DELTA), float(c.BOXPC_WEIGHT_DELTA_CENTER_PERCENT),
                             float(c.BOXPC_WEIGHT_DELTA_SIZE_PERCENT), float(c.BOXPC_WEIGHT_DELTA_ANGLE_PERCENT),
-                            1 if c.BOXPC_DELTA_LOSS_TYPE == 'huber' else 0, ptr(cls_l), ptr(del_l), ptr(total), ptr(g9))
+                            1 if c.BOXPC_DELTA_LOSS_TYPE == 'huber' else 0, ptr(cls_l), ptr(del_l), ptr(total), ptr(g9),
+                            0, loss_weigh, 1 if c.BOXPC_STOP_GRAD_OF_CLS_VIA_DELTA else 0)
     call('t3d_boxpc_loss', ctypes.byref(a), stream())
     if end_points is not None:
         end_points['boxpc_loss_grad'] = g9        # columns: delta_center 0:3, delta_size 3:6, delta_angle 6, fit logits 7:9

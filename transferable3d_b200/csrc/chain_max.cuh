@@ -28,7 +28,7 @@ namespace t3d {
 constexpr int kChunkBytes = 16384;        // [128 rows x 64 bf16]
 constexpr int kRingStages = 4;
 
-enum ChainKind { CHAIN_SEG1 = 0, CHAIN_TNET = 1, CHAIN_BOX = 2, CHAIN_BOXPC = 3 };
+enum ChainKind { CHAIN_SEG1 = 0, CHAIN_TNET = 1, CHAIN_BOX = 2, CHAIN_BOXPC = 3, CHAIN_BOXPCB = 4 };
 
 template <int KIND> struct ChainSpec;
 template <> struct ChainSpec<CHAIN_SEG1> {
@@ -70,6 +70,18 @@ template <> struct ChainSpec<CHAIN_BOXPC> {
   static constexpr int BUF_BYTES(int i) { return i == 0 ? 32768 : i == 1 ? 32768 : 65536; }
   static constexpr int FRONT_FREE_LAYER = 0, EMIT_LAYER = -1;
   static constexpr bool BOXPC = true;
+};
+
+// BoxPC representation B (semisup_models.py:400-471): the conv stack sees the raw 6-channel points, no box prologue
+template <> struct ChainSpec<CHAIN_BOXPCB> {
+  static constexpr int CIN = 6, CRAW = 6, C1 = 128, NH = 2, NSUB = 1;
+  static constexpr int FK = 256, FC = 512;
+  static constexpr int HK(int i) { return i == 0 ? 128 : i == 1 ? 128 : 0; }
+  static constexpr int HN(int i) { return i == 0 ? 128 : i == 1 ? 256 : 0; }
+  static constexpr int ACT_BUF(int i) { return i == 0 ? 0 : i == 1 ? 1 : i == 2 ? 2 : 0; }
+  static constexpr int BUF_BYTES(int i) { return i == 0 ? 32768 : i == 1 ? 32768 : 65536; }
+  static constexpr int FRONT_FREE_LAYER = 0, EMIT_LAYER = -1;
+  static constexpr bool BOXPC = false;
 };
 
 template <typename S> __host__ __device__ constexpr int chain_num_chunks() {

@@ -109,14 +109,23 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
     if (lane == 0) {
       constexpr uint32_t kHalf = kChunkBytes / kClusterSize;
       uint32_t it = 0;
-      for (int i = 0; i < iters; ++i)
-        for (int c = 0; c < kSeg2XChunks; ++c, ++it) {
-          const int s = it % ST;
-          mbar_wait(ring_empty(s), ((it / ST) & 1) ^ 1);
-          mbar_arrive_expect_tx(ring_full(s), kChunkBytes);
-          bulk_g2s_mc(sbase + L::RING + s * kChunkBytes + crank * kHalf, args.arena + (size_t)c * kChunkBytes + crank * kHalf,
-                      kHalf, ring_full(s), kAllCtas);
-        }
+      auto push = [&](int c) {
+        const int s = it % ST;
+        mbar_wait(ring_empty(s), ((it / ST) & 1) ^ 1);
+        mbar_arrive_expect_tx(ring_full(s), kChunkBytes);
+        bulk_g2s_mc(sbase + L::RING + s * kChunkBytes + crank * kHalf, args.arena + (size_t)c * kChunkBytes + crank * kHalf,
+                    kHalf, ring_full(s), kAllCtas);
+        ++it;
+      };
+      // The stream follows the MMA warp's CONSUMPTION order, not the arena order: the first conv6' block of tile i + 1
+      // (arena chunks 0, 1) is issued under the e7 epilogue of tile i, i.e. between conv7 (chunks 2 .. kC8 - 1) and conv8.
+      constexpr int kC8 = kSeg2XChunks - 12;          // conv8 (4 K-blocks x [lo, hi]) + conv9 (2 x [lo, hi]) close the arena
+      for (int i = 0; i < iters; ++i) {
+        if (i == 0) { push(0); push(1); }
+        for (int c = 2; c < kC8; ++c) push(c);
+        if (i + 1 < iters) { push(0); push(1); }
+        for (int c = kC8; c < kSeg2XChunks; ++c) push(c);
+      }
     }
   } else if (warp == 3) {
     // ================================================================ input producer: point_feat tile (hi + lo) + gbias

@@ -493,6 +493,55 @@ __global__ void box3d_corners_all_kernel(const float* center, const float* headi
   box_corners(center + b * 3, heading, sz, out + (size_t)i * 24);
 }
 
+// ----------------------------------------------------------------------------- point-cloud normalisation (NORMALIZE_PC options)
+// tf_normalize_point_clouds_to_mean_zero_and_unit_var (mode 0, models/tf_util.py:157-173): (x - mean) / (sqrt(var) + 1e-5) per
+// cloud and channel, biased variance; tf_normalize_point_clouds_to_01 (mode 1, :134-155): (x - mean) / (largest xyz extent
+// + 1e-5).  Only the first 3 channels are normalised, channels >= 3 are copied (the concat of both reference functions).
+// One CTA per cloud; mean first, then the centred second pass (what tf.nn.moments computes), then the write.
+__device__ __forceinline__ float block_reduce(float v, int op, float* sh) {      // op 0 sum, 1 max, 2 min; 256 threads
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = op == 0 ? v + w : (op == 1 ? fmaxf(v, w) : fminf(v, w));
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+  for (int i = 1; i < 8; ++i) r = op == 0 ? r + sh[i] : (op == 1 ? fmaxf(r, sh[i]) : fminf(r, sh[i]));
+  return r;
+}
+__global__ void __launch_bounds__(256) normalize_pc_kernel(const float* __restrict__ pc, int N, int C, int mode, float* __restrict__ out) {
+  __shared__ float sh[8];
+  const float* p = pc + (size_t)blockIdx.x * N * C;
+  float* q = out + (size_t)blockIdx.x * N * C;
+  float mean[3], div[3];
+  for (int k = 0; k < 3; ++k) {
+    float s = 0.f;
+    for (int n = threadIdx.x; n < N; n += 256) s += p[(size_t)n * C + k];
+    mean[k] = block_reduce(s, 0, sh) / (float)N;
+  }
+  if (mode == 0) {
+    for (int k = 0; k < 3; ++k) {
+      float s = 0.f;
+      for (int n = threadIdx.x; n < N; n += 256) { const float d = p[(size_t)n * C + k] - mean[k]; s = fmaf(d, d, s); }
+      div[k] = sqrtf(block_reduce(s, 0, sh) / (float)N) + 1e-5f;
+    }
+  } else {
+    float ext = -INFINITY;
+    for (int k = 0; k < 3; ++k) {
+      float mx = -INFINITY, mn = INFINITY;
+      for (int n = threadIdx.x; n < N; n += 256) { const float d = p[(size_t)n * C + k] - mean[k]; mx = fmaxf(mx, d); mn = fminf(mn, d); }
+      ext = fmaxf(ext, block_reduce(mx, 1, sh) - block_reduce(mn, 2, sh));
+    }
+    div[0] = div[1] = div[2] = ext + 1e-5f;
+  }
+  for (int n = threadIdx.x; n < N; n += 256) {
+    for (int k = 0; k < 3; ++k) q[(size_t)n * C + k] = (p[(size_t)n * C + k] - mean[k]) / div[k];
+    for (int k = 3; k < C; ++k) q[(size_t)n * C + k] = p[(size_t)n * C + k];
+  }
+}
+
 // ----------------------------------------------------------------------------- weight packing for tcgen05
 // chunk image: [128 rows x 64 K] bf16, K-major SWIZZLE_128B; row r = output channel row0+r, K = k0..k0+63 of
 // W[K_total, Nout] (row-major, TF layout).  Rows >= nrows and k >= K_total are zero.

@@ -501,6 +501,7 @@ static int chain_launch(const ChainArgs& a, int out_elems, cudaStream_t st) {
     case CHAIN_TNET: { constexpr int K_ = CHAIN_TNET; EXPR; } break;   \
     case CHAIN_BOX: { constexpr int K_ = CHAIN_BOX; EXPR; } break;     \
     case CHAIN_BOXPC: { constexpr int K_ = CHAIN_BOXPC; EXPR; } break; \
+    case CHAIN_BOXPCB: { constexpr int K_ = CHAIN_BOXPCB; EXPR; } break; \
     default: return T3D_ERR_ARG;                         \
   }
 
@@ -511,6 +512,7 @@ extern "C" size_t t3d_chain_arena_bytes(int kind) {
     case CHAIN_TNET: r = chain_arena_bytes<ChainSpec<CHAIN_TNET>>(); break;
     case CHAIN_BOX: r = chain_arena_bytes<ChainSpec<CHAIN_BOX>>(); break;
     case CHAIN_BOXPC: r = chain_arena_bytes<ChainSpec<CHAIN_BOXPC>>(); break;
+    case CHAIN_BOXPCB: r = chain_arena_bytes<ChainSpec<CHAIN_BOXPCB>>(); break;
     default: r = 0;
   }
   return r;
@@ -521,6 +523,7 @@ extern "C" int t3d_chain_num_layers(int kind) {
     case CHAIN_TNET: return 2 + ChainSpec<CHAIN_TNET>::NH;
     case CHAIN_BOX: return 2 + ChainSpec<CHAIN_BOX>::NH;
     case CHAIN_BOXPC: return 2 + ChainSpec<CHAIN_BOXPC>::NH;
+    case CHAIN_BOXPCB: return 2 + ChainSpec<CHAIN_BOXPCB>::NH;
     default: return T3D_ERR_ARG;
   }
 }
@@ -530,6 +533,7 @@ extern "C" int t3d_chain_tile_points(int kind) {
     case CHAIN_TNET: return 128 * ChainSpec<CHAIN_TNET>::NSUB;
     case CHAIN_BOX: return 128 * ChainSpec<CHAIN_BOX>::NSUB;
     case CHAIN_BOXPC: return 128 * ChainSpec<CHAIN_BOXPC>::NSUB;
+    case CHAIN_BOXPCB: return 128 * ChainSpec<CHAIN_BOXPCB>::NSUB;
     default: return T3D_ERR_ARG;
   }
 }
@@ -539,6 +543,7 @@ extern "C" int t3d_chain_out_channels(int kind) {
     case CHAIN_TNET: return ChainSpec<CHAIN_TNET>::FC;
     case CHAIN_BOX: return ChainSpec<CHAIN_BOX>::FC;
     case CHAIN_BOXPC: return ChainSpec<CHAIN_BOXPC>::FC;
+    case CHAIN_BOXPCB: return ChainSpec<CHAIN_BOXPCB>::FC;
     default: return T3D_ERR_ARG;
   }
 }
@@ -560,12 +565,20 @@ extern "C" int t3d_chain_max_bf16(int kind, const float* pc, int B, int N, int C
   if ((tiles != nullptr) != (num_tiles != nullptr)) return T3D_ERR_ARG;
   if (idx && idx_stride <= 0) return T3D_ERR_SHAPE;
   if (kind == CHAIN_BOXPC && (!box_center || !box_dims || !box_orient)) return T3D_ERR_ARG;
-  if (kind == CHAIN_BOXPC ? C != 6 : (kind == CHAIN_SEG1 ? C != 6 : C < 3)) return T3D_ERR_SHAPE;
+  if ((kind == CHAIN_BOXPC || kind == CHAIN_BOXPCB || kind == CHAIN_SEG1) ? C != 6 : C < 3) return T3D_ERR_SHAPE;
   if (emit && (kind != CHAIN_SEG1 || ((uintptr_t)emit & 15))) return T3D_ERR_ARG;
   ChainArgs a{pc, B, N, C, center, idx, idx_stride, count, reinterpret_cast<const int4*>(tiles), num_tiles,
               box_center, box_dims, box_orient, reinterpret_cast<const uint8_t*>(arena), out,
               reinterpret_cast<__nv_bfloat16*>(emit), g_trace};
   CHAIN_SWITCH(kind, return chain_launch<K_>(a, B * ChainSpec<K_>::FC, S(stream)));
+  return 0;
+}
+
+extern "C" int t3d_normalize_pc(const float* pc, int B, int N, int C, int mode, float* out, t3d_stream_t stream) {
+  if (!pc || !out) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0 || C < 3 || (mode != 0 && mode != 1)) return T3D_ERR_SHAPE;
+  normalize_pc_kernel<<<B, 256, 0, S(stream)>>>(pc, N, C, mode, out);
+  T3D_CHECK_LAUNCH();
   return 0;
 }
 
@@ -714,6 +727,7 @@ extern "C" size_t t3d_chain_arena_bytes_x2(int kind) {
     case CHAIN_TNET: return x2_arena_bytes<ChainSpec<CHAIN_TNET>>();
     case CHAIN_BOX: return x2_arena_bytes<ChainSpec<CHAIN_BOX>>();
     case CHAIN_BOXPC: return x2_arena_bytes<ChainSpec<CHAIN_BOXPC>>();
+    case CHAIN_BOXPCB: return x2_arena_bytes<ChainSpec<CHAIN_BOXPCB>>();
     default: return 0;
   }
 }
@@ -736,7 +750,7 @@ extern "C" int t3d_chain_max_x2(int kind, const float* pc, int B, int N, int C, 
   if ((tiles != nullptr) != (num_tiles != nullptr)) return T3D_ERR_ARG;
   if (idx && idx_stride <= 0) return T3D_ERR_SHAPE;
   if (kind == CHAIN_BOXPC && (!box_center || !box_dims || !box_orient)) return T3D_ERR_ARG;
-  if (kind == CHAIN_BOXPC ? C != 6 : (kind == CHAIN_SEG1 ? C != 6 : C < 3)) return T3D_ERR_SHAPE;
+  if ((kind == CHAIN_BOXPC || kind == CHAIN_BOXPCB || kind == CHAIN_SEG1) ? C != 6 : C < 3) return T3D_ERR_SHAPE;
   if (emit && (kind != CHAIN_SEG1 || ((uintptr_t)emit & 15))) return T3D_ERR_ARG;
   ChainArgs a{pc, B, N, C, center, idx, idx_stride, count, reinterpret_cast<const int4*>(tiles), num_tiles,
               box_center, box_dims, box_orient, reinterpret_cast<const uint8_t*>(arena), out,
@@ -1173,7 +1187,8 @@ extern "C" int t3d_boxpc_loss(const t3d_boxpc_loss_args* p, t3d_stream_t stream)
   if (p->B <= 0) return T3D_ERR_SHAPE;
   T3D_CUDA(cudaMemsetAsync(p->total, 0, sizeof(float), S(stream)));
   BoxpcLossArgs a{p->out9, p->y_iou, p->y_dc, p->y_ds, p->y_da, p->B, p->fit_bound, p->w_cls, p->w_delta, p->wc, p->ws, p->wa,
-                  p->huber, p->cls_losses, p->delta_losses, p->total, p->grad};
+                  p->huber, p->cls_losses, p->delta_losses, p->total, p->grad, p->pred_weigh, p->loss_weigh, p->stop_grad};
+  if (p->pred_weigh < 0 || p->pred_weigh > 1 || p->loss_weigh < 0 || p->loss_weigh > 2) return T3D_ERR_ARG;
   boxpc_loss_kernel<<<(p->B + 127) / 128, 128, 0, S(stream)>>>(a);
   T3D_CHECK_LAUNCH();
   return 0;

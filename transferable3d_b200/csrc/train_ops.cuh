@@ -434,6 +434,11 @@ struct BoxpcLossArgs {
   const float* out9; const float* y_iou; const float* y_dc; const float* y_ds; const float* y_da;
   int B; float fit_bound, w_cls, w_delta, wc, ws, wa; int huber;     // huber=1, else mse
   float* cls_losses; float* delta_losses; float* total; float* grad;
+  // class-confidence weighting (boxpc_sunrgbd.py:76-91, 166-177), p1 = softmax(fit logits)[1]:
+  //   pred_weigh  1: the deltas entering the loss are out9[0:7] * (1 - p1)      (BOXPC_WEIGH_DELTA_PRED_BY_CLS_CONF)
+  //   loss_weigh  1: delta loss * (1 - p1) (..._LOSS_BY_CLS_CONF), 2: * (1 - y_iou) (..._LOSS_BY_CLS_GT)
+  //   stop_grad   1: p1 is a constant in both (BOXPC_STOP_GRAD_OF_CLS_VIA_DELTA)
+  int pred_weigh, loss_weigh, stop_grad;
 };
 __device__ __forceinline__ void huber1(float err, float& loss, float& dloss) {   // tf.losses.huber_loss delta=1 on (pred-label)
   const float a = fabsf(err), q = fminf(a, 1.0f);
@@ -448,22 +453,35 @@ __global__ void boxpc_loss_kernel(const BoxpcLossArgs a) {
     float g[9];
     const float l0 = o[7], l1 = o[8], mx = fmaxf(l0, l1);
     const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), z = e0 + e1;
+    const float p0 = e0 / z, p1 = e1 / z;
     const int lab = a.y_iou[b] > a.fit_bound ? 1 : 0;
     const float cls = logf(z) + mx - (lab ? l1 : l0);
     const float inv_b = 1.0f / (float)a.B;
-    g[7] = a.w_cls * inv_b * (e0 / z - (lab == 0 ? 1.f : 0.f));
-    g[8] = a.w_cls * inv_b * (e1 / z - (lab == 1 ? 1.f : 0.f));
+    g[7] = a.w_cls * inv_b * (p0 - (lab == 0 ? 1.f : 0.f));
+    g[8] = a.w_cls * inv_b * (p1 - (lab == 1 ? 1.f : 0.f));
+    const float wp = a.pred_weigh ? 1.0f - p1 : 1.0f;                                     // scales the predicted deltas
+    const float wl = a.loss_weigh == 1 ? 1.0f - p1 : (a.loss_weigh == 2 ? 1.0f - a.y_iou[b] : 1.0f);      // scales the loss
     float lc = 0.f, ls = 0.f, la, d;
+    float dot = 0.f;                       // sum_k dD/dd'_k * o_k : how D moves with wp
     for (int k = 0; k < 3; ++k) {
       float l;
-      if (a.huber) huber1(o[k] - a.y_dc[b * 3 + k], l, d); else { const float e = o[k] - a.y_dc[b * 3 + k]; l = e * e; d = 2.f * e; }
-      lc += l; g[k] = a.w_delta * inv_b * a.wc * d / 3.0f;
-      if (a.huber) huber1(o[3 + k] - a.y_ds[b * 3 + k], l, d); else { const float e = o[3 + k] - a.y_ds[b * 3 + k]; l = e * e; d = 2.f * e; }
-      ls += l; g[3 + k] = a.w_delta * inv_b * a.ws * d / 3.0f;
+      const float ec = o[k] * wp - a.y_dc[b * 3 + k], es = o[3 + k] * wp - a.y_ds[b * 3 + k];
+      if (a.huber) huber1(ec, l, d); else { l = ec * ec; d = 2.f * ec; }
+      lc += l; d *= a.wc / 3.0f; dot = fmaf(d, o[k], dot); g[k] = a.w_delta * inv_b * wl * wp * d;
+      if (a.huber) huber1(es, l, d); else { l = es * es; d = 2.f * es; }
+      ls += l; d *= a.ws / 3.0f; dot = fmaf(d, o[3 + k], dot); g[3 + k] = a.w_delta * inv_b * wl * wp * d;
     }
-    if (a.huber) huber1(o[6] - a.y_da[b], la, d); else { const float e = o[6] - a.y_da[b]; la = e * e; d = 2.f * e; }
-    g[6] = a.w_delta * inv_b * a.wa * d;
-    const float delta = a.wc * lc / 3.0f + a.ws * ls / 3.0f + a.wa * la;
+    const float ea = o[6] * wp - a.y_da[b];
+    if (a.huber) huber1(ea, la, d); else { la = ea * ea; d = 2.f * ea; }
+    d *= a.wa; dot = fmaf(d, o[6], dot); g[6] = a.w_delta * inv_b * wl * wp * d;
+    const float D = a.wc * lc / 3.0f + a.ws * ls / 3.0f + a.wa * la;
+    const float delta = wl * D;
+    if (!a.stop_grad && (a.pred_weigh || a.loss_weigh == 1)) {
+      // d total / d p1, then through the softmax: d p1 / d l1 = p0 p1 = - d p1 / d l0
+      const float dp1 = a.w_delta * inv_b * ((a.loss_weigh == 1 ? -D : 0.0f) + (a.pred_weigh ? -wl * dot : 0.0f));
+      g[8] += dp1 * p0 * p1;
+      g[7] -= dp1 * p0 * p1;
+    }
     if (a.cls_losses) a.cls_losses[b] = cls;
     if (a.delta_losses) a.delta_losses[b] = delta;
     if (a.grad) for (int k = 0; k < 9; ++k) a.grad[(size_t)b * 9 + k] = g[k];

@@ -20,7 +20,7 @@ from ._lib import ptr, stream, call
 from .weights import fold_bn
 
 ACT = {'none': 0, None: 0, 'relu': 1, 'leaky_relu': 2, 'tanh': 3}
-CHAIN_SEG1, CHAIN_TNET, CHAIN_BOX, CHAIN_BOXPC = 0, 1, 2, 3
+CHAIN_SEG1, CHAIN_TNET, CHAIN_BOX, CHAIN_BOXPC, CHAIN_BOXPCB = 0, 1, 2, 3, 4
 
 PRECISIONS = ('bf16', 'f16x2', 'fp32')
 FUSED = ('bf16', 'f16x2')          # modes that run the fused tcgen05 chains

@@ -57,6 +57,43 @@ def _cat(parts):
     return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1).contiguous()
 
 
+def mlps(input_feat, layers, is_training, bn=True, bn_decay=None, c=None, scope=None, reuse=None):
+    """semisup_models.py:30-42: fully connected stack; the last layer has neither batch norm nor activation."""
+    rt.require_eval(is_training)
+    with rt.variable_scope(scope):
+        net = input_feat
+        for i, layer_size in enumerate(layers):
+            last = (len(layers) - 1 == i)
+            net = tf_util.fully_connected(net, layer_size, scope='fc%d' % i, bn=(False if last else bn),
+                                          activation_fn=(None if last else 'relu'), is_training=is_training, bn_decay=bn_decay)
+    return net
+
+
+def _normalize_xyz(pc, normalize_method):
+    """semisup_models.py:335-343 / :413-421: xyz normalised per cloud, the remaining channels untouched (t3d_normalize_pc)."""
+    if normalize_method == 'SD':
+        return tf_util.tf_normalize_point_clouds_to_mean_zero_and_unit_var(pc)
+    if normalize_method == 'Spread':
+        return tf_util.tf_normalize_point_clouds_to_01(pc)
+    raise Exception('Invalid normalization method')
+
+
+def _conv_stack_max(x3d, names, full, mask=None):
+    """conv2d + BN + ReLU stack over (B,N,D) points followed by (* mask and) the max over points, layer by layer through
+    t3d_linear_f32 (BN folded): the path of the inputs the fused chains do not take (normalised clouds, an extra mask
+    channel) and of the fp32 mode."""
+    st = rt.store()
+    B, N, D = x3d.shape
+    x = rt.f32(x3d).reshape(B * N, D)
+    for name in names[:-1]:
+        w, b = st.folded(full + '/' + name)
+        x, _ = rt.linear(x, w, b, 'relu')
+    w, b = st.folded(full + '/' + names[-1])
+    rowmask = None if mask is None else rt.f32(mask).reshape(B * N).contiguous()
+    _, net = rt.linear(x, w, b, 'relu', rows_per_group=N, gmax_groups=B, want_y=False, rowmask=rowmask)
+    return net
+
+
 def mlps_with_dropout(input_feat, layers, activation_fns, keep_probs, is_training, bn=True, bn_decay=None,
                       c=None, scope=None, reuse=None):
     """semisup_models.py:44-63 (activation_fns are 'relu' / 'leaky_relu' / 'tanh' / None)."""
@@ -218,37 +255,39 @@ def box_pc_mask_features_model(box, pc, logits, num_outputs, is_training, end_po
                                bn_decay=None, c=None, scope=None):
     """semisup_models.py:297-324."""
     if c.BOX_PC_MASK_REPRESENTATION == 'A':
-        return combined_box_pc_mask_features_model(box, pc, logits, num_outputs, is_training, end_points=end_points,
-                                                   reuse=reuse, normalize_pc=normalize_pc,
-                                                   normalize_method=normalize_method, bn_for_output=False,
-                                                   one_hot_vec=one_hot_vec, norm_box2D=None, bn_decay=bn_decay, c=c,
-                                                   scope='box_pc_mask_model')
-    raise Exception('Box pc mask representation not implemented: %s' % c.BOX_PC_MASK_REPRESENTATION)
+        fn = combined_box_pc_mask_features_model
+    elif c.BOX_PC_MASK_REPRESENTATION == 'B':
+        fn = independent_box_pc_mask_features_model
+    else:
+        raise Exception('Box pc mask representation not implemented: %s' % c.BOX_PC_MASK_REPRESENTATION)
+    return fn(box, pc, logits, num_outputs, is_training, end_points=end_points, reuse=reuse, normalize_pc=normalize_pc,
+              normalize_method=normalize_method, bn_for_output=False, one_hot_vec=one_hot_vec, norm_box2D=None,
+              bn_decay=bn_decay, c=c, scope='box_pc_mask_model')
 
 
 def combined_box_pc_mask_features_model(box_reg, pc, mask, num_outputs, is_training, end_points, reuse, bn_for_output,
                                         normalize_pc=False, normalize_method='SD', one_hot_vec=None, norm_box2D=None,
                                         bn_decay=None, c=None, scope=None):
-    """semisup_models.py:326-398 (mask=None, normalize_pc=False: the configuration every caller uses)."""
+    """semisup_models.py:326-398.  mask=None, normalize_pc=False (what every caller in the reference passes) runs the fused
+    chain with the plane distances in its prologue; a normalised representation or a mask channel takes the layer-wise
+    path on the materialised (B,N,C+6[+1]) representation."""
     rt.require_eval(is_training)
-    if normalize_pc or mask is not None:
-        raise NotImplementedError('normalize_pc / mask inputs of the BoxPC model are not on the hot path')
     st = rt.store()
     pc = rt.f32(pc)
     B, N, C = pc.shape
     names = ['conv-reg1', 'conv-reg2', 'conv-reg3', 'conv-reg4']
     with rt.variable_scope(scope):
         full = st.scope_name()
-        if rt.get_precision() in rt.FUSED:
+        if not normalize_pc and mask is None and rt.get_precision() in rt.FUSED:
             arena = st.chain_arena(full, rt.CHAIN_BOXPC, names, x2=rt.is_x2())
             net = rt.chain_max(rt.CHAIN_BOXPC, pc, arena, box=box_reg, x2=rt.is_x2())
         else:
-            x = tf_util.tf_get_box_pc_representation(box_reg, pc).reshape(B * N, C + 6)
-            for name in names[:-1]:
-                w, b = st.folded(full + '/' + name)
-                x, _ = rt.linear(x, w, b, 'relu')
-            w, b = st.folded(full + '/' + names[-1])
-            _, net = rt.linear(x, w, b, 'relu', rows_per_group=N, gmax_groups=B, want_y=False)
+            rep = tf_util.tf_get_box_pc_representation(box_reg, pc)
+            if normalize_pc:
+                rep = _normalize_xyz(rep, normalize_method)
+            if mask is not None:
+                rep = torch.cat([rep, rt.f32(mask).reshape(B, N, 1)], dim=2).contiguous()
+            net = _conv_stack_max(rep, names, full, mask)
         net = _cat([net, one_hot_vec, norm_box2D])
         features_lv1 = net
         net = tf_util.fully_connected(net, 512, bn=True, is_training=is_training, scope='fc1', bn_decay=bn_decay)
@@ -259,6 +298,47 @@ def combined_box_pc_mask_features_model(box_reg, pc, mask, num_outputs, is_train
         net = tf_util.dropout(net, keep_prob=0.7, is_training=is_training, scope='dp2')
         net = tf_util.fully_connected(net, num_outputs, bn=bn_for_output, is_training=is_training, activation_fn=None,
                                       scope='fc3', bn_decay=bn_decay)
+        features = {'%s_feats_lv1' % scope: features_lv1, '%s_feats_lv2' % scope: features_lv2,
+                    '%s_feats_lv3' % scope: features_lv3}
+    return net, features
+
+
+def independent_box_pc_mask_features_model(box_reg, pc, mask, num_outputs, is_training, end_points, reuse, bn_for_output,
+                                           normalize_pc=False, normalize_method='SD', one_hot_vec=None, norm_box2D=None,
+                                           bn_decay=None, c=None, scope=None):
+    """semisup_models.py:400-471 (BoxPC representation B): the box (B,7) goes through the `extract_box_feats` FC stack, the
+    raw points through conv 128-128-256-512 + max (one fused chain, CHAIN_BOXPCB, in the bf16 / f16x2 modes), and the
+    concatenation [box_feat, point_feat (, norm_box2D) (, one_hot)] through the 4-layer FC head."""
+    rt.require_eval(is_training)
+    st = rt.store()
+    pc = rt.f32(pc)
+    B, N, D = pc.shape
+    names = ['conv-reg1', 'conv-reg2', 'conv-reg3', 'conv-reg4']
+    with rt.variable_scope(scope):
+        full = st.scope_name()
+        box7 = torch.cat([rt.f32(box_reg[0]).reshape(B, 3), rt.f32(box_reg[1]).reshape(B, 3), rt.f32(box_reg[2]).reshape(B, 1)],
+                         dim=1).contiguous()
+        box_feat = mlps(box7, [128, 128, 256, 512], is_training, bn=True, bn_decay=bn_decay, c=c, scope='extract_box_feats',
+                        reuse=reuse)
+        if normalize_pc:
+            pc = _normalize_xyz(pc, normalize_method)
+        if mask is None and D == 6 and rt.get_precision() in rt.FUSED:
+            arena = st.chain_arena(full, rt.CHAIN_BOXPCB, names, x2=rt.is_x2())
+            net = rt.chain_max(rt.CHAIN_BOXPCB, pc, arena, x2=rt.is_x2())
+        else:
+            net = _conv_stack_max(pc, names, full, mask)
+        net = _cat([box_feat, net])
+        features_lv1 = net
+        net = _cat([net, norm_box2D, one_hot_vec])
+        net = tf_util.fully_connected(net, 512, bn=True, is_training=is_training, scope='fc1', bn_decay=bn_decay)
+        net = tf_util.fully_connected(net, 512, bn=True, is_training=is_training, scope='fc2', bn_decay=bn_decay)
+        features_lv2 = net
+        net = tf_util.dropout(net, keep_prob=0.7, is_training=is_training, scope='dp2')
+        net = tf_util.fully_connected(net, 256, bn=True, is_training=is_training, scope='fc3', bn_decay=bn_decay)
+        features_lv3 = net
+        net = tf_util.dropout(net, keep_prob=0.7, is_training=is_training, scope='dp3')
+        net = tf_util.fully_connected(net, num_outputs, bn=bn_for_output, is_training=is_training, activation_fn=None,
+                                      scope='fc4', bn_decay=bn_decay)
         features = {'%s_feats_lv1' % scope: features_lv1, '%s_feats_lv2' % scope: features_lv2,
                     '%s_feats_lv3' % scope: features_lv3}
     return net, features

@@ -81,6 +81,24 @@ def tf_normalize_2D_bboxes(box2D, image_dim):
     return torch.stack([box2D[:, 0] / cols, box2D[:, 1] / rows, box2D[:, 2] / cols, box2D[:, 3] / rows], dim=1)
 
 
+def _normalize_pc(point_clouds, mode):
+    pc = rt.f32(point_clouds).contiguous()
+    B, N, C = pc.shape
+    out = torch.empty_like(pc)
+    call('t3d_normalize_pc', ptr(pc), B, N, C, mode, ptr(out), stream())
+    return out
+
+
+def tf_normalize_point_clouds_to_mean_zero_and_unit_var(point_clouds):
+    """tf_util.py:157-173: xyz -> (x - mean) / (sqrt(var) + 1e-5) per cloud; channels >= 3 kept."""
+    return _normalize_pc(point_clouds, 0)
+
+
+def tf_normalize_point_clouds_to_01(point_clouds):
+    """tf_util.py:134-155: xyz -> (x - mean) / (largest xyz extent + 1e-5) per cloud; channels >= 3 kept."""
+    return _normalize_pc(point_clouds, 1)
+
+
 def tf_get_box_pc_representation(box_reg, pc):
     """tf_util.py:764-795: (B,N,C) -> (B,N,C+6) = pc ++ 6 signed plane distances."""
     center, dims, orient = [rt.f32(t) for t in box_reg]

@@ -24,6 +24,12 @@ BN_DECAY_DECAY_RATE = 0.5
 BN_DECAY_CLIP = 0.99
 
 
+def _scale_mask(x, mask, scale):
+    out = torch.empty_like(x)
+    call('t3d_scale_mask', ptr(x), ptr(mask), float(scale), ptr(out), x.numel(), stream())
+    return out
+
+
 def get_learning_rate(batch, batch_size, base_learning_rate=0.001, decay_step=800000, decay_rate=0.5):
     """train_boxpc.py:134-142: staircase exponential decay (the clip line there is a no-op typo)."""
     return base_learning_rate * decay_rate ** ((batch * batch_size) // decay_step)
@@ -47,7 +53,10 @@ class BoxPCTrainGraph(object):
         self.scope = scope
         self.pg = process_group
         self.use_one_hot = bool(getattr(FLAGS, 'use_one_hot_boxpc', False))
-        table = net_table('box_pc_mask_model', num_channels, one_hot=self.use_one_hot)
+        self.rep = str(getattr(FLAGS, 'BOX_PC_MASK_REPRESENTATION', 'A'))
+        if self.rep not in ('A', 'B'):
+            raise Exception('Box pc mask representation not implemented: %s' % self.rep)
+        table = net_table('box_pc_mask_model' if self.rep == 'A' else 'box_pc_mask_model_B', num_channels, one_hot=self.use_one_hot)
         # flat arenas (parameters, gradients, Adam moments); moving statistics are not trainable
         names, sizes = [], []
         for lname, kind, kw, cin, cout, bn in table:
@@ -91,7 +100,8 @@ class BoxPCTrainGraph(object):
 
     def forward_backward(self, feed, dropout_masks):
         """One forward + backward in training mode. feed: dict keyed like boxpc_sunrgbd.placeholder_inputs;
-        dropout_masks: {'dp1': (B,512) keep mask, 'dp2': (B,256)}. Leaves gradients in self.grad."""
+        dropout_masks: {'dp1': (B,512) keep mask, 'dp2': (B,256)} (representation B: {'dp2': (B,512), 'dp3': (B,256)}).
+        Leaves gradients in self.grad."""
         dev = self.device
         T = lambda v, dt=torch.float32: (v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v))).to(device=dev, dtype=dt).contiguous()
         B, N, C = self.B, self.Npt, self.C
@@ -103,23 +113,37 @@ class BoxPCTrainGraph(object):
         box_reg = boxpc_sunrgbd.convert_raw_y_box_to_reg_format(x_box, one_hot)
         bn_decay = get_bn_decay(self.global_step, B, self.decay_step)
         from . import tf_util
-        rep = tf_util.tf_get_box_pc_representation(box_reg, pc).reshape(B * N, C + 6)
         L = self.layers
-        x = rep
-        for l in L[:4]:
+        drop = lambda h, m: _scale_mask(h, m, 1.0 / 0.7)
+        if self.rep == 'A':
+            # semisup_models.py:326-398: conv stack on [pc, 6 plane distances], max, fc1 - dp1 - fc2 - dp2 - fc3
+            conv, head, dps = L[:4], L[4:], ('dp1', 'dp2')
+            x = tf_util.tf_get_box_pc_representation(box_reg, pc).reshape(B * N, C + 6)
+        else:
+            # semisup_models.py:400-471: box (B,7) through extract_box_feats, conv stack on the raw points, max,
+            # [box_feat, point_feat] through fc1 - fc2 - dp2 - fc3 - dp3 - fc4
+            boxfc, conv, head, dps = L[:4], L[4:8], L[8:], ('dp2', 'dp3')
+            h = torch.cat([box_reg[0], box_reg[1], box_reg[2].reshape(B, 1)], dim=1).contiguous()
+            for l in boxfc:
+                h = l.forward(h, bn_decay)
+            box_feat = h
+            x = pc.reshape(B * N, C)
+        for l in conv:
             x = l.forward(x, bn_decay, lazy=True)       # lazy BN: statistics from the GEMM epilogue, BN map applied by the consumer
         pooled, self.arg = maxpool(x, B, N, 512)
-        feat = torch.cat([pooled, one_hot], dim=1).contiguous() if self.use_one_hot else pooled
-        h1 = L[4].forward(feat, bn_decay)
-        m1 = T(dropout_masks['dp1'])
-        d1 = torch.empty_like(h1)
-        call('t3d_scale_mask', ptr(h1), ptr(m1), 1.0 / 0.7, ptr(d1), h1.numel(), stream())
-        h2 = L[5].forward(d1, bn_decay)
-        m2 = T(dropout_masks['dp2'])
-        d2 = torch.empty_like(h2)
-        call('t3d_scale_mask', ptr(h2), ptr(m2), 1.0 / 0.7, ptr(d2), h2.numel(), stream())
-        out9 = L[6].forward(d2, bn_decay)
-        # loss + d loss / d out9
+        parts = ([pooled] if self.rep == 'A' else [box_feat, pooled]) + ([one_hot] if self.use_one_hot else [])
+        feat = torch.cat(parts, dim=1).contiguous() if len(parts) > 1 else pooled
+        m1, m2 = T(dropout_masks[dps[0]]), T(dropout_masks[dps[1]])
+        if self.rep == 'A':
+            h1 = head[0].forward(feat, bn_decay)
+            h2 = head[1].forward(drop(h1, m1), bn_decay)
+            out9 = head[2].forward(drop(h2, m2), bn_decay)
+        else:
+            h1 = head[0].forward(feat, bn_decay)
+            h2 = head[1].forward(h1, bn_decay)
+            h3 = head[2].forward(drop(h2, m1), bn_decay)
+            out9 = head[3].forward(drop(h3, m2), bn_decay)
+        # loss + d loss / d out9 (the RAW network output: the class-confidence weighting of the deltas is inside the kernel)
         c = self.FLAGS
         total = torch.empty(1, device=dev)
         g9 = torch.empty((B, 9), device=dev)
@@ -127,31 +151,41 @@ class BoxPCTrainGraph(object):
         del_l = torch.empty(B, device=dev)
         # keep the label tensors referenced until the kernel is enqueued (their memory must not be recycled)
         y_iou, y_dc, y_ds, y_da = T(feed['y_box_iou']), T(feed['y_center_delta']), T(feed['y_dims_delta']), T(feed['y_orient_delta'])
+        assert not (c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_CONF and c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_GT)
+        pred_weigh = 1 if c.BOXPC_WEIGH_DELTA_PRED_BY_CLS_CONF else 0
+        loss_weigh = 1 if c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_CONF else (2 if c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_GT else 0)
         a = t3d_boxpc_loss_args(ptr(out9), ptr(y_iou), ptr(y_dc), ptr(y_ds), ptr(y_da), B, float(c.BOXPC_FIT_BOUNDS[0]), float(c.BOXPC_WEIGHT_CLS),
                                 float(c.BOXPC_WEIGHT_DELTA), float(c.BOXPC_WEIGHT_DELTA_CENTER_PERCENT),
                                 float(c.BOXPC_WEIGHT_DELTA_SIZE_PERCENT), float(c.BOXPC_WEIGHT_DELTA_ANGLE_PERCENT),
-                                1 if c.BOXPC_DELTA_LOSS_TYPE == 'huber' else 0, ptr(cls_l), ptr(del_l), ptr(total), ptr(g9))
-        if c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_CONF or c.BOXPC_WEIGH_DELTA_LOSS_BY_CLS_GT or c.BOXPC_WEIGH_DELTA_PRED_BY_CLS_CONF:
-            raise NotImplementedError('BOXPC_WEIGH_DELTA_* options are not on the recipe path (scripts/train_semisup_bed.sh)')
+                                1 if c.BOXPC_DELTA_LOSS_TYPE == 'huber' else 0, ptr(cls_l), ptr(del_l), ptr(total), ptr(g9),
+                                pred_weigh, loss_weigh, 1 if c.BOXPC_STOP_GRAD_OF_CLS_VIA_DELTA else 0)
         call('t3d_boxpc_loss', ctypes.byref(a), stream())
         # backward
-        g = L[6].backward(g9)
-        gd = torch.empty_like(g)
-        call('t3d_scale_mask', ptr(g), ptr(m2), 1.0 / 0.7, ptr(gd), g.numel(), stream())
-        g = L[5].backward(gd)
-        gd = torch.empty_like(g)
-        call('t3d_scale_mask', ptr(g), ptr(m1), 1.0 / 0.7, ptr(gd), g.numel(), stream())
-        g = L[4].backward(gd)
-        if self.use_one_hot:
-            g = g[:, :512].contiguous()
-        g = L[3].backward_pooled(g.contiguous(), self.arg, B, N)     # max-pool + BN backward without the dense pooled gradient
-        g = L[2].backward(g)
-        g = L[1].backward(g)
-        L[0].backward(g, need_dx=False)
+        if self.rep == 'A':
+            g = head[2].backward(g9)
+            g = head[1].backward(drop(g, m2))
+            g = head[0].backward(drop(g, m1))
+            g_pool = g[:, :512].contiguous() if self.use_one_hot else g
+        else:
+            g = head[3].backward(g9)
+            g = head[2].backward(drop(g, m2))
+            g = head[1].backward(drop(g, m1))
+            g = head[0].backward(g)
+            g_box, g_pool = g[:, :512].contiguous(), g[:, 512:1024].contiguous()
+        g = conv[3].backward_pooled(g_pool.contiguous(), self.arg, B, N)     # max-pool + BN backward without the dense pooled gradient
+        g = conv[2].backward(g)
+        g = conv[1].backward(g)
+        conv[0].backward(g, need_dx=False)
+        if self.rep == 'B':
+            g = boxfc[3].backward(g_box)
+            g = boxfc[2].backward(g)
+            g = boxfc[1].backward(g)
+            boxfc[0].backward(g, need_dx=False)
         fit_prob = torch.softmax(out9[:, 7:9], dim=1)[:, 1]
+        w = (1.0 - fit_prob) if pred_weigh else torch.ones_like(fit_prob)
         return {'loss': total, 'boxpc_cls_losses': cls_l, 'boxpc_delta_losses': del_l, 'output': out9,
-                'pred_boxpc_fit': (fit_prob > 0.5).to(torch.int32), 'boxpc_delta_center': out9[:, 0:3],
-                'boxpc_delta_size': out9[:, 3:6], 'boxpc_delta_angle': out9[:, 6]}
+                'pred_boxpc_fit': (fit_prob > 0.5).to(torch.int32), 'boxpc_delta_center': out9[:, 0:3] * w[:, None],
+                'boxpc_delta_size': out9[:, 3:6] * w[:, None], 'boxpc_delta_angle': out9[:, 6] * w}
 
     def apply_gradients(self):
         """Adam over every variable (optimizer.minimize(loss, global_step=batch), train_boxpc.py:249-256)."""

@@ -114,6 +114,7 @@ class TrainLayer(object):
         fused = False
         if y is None:
             kind = bn_supported(M, self.N, self.K, 0) if self.bn else 0
+
             if isinstance(x, Lazy) and kind != 1:
                 x = x.materialize()
             if kind:
@@ -200,6 +201,7 @@ class TrainLayer(object):
         The pooled gradient is never scattered into a dense B*N x C tensor (t3d_pool_bn_backward)."""
         assert self.bn and self.lazy_out
         dev = gpool.device
+
         g = self.grads
         trainable = g is not None and (self.name + '/weights') in g
         if not trainable and not need_dx:
@@ -281,6 +283,7 @@ def maxpool(x, B, N, C, rowmask=None):
     pooled = torch.empty((B, C), dtype=torch.float32, device=x.device)
     arg = torch.empty((B, C), dtype=torch.int32, device=x.device)
     keys = torch.empty((B, C), dtype=torch.int64, device=x.device)          # scratch of the row-split kernel
+
     if isinstance(x, Lazy):
         call('t3d_maxpool_fwd_ws', ptr(x.y), ptr(x.scale), ptr(x.shift), ptr(rowmask), B, N, C, ptr(pooled), ptr(arg), ptr(keys), stream())
     else:
