@@ -238,6 +238,13 @@ int t3d_maxpool_bwd(const float* dout, const int* arg, int B, int N, int C, floa
 int t3d_maxpool_masked_fwd(const float* x, const float* rowmask, int B, int N, int C, float* out, int* arg, t3d_stream_t stream);
 int t3d_maxpool_masked_bwd(const float* dout, const int* arg, const float* rowmask, int B, int N, int C, float* dx,
                            t3d_stream_t stream);
+/* model-A training step (train_semisup.py:199-262): soft_mask = softmax(logits)[1] (semisup_v1_sunrgbd.py:103); gradient of
+ * sum_b w[b] * mean_n CE(logits[b,n,:], labels[b,n]) + (surface loss through soft_mask, gmask = d total / d soft_mask or
+ * NULL) w.r.t. the mask logits; out[b,c] = sum_n x[b,n,c] (the gradient of conv6's per-frustum global half). */
+int t3d_soft_mask(const float* logits, int B, int N, float* out, t3d_stream_t stream);
+int t3d_seg_ce_bwd(const float* logits, const int* labels, const float* w, const float* gmask, int B, int N, float* dlogits,
+                   t3d_stream_t stream);
+int t3d_group_colsum(const float* x, int B, int N, int C, float* out, t3d_stream_t stream);
 /* NORMALIZE_PC options of the BoxPC models (semisup_models.py:335-343, 413-421): pc [B,N,C] -> out [B,N,C] with xyz normalised
  * per cloud, channels >= 3 copied.  mode 0 'SD' = tf_normalize_point_clouds_to_mean_zero_and_unit_var (models/tf_util.py:157-173),
  * mode 1 'Spread' = tf_normalize_point_clouds_to_01 (:134-155). */

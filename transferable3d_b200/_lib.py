@@ -147,6 +147,9 @@ SIGNATURES = {
     't3d_bn_backward_lazy': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     't3d_maxpool_lazy_fwd': (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     't3d_maxpool_fwd_ws': (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    't3d_soft_mask': (_I, [_P, _I, _I, _P, _P]),
+    't3d_seg_ce_bwd': (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
+    't3d_group_colsum': (_I, [_P, _I, _I, _I, _P, _P]),
     't3d_normalize_pc': (_I, [_P, _I, _I, _I, _I, _P, _P]),
     't3d_pool_bn_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     't3d_maxpool_fwd': (_I, [_P, _I, _I, _I, _P, _P, _P]),

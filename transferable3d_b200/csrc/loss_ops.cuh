@@ -100,6 +100,46 @@ __global__ void __launch_bounds__(256) seg_ce_kernel(const float* __restrict__ l
   }
 }
 
+// soft_mask[b,n] = softmax(logits[b,n,:])[1]   (end_points['soft_mask'], semisup_v1_sunrgbd.py:103)
+__global__ void __launch_bounds__(256) soft_mask_kernel(const float* __restrict__ logits, size_t n, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 l = *reinterpret_cast<const float2*>(logits + 2 * i);
+  const float mx = fmaxf(l.x, l.y), e0 = expf(l.x - mx), e1 = expf(l.y - mx);
+  out[i] = e1 / (e0 + e1);
+}
+// Gradient of the model-A loss (train_semisup.py) w.r.t. the mask logits: the cross-entropy term
+// w[b] * mean_n CE(logits[b,n,:], labels[b,n]) and, when gmask != null, the surface loss through
+// soft_mask = softmax(logits)[1] (gmask = d total / d soft_mask): d p1 / d l1 = p0 p1 = - d p1 / d l0.
+__global__ void __launch_bounds__(256) seg_ce_bwd_kernel(const float* __restrict__ logits, const int* __restrict__ labels,
+                                                         const float* __restrict__ w, const float* __restrict__ gmask, int B, int N,
+                                                         float* __restrict__ dlogits) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * N) return;
+  const int b = (int)(i / N);
+  const float2 l = *reinterpret_cast<const float2*>(logits + 2 * i);
+  const float mx = fmaxf(l.x, l.y), e0 = expf(l.x - mx), e1 = expf(l.y - mx), z = e0 + e1;
+  const float p0 = e0 / z, p1 = e1 / z;
+  const float wb = w[b] / (float)N;
+  const int lab = labels[i];
+  float g0 = wb * (p0 - (lab == 0 ? 1.f : 0.f)), g1 = wb * (p1 - (lab != 0 ? 1.f : 0.f));
+  if (gmask) { const float t = gmask[i] * p0 * p1; g0 -= t; g1 += t; }
+  *reinterpret_cast<float2*>(dlogits + 2 * i) = make_float2(g0, g1);
+}
+// out[b, c] = sum_n x[b, n, c]   (any C; the gradient of a per-frustum term broadcast over the N points: conv6's global half)
+__global__ void __launch_bounds__(256) group_colsum_kernel(const float* __restrict__ x, int N, int C, int rows_per_chunk,
+                                                           float* __restrict__ out) {
+  const int c = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+  if (c >= C) return;
+  const int n0 = blockIdx.z * rows_per_chunk, n1 = min(N, n0 + rows_per_chunk);
+  const float* p = x + ((size_t)b * N + n0) * C + c;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
+  int n = n0;
+  for (; n + 4 <= n1; n += 4, p += (size_t)4 * C) { s[0] += p[0]; s[1] += p[C]; s[2] += p[2 * (size_t)C]; s[3] += p[3 * (size_t)C]; }
+  for (; n < n1; ++n, p += C) s[0] += p[0];
+  atomicAdd(out + (size_t)b * C + c, (s[0] + s[1]) + (s[2] + s[3]));
+}
+
 // ----------------------------------------------------------------------------- per-class batch statistics of dims
 // cls_sum[c,:] = sum of dims_reg over the samples of class c, cls_cnt[c] = their number (zero-initialised, atomics)
 __global__ void class_dims_stats_kernel(const float* __restrict__ dims_reg, const float* __restrict__ one_hot, int B, int NC,

@@ -1289,6 +1289,36 @@ extern "C" int t3d_rowmask_mul(const float* x, const float* rowmask, float* out,
   return 0;
 }
 
+extern "C" int t3d_soft_mask(const float* logits, int B, int N, float* out, t3d_stream_t stream) {
+  if (!logits || !out) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0 || (((uintptr_t)logits) & 7)) return T3D_ERR_SHAPE;
+  const size_t n = (size_t)B * N;
+  soft_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(logits, n, out);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int t3d_seg_ce_bwd(const float* logits, const int* labels, const float* w, const float* gmask, int B, int N,
+                              float* dlogits, t3d_stream_t stream) {
+  if (!logits || !labels || !w || !dlogits) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0 || (((uintptr_t)logits | (uintptr_t)dlogits) & 7)) return T3D_ERR_SHAPE;
+  const size_t n = (size_t)B * N;
+  seg_ce_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, S(stream)>>>(logits, labels, w, gmask, B, N, dlogits);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int t3d_group_colsum(const float* x, int B, int N, int C, float* out, t3d_stream_t stream) {
+  if (!x || !out) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0 || C <= 0) return T3D_ERR_SHAPE;
+  T3D_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * C, S(stream)));
+  const int cb = (C + 255) / 256;
+  int split = (xg_num_sms() * 8 + cb * B - 1) / (cb * B);
+  if (split > N / 32) split = N / 32;
+  if (split < 1) split = 1;
+  const int rows = (N + split - 1) / split;
+  group_colsum_kernel<<<dim3(cb, B, (N + rows - 1) / rows), 256, 0, S(stream)>>>(x, N, C, rows, out);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
 extern "C" int t3d_group_sum(const float* x, int B, int N, int C, float scale, float* out, t3d_stream_t stream) {
   if (!x || !out) return T3D_ERR_ARG;
   if (B <= 0 || N <= 0 || C <= 0 || C > 8) return T3D_ERR_SHAPE;

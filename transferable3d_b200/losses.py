@@ -36,11 +36,14 @@ def _consts(dev):
 
 
 def semi_loss(FLAGS, F_output, stage1_center, one_hot, feed, dev, logits=None, mask_losses=None, fit_logits=None, F_reg=None,
-              icv_mask=None, finish=True, mean_size=None, orient_anchors=None, reg_in=None):
+              icv_mask=None, finish=True, mean_size=None, orient_anchors=None, reg_in=None, model_a=False):
     """Runs t3d_seg_ce (if `logits` is given), t3d_class_dims_stats and t3d_semi_loss.
     feed: dict with LABEL_KEYS (+ 'labels' when logits is given).  finish=True also folds g_reg into dF / ds1
     (t3d_box_reg_backward); the training graph passes finish=False, adds the BoxPC input gradient to g_reg and calls
-    finish_box_reg itself.  Returns dict(total[8], dF, ds1, g_reg, dfit, per_sample[B,6], mask_losses)."""
+    finish_box_reg itself.  model_a: the mixing of get_semi_loss_backbone (semisup_v1_sunrgbd.py:256-321) --
+    mean_B[(1 - is2D)(mask + strong) + is2D * mult * W_r * reprojection]: strong terms weighted 1 / B, reprojection on the 2D
+    samples only, no intra-class-variance / fit / inactive-volume terms (the surface term is added by the caller).
+    Returns dict(total[8], dF, ds1, g_reg, dfit, per_sample[B,6], mask_losses)."""
     c = FLAGS
     T = lambda v, dt=torch.float32: (v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v))).to(device=dev, dtype=dt).contiguous()
     B = F_output.shape[0]
@@ -90,9 +93,11 @@ def semi_loss(FLAGS, F_output, stage1_center, one_hot, feed, dev, logits=None, m
     a.reproj_mse, a.icv_mse = int(c.WEAK_REPROJECTION_LOSS_TYPE == 'mse'), int(c.WEAK_DIMS_LOSS_TYPE == 'mse')
     a.train_box_mask = (1 if tb[0] else 0) | (2 if tb[1] else 0) | (4 if tb[2] else 0)
     a.inv_n3d = inv_n3d
+    if model_a:
+        a.inv_n3d, a.reproj_only_2d, a.w_icv, a.w_fit = 1.0 / B, 1, 0.0, 0.0
     call('t3d_semi_loss', ctypes.byref(a), stream())
     iv_out = None
-    if c.WEAK_WEIGHT_INACTIVE_VOLUME != 0:           # semisup_v1_sunrgbd.py:348-360: folded into total / weak_loss / g_reg
+    if c.WEAK_WEIGHT_INACTIVE_VOLUME != 0 and not model_a:           # semisup_v1_sunrgbd.py:348-360: folded into total / weak_loss / g_reg
         assert len(c.WEAK_INACTIVE_VOL_LOSS_MARGINS) == NUM_CLASS
         margins = T(np.asarray(c.WEAK_INACTIVE_VOL_LOSS_MARGINS, dtype=np.float32))
         iv_out = E(1)

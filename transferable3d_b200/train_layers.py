@@ -170,30 +170,42 @@ class TrainLayer(object):
         """dout: gradient w.r.t. this layer's output (overwritten in place).  Returns dX or None.
         A layer whose variables are not in the gradient arena (frozen, but still in the training-mode graph: batch
         statistics) only propagates the input gradient -- TF back-propagates through frozen variables to their input."""
-        M = self.y.shape[0]
-        dev = dout.device
         g = self.grads
         trainable = g is not None and (self.name + '/weights') in g
         if not trainable and not need_dx:
             return None
-        if self.bn:
-            s1 = torch.empty(self.N, device=dev)
-            s2 = torch.empty(self.N, device=dev)
-            if self.lazy_out:
-                call('t3d_colstats_lazy', ptr(dout), ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(self.a_scale), ptr(self.a_shift),
-                     ptr(s1), ptr(s2), M, self.N, stream())
-                call('t3d_bn_backward_lazy', ptr(dout), ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(self.p('bn/gamma')),
-                     ptr(self.a_scale), ptr(self.a_shift), ptr(s1), ptr(s2), M, self.N, stream())
-            else:
-                outp = ptr(self.out) if self.act != ACT_NONE else None
-                call('t3d_colstats', ptr(dout), outp, ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(s1), ptr(s2), M, self.N, 1,
-                     self.act, stream())
-                call('t3d_bn_backward', ptr(dout), outp, ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(self.p('bn/gamma')),
-                     ptr(s1), ptr(s2), M, self.N, self.act, stream())
-            if trainable:
-                g[self.name + '/bn/beta'].copy_(s1)
-                g[self.name + '/bn/gamma'].copy_(s2)
-        return self._backward_gemms(dout, trainable, need_dx)
+        return self._backward_gemms(self._backward_bn(dout), trainable, need_dx)
+
+    def _backward_bn(self, dout):
+        """dout (gradient w.r.t. the layer output) -> gradient w.r.t. the pre-BN values, in place; d beta / d gamma."""
+        if not self.bn:
+            return dout
+        M = self.y.shape[0]
+        dev = dout.device
+        g = self.grads
+        trainable = g is not None and (self.name + '/weights') in g
+        s1 = torch.empty(self.N, device=dev)
+        s2 = torch.empty(self.N, device=dev)
+        if self.lazy_out:
+            call('t3d_colstats_lazy', ptr(dout), ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(self.a_scale), ptr(self.a_shift),
+                 ptr(s1), ptr(s2), M, self.N, stream())
+            call('t3d_bn_backward_lazy', ptr(dout), ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(self.p('bn/gamma')),
+                 ptr(self.a_scale), ptr(self.a_shift), ptr(s1), ptr(s2), M, self.N, stream())
+        else:
+            outp = ptr(self.out) if self.act != ACT_NONE else None
+            call('t3d_colstats', ptr(dout), outp, ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(s1), ptr(s2), M, self.N, 1,
+                 self.act, stream())
+            call('t3d_bn_backward', ptr(dout), outp, ptr(self.y), ptr(self.mean), ptr(self.rstd), ptr(self.p('bn/gamma')),
+                 ptr(s1), ptr(s2), M, self.N, self.act, stream())
+        if trainable:
+            g[self.name + '/bn/beta'].copy_(s1)
+            g[self.name + '/bn/gamma'].copy_(s2)
+        return dout
+
+    def backward_bn_only(self, dout):
+        """BN (+ activation) part of backward() for a layer whose pre-BN values were computed by the caller (forward(None, y=...)):
+        returns dY (dout, overwritten) and leaves d gamma / d beta in the gradient arena; the caller owns the GEMMs."""
+        return self._backward_bn(dout)
 
     def backward_pooled(self, gpool, arg, B, N, rowmask=None, need_dx=True):
         """Backward of this (lazy BN + ReLU) layer when its output only feeds a max-pool over the N rows of each group
