@@ -450,12 +450,14 @@ def run_train(args):
         macs_fr = seg + tnet + box + refine + boxpc
     step_flops = 2.0 * macs_fr * B
     pk = peaks()
-    roof = {'kernel': 'whole training step (tcgen05 bf16 x 3 GEMMs + BN / pooling / loss / Adam kernels)', 'bound': 'tensor',
+    roof = {'kernel': 'whole training step (tcgen05 bf16 x 3 GEMMs with fused BN statistics / lazy BN + pooling / loss / Adam kernels)', 'bound': 'tensor',
             'achieved': step_flops / (ms * 1e-3) / 1e12, 'peak': pk['bf16_burst'], 'unit': 'TFLOP/s',
             'frac': step_flops / (ms * 1e-3) / 1e12 / pk['bf16_burst'], 'traffic': None,
             'algorithmic_flops_per_step': step_flops,
-            'note': 'fp32-accurate GEMMs issue 6 bf16 tensor-core products per MAC (engine tc); the step is bound by the fp32 '
-                    'activation traffic of the batch-norm passes, not by the tensor pipe (DESIGN.md section 5)',
+            'note': 'fp32-accurate GEMMs issue 6 bf16 tensor-core products per MAC (engine tc); batch-norm statistics come out of '
+                    'the GEMM epilogues and the BN map is applied by the consumers (lazy batch norm); the step is bound by the '
+                    'loaders / epilogues of the fp32-operand GEMM kernels and the fp32 activation traffic, not by the tensor pipe '
+                    '(DESIGN.md section 5)',
             'peak_source': '%s, burst bf16' % pk['src']}
     nparam = int((g.flat_param if workload == 'cfg4' else g.arena.flat_param).numel())
     line = {'metric': 'frustums_per_sec', 'value': B * world / ms * 1e3, 'unit': 'frustums/s', 'n_gpus': world, 'steps': args.steps,
