@@ -245,6 +245,14 @@ int t3d_soft_mask(const float* logits, int B, int N, float* out, t3d_stream_t st
 int t3d_seg_ce_bwd(const float* logits, const int* labels, const float* w, const float* gmask, int B, int N, float* dlogits,
                    t3d_stream_t stream);
 int t3d_group_colsum(const float* x, int B, int N, int C, float* out, t3d_stream_t stream);
+/* Row-sparse backward through a frozen (eval-mode) stack behind a max-pool (the BoxPC branch of train_semisup_adv.py:364-388):
+ * the input gradient of the pooled layer is non-zero only in the rows that are the arg-max of some channel.  t3d_pool_rows:
+ * per frustum the ascending list of distinct arg-max rows, padded with -1 to S >= min(C, N) slots (rows [B,S]), the slot of
+ * every channel's arg-max row (slot [B,C]) and the number of distinct rows (count [B]); t3d_gather_rows: dst[b*S+s,:] =
+ * src[b*N+rows[b,s],:] (zero rows for -1); t3d_scatter_pool_grad: dst [B*S,C] = 0, dst[b*S+slot[b,c], c] = g[b,c]. */
+int t3d_pool_rows(const int* arg, int B, int N, int C, int S, int* rows, int* slot, int* count, t3d_stream_t stream);
+int t3d_gather_rows(const float* src, const int* rows, int B, int N, int S, int C, float* dst, t3d_stream_t stream);
+int t3d_scatter_pool_grad(const float* g, const int* slot, int B, int C, int S, float* dst, t3d_stream_t stream);
 /* NORMALIZE_PC options of the BoxPC models (semisup_models.py:335-343, 413-421): pc [B,N,C] -> out [B,N,C] with xyz normalised
  * per cloud, channels >= 3 copied.  mode 0 'SD' = tf_normalize_point_clouds_to_mean_zero_and_unit_var (models/tf_util.py:157-173),
  * mode 1 'Spread' = tf_normalize_point_clouds_to_01 (:134-155). */

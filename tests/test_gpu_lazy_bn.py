@@ -181,3 +181,42 @@ def test_maxpool_row_split_equals_serial(B, N, C, lazy, masked, built_lib):
     if masked:
         v = v * rm.reshape(B, N, 1).astype(np.float32)
     assert np.allclose(p2.cpu().numpy(), v.max(1), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('B,N,C', [(5, 2048, 512), (3, 300, 512), (2, 64, 256)])
+def test_pool_rows_gather_scatter(B, N, C, built_lib):
+    """Row compaction behind a max-pool (t3d_pool_rows / t3d_gather_rows / t3d_scatter_pool_grad): the compacted tensors hold
+    exactly what the dense scatter (t3d_maxpool_bwd) and a row gather would."""
+    from transferable3d_b200.train_layers import pool_rows, gather_rows, scatter_pool_grad
+    rng = np.random.RandomState(B + N)
+    arg = rng.randint(0, N, size=(B, C)).astype(np.int32)
+    arg[0, :] = 7                                                   # one frustum whose channels all pick the same row
+    d_arg = torch.as_tensor(arg).to(DEV)
+    rows, slot, count, S = pool_rows(d_arg, B, N, C)
+    assert S == min(C, N)
+    rows_h, slot_h, count_h = rows.cpu().numpy(), slot.cpu().numpy(), count.cpu().numpy()
+    for b in range(B):
+        uniq = np.unique(arg[b])
+        assert count_h[b] == len(uniq)
+        assert np.array_equal(rows_h[b, :len(uniq)], uniq) and (rows_h[b, len(uniq):] == -1).all()
+        assert np.array_equal(rows_h[b, slot_h[b]], arg[b])
+    src = _dev(rng.randn(B * N, 12))
+    got = gather_rows(src, rows, B, N, S).cpu().numpy().reshape(B, S, 12)
+    src_h = src.cpu().numpy().reshape(B, N, 12)
+    for b in range(B):
+        n = count_h[b]
+        assert np.array_equal(got[b, :n], src_h[b, rows_h[b, :n]]) and (got[b, n:] == 0).all()
+    src6 = _dev(rng.randn(B * N, 6))                                # C % 4 != 0: scalar path
+    got6 = gather_rows(src6, rows, B, N, S).cpu().numpy().reshape(B, S, 6)
+    assert np.array_equal(got6[1, :count_h[1]], src6.cpu().numpy().reshape(B, N, 6)[1, rows_h[1, :count_h[1]]])
+    g = _dev(rng.randn(B, C))
+    comp = scatter_pool_grad(g, slot, B, C, S).cpu().numpy().reshape(B, S, C)
+    dense = torch.empty(B * N, C, device=DEV)
+    call('t3d_maxpool_bwd', ptr(g), ptr(d_arg), B, N, C, ptr(dense), stream())
+    dense = dense.cpu().numpy().reshape(B, N, C)
+    for b in range(B):
+        n = count_h[b]
+        assert np.array_equal(comp[b, :n], dense[b, rows_h[b, :n]]) and (comp[b, n:] == 0).all()
+        rest = np.ones(N, bool)
+        rest[rows_h[b, :n]] = False
+        assert (dense[b, rest] == 0).all()

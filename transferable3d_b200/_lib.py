@@ -150,6 +150,9 @@ SIGNATURES = {
     't3d_soft_mask': (_I, [_P, _I, _I, _P, _P]),
     't3d_seg_ce_bwd': (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
     't3d_group_colsum': (_I, [_P, _I, _I, _I, _P, _P]),
+    't3d_pool_rows': (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    't3d_gather_rows': (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    't3d_scatter_pool_grad': (_I, [_P, _P, _I, _I, _I, _P, _P]),
     't3d_normalize_pc': (_I, [_P, _I, _I, _I, _I, _P, _P]),
     't3d_pool_bn_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     't3d_maxpool_fwd': (_I, [_P, _I, _I, _I, _P, _P, _P]),

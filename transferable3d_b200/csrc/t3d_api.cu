@@ -1171,6 +1171,33 @@ extern "C" int t3d_maxpool_bwd(const float* dout, const int* arg, int B, int N, 
   return t3d_maxpool_masked_bwd(dout, arg, nullptr, B, N, C, dx, stream);
 }
 
+extern "C" int t3d_pool_rows(const int* arg, int B, int N, int C, int nslot, int* rows, int* slot, int* count, t3d_stream_t stream) {
+  if (!arg || !rows || !slot || !count) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0 || C <= 0 || nslot < (C < N ? C : N)) return T3D_ERR_SHAPE;
+  const int words = (N + 31) / 32;
+  if (sizeof(unsigned) * 2 * (size_t)words > 48 * 1024) return T3D_ERR_SHAPE;
+  pool_rows_kernel<<<B, 256, sizeof(unsigned) * 2 * words, S(stream)>>>(arg, N, C, nslot, rows, slot, count);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int t3d_gather_rows(const float* src, const int* rows, int B, int N, int nslot, int C, float* dst, t3d_stream_t stream) {
+  if (!src || !rows || !dst) return T3D_ERR_ARG;
+  if (B <= 0 || N <= 0 || nslot <= 0 || C <= 0) return T3D_ERR_SHAPE;
+  if (C % 4 == 0 && ((((uintptr_t)src) | ((uintptr_t)dst)) & 15)) return T3D_ERR_ALIGN;
+  const size_t total = (size_t)B * nslot, items = total * (size_t)(C % 4 == 0 ? C / 4 : C);
+  gather_rows_kernel<<<(unsigned)((items + 255) / 256), 256, 0, S(stream)>>>(src, rows, N, nslot, C, total, dst);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+extern "C" int t3d_scatter_pool_grad(const float* g, const int* slot, int B, int C, int nslot, float* dst, t3d_stream_t stream) {
+  if (!g || !slot || !dst) return T3D_ERR_ARG;
+  if (B <= 0 || C <= 0 || nslot <= 0) return T3D_ERR_SHAPE;
+  T3D_CUDA(cudaMemsetAsync(dst, 0, sizeof(float) * (size_t)B * nslot * C, S(stream)));
+  scatter_pool_grad_kernel<<<(B * C + 255) / 256, 256, 0, S(stream)>>>(g, slot, B, C, nslot, dst);
+  T3D_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int t3d_scale_mask(const float* x, const float* mask, float scale, float* out, long long n, t3d_stream_t stream) {
   if (!x || !mask || !out || n <= 0) return T3D_ERR_ARG;
   if (ew4_ok((size_t)n, 4, {x, mask, out})) {

@@ -421,6 +421,62 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dout, const int* __
   dx[row * C + c] = rowmask ? dout[i] * rowmask[row] : dout[i];       // dx is zero-initialised by the caller
 }
 
+// ---- row-sparse backward through a frozen stack behind a max-pool ----------------------------------------------------------
+// The gradient entering a max-pool's input is non-zero only in the rows that are the arg-max of some channel: at most
+// min(C, N) of the N rows of a frustum.  Through layers WITHOUT batch statistics (eval-mode BN folded: the frozen BoxPC
+// branch of train_semisup_adv.py:364-388) the input gradient stays confined to those rows, so the whole backward chain
+// runs on the compacted rows.  pool_rows_kernel: per frustum, the ascending list of distinct arg-max rows (padded with -1
+// to S slots) and, per channel, the slot of its arg-max row.
+__global__ void __launch_bounds__(256) pool_rows_kernel(const int* __restrict__ arg, int N, int C, int S, int* __restrict__ rows,
+                                                       int* __restrict__ slot, int* __restrict__ count) {
+  extern __shared__ unsigned pr_bits[];               // [words] bitmap, then [words] exclusive popcount prefix
+  const int b = blockIdx.x, words = (N + 31) / 32;
+  unsigned* pre = pr_bits + words;
+  for (int w = threadIdx.x; w < words; w += 256) pr_bits[w] = 0u;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) { const int r = arg[(size_t)b * C + c]; atomicOr(&pr_bits[r >> 5], 1u << (r & 31)); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned run = 0;
+    for (int w = 0; w < words; ++w) { pre[w] = run; run += __popc(pr_bits[w]); }
+    count[b] = (int)run;
+  }
+  __syncthreads();
+  const int cnt = min(count[b], S);
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int r = arg[(size_t)b * C + c];
+    const int sl = (int)(pre[r >> 5] + __popc(pr_bits[r >> 5] & ((1u << (r & 31)) - 1u)));
+    slot[(size_t)b * C + c] = sl;
+    if (sl < S) rows[(size_t)b * S + sl] = r;
+  }
+  for (int s2 = cnt + threadIdx.x; s2 < S; s2 += 256) rows[(size_t)b * S + s2] = -1;
+}
+// dst[b*S + s, :] = src[b*N + rows[b,s], :]  (zeros where rows = -1); C % 4 == 0 takes 128-bit copies
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ rows, int N, int S, int C,
+                                                         size_t total_rows, float* __restrict__ dst) {
+  const int per_row = (C % 4 == 0) ? C / 4 : C;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_rows * per_row) return;
+  const size_t row = i / per_row;
+  const int j = (int)(i % per_row);
+  const int b = (int)(row / S), r = rows[row];
+  if (C % 4 == 0) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r >= 0) v = *reinterpret_cast<const float4*>(src + ((size_t)b * N + r) * C + 4 * j);
+    *reinterpret_cast<float4*>(dst + row * C + 4 * j) = v;
+  } else {
+    dst[row * C + j] = r >= 0 ? src[((size_t)b * N + r) * C + j] : 0.0f;
+  }
+}
+// dst[b*S + slot[b,c], c] = g[b,c]   (dst zero-initialised by the caller)
+__global__ void __launch_bounds__(256) scatter_pool_grad_kernel(const float* __restrict__ g, const int* __restrict__ slot, int B, int C, int S,
+                                                               float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i % C, sl = slot[i];
+  if (sl < S) dst[((size_t)b * S + sl) * C + c] = g[i];
+}
+
 // out = x * mask * scale  (tf.nn.dropout forward and backward with the same keep mask, scale = 1/keep_prob)
 __global__ void scale_mask_kernel(const float* __restrict__ x, const float* __restrict__ mask, float scale, float* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -279,11 +279,14 @@ class EvalLayer(object):
         self.out = y
         return y
 
-    def backward(self, dout, k_lo=0, k_hi=None):
-        """dX[:, k_lo:k_hi] = (dout * act'(out)) . W[k_lo:k_hi, :]^T   (dout is overwritten)."""
+    def backward(self, dout, k_lo=0, k_hi=None, out=None):
+        """dX[:, k_lo:k_hi] = (dout * act'(out)) . W[k_lo:k_hi, :]^T   (dout is overwritten).  `out`: this layer's forward
+        output at the rows of dout when the backward pass runs on a row subset (pool_rows / gather_rows)."""
         M = dout.shape[0]
+        out = self.out if out is None else out
+        assert out.shape == dout.shape
         if self.act != ACT_NONE:
-            call('t3d_act_bwd', ptr(dout), ptr(self.out), dout.numel(), self.act, stream())
+            call('t3d_act_bwd', ptr(dout), ptr(out), dout.numel(), self.act, stream())
         k_hi = self.K if k_hi is None else k_hi
         Wsub = self.Wf[k_lo:k_hi]                    # contiguous row block [k, N]
         return gemm(dout, self.N, 1, Wsub, 1, self.N, M, k_hi - k_lo, self.N)
@@ -320,3 +323,27 @@ def dropout(x, keep_mask, keep_prob):
     out = torch.empty_like(x)
     call('t3d_scale_mask', ptr(x), ptr(keep_mask), 1.0 / keep_prob, ptr(out), x.numel(), stream())
     return out
+
+
+def pool_rows(arg, B, N, C):
+    """Distinct arg-max rows of every frustum: rows [B,S] (ascending, -1 padded), slot [B,C], count [B]; S = min(C, N)."""
+    S = min(C, N)
+    rows = torch.empty((B, S), dtype=torch.int32, device=arg.device)
+    slot = torch.empty((B, C), dtype=torch.int32, device=arg.device)
+    count = torch.empty((B,), dtype=torch.int32, device=arg.device)
+    call('t3d_pool_rows', ptr(arg), B, N, C, S, ptr(rows), ptr(slot), ptr(count), stream())
+    return rows, slot, count, S
+
+
+def gather_rows(src, rows, B, N, S):
+    """src [B*N, C] -> [B*S, C]: the rows listed per frustum (zeros where -1)."""
+    C = src.shape[-1]
+    dst = torch.empty((B * S, C), dtype=torch.float32, device=src.device)
+    call('t3d_gather_rows', ptr(src), ptr(rows), B, N, S, C, ptr(dst), stream())
+    return dst
+
+
+def scatter_pool_grad(g, slot, B, C, S):
+    dst = torch.empty((B * S, C), dtype=torch.float32, device=g.device)
+    call('t3d_scatter_pool_grad', ptr(g), ptr(slot), B, C, S, ptr(dst), stream())
+    return dst

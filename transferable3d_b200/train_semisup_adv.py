@@ -31,7 +31,7 @@ from .constants import NUM_HEADING_BIN, NUM_SIZE_CLUSTER, NUM_CLASS, MEAN_DIMS_A
 from .weights import net_table
 from .train_boxpc import get_learning_rate, get_bn_decay          # same schedules (train_semisup_adv.py:135-153)
 from .train_layers import (ParamArena, TrainLayer, EvalLayer, ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH, maxpool, maxpool_bwd,
-                           rowmask_mul, dropout, gemm, dense)
+                           rowmask_mul, dropout, gemm, dense, pool_rows, gather_rows, scatter_pool_grad)
 
 
 def train_var_prefixes(FLAGS):
@@ -256,12 +256,16 @@ class SemiAdvTrainGraph(object):
             g = P[4].backward(g)
             if self.boxpc_one_hot:
                 g = g[:, :512].contiguous()
-            g = maxpool_bwd(g, p_arg, B, N, 512)
-            g = P[3].backward(g)
-            g = P[2].backward(g)
-            g = P[1].backward(g)
-            g6 = P[0].backward(g, k_lo=C, k_hi=C + 6)           # only the 6 plane-distance channels depend on the box
-            call('t3d_boxpc_features_bwd', ptr(pc), B, N, C, ptr(F_reg[0]), ptr(F_reg[2]), ptr(g6), ptr(g_reg), stream())
+            # the pooled gradient lives in the <= 512 arg-max rows of each frustum and, through these eval-mode layers (no
+            # batch statistics), stays there: the whole chain runs on the compacted rows (B x 512 instead of B x N)
+            rows, slot, _, Sr = pool_rows(p_arg, B, N, 512)
+            g = scatter_pool_grad(g.contiguous(), slot, B, 512, Sr)
+            g = P[3].backward(g, out=gather_rows(P[3].out, rows, B, N, Sr))
+            g = P[2].backward(g, out=gather_rows(P[2].out, rows, B, N, Sr))
+            g = P[1].backward(g, out=gather_rows(P[1].out, rows, B, N, Sr))
+            g6 = P[0].backward(g, k_lo=C, k_hi=C + 6, out=gather_rows(P[0].out, rows, B, N, Sr))     # only the 6 plane-distance channels depend on the box
+            pc_rows = gather_rows(pc.reshape(B * N, C), rows, B, N, Sr)
+            call('t3d_boxpc_features_bwd', ptr(pc_rows), B, Sr, C, ptr(F_reg[0]), ptr(F_reg[2]), ptr(g6), ptr(g_reg), stream())
             del g, g6
         losses.finish_box_reg(res)
 
