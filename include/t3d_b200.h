@@ -271,6 +271,17 @@ int t3d_gemm_bn_supported(int M, int N, int K, int kind);
 int t3d_gemm_bn_f32(const float* A, long long sam, long long sak, const float* a_scale, const float* a_shift, const float* B,
                     long long sbk, long long sbn, float* C, int ldc, int M, int N, int K, int splitk, const float* bias,
                     float* st_sum, float* st_sq, const float* st_shift, void* ws, size_t ws_bytes, t3d_stream_t stream);
+/* Forward-only lazy BN layer whose output only feeds the max-pool over the pool_rows rows of each group (inst_seg conv5 in
+ * the semi-supervised step, semisup_models.py:93-97 with the net frozen): the GEMM epilogue produces the batch statistics
+ * and, per group, the column max and min of the pre-BN output as order-preserving keys; the [M, N] output is never written.
+ * relu(a x + b) is monotone in x, so t3d_pool_bn_finish gives pooled = relu(a max + b) (a >= 0) or relu(a min + b).
+ * Needs the tensor-core workspace path (M >= 4096, 32 <= K <= 2048, K % 32 == 0), pool_rows % 128 == 0, M % pool_rows == 0;
+ * key buffers: [M / pool_rows, N] 32-bit words each. */
+int t3d_gemm_bn_pool_f32(const float* A, long long lda, const float* a_scale, const float* a_shift, const float* W, int ldw, int M,
+                         int N, int K, const float* bias, float* st_sum, float* st_sq, const float* st_shift, int pool_rows,
+                         void* pool_max_keys, void* pool_min_keys, void* ws, size_t ws_bytes, t3d_stream_t stream);
+int t3d_pool_bn_finish(const void* pool_max_keys, const void* pool_min_keys, const float* a_scale, const float* a_shift, int groups,
+                       int C, float* out, t3d_stream_t stream);
 /* y0[n] = sum_k a(k) W[k, n] + bias[n] for one row a (lazy BN applied when a_scale != NULL): the shift of the statistics */
 int t3d_row0(const float* a, const float* a_scale, const float* a_shift, const float* W, int ldw, const float* bias, int K, int N,
              float* y0, t3d_stream_t stream);

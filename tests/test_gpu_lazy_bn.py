@@ -220,3 +220,38 @@ def test_pool_rows_gather_scatter(B, N, C, built_lib):
         rest = np.ones(N, bool)
         rest[rows_h[b, :n]] = False
         assert (dense[b, rest] == 0).all()
+
+
+@pytest.mark.parametrize('B,N,K,C', [(6, 1024, 128, 1024), (40, 128, 64, 128), (5, 2048, 256, 512)])
+def test_gemm_bn_pool_forward_only_layer(B, N, K, C, built_lib):
+    """t3d_gemm_bn_pool_f32 + t3d_pool_bn_finish == GEMM -> batch statistics -> BN -> ReLU -> max over the N rows of each group,
+    without the B*N x C output; channels with a negative BN scale take the group minimum."""
+    rng = np.random.RandomState(B + K + C)
+    M = B * N
+    yp = rng.randn(M, K).astype(np.float32)
+    sc = ((rng.rand(K) + 0.5) * np.where(rng.rand(K) < 0.2, -1, 1)).astype(np.float32)
+    sh = (rng.randn(K) * 0.5).astype(np.float32)
+    W = (rng.randn(K, C) / np.sqrt(K)).astype(np.float32)
+    b = rng.randn(C).astype(np.float32)
+    gamma = ((rng.rand(C) + 0.5) * np.where(rng.rand(C) < 0.3, -1, 1)).astype(np.float32)
+    beta = (rng.randn(C) * 0.3).astype(np.float32)
+    x64 = np.maximum(sc.astype(np.float64) * yp + sh, 0)
+    y = x64 @ W.astype(np.float64) + b
+    mu, var = y.mean(0), y.var(0)
+    out = np.maximum(gamma * (y - mu) / np.sqrt(var + 1e-3) + beta, 0).reshape(B, N, C).max(1)
+    d = [_dev(a) for a in (yp, sc, sh, W, b, gamma, beta)]
+    E = lambda: torch.empty(C, device=DEV)
+    y0, s0, s1, mean, rstd, a_sc, a_sh = E(), E(), E(), E(), E(), E(), E()
+    call('t3d_row0', ptr(d[0]), ptr(d[1]), ptr(d[2]), ptr(d[3]), C, ptr(d[4]), K, C, ptr(y0), stream())
+    kmax = torch.empty((B, C), dtype=torch.int32, device=DEV)
+    kmin = torch.empty((B, C), dtype=torch.int32, device=DEV)
+    ws = gemm_workspace()
+    call('t3d_gemm_bn_pool_f32', ptr(d[0]), K, ptr(d[1]), ptr(d[2]), ptr(d[3]), C, M, C, K, ptr(d[4]), ptr(s0), ptr(s1), ptr(y0), N,
+         ptr(kmax), ptr(kmin), ptr(ws), ws.numel(), stream())
+    call('t3d_bn_finalize_affine', ptr(s0), ptr(s1), ptr(y0), M, C, 1e-3, 0.5, ptr(d[5]), ptr(d[6]), ptr(mean), ptr(rstd), ptr(a_sc),
+         ptr(a_sh), None, None, stream())
+    pooled = torch.empty((B, C), device=DEV)
+    call('t3d_pool_bn_finish', ptr(kmax), ptr(kmin), ptr(a_sc), ptr(a_sh), B, C, ptr(pooled), stream())
+    got = pooled.cpu().numpy()
+    assert np.allclose(mean.cpu().numpy(), mu, rtol=1e-5, atol=1e-5)
+    assert np.abs(got - out).max() <= 2e-4 * max(1.0, np.abs(out).max()), np.abs(got - out).max()

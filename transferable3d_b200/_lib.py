@@ -141,6 +141,8 @@ SIGNATURES = {
     't3d_bn_backward': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     't3d_gemm_bn_supported': (_I, [_I, _I, _I, _I]),
     't3d_gemm_bn_f32': (_I, [_P, _L, _L, _P, _P, _P, _L, _L, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _c.c_size_t, _P]),
+    't3d_gemm_bn_pool_f32': (_I, [_P, _L, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P, _c.c_size_t, _P]),
+    't3d_pool_bn_finish': (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
     't3d_row0': (_I, [_P, _P, _P, _P, _I, _P, _I, _I, _P, _P]),
     't3d_bn_finalize_affine': (_I, [_P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     't3d_colstats_lazy': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),

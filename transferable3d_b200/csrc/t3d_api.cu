@@ -828,20 +828,30 @@ extern "C" int t3d_seg_stage2_x2(const void* point_feat, const float* gbias, con
 struct GemmBnExtras {
   const float* a_scale = nullptr; const float* a_shift = nullptr;      // A := relu(a_scale[c] * A + a_shift[c])
   float* st_sum = nullptr; float* st_sq = nullptr; const float* st_shift = nullptr;
+  unsigned* pool_max = nullptr; unsigned* pool_min = nullptr; int pool_rows = 0;      // fused max-pool keys (C may be null)
   bool any() const { return a_scale != nullptr || st_sum != nullptr; }
 };
 
 static int gemm_f32_impl(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
                          int ldc, int M, int N, int K, int splitk, const float* bias, void* ws, size_t ws_bytes,
                          t3d_stream_t stream, const GemmBnExtras& x) {
-  if (!A || !B || !C) return T3D_ERR_ARG;
+  if (!A || !B || (!C && !x.pool_max)) return T3D_ERR_ARG;
   if (M <= 0 || N <= 0 || K <= 0 || splitk <= 0 || ldc < N) return T3D_ERR_SHAPE;
   if ((sam != 1 && sak != 1) || (sbk != 1 && sbn != 1)) return T3D_ERR_SHAPE;
   if (splitk > 1) T3D_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, S(stream)));
-  GemmArgs a{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias, x.st_sum, x.st_sq, x.st_shift};
+  GemmArgs a{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias, x.st_sum, x.st_sq, x.st_shift, x.pool_max, x.pool_min, x.pool_rows};
   if (x.st_sum != nullptr) {
     T3D_CUDA(cudaMemsetAsync(x.st_sum, 0, sizeof(float) * N, S(stream)));
     T3D_CUDA(cudaMemsetAsync(x.st_sq, 0, sizeof(float) * N, S(stream)));
+  }
+  if (x.pool_max != nullptr) {
+    // the fused max-pool lives in the statistics epilogue of the tensor-core path: whole tiles inside one group
+    if (!x.st_sum || !x.pool_min || x.pool_rows <= 0 || x.pool_rows % kXgBM != 0 || M % x.pool_rows != 0 || splitk != 1 || sak != 1 ||
+        !xg_fits(M, N, K) || (K <= kSkinnyMax))
+      return T3D_ERR_SHAPE;
+    const size_t groups = (size_t)(M / x.pool_rows);
+    T3D_CUDA(cudaMemsetAsync(x.pool_max, 0x00, sizeof(unsigned) * groups * N, S(stream)));
+    T3D_CUDA(cudaMemsetAsync(x.pool_min, 0xff, sizeof(unsigned) * groups * N, S(stream)));
   }
   {   // HBM-bound first-layer shapes (skinny_gemm.cuh); 128-bit accesses need aligned bases and leading dimensions
     auto al16 = [](const void* p) { return (((uintptr_t)p) & 15) == 0; };
@@ -903,6 +913,7 @@ static int gemm_f32_impl(const float* A, long long sam, long long sak, const flo
       if (x.a_scale && ak && (!pre || K % kXgBK != 0 || (((uintptr_t)x.a_scale | (uintptr_t)x.a_shift) & 15))) return T3D_ERR_SHAPE;
       if (x.a_scale && !ak && pre) return T3D_ERR_SHAPE;
       if (x.st_sum && sk != 1) return T3D_ERR_SHAPE;
+      if (x.pool_max && !pre) return T3D_ERR_SHAPE;
     }
     if (pre) {     // forward / dgrad: pre-split B
       o.bpre = reinterpret_cast<const uint8_t*>(ws);
@@ -980,6 +991,30 @@ extern "C" int t3d_gemm_bn_f32(const float* A, long long sam, long long sak, con
   GemmBnExtras x;
   x.a_scale = a_scale; x.a_shift = a_shift; x.st_sum = st_sum; x.st_sq = st_sq; x.st_shift = st_shift;
   return gemm_f32_impl(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, splitk, bias, ws, ws_bytes, stream, x);
+}
+
+// Forward GEMM of a forward-only lazy BN layer whose output only feeds the max-pool over the pool_rows rows of each group
+// (the segmentation net's conv5 in the semi-supervised step): statistics AND the per-group column max / min come out of the
+// epilogue, the [M, N] output is never written.  t3d_pool_bn_finish turns the keys into the pooled activations.
+extern "C" int t3d_gemm_bn_pool_f32(const float* A, long long lda, const float* a_scale, const float* a_shift, const float* W, int ldw,
+                                    int M, int N, int K, const float* bias, float* st_sum, float* st_sq, const float* st_shift,
+                                    int pool_rows, void* pool_max_keys, void* pool_min_keys, void* ws, size_t ws_bytes,
+                                    t3d_stream_t stream) {
+  if ((a_scale != nullptr) != (a_shift != nullptr) || !st_sum || !st_sq || !pool_max_keys || !pool_min_keys) return T3D_ERR_ARG;
+  GemmBnExtras x;
+  x.a_scale = a_scale; x.a_shift = a_shift; x.st_sum = st_sum; x.st_sq = st_sq; x.st_shift = st_shift;
+  x.pool_max = reinterpret_cast<unsigned*>(pool_max_keys); x.pool_min = reinterpret_cast<unsigned*>(pool_min_keys); x.pool_rows = pool_rows;
+  return gemm_f32_impl(A, lda, 1, W, ldw, 1, nullptr, N, M, N, K, 1, bias, ws, ws_bytes, stream, x);
+}
+extern "C" int t3d_pool_bn_finish(const void* pool_max_keys, const void* pool_min_keys, const float* a_scale, const float* a_shift,
+                                  int groups, int C, float* out, t3d_stream_t stream) {
+  if (!pool_max_keys || !pool_min_keys || !a_scale || !a_shift || !out) return T3D_ERR_ARG;
+  if (groups <= 0 || C <= 0) return T3D_ERR_SHAPE;
+  pool_bn_finish_kernel<<<(groups * C + 255) / 256, 256, 0, S(stream)>>>(reinterpret_cast<const unsigned*>(pool_max_keys),
+                                                                        reinterpret_cast<const unsigned*>(pool_min_keys), a_scale, a_shift,
+                                                                        groups * C, C, out);
+  T3D_CHECK_LAUNCH();
+  return 0;
 }
 
 // y0[n] = sum_k a(k) W[k, n] + bias[n] for ONE row a (lazy BN applied when a_scale != null): the shift of the fused statistics

@@ -20,6 +20,11 @@ struct GemmArgs {
   // fused batch-norm statistics of C (tensor-core path, splitk == 1): st_sum[n] += sum_m (C - st_shift[n]),
   // st_sq[n] += sum_m (C - st_shift[n])^2; zero-initialised by the caller.  null: off
   float* st_sum; float* st_sq; const float* st_shift;
+  // fused max-pool of a forward-only lazy BN layer (C == null: the output is never stored): per group of pool_rows rows the
+  // column maximum and minimum of the pre-BN output, as order-preserving keys (f32_ordered) merged by atomic max / min into
+  // pool_max / pool_min [groups, N] (initialised to 0 / 0xffffffff).  relu(a x + b) is monotone in x, so the pooled value is
+  // relu(a max + b) for a >= 0 and relu(a min + b) otherwise (pool_bn_finish_kernel).  pool_rows % 128 == 0.
+  unsigned* pool_max; unsigned* pool_min; int pool_rows;
 };
 
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs a) {
@@ -135,15 +140,36 @@ __global__ void __launch_bounds__(256) colstats_kernel(const ColStatArgs a) {
     const float mu = a.mode == 1 ? a.mean[c] : 0.f, rs = a.mode == 1 ? a.rstd[c] : 0.f;
     const float shift = (a.mode == 0 && a.y) ? a.y[c] : 0.f;
     const float asc = a.a_scale ? a.a_scale[c] : 0.f, ash = a.a_scale ? a.a_shift[c] : 0.f;
-    for (int r = r0 + rl; r < r1; r += 8) {
-      const size_t i = (size_t)r * a.C + c;
-      if (a.mode == 0) { const float x = a.X[i] - shift; s0 += x; s1 = fmaf(x, x, s1); }
-      else {
-        float dy = a.X[i];
-        const float yv = a.y[i];
-        if (a.out) dy *= act_grad_from_out(a.out[i], a.act);
+    // four rows in flight per thread (the loop carried 2 loads: 16 KB in flight per SM, 3.4 TB/s)
+    int r = r0 + rl;
+    if (a.mode == 0) {
+      for (; r + 24 < r1; r += 32) {
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = a.X[(size_t)(r + 8 * u) * a.C + c];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const float d = x[u] - shift; s0 += d; s1 = fmaf(d, d, s1); }
+      }
+      for (; r < r1; r += 8) { const float d = a.X[(size_t)r * a.C + c] - shift; s0 += d; s1 = fmaf(d, d, s1); }
+    } else {
+      auto term = [&](float dy, float yv, float ov) {
+        if (a.out) dy *= act_grad_from_out(ov, a.act);
         else if (a.a_scale) dy = fmaf(asc, yv, ash) > 0.0f ? dy : 0.0f;
         s0 += dy; s1 = fmaf(dy, (yv - mu) * rs, s1);
+      };
+      for (; r + 24 < r1; r += 32) {
+        float d[4], yv[4], ov[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const size_t i = (size_t)(r + 8 * u) * a.C + c;
+          d[u] = a.X[i]; yv[u] = a.y[i]; ov[u] = a.out ? a.out[i] : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) term(d[u], yv[u], ov[u]);
+      }
+      for (; r < r1; r += 8) {
+        const size_t i = (size_t)r * a.C + c;
+        term(a.X[i], a.y[i], a.out ? a.out[i] : 0.0f);
       }
     }
   }
@@ -308,6 +334,17 @@ __global__ void maxpool_split_finish_kernel(const unsigned long long* __restrict
   const unsigned long long k = keys[i];
   out[i] = f32_unordered((uint32_t)(k >> 32));
   arg[i] = (int)(0xffffffffu - (uint32_t)(k & 0xffffffffull));
+}
+
+// pooled[g, c] = relu(a_scale[c] * (a_scale[c] >= 0 ? max : min) + a_shift[c]) from the keys of the fused max-pool epilogue
+__global__ void pool_bn_finish_kernel(const unsigned* __restrict__ kmax, const unsigned* __restrict__ kmin, const float* __restrict__ a_scale,
+                                      const float* __restrict__ a_shift, int total, int C, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = i % C;
+  const float sc = a_scale[c];
+  const float x = sc >= 0.0f ? f32_unordered(kmax[i]) : f32_unordered(kmin[i]);
+  out[i] = fmaxf(fmaf(sc, x, a_shift[c]), 0.0f);
 }
 
 // ---- backward of [BN -> ReLU -> (row mask) -> max-pool] without the dense pooled-gradient tensor ------------------------

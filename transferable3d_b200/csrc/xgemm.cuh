@@ -506,10 +506,14 @@ constexpr uint32_t kXgPatchRow = 144, kXgPatchBytes = 32 * kXgPatchRow;
 // STATS: the column sums of (x - shift[col]) and of its square over the chunk's valid rows are added to st_sum / st_sq
 // (training-mode batch norm: the statistics pass over the layer output is fused here; shift = row 0 of the output keeps
 // E[d^2] - E[d]^2 well conditioned).  Each lane sums its 8 rows of 4 columns, two shuffles fold the 4 row groups.
+// pool_max != null (STATS kernels): additionally the column max / min of the chunk's valid rows as ordered keys, merged into
+// pool_max / pool_min + pool_off (the group's row of the [groups, N] key arrays); C == null skips the store.
 template <bool ATOMIC, bool STATS = false>
 __device__ __forceinline__ void xg_store_chunk(const XgTile& t, float* __restrict__ C, long long ldc, int M, int N, int row0, int col0,
                                                const float (&v)[32], float* __restrict__ st_sum = nullptr,
-                                               float* __restrict__ st_sq = nullptr, const float* __restrict__ st_shift = nullptr) {
+                                               float* __restrict__ st_sq = nullptr, const float* __restrict__ st_shift = nullptr,
+                                               unsigned* __restrict__ pool_max = nullptr, unsigned* __restrict__ pool_min = nullptr,
+                                               size_t pool_off = 0) {
   const uint32_t patch = t.sbase + (uint32_t)t.warp * kXgPatchBytes;
   __syncwarp();                                          // the previous chunk's reads are done
 #pragma unroll
@@ -519,6 +523,7 @@ __device__ __forceinline__ void xg_store_chunk(const XgTile& t, float* __restric
   __syncwarp();
   const int cq = (t.lane & 7) * 4, gn = col0 + cq;
   float ss[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f}, sf[4] = {0.f, 0.f, 0.f, 0.f};
+  float pmx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, pmn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
   if (STATS && st_shift != nullptr) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) sf[e] = (gn + e < N) ? __ldg(st_shift + gn + e) : 0.0f;
@@ -532,7 +537,10 @@ __device__ __forceinline__ void xg_store_chunk(const XgTile& t, float* __restric
       const float d0 = x.x - sf[0], d1 = x.y - sf[1], d2 = x.z - sf[2], d3 = x.w - sf[3];
       ss[0] += d0; ss[1] += d1; ss[2] += d2; ss[3] += d3;
       sq[0] = fmaf(d0, d0, sq[0]); sq[1] = fmaf(d1, d1, sq[1]); sq[2] = fmaf(d2, d2, sq[2]); sq[3] = fmaf(d3, d3, sq[3]);
+      pmx[0] = fmaxf(pmx[0], x.x); pmx[1] = fmaxf(pmx[1], x.y); pmx[2] = fmaxf(pmx[2], x.z); pmx[3] = fmaxf(pmx[3], x.w);
+      pmn[0] = fminf(pmn[0], x.x); pmn[1] = fminf(pmn[1], x.y); pmn[2] = fminf(pmn[2], x.z); pmn[3] = fminf(pmn[3], x.w);
     }
+    if (C == nullptr) continue;
     float* c = C + (long long)gm * ldc + gn;
     if (gn + 4 <= N && (((uintptr_t)c) & 15) == 0) {
       if (ATOMIC) red_add_v4(c, x.x, x.y, x.z, x.w);
@@ -553,6 +561,21 @@ __device__ __forceinline__ void xg_store_chunk(const XgTile& t, float* __restric
     for (int e = 0; e < 4; ++e) {
       ss[e] += __shfl_xor_sync(0xffffffffu, ss[e], 8); ss[e] += __shfl_xor_sync(0xffffffffu, ss[e], 16);
       sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 8); sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 16);
+    }
+    if (pool_max != nullptr) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        pmx[e] = fmaxf(pmx[e], __shfl_xor_sync(0xffffffffu, pmx[e], 8)); pmx[e] = fmaxf(pmx[e], __shfl_xor_sync(0xffffffffu, pmx[e], 16));
+        pmn[e] = fminf(pmn[e], __shfl_xor_sync(0xffffffffu, pmn[e], 8)); pmn[e] = fminf(pmn[e], __shfl_xor_sync(0xffffffffu, pmn[e], 16));
+      }
+      if (t.lane < 8 && pmx[0] >= pmn[0]) {         // at least one valid row in the chunk
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (gn + e < N) {
+            atomicMax(pool_max + pool_off + gn + e, f32_ordered(pmx[e]));
+            atomicMin(pool_min + pool_off + gn + e, f32_ordered(pmn[e]));
+          }
+      }
     }
     if (t.lane < 8 && gn < N) {
       if (gn + 4 <= N && ((((uintptr_t)(st_sum + gn)) | ((uintptr_t)(st_sq + gn))) & 15) == 0) {
@@ -588,7 +611,9 @@ __device__ __forceinline__ void xg_epilogue_gemm(const GemmArgs& a, const XgTile
         for (int j = 0; j < 32; ++j) v[j] += q[j];
       }
       if (a.splitk > 1) xg_store_chunk<true>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v);
-      else if (a.st_sum != nullptr) xg_store_chunk<false, true>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v, a.st_sum, a.st_sq, a.st_shift);
+      else if (a.st_sum != nullptr)
+        xg_store_chunk<false, true>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v, a.st_sum, a.st_sq, a.st_shift, a.pool_max, a.pool_min,
+                                    a.pool_max != nullptr ? (size_t)(t.m0 / a.pool_rows) * a.N : 0);
       else xg_store_chunk<false>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v);
     }
   }

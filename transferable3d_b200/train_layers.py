@@ -166,6 +166,35 @@ class TrainLayer(object):
             self.mean, self.rstd, self.out = mean, rstd, out
         return out
 
+    def forward_pooled(self, x, bn_decay, B, N):
+        """Forward-only BN + ReLU layer whose output only feeds the max-pool over the N rows of each of the B groups: returns the
+        pooled activations [B, C].  On the tensor-core path the statistics and the per-group max / min of the pre-BN output
+        come out of the GEMM epilogue and the B*N x C output is never written (t3d_gemm_bn_pool_f32); otherwise forward +
+        maxpool."""
+        M = B * N
+        ok = self.bn and self.act == ACT_RELU and N % 128 == 0 and bn_supported(M, self.N, self.K, 0) == 1
+        if not ok:
+            pooled, _ = maxpool(self.forward(x, bn_decay, keep=False, lazy=True), B, N, self.N)
+            return pooled
+        dev = x.device
+        E = lambda: torch.empty(self.N, device=dev)
+        xl = x if isinstance(x, Lazy) else None
+        xa = xl.y if xl is not None else x
+        sc, sh = (ptr(xl.scale), ptr(xl.shift)) if xl is not None else (None, None)
+        y0, s0, s1, mean, rstd, a_scale, a_shift = E(), E(), E(), E(), E(), E(), E()
+        call('t3d_row0', ptr(xa), sc, sh, ptr(self.W()), self.N, ptr(self.p('biases')), self.K, self.N, ptr(y0), stream())
+        kmax = torch.empty((B, self.N), dtype=torch.int32, device=dev)
+        kmin = torch.empty((B, self.N), dtype=torch.int32, device=dev)
+        ws = gemm_workspace()
+        call('t3d_gemm_bn_pool_f32', ptr(xa), self.K, sc, sh, ptr(self.W()), self.N, M, self.N, self.K, ptr(self.p('biases')), ptr(s0),
+             ptr(s1), ptr(y0), N, ptr(kmax), ptr(kmin), ptr(ws), ws.numel(), stream())
+        mm, mv = self.moving[self.name + '/bn/moving_mean'], self.moving[self.name + '/bn/moving_variance']
+        call('t3d_bn_finalize_affine', ptr(s0), ptr(s1), ptr(y0), M, self.N, BN_EPS, float(bn_decay), ptr(self.p('bn/gamma')),
+             ptr(self.p('bn/beta')), ptr(mean), ptr(rstd), ptr(a_scale), ptr(a_shift), ptr(mm), ptr(mv), stream())
+        pooled = torch.empty((B, self.N), dtype=torch.float32, device=dev)
+        call('t3d_pool_bn_finish', ptr(kmax), ptr(kmin), ptr(a_scale), ptr(a_shift), B, self.N, ptr(pooled), stream())
+        return pooled
+
     def backward(self, dout, need_dx=True):
         """dout: gradient w.r.t. this layer's output (overwritten in place).  Returns dX or None.
         A layer whose variables are not in the gradient arena (frozen, but still in the training-mode graph: batch

@@ -141,8 +141,7 @@ class SemiAdvTrainGraph(object):
         x = S[1].forward(x, bn_decay, keep=False, lazy=True)
         pf_lazy = S[2].forward(x, bn_decay, keep=False, lazy=True)
         x = S[3].forward(pf_lazy, bn_decay, keep=False, lazy=True)
-        x = S[4].forward(x, bn_decay, keep=False, lazy=True)
-        gfeat, _ = maxpool(x, B, N, 1024)
+        gfeat = S[4].forward_pooled(x, bn_decay, B, N)                  # conv5 + BN + ReLU + max-pool: the B*N x 1024 output never exists
         del x
         point_feat = dense(pf_lazy)                                      # [B*N, 64]: the operand of the folded conv6
         W6 = S[5].W()                                                    # [64 + 1024, 512]
