@@ -910,7 +910,7 @@ static int gemm_f32_impl(const float* A, long long sam, long long sak, const flo
     if (x.any()) {
       // lazy BN of a k-contiguous A lives in the pre-split-B loaders (128-bit parameter loads: K % 32 == 0, aligned arrays);
       // of a row-contiguous A (wgrad) in the generic loader.  Statistics need the whole K range in one CTA.
-      if (x.a_scale && ak && (!pre || K % kXgBK != 0 || (((uintptr_t)x.a_scale | (uintptr_t)x.a_shift) & 15))) return T3D_ERR_SHAPE;
+      if (x.a_scale && ak && (!pre || K % kXgBK != 0 || K > kXgLazyMaxK)) return T3D_ERR_SHAPE;
       if (x.a_scale && !ak && pre) return T3D_ERR_SHAPE;
       if (x.st_sum && sk != 1) return T3D_ERR_SHAPE;
       if (x.pool_max && !pre) return T3D_ERR_SHAPE;
@@ -977,7 +977,7 @@ extern "C" int t3d_gemm_bn_supported(int M, int N, int K, int kind) {
     if (M >= 4096 && K <= kSkinnyMax && N % 4 == 0 && N <= 1024 && 256 % (N / 4) == 0 &&
         sizeof(float) * (size_t)(K * N + 3 * N) <= kSkinnySmemMax)
       return 2;                                     // first-layer kernel: statistics only (its input is never a lazy BN)
-    return (xg_fits(M, N, K) && M >= 4096 && K <= kXgMaxKChunk && K % kXgBK == 0) ? 1 : 0;
+    return (xg_fits(M, N, K) && M >= 4096 && K <= kXgLazyMaxK && K % kXgBK == 0) ? 1 : 0;
   }
   if (kind == 1) return (xg_fits(M, N, K) && !(K >= 4096 && M <= kSkinnyMax)) ? 1 : 0;
   return 0;

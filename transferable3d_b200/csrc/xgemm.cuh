@@ -46,7 +46,9 @@ constexpr int kXgMinBlocks = XG_MINB;                          // CTAs per SM th
 constexpr int kXgMaxKChunk = 2048;                            // longest K range accumulated in TMEM by one CTA
 constexpr uint32_t kXgImage = 128 * 128;                       // bytes of one [128 x 64] bf16 image
 constexpr uint32_t kXgBars = 6 * kXgImage;                     // barrier block offset
-constexpr uint32_t kXgSmemBytes = 6 * kXgImage + 64 + 1024;    // + barriers / TMEM slot + 1024-byte alignment slack
+constexpr int kXgLazyMaxK = 512;                               // lazy BN of a k-contiguous A: scale / shift tables in shared memory
+constexpr uint32_t kXgParams = kXgBars + 64;                   // [a_scale K][a_shift K] fp32 (one-tile kernels: K <= kXgLazyMaxK)
+constexpr uint32_t kXgSmemBytes = 6 * kXgImage + 64 + 8 * kXgLazyMaxK + 1024;    // + barriers / TMEM slot + tables + 1024-byte alignment slack
 
 struct XgOperands {
   const float* A; long long lda;      // UNIT_K: A(m,k) = A[m*lda + k];  else A(m,k) = A[k*lda + m]
@@ -292,7 +294,7 @@ template <int PARTS>
 __device__ __forceinline__ void xg_loader_pre(const float* __restrict__ P, long long ld, int row0, int nrows, int kend, bool vec,
                                               uint32_t a_img, uint32_t b_img, const uint8_t* __restrict__ bsrc, int w, int lane, int nst,
                                               uint32_t full0, uint32_t empty0, XgTracer& tr,
-                                              const float* __restrict__ tsc = nullptr, const float* __restrict__ tsh = nullptr) {
+                                              uint32_t tsc = 0, uint32_t tsh = 0) {      // shared-memory tables of the lazy BN map (0: none)
   const int rsub = lane >> 3, c = lane & 7;
   auto rowof = [&](int i) { return w * 16 + (i >> 1) * 8 + (i & 1) * 2 + (rsub & 1) * 4 + (rsub >> 1); };
   const int row = row0 + rowof(0), kofs = 4 * c;
@@ -324,9 +326,9 @@ __device__ __forceinline__ void xg_loader_pre(const float* __restrict__ P, long 
   const int tid = w * 32 + lane;
   auto emit = [&](int it, float (&r)[16]) {
     const int s = it & 1;
-    if (tsc != nullptr) {      // lazy BN: this thread's 4 channels of the stage (issued before the slot wait)
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(tsc + it * kXgBK + kofs));
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(tsh + it * kXgBK + kofs));
+    if (tsc != 0) {            // lazy BN: this thread's 4 channels of the stage
+      const float4 sc = ld_shared_f4(tsc + 4u * (uint32_t)(it * kXgBK + kofs));
+      const float4 sh = ld_shared_f4(tsh + 4u * (uint32_t)(it * kXgBK + kofs));
 #pragma unroll
       for (int i = 0; i < 4; ++i) xg_bn4(&r[4 * i], sc, sh);
     }
@@ -411,6 +413,10 @@ __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_r
     fence_barrier_init();
   }
   if (warp == 8) tmem_alloc<256>(tmem_slot);
+  if (B_PRE && o.a_scale != nullptr) {      // lazy BN tables of the A operand (K <= kXgLazyMaxK, checked by the host)
+    float* tab = reinterpret_cast<float*>(smem + kXgParams);
+    for (int i = threadIdx.x; i < o.K; i += kXgThreads) { tab[i] = __ldg(o.a_scale + i); tab[o.K + i] = __ldg(o.a_shift + i); }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -424,7 +430,7 @@ __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_r
     // ---------------------------------------------------------------- loaders: global fp32 -> registers -> 3 bf16 images
     if (B_PRE) xg_loader_pre<PARTS>(o.A, o.lda, m0, o.M, kend, o.vecA != 0, sbase, sbase + 3u * kXgImage,
                                     o.bpre + (size_t)(blockIdx.x % o.ntn) * o.nkb * kXgPreBlockBytes, warp, lane, nst, full(0), empty(0), tr,
-                                    o.a_scale, o.a_shift);
+                                    o.a_scale != nullptr ? sbase + kXgParams : 0u, sbase + kXgParams + 4u * (uint32_t)o.K);
     else if (warp < 4) xg_loader<A_UNIT_K, PARTS>(o.A, o.lda, m0, o.M, kbeg, kend, o.vecA != 0, sbase, warp & 3, lane, nst, full(0), empty(0), tr,
                                                   o.a_scale, o.a_shift);
     else xg_loader<B_UNIT_K, PARTS>(o.B, o.ldb, n0, o.N, kbeg, kend, o.vecB != 0, sbase + 3u * kXgImage, warp & 3, lane, nst, full(0), empty(0), tr);
@@ -503,17 +509,34 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 // Patch rows are 144 bytes apart, so both the 128-bit writes (thread = row) and reads (8 lanes = one row) are
 // conflict-free.
 constexpr uint32_t kXgPatchRow = 144, kXgPatchBytes = 32 * kXgPatchRow;
-// STATS: the column sums of (x - shift[col]) and of its square over the chunk's valid rows are added to st_sum / st_sq
+// MODE 1: the column sums of (x - shift[col]) and of its square over the chunk's valid rows are added to st_sum / st_sq
 // (training-mode batch norm: the statistics pass over the layer output is fused here; shift = row 0 of the output keeps
-// E[d^2] - E[d]^2 well conditioned).  Each lane sums its 8 rows of 4 columns, two shuffles fold the 4 row groups.
-// pool_max != null (STATS kernels): additionally the column max / min of the chunk's valid rows as ordered keys, merged into
+// E[d^2] - E[d]^2 well conditioned).  Each lane sums its 8 rows of 4 columns with packed fp32 arithmetic (FFMA2: the
+// epilogue warps are the limit of the K <= 128 kernels, and the scalar version of this block cost them 30 %), two shuffles
+// fold the 4 row groups.  MODE 2: additionally the column max / min of the chunk's valid rows as ordered keys, merged into
 // pool_max / pool_min + pool_off (the group's row of the [groups, N] key arrays); C == null skips the store.
-template <bool ATOMIC, bool STATS = false>
+__device__ __forceinline__ unsigned long long xg_pk2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void xg_upk2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long xg_add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long xg_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+template <bool ATOMIC, int MODE = 0>
 __device__ __forceinline__ void xg_store_chunk(const XgTile& t, float* __restrict__ C, long long ldc, int M, int N, int row0, int col0,
                                                const float (&v)[32], float* __restrict__ st_sum = nullptr,
                                                float* __restrict__ st_sq = nullptr, const float* __restrict__ st_shift = nullptr,
                                                unsigned* __restrict__ pool_max = nullptr, unsigned* __restrict__ pool_min = nullptr,
-                                               size_t pool_off = 0) {
+                                               size_t pool_off = 0, float4 sfv = make_float4(0.f, 0.f, 0.f, 0.f)) {
   const uint32_t patch = t.sbase + (uint32_t)t.warp * kXgPatchBytes;
   __syncwarp();                                          // the previous chunk's reads are done
 #pragma unroll
@@ -522,25 +545,25 @@ __device__ __forceinline__ void xg_store_chunk(const XgTile& t, float* __restric
                  __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
   __syncwarp();
   const int cq = (t.lane & 7) * 4, gn = col0 + cq;
-  float ss[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f}, sf[4] = {0.f, 0.f, 0.f, 0.f};
+  // packed accumulators: columns (0, 1) and (2, 3) of this lane's quad; the shift enters negated (sfv fetched by the caller)
+  unsigned long long ss01 = 0ull, ss23 = 0ull, sq01 = 0ull, sq23 = 0ull;
+  const unsigned long long nsf01 = xg_pk2(-sfv.x, -sfv.y), nsf23 = xg_pk2(-sfv.z, -sfv.w);
   float pmx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, pmn[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-  if (STATS && st_shift != nullptr) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) sf[e] = (gn + e < N) ? __ldg(st_shift + gn + e) : 0.0f;
-  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = (t.lane >> 3) + 4 * i, gm = row0 + r;
     const float4 x = ld_shared_f4(patch + (uint32_t)r * kXgPatchRow + 4u * cq);
     if (gm >= M || gn >= N) continue;
-    if (STATS) {
-      const float d0 = x.x - sf[0], d1 = x.y - sf[1], d2 = x.z - sf[2], d3 = x.w - sf[3];
-      ss[0] += d0; ss[1] += d1; ss[2] += d2; ss[3] += d3;
-      sq[0] = fmaf(d0, d0, sq[0]); sq[1] = fmaf(d1, d1, sq[1]); sq[2] = fmaf(d2, d2, sq[2]); sq[3] = fmaf(d3, d3, sq[3]);
+    if (MODE >= 1) {
+      const unsigned long long d01 = xg_add2(xg_pk2(x.x, x.y), nsf01), d23 = xg_add2(xg_pk2(x.z, x.w), nsf23);
+      ss01 = xg_add2(ss01, d01); ss23 = xg_add2(ss23, d23);
+      sq01 = xg_fma2(d01, d01, sq01); sq23 = xg_fma2(d23, d23, sq23);
+    }
+    if (MODE == 2) {
       pmx[0] = fmaxf(pmx[0], x.x); pmx[1] = fmaxf(pmx[1], x.y); pmx[2] = fmaxf(pmx[2], x.z); pmx[3] = fmaxf(pmx[3], x.w);
       pmn[0] = fminf(pmn[0], x.x); pmn[1] = fminf(pmn[1], x.y); pmn[2] = fminf(pmn[2], x.z); pmn[3] = fminf(pmn[3], x.w);
+      if (C == nullptr) continue;
     }
-    if (C == nullptr) continue;
     float* c = C + (long long)gm * ldc + gn;
     if (gn + 4 <= N && (((uintptr_t)c) & 15) == 0) {
       if (ATOMIC) red_add_v4(c, x.x, x.y, x.z, x.w);
@@ -556,13 +579,15 @@ __device__ __forceinline__ void xg_store_chunk(const XgTile& t, float* __restric
       }
     }
   }
-  if (STATS) {
+  if (MODE >= 1) {
+    float ss[4], sq[4];
+    xg_upk2(ss01, ss[0], ss[1]); xg_upk2(ss23, ss[2], ss[3]); xg_upk2(sq01, sq[0], sq[1]); xg_upk2(sq23, sq[2], sq[3]);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       ss[e] += __shfl_xor_sync(0xffffffffu, ss[e], 8); ss[e] += __shfl_xor_sync(0xffffffffu, ss[e], 16);
       sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 8); sq[e] += __shfl_xor_sync(0xffffffffu, sq[e], 16);
     }
-    if (pool_max != nullptr) {
+    if (MODE == 2) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         pmx[e] = fmaxf(pmx[e], __shfl_xor_sync(0xffffffffu, pmx[e], 8)); pmx[e] = fmaxf(pmx[e], __shfl_xor_sync(0xffffffffu, pmx[e], 16));
@@ -601,6 +626,12 @@ __device__ __forceinline__ void xg_epilogue_gemm(const GemmArgs& a, const XgTile
 #pragma unroll 1
     for (int ch = 0; ch < nchunks; ++ch) {
       const int c0 = (nchunks == 2 ? (t.warp >> 2) * 64 : 0) + ch * 32;
+      float4 sfv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.st_sum != nullptr && a.st_shift != nullptr) {     // this lane's 4 statistic shifts, in flight during the TMEM load
+        const int gs = t.n0 + c0 + (t.lane & 7) * 4;
+        sfv.x = gs < a.N ? __ldg(a.st_shift + gs) : 0.f; sfv.y = gs + 1 < a.N ? __ldg(a.st_shift + gs + 1) : 0.f;
+        sfv.z = gs + 2 < a.N ? __ldg(a.st_shift + gs + 2) : 0.f; sfv.w = gs + 3 < a.N ? __ldg(a.st_shift + gs + 3) : 0.f;
+      }
       float v[32];
       xg_acc32<PARTS>(t, c0, v);
       if (a.bias && first_split) {
@@ -611,9 +642,11 @@ __device__ __forceinline__ void xg_epilogue_gemm(const GemmArgs& a, const XgTile
         for (int j = 0; j < 32; ++j) v[j] += q[j];
       }
       if (a.splitk > 1) xg_store_chunk<true>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v);
+      else if (a.pool_max != nullptr)
+        xg_store_chunk<false, 2>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v, a.st_sum, a.st_sq, a.st_shift, a.pool_max, a.pool_min,
+                                 (size_t)(t.m0 / a.pool_rows) * a.N, sfv);
       else if (a.st_sum != nullptr)
-        xg_store_chunk<false, true>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v, a.st_sum, a.st_sq, a.st_shift, a.pool_max, a.pool_min,
-                                    a.pool_max != nullptr ? (size_t)(t.m0 / a.pool_rows) * a.N : 0);
+        xg_store_chunk<false, 1>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v, a.st_sum, a.st_sq, a.st_shift, nullptr, nullptr, 0, sfv);
       else xg_store_chunk<false>(t, a.C, a.ldc, a.M, a.N, row0, t.n0 + c0, v);
     }
   }
@@ -749,7 +782,8 @@ constexpr int kXgPPSlots = 4;
 constexpr uint32_t kXgPPImages = 12 * kXgImage;                                  // A: 3 parts x 2 blocks, then B the same
 constexpr uint32_t kXgPPPatch = kXgPPImages;                                    // 4 x kXgPatchBytes
 constexpr uint32_t kXgPPBars = kXgPPPatch + 4 * kXgPatchBytes;
-constexpr uint32_t kXgPPSmemBytes = kXgPPBars + 128 + 1024;
+constexpr uint32_t kXgPPParams = kXgPPBars + 128;                               // [a_scale 128][a_shift 128] fp32 (K <= 128 here)
+constexpr uint32_t kXgPPSmemBytes = kXgPPBars + 128 + 1024 + 1024;
 
 // shared address of (part p, ring slot s) of an operand whose images start at `base`: block s >> 1 of image p; the
 // stage is half s & 1 of that block
@@ -777,6 +811,10 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs g
     fence_barrier_init();
   }
   if (warp == kXgPPLoaders + 4) tmem_alloc<512>(tmem_slot);
+  if (o.a_scale != nullptr) {               // lazy BN tables of the A operand (K <= 128)
+    float* tab = reinterpret_cast<float*>(smem + kXgPPParams);
+    for (int i = threadIdx.x; i < o.K; i += kXgPPThreads) { tab[i] = __ldg(o.a_scale + i); tab[128 + i] = __ldg(o.a_shift + i); }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -839,8 +877,8 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs g
     auto emit = [&](int g, float (&r)[kXgPPVals]) {
       const int s = g & 3;
       if (o.a_scale != nullptr) {      // lazy BN of A: the 4 channels of this thread in stage e_it
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(o.a_scale + e_it * kXgBK + kofs));
-        const float4 sh = __ldg(reinterpret_cast<const float4*>(o.a_shift + e_it * kXgBK + kofs));
+        const float4 sc = ld_shared_f4(sbase + kXgPPParams + 4u * (uint32_t)(e_it * kXgBK + kofs));
+        const float4 sh = ld_shared_f4(sbase + kXgPPParams + 512u + 4u * (uint32_t)(e_it * kXgBK + kofs));
 #pragma unroll
         for (int i = 0; i < NI; ++i) xg_bn4(&r[4 * i], sc, sh);
       }
@@ -985,6 +1023,10 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs g
     fence_barrier_init();
   }
   if (warp == kXgPPLoaders + 4) tmem_alloc<512>(tmem_slot);
+  if (o.a_scale != nullptr) {               // lazy BN tables of the A operand (K <= 128)
+    float* tab = reinterpret_cast<float*>(smem + kXgPPParams);
+    for (int i = threadIdx.x; i < o.K; i += kXgPPThreads) { tab[i] = __ldg(o.a_scale + i); tab[128 + i] = __ldg(o.a_shift + i); }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1029,8 +1071,8 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs g
       for (int it = 0; it < 4; ++it) {
         if (it < nst) {
           if (o.a_scale != nullptr) {      // lazy BN of A
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(o.a_scale + it * kXgBK + kofs));
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(o.a_shift + it * kXgBK + kofs));
+            const float4 sc = ld_shared_f4(sbase + kXgPPParams + 4u * (uint32_t)(it * kXgBK + kofs));
+            const float4 sh = ld_shared_f4(sbase + kXgPPParams + 512u + 4u * (uint32_t)(it * kXgBK + kofs));
 #pragma unroll
             for (int i = 0; i < NI; ++i) xg_bn4(&rA[it][4 * i], sc, sh);
           }
