@@ -454,10 +454,10 @@ def run_train(args):
             'achieved': step_flops / (ms * 1e-3) / 1e12, 'peak': pk['bf16_burst'], 'unit': 'TFLOP/s',
             'frac': step_flops / (ms * 1e-3) / 1e12 / pk['bf16_burst'], 'traffic': None,
             'algorithmic_flops_per_step': step_flops,
-            'note': 'fp32-accurate GEMMs issue 6 bf16 tensor-core products per MAC (engine tc); batch-norm statistics come out of '
+            'note': 'GEMMs issue %s bf16 tensor-core products per MAC (engine %s); batch-norm statistics come out of '
                     'the GEMM epilogues and the BN map is applied by the consumers (lazy batch norm); the step is bound by the '
                     'loaders / epilogues of the fp32-operand GEMM kernels and the fp32 activation traffic, not by the tensor pipe '
-                    '(DESIGN.md section 5)',
+                    '(DESIGN.md section 5)' % ({'tc': 6, 'tc2': 3, 'bf16': 1, 'simt': 0}[args.f32_engine], args.f32_engine),
             'peak_source': '%s, burst bf16' % pk['src']}
     nparam = int((g.flat_param if workload == 'cfg4' else g.arena.flat_param).numel())
     line = {'metric': 'frustums_per_sec', 'value': B * world / ms * 1e3, 'unit': 'frustums/s', 'n_gpus': world, 'steps': args.steps,
@@ -469,6 +469,9 @@ def run_train(args):
                        'global_batch': B * world, 'allreduce_bytes': 4 * nparam, 'parallelism': 'dp%d' % world,
                        'precision': {'tc': 'fp32 in HBM; GEMMs on tcgen05 with every operand split into 3 bf16 pieces, 6 partial products, '
                                            'fp32 accumulate (fp32-accurate); BN / loss / Adam kernels fp32 on CUDA cores',
+                                     'tc2': 'fp32 in HBM; GEMMs on tcgen05 with every operand split into 2 bf16 pieces (rounded to nearest, '
+                                            'residual <= 2^-18), 3 partial products, fp32 accumulate: ~1e-5 of sum|a||b| (between TF32 and fp32); '
+                                            'BN / loss / Adam kernels fp32 on CUDA cores',
                                      'simt': 'fp32 CUDA-core kernels throughout',
                                      'bf16': 'fp32 in HBM; GEMM operands rounded to bf16, one tcgen05 pass, fp32 accumulate; '
                                              'BN / loss / Adam kernels fp32'}[args.f32_engine],
@@ -513,8 +516,9 @@ def main():
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: every GPU processes the full cfg3 batch of 8192 frustums (no data-path collective); '
                          'strong: one global batch of 8192 split over the GPUs')
-    ap.add_argument('--f32-engine', default='tc', choices=['tc', 'simt', 'bf16'],
+    ap.add_argument('--f32-engine', default='tc', choices=['tc', 'tc2', 'simt', 'bf16'],
                     help='GEMM engine of the training workloads (cfg4 / cfg5): tc = tcgen05 bf16 x 3 split (fp32-accurate), '
+                         'tc2 = bf16 x 2 split (three products, ~1e-5), '
                          'simt = CUDA-core SGEMM, bf16 = one tcgen05 pass on bf16-rounded operands')
     ap.add_argument('--ref-sample', type=int, default=32, help='frustums per step of the reference (CPU) arm')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'f16x2'],
@@ -755,7 +759,7 @@ def main():
         products = 3 if precision == 'f16x2' else 1
         roofs = {}
         for key, flop_pt, kname, traffic, traffic_alg in (
-                ('seg2', FLOP_SEG2_PT, 'seg_stage2_x2_kernel' if products == 3 else 'seg_stage2_pipe_kernel',
+                ('seg2', FLOP_SEG2_PT, 'seg_stage2_x2_kernel' if products == 3 else 'seg_stage2_pair_kernel',
                  NCU_DRAM_BYTES_FR['seg2'], 262144 + 2048 + 16384),
                 ('seg1', FLOP_SEG1_PT, 'chain_max_x2_kernel<SEG1>' if products == 3 else 'chain_max_kernel<SEG1>',
                  NCU_DRAM_BYTES_FR['seg1'], 49152 + 262144 + 4096)):

@@ -206,7 +206,10 @@ int t3d_gemm_f32(const float* A, long long sam, long long sak, const float* B, l
  *                 partial products accumulated in fp32 (csrc/xgemm.cuh): fp32-level accuracy at 1/6 of the bf16 rate;
  *   0           = CUDA-core SGEMM (csrc/sgemm.cuh);
  *   2           = tcgen05 with the operands rounded once to bf16 (round to nearest) and fp32 accumulation: the bf16 mode
- *                 of the training steps (rel 1e-2 class accuracy), one tensor-core pass instead of six.
+ *                 of the training steps (rel 1e-2 class accuracy), one tensor-core pass instead of six;
+ *   3           = tcgen05 with every operand split into two bf16 pieces, both rounded to nearest (x = h + m + O(2^-18 x)),
+ *                 and the three leading partial products: results within ~1e-5 of the fp32 value relative to
+ *                 sum_k |a||b| (30 x tighter than TF32) at half the tensor-core work of engine 1.
  * The reference computes these layers with tf.nn.conv2d / tf.matmul in fp32 (models/tf_util.py:1308,1489). */
 int t3d_set_f32_engine(int engine);
 /* Same calls with a caller-owned device workspace (16-byte aligned, >= t3d_gemm_ws_bytes(N, K) bytes, private to the stream):

@@ -131,3 +131,39 @@ def test_boxpc_train_step_bf16_engine(built_lib):
         losses = [float(g2.step(feed, masks)['loss']) for _ in range(10)]
     assert np.isfinite(losses).all() and losses[-1] < 0.7 * losses[0], losses
     assert rt.get_f32_engine() == 'tc'
+
+
+def test_boxpc_train_step_tc2_engine(built_lib):
+    """The three-product engine (`tc2`: bf16 x 2 split, operand residual <= 2^-18; `bench.py --f32-engine tc2`) against the fp32
+    oracle on a batch without pooled near-ties: loss within 1e-4 (the north star's TF32 / fp32-mode tolerance) and every
+    weight gradient within relative Frobenius error 5e-3 / cosine 0.99999 (measured: 2.4e-5 .. 3.9e-5 for conv4 and the FC
+    layers, 1.3e-3 .. 1.4e-3 for the three layers whose gradient passes through ReLUs that the 1e-5 operand error flips near
+    zero; cosine >= 0.999999) -- two orders tighter than the one-product bf16 engine, at half the tensor-core work of the
+    default six-product engine."""
+    from oracle import train_boxpc as otb
+    from transferable3d_b200 import runtime as rt
+    B, N = 16, 2048
+    seed = boxpc_seed_without_pool_ties(lambda s: _setup(B, N, seed=s), B, N, conv_last=3)
+    v, feed, masks, FLAGS = _setup(B, N, seed=seed)
+    oloss, ograds, _, _ = otb.loss_and_grads(v, FLAGS, feed, masks, global_step=0)
+    with rt.f32_engine('tc2'):
+        g = tb.BoxPCTrainGraph(v, FLAGS, B, N, 6, DEV)
+        out = g.forward_backward(feed, masks)
+        torch.cuda.synchronize()
+    assert abs(float(out['loss']) - float(oloss)) <= 1e-4 * max(1.0, abs(float(oloss)))
+    report = []
+    for name, og in ograds.items():
+        if not name.endswith('weights'):
+            continue
+        got = g.grad[name[len('box_pc_mask_model/'):]].cpu().double().reshape(-1)
+        ref = og.double().reshape(-1)
+        nr = float(ref.norm())
+        if nr < 1e-9:
+            continue
+        rel = float((got - ref).norm()) / nr
+        cos = float(torch.dot(got, ref)) / (float(got.norm()) * nr + 1e-30)
+        report.append((name.split('/', 1)[1], float('%.3g' % rel), round(cos, 7)))
+    print('tc2 engine, gradient (relative Frobenius error, cosine) per tensor:', report)
+    for name, rel, cos in report:
+        assert rel < 5e-3 and cos > 0.99999, (name, rel, cos)
+    assert rt.get_f32_engine() == 'tc'

@@ -216,3 +216,33 @@ def test_skinny_linear_first_and_last_layers():
         if act == 'relu':
             ref = torch.relu(ref)
         assert float((y.double() - ref).abs().max()) < 2e-5, (K, N, act)
+
+
+@pytest.mark.parametrize('M', [1024, 8192, 32768])      # plain / pre-split one-tile / persistent + A-stationary kernels
+@pytest.mark.parametrize('K,N', [(128, 512), (256, 384), (96, 128)])
+def test_tc2_engine_three_products(M, K, N):
+    """Engine 'tc2' (bf16 x 2 split, three products per MAC): error <= 2e-5 of sum_k |a||b| on forward / dgrad / wgrad
+    (the dropped m.m product and the two operand residuals are each <= 2^-18), i.e. far inside the 1e-4 of the TF32-class
+    mode the north star allows, and at least 20 x tighter than one bf16 product."""
+    rt = _rt()
+    g = torch.Generator(device='cuda').manual_seed(M + K + N)
+    x = torch.randn(M, K, generator=g, device='cuda')
+    w = torch.randn(K, N, generator=g, device='cuda') * 0.1
+    dy = torch.randn(M, N, generator=g, device='cuda')
+    ref = (x.double() @ w.double(), dy.double() @ w.double().t(), x.double().t() @ dy.double())
+    scl = (x.double().abs() @ w.double().abs(), dy.double().abs() @ w.double().abs().t(), x.double().abs().t() @ dy.double().abs())
+    err = {}
+    for eng in ('tc2', 'bf16'):
+        with rt.f32_engine(eng):
+            y = _gemm(x, K, 1, w, N, 1, M, N, K)
+            dx = _gemm(dy, N, 1, w, 1, N, M, K, N)
+            dw = _gemm(x, 1, K, dy, N, 1, K, N, M, splitk=8)
+            y2, _ = rt.linear(x, w, None, 'relu')
+        err[eng] = [float(((o.double() - r).abs() / s).max()) for o, r, s in zip((y, dx, dw), ref, scl)]
+        if eng == 'tc2':
+            assert float(((y2.double() - torch.relu(ref[0])).abs() / scl[0]).max()) < 2e-5
+    for i, name in enumerate(('forward', 'dgrad', 'wgrad')):
+        assert err['tc2'][i] < 2e-5, '%s: %.3g' % (name, err['tc2'][i])
+        # (a wgrad whose output is smaller than one 128 x 64 tile runs on the CUDA cores under every engine)
+        assert err['bf16'][i] < 1e-6 or err['tc2'][i] * 20 < err['bf16'][i], '%s: tc2 %.3g vs bf16 %.3g' % (name, err['tc2'][i], err['bf16'][i])
+    assert rt.get_f32_engine() == 'tc'

@@ -196,6 +196,22 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(cta_mask) : "memory");
 }
+// warp-convergent variants (see "warp-convergent issue" above): the whole MMA warp of the leader CTA runs them converged
+__device__ __forceinline__ void umma_bf16_pair_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_w(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"(cta_mask) : "memory");
+}
 // arrive on the barrier at the same offset in CTA `cta` of the cluster (default semantics, as CUTLASS's ClusterBarrier::arrive:
 // an explicit .release.cluster costs a cluster-scope fence per arrive)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
@@ -258,6 +274,24 @@ __device__ __forceinline__ void split_f16x2_relu(float x0, float x1, uint32_t& h
   const float h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
   asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(h1), "f"(h0));
   asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - h1), "f"(x0 - h0));
+}
+// packed fp32 pairs (Blackwell FADD2 / FFMA2: two lanes of fp32 per instruction, half the issue slots and pipe cycles of the
+// scalar forms in the epilogue loops)
+__device__ __forceinline__ unsigned long long xg_pk2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void xg_upk2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long xg_add2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long xg_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;

@@ -5,7 +5,7 @@
 #include "common.cuh"
 #include "simt_ops.cuh"
 #include "chain_max.cuh"
-#include "seg_stage2_pipe.cuh"
+#include "seg_stage2_pair.cuh"
 #include "chain_x2.cuh"
 #include "seg_stage2_x2.cuh"
 #include "train_ops.cuh"
@@ -50,11 +50,21 @@ extern "C" const char* t3d_error_string(int code) {
   return "t3d: unknown error";
 }
 
-// fp32 GEMM engine for tile-sized problems: 1 = tcgen05 "bf16 x 3" split (xgemm.cuh, fp32-accurate, default),
-// 0 = CUDA-core SGEMM (sgemm.cuh).  Process-wide configuration, not per-call state.
+// fp32 GEMM engine for tile-sized problems: 1 = tcgen05 "bf16 x 3" split (xgemm.cuh: six products per MAC, fp32-accurate,
+// default), 0 = CUDA-core SGEMM (sgemm.cuh), 2 = one bf16 product per MAC (approximate), 3 = "bf16 x 2" split (three
+// products per MAC, operand error <= 2^-18: 30 x tighter than TF32).  Process-wide configuration, not per-call state.
 static int g_f32_engine = 1;
+static inline int xg_parts() { return g_f32_engine == 1 ? 3 : (g_f32_engine == 3 ? 2 : 1); }
+// launches `CALL` (an expression using the template parameter P) for the engine's number of operand pieces
+#define XG_BY_PARTS(CALL)                            \
+  do {                                               \
+    const int parts_ = xg_parts();                   \
+    if (parts_ == 3) { constexpr int P = 3; CALL; }  \
+    else if (parts_ == 2) { constexpr int P = 2; CALL; } \
+    else { constexpr int P = 1; CALL; }              \
+  } while (0)
 extern "C" int t3d_set_f32_engine(int engine) {
-  if (engine < 0 || engine > 2) return T3D_ERR_ARG;
+  if (engine < 0 || engine > 3) return T3D_ERR_ARG;
   g_f32_engine = engine;
   return 0;
 }
@@ -130,12 +140,13 @@ extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ld
   if (xg_fits(M, N, K)) {                    // tensor cores, bf16 x 3 split (xgemm.cuh)
     static int prepared[kMaxDevices] = {0};
     if (int e = once_per_device(prepared, [] {
-          return xg_prepare(xlinear_kernel<3>) | xg_prepare(xlinear_kernel<1>) | xg_prepare(xlinear_pre_kernel<3>) |
-                 xg_prepare(xlinear_pre_kernel<1>) | xg_prepare_pp(xg_as_kernel<3, true>) | xg_prepare_pp(xg_as_kernel<1, true>);
+          return xg_prepare(xlinear_kernel<3>) | xg_prepare(xlinear_kernel<2>) | xg_prepare(xlinear_kernel<1>) |
+                 xg_prepare(xlinear_pre_kernel<3>) | xg_prepare(xlinear_pre_kernel<2>) | xg_prepare(xlinear_pre_kernel<1>) |
+                 xg_prepare_pp(xg_as_kernel<3, true>) | xg_prepare_pp(xg_as_kernel<2, true>) | xg_prepare_pp(xg_as_kernel<1, true>);
         }))
       return e;
     const int ntm = (M + kXgBM - 1) / kXgBM, ntn = (N + kXgBN - 1) / kXgBN;
-    const int parts = g_f32_engine == 1 ? 3 : 1;
+    const int parts = xg_parts();
     XgOperands o{X, ldx, W, ldw, M, N, K, (K + kXgBK - 1) / kXgBK * kXgBK, xg_aligned16(X, ldx) ? 1 : 0, 0, ntn, g_trace, nullptr, 0};
     const dim3 grid((unsigned)ntm * ntn, 1);
     if (xg_pre_ok(M, N, K, ws, ws_bytes)) {
@@ -144,13 +155,10 @@ extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ld
       xg_presplit_kernel<<<dim3(o.nkb, ntn, 4), 256, 0, S(stream)>>>(W, ldw, 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
       if (xg_use_as(K, ntn, true, Y != nullptr)) {
         const int g = ntm < xg_num_sms() ? ntm : xg_num_sms();
-        if (parts == 3) xg_as_kernel<3, true><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(GemmArgs{}, a, o);
-        else xg_as_kernel<1, true><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(GemmArgs{}, a, o);
-      } else if (parts == 3) xlinear_pre_kernel<3><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
-      else xlinear_pre_kernel<1><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+        XG_BY_PARTS((xg_as_kernel<P, true><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(GemmArgs{}, a, o)));
+      } else XG_BY_PARTS((xlinear_pre_kernel<P><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o)));
     } else {
-      if (parts == 3) xlinear_kernel<3><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
-      else xlinear_kernel<1><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+      XG_BY_PARTS((xlinear_kernel<P><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o)));
     }
     T3D_CHECK_LAUNCH();
     return 0;
@@ -597,8 +605,7 @@ extern "C" int t3d_pack_seg2(const float* W6p, const float* W7, const float* W8,
     for (int kb = 0; kb < 2; ++kb)
       for (int nh = 0; nh < 2; ++nh) tab.d[n++] = PackDesc{W7, 256, 512, nb * 128 + kb * 64, nh * 128, 128};
   };
-  // arena order (seg_stage2_pipe.cuh indexes it through kSeg2POrder): c6(0) c6(1) c7(0) c6(2) c6(3) c7(1) c7(2) c7(3) conv8 conv9
-  // (every conv7 chunk pair starts at an even position of the chunk stream = even ring stage)
+  // arena order (seg_stage2_pair.cuh / seg_stage2_x2.cuh index it by chunk id): c6(0) c6(1) c7(0) c6(2) c6(3) c7(1) c7(2) c7(3) conv8 conv9
   c6(0); c6(1); c7(0); c6(2); c6(3); c7(1); c7(2); c7(3);
   for (int kb = 0; kb < 4; ++kb) tab.d[n++] = PackDesc{W8, 128, 256, kb * 64, 0, 128};
   for (int kb = 0; kb < 2; ++kb) tab.d[n++] = PackDesc{W9, 128, 128, kb * 64, 0, 128};
@@ -623,7 +630,7 @@ extern "C" int t3d_seg_stage2_bf16(const void* point_feat, const float* gbias, c
     return T3D_ERR_ALIGN;
   static int prepared[kMaxDevices] = {0};
   if (int e = once_per_device(prepared, [] {
-        return (int)cudaFuncSetAttribute(seg_stage2_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2PSmem::TOTAL + 1024);
+        return (int)cudaFuncSetAttribute(seg_stage2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Seg2QSmem::TOTAL + 1024);
       }))
     return e;
   const int sms = xg_num_sms();
@@ -632,7 +639,7 @@ extern "C" int t3d_seg_stage2_bf16(const void* point_feat, const float* gbias, c
   int grid = sms - (sms % kClusterSize);
   const int need = ((nt + kClusterSize - 1) / kClusterSize) * kClusterSize;
   if (need < grid) grid = need;
-  seg_stage2_pipe_kernel<<<grid, kSeg2PThreads, Seg2PSmem::TOTAL + 1024, S(stream)>>>(a);
+  seg_stage2_pair_kernel<<<grid, kSeg2PThreads, Seg2QSmem::TOTAL + 1024, S(stream)>>>(a);
   T3D_CHECK_LAUNCH();
   return 0;
 }
@@ -884,11 +891,13 @@ static int gemm_f32_impl(const float* A, long long sam, long long sak, const flo
     if (int e = once_per_device(prepared, [] {
           return xg_prepare(xgemm_kernel<true, true, 3>) | xg_prepare(xgemm_kernel<true, false, 3>) |
                  xg_prepare(xgemm_kernel<false, true, 3>) | xg_prepare(xgemm_kernel<false, false, 3>) |
+                 xg_prepare(xgemm_kernel<true, true, 2>) | xg_prepare(xgemm_kernel<true, false, 2>) |
+                 xg_prepare(xgemm_kernel<false, true, 2>) | xg_prepare(xgemm_kernel<false, false, 2>) |
                  xg_prepare(xgemm_kernel<true, true, 1>) | xg_prepare(xgemm_kernel<true, false, 1>) |
                  xg_prepare(xgemm_kernel<false, true, 1>) | xg_prepare(xgemm_kernel<false, false, 1>) |
-                 xg_prepare(xgemm_pre_kernel<3>) | xg_prepare(xgemm_pre_kernel<1>) |
-                 xg_prepare_pp(xg_as_kernel<3, false>) | xg_prepare_pp(xg_as_kernel<1, false>) |
-                 xg_prepare_pp(xg_pp_kernel<3, false>) | xg_prepare_pp(xg_pp_kernel<1, false>);
+                 xg_prepare(xgemm_pre_kernel<3>) | xg_prepare(xgemm_pre_kernel<2>) | xg_prepare(xgemm_pre_kernel<1>) |
+                 xg_prepare_pp(xg_as_kernel<3, false>) | xg_prepare_pp(xg_as_kernel<2, false>) | xg_prepare_pp(xg_as_kernel<1, false>) |
+                 xg_prepare_pp(xg_pp_kernel<3, false>) | xg_prepare_pp(xg_pp_kernel<2, false>) | xg_prepare_pp(xg_pp_kernel<1, false>);
         }))
       return e;
     // The tensor core adds each 16-deep partial sum into the fp32 accumulator with truncation, a bias of ~0.5 ulp per
@@ -918,18 +927,14 @@ static int gemm_f32_impl(const float* A, long long sam, long long sak, const flo
     if (pre) {     // forward / dgrad: pre-split B
       o.bpre = reinterpret_cast<const uint8_t*>(ws);
       o.nkb = (K + 63) / 64;
-      const int parts = g_f32_engine == 1 ? 3 : 1;
-      xg_presplit_kernel<<<dim3(o.nkb, ntn, 4), 256, 0, S(stream)>>>(B, ldb, bk ? 1 : 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
+      xg_presplit_kernel<<<dim3(o.nkb, ntn, 4), 256, 0, S(stream)>>>(B, ldb, bk ? 1 : 0, N, K, xg_parts(), reinterpret_cast<uint8_t*>(ws));
       if (xg_use_as(K, ntn)) {
         const int g = ntm < xg_num_sms() ? ntm : xg_num_sms();
-        if (parts == 3) xg_as_kernel<3, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o);
-        else xg_as_kernel<1, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o);
+        XG_BY_PARTS((xg_as_kernel<P, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o)));
       } else if (xg_use_pp(K)) {
         const int g = ntm * ntn < xg_num_sms() ? ntm * ntn : xg_num_sms();
-        if (parts == 3) xg_pp_kernel<3, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o);
-        else xg_pp_kernel<1, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o);
-      } else if (parts == 3) xgemm_pre_kernel<3><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
-      else xgemm_pre_kernel<1><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+        XG_BY_PARTS((xg_pp_kernel<P, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o)));
+      } else XG_BY_PARTS((xgemm_pre_kernel<P><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o)));
       T3D_CHECK_LAUNCH();
       return 0;
     }
@@ -940,8 +945,7 @@ static int gemm_f32_impl(const float* A, long long sam, long long sak, const flo
     else if (bk) xgemm_kernel<false, true, P><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);        \
     else xgemm_kernel<false, false, P><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);               \
   } while (0)
-    if (g_f32_engine == 1) XG_LAUNCH(3);
-    else XG_LAUNCH(1);
+    XG_BY_PARTS(XG_LAUNCH(P));
 #undef XG_LAUNCH
     T3D_CHECK_LAUNCH();
     return 0;

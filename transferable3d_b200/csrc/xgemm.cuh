@@ -138,6 +138,31 @@ __device__ __forceinline__ uint32_t xg_pack_rn(float lo, float hi) {      // rou
   return r;
 }
 
+// PARTS images of 4 consecutive fp32 values as packed bf16 pairs: w[p][0] = (x0, x1), w[p][1] = (x2, x3) of image p.
+//   PARTS 1: round to nearest (one product per MAC, the approximate `bf16` engine)
+//   PARTS 2: x = h + m + O(2^-18 x), both pieces rounded to nearest (three products per MAC, the `tc2` engine)
+//   PARTS 3: x = h + m + l exactly, by truncation (six products per MAC, the fp32-accurate `tc` engine)
+template <int PARTS>
+__device__ __forceinline__ void xg_split4(const float* x, uint32_t (&w)[3][2]) {
+  if (PARTS == 1) {
+    w[0][0] = xg_pack_rn(x[0], x[1]); w[0][1] = xg_pack_rn(x[2], x[3]);
+  } else if (PARTS == 2) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t h = xg_pack_rn(x[2 * q], x[2 * q + 1]);
+      w[0][q] = h;
+      w[1][q] = xg_pack_rn(x[2 * q] - __uint_as_float(h << 16), x[2 * q + 1] - __uint_as_float(h & 0xffff0000u));
+    }
+  } else {
+    uint32_t h[4], m[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) xg_split(x[e], h[e], m[e], l[e]);
+    w[0][0] = xg_pack(h[0], h[1]); w[0][1] = xg_pack(h[2], h[3]);
+    w[1][0] = xg_pack(m[0], m[1]); w[1][1] = xg_pack(m[2], m[3]);
+    w[2][0] = xg_pack(l[0], l[1]); w[2][1] = xg_pack(l[2], l[3]);
+  }
+}
+
 template <bool UNIT_K, int PARTS>
 __device__ __forceinline__ void xg_split_store(uint32_t img, int s, int w, int lane, const float (&r)[32]) {
   if (UNIT_K) {
@@ -145,33 +170,21 @@ __device__ __forceinline__ void xg_split_store(uint32_t img, int s, int w, int l
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint32_t addr = img + sw128_offset((uint32_t)xg_row_unit_k(w, i, lane), (uint32_t)(4 * s + (c >> 1))) + (uint32_t)(c & 1) * 8u;
-      if (PARTS == 1) {
-        st_shared_v2(addr, xg_pack_rn(r[4 * i], r[4 * i + 1]), xg_pack_rn(r[4 * i + 2], r[4 * i + 3]));
-      } else {
-        uint32_t h[4], m[4], l[4];
+      uint32_t w[3][2];
+      xg_split4<PARTS>(&r[4 * i], w);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) xg_split(r[4 * i + e], h[e], m[e], l[e]);
-        st_shared_v2(addr, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]));
-        st_shared_v2(addr + kXgImage, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]));
-        st_shared_v2(addr + 2 * kXgImage, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]));
-      }
+      for (int p = 0; p < PARTS; ++p) st_shared_v2(addr + (uint32_t)p * kXgImage, w[p][0], w[p][1]);
     }
   } else {
     const uint32_t row = (uint32_t)(w * 32 + lane);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t addr = img + sw128_offset(row, (uint32_t)(4 * s + j));
-      if (PARTS == 1) {
-        st_shared_v4(addr, xg_pack_rn(r[8 * j], r[8 * j + 1]), xg_pack_rn(r[8 * j + 2], r[8 * j + 3]),
-                     xg_pack_rn(r[8 * j + 4], r[8 * j + 5]), xg_pack_rn(r[8 * j + 6], r[8 * j + 7]));
-      } else {
-        uint32_t h[8], m[8], l[8];
+      uint32_t w0[3][2], w1[3][2];
+      xg_split4<PARTS>(&r[8 * j], w0);
+      xg_split4<PARTS>(&r[8 * j + 4], w1);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) xg_split(r[8 * j + e], h[e], m[e], l[e]);
-        st_shared_v4(addr, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]), xg_pack(h[4], h[5]), xg_pack(h[6], h[7]));
-        st_shared_v4(addr + kXgImage, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]), xg_pack(m[4], m[5]), xg_pack(m[6], m[7]));
-        st_shared_v4(addr + 2 * kXgImage, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]), xg_pack(l[4], l[5]), xg_pack(l[6], l[7]));
-      }
+      for (int p = 0; p < PARTS; ++p) st_shared_v4(addr + (uint32_t)p * kXgImage, w0[p][0], w0[p][1], w1[p][0], w1[p][1]);
     }
   }
 }
@@ -266,16 +279,12 @@ __global__ void __launch_bounds__(256) xg_presplit_kernel(const float* __restric
     v[e] = (n < N && k < K) ? (unit_k ? B[(long long)n * ldb + k] : B[(long long)k * ldb + n]) : 0.0f;
   }
   const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)kg);
-  if (parts == 1) {
-    *reinterpret_cast<uint4*>(dst + off) = make_uint4(xg_pack_rn(v[0], v[1]), xg_pack_rn(v[2], v[3]), xg_pack_rn(v[4], v[5]), xg_pack_rn(v[6], v[7]));
-  } else {
-    uint32_t h[8], m[8], l[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) xg_split(v[e], h[e], m[e], l[e]);
-    *reinterpret_cast<uint4*>(dst + off) = make_uint4(xg_pack(h[0], h[1]), xg_pack(h[2], h[3]), xg_pack(h[4], h[5]), xg_pack(h[6], h[7]));
-    *reinterpret_cast<uint4*>(dst + kXgImage + off) = make_uint4(xg_pack(m[0], m[1]), xg_pack(m[2], m[3]), xg_pack(m[4], m[5]), xg_pack(m[6], m[7]));
-    *reinterpret_cast<uint4*>(dst + 2 * kXgImage + off) = make_uint4(xg_pack(l[0], l[1]), xg_pack(l[2], l[3]), xg_pack(l[4], l[5]), xg_pack(l[6], l[7]));
-  }
+  uint32_t w0[3][2], w1[3][2];
+  if (parts == 1) { xg_split4<1>(v, w0); xg_split4<1>(v + 4, w1); }
+  else if (parts == 2) { xg_split4<2>(v, w0); xg_split4<2>(v + 4, w1); }
+  else { xg_split4<3>(v, w0); xg_split4<3>(v + 4, w1); }
+  for (int p = 0; p < parts; ++p)
+    *reinterpret_cast<uint4*>(dst + (size_t)p * kXgImage + off) = make_uint4(w0[p][0], w0[p][1], w1[p][0], w1[p][1]);
 }
 
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {      // contiguous range -> L2 (16-byte granularity)
@@ -346,16 +355,10 @@ __device__ __forceinline__ void xg_loader_pre(const float* __restrict__ P, long 
 #pragma unroll
     for (int i = 0; i < ((XG_DBG & 2) ? 0 : 4); ++i) {
       const uint32_t addr = a_img + sw128_offset((uint32_t)rowof(i), (uint32_t)(4 * s + (c >> 1))) + (uint32_t)(c & 1) * 8u;
-      if (PARTS == 1) {
-        st_shared_v2(addr, xg_pack_rn(r[4 * i], r[4 * i + 1]), xg_pack_rn(r[4 * i + 2], r[4 * i + 3]));
-      } else {
-        uint32_t h[4], m[4], l[4];
+      uint32_t w[3][2];
+      xg_split4<PARTS>(&r[4 * i], w);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) xg_split(r[4 * i + e], h[e], m[e], l[e]);
-        st_shared_v2(addr, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]));
-        st_shared_v2(addr + kXgImage, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]));
-        st_shared_v2(addr + 2 * kXgImage, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]));
-      }
+      for (int p = 0; p < PARTS; ++p) st_shared_v2(addr + (uint32_t)p * kXgImage, w[p][0], w[p][1]);
     }
     if (XG_DBG & 2) {      // keep the loads alive without the stores
       uint32_t x = 0;
@@ -382,6 +385,23 @@ __device__ __forceinline__ void xg_loader_pre(const float* __restrict__ P, long 
       }
     }
   }
+}
+
+// the partial products of one K = 16 step (warp-convergent): small accumulator first, the leading product last
+template <int PARTS>
+__device__ __forceinline__ void xg_issue(uint32_t d_main, uint32_t d_small, uint64_t a1, uint64_t a2, uint64_t a3, uint64_t b1, uint64_t b2,
+                                         uint64_t b3, uint32_t idesc, uint32_t accum) {
+  if (PARTS == 3) {
+    umma_bf16_w(d_small, a3, b1, idesc, accum);
+    umma_bf16_w(d_small, a1, b3, idesc, 1);
+    umma_bf16_w(d_small, a2, b2, idesc, 1);
+    umma_bf16_w(d_small, a2, b1, idesc, 1);
+    umma_bf16_w(d_small, a1, b2, idesc, 1);
+  } else if (PARTS == 2) {
+    umma_bf16_w(d_small, a2, b1, idesc, accum);
+    umma_bf16_w(d_small, a1, b2, idesc, 1);
+  }
+  umma_bf16_w(d_main, a1, b1, idesc, accum);
 }
 
 struct XgTile {
@@ -457,14 +477,7 @@ __device__ __forceinline__ void xg_mainloop(const XgOperands& o, uint8_t* smem_r
                        b3 = make_sdesc_k128(b_img + 2 * kXgImage + off);
         const uint32_t first = (it | ks) != 0;
         if (XG_DBG & 4) continue;
-        if (PARTS == 3) {
-          umma_bf16_w(d_small, a3, b1, idesc, first);
-          umma_bf16_w(d_small, a1, b3, idesc, 1);
-          umma_bf16_w(d_small, a2, b2, idesc, 1);
-          umma_bf16_w(d_small, a2, b1, idesc, 1);
-          umma_bf16_w(d_small, a1, b2, idesc, 1);
-        }
-        umma_bf16_w(d_main, a1, b1, idesc, first);
+        xg_issue<PARTS>(d_main, d_small, a1, a2, a3, b1, b2, b3, idesc, first);
       }
       umma_commit_w(empty(s));
       tr.mark(0x20);
@@ -479,7 +492,7 @@ __device__ __forceinline__ void xg_acc32(const XgTile& t, int c0, float (&v)[32]
   const uint32_t taddr = t.tmem_base + ((uint32_t)((t.warp & 3) * 32) << 16) + (uint32_t)c0;
   uint32_t va[32];
   tmem_ld32(taddr, va);
-  if (PARTS == 3) {
+  if (PARTS >= 2) {
     uint32_t vb[32];
     tmem_ld32(taddr + 128, vb);
     tmem_ld_wait();
@@ -515,22 +528,6 @@ constexpr uint32_t kXgPatchRow = 144, kXgPatchBytes = 32 * kXgPatchRow;
 // epilogue warps are the limit of the K <= 128 kernels, and the scalar version of this block cost them 30 %), two shuffles
 // fold the 4 row groups.  MODE 2: additionally the column max / min of the chunk's valid rows as ordered keys, merged into
 // pool_max / pool_min + pool_off (the group's row of the [groups, N] key arrays); C == null skips the store.
-__device__ __forceinline__ unsigned long long xg_pk2(float a, float b) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void xg_upk2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ unsigned long long xg_add2(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ unsigned long long xg_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
 template <bool ATOMIC, int MODE = 0>
 __device__ __forceinline__ void xg_store_chunk(const XgTile& t, float* __restrict__ C, long long ldc, int M, int N, int row0, int col0,
                                                const float (&v)[32], float* __restrict__ st_sum = nullptr,
@@ -891,16 +888,10 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs g
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const uint32_t off = sw128_offset((uint32_t)rowof(i), (uint32_t)(4 * (s & 1) + (c >> 1))) + (uint32_t)(c & 1) * 8u;
-        if (PARTS == 1) {
-          st_shared_v2(xg_pp_block(a_img, 0, s) + off, xg_pack_rn(r[4 * i], r[4 * i + 1]), xg_pack_rn(r[4 * i + 2], r[4 * i + 3]));
-        } else {
-          uint32_t h[4], m[4], l[4];
+        uint32_t w[3][2];
+        xg_split4<PARTS>(&r[4 * i], w);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) xg_split(r[4 * i + e], h[e], m[e], l[e]);
-          st_shared_v2(xg_pp_block(a_img, 0, s) + off, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]));
-          st_shared_v2(xg_pp_block(a_img, 1, s) + off, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]));
-          st_shared_v2(xg_pp_block(a_img, 2, s) + off, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]));
-        }
+        for (int p = 0; p < PARTS; ++p) st_shared_v2(xg_pp_block(a_img, p, s) + off, w[p][0], w[p][1]);
       }
       tr.mark(0x28);
       asm volatile("cp.async.wait_group %0;" ::"n"(kXgPPBAhead) : "memory");      // all but the newest groups: this stage's B has landed
@@ -954,14 +945,7 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs g
           const uint64_t b1 = make_sdesc_k128(xg_pp_block(b_img, 0, s) + off), b2 = make_sdesc_k128(xg_pp_block(b_img, 1, s) + off),
                          b3 = make_sdesc_k128(xg_pp_block(b_img, 2, s) + off);
           const uint32_t first = (it | ks) != 0;
-          if (PARTS == 3) {
-            umma_bf16_w(d_small, a3, b1, idesc, first);
-            umma_bf16_w(d_small, a1, b3, idesc, 1);
-            umma_bf16_w(d_small, a2, b2, idesc, 1);
-            umma_bf16_w(d_small, a2, b1, idesc, 1);
-            umma_bf16_w(d_small, a1, b2, idesc, 1);
-          }
-          umma_bf16_w(d_main, a1, b1, idesc, first);
+          xg_issue<PARTS>(d_main, d_small, a1, a2, a3, b1, b2, b3, idesc, first);
         }
         umma_commit_w(empty(s));
         tr.mark(0x20);
@@ -1080,16 +1064,10 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs g
           for (int i = 0; i < NI; ++i) {
             const uint32_t off = sw128_offset((uint32_t)rowof(i), (uint32_t)(4 * (it & 1) + (c >> 1))) + (uint32_t)(c & 1) * 8u;
             const float* r = &rA[it][4 * i];
-            if (PARTS == 1) {
-              st_shared_v2(xg_pp_block(a_img, 0, it) + off, xg_pack_rn(r[0], r[1]), xg_pack_rn(r[2], r[3]));
-            } else {
-              uint32_t h[4], m[4], l[4];
+            uint32_t w[3][2];
+            xg_split4<PARTS>(r, w);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) xg_split(r[e], h[e], m[e], l[e]);
-              st_shared_v2(xg_pp_block(a_img, 0, it) + off, xg_pack(h[0], h[1]), xg_pack(h[2], h[3]));
-              st_shared_v2(xg_pp_block(a_img, 1, it) + off, xg_pack(m[0], m[1]), xg_pack(m[2], m[3]));
-              st_shared_v2(xg_pp_block(a_img, 2, it) + off, xg_pack(l[0], l[1]), xg_pack(l[2], l[3]));
-            }
+            for (int p = 0; p < PARTS; ++p) st_shared_v2(xg_pp_block(a_img, p, it) + off, w[p][0], w[p][1]);
           }
         }
       }
@@ -1161,14 +1139,7 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs g
             const uint64_t b1 = make_sdesc_k128(xg_pp_block(b_img, 0, s) + offb), b2 = make_sdesc_k128(xg_pp_block(b_img, 1, s) + offb),
                            b3 = make_sdesc_k128(xg_pp_block(b_img, 2, s) + offb);
             const uint32_t accum = (it | ks) != 0;
-            if (PARTS == 3) {
-              umma_bf16_w(d_small, a3, b1, idesc, accum);
-              umma_bf16_w(d_small, a1, b3, idesc, 1);
-              umma_bf16_w(d_small, a2, b2, idesc, 1);
-              umma_bf16_w(d_small, a2, b1, idesc, 1);
-              umma_bf16_w(d_small, a1, b2, idesc, 1);
-            }
-            umma_bf16_w(d_main, a1, b1, idesc, accum);
+            xg_issue<PARTS>(d_main, d_small, a1, a2, a3, b1, b2, b3, idesc, accum);
           }
           umma_commit_w(empty(s));
         }

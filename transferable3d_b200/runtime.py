@@ -72,14 +72,15 @@ def default_device():
 
 def set_f32_engine(engine):
     """Engine of the fp32 GEMMs (fp32-mode layers, training steps): 'tc' = tcgen05 bf16 x 3 split (fp32-accurate,
-    default), 'simt' = CUDA-core SGEMM, 'bf16' = tcgen05 with operands rounded to bf16 (one pass, fp32 accumulate).
+    default), 'tc2' = tcgen05 bf16 x 2 split (three products per MAC, operand error <= 2^-18: between TF32 and fp32),
+    'simt' = CUDA-core SGEMM, 'bf16' = tcgen05 with operands rounded to bf16 (one pass, fp32 accumulate).
     See include/t3d_b200.h: t3d_set_f32_engine."""
     if engine not in F32_ENGINES:
         raise ValueError(engine)
     _lib.check(_lib.load().t3d_set_f32_engine(F32_ENGINES[engine]))
 
 
-F32_ENGINES = {'simt': 0, 'tc': 1, 'bf16': 2}
+F32_ENGINES = {'simt': 0, 'tc': 1, 'bf16': 2, 'tc2': 3}
 
 
 def get_f32_engine():

@@ -2,7 +2,7 @@
 end_points keys), evaluated on the B200.
 
 bf16 / f16x2 modes: every per-point conv stack + max-pool is ONE fused tcgen05 kernel (csrc/chain_max.cuh,
-csrc/seg_stage2_pipe.cuh; split-precision twins csrc/chain_x2.cuh, csrc/seg_stage2_x2.cuh); the masked stacks (tnet,
+csrc/seg_stage2_pair.cuh; split-precision twins csrc/chain_x2.cuh, csrc/seg_stage2_x2.cuh); the masked stacks (tnet,
 box_est) run on the compacted masked-in points, which equals the reference's max(net*mask) because post-ReLU
 activations are >= 0.
 fp32 mode: layer-by-layer fp32 GEMMs (t3d_linear_f32) with the literal mask multiply.
