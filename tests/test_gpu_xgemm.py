@@ -246,3 +246,23 @@ def test_tc2_engine_three_products(M, K, N):
         # (a wgrad whose output is smaller than one 128 x 64 tile runs on the CUDA cores under every engine)
         assert err['bf16'][i] < 1e-6 or err['tc2'][i] * 20 < err['bf16'][i], '%s: tc2 %.3g vs bf16 %.3g' % (name, err['tc2'][i], err['bf16'][i])
     assert rt.get_f32_engine() == 'tc'
+
+
+@pytest.mark.parametrize('a_unit_k,b_unit_k', [(True, False), (True, True), (False, False), (False, True)])
+@pytest.mark.parametrize('M,N,K', [(256, 256, 64), (300, 515, 70), (1000, 333, 200), (4500, 512, 256), (512, 1024, 4100)])
+def test_tc2_pair_kernel_layouts(M, N, K, a_unit_k, b_unit_k):
+    """The CTA-pair kernel (256 x 256 tiles, cta_group::2) behind the tc2 / bf16 engines, every operand layout, ragged M / N / K,
+    split-K (K > 2048 is chunked): error <= 3e-5 of sum_k |a||b| (two-piece operands + one truncating accumulator)."""
+    rt = _rt()
+    a, b, A, sam, sak, Bm, sbk, sbn = _operands(M, N, K, a_unit_k, b_unit_k, seed=M + N + K)
+    bias = torch.randn(N, device='cuda')
+    with rt.f32_engine('tc2'):
+        C = _gemm(A, sam, sak, Bm, sbk, sbn, M, N, K)
+        Cb = _gemm(A, sam, sak, Bm, sbk, sbn, M, N, K, bias=bias)
+        Cs = _gemm(A, sam, sak, Bm, sbk, sbn, M, N, K, splitk=3)
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double()
+    scale = a.double().abs() @ b.double().abs()
+    for name, out in (('plain', C), ('bias', Cb - bias), ('splitk', Cs)):
+        err = float(((out.double() - ref).abs() / scale).max())
+        assert err < 3e-5, (name, err)

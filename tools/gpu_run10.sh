@@ -1,5 +1,4 @@
-mkdir -p gpurun_out/r02r
-for e in tc2; do
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02r/launches_cfg4_$e.csv python bench.py --workload cfg4 --steps 2 --warmup 3 --no-cpu-baseline --f32-engine $e > gpurun_out/r02r/ncu_$e.log 2>&1
-done
-tail -2 gpurun_out/r02r/ncu_tc2.log | cut -c 1-300
+# ncu launch list of one training workload: usage gpu_run10.sh <outdir> <workload> <engine>
+mkdir -p gpurun_out/$1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/$1/launches_$2_$3.csv python bench.py --workload $2 --steps 2 --warmup 3 --no-cpu-baseline --f32-engine $3 > gpurun_out/$1/ncu_$2_$3.log 2>&1
+tail -1 gpurun_out/$1/ncu_$2_$3.log | cut -c 1-200

@@ -32,11 +32,11 @@ def dump(buf, title):
 def main():
     M = 524288
     buf = torch.zeros(4 * SLOTS, dtype=torch.int64, device='cuda')
-    for K, N in ((128, 128), (256, 512)):
+    for K, N in ((256, 512),) if os.environ.get('ENGINES') else ((128, 128), (256, 512)):
         x = torch.randn(M, K, device='cuda')
         w = torch.randn(K, N, device='cuda') * 0.1
         dy = torch.randn(M, N, device='cuda')
-        for eng in ('tc', 'bf16'):
+        for eng in (os.environ.get('ENGINES', 'tc,bf16').split(',')):
             with rt.f32_engine(eng):
                 gemm(x, K, 1, w, N, 1, M, N, K)
                 torch.cuda.synchronize()
@@ -49,6 +49,10 @@ def main():
                 gemm(dy, N, 1, w, 1, N, M, K, N)
                 torch.cuda.synchronize()
                 dump(buf, 'dgrad %d<-%d engine %s' % (K, N, eng))
+                buf.zero_()
+                gemm(x, 1, K, dy, N, 1, K, N, M, splitk=1)
+                torch.cuda.synchronize()
+                dump(buf, 'wgrad [%d x %d] engine %s' % (K, N, eng))
                 _lib.call('t3d_set_trace_buffer', None)
 
 

@@ -915,7 +915,37 @@ static int gemm_f32_impl(const float* A, long long sam, long long sak, const flo
     XgOperands o{A, lda, B, ldb, M, N, K, kchunk, (ak && xg_aligned16(A, lda)) ? 1 : 0, (bk && xg_aligned16(B, ldb)) ? 1 : 0, ntn, g_trace, nullptr, 0,
                  x.a_scale, x.a_shift};
     const dim3 grid((unsigned)ntm * ntn, nz);
-    const bool pre = ak && nz == 1 && sk == 1 && xg_pre_ok(M, N, K, ws, ws_bytes);
+    // CTA-pair kernel (256 x 256 tiles, xgemm.cuh) for the engines with at most two operand pieces: every shape with at
+    // least 256 rows and columns except the K <= 128 forward / dgrad layers, which stay on the persistent kernels
+    const bool pair = xg_parts() <= 2 && M >= 256 && N >= 256 && !(ak && nz == 1 && sk == 1 && K <= 128 && xg_pre_ok(M, N, K, ws, ws_bytes));
+    const bool pre = !pair && ak && nz == 1 && sk == 1 && xg_pre_ok(M, N, K, ws, ws_bytes);
+    if (pair) {
+      if (x.a_scale && K % kXgBK != 0) return T3D_ERR_SHAPE;
+      if (x.st_sum && sk != 1) return T3D_ERR_SHAPE;
+      static int prepared_pair[kMaxDevices] = {0};
+      if (int e = once_per_device(prepared_pair, [] {
+            return xg_prepare(xgemm_pair_kernel<true, true, 2>) | xg_prepare(xgemm_pair_kernel<true, false, 2>) |
+                   xg_prepare(xgemm_pair_kernel<false, true, 2>) | xg_prepare(xgemm_pair_kernel<false, false, 2>) |
+                   xg_prepare(xgemm_pair_kernel<true, true, 1>) | xg_prepare(xgemm_pair_kernel<true, false, 1>) |
+                   xg_prepare(xgemm_pair_kernel<false, true, 1>) | xg_prepare(xgemm_pair_kernel<false, false, 1>);
+          }))
+        return e;
+      const int ntm2 = (M + 255) / 256, ntn2 = (N + 255) / 256;
+      o.ntn = ntn2;
+      const dim3 pgrid((unsigned)ntm2 * ntn2 * 2, nz);
+#define XG_LAUNCH_PAIR(P)                                                                                     \
+  do {                                                                                                        \
+    if (ak && bk) xgemm_pair_kernel<true, true, P><<<pgrid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);      \
+    else if (ak) xgemm_pair_kernel<true, false, P><<<pgrid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);      \
+    else if (bk) xgemm_pair_kernel<false, true, P><<<pgrid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);      \
+    else xgemm_pair_kernel<false, false, P><<<pgrid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);             \
+  } while (0)
+      if (xg_parts() == 2) XG_LAUNCH_PAIR(2);
+      else XG_LAUNCH_PAIR(1);
+#undef XG_LAUNCH_PAIR
+      T3D_CHECK_LAUNCH();
+      return 0;
+    }
     if (x.any()) {
       // lazy BN of a k-contiguous A lives in the pre-split-B loaders (128-bit parameter loads: K % 32 == 0, aligned arrays);
       // of a row-contiguous A (wgrad) in the generic loader.  Statistics need the whole K range in one CTA.

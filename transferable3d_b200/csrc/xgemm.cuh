@@ -208,7 +208,8 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
 template <bool UNIT_K, int PARTS>
 __device__ __forceinline__ void xg_loader(const float* __restrict__ P, long long ld, int row0, int nrows, int kbeg, int kend, bool vec,
                                           uint32_t img, int w, int lane, int nst, uint32_t full0, uint32_t empty0, XgTracer& tr,
-                                          const float* __restrict__ tsc = nullptr, const float* __restrict__ tsh = nullptr) {
+                                          const float* __restrict__ tsc = nullptr, const float* __restrict__ tsh = nullptr,
+                                          bool remote_full = false) {      // remote_full: the full barriers live in cluster rank 0 (CTA-pair kernel)
   const int row = row0 + (UNIT_K ? xg_row_unit_k(w, 0, lane) : w * 32 + lane);      // first (or only) row of this thread
   const int kofs = UNIT_K ? 4 * (lane & 7) : 0;
   const float* p = UNIT_K ? P + (long long)row * ld + kbeg + kofs : P + (long long)kbeg * ld + row;
@@ -229,12 +230,19 @@ __device__ __forceinline__ void xg_loader(const float* __restrict__ P, long long
 #pragma unroll
       for (int kk = 0; kk < 32; ++kk) r[kk] = (row < nrows && k0 + kk < kend) ? fmaxf(fmaf(bsc, r[kk], bsh), 0.0f) : 0.0f;
     }
+    if (UNIT_K && tsc != nullptr) {      // lazy BN of a k-contiguous operand (forward): this thread's 4 channels of the stage (K % 32 == 0)
+      const int k = kbeg + it * kXgBK + kofs;
+      const float4 sc = make_float4(__ldg(tsc + k), __ldg(tsc + k + 1), __ldg(tsc + k + 2), __ldg(tsc + k + 3));
+      const float4 sh = make_float4(__ldg(tsh + k), __ldg(tsh + k + 1), __ldg(tsh + k + 2), __ldg(tsh + k + 3));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xg_bn4(&r[4 * i], sc, sh);
+    }
     mbar_wait_backoff(empty0 + 8u * s, ((it >> 1) & 1) ^ 1);
     tr.mark(0x20);
     xg_split_store<UNIT_K, PARTS>(img, s, w, lane, r);
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) mbar_arrive(full0 + 8u * s);
+    if (lane == 0) { if (remote_full) mbar_arrive_remote(full0 + 8u * s, 0); else mbar_arrive(full0 + 8u * s); }
     tr.mark(0x30);
   };
   // kXgSets register sets: stage `it` lives in set it % kXgSets; kXgSets - 1 stages are in flight while one is consumed
@@ -622,7 +630,7 @@ __device__ __forceinline__ void xg_epilogue_gemm(const GemmArgs& a, const XgTile
     const int row0 = t.m0 + (t.warp & 3) * 32;
 #pragma unroll 1
     for (int ch = 0; ch < nchunks; ++ch) {
-      const int c0 = (nchunks == 2 ? (t.warp >> 2) * 64 : 0) + ch * 32;
+      const int c0 = (t.warp >> 2) * (32 * nchunks) + ch * 32;      // warps 4-7 of the one-tile kernels: the second column half
       float4 sfv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a.st_sum != nullptr && a.st_shift != nullptr) {     // this lane's 4 statistic shifts, in flight during the TMEM load
         const int gs = t.n0 + c0 + (t.lane & 7) * 4;
@@ -665,6 +673,98 @@ __global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xgemm_pre_kernel(con
   xg_mainloop<true, false, PARTS, true>(o, xg_smem, t);
   xg_epilogue_gemm<PARTS>(a, t, 2, blockIdx.y == 0);
   xg_finish(t);
+}
+
+// ---- CTA-pair variant: one 256 x 256 output tile per cluster of two CTAs (tcgen05 cta_group::2) -----------------------------
+// For the two-piece and one-piece engines (PARTS <= 2).  CTA r of the pair loads, splits and keeps in ITS shared memory the
+// A rows [m0 + 128 r, +128) and the B columns [n0 + 128 r, +128) of every stage; the leader's MMA warp issues M = 256 x N = 256
+// instructions that read both shared memories and fill a [128 x 256] fp32 accumulator in each CTA's TMEM.  Against the
+// 128 x 128 tile of the kernels above every operand value loaded and split feeds twice the tensor-core work (these kernels
+// are bound by their loaders and by the L2 -> SM operand traffic, not by the tensor pipe: DESIGN.md section 4b), and B needs
+// no pre-split pass.  One accumulator (the products of the low pieces are summed into the main one): 256 TMEM columns per
+// CTA, so two clusters share an SM pair and one's epilogue runs under the other's main loop.  The loaders of the peer arrive
+// remotely on the leader's full barriers; the leader's commits are multicast to both CTAs.
+template <bool A_UNIT_K, bool B_UNIT_K, int PARTS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXgThreads, kXgMinBlocks) xgemm_pair_kernel(const GemmArgs a, const XgOperands o) {
+  static_assert(PARTS <= 2, "xgemm_pair: one accumulator");
+  extern __shared__ uint8_t xg_smem[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)xg_smem + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t bar0 = sbase + kXgBars;
+  auto full = [&](int s) { return bar0 + 8u * s; };
+  auto empty = [&](int s) { return bar0 + 8u * (2 + s); };
+  const uint32_t acc_full = bar0 + 32u;
+  const uint32_t tmem_slot = bar0 + 40u;
+  const int ptile = (int)(blockIdx.x >> 1);                      // o.ntn = number of 256-wide column tiles
+  const int m0 = (ptile / o.ntn) * 256 + 128 * (int)rank, n0 = (ptile % o.ntn) * 256;
+  const int kbeg = blockIdx.y * o.kchunk, kend = min(o.K, kbeg + o.kchunk);
+  const int nst = (kend - kbeg + kXgBK - 1) / kXgBK;
+
+  if (threadIdx.x == 0) {
+    mbar_init(full(0), 16); mbar_init(full(1), 16);             // 8 loader warps of each CTA (used in the leader only)
+    mbar_init(empty(0), 1); mbar_init(empty(1), 1);
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  const long long t_entry = clock64();
+  if (warp == 8) tmem_alloc_pair<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kXgBars + 40);
+  XgTile t;
+  t.sbase = sbase; t.tmem_base = tmem_base; t.m0 = m0; t.n0 = n0; t.warp = warp; t.lane = lane;
+  XgTracer tr;
+  tr.init(o.trace, warp == 0 ? 0 : (warp == 4 ? 1 : 2), lane == 0 && (warp == 0 || warp == 4 || warp == 8));
+  if (tr.buf != nullptr) tr.buf[tr.n++] = ((unsigned long long)t_entry << 8) | 0x01;      // kernel entry
+  tr.mark(0x02);
+
+  if (warp < 8) {
+    if (warp < 4) xg_loader<A_UNIT_K, PARTS>(o.A, o.lda, m0, o.M, kbeg, kend, o.vecA != 0, sbase, warp, lane, nst, full(0), empty(0), tr,
+                                             o.a_scale, o.a_shift, rank != 0);
+    else xg_loader<B_UNIT_K, PARTS>(o.B, o.ldb, n0 + 128 * (int)rank, o.N, kbeg, kend, o.vecB != 0, sbase + 3u * kXgImage, warp & 3, lane, nst,
+                                    full(0), empty(0), tr, nullptr, nullptr, rank != 0);
+    mbar_wait_backoff(acc_full, 0);
+    tc_fence_after();
+    tr.mark(0x40);
+  } else if (rank == 0) {
+    // ---------------------------------------------------------------- MMA issue (leader; warp-convergent, one elected lane)
+    const uint32_t idesc = make_idesc_bf16(256, 256);
+    const uint32_t a_img = sbase, b_img = sbase + 3 * kXgImage;
+    for (int it = 0; it < nst; ++it) {
+      const int s = it & 1;
+      mbar_wait_w(full(s), (it >> 1) & 1);
+      tc_fence_after();
+      tr.mark(0x10);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t off = (uint32_t)(2 * s + ks) * 32u;
+        const uint64_t a1 = make_sdesc_k128(a_img + off), a2 = make_sdesc_k128(a_img + kXgImage + off);
+        const uint64_t b1 = make_sdesc_k128(b_img + off), b2 = make_sdesc_k128(b_img + kXgImage + off);
+        const uint32_t accum = (it | ks) != 0;
+        if (PARTS == 2) {
+          umma_bf16_pair_w(tmem_base, a2, b1, idesc, accum);
+          umma_bf16_pair_w(tmem_base, a1, b2, idesc, 1);
+          umma_bf16_pair_w(tmem_base, a1, b1, idesc, 1);
+        } else {
+          umma_bf16_pair_w(tmem_base, a1, b1, idesc, accum);
+        }
+      }
+      umma_commit_pair_w(empty(s), 3);
+      tr.mark(0x20);
+    }
+    umma_commit_pair_w(acc_full, 3);
+  }
+  xg_epilogue_gemm<1>(a, t, 4, blockIdx.y == 0);
+  tr.mark(0x50);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                            // neither CTA leaves while its partner may still signal it
+  tr.mark(0x60);
+  if (warp == 8) tmem_dealloc_pair<256>(tmem_base);
 }
 
 // ---- t3d_linear_f32 (same contract as linear_f32_kernel, simt_ops.cuh): Y = act(X.W + bias + gbias[row / rows_per_group])
