@@ -924,21 +924,27 @@ static int gemm_f32_impl(const float* A, long long sam, long long sak, const flo
       if (x.st_sum && sk != 1) return T3D_ERR_SHAPE;
       static int prepared_pair[kMaxDevices] = {0};
       if (int e = once_per_device(prepared_pair, [] {
-            return xg_prepare(xgemm_pair_kernel<true, true, 2>) | xg_prepare(xgemm_pair_kernel<true, false, 2>) |
-                   xg_prepare(xgemm_pair_kernel<false, true, 2>) | xg_prepare(xgemm_pair_kernel<false, false, 2>) |
-                   xg_prepare(xgemm_pair_kernel<true, true, 1>) | xg_prepare(xgemm_pair_kernel<true, false, 1>) |
-                   xg_prepare(xgemm_pair_kernel<false, true, 1>) | xg_prepare(xgemm_pair_kernel<false, false, 1>);
+            auto prep = [](auto kern) { return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kXgSmemBytes + 24u * 1024u)); };
+            return prep(xgemm_pair_kernel<true, true, 2>) | prep(xgemm_pair_kernel<true, false, 2>) |
+                   prep(xgemm_pair_kernel<false, true, 2>) | prep(xgemm_pair_kernel<false, false, 2>) |
+                   prep(xgemm_pair_kernel<true, true, 1>) | prep(xgemm_pair_kernel<true, false, 1>) |
+                   prep(xgemm_pair_kernel<false, true, 1>) | prep(xgemm_pair_kernel<false, false, 1>);
           }))
         return e;
+#ifndef XG_PAIR_SOLO
+#define XG_PAIR_SOLO 0
+#endif
+      // XG_PAIR_SOLO: request more than half of the shared memory so that only one cluster is resident per SM pair
+      constexpr uint32_t kPairSmem = kXgSmemBytes + (XG_PAIR_SOLO ? 24u * 1024u : 0u);
       const int ntm2 = (M + 255) / 256, ntn2 = (N + 255) / 256;
       o.ntn = ntn2;
       const dim3 pgrid((unsigned)ntm2 * ntn2 * 2, nz);
 #define XG_LAUNCH_PAIR(P)                                                                                     \
   do {                                                                                                        \
-    if (ak && bk) xgemm_pair_kernel<true, true, P><<<pgrid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);      \
-    else if (ak) xgemm_pair_kernel<true, false, P><<<pgrid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);      \
-    else if (bk) xgemm_pair_kernel<false, true, P><<<pgrid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);      \
-    else xgemm_pair_kernel<false, false, P><<<pgrid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);             \
+    if (ak && bk) xgemm_pair_kernel<true, true, P><<<pgrid, kXgThreads, kPairSmem, S(stream)>>>(a, o);      \
+    else if (ak) xgemm_pair_kernel<true, false, P><<<pgrid, kXgThreads, kPairSmem, S(stream)>>>(a, o);      \
+    else if (bk) xgemm_pair_kernel<false, true, P><<<pgrid, kXgThreads, kPairSmem, S(stream)>>>(a, o);      \
+    else xgemm_pair_kernel<false, false, P><<<pgrid, kXgThreads, kPairSmem, S(stream)>>>(a, o);             \
   } while (0)
       if (xg_parts() == 2) XG_LAUNCH_PAIR(2);
       else XG_LAUNCH_PAIR(1);
