@@ -38,9 +38,9 @@ FLOP_SEG_GLOBAL_FR = 2 * (1024 + 10) * 512
 FLOP_TNET_PT, FLOP_BOX_PT = 99072, 361216
 FLOP_FC_FR = 2 * (98688 + 2560 + 410368 + 5120)
 # DRAM bytes per frustum (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at 8192 frustums per
-# launch, profiles/r01_ncu_full_v3_kernels.csv); algorithmic: stage 2 reads point_feat 262 144 B + gbias 2 048 B and writes
-# logits 16 384 B, stage 1 reads the points 49 152 B and writes point_feat 262 144 B + gfeat 4 096 B
-NCU_DRAM_BYTES_FR = {'seg2': (2.169102e9 + 0.134332e9) / 8192, 'seg1': (0.436980e9 + 2.125062e9) / 8192}
+# launch of the final round-2 build, profiles/r02_ncu_cfg3_kernels_final.csv); algorithmic: stage 2 reads point_feat 262 144 B +
+# gbias 2 048 B and writes logits 16 384 B, stage 1 reads the points 49 152 B and writes point_feat 262 144 B + gfeat 4 096 B
+NCU_DRAM_BYTES_FR = {'seg2': (2.169e9 + 0.134e9) / 8192, 'seg1': (0.437e9 + 2.124e9) / 8192}
 
 
 def peaks():

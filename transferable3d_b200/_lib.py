@@ -204,11 +204,13 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        engine = os.environ.get('T3D_F32_ENGINE')       # 'simt' = CUDA-core SGEMM, 'tc' = tcgen05 bf16 x 3 (default), 'bf16' = one pass
+        # 'simt' = CUDA-core SGEMM, 'tc' = tcgen05 bf16 x 3 (default), 'tc2' = bf16 x 2 (three products), 'bf16' = one pass
+        engine = os.environ.get('T3D_F32_ENGINE')
         if engine is not None:
-            if engine not in ('simt', 'tc', 'bf16'):
-                raise T3DError("T3D_F32_ENGINE must be 'simt', 'tc' or 'bf16'")
-            lib.t3d_set_f32_engine({'simt': 0, 'tc': 1, 'bf16': 2}[engine])
+            codes = {'simt': 0, 'tc': 1, 'bf16': 2, 'tc2': 3}
+            if engine not in codes:
+                raise T3DError("T3D_F32_ENGINE must be one of %s" % sorted(codes))
+            lib.t3d_set_f32_engine(codes[engine])
         _lib = lib
     return _lib
 
