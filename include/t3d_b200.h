@@ -156,6 +156,13 @@ int t3d_chain_max_bf16(int kind, const float* pc, int B, int N, int C, const flo
                        int idx_stride, const int* count, const void* tiles, const int* num_tiles,
                        const float* box_center, const float* box_dims, const float* box_orient,
                        const void* arena, float* out, void* emit, t3d_stream_t stream);
+/* Same with the 6-channel input in the wire format of t3d_assemble_points (xyz [B,N,3] fp32 + rgb [B,N,3] uint8, colour = k / 255
+ * by IEEE division: bit-identical to assembling the (B,N,6) placeholder of semisup_v1_sunrgbd.py:39 first): the first layer of
+ * the inst_seg chain (kind 0) / BoxPC representation B (kind 4) reads it directly, so the fp32 (B,N,6) tensor is never built. */
+int t3d_chain_max_bf16_wire(int kind, const float* xyz, const uint8_t* rgb, int B, int N, const float* center,
+                            const int* idx, int idx_stride, const int* count, const void* tiles, const int* num_tiles,
+                            const float* box_center, const float* box_dims, const float* box_orient,
+                            const void* arena, float* out, void* emit, t3d_stream_t stream);
 
 /* inst_seg conv6'..conv10 (semisup_models.py:107-135) with conv6's global half folded into gbias [B,512]. */
 size_t t3d_seg2_arena_bytes(void);

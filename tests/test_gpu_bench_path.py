@@ -188,3 +188,29 @@ def test_cfg1_session_batch_32(mode, built_lib):
     for k in fetch[1:]:
         check_mode(mode, got[k], oep[k], 'cfg1 ' + k, bf16_frac=0.99)
     rt.set_default_store(None)
+
+
+@pytest.mark.parametrize('mode', ['bf16', 'f16x2', 'fp32'])
+def test_wire_format_input_equals_assembled_input(mode, built_lib, big):
+    """The e2e path of bench.py feeds the pipeline the wire format (xyz fp32 + rgb uint8) lazily: the fused bf16 inst_seg chain
+    converts the colours while it loads the points (t3d_chain_max_bf16_wire) and the (B,N,6) tensor is never built.  Every
+    output must equal, bit for bit, the run on the assembled (B,N,6) fp32 tensor (k / 255 by IEEE division in both), in every
+    precision mode (f16x2 / fp32 assemble the dense tensor behind the same object); N = 2000 for ragged tiles."""
+    rt.set_default_store(big['store'])
+    B = 256 if mode != 'fp32' else 32
+    xyz = big['pc'][:B, :2000, :3].contiguous()
+    rgb = torch.randint(0, 256, (B, 2000, 3), dtype=torch.uint8, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    oh = big['oh'][:B].contiguous()
+    dense = mu.assemble_point_cloud(xyz, rgb)
+    # (CPU float32 division: torch's CUDA `x / 255.0` multiplies by the reciprocal)
+    assert torch.equal(dense[..., 3:].cpu(), rgb.cpu().float() / 255.0) and torch.equal(dense[..., :3], xyz)
+    with rt.precision(mode), torch.no_grad():
+        mu.set_resample_rng('philox', seed=5)
+        a = fpn.inference(dense, oh)
+        mu.set_resample_rng('philox', seed=5)
+        b = fpn.inference(mu.assemble_point_cloud(xyz, rgb, lazy=True), oh)
+    for k in ('pred_seg', 'center', 'heading_cls', 'heading_res', 'size_cls', 'size_res', 'scores'):
+        assert torch.equal(a[k], b[k]), (mode, k)
+    for k in ('mask_logits', 'object_pc_indices', 'stage1_center'):
+        assert torch.equal(a['end_points'][k], b['end_points'][k]), (mode, k)
+    rt.set_default_store(None)

@@ -117,6 +117,7 @@ SIGNATURES = {
     't3d_chain_out_channels': (_I, [_I]),
     't3d_pack_chain': (_I, [_I, _c.POINTER(_P), _c.POINTER(_P), _P, _P]),
     't3d_chain_max_bf16': (_I, [_I, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    't3d_chain_max_bf16_wire': (_I, [_I, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     't3d_seg2_arena_bytes': (_c.c_size_t, []),
     't3d_pack_seg2': (_I, [_P] * 10 + [_P]),
     't3d_seg_stage2_bf16': (_I, [_P, _P, _P, _P, _I, _I, _P]),

@@ -117,6 +117,8 @@ struct ChainArgs {
   float* out;               // [B, FC] fp32, zero-initialised by the caller; atomic max target
   __nv_bfloat16* emit;      // [B*N, HN[EMIT_LAYER]] bf16 (seg1: point_feat) or null
   unsigned long long* trace; // debug timeline of CTA 0 (null: off)
+  const uint8_t* rgb;       // wire format of a 6-channel input (null: pc holds all C channels): pc = xyz [B, N, 3] fp32 and
+                            // channels 3..5 = rgb[B, N, 3] / 255 (IEEE division: bit-identical to t3d_assemble_points)
 };
 
 // smem carve-up (offsets from the 1024-aligned base)
@@ -446,10 +448,16 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kChainThr
         int j = min(grow, npts - 1);               // padded rows duplicate the last valid point
         j += start;
         const int src = args.idx ? args.idx[(size_t)fr * args.idx_stride + j] : j;
-        const float* pp = args.pc + ((size_t)fr * args.N + src) * args.C;
         float x[S::CIN];
+        if (S::CRAW == 6 && args.rgb != nullptr) {
+          const size_t pi = ((size_t)fr * args.N + src) * 3;
 #pragma unroll
-        for (int k = 0; k < S::CRAW; ++k) x[k] = pp[k];
+          for (int k = 0; k < 3; ++k) { x[k] = args.pc[pi + k]; x[3 + k] = __fdiv_rn((float)args.rgb[pi + k], 255.0f); }
+        } else {
+          const float* pp = args.pc + ((size_t)fr * args.N + src) * args.C;
+#pragma unroll
+          for (int k = 0; k < S::CRAW; ++k) x[k] = pp[k];
+        }
         x[0] -= cx; x[1] -= cy; x[2] -= cz;
         if (S::BOXPC) {
           // 6 signed plane distances (models/tf_util.py:764-795, closed form in SURVEY a14)

@@ -563,11 +563,31 @@ extern "C" int t3d_pack_chain(int kind, const float* const* W, const float* cons
   return 0;
 }
 
+static int chain_max_bf16_impl(int kind, const float* pc, const uint8_t* rgb, int B, int N, int C, const float* center, const int* idx,
+                               int idx_stride, const int* count, const void* tiles, const int* num_tiles,
+                               const float* box_center, const float* box_dims, const float* box_orient, const void* arena,
+                               float* out, void* emit, t3d_stream_t stream);
 extern "C" int t3d_chain_max_bf16(int kind, const float* pc, int B, int N, int C, const float* center, const int* idx,
                                   int idx_stride, const int* count, const void* tiles, const int* num_tiles,
                                   const float* box_center, const float* box_dims, const float* box_orient, const void* arena,
                                   float* out, void* emit, t3d_stream_t stream) {
+  return chain_max_bf16_impl(kind, pc, nullptr, B, N, C, center, idx, idx_stride, count, tiles, num_tiles, box_center, box_dims, box_orient,
+                             arena, out, emit, stream);
+}
+extern "C" int t3d_chain_max_bf16_wire(int kind, const float* xyz, const uint8_t* rgb, int B, int N, const float* center, const int* idx,
+                                       int idx_stride, const int* count, const void* tiles, const int* num_tiles,
+                                       const float* box_center, const float* box_dims, const float* box_orient, const void* arena,
+                                       float* out, void* emit, t3d_stream_t stream) {
+  if (!rgb) return T3D_ERR_ARG;
+  return chain_max_bf16_impl(kind, xyz, rgb, B, N, 6, center, idx, idx_stride, count, tiles, num_tiles, box_center, box_dims, box_orient,
+                             arena, out, emit, stream);
+}
+static int chain_max_bf16_impl(int kind, const float* pc, const uint8_t* rgb, int B, int N, int C, const float* center, const int* idx,
+                               int idx_stride, const int* count, const void* tiles, const int* num_tiles,
+                               const float* box_center, const float* box_dims, const float* box_orient, const void* arena,
+                               float* out, void* emit, t3d_stream_t stream) {
   if (!pc || !arena || !out) return T3D_ERR_ARG;
+  if (rgb && kind != CHAIN_SEG1 && kind != CHAIN_BOXPCB) return T3D_ERR_ARG;      // the chains whose raw input has 6 channels
   if (B <= 0 || N <= 0) return T3D_ERR_SHAPE;
   if ((uintptr_t)arena & 15) return T3D_ERR_ALIGN;
   if ((tiles != nullptr) != (num_tiles != nullptr)) return T3D_ERR_ARG;
@@ -577,7 +597,7 @@ extern "C" int t3d_chain_max_bf16(int kind, const float* pc, int B, int N, int C
   if (emit && (kind != CHAIN_SEG1 || ((uintptr_t)emit & 15))) return T3D_ERR_ARG;
   ChainArgs a{pc, B, N, C, center, idx, idx_stride, count, reinterpret_cast<const int4*>(tiles), num_tiles,
               box_center, box_dims, box_orient, reinterpret_cast<const uint8_t*>(arena), out,
-              reinterpret_cast<__nv_bfloat16*>(emit), g_trace};
+              reinterpret_cast<__nv_bfloat16*>(emit), g_trace, rgb};
   CHAIN_SWITCH(kind, return chain_launch<K_>(a, B * ChainSpec<K_>::FC, S(stream)));
   return 0;
 }

@@ -122,14 +122,18 @@ def placeholder_inputs(batch_size, num_point, num_channel=4, num_class=3, device
             Z((B,), i), Z((B, 3), f))
 
 
-def assemble_point_cloud(xyz, rgb_u8, out=None):
+def assemble_point_cloud(xyz, rgb_u8, out=None, lazy=False):
     """Wire format of the inference input -> the (B,N,6) fp32 point cloud of the reference placeholder
     (semisup_v1_sunrgbd.py:39): xyz (B,N,3) fp32 + rgb (B,N,3) uint8, colours = k / 255 (bit-identical to the host's
-    float32 division).  15 instead of 24 bytes per point cross PCIe.  `out`: optional preallocated (B,N,6) tensor."""
+    float32 division).  15 instead of 24 bytes per point cross PCIe.  `out`: optional preallocated (B,N,6) tensor.
+    lazy=True returns an rt.WirePoints instead: frustum_pointnets_v1.get_model / inference and v1_inst_seg accept it, the fused
+    bf16 inst_seg chain converts the colours while it loads the points and the (B,N,6) tensor is never written."""
     xyz = rt.f32(xyz)
     if rgb_u8.dtype != torch.uint8 or tuple(rgb_u8.shape) != tuple(xyz.shape) or xyz.shape[-1] != 3:
         raise ValueError('assemble_point_cloud: xyz (B,N,3) float32 and rgb (B,N,3) uint8 expected')
     rgb_u8 = rgb_u8.contiguous()
+    if lazy:
+        return rt.WirePoints(xyz, rgb_u8)
     B, N = xyz.shape[0], xyz.shape[1]
     if out is None:
         out = torch.empty((B, N, 6), dtype=torch.float32, device=xyz.device)
@@ -140,6 +144,8 @@ def assemble_point_cloud(xyz, rgb_u8, out=None):
 def point_cloud_masking(point_cloud, logits, end_points, xyz_only=True):
     """model_util.py:241-286 -> (object_point_cloud (B,512,3|C), mask_xyz_mean (B,3), end_points)."""
     pc = rt.f32(point_cloud)
+    if isinstance(pc, rt.WirePoints):
+        pc = pc.xyz if xyz_only else pc.dense()          # mask, centroid and the gathered object points use xyz only
     B, N, C = pc.shape
     mask, count, mean, _, idx = rt.mask_centroid(logits, pc)
     end_points['mask'] = mask

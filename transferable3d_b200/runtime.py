@@ -243,7 +243,29 @@ def require_eval(is_training):
                                   'B200 path yet; only is_training=False')
 
 
+class WirePoints(object):
+    """The 6-channel frustum input in its wire format (model_util.assemble_point_cloud(..., lazy=True)): xyz (B,N,3) fp32 and
+    rgb (B,N,3) uint8, colours = k / 255.  The fused bf16 inst_seg chain reads it directly (t3d_chain_max_bf16_wire); every
+    other consumer of the point cloud downstream of the segmentation net uses xyz only (model_util.py:241-286), and
+    `dense()` builds the (B,N,6) fp32 placeholder tensor for the paths that need it (f16x2 / fp32 precision modes)."""
+
+    def __init__(self, xyz, rgb):
+        self.xyz, self.rgb = xyz, rgb
+        self.shape = (xyz.shape[0], xyz.shape[1], 6)
+        self.device = xyz.device
+        self._dense = None
+
+    def dense(self):
+        if self._dense is None:
+            out = torch.empty(self.shape, dtype=torch.float32, device=self.device)
+            call('t3d_assemble_points', ptr(self.xyz), ptr(self.rgb), self.shape[0] * self.shape[1], ptr(out), stream())
+            self._dense = out
+        return self._dense
+
+
 def f32(t):
+    if isinstance(t, WirePoints):
+        return t
     return t.to(torch.float32).contiguous()
 
 
@@ -287,6 +309,9 @@ def build_tiles(count, tile_pts, max_per_frustum):
 def chain_max(kind, pc, arena, center=None, idx=None, count=None, box=None, emit=None, x2=False):
     """Fused per-point chain + max on tcgen05. Returns (B, FC) fp32.  x2: the f16x2 kernel (arena packed with x2=True)."""
     lib = _lib.load()
+    wire = isinstance(pc, WirePoints)
+    if wire and x2:
+        pc, wire = pc.dense(), False
     B, N, C = pc.shape
     fc = lib.t3d_chain_out_channels(kind)
     out = torch.empty((B, fc), dtype=torch.float32, device=pc.device)
@@ -300,6 +325,10 @@ def chain_max(kind, pc, arena, center=None, idx=None, count=None, box=None, emit
     bc = bd = bo = None
     if box is not None:
         bc, bd, bo = [f32(t) for t in box]
+    if wire:
+        call('t3d_chain_max_bf16_wire', kind, ptr(pc.xyz), ptr(pc.rgb), B, N, ptr(center), ptr(idx), idx_stride, ptr(count), ptr(tiles), ptr(num),
+             ptr(bc), ptr(bd), ptr(bo), ptr(arena), ptr(out), ptr(emit), stream())
+        return out
     call('t3d_chain_max_x2' if x2 else 't3d_chain_max_bf16', kind, ptr(pc), B, N, C, ptr(center), ptr(idx), idx_stride, ptr(count), ptr(tiles), ptr(num),
          ptr(bc), ptr(bd), ptr(bo), ptr(arena), ptr(out), ptr(emit), stream())
     return out

@@ -139,6 +139,8 @@ def v1_inst_seg(point_cloud, img_feats, one_hot_vec, end_points, is_training, bn
             gbias, _ = rt.linear(g, w6g, b6g)                                               # conv6 global half
             logits = rt.seg_stage2(point_feat, gbias, arena2, B, N, x2=x2)
         else:
+            if isinstance(pc, rt.WirePoints):
+                pc = pc.dense()
             x = pc.reshape(B * N, D)
             for name in ('conv1', 'conv2', 'conv3'):
                 w, b = st.folded(full + '/' + name)
