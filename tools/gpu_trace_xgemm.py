@@ -32,7 +32,8 @@ def dump(buf, title):
 def main():
     M = 524288
     buf = torch.zeros(4 * SLOTS, dtype=torch.int64, device='cuda')
-    for K, N in ((256, 512),) if os.environ.get('ENGINES') else ((128, 128), (256, 512)):
+    shapes = [tuple(int(v) for v in kn.split('x')) for kn in os.environ['SHAPES'].split(',')] if os.environ.get('SHAPES') else None
+    for K, N in shapes or (((256, 512),) if os.environ.get('ENGINES') else ((128, 128), (256, 512))):
         x = torch.randn(M, K, device='cuda')
         w = torch.randn(K, N, device='cuda') * 0.1
         dy = torch.randn(M, N, device='cuda')

@@ -108,9 +108,9 @@ static int once_per_device(int (&state)[kMaxDevices], F prep) {
   if (state[dev] == 0) { const int e = prep(); if (e != 0) return e; state[dev] = 1; }
   return 0;
 }
-template <typename Kern>
+template <int PARTS, typename Kern>
 static int xg_prepare_pp(Kern kern) {
-  return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kXgPPSmemBytes);
+  return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XgPP<PARTS>::SMEM);
 }
 
 extern "C" size_t t3d_gemm_ws_bytes(int N, int K) { return (N > 0 && K > 0) ? xg_pre_bytes(N, K) : 0; }
@@ -142,7 +142,7 @@ extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ld
     if (int e = once_per_device(prepared, [] {
           return xg_prepare(xlinear_kernel<3>) | xg_prepare(xlinear_kernel<2>) | xg_prepare(xlinear_kernel<1>) |
                  xg_prepare(xlinear_pre_kernel<3>) | xg_prepare(xlinear_pre_kernel<2>) | xg_prepare(xlinear_pre_kernel<1>) |
-                 xg_prepare_pp(xg_as_kernel<3, true>) | xg_prepare_pp(xg_as_kernel<2, true>) | xg_prepare_pp(xg_as_kernel<1, true>);
+                 xg_prepare_pp<3>(xg_as_kernel<3, true>) | xg_prepare_pp<2>(xg_as_kernel<2, true>) | xg_prepare_pp<1>(xg_as_kernel<1, true>);
         }))
       return e;
     const int ntm = (M + kXgBM - 1) / kXgBM, ntn = (N + kXgBN - 1) / kXgBN;
@@ -155,7 +155,7 @@ extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ld
       xg_presplit_kernel<<<dim3(o.nkb, ntn, 4), 256, 0, S(stream)>>>(W, ldw, 0, N, K, parts, reinterpret_cast<uint8_t*>(ws));
       if (xg_use_as(K, ntn, true, Y != nullptr)) {
         const int g = ntm < xg_num_sms() ? ntm : xg_num_sms();
-        XG_BY_PARTS((xg_as_kernel<P, true><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(GemmArgs{}, a, o)));
+        XG_BY_PARTS((xg_as_kernel<P, true><<<g, XgPP<P>::THREADS, XgPP<P>::SMEM, S(stream)>>>(GemmArgs{}, a, o)));
       } else XG_BY_PARTS((xlinear_pre_kernel<P><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o)));
     } else {
       XG_BY_PARTS((xlinear_kernel<P><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o)));
@@ -916,8 +916,8 @@ static int gemm_f32_impl(const float* A, long long sam, long long sak, const flo
                  xg_prepare(xgemm_kernel<true, true, 1>) | xg_prepare(xgemm_kernel<true, false, 1>) |
                  xg_prepare(xgemm_kernel<false, true, 1>) | xg_prepare(xgemm_kernel<false, false, 1>) |
                  xg_prepare(xgemm_pre_kernel<3>) | xg_prepare(xgemm_pre_kernel<2>) | xg_prepare(xgemm_pre_kernel<1>) |
-                 xg_prepare_pp(xg_as_kernel<3, false>) | xg_prepare_pp(xg_as_kernel<2, false>) | xg_prepare_pp(xg_as_kernel<1, false>) |
-                 xg_prepare_pp(xg_pp_kernel<3, false>) | xg_prepare_pp(xg_pp_kernel<2, false>) | xg_prepare_pp(xg_pp_kernel<1, false>);
+                 xg_prepare_pp<3>(xg_as_kernel<3, false>) | xg_prepare_pp<2>(xg_as_kernel<2, false>) | xg_prepare_pp<1>(xg_as_kernel<1, false>) |
+                 xg_prepare_pp<3>(xg_pp_kernel<3, false>) | xg_prepare_pp<2>(xg_pp_kernel<2, false>) | xg_prepare_pp<1>(xg_pp_kernel<1, false>);
         }))
       return e;
     // The tensor core adds each 16-deep partial sum into the fp32 accumulator with truncation, a bias of ~0.5 ulp per
@@ -986,10 +986,10 @@ static int gemm_f32_impl(const float* A, long long sam, long long sak, const flo
       xg_presplit_kernel<<<dim3(o.nkb, ntn, 4), 256, 0, S(stream)>>>(B, ldb, bk ? 1 : 0, N, K, xg_parts(), reinterpret_cast<uint8_t*>(ws));
       if (xg_use_as(K, ntn)) {
         const int g = ntm < xg_num_sms() ? ntm : xg_num_sms();
-        XG_BY_PARTS((xg_as_kernel<P, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o)));
+        XG_BY_PARTS((xg_as_kernel<P, false><<<g, XgPP<P>::THREADS, XgPP<P>::SMEM, S(stream)>>>(a, LinearArgs{}, o)));
       } else if (xg_use_pp(K)) {
         const int g = ntm * ntn < xg_num_sms() ? ntm * ntn : xg_num_sms();
-        XG_BY_PARTS((xg_pp_kernel<P, false><<<g, kXgPPThreads, kXgPPSmemBytes, S(stream)>>>(a, LinearArgs{}, o)));
+        XG_BY_PARTS((xg_pp_kernel<P, false><<<g, XgPP<P>::THREADS, XgPP<P>::SMEM, S(stream)>>>(a, LinearArgs{}, o)));
       } else XG_BY_PARTS((xgemm_pre_kernel<P><<<grid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o)));
       T3D_CHECK_LAUNCH();
       return 0;

@@ -872,27 +872,36 @@ __global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xlinear_pre_kernel(c
 #define XG_PP_LOADERS 8
 #endif
 constexpr int kXgPPLoaders = XG_PP_LOADERS;                     // loader warps: 8 (16 rows each) or 16 (8 rows each)
-constexpr int kXgPPThreads = (kXgPPLoaders + 5) * 32;           // + 4 epilogue warps + the MMA warp
 constexpr int kXgPPBAhead = 2;                                  // stages the B copies run ahead of the A split (<= 2 with 4 slots)
 constexpr int kXgPPVals = 128 / kXgPPLoaders;                   // A values per thread and stage (16 or 8)
 constexpr int kXgPPSlots = 4;
-constexpr uint32_t kXgPPImages = 12 * kXgImage;                                  // A: 3 parts x 2 blocks, then B the same
-constexpr uint32_t kXgPPPatch = kXgPPImages;                                    // 4 x kXgPatchBytes
-constexpr uint32_t kXgPPBars = kXgPPPatch + 4 * kXgPatchBytes;
-constexpr uint32_t kXgPPParams = kXgPPBars + 128;                               // [a_scale 128][a_shift 128] fp32 (K <= 128 here)
-constexpr uint32_t kXgPPSmemBytes = kXgPPBars + 128 + 1024 + 1024;
+// Geometry of the persistent kernels by number of operand pieces.  With three pieces the 12 operand images (192 KB) leave room
+// for 4 epilogue warps (one staging patch each); with two or one the images are 128 / 64 KB and EIGHT epilogue warps drain an
+// accumulator (lane quarter x column half) -- the 4-warp epilogue was the limit of these kernels (5.6 k cycles per 128 x 128
+// tile against 3.3 k for its MMAs in the clock64 trace of the A-stationary kernel, profiles/r02_trace_xgemm_tc2.txt).
+template <int PARTS> struct XgPP {
+  static constexpr int EPI = PARTS == 3 ? 4 : 8;                                  // epilogue warps
+  static constexpr int THREADS = (kXgPPLoaders + EPI + 1) * 32;                   // loaders + epilogue + the MMA warp
+  static constexpr int MMA_WARP = kXgPPLoaders + EPI;
+  static constexpr uint32_t B_IMG = 2u * PARTS * kXgImage;                         // A: PARTS x 2 blocks, then B the same
+  static constexpr uint32_t PATCH = 4u * PARTS * kXgImage;                         // EPI x kXgPatchBytes
+  static constexpr uint32_t BARS = PATCH + EPI * kXgPatchBytes;
+  static constexpr uint32_t PARAMS = BARS + 128;                                   // [a_scale 128][a_shift 128] fp32 (K <= 128 here)
+  static constexpr uint32_t SMEM = BARS + 128 + 1024 + 1024;
+};
 
 // shared address of (part p, ring slot s) of an operand whose images start at `base`: block s >> 1 of image p; the
 // stage is half s & 1 of that block
 __device__ __forceinline__ uint32_t xg_pp_block(uint32_t base, int p, int s) { return base + (uint32_t)(p * 2 + (s >> 1)) * kXgImage; }
 
 template <int PARTS, bool LINEAR>
-__global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs ga, const LinearArgs la, const XgOperands o) {
+__global__ void __launch_bounds__(XgPP<PARTS>::THREADS, 1) xg_pp_kernel(const GemmArgs ga, const LinearArgs la, const XgOperands o) {
   extern __shared__ uint8_t xg_smem[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)xg_smem + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
+  using G = XgPP<PARTS>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar0 = sbase + kXgPPBars;
+  const uint32_t bar0 = sbase + G::BARS;
   auto full = [&](int s) { return bar0 + 8u * s; };
   auto empty = [&](int s) { return bar0 + 8u * (4 + s); };
   auto acc_full = [&](int b) { return bar0 + 8u * (8 + b); };
@@ -900,24 +909,24 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs g
   const uint32_t tmem_slot = bar0 + 96u;
   const int ntm = (o.M + kXgBM - 1) / kXgBM, ntiles = ntm * o.ntn;
   const int nst = (o.K + kXgBK - 1) / kXgBK;
-  const uint32_t a_img = sbase, b_img = sbase + 6u * kXgImage;
+  const uint32_t a_img = sbase, b_img = sbase + G::B_IMG;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kXgPPSlots; ++s) { mbar_init(full(s), kXgPPLoaders); mbar_init(empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), G::EPI); }
     fence_barrier_init();
   }
-  if (warp == kXgPPLoaders + 4) tmem_alloc<512>(tmem_slot);
+  if (warp == G::MMA_WARP) tmem_alloc<512>(tmem_slot);
   if (o.a_scale != nullptr) {               // lazy BN tables of the A operand (K <= 128)
-    float* tab = reinterpret_cast<float*>(smem + kXgPPParams);
-    for (int i = threadIdx.x; i < o.K; i += kXgPPThreads) { tab[i] = __ldg(o.a_scale + i); tab[128 + i] = __ldg(o.a_shift + i); }
+    float* tab = reinterpret_cast<float*>(smem + G::PARAMS);
+    for (int i = threadIdx.x; i < o.K; i += G::THREADS) { tab[i] = __ldg(o.a_scale + i); tab[128 + i] = __ldg(o.a_shift + i); }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kXgPPBars + 96);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + G::BARS + 96);
   XgTracer tr;      // roles: 0 loader warp 0, 1 MMA warp, 2 epilogue warp 0
-  tr.init(o.trace, warp == 0 ? 0 : (warp == kXgPPLoaders + 4 ? 1 : 2), lane == 0 && (warp == 0 || warp == kXgPPLoaders + 4 || warp == kXgPPLoaders));
+  tr.init(o.trace, warp == 0 ? 0 : (warp == G::MMA_WARP ? 1 : 2), lane == 0 && (warp == 0 || warp == G::MMA_WARP || warp == kXgPPLoaders));
   tr.mark(0x02);
 
   if (warp < kXgPPLoaders) {
@@ -974,8 +983,8 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs g
     auto emit = [&](int g, float (&r)[kXgPPVals]) {
       const int s = g & 3;
       if (o.a_scale != nullptr) {      // lazy BN of A: the 4 channels of this thread in stage e_it
-        const float4 sc = ld_shared_f4(sbase + kXgPPParams + 4u * (uint32_t)(e_it * kXgBK + kofs));
-        const float4 sh = ld_shared_f4(sbase + kXgPPParams + 512u + 4u * (uint32_t)(e_it * kXgBK + kofs));
+        const float4 sc = ld_shared_f4(sbase + G::PARAMS + 4u * (uint32_t)(e_it * kXgBK + kofs));
+        const float4 sh = ld_shared_f4(sbase + G::PARAMS + 512u + 4u * (uint32_t)(e_it * kXgBK + kofs));
 #pragma unroll
         for (int i = 0; i < NI; ++i) xg_bn4(&r[4 * i], sc, sh);
       }
@@ -1022,7 +1031,7 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs g
         }
       }
     }
-  } else if (warp == kXgPPLoaders + 4) {
+  } else if (warp == G::MMA_WARP) {
     // ------------------------------------------------------------------------------------------------ MMA issue
     int g = 0, lt = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
@@ -1058,13 +1067,13 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs g
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++lt) {
       const int ab = lt & 1;
       XgTile t;
-      t.sbase = sbase + kXgPPPatch; t.tmem_base = tmem_base + (uint32_t)ab * 256u;
+      t.sbase = sbase + G::PATCH; t.tmem_base = tmem_base + (uint32_t)ab * 256u;
       t.m0 = (tile / o.ntn) * kXgBM; t.n0 = (tile % o.ntn) * kXgBN; t.warp = warp - kXgPPLoaders; t.lane = lane;
       mbar_wait_backoff(acc_full(ab), (lt >> 1) & 1);
       tc_fence_after();
       tr.mark(0x40);
-      if (LINEAR) xg_epilogue_linear<PARTS>(la, t, 4);
-      else xg_epilogue_gemm<PARTS>(ga, t, 4, true);
+      if (LINEAR) xg_epilogue_linear<PARTS>(la, t, 16 / G::EPI);
+      else xg_epilogue_gemm<PARTS>(ga, t, 16 / G::EPI, true);
       tc_fence_before();                                  // the tcgen05.ld of this tile are complete (wait::ld inside)
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty(ab));
@@ -1073,7 +1082,7 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs g
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kXgPPLoaders + 4) tmem_dealloc<512>(tmem_base);
+  if (warp == G::MMA_WARP) tmem_dealloc<512>(tmem_base);
 }
 // ---- A-stationary variant for K <= 128 and several column tiles -----------------------------------------------------------
 // Same roles and shared-memory map as xg_pp_kernel, but a CTA owns ROW tiles: the split images of its A block (at most 4
@@ -1083,12 +1092,13 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_pp_kernel(const GemmArgs g
 // registers while the current one is multiplied; the images are rewritten once the last MMA of the row tile has retired
 // (a_free), which costs a short bubble per row tile.
 template <int PARTS, bool LINEAR>
-__global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs ga, const LinearArgs la, const XgOperands o) {
+__global__ void __launch_bounds__(XgPP<PARTS>::THREADS, 1) xg_as_kernel(const GemmArgs ga, const LinearArgs la, const XgOperands o) {
   extern __shared__ uint8_t xg_smem[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)xg_smem + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
+  using G = XgPP<PARTS>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar0 = sbase + kXgPPBars;
+  const uint32_t bar0 = sbase + G::BARS;
   auto full = [&](int s) { return bar0 + 8u * s; };
   auto empty = [&](int s) { return bar0 + 8u * (4 + s); };
   auto acc_full = [&](int b) { return bar0 + 8u * (8 + b); };
@@ -1097,24 +1107,27 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs g
   const uint32_t tmem_slot = bar0 + 96u;
   const int ntm = (o.M + kXgBM - 1) / kXgBM, ntn = o.ntn;
   const int nst = (o.K + kXgBK - 1) / kXgBK;                       // <= 4
-  const uint32_t a_img = sbase, b_img = sbase + 6u * kXgImage;
+  const uint32_t a_img = sbase, b_img = sbase + G::B_IMG;
   const int my_mt = (ntm - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // row tiles of this CTA
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kXgPPSlots; ++s) { mbar_init(full(s), kXgPPLoaders); mbar_init(empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), G::EPI); }
     mbar_init(a_ready, kXgPPLoaders); mbar_init(a_free, 1);
     fence_barrier_init();
   }
-  if (warp == kXgPPLoaders + 4) tmem_alloc<512>(tmem_slot);
+  if (warp == G::MMA_WARP) tmem_alloc<512>(tmem_slot);
   if (o.a_scale != nullptr) {               // lazy BN tables of the A operand (K <= 128)
-    float* tab = reinterpret_cast<float*>(smem + kXgPPParams);
-    for (int i = threadIdx.x; i < o.K; i += kXgPPThreads) { tab[i] = __ldg(o.a_scale + i); tab[128 + i] = __ldg(o.a_shift + i); }
+    float* tab = reinterpret_cast<float*>(smem + G::PARAMS);
+    for (int i = threadIdx.x; i < o.K; i += G::THREADS) { tab[i] = __ldg(o.a_scale + i); tab[128 + i] = __ldg(o.a_shift + i); }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kXgPPBars + 96);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + G::BARS + 96);
+  XgTracer tr;      // roles: 0 loader warp 0, 1 MMA warp, 2 epilogue warp 0
+  tr.init(o.trace, warp == 0 ? 0 : (warp == G::MMA_WARP ? 1 : 2), lane == 0 && (warp == 0 || warp == G::MMA_WARP || warp == kXgPPLoaders));
+  tr.mark(0x02);
 
   if (warp < kXgPPLoaders) {
     // ------------------------------------------------------------------------------------------------ loaders
@@ -1155,8 +1168,8 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs g
       for (int it = 0; it < 4; ++it) {
         if (it < nst) {
           if (o.a_scale != nullptr) {      // lazy BN of A
-            const float4 sc = ld_shared_f4(sbase + kXgPPParams + 4u * (uint32_t)(it * kXgBK + kofs));
-            const float4 sh = ld_shared_f4(sbase + kXgPPParams + 512u + 4u * (uint32_t)(it * kXgBK + kofs));
+            const float4 sc = ld_shared_f4(sbase + G::PARAMS + 4u * (uint32_t)(it * kXgBK + kofs));
+            const float4 sh = ld_shared_f4(sbase + G::PARAMS + 512u + 4u * (uint32_t)(it * kXgBK + kofs));
 #pragma unroll
             for (int i = 0; i < NI; ++i) xg_bn4(&rA[it][4 * i], sc, sh);
           }
@@ -1198,11 +1211,14 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs g
       }
       int g = 0;
       for (int i = 0; i < my_mt; ++i) {
+        tr.mark(0x10);
         mbar_wait_backoff(a_free, (i & 1) ^ 1);                     // every MMA of the previous row tile has retired
+        tr.mark(0x11);
         store_a();
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_ready);
+        tr.mark(0x12);
         if (i + 1 < my_mt) load_a((int)blockIdx.x + (i + 1) * (int)gridDim.x);      // in flight during this row tile's B stream
         for (int q = 0; q < per_mt; ++q, ++g) {
           if (g + kXgPPBAhead < total) copy_b(g + kXgPPBAhead);
@@ -1211,10 +1227,11 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs g
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(full(g & 3));
+          if ((q & 3) == 3) tr.mark(0x20);                           // B stages of one column tile delivered (nst = 4)
         }
       }
     }
-  } else if (warp == kXgPPLoaders + 4) {
+  } else if (warp == G::MMA_WARP) {
     // ------------------------------------------------------------------------------------------------ MMA issue
     int g = 0, lt = 0;
     for (int i = 0; i < my_mt; ++i) {
@@ -1227,6 +1244,7 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs g
         const uint32_t d_main = tmem_base + (uint32_t)ab * 256u, d_small = d_main + 128u;
         mbar_wait_w(acc_empty(ab), ((lt >> 1) & 1) ^ 1);
         tc_fence_after();
+        tr.mark(0x10);
         for (int it = 0; it < nst; ++it, ++g) {
           const int s = g & 3;
           mbar_wait_w(full(s), (g >> 2) & 1);
@@ -1244,6 +1262,7 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs g
           umma_commit_w(empty(s));
         }
         umma_commit_w(acc_full(ab));
+        tr.mark(0x20);
       }
       umma_commit_w(a_free);                                        // the resident A images may be rewritten
     }
@@ -1255,21 +1274,23 @@ __global__ void __launch_bounds__(kXgPPThreads, 1) xg_as_kernel(const GemmArgs g
       for (int nt = 0; nt < ntn; ++nt, ++lt) {
         const int ab = lt & 1;
         XgTile t;
-        t.sbase = sbase + kXgPPPatch; t.tmem_base = tmem_base + (uint32_t)ab * 256u;
+        t.sbase = sbase + G::PATCH; t.tmem_base = tmem_base + (uint32_t)ab * 256u;
         t.m0 = mt * kXgBM; t.n0 = nt * kXgBN; t.warp = warp - kXgPPLoaders; t.lane = lane;
         mbar_wait_backoff(acc_full(ab), (lt >> 1) & 1);
         tc_fence_after();
-        if (LINEAR) xg_epilogue_linear<PARTS>(la, t, 4);
-        else xg_epilogue_gemm<PARTS>(ga, t, 4, true);
+        tr.mark(0x40);
+        if (LINEAR) xg_epilogue_linear<PARTS>(la, t, 16 / G::EPI);
+        else xg_epilogue_gemm<PARTS>(ga, t, 16 / G::EPI, true);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc_empty(ab));
+        tr.mark(0x50);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kXgPPLoaders + 4) tmem_dealloc<512>(tmem_base);
+  if (warp == G::MMA_WARP) tmem_dealloc<512>(tmem_base);
 }
 #endif
 
