@@ -892,9 +892,11 @@ static int gemm_f32_impl(const float* A, long long sam, long long sak, const flo
       return 0;
     }
     if (x.any() && !xg_fits(M, N, K)) return T3D_ERR_SHAPE;      // the extras exist on the tensor-core path (and skinny_k) only
-    if (!x.any() && M >= 4096 && N <= kSkinnyMax && sak == 1 && sbk == 1 && sbn != 1 && K % 4 == 0 && K <= 1024 && al16(A) && sam % 4 == 0 &&
+    // (either layout of the small operand: dgrad passes W as [N, K] rows, a forward layer with <= 16 outputs -- inst_seg conv10,
+    // 128 -> 2 -- as [K, N]; the kernel stages it in shared memory by element strides)
+    if (!x.any() && M >= 4096 && N <= kSkinnyMax && sak == 1 && K % 4 == 0 && K <= 1024 && al16(A) && sam % 4 == 0 && splitk == 1 &&
         sizeof(float) * (size_t)N * K <= kSkinnySmemMax) {
-      skinny_n_kernel<<<sms * 8, 256, sizeof(float) * (size_t)N * K, S(stream)>>>(A, sam, B, sbn, bias, C, ldc, M, N, K);
+      skinny_n_kernel<<<sms * 8, 256, sizeof(float) * (size_t)N * K, S(stream)>>>(A, sam, B, sbn, bias, C, ldc, M, N, K, sbk);
       T3D_CHECK_LAUNCH();
       return 0;
     }
@@ -936,8 +938,10 @@ static int gemm_f32_impl(const float* A, long long sam, long long sak, const flo
                  x.a_scale, x.a_shift};
     const dim3 grid((unsigned)ntm * ntn, nz);
     // CTA-pair kernel (256 x 256 tiles, xgemm.cuh) for the engines with at most two operand pieces: every shape with at
-    // least 256 rows and columns except the K <= 128 forward / dgrad layers, which stay on the persistent kernels
-    const bool pair = xg_parts() <= 2 && M >= 256 && N >= 256 && !(ak && nz == 1 && sk == 1 && K <= 128 && xg_pre_ok(M, N, K, ws, ws_bytes));
+    // least 256 rows and columns except the K <= 128 forward / dgrad layers, which stay on the persistent kernels,
+    // and the problems with fewer pair CTAs than SMs (FC heads: a handful of 256 x 256 tiles each walking the whole K range alone)
+    const bool pair = xg_parts() <= 2 && M >= 256 && N >= 256 && !(ak && nz == 1 && sk == 1 && K <= 128 && xg_pre_ok(M, N, K, ws, ws_bytes)) &&
+                      (long long)((M + 255) / 256) * ((N + 255) / 256) * 2 * nz >= xg_num_sms();
     const bool pre = !pair && ak && nz == 1 && sk == 1 && xg_pre_ok(M, N, K, ws, ws_bytes);
     if (pair) {
       if (x.a_scale && K % kXgBK != 0) return T3D_ERR_SHAPE;
