@@ -42,7 +42,8 @@ def _ulp_err(C, a, b):
     return float(((C.double() - ref).abs() / scale).max()) / 2.0 ** -24
 
 
-SHAPES = [(256, 128, 128), (384, 256, 96), (1000, 200, 333), (128, 64, 32), (130, 515, 70), (4096, 512, 256), (4500, 200, 333)]
+SHAPES = [(256, 128, 128), (384, 256, 96), (1000, 200, 333), (128, 64, 32), (130, 515, 70), (4096, 512, 256), (4500, 200, 333),
+          (64, 512, 8192), (100, 130, 5000)]      # M < 128 with a long reduction: the weight gradient of a 64-channel layer
 
 
 @pytest.mark.parametrize('a_unit_k,b_unit_k', [(True, False), (True, True), (False, False), (False, True)])
@@ -60,8 +61,13 @@ def test_gemm_layouts_fp32_accurate(M, N, K, a_unit_k, b_unit_k):
     e_tc, e_simt = _ulp_err(C, a, b), _ulp_err(C0, a, b)
     # the bar is the CUDA-core fp32 SGEMM itself (K sequential roundings): measured 12.8 ulp of sum|a||b| at K = 128 on the
     # worst of 32768 outputs, against 13.7 for the split
-    assert e_tc < max(4.0, 1.5 * e_simt), 'tcgen05 bf16x3: %.2f ulp of sum|a||b| (CUDA-core SGEMM: %.2f)' % (e_tc, e_simt)
-    assert torch.equal(Cb, C + bias)
+    # (reductions longer than one 2048-deep chunk add the tensor core's truncating accumulation, ~0.5 ulp per K = 16 step inside
+    # a chunk: 68 ulp against 45 for the SGEMM at K = 5000, held to 2 x there)
+    assert e_tc < max(4.0, (1.5 if K <= 2048 else 2.0) * e_simt), 'tcgen05 bf16x3: %.2f ulp of sum|a||b| (CUDA-core SGEMM: %.2f)' % (e_tc, e_simt)
+    if K <= 2048:
+        assert torch.equal(Cb, C + bias)
+    else:      # K ranges beyond 2048 are chunked and summed with atomics: the order of the partial sums varies from call to call
+        assert float(((Cb - bias - C).abs() / (a.double().abs() @ b.double().abs()).float()).max()) < 1e-6
 
 
 @pytest.mark.parametrize('splitk', [2, 7, 33])

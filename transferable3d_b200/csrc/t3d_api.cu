@@ -76,7 +76,9 @@ static int xg_prepare(Kern kern) {      // opt in to 97 KB of dynamic shared mem
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   return (int)e;
 }
-static inline bool xg_fits(int M, int N, int K) { return g_f32_engine != 0 && M >= 128 && N >= 64 && K >= 32; }
+// (M in [64, 128) with a long reduction -- the weight gradient of a 64-channel layer over B*N rows -- runs as a half-empty row
+// tile: 0.23 ms against 1.39 ms on the CUDA-core kernel for [64 x 512] over 524288 rows)
+static inline bool xg_fits(int M, int N, int K) { return g_f32_engine != 0 && (M >= 128 || (M >= 64 && K >= 4096)) && N >= 64 && K >= 32; }
 
 // B_PRE path: forward / dgrad with the small operand pre-split once per call into the caller's workspace (xgemm.cuh)
 static inline bool xg_pre_ok(int M, int N, int K, const void* ws, size_t ws_bytes) {
