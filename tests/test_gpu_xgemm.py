@@ -272,3 +272,33 @@ def test_tc2_pair_kernel_layouts(M, N, K, a_unit_k, b_unit_k):
     for name, out in (('plain', C), ('bias', Cb - bias), ('splitk', Cs)):
         err = float(((out.double() - ref).abs() / scale).max())
         assert err < 3e-5, (name, err)
+
+
+@pytest.mark.parametrize('act', [None, 'relu', 'tanh'])
+def test_linear_epilogues_tc2_pair_kernel(act):
+    """t3d_linear_f32 on the CTA-pair kernel (engine tc2, N >= 256, grid >= one CTA per SM): bias, per-group bias, row mask,
+    activation, group max (aligned and ragged groups), ragged N -- against float64."""
+    rt = _rt()
+    G, R, K, N = 80, 256, 192, 333                     # 80 row tiles of 256 x 2 column tiles = 320 CTAs
+    M = G * R
+    g = torch.Generator(device='cuda').manual_seed(13)
+    x = torch.randn(M, K, generator=g, device='cuda')
+    w = torch.randn(K, N, generator=g, device='cuda') * 0.1
+    b = torch.randn(N, generator=g, device='cuda')
+    gb = torch.randn(G, N, generator=g, device='cuda')
+    rm = (torch.rand(M, generator=g, device='cuda') < 0.5).float()
+    pre = (x.double() @ w.double() + b.double()).view(G, R, N) + gb.double()[:, None, :]
+    f = {None: lambda v: v, 'relu': torch.relu, 'tanh': torch.tanh}[act]
+    ref = (f(pre) * rm.double().view(G, R, 1)).view(M, N)
+    scale = (x.double().abs() @ w.double().abs()).max()
+    with rt.f32_engine('tc2'):
+        y, _ = rt.linear(x, w, b, act, gbias=gb, rows_per_group=R, rowmask=rm)
+        assert float((y.double() - ref).abs().max()) < 3e-5 * float(scale)
+        if act == 'relu':
+            y2, gmax = rt.linear(x, w, b, act, gbias=gb, rows_per_group=R, rowmask=rm, gmax_groups=G)
+            _, gmax_ragged = rt.linear(x[:64 * 300], w, b, act, rows_per_group=300, gmax_groups=64, want_y=False)
+            assert torch.equal(y2, y)
+            assert torch.equal(gmax, y.view(G, R, N).max(dim=1).values.clamp_min(0.0))
+            ref_r = torch.relu(x[:64 * 300].double() @ w.double() + b.double()).view(64, 300, N).max(dim=1).values
+            assert float((gmax_ragged.double() - ref_r).abs().max()) < 3e-5 * float(scale)
+    assert rt.get_f32_engine() == 'tc'

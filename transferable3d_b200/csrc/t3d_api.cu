@@ -151,6 +151,21 @@ extern "C" int t3d_linear_f32_ws(const float* X, int ldx, const float* W, int ld
     const int parts = xg_parts();
     XgOperands o{X, ldx, W, ldw, M, N, K, (K + kXgBK - 1) / kXgBK * kXgBK, xg_aligned16(X, ldx) ? 1 : 0, 0, ntn, g_trace, nullptr, 0};
     const dim3 grid((unsigned)ntm * ntn, 1);
+    // CTA-pair kernel (256 x 256 tiles, no pre-split pass) for the engines with at most two operand pieces, when the grid
+    // fills the machine and the A-stationary kernel does not apply (measured in the cfg5 step, where the frozen branches run
+    // through this call: 15.5 -> 15.3 ms; restricted to K > 128: 15.4)
+    const int ntm2 = (M + 255) / 256, ntn2 = (N + 255) / 256;
+    if (parts <= 2 && M >= 256 && N >= 256 && (long long)ntm2 * ntn2 * 2 >= xg_num_sms() &&
+        !(xg_pre_ok(M, N, K, ws, ws_bytes) && xg_use_as(K, ntn, true, Y != nullptr))) {
+      static int prepared_pair[kMaxDevices] = {0};
+      if (int e = once_per_device(prepared_pair, [] { return xg_prepare(xlinear_pair_kernel<2>) | xg_prepare(xlinear_pair_kernel<1>); })) return e;
+      o.ntn = ntn2;
+      const dim3 pgrid((unsigned)ntm2 * ntn2 * 2, 1);
+      if (parts == 2) xlinear_pair_kernel<2><<<pgrid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+      else xlinear_pair_kernel<1><<<pgrid, kXgThreads, kXgSmemBytes, S(stream)>>>(a, o);
+      T3D_CHECK_LAUNCH();
+      return 0;
+    }
     if (xg_pre_ok(M, N, K, ws, ws_bytes)) {
       o.bpre = reinterpret_cast<const uint8_t*>(ws);
       o.nkb = (K + 63) / 64;

@@ -684,11 +684,12 @@ __global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xgemm_pre_kernel(con
 // no pre-split pass.  One accumulator (the products of the low pieces are summed into the main one): 256 TMEM columns per
 // CTA, so two clusters share an SM pair and one's epilogue runs under the other's main loop.  The loaders of the peer arrive
 // remotely on the leader's full barriers; the leader's commits are multicast to both CTAs.
+// main loop of one pair tile; returns in every warp once both CTAs' accumulators are complete (acc_full).  Every thread then
+// runs its epilogue and calls xg_pair_finish().
 template <bool A_UNIT_K, bool B_UNIT_K, int PARTS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXgThreads, kXgMinBlocks) xgemm_pair_kernel(const GemmArgs a, const XgOperands o) {
+__device__ __forceinline__ void xg_pair_mainloop(const XgOperands& o, uint8_t* smem_raw, XgTile& t, XgTracer& tr) {
   static_assert(PARTS <= 2, "xgemm_pair: one accumulator");
-  extern __shared__ uint8_t xg_smem[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)xg_smem + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -715,9 +716,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXgThreads, kXgMinBl
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kXgBars + 40);
-  XgTile t;
   t.sbase = sbase; t.tmem_base = tmem_base; t.m0 = m0; t.n0 = n0; t.warp = warp; t.lane = lane;
-  XgTracer tr;
   tr.init(o.trace, warp == 0 ? 0 : (warp == 4 ? 1 : 2), lane == 0 && (warp == 0 || warp == 4 || warp == 8));
   if (tr.buf != nullptr) tr.buf[tr.n++] = ((unsigned long long)t_entry << 8) | 0x01;      // kernel entry
   tr.mark(0x02);
@@ -758,13 +757,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXgThreads, kXgMinBl
     }
     umma_commit_pair_w(acc_full, 3);
   }
-  xg_epilogue_gemm<1>(a, t, 4, blockIdx.y == 0);
+}
+__device__ __forceinline__ void xg_pair_finish(const XgTile& t, XgTracer& tr) {
   tr.mark(0x50);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                                            // neither CTA leaves while its partner may still signal it
   tr.mark(0x60);
-  if (warp == 8) tmem_dealloc_pair<256>(tmem_base);
+  if (t.warp == 8) tmem_dealloc_pair<256>(t.tmem_base);
+}
+
+template <bool A_UNIT_K, bool B_UNIT_K, int PARTS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXgThreads, kXgMinBlocks) xgemm_pair_kernel(const GemmArgs a, const XgOperands o) {
+  extern __shared__ uint8_t xg_smem[];
+  XgTile t;
+  XgTracer tr;
+  xg_pair_mainloop<A_UNIT_K, B_UNIT_K, PARTS>(o, xg_smem, t, tr);
+  xg_epilogue_gemm<1>(a, t, 4, blockIdx.y == 0);
+  xg_pair_finish(t, tr);
 }
 
 // ---- t3d_linear_f32 (same contract as linear_f32_kernel, simt_ops.cuh): Y = act(X.W + bias + gbias[row / rows_per_group])
@@ -780,7 +790,7 @@ __device__ __forceinline__ void xg_epilogue_linear(const LinearArgs& a, const Xg
     const bool one_group = a.gmax && (a.rows_per_group % kXgBM == 0) && (t.m0 + kXgBM <= a.M);
 #pragma unroll 1
     for (int ch = 0; ch < nchunks; ++ch) {
-      const int c0 = (nchunks == 2 ? (t.warp >> 2) * 64 : 0) + ch * 32;
+      const int c0 = (t.warp >> 2) * (32 * nchunks) + ch * 32;
       float v[32];
       xg_acc32<PARTS>(t, c0, v);
       // bias, then the per-group bias: 32 consecutive floats each, fetched as eight independent 128-bit loads before the
@@ -859,6 +869,16 @@ __global__ void __launch_bounds__(kXgThreads, kXgMinBlocks) xlinear_pre_kernel(c
   xg_mainloop<true, false, PARTS, true>(o, xg_smem, t);
   xg_epilogue_linear<PARTS>(a, t);
   xg_finish(t);
+}
+// CTA-pair variant of t3d_linear_f32 (X k-contiguous, W [K, N]) for the engines with at most two operand pieces
+template <int PARTS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kXgThreads, kXgMinBlocks) xlinear_pair_kernel(const LinearArgs a, const XgOperands o) {
+  extern __shared__ uint8_t xg_smem[];
+  XgTile t;
+  XgTracer tr;
+  xg_pair_mainloop<true, false, PARTS>(o, xg_smem, t, tr);
+  xg_epilogue_linear<1>(a, t, 4);
+  xg_pair_finish(t, tr);
 }
 // ---- persistent variant for forward / dgrad (k-contiguous A, pre-split B) ------------------------------------------------
 // One CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The per-tile costs of the one-tile kernel that the
