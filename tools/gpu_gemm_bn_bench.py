@@ -9,6 +9,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from transferable3d_b200._lib import ptr, stream, call, gemm_workspace   # noqa: E402
+from transferable3d_b200 import runtime as rt   # noqa: E402
+
+rt.set_f32_engine(os.environ.get('ENGINE', 'tc'))
 
 M = 524288
 dev = 'cuda:0'
