@@ -11,8 +11,11 @@
 // one fp32 accumulator, the two small ones first; the first conv6' block of tile i+1 is issued under the e7 epilogue of
 // tile i.  16 epilogue warps (4 lane quarters x 4 column quarters of a K-block).
 // TMEM: R6 = cols 0..127 (conv6' block), R89 = 128..255 (conv8, conv9), R7 = 256..511 (conv7).
-// Weight chunks (fp16 hi / lo images, 16 KB) stream through a 5-stage ring, each CTA of the cluster fetching half of
-// every chunk and multicasting it; the input tile (stage 1's hi + lo point_feat images, 32 KB) and gbias are double-buffered.
+// The two CTAs of a cluster are one tcgen05 cta_group::2 pair (as in seg_stage2_pair.cuh): M = 256 = their two tiles, every weight
+// chunk (fp16 hi / lo image, 16 KB) SPLIT between the two shared memories (rows 64 r .. 64 r + 63 in CTA r: an 8 KB ring stage,
+// 10 stages), the leader issues every MMA / commit (multicast to both CTAs' barriers), the peer's epilogue warps arrive remotely on
+// the leader's barriers and two relay lanes forward its TMA completions.  The input tile (stage 1's hi + lo point_feat images,
+// 32 KB) and gbias are double-buffered.
 #pragma once
 #include "common.cuh"
 #include "chain_max.cuh"
@@ -35,11 +38,12 @@ struct Seg2XArgs {
 };
 
 struct Seg2XSmem {
-  static constexpr int STAGES = 5;
+  static constexpr int STAGES = 10;
+  static constexpr int STAGE_BYTES = kChunkBytes / 2;   // this CTA's 64 rows of a chunk
   static constexpr int IN = 0;                          // 2 x 32 KB
   static constexpr int SL = 65536;                      // 2 slots x 32 KB
   static constexpr int RING = SL + 65536;
-  static constexpr int GB = RING + STAGES * kChunkBytes;   // 2 x 512 fp32
+  static constexpr int GB = RING + STAGES * STAGE_BYTES;   // 2 x 512 fp32
   static constexpr int FL = GB + 2 * 2048;
   static constexpr int LX = FL + ((kSeg2XFloats * 4 + 15) / 16) * 16;   // [128][3][2] fp32 partial logits
   static constexpr int BARS = LX + 128 * 24;
@@ -50,7 +54,9 @@ struct Seg2XSmem {
 };
 static_assert(Seg2XSmem::TOTAL + 1024 <= 232448, "seg_stage2_x2: shared memory budget");
 
-constexpr int kSeg2XThreads = 640;   // warp 0 weight producer, 1 MMA, 2 TMEM alloc, 3 input producer, 4-19 epilogue
+constexpr int kSeg2XThreads = 640;   // warp 0 weight producer, 1 MMA (leader) / ring relay (peer), 2 TMEM alloc (+ input relay in the peer),
+                                     // 3 input producer, 4-19 epilogue
+static_assert(kClusterSize == 2, "seg_stage2_x2: one CTA pair per cluster");
 
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThreads, 1) seg_stage2_x2_kernel(const Seg2XArgs args) {
   using L = Seg2XSmem;
@@ -61,7 +67,9 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
-  constexpr uint16_t kAllCtas = (1u << kClusterSize) - 1;
+  const bool leader = crank == 0;
+  constexpr uint16_t kBoth = 3;
+  constexpr uint32_t kStageBytes = L::STAGE_BYTES;
 
   const uint32_t bar0 = sbase + L::BARS;
   auto ring_full = [&](int s) { return bar0 + 8u * s; };
@@ -83,16 +91,21 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
   const int cend = (int)(((long long)num_tiles * (cl + 1)) / ncl);
   const int iters = (cend - cbegin + kClusterSize - 1) / kClusterSize;
   auto tile_of = [&](int i) { return min(cbegin + i * kClusterSize + (int)crank, cend - 1); };
+  // epilogue -> MMA-warp signals: the MMA warp lives in the leader CTA
+  auto arrive_mma = [&](uint32_t bar) { if (leader) mbar_arrive(bar); else mbar_arrive_remote(bar, 0); };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < ST; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), kClusterSize); }
-    for (int b = 0; b < 2; ++b) { mbar_init(in_ready(b), 1); mbar_init(in_free(b), 1); mbar_init(sl_ready(b), 16); mbar_init(sl_free(b), 1); }
-    mbar_init(r6_full, 1); mbar_init(r6_empty, 16);
-    mbar_init(r7_full, 1); mbar_init(r7_empty, 16);
-    mbar_init(r89_full, 1); mbar_init(r89_empty, 16);
+    // the leader's ring_full / in_ready also count the peer's forwarded completion; its epilogue-side barriers count the 16
+    // warps of both CTAs; everything the MMA warp signals is one multicast commit per CTA
+    const uint32_t fwd = leader ? 2 : 1;
+    for (int s = 0; s < ST; ++s) { mbar_init(ring_full(s), fwd); mbar_init(ring_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(in_ready(b), fwd); mbar_init(in_free(b), 1); mbar_init(sl_ready(b), 32); mbar_init(sl_free(b), 1); }
+    mbar_init(r6_full, 1); mbar_init(r6_empty, 32);
+    mbar_init(r7_full, 1); mbar_init(r7_empty, 32);
+    mbar_init(r89_full, 1); mbar_init(r89_empty, 32);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(sbase + L::TMEM_SLOT);
+  if (warp == 2) tmem_alloc_pair<512>(sbase + L::TMEM_SLOT);
   {
     const float* fsrc = reinterpret_cast<const float*>(args.arena + (size_t)kSeg2XChunks * kChunkBytes);
     float* fdst = reinterpret_cast<float*>(smem + L::FL);
@@ -105,16 +118,14 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L::TMEM_SLOT);
 
   if (warp == 0) {
-    // ================================================================ weight producer (half of every chunk, multicast)
+    // ================================================================ weight producer: this CTA's 64 rows of every chunk, kept local
     if (lane == 0) {
-      constexpr uint32_t kHalf = kChunkBytes / kClusterSize;
       uint32_t it = 0;
       auto push = [&](int c) {
         const int s = it % ST;
         mbar_wait(ring_empty(s), ((it / ST) & 1) ^ 1);
-        mbar_arrive_expect_tx(ring_full(s), kChunkBytes);
-        bulk_g2s_mc(sbase + L::RING + s * kChunkBytes + crank * kHalf, args.arena + (size_t)c * kChunkBytes + crank * kHalf,
-                    kHalf, ring_full(s), kAllCtas);
+        mbar_arrive_expect_tx(ring_full(s), kStageBytes);
+        bulk_g2s(sbase + L::RING + s * kStageBytes, args.arena + (size_t)c * kChunkBytes + crank * kStageBytes, kStageBytes, ring_full(s));
         ++it;
       };
       // The stream follows the MMA warp's CONSUMPTION order, not the arena order: the first conv6' block of tile i + 1
@@ -125,6 +136,24 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
         for (int c = 2; c < kC8; ++c) push(c);
         if (i + 1 < iters) { push(0); push(1); }
         for (int c = kC8; c < kSeg2XChunks; ++c) push(c);
+      }
+    }
+  } else if (!leader && warp == 1) {
+    // ================================================================ peer: relay the ring's TMA completions to the leader's MMA warp
+    if (lane == 0) {
+      const uint32_t total = (uint32_t)iters * (uint32_t)kSeg2XChunks;
+      for (uint32_t it = 0; it < total; ++it) {
+        const int s = it % ST;
+        mbar_wait(ring_full(s), (it / ST) & 1);
+        mbar_arrive_remote(ring_full(s), 0);
+      }
+    }
+  } else if (!leader && warp == 2) {
+    // ================================================================ peer: relay "input tile landed" to the leader's MMA warp
+    if (lane == 0) {
+      for (int i = 0; i < iters; ++i) {
+        mbar_wait(in_ready(i & 1), (i >> 1) & 1);
+        mbar_arrive_remote(in_ready(i & 1), 0);
       }
     }
   } else if (warp == 3) {
@@ -141,21 +170,22 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (whole warp converged, one elected lane issues)
+    // ================================================================ MMA issuer (leader: one instruction drives both SMs; whole warp
+    // converged, one elected lane issues)
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
     uint32_t it = 0, n_r6 = 0, n_r89 = 0, n_sl[2] = {0, 0};
-    const uint32_t idesc = make_idesc_f16(128, 128);
+    const uint32_t idesc = make_idesc_f16(256, 128);
     Tracer tr; tr.init(lane == 0 ? args.trace : nullptr, 1);
     auto ring_wait = [&](uint32_t j) -> uint32_t {          // chunk j of the stream has landed; returns its smem address
       const uint32_t s = j % ST;
       mbar_wait_w(ring_full(s), (j / ST) & 1);
-      return sbase + L::RING + s * kChunkBytes;
+      return sbase + L::RING + s * kStageBytes;
     };
-    auto ring_release = [&](uint32_t j) { umma_commit_mc_w(ring_empty(j % ST), kAllCtas); };
+    auto ring_release = [&](uint32_t j) { umma_commit_pair_w(ring_empty(j % ST), kBoth); };
     auto mma4 = [&](uint32_t d, uint32_t a_addr, uint32_t b_addr, bool first) {
       const uint64_t ad = make_sdesc_k128(a_addr), bd = make_sdesc_k128(b_addr);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_bf16_w(d, ad + 2u * k, bd + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
+      for (int k = 0; k < 4; ++k) umma_bf16_pair_w(d, ad + 2u * k, bd + 2u * k, idesc, (first && k == 0) ? 0u : 1u);
     };
     // one K-block (hi at a, lo at a + 16 KB) against the next [lo, hi] chunk pair: a_hi.w_lo, a_lo.w_hi, a_hi.w_hi
     auto kblock = [&](uint32_t d, uint32_t a, bool first) {
@@ -181,14 +211,14 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
         tc_fence_after();
         tr.mark(0x20 + nb);
         kblock(tm + kR6, in_addr, true);
-        umma_commit_w(r6_full); n_r6++;
+        umma_commit_pair_w(r6_full, kBoth); n_r6++;
       };
       // conv7 K-block kbg (slot kbg & 1): chunks [lo rows 0-127][lo rows 128-255][hi rows 0-127][hi rows 128-255]
       auto c7 = [&](int kbg) {
         const int b = kbg & 1;
         slot_wait(b);
         if (kbg == 0) { mbar_wait_w(r7_empty, (i & 1) ^ 1); tc_fence_after(); }
-        if (kbg == 7) umma_commit_w(in_free(ib));        // e6(3) has read its gbias, every conv6' MMA of the tile is issued
+        if (kbg == 7) umma_commit_pair_w(in_free(ib), kBoth);        // e6(3) has read its gbias, every conv6' MMA of the tile is issued
         tr.mark(0x30 + kbg);
         const uint32_t a = sbase + L::SL + b * 32768;
         const uint32_t wl0 = ring_wait(it), wl1 = ring_wait(it + 1);
@@ -205,8 +235,8 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
         mma4(tm + kR7 + 128, a, wh1, false);
         ring_release(it + 3);
         it += 4;
-        umma_commit_w(sl_free(b));
-        if (kbg == 7) umma_commit_w(r7_full);
+        umma_commit_pair_w(sl_free(b), kBoth);
+        if (kbg == 7) umma_commit_pair_w(r7_full, kBoth);
       };
       if (!pre) {
         mbar_wait_w(in_ready(ib), (i >> 1) & 1);
@@ -229,20 +259,20 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
         if (kb == 0) { mbar_wait_w(r89_empty, (n_r89 & 1) ^ 1); tc_fence_after(); }
         tr.mark(0x40 + kb);
         kblock(tm + kR89, sbase + L::SL + b * 32768, kb == 0);
-        umma_commit_w(sl_free(b));
+        umma_commit_pair_w(sl_free(b), kBoth);
       }
-      umma_commit_w(r89_full); n_r89++;
+      umma_commit_pair_w(r89_full, kBoth); n_r89++;
       // conv9: the two K-blocks of the conv8 activation sit in the two slots
       slot_wait(0);
       mbar_wait_w(r89_empty, (n_r89 & 1) ^ 1);
       tc_fence_after();
       tr.mark(0x50);
       kblock(tm + kR89, sbase + L::SL, true);
-      umma_commit_w(sl_free(0));
+      umma_commit_pair_w(sl_free(0), kBoth);
       slot_wait(1);
       kblock(tm + kR89, sbase + L::SL + 32768, false);
-      umma_commit_w(r89_full); n_r89++;
-      umma_commit_w(sl_free(1));
+      umma_commit_pair_w(r89_full, kBoth); n_r89++;
+      umma_commit_pair_w(sl_free(1), kBoth);
       tr.mark(0x51);
     }
   } else if (warp >= 4) {
@@ -262,7 +292,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
     auto release_acc = [&](uint32_t empty_bar) {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty_bar);
+      if (lane == 0) arrive_mma(empty_bar);
     };
     // this warp's 16 columns [sub*16, +16) of a K-block: x = acc * inv + bias, ReLU, f16 hi / lo images of slot b
     auto store16 = [&](const uint32_t (&v)[16], float inv, uint32_t bias, int b) {
@@ -285,7 +315,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(sl_ready(b));
+      if (lane == 0) arrive_mma(sl_ready(b));
     };
 
     for (int i = 0; i < iters; ++i) {
@@ -376,7 +406,7 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kSeg2XThr
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (warp == 2) tmem_dealloc_pair<512>(tmem_base);
 }
 
 }  // namespace t3d
