@@ -135,11 +135,12 @@ def test_boxpc_train_step_bf16_engine(built_lib):
 
 def test_boxpc_train_step_tc2_engine(built_lib):
     """The three-product engine (`tc2`: bf16 x 2 split, operand residual <= 2^-18; `bench.py --f32-engine tc2`) against the fp32
-    oracle on a batch without pooled near-ties: loss within 1e-4 (the north star's TF32 / fp32-mode tolerance) and every
-    weight gradient within relative Frobenius error 5e-3 / cosine 0.99999 (measured: 2.4e-5 .. 3.9e-5 for conv4 and the FC
-    layers, 1.3e-3 .. 1.4e-3 for the three layers whose gradient passes through ReLUs that the 1e-5 operand error flips near
-    zero; cosine >= 0.999999) -- two orders tighter than the one-product bf16 engine, at half the tensor-core work of the
-    default six-product engine."""
+    oracle on a batch without pooled near-ties: loss within 1e-4 (the north star's TF32 / fp32-mode tolerance); the weight
+    gradients of conv4 and the FC layers within relative Frobenius error 5e-4 / cosine 0.999999 (measured 2.4e-5 .. 3.9e-5);
+    the three layers below, whose gradient passes through ReLUs (and pooled arg-maxes with a top-2 gap under the engine's
+    1e-5 operand error) that flip near zero, within the whole-tensor bound of assert_grad_close, 1e-2 / 0.9999 (measured
+    1.3e-3 .. 4.6e-3 from run to run: the flips follow the summation order of the batch statistics, which are atomics).  One
+    to two orders tighter than the one-product bf16 engine, at half the tensor-core work of the default six-product engine."""
     from oracle import train_boxpc as otb
     from transferable3d_b200 import runtime as rt
     B, N = 16, 2048
@@ -165,5 +166,8 @@ def test_boxpc_train_step_tc2_engine(built_lib):
         report.append((name.split('/', 1)[1], float('%.3g' % rel), round(cos, 7)))
     print('tc2 engine, gradient (relative Frobenius error, cosine) per tensor:', report)
     for name, rel, cos in report:
-        assert rel < 5e-3 and cos > 0.99999, (name, rel, cos)
+        if name.split('/')[0] in ('conv-reg1', 'conv-reg2', 'conv-reg3'):
+            assert rel < 1e-2 and cos > 0.9999, (name, rel, cos)
+        else:
+            assert rel < 5e-4 and cos > 0.999999, (name, rel, cos)
     assert rt.get_f32_engine() == 'tc'
