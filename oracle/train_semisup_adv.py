@@ -7,9 +7,10 @@ baseline may import this.
 
 What the reference builds but the step never evaluates (TF prunes it from the fetches) is not restated: the
 real/fake "D" branches and D_loss (:326-354; never minimised, in no summary), get_iou_summary (:414-416,
-metrics-only tf.py_func around the missing box_util.box3d_iou).  With SEMI_REFINE_USING_BOXPC_DELTA_NUM = 1 the
-"fake" branch and the loop branch evaluate BoxPC on the same box with shared weights, so boxpc_fit_prob is the
-same tensor whether or not SEMI_BOXPC_MIN_FIT_LOSS_AFT_REFINE is set (:355,390-391).
+metrics-only tf.py_func around the missing box_util.box3d_iou).  The "fake" BoxPC branch on the un-refined box
+(:339-343) IS restated: its fit probability feeds the loss unless SEMI_BOXPC_MIN_FIT_LOSS_AFT_REFINE (:355, :390-391;
+the two differ as soon as SEMI_REFINE_USING_BOXPC_DELTA_NUM > 1 -- found by running the reference's own train() graph,
+tests/golden/reference_cases.py).
 """
 import numpy as np
 import torch
@@ -94,7 +95,12 @@ def _run_graph_training(vs, FLAGS, pc, one_hot, box2D, img_dim, bn_decay):
     tot_c = torch.zeros_like(curr_box[0])
     tot_s = torch.zeros_like(curr_box[1])
     tot_a = torch.zeros_like(curr_box[2])
-    ep = None
+    # the "fake" branch on the un-refined box (:339-343, :355): its fit probability is the one the loss sees unless
+    # SEMI_BOXPC_MIN_FIT_LOSS_AFT_REFINE re-reads it after the loop (:390-391); with one refinement step both are the same tensor
+    with vs.variable_scope('D_boxpc_branch'):
+        _, ep = boxpc_sunrgbd.get_model((curr_box, pc), False, one_hot, vs,
+                                        use_one_hot_vec=getattr(FLAGS, 'use_one_hot_boxpc', False), c=FLAGS)
+    fake_fit_logits = ep['boxpc_fit_logits']
     for _ in range(int(FLAGS.SEMI_REFINE_USING_BOXPC_DELTA_NUM)):
         with vs.variable_scope('D_boxpc_branch'):
             _, ep = boxpc_sunrgbd.get_model((curr_box, pc), False, one_hot, vs,
@@ -103,8 +109,10 @@ def _run_graph_training(vs, FLAGS, pc, one_hot, box2D, img_dim, bn_decay):
         dc, da, ds = ep['boxpc_delta_center'] * w.unsqueeze(1), ep['boxpc_delta_angle'] * w, ep['boxpc_delta_size'] * w.unsqueeze(1)
         curr_box = (curr_box[0] - dc, curr_box[1] - ds, curr_box[2] - da)
         tot_c, tot_s, tot_a = tot_c + dc, tot_s + ds, tot_a + da
-    end_points['boxpc_fit_prob'] = torch.softmax(ep['boxpc_fit_logits'], dim=1)[:, 1]
-    end_points['boxpc_fit_logits'] = ep['boxpc_fit_logits']
+    if FLAGS.SEMI_BOXPC_MIN_FIT_LOSS_AFT_REFINE:
+        fake_fit_logits = ep['boxpc_fit_logits']
+    end_points['boxpc_fit_prob'] = torch.softmax(fake_fit_logits, dim=1)[:, 1]
+    end_points['boxpc_fit_logits'] = fake_fit_logits
     end_points['boxpc_delta_center'] = ep['boxpc_delta_center']
     end_points['boxpc_delta_size'] = ep['boxpc_delta_size']
     end_points['boxpc_delta_angle'] = ep['boxpc_delta_angle']

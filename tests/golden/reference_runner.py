@@ -1,0 +1,157 @@
+"""Runs the reference's own Python files (from /root/reference, unmodified, where they lie) on the TF1 stand-in of
+tests/golden/tf1_shim.py.  TEST INFRASTRUCTURE: imported by make_reference_golden.py (which writes the committed fixtures
+tests/golden/ref_*.npz) and by tests/test_oracle_vs_reference_cpu.py for the live re-run when the reference is present.
+
+Modules the reference imports but does not ship / that need Python 2:
+  box_util   (frustum-pointnets train/box_util.py, absent from the reference tree): only `box3d_iou` is imported; it is
+             provided by oracle/box_util.py (a restatement of the published polygon-clipping routine) and is not called by
+             any pinned function except compute_box3d_iou (metrics, not on the compared outputs);
+  cPickle    -> pickle (sunrgbd_data/utils.py:338).
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get('T3D_REFERENCE_ROOT', '/root/reference')
+REF_DIRS = ['models', 'sunrgbd/sunrgbd_detection', 'sunrgbd/sunrgbd_data']
+REF_MODULES = ['tf_util', 'model_util', 'weak_losses', 'config', 'timer', 'utils', 'roi_seg_box3d_dataset', 'semisup_models',
+               'semisup_v1_sunrgbd', 'boxpc_sunrgbd', 'box_pc_fit_dataset', 'eval_det', 'test_semisup', 'train_boxpc',
+               'train_semisup', 'train_semisup_adv', 'train_util', 'roi_semi_dataset', 'box_util', 'cPickle', 'tensorflow']
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, 'models'))
+
+
+class Reference(object):
+    """Context manager: installs the shim + stubs, puts the reference directories on sys.path, imports on demand, and
+    removes every trace on exit (the reference's module names -- tf_util, utils, config -- must not leak into pytest)."""
+
+    def __enter__(self):
+        if ROOT not in sys.path:
+            sys.path.insert(0, ROOT)
+        if HERE not in sys.path:
+            sys.path.insert(0, HERE)
+        self._saved_modules = {k: sys.modules.get(k) for k in REF_MODULES}
+        for k in REF_MODULES:
+            sys.modules.pop(k, None)
+        self._saved_path = list(sys.path)
+        self._saved_argv = list(sys.argv)
+        sys.argv = [sys.argv[0]]
+        import tf1_shim
+        self.tf = tf1_shim.install()
+        import pickle
+        sys.modules['cPickle'] = pickle
+        from oracle import box_util as obu
+        bu = types.ModuleType('box_util')
+        bu.box3d_iou = obu.box3d_iou
+        sys.modules['box_util'] = bu
+        for d in REF_DIRS:
+            sys.path.insert(0, os.path.join(REF, d))
+        self._stdout = sys.stdout
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout = self._stdout
+        sys.path[:] = self._saved_path
+        sys.argv = self._saved_argv
+        for k in REF_MODULES:
+            sys.modules.pop(k, None)
+            if self._saved_modules[k] is not None:
+                sys.modules[k] = self._saved_modules[k]
+        return False
+
+    def quiet(self, on=True):
+        """The reference prints every layer's shape while building a graph."""
+        sys.stdout = open(os.devnull, 'w') if on else self._stdout
+
+    def mod(self, name):
+        m = importlib.import_module(name)
+        f = getattr(m, '__file__', '') or ''
+        if name not in ('box_util', 'cPickle', 'tensorflow'):
+            assert os.path.realpath(f).startswith(os.path.realpath(REF)), (name, f)
+        return m
+
+    def flags(self, **overrides):
+        """The reference's own defaults (models/config.py), as parse_special_args() returns them with no command line."""
+        cfg = self.mod('config').cfg
+        flags = cfg.parse_special_args()
+        for k, v in overrides.items():
+            setattr(flags, k, v)
+        return flags
+
+    def reset(self, variables, float_dtype=torch.float64, requires_grad=False, dropout_masks=None, feeds=None):
+        import tf1_shim
+        tf1_shim.set_float(float_dtype)
+        tf1_shim.STATE.reset(variables, trainable_grad=requires_grad)
+        tf1_shim.STATE.dropout_masks = dict(dropout_masks or {})
+        tf1_shim.STATE.feeds = list(feeds or [])
+        return tf1_shim.STATE
+
+
+def to_np(v):
+    """T / torch / nested containers -> numpy (float64 where floating)."""
+    import tf1_shim
+    if isinstance(v, tf1_shim.T):
+        v = v.t
+    if isinstance(v, torch.Tensor):
+        return v.detach().cpu().numpy()
+    if isinstance(v, (list, tuple)):
+        return [to_np(x) for x in v]
+    if isinstance(v, dict):
+        return {k: to_np(x) for k, x in v.items()}
+    return v
+
+
+def _is_literal(node):
+    import ast
+    try:
+        ast.literal_eval(node)
+        return True
+    except Exception:
+        return False
+
+
+def exec_train_graph(R, script, namespace):
+    """Executes the graph-building statements of a reference training script -- the body of
+    `with tf.Graph().as_default(): with tf.device(...):` inside its train() -- verbatim from the script's AST, in `namespace`.
+    The script's module level cannot be imported (it parses a command line, creates log directories, copies files and loads the
+    frustum pickles), so `namespace` supplies what that level would have bound (FLAGS, MODEL, BATCH_SIZE, NUM_POINT, ...);
+    the script's own top-level functions (get_bn_decay, get_learning_rate, get_scope_vars, ...) and literal constants
+    (BN_INIT_DECAY, ...) are taken from the same AST.  Returns the namespace with every local of the block bound."""
+    import ast
+    path = os.path.join(REF, 'sunrgbd/sunrgbd_detection', script)
+    tree = ast.parse(open(path).read(), filename=path)
+    pre = []
+    train_fn = None
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef):
+            if node.name == 'train':
+                train_fn = node
+            pre.append(node)
+        elif isinstance(node, ast.Assign) and _is_literal(node.value) and all(isinstance(t, ast.Name) for t in node.targets):
+            if not all(t.id in namespace for t in node.targets):
+                pre.append(node)
+    assert train_fn is not None, script
+    block = None
+    for node in train_fn.body:
+        if isinstance(node, ast.With) and 'Graph' in ast.dump(node.items[0]):
+            inner = node.body[0]
+            assert isinstance(inner, ast.With) and 'device' in ast.dump(inner.items[0]), ast.dump(inner.items[0])
+            block = inner.body
+    assert block is not None, script
+    ns = dict(namespace)
+    ns.setdefault('tf', R.tf)
+    ns.setdefault('np', np)
+    ns.setdefault('log_string', lambda s: None)
+    exec(compile(ast.Module(body=pre, type_ignores=[]), path, 'exec'), ns)
+    ns['log_string'] = namespace.get('log_string', lambda s: None)
+    exec(compile(ast.Module(body=block, type_ignores=[]), path, 'exec'), ns)
+    ns['_block_lines'] = (block[0].lineno, max(getattr(n, 'end_lineno', n.lineno) for n in block))
+    return ns
