@@ -255,6 +255,271 @@ def _semi_train_oracle(model, flags):
     return out
 
 
+# ---- case 5: the F-PointNet v1 helpers of models/model_util.py, called directly ----------------------------------------------
+def _fpn_inputs(B=4, N=700, seed=7):
+    rng = np.random.RandomState(seed)
+    b = synth.make_batch(B, N, 6, seed=seed)
+    logits = rng.standard_normal((B, N, 2))
+    logits[0, :, 1] += 3.0                 # > 512 selected points: the sample-without-replacement branch
+    logits[1, :, 1] -= 3.0                 # a handful selected: pad-with-replacement
+    logits[2, :, 0] = 10.0                 # nothing selected
+    labels = dict(mask=(rng.rand(B, N) < 0.4).astype(np.int32), center=rng.standard_normal((B, 3)), hcls=rng.randint(0, 12, B),
+                  hres=rng.uniform(-0.26, 0.26, B), scls=rng.randint(0, 8, B), sres=rng.uniform(-0.2, 0.2, (B, 3)))
+    out59 = rng.standard_normal((B, 3 + 2 * 12 + 4 * 8)) * 0.3          # the KITTI-sized head the module constants describe
+    f32 = lambda a: np.asarray(a, dtype=np.float32) if np.asarray(a).dtype.kind == 'f' else a      # float32-representable inputs
+    return weights.make_weights_model_A(seed=5), b, f32(logits), {k: f32(x) for k, x in labels.items()}, f32(out59)
+
+
+def _fpn_reference():
+    v, b, logits, lab, out59 = _fpn_inputs()
+    out = {}
+    with rr.Reference() as R:
+        tf = R.tf
+        mu = R.mod('model_util')
+        R.reset(v)
+        R.quiet()
+        c = lambda a, dt=tf.float32: tf.constant(np.asarray(a), dtype=dt)
+        ep = {}
+        np.random.seed(1234)           # mask_to_indices draws from numpy's global legacy stream (model_util.py:71-87)
+        obj, mean, ep = mu.point_cloud_masking(c(b['pc']), c(logits), ep)
+        with tf.variable_scope('tnet'):
+            delta, ep = mu.get_center_regression_net(obj, c(b['one_hot']), tf.constant(False), None, ep)
+        np.random.seed(99)
+        obj6, _, _ = mu.point_cloud_masking(c(b['pc']), c(logits), {}, xyz_only=False)
+        ep = mu.parse_output_to_tensors(c(out59), ep)
+        ep['stage1_center'] = delta + mean
+        ep['center'] = ep['center_boxnet'] + ep['stage1_center']
+        ep['mask_logits'] = c(logits)
+        loss = mu.get_loss(c(lab['mask'], tf.int32), c(lab['center']), c(lab['hcls'], tf.int32), c(lab['hres']), c(lab['scls'], tf.int32),
+                           c(lab['sres']), ep)
+        R.quiet(False)
+        pack(out, 'object_pc', obj)
+        pack(out, 'object_pc_6ch', obj6)
+        pack(out, 'mask_xyz_mean', mean)
+        pack(out, 'tnet_delta', delta)
+        pack(out, 'loss', loss)
+        for k in ('mask', 'center_boxnet', 'heading_scores', 'heading_residuals_normalized', 'heading_residuals', 'size_scores',
+                  'size_residuals_normalized', 'size_residuals'):
+            pack(out, 'ep.' + k, ep[k])
+        pack(out, 'corners_kitti', mu.get_box3d_corners(ep['center'], ep['heading_residuals'], ep['size_residuals']))
+        sun_res = c((np.random.RandomState(3).standard_normal((4, 10, 3)) * 0.1).astype(np.float32))
+        pack(out, 'corners_sunrgbd', mu.get_box3d_corners_sunrgbd(ep['center'], ep['heading_residuals'], sun_res))
+        pack(out, 'corners_helper', mu.get_box3d_corners_helper(c(lab['center']), c(lab['hres']), c(np.abs(lab['sres']) + 0.5)))
+        pack(out, 'huber', mu.huber_loss(c(lab['sres']) * 5.0, 1.0))
+        pack(out, 'g_mean_size_arr', mu.g_mean_size_arr)
+        pack(out, 'sun_mean_size_arr', mu.sun_mean_size_arr)
+    return out
+
+
+def _fpn_oracle():
+    from oracle.tf_layers import VarStore
+    from oracle import model_util as omu
+    v, b, logits, lab, out59 = _fpn_inputs()
+    t = lambda a, dt=F64: torch.as_tensor(np.asarray(a)).to(dt)
+    g32 = lambda a: np.asarray(a, dtype=np.float64)
+    from transferable3d_b200.constants import g_mean_size_arr, MEAN_DIMS_ARR
+    vs = VarStore(v, dtype=F64)
+    out = {}
+    with torch.no_grad():
+        ep = {}
+        obj, mean, ep = omu.point_cloud_masking(t(b['pc']), t(logits), ep, rng_mode='numpy_legacy', rng=np.random.RandomState(1234))
+        with vs.variable_scope('tnet'):
+            delta, ep = omu.get_center_regression_net(obj, t(b['one_hot']), False, None, ep, vs)
+        obj6, _, _ = omu.point_cloud_masking(t(b['pc']), t(logits), {}, xyz_only=False, rng_mode='numpy_legacy', rng=np.random.RandomState(99))
+        ep = omu.parse_output_to_tensors(t(out59), ep, 12, g_mean_size_arr)
+        ep['stage1_center'] = delta + mean
+        ep['center'] = ep['center_boxnet'] + ep['stage1_center']
+        ep['mask_logits'] = t(logits)
+        I = torch.int64
+        loss = omu.get_loss(t(lab['mask'], I), t(lab['center']), t(lab['hcls'], I), t(lab['hres']), t(lab['scls'], I), t(lab['sres']), ep,
+                            mean_size_arr=g_mean_size_arr)
+        pack(out, 'object_pc', obj)
+        pack(out, 'object_pc_6ch', obj6)
+        pack(out, 'mask_xyz_mean', mean)
+        pack(out, 'tnet_delta', delta)
+        pack(out, 'loss', loss)
+        for k in ('mask', 'center_boxnet', 'heading_scores', 'heading_residuals_normalized', 'heading_residuals', 'size_scores',
+                  'size_residuals_normalized', 'size_residuals'):
+            pack(out, 'ep.' + k, ep[k])
+        pack(out, 'corners_kitti', omu.get_box3d_corners(ep['center'], ep['heading_residuals'], ep['size_residuals'], g_mean_size_arr, 12))
+        sun_res = t((np.random.RandomState(3).standard_normal((4, 10, 3)) * 0.1).astype(np.float32))
+        pack(out, 'corners_sunrgbd', omu.get_box3d_corners_sunrgbd(ep['center'], ep['heading_residuals'], sun_res))
+        pack(out, 'corners_helper', omu.get_box3d_corners_helper(t(lab['center']), t(lab['hres']), t(np.abs(lab['sres']) + 0.5)))
+        pack(out, 'huber', omu.huber_loss(t(lab['sres']) * 5.0, 1.0))
+        pack(out, 'g_mean_size_arr', g32(g_mean_size_arr))
+        pack(out, 'sun_mean_size_arr', g32(MEAN_DIMS_ARR))
+    return out
+
+
+# ---- case 6: the numpy side (roi_seg_box3d_dataset helpers, eval_det, the BoxPC perturbation sampler) ------------------------
+def _scene(seed, nimg=40, classes=('bed', 'chair', 'table')):
+    """Synthetic detections (as tests/test_gpu_eval_det.py builds them); corners from the callee-independent get_3d_box below."""
+    from transferable3d_b200.constants import type_mean_size
+    from oracle import box_util as ob
+    rng = np.random.RandomState(seed)
+    pred_all, gt_all = {}, {}
+    for img in range(nimg):
+        gts, preds = [], []
+        for _ in range(rng.randint(0, 5)):
+            cls = classes[rng.randint(len(classes))]
+            size = type_mean_size[cls] * rng.uniform(0.8, 1.2, 3)
+            center = np.array([rng.uniform(-3, 3), rng.uniform(-0.5, 0.5), rng.uniform(1.5, 6)])
+            heading = rng.uniform(-np.pi, np.pi)
+            gts.append((cls, ob.get_3d_box(size, heading, center)))
+            for _ in range(rng.randint(0, 4)):
+                j = rng.choice([0.02, 0.1, 0.3, 0.6])
+                c2 = center + rng.randn(3) * j * size
+                s2 = size * (1 + rng.randn(3) * 0.5 * j)
+                preds.append((cls, ob.get_3d_box(np.abs(s2) + 0.05, heading + rng.randn() * j, c2), float(rng.rand())))
+        for _ in range(rng.randint(0, 2)):
+            cls = classes[rng.randint(len(classes))]
+            preds.append((cls, ob.get_3d_box(type_mean_size[cls], rng.uniform(-3, 3), rng.uniform(-5, 5, 3) + [0, 0, 5]), float(rng.rand())))
+        if img % 11 != 3:
+            gt_all[img] = gts
+        if preds and img % 7 != 5:
+            pred_all[img] = preds
+    return pred_all, gt_all
+
+
+def _numpy_side(ds, ed, perturb, make_rng):
+    """ds / ed: the dataset-helper and eval_det modules of one side; perturb(center, size, heading, bounds, rng) -> tuple."""
+    out = {}
+    rng = np.random.RandomState(21)
+    angles = np.concatenate([rng.uniform(-2 * np.pi, 4 * np.pi, 40), [0.0, np.pi / 12, -np.pi / 12, 2 * np.pi - 1e-9, np.pi]])
+    a2c = np.array([ds.angle2class(a, 12) for a in angles], dtype=np.float64)
+    out['angle2class'] = a2c
+    out['class2angle'] = np.array([[ds.class2angle(int(c), r, 12), ds.class2angle(int(c), r, 12, to_label_format=False)] for c, r in a2c])
+    types = ['bed', 'table', 'sofa', 'chair', 'toilet', 'desk', 'dresser', 'night_stand', 'bookshelf', 'bathtub']
+    s2c = [ds.size2class(rng.uniform(0.3, 2.5, 3), t) for t in types]
+    out['size2class.cls'] = np.array([c for c, _ in s2c], dtype=np.float64)
+    out['size2class.res'] = np.array([r for _, r in s2c])
+    out['class2size'] = np.array([ds.class2size(int(c), r) for c, r in s2c])
+    pc = rng.standard_normal((50, 6))
+    out['rotate_pc_along_y'] = np.array([ds.rotate_pc_along_y(pc.copy(), a) for a in (0.3, -1.2, np.pi)])
+    lab = [ds.from_prediction_to_label_format(rng.standard_normal(3), int(rng.randint(12)), rng.uniform(-0.26, 0.26), int(rng.randint(10)),
+                                              rng.uniform(-0.2, 0.2, 3), rng.uniform(-1, 1)) for _ in range(8)]
+    out['from_prediction_to_label_format'] = np.array([[h, w, l, tx, ty, tz, ry] for h, w, l, tx, ty, tz, ry in lab])
+    if hasattr(ds, 'get_3d_box'):
+        out['get_3d_box'] = np.array([ds.get_3d_box(rng.uniform(0.5, 2, 3), rng.uniform(-3, 3), rng.standard_normal(3)) for _ in range(6)])
+    B = 6
+    iou2d, iou3d = ds.compute_box3d_iou(rng.standard_normal((B, 3)) * 0.1, rng.standard_normal((B, 12)), rng.uniform(-0.2, 0.2, (B, 12)),
+                                        rng.standard_normal((B, 10)), rng.uniform(-0.1, 0.1, (B, 10, 3)), rng.standard_normal((B, 3)) * 0.1,
+                                        rng.randint(0, 12, B), rng.uniform(-0.2, 0.2, B), rng.randint(0, 10, B), rng.uniform(-0.1, 0.1, (B, 3)))
+    out['compute_box3d_iou'] = np.stack([iou2d, iou3d])
+    rec = np.sort(rng.rand(30))
+    prec = np.sort(rng.rand(30))[::-1].copy()
+    out['voc_ap'] = np.array([ed.voc_ap(rec, prec, False), ed.voc_ap(rec, prec, True)])
+    pred_all, gt_all = _scene(0)
+    for tag, thr, m07 in (('a', 0.25, False), ('b', {'bed': 0.25, 'chair': 0.5, 'table': 0.1}, True)):
+        r, p, ap = ed.eval_det(pred_all, gt_all, thr, use_07_metric=m07)
+        for c in sorted(ap):
+            out['eval_det.%s.%s.rec' % (tag, c)] = np.asarray(r[c], dtype=np.float64)
+            out['eval_det.%s.%s.prec' % (tag, c)] = np.asarray(p[c], dtype=np.float64)
+            out['eval_det.%s.%s.ap' % (tag, c)] = np.array([ap[c]])
+    g = make_rng(77)
+    rows = []
+    for bounds in ((0.7, 1.0), (0.01, 0.25), (0.5, 0.6)):
+        for _ in range(3):
+            res = perturb(np.array([0.2, -0.1, 3.0]), np.array([1.9, 0.9, 1.1]), 0.4, bounds, g)
+            rows.append(np.concatenate([res[0], res[1], [res[2], res[3]], res[4], res[5], [res[6]]]))
+    out['perturb_box_to_diff_ious'] = np.array(rows)
+    return out
+
+
+def _numpy_reference():
+    import types
+    with rr.Reference() as R:
+        ds, ed, bpf = R.mod('roi_seg_box3d_dataset'), R.mod('eval_det'), R.mod('box_pc_fit_dataset')
+        me = types.SimpleNamespace(center_perturbation=0.8, size_perturbation=0.2, angle_perturbation=np.pi)      # models/config.py:30-32
+
+        def perturb(c, s, h, bounds, g):
+            return bpf.BoxPCFitDataset.perturb_box_to_diff_ious(me, c, s, h, bounds)       # draws from numpy's global stream
+
+        def make_rng(seed):
+            np.random.seed(seed)
+            return None
+        return _numpy_side(ds, ed, perturb, make_rng)
+
+
+def _numpy_oracle():
+    import types
+    from oracle import roi_seg_box3d_dataset as ods, eval_det as oed, box_pc_fit_dataset as obpf, box_util as obu
+    ds = types.SimpleNamespace(**{k: getattr(ods, k) for k in ('angle2class', 'class2angle', 'size2class', 'class2size', 'rotate_pc_along_y',
+                                                               'from_prediction_to_label_format')})
+    ds.get_3d_box, ds.compute_box3d_iou = obu.get_3d_box, obu.compute_box3d_iou
+
+    def perturb(c, s, h, bounds, g):
+        return obpf.perturb_box_to_diff_ious(c, s, h, bounds, 0.8, 0.2, np.pi, rng_mode='numpy_legacy', rng=g)[:7]
+    return _numpy_side(ds, oed, perturb, lambda seed: np.random.RandomState(seed))
+
+
+# ---- case 7: models/tf_util.py geometry, function by function ---------------------------------------------------------------
+def _tf_util_calls(tu, c, ci):
+    """tu: tf_util of one side; c / ci: float / int tensor constructors of that side.  Same-named functions, same arguments."""
+    rng = np.random.RandomState(5)
+    f = lambda *shape: rng.standard_normal(shape).astype(np.float32)
+    B, N = 5, 40
+    box2D = np.stack([rng.uniform(10, 200, B), rng.uniform(10, 200, B), rng.uniform(300, 600, B), rng.uniform(250, 500, B)], 1).astype(np.float32)
+    img_dim = np.stack([rng.uniform(400, 600, B), rng.uniform(500, 700, B)], 1).astype(np.float32)
+    pcs = (f(B, N, 3) + np.array([0, 0, 3], dtype=np.float32))
+    ang = rng.uniform(-0.3, 0.3, B)
+    Rtilt = np.stack([np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]]) for a in ang]).astype(np.float32)
+    K = np.stack([np.array([[520 + i, 0, 320], [0, 525 - i, 240], [0, 0, 1]]) for i in range(B)]).astype(np.float32)
+    centers, dims, orients = f(B, 3), rng.uniform(0.4, 2.0, (B, 3)).astype(np.float32), rng.uniform(-3, 3, B).astype(np.float32)
+    box = (c(centers), c(dims), c(orients))
+    out = {}
+
+    def put(name, v):
+        if isinstance(v, (list, tuple)) and len(v) == 1:
+            v = v[0]
+        v = rr.to_np(v)
+        if isinstance(v, (list, tuple)) and all(np.ndim(x) == 0 for x in v):       # [left, top, right, bottom] of scalars
+            v = np.stack([np.asarray(x) for x in v])
+        pack(out, name, v)
+    put('tf_expand_tile', tu.tf_expand_tile(c(f(3, 4)), axis=1, tile=[1, 6, 1]))
+    put('tf_get_2D_bbox_of_points', tu.tf_get_2D_bbox_of_points(c(f(N, 2))))
+    put('tf_get_2D_softmax_bbox_of_points', tu.tf_get_2D_softmax_bbox_of_points(c(f(N, 2)), 10.))
+    put('tf_normalize_2D_bboxes', tu.tf_normalize_2D_bboxes(c(box2D), c(img_dim)))
+    put('tf_dilate_2D_bboxes', tu.tf_dilate_2D_bboxes(c(box2D), 1.5))
+    put('tf_clip_2D_bbox_to_image_dims_multi', tu.tf_clip_2D_bbox_to_image_dims_multi(c(box2D * 1.4 - 60), c(img_dim)))
+    put('flip_axis_to_camera', tu.flip_axis_to_camera(c(pcs)))
+    put('flip_axis_to_depth', tu.flip_axis_to_depth(c(pcs)))
+    put('project_upright_depth_to_camera', tu.project_upright_depth_to_camera(c(pcs), c(Rtilt)))
+    put('project_upright_depth_to_image', tu.project_upright_depth_to_image(c(pcs), c(Rtilt), c(K)))
+    put('tf_get_2D_bbox_of_projection_sunrgbd_multi', tu.tf_get_2D_bbox_of_projection_sunrgbd_multi(c(pcs), c(Rtilt), c(K)))
+    put('tf_get_2D_bbox_of_softmax_projection_sunrgbd_multi',
+        tu.tf_get_2D_bbox_of_softmax_projection_sunrgbd_multi(c(pcs), c(Rtilt), c(K), 10.))
+    for tr in (False, True):
+        put('tf_create_3D_box_by_vertices_multi.%d' % tr, tu.tf_create_3D_box_by_vertices_multi(box, apply_translation=tr))
+        put('tf_create_3D_box_by_surface_centers_multi.%d' % tr, tu.tf_create_3D_box_by_surface_centers_multi(box, apply_translation=tr))
+    put('tf_distance_to_closest_3D_box_surface_multi', tu.tf_distance_to_closest_3D_box_surface_multi(c(pcs - np.array([0, 0, 3], dtype=np.float32)), box))
+    put('tf_normalize_point_clouds_to_01', tu.tf_normalize_point_clouds_to_01(c(f(B, N, 6))))
+    put('tf_normalize_point_clouds_to_mean_zero_and_unit_var', tu.tf_normalize_point_clouds_to_mean_zero_and_unit_var(c(f(B, N, 6))))
+    put('tf_get_box_pc_representation', tu.tf_get_box_pc_representation(box, c(f(B, N, 6))))
+    from transferable3d_b200.constants import MEAN_DIMS_ARR
+    anchors_d = c(MEAN_DIMS_ARR.astype(np.float32))
+    anchors_o = c(np.arange(0, 2 * np.pi, 2 * np.pi / 12).astype(np.float32))
+    bp = (c(centers), c(f(B, 10)), c(f(B, 10, 3) * 0.1), c(f(B, 12)), c(f(B, 12) * 0.1))
+    put('tf_convert_box_params_from_anchor_to_reg_format_multi',
+        tu.tf_convert_box_params_from_anchor_to_reg_format_multi(bp, ci(rng.randint(0, 10, B)), anchors_d, anchors_o))
+    put('tf_rot_box_params_multi', tu.tf_rot_box_params_multi(box, c(rng.uniform(-1, 1, B).astype(np.float32))))
+    return out
+
+
+def _tf_util_reference():
+    with rr.Reference() as R:
+        tf = R.tf
+        R.reset({})
+        return _tf_util_calls(R.mod('tf_util'), lambda a: tf.constant(np.asarray(a), dtype=tf.float32),
+                              lambda a: tf.constant(np.asarray(a), dtype=tf.int32))
+
+
+def _tf_util_oracle():
+    from oracle import tf_util as otu
+    with torch.no_grad():
+        return _tf_util_calls(otu, lambda a: torch.as_tensor(np.asarray(a)).to(F64), lambda a: torch.as_tensor(np.asarray(a)).long())
+
+
 def _case(ref, orc, *args, **kw):
     lean = kw.get('lean', False)
 
@@ -308,6 +573,9 @@ CASES = {
     'semisup_A_train_softmax_proj': _case(_semi_train_reference, _semi_train_oracle, 'A',
                                           dict(CFG_A, WEAK_TRAIN_BOX_W_SURFACE=[True, False, True], WEAK_REPROJECTION_USE_SOFTMAX_PROJ=True), lean=True),
 }
+CASES['fpointnet_v1_helpers'] = _case(_fpn_reference, _fpn_oracle)
+CASES['numpy_helpers'] = _case(_numpy_reference, _numpy_oracle)
+CASES['tf_util_functions'] = _case(_tf_util_reference, _tf_util_oracle)
 for _i, _f in enumerate(REPROJ_VARIANTS):
     CASES['semisup_adv_train_variant%d' % _i] = _case(_semi_train_reference, _semi_train_oracle, 'F', dict(CFG5, **_f), lean=True)
 for _i, _f in enumerate(BOXPC_VARIANTS):
