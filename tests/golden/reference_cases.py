@@ -68,36 +68,40 @@ def _np(t):
 
 
 # ---- case 1: the test graph of model F (test_semisup.get_model, test_semisup.py:61-180, called as is) -------------------
-def _model_F_inputs(B=4, N=128):
-    return weights.make_weights_model_F(seed=11), synth.make_batch(B, N, 6, seed=2024)
+def _model_F_inputs(B=4, N=128, box2d_feats=False):
+    return weights.make_weights_model_F(seed=11, norm_box2d=box2d_feats), synth.make_batch(B, N, 6, seed=2024)
 
 
-def _model_F_reference(refine, mask_pc):
-    v, b = _model_F_inputs()
+def _model_F_reference(refine, mask_pc, oracle_mask=False, box2d_feats=False):
+    v, b = _model_F_inputs(box2d_feats=box2d_feats)
     B, N = b['pc'].shape[:2]
     out = {}
     with rr.Reference() as R:
         ts = R.mod('test_semisup')
-        FLAGS = R.flags(use_one_hot=True, refine=refine, mask_pc_for_boxpc=mask_pc, SEMI_MODEL='F', BOX_PC_MASK_REPRESENTATION='A')
+        FLAGS = R.flags(use_one_hot=True, refine=refine, mask_pc_for_boxpc=mask_pc, SEMI_MODEL='F', BOX_PC_MASK_REPRESENTATION='A',
+                        USE_NORMALIZED_BOX2D_AS_FEATS=box2d_feats)
         ts.FLAGS, ts.MODEL, ts.GPU_INDEX, ts.MODEL_PATH = FLAGS, R.mod('semisup_v1_sunrgbd'), 0, None
-        # placeholders in creation order: is_training, then semisup_v1_sunrgbd.placeholder_inputs (pc, bg_pc, img, one_hot, ...)
-        R.reset(v, feeds=[False, b['pc'], None, None, b['one_hot']] + [None] * 14)
+        # placeholders in creation order: is_training, then semisup_v1_sunrgbd.placeholder_inputs (pc, bg_pc, img, one_hot, y_seg, ...)
+        feeds = [False] + [None if k is None else b[k] for k in SEMI_FEED_ORDER]
+        R.reset(v, feeds=feeds)
         R.quiet()
-        _, ops = ts.get_model(B, N, 6)
+        _, ops = ts.get_model(B, N, 6, use_oracle_mask=oracle_mask)
         R.quiet(False)
         pack(out, 'logits', ops['logits'])
         pack_end_points(out, ops['end_points'])
     return out
 
 
-def _model_F_oracle(refine, mask_pc):
+def _model_F_oracle(refine, mask_pc, oracle_mask=False, box2d_feats=False):
     from oracle.tf_layers import VarStore
     from oracle import test_semisup as ots
-    v, b = _model_F_inputs()
-    FLAGS = config.cfg(refine=refine, mask_pc_for_boxpc=mask_pc)
+    v, b = _model_F_inputs(box2d_feats=box2d_feats)
+    FLAGS = config.cfg(refine=refine, mask_pc_for_boxpc=mask_pc, USE_NORMALIZED_BOX2D_AS_FEATS=box2d_feats)
     vs = VarStore(v, dtype=F64)
+    t = lambda a: torch.as_tensor(np.asarray(a)).to(F64)
     with torch.no_grad():
-        logits, ep = ots.run_graph(vs, FLAGS, torch.as_tensor(b['pc']).to(F64), torch.as_tensor(b['one_hot']).to(F64))
+        logits, ep = ots.run_graph(vs, FLAGS, t(b['pc']), t(b['one_hot']), box2D=t(b['box2D']), img_dim=t(b['img_dim']),
+                                   oracle_mask=t(b['labels']) if oracle_mask else None)
     out = {}
     pack(out, 'logits', logits)
     pack_end_points(out, ep)
@@ -520,6 +524,161 @@ def _tf_util_oracle():
         return _tf_util_calls(otu, lambda a: torch.as_tensor(np.asarray(a)).to(F64), lambda a: torch.as_tensor(np.asarray(a)).long())
 
 
+# ---- case 8: test_semisup.inference (test_semisup.py:187-260), run as is over a re-executing session ---------------------------
+class _Py2Int(int):
+    """`num_batches = pc.shape[0]/batch_size` (test_semisup.py:191) is an integer division in the reference's Python 2."""
+    def __truediv__(self, o):
+        return _Py2Int(int(self) // int(o))
+
+
+class _Py2Array(np.ndarray):
+    @property
+    def shape(self):
+        s = np.ndarray.shape.__get__(self)
+        return (_Py2Int(s[0]),) + tuple(s[1:])
+
+
+class _ReexecutingSession(object):
+    """sess.run(fetches, feed_dict) for the eager stand-in: rebuilds the graph with the fed values (the reference's own
+    get_model again) and returns the tensors that sit where the fetched ones sat in `ops` / `ops['end_points']`."""
+    def __init__(self, build, ops):
+        self.build, self.ops = build, ops
+
+    def _where(self, t):
+        for k, v in self.ops.items():
+            if v is t:
+                return None, k
+        for k, v in self.ops['end_points'].items():
+            if v is t:
+                return 'end_points', k
+        raise KeyError('fetch is not an op of this graph')
+
+    def run(self, fetches, feed_dict):
+        fed = {self._where(k)[1]: v for k, v in feed_dict.items()}
+        new_ops = self.build(fed)
+        res = []
+        for t in fetches:
+            where, k = self._where(t)
+            res.append(rr.to_np(new_ops[k] if where is None else new_ops[where][k]))
+        return res
+
+
+def _inference_inputs(B=8, N=96):
+    return weights.make_weights_model_F(seed=11), synth.make_batch(B, N, 6, seed=77)
+
+
+def _pack_inference(out, tag, res):
+    for name, v in zip(('pred_seg', 'centers', 'orient_cls', 'orient_reg', 'dims_cls', 'dims_reg', 'scores'), res):
+        pack(out, '%s.%s' % (tag, name), np.asarray(v))
+
+
+def _inference_reference():
+    v, b = _inference_inputs()
+    bs, N = 4, b['pc'].shape[1]
+    out = {}
+    with rr.Reference() as R:
+        ts = R.mod('test_semisup')
+        FLAGS = R.flags(use_one_hot=True, refine=1, mask_pc_for_boxpc=False, SEMI_MODEL='F', BOX_PC_MASK_REPRESENTATION='A')
+        ts.FLAGS, ts.MODEL, ts.GPU_INDEX, ts.MODEL_PATH = FLAGS, R.mod('semisup_v1_sunrgbd'), 0, None
+
+        def build(fed):
+            R.reset(v, feeds=[fed.get('is_training_pl', False), fed.get('pc_pl'), None, None, fed.get('one_hot_vec_pl')] + [None] * 14)
+            return ts.get_model(bs, N, 6)[1]
+        R.quiet()
+        ops = build(dict(pc_pl=b['pc'][:bs], one_hot_vec_pl=b['one_hot'][:bs]))
+        sess = _ReexecutingSession(build, ops)
+        pc = np.asarray(b['pc'], dtype=np.float64).view(_Py2Array)
+        for tag, kw in (('F', dict(prefix='F_')), ('F2_fit', dict(prefix='F2_', use_boxpc_fit_prob=True))):
+            _pack_inference(out, tag, ts.inference(sess, ops, pc, b['one_hot'], bs, **kw))
+        R.quiet(False)
+        x = np.random.RandomState(2).standard_normal((3, 5, 7))
+        pack(out, 'softmax', ts.softmax(x))
+    return out
+
+
+def _inference_oracle():
+    from oracle.tf_layers import VarStore
+    from oracle import test_semisup as ots
+    v, b = _inference_inputs()
+    out = {}
+    FLAGS = config.cfg(refine=1)
+    for tag, kw in (('F', dict(prefix='F_')), ('F2_fit', dict(prefix='F2_', use_boxpc_fit_prob=True))):
+        _pack_inference(out, tag, ots.inference(VarStore(v, dtype=F64), FLAGS, np.asarray(b['pc'], dtype=np.float64), b['one_hot'], 4, **kw))
+    pack(out, 'softmax', ots.softmax(np.random.RandomState(2).standard_normal((3, 5, 7))))
+    return out
+
+
+# ---- case 9: semisup_models.box_pc_mask_features_model (both representations, NORMALIZE_PC, mask input) and mlps ---------------
+BOXPC_MODEL_VARIANTS = [(False, 'SD', False), (True, 'SD', False), (True, 'Spread', True), (False, 'SD', True)]
+
+
+def _boxpc_model_inputs(rep, masked, B=5, N=64, seed=11):
+    rng = np.random.RandomState(seed)
+    pc = np.concatenate([rng.randn(B, N, 3) * [1.0, 0.5, 1.5] + [0.3, -0.2, 4.0], rng.rand(B, N, 3)], axis=2).astype(np.float32)
+    box = (pc[:, :, :3].mean(1) + rng.randn(B, 3).astype(np.float32) * 0.2,
+           (rng.rand(B, 3) * 1.5 + 0.5).astype(np.float32), (rng.rand(B) * 6.28).astype(np.float32))
+    one_hot = np.eye(10, dtype=np.float32)[rng.randint(0, 10, B)]
+    mask = (rng.rand(B, N, 1) < 0.5).astype(np.float32)
+    v = weights.make_weights_boxpc(use_one_hot=True, rep=rep)
+    if masked and rep == 'A':      # the mask channel widens conv-reg1 of representation A (semisup_models.py:345-350)
+        w = v['box_pc_mask_model/conv-reg1/weights']
+        v['box_pc_mask_model/conv-reg1/weights'] = np.concatenate([w, np.random.RandomState(5).randn(1, 1, 1, 128).astype(np.float32) * 0.1], axis=1)
+    return v, pc, box, one_hot, mask
+
+
+def _mlps_inputs():
+    rng = np.random.RandomState(8)
+    f = lambda *s: (rng.standard_normal(s) * 0.3).astype(np.float32)
+    v = {'m/fc0/weights': f(16, 32), 'm/fc0/biases': f(32), 'm/fc0/bn/beta': f(32), 'm/fc0/bn/gamma': 1 + f(32),
+         'm/fc0/bn/moving_mean': f(32), 'm/fc0/bn/moving_variance': np.abs(f(32)) + 0.5, 'm/fc1/weights': f(32, 8), 'm/fc1/biases': f(8)}
+    return v, f(6, 16)
+
+
+def _boxpc_model_reference():
+    out = {}
+    with rr.Reference() as R:
+        tf = R.tf
+        sm = R.mod('semisup_models')
+        c = lambda a: tf.constant(np.asarray(a), dtype=tf.float32)
+        for rep in ('A', 'B'):
+            for i, (normalize, method, masked) in enumerate(BOXPC_MODEL_VARIANTS):
+                v, pc, box, one_hot, mask = _boxpc_model_inputs(rep, masked)
+                FLAGS = R.flags(BOX_PC_MASK_REPRESENTATION=rep)
+                R.reset(v)
+                R.quiet()
+                o, feats = sm.box_pc_mask_features_model(tuple(c(x) for x in box), c(pc), c(mask) if masked else None, 9, tf.constant(False), {},
+                                                         None, False, normalize_pc=normalize, normalize_method=method, one_hot_vec=c(one_hot),
+                                                         c=FLAGS, scope='box_pc_mask_model')
+                R.quiet(False)
+                pack(out, '%s%d.output' % (rep, i), o)
+                pack(out, '%s%d.feats' % (rep, i), feats)
+        v, x = _mlps_inputs()
+        R.reset(v)
+        R.quiet()
+        pack(out, 'mlps', sm.mlps(c(x), [32, 8], tf.constant(False), scope='m'))
+        R.quiet(False)
+    return out
+
+
+def _boxpc_model_oracle():
+    from oracle.tf_layers import VarStore
+    from oracle import semisup_models as osm
+    t = lambda a: torch.as_tensor(np.asarray(a)).to(F64)
+    out = {}
+    with torch.no_grad():
+        for rep in ('A', 'B'):
+            for i, (normalize, method, masked) in enumerate(BOXPC_MODEL_VARIANTS):
+                v, pc, box, one_hot, mask = _boxpc_model_inputs(rep, masked)
+                o, feats = osm.box_pc_mask_features_model(tuple(t(x) for x in box), t(pc), t(mask) if masked else None, 9, False, {}, False, False,
+                                                          VarStore(v, dtype=F64), normalize_pc=normalize, normalize_method=method,
+                                                          one_hot_vec=t(one_hot), c=config.cfg(BOX_PC_MASK_REPRESENTATION=rep), scope='box_pc_mask_model')
+                pack(out, '%s%d.output' % (rep, i), o)
+                pack(out, '%s%d.feats' % (rep, i), feats)
+        v, x = _mlps_inputs()
+        pack(out, 'mlps', osm.mlps(t(x), [32, 8], False, VarStore(v, dtype=F64), scope='m'))
+    return out
+
+
 def _case(ref, orc, *args, **kw):
     lean = kw.get('lean', False)
 
@@ -556,8 +715,8 @@ BOXPC_VARIANTS = [
     dict(BOXPC_WEIGH_DELTA_PRED_BY_CLS_CONF=True, BOXPC_STOP_GRAD_OF_CLS_VIA_DELTA=False),
     dict(BOXPC_WEIGH_DELTA_PRED_BY_CLS_CONF=True, BOXPC_WEIGH_DELTA_LOSS_BY_CLS_CONF=True, BOXPC_STOP_GRAD_OF_CLS_VIA_DELTA=False,
          BOXPC_DELTA_LOSS_TYPE='mse'),
-    dict(NORMALIZE_PC_BEFORE_SEG=True, NORMALIZATION_METHOD='01'),
-    dict(NORMALIZE_PC_BEFORE_SEG=True, NORMALIZATION_METHOD='mean_zero_unit_var'),
+    dict(BOXPC_WEIGHT_CLS=2.5, BOXPC_FIT_BOUNDS=[0.5, 1.0]),
+    dict(BOXPC_DELTA_LOSS_TYPE='mse', BOXPC_WEIGH_DELTA_LOSS_BY_CLS_GT=True),          # on representation B
 ]
 
 
@@ -565,6 +724,8 @@ CASES = {
     # name: (reference thunk, oracle thunk)
     'model_F_test_graph_refine2': _case(_model_F_reference, _model_F_oracle, 2, False),
     'model_F_test_graph_masked_pc': _case(_model_F_reference, _model_F_oracle, 1, True),
+    'model_F_test_graph_oracle_mask': _case(_model_F_reference, _model_F_oracle, 1, False, True, False),
+    'model_F_test_graph_box2d_feats': _case(_model_F_reference, _model_F_oracle, 1, False, False, True),
     'boxpc_train_rep_A': _case(_boxpc_train_reference, _boxpc_train_oracle, 'A', dict(BOXPC_WEIGHT_DELTA=4.)),
     'boxpc_train_rep_B': _case(_boxpc_train_reference, _boxpc_train_oracle, 'B', dict(BOXPC_WEIGHT_DELTA=4.)),
     'semisup_adv_train_cfg5': _case(_semi_train_reference, _semi_train_oracle, 'F', CFG5),
@@ -575,6 +736,8 @@ CASES = {
 }
 CASES['fpointnet_v1_helpers'] = _case(_fpn_reference, _fpn_oracle)
 CASES['numpy_helpers'] = _case(_numpy_reference, _numpy_oracle)
+CASES['boxpc_features_model_variants'] = _case(_boxpc_model_reference, _boxpc_model_oracle)
+CASES['test_semisup_inference'] = _case(_inference_reference, _inference_oracle)
 CASES['tf_util_functions'] = _case(_tf_util_reference, _tf_util_oracle)
 for _i, _f in enumerate(REPROJ_VARIANTS):
     CASES['semisup_adv_train_variant%d' % _i] = _case(_semi_train_reference, _semi_train_oracle, 'F', dict(CFG5, **_f), lean=True)
