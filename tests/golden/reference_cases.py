@@ -108,8 +108,53 @@ def _model_F_oracle(refine, mask_pc, oracle_mask=False, box2d_feats=False):
     return out
 
 
+# The training-step fixtures are also compared with the CUDA path (tests/test_gpu_reference_fixtures.py).  The gradient of a
+# max-pool is discontinuous where the two largest values of a pooled column tie, so their batches are drawn with seeds for which
+# every pooled column of the float64 oracle forward has a relative top-2 gap >= MIN_POOL_GAP (find_tie_free_seed below; sizes
+# B = 8, N = 256 are the ones the GPU training tests already run).
+MIN_POOL_GAP = 2e-5
+TIE_FREE_SEEDS = {'boxpc_A': 3, 'boxpc_B': 1, 'semi_F': 74, 'semi_A': 8}
+
+
+def min_pool_gap(thunk):
+    """Runs `thunk` (an oracle forward) and returns the smallest relative top-2 gap over every max-pooled column."""
+    import oracle.tf_layers as L
+    import oracle.semisup_models as osm
+    import oracle.model_util as omu
+    gaps = []
+    orig = L.max_pool_points
+
+    def spy(x):
+        top2 = torch.topk(x.detach(), 2, dim=1).values
+        rel = torch.where(top2[:, 0] > 0, (top2[:, 0] - top2[:, 1]) / top2[:, 0].clamp_min(1e-30), torch.ones_like(top2[:, 0]))
+        gaps.append(float(rel.min()))
+        return orig(x)
+    mods = [m for m in (L, osm, omu) if hasattr(m, 'max_pool_points')]
+    for m in mods:
+        m.max_pool_points = spy
+    try:
+        thunk()
+    finally:
+        for m in mods:
+            m.max_pool_points = orig
+    return min(gaps)
+
+
+def find_tie_free_seed(kind, first=1, last=200):
+    """kind: a key of TIE_FREE_SEEDS.  python -c "import reference_cases as rc; print(rc.find_tie_free_seed('boxpc_A'))"."""
+    for seed in range(first, last):
+        if kind.startswith('boxpc'):
+            run = lambda: _boxpc_train_oracle(kind[-1], dict(BOXPC_WEIGHT_DELTA=4.), seed=seed)
+        else:
+            run = lambda: _semi_train_oracle(kind[-1], CFG5 if kind[-1] == 'F' else CFG_A, seed=seed)
+        if min_pool_gap(run) >= MIN_POOL_GAP:
+            return seed
+    raise AssertionError('no tie-free seed in range')
+
+
 # ---- case 2: the BoxPC training graph (train_boxpc.train(), graph block executed from the script's AST) -----------------
-def _boxpc_inputs(rep, B=6, N=96, seed=3):
+def _boxpc_inputs(rep, B=8, N=256, seed=None):
+    seed = TIE_FREE_SEEDS['boxpc_' + rep] if seed is None else seed
     v = weights.make_weights_boxpc(rep=rep)
     feed = synth.make_boxpc_batch(B, N, 6, seed=seed)
     rng = np.random.RandomState(seed)
@@ -137,8 +182,8 @@ def _pack_step(out, loss, grads, moving, ep=None):
         pack_end_points(out, ep)
 
 
-def _boxpc_train_reference(rep, flags):
-    v, feed, masks = _boxpc_inputs(rep)
+def _boxpc_train_reference(rep, flags, seed=None):
+    v, feed, masks = _boxpc_inputs(rep, seed=seed)
     B, N = feed['pc'].shape[:2]
     out = {}
     with rr.Reference() as R:
@@ -166,9 +211,9 @@ def _boxpc_train_reference(rep, flags):
     return out
 
 
-def _boxpc_train_oracle(rep, flags):
+def _boxpc_train_oracle(rep, flags, seed=None):
     from oracle import train_boxpc as otb
-    v, feed, masks = _boxpc_inputs(rep)
+    v, feed, masks = _boxpc_inputs(rep, seed=seed)
     B = feed['pc'].shape[0]
     FLAGS = config.cfg(BOX_PC_MASK_REPRESENTATION=rep, **flags)
     loss, grads, vs, ep = otb.loss_and_grads(v, FLAGS, feed, masks, global_step=0, dtype=F64)
@@ -191,7 +236,8 @@ SEMI_FEED_ORDER = ['pc', None, None, 'one_hot', 'labels', 'centers', 'y_orient_c
                    'Rtilt', 'K', 'rot_frust', 'box2D', 'img_dim', 'is_data_2D']       # semisup_v1_sunrgbd.py:37-64, creation order
 
 
-def _semi_inputs(model, B=8, N=64, seed=11):
+def _semi_inputs(model, B=8, N=256, seed=None):
+    seed = TIE_FREE_SEEDS['semi_' + model] if seed is None else seed
     v = weights.make_weights_model_F() if model == 'F' else weights.make_weights_model_A()
     feed = synth.make_batch(B, N, 6, seed=seed, is_data_2D=(np.arange(B) % 2))
     rng = np.random.RandomState(seed)
@@ -210,8 +256,8 @@ SEMI_EP_KEYS_F = ('stage1_center', 'F_center', 'F_heading_scores', 'F_heading_re
 SEMI_EP_KEYS_A = ('stage1_center', 'center', 'heading_scores', 'heading_residuals', 'size_scores', 'size_residuals', 'soft_mask')
 
 
-def _semi_train_reference(model, flags):
-    v, feed, masks = _semi_inputs(model)
+def _semi_train_reference(model, flags, seed=None):
+    v, feed, masks = _semi_inputs(model, seed=seed)
     B, N = feed['pc'].shape[:2]
     script = 'train_semisup_adv.py' if model == 'F' else 'train_semisup.py'
     out = {}
@@ -241,8 +287,8 @@ def _semi_train_reference(model, flags):
     return out
 
 
-def _semi_train_oracle(model, flags):
-    v, feed, masks = _semi_inputs(model)
+def _semi_train_oracle(model, flags, seed=None):
+    v, feed, masks = _semi_inputs(model, seed=seed)
     if model == 'F':
         from oracle import train_semisup_adv as ot
         FLAGS = config.cfg(**flags)

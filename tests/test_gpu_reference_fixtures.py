@@ -1,0 +1,151 @@
+"""-m gpu: the CUDA path (through the C ABI) against the committed REFERENCE fixtures tests/golden/ref_*.npz -- outputs of the
+reference's own unmodified source run on the TF1 stand-in (tests/golden/make_reference_golden.py; float64) -- on the same seeded
+inputs, weights, flags and dropout masks, with no oracle in between:
+
+  * the test graph of model F (test_semisup.get_model: refine = 2, masked point cloud, oracle mask, normalised 2D box feature)
+    in the fp32 and f16x2 modes: mask logits within 1e-4 of the logit scale, every box output within 2e-4 of its scale;
+  * one training step of BoxPC-Fit (representations A and B), of the semi-supervised adversarial graph (cfg5 flags) and of
+    model A, at B = 8, N = 256: loss within 2e-4, head outputs within 2e-3, the set of trained variables, every gradient through
+    the fixture's signature (norm within 2 %, four seeded random projections within 6 % of the norm: the whole-tensor bound of
+    tests/util.py:assert_grad_close -- ReLU flips near zero move a weight gradient by ~1e-3), the updated moving statistics.
+    The batches are drawn with seeds whose max-pooled columns have no near-tie (reference_cases.find_tie_free_seed) and whose
+    smallest mask-logit margin is > 4e-4, so every assertion is unconditional.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from util import err_stats
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+sys.path.insert(0, GOLDEN)
+
+if torch.cuda.is_available():
+    import reference_cases as rc
+    from transferable3d_b200 import runtime as rt, test_semisup as ts, config
+    from transferable3d_b200 import train_boxpc as tb, train_semisup_adv as tsa, train_semisup as tsm
+
+DEV = 'cuda:0'
+
+
+def _fixture(name):
+    return dict(np.load(os.path.join(GOLDEN, 'ref_%s.npz' % name)))
+
+
+def _close(got, want, tol, what, floor=1e-6):
+    got = np.asarray(got.detach().float().cpu().numpy() if isinstance(got, torch.Tensor) else got, dtype=np.float64).reshape(np.shape(want))
+    assert np.isfinite(got).all(), what
+    scale = max(float(np.abs(want).mean()), floor)
+    err = float(np.abs(got - want).max())
+    assert err <= tol * scale, (what, err, scale)
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'f16x2'])
+@pytest.mark.parametrize('case,refine,mask_pc,oracle_mask,box2d', [('refine2', 2, False, False, False), ('masked_pc', 1, True, False, False),
+                                                                   ('oracle_mask', 1, False, True, False), ('box2d_feats', 1, False, False, True)])
+def test_model_F_test_graph_vs_reference_fixture(case, refine, mask_pc, oracle_mask, box2d, mode, built_lib):
+    want = _fixture('model_F_test_graph_' + case)
+    v, b = rc._model_F_inputs(box2d_feats=box2d)
+    FLAGS = config.cfg(refine=refine, mask_pc_for_boxpc=mask_pc, USE_NORMALIZED_BOX2D_AS_FEATS=box2d)
+    rt.set_default_store(rt.VariableStore(v, DEV))
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32)).to(DEV)
+    with rt.precision(mode), torch.no_grad():
+        logits, ep = ts.build_graph(FLAGS, t(b['pc']), t(b['one_hot']), box2D=t(b['box2D']), img_dim=t(b['img_dim']),
+                                    oracle_mask=t(b['labels']) if oracle_mask else None)
+    torch.cuda.synchronize()
+    wl = want['logits']
+    margin = np.abs(wl[..., 1] - wl[..., 0]).min()
+    assert margin > 1e-2 * np.abs(wl).mean()                       # no point near the strict compare: the masks must be identical
+    _close(logits, wl, 1e-4, 'logits')
+    assert np.array_equal((logits[..., 0] < logits[..., 1]).cpu().numpy(), wl[..., 0] < wl[..., 1])
+    for k in ('stage1_center', 'F_center', 'F_heading_scores', 'F_heading_residuals', 'F_size_scores', 'F_size_residuals', 'F2_center',
+              'F2_heading_residuals', 'F2_size_residuals', 'boxpc_fit_prob'):
+        _close(ep[k], want['ep.' + k], 2e-4, k)
+    for k in ('center', 'heading_scores', 'heading_residuals', 'size_scores', 'size_residuals', 'box_params'):      # the W_ branch, where exposed
+        if isinstance(ep.get(k), torch.Tensor):
+            _close(ep[k], want['ep.' + k], 2e-4, k)
+    for i, part in enumerate(ep['F_pred_box_reg']):
+        _close(part, want['ep.F_pred_box_reg.%d' % i], 2e-4, 'F_pred_box_reg.%d' % i)
+
+
+def _check_grads(want, grads, strip=''):
+    """grads: {name: tensor} of the CUDA step.  Same trained variables, same None pattern, signatures inside the whole-tensor bound."""
+    names = sorted(k[len('has_grad.'):] for k in want if k.startswith('has_grad.'))
+    assert int(want['n_trained'][0]) == len(names)
+    reached = [n for n in names if want['has_grad.' + n][0] > 0]
+    assert sorted(grads) == sorted(n[len(strip):] for n in reached), sorted(set(grads) ^ set(n[len(strip):] for n in reached))
+    wnorm = {}
+    for n in reached:
+        if n.endswith('weights'):
+            wnorm[n.rsplit('/', 1)[0]] = float(want['grad.' + n + '#sig'][0])
+    for n in reached:
+        ref = want['grad.' + n + '#sig']
+        got = rc.sig(grads[n[len(strip):]].detach().float().cpu().numpy())
+        layer = n.rsplit('/', 1)[0] if not n.endswith(('gamma', 'beta')) else n.rsplit('/', 2)[0]
+        floor = 1e-2 * wnorm.get(layer, 0.0) + 1e-7               # a bias in front of a batch norm has an analytically zero gradient
+        assert np.isfinite(got).all(), n
+        assert abs(got[0] - ref[0]) <= 2e-2 * ref[0] + floor, (n, got[0], ref[0])
+        assert np.abs(got[2:] - ref[2:]).max() <= 6e-2 * ref[0] + 3 * floor, (n, got, ref)
+
+
+def _check_moving(want, moving, prefix=''):
+    for k, mv in moving.items():
+        ref = want['moving.' + prefix + k]
+        small = k.endswith('variance') and 'fc' in k.split('/')[-3]
+        s = err_stats(mv.cpu().numpy().reshape(ref.shape), ref)
+        assert s['max_abs'] <= (2e-2 if small else 5e-4) * max(s['ref_scale'], 1e-3), (k, s)
+
+
+@pytest.mark.parametrize('rep', ['A', 'B'])
+def test_boxpc_train_step_vs_reference_fixture(rep, built_lib):
+    want = _fixture('boxpc_train_rep_' + rep)
+    v, feed, masks = rc._boxpc_inputs(rep)
+    B, N = feed['pc'].shape[:2]
+    FLAGS = config.cfg(BOXPC_WEIGHT_DELTA=4., BOX_PC_MASK_REPRESENTATION=rep)
+    g = tb.BoxPCTrainGraph(v, FLAGS, B, N, 6, DEV)
+    out = g.forward_backward(feed, masks)
+    torch.cuda.synchronize()
+    assert abs(float(out['loss']) - want['loss'][0]) <= 2e-4 * max(1.0, abs(want['loss'][0]))
+    assert np.abs(out['boxpc_delta_center'].cpu().numpy() - want['ep.boxpc_delta_center']).max() <= 2e-4
+    for k in ('boxpc_delta_size', 'boxpc_delta_angle', 'boxpc_fit_logits'):
+        if isinstance(out.get(k), torch.Tensor):
+            assert np.abs(out[k].cpu().numpy().reshape(want['ep.' + k].shape) - want['ep.' + k]).max() <= 2e-4, k
+    _check_grads(want, g.grad, strip='box_pc_mask_model/')
+    _check_moving(want, g.moving, prefix='box_pc_mask_model/')
+    from oracle.train_boxpc import get_learning_rate, get_bn_decay          # schedules (plain arithmetic) against the script's own
+    assert abs(get_learning_rate(0, B) - want['learning_rate'][0]) < 1e-12 and abs(get_bn_decay(0, B) - want['bn_decay'][0]) < 1e-12
+
+
+def test_semisup_adv_train_step_vs_reference_fixture(built_lib):
+    want = _fixture('semisup_adv_train_cfg5')
+    v, feed, masks = rc._semi_inputs('F')
+    B, N = feed['pc'].shape[:2]
+    g = tsa.SemiAdvTrainGraph(v, config.cfg(**rc.CFG5), B, N, 6, DEV)
+    ep = g.forward_backward(feed, masks)
+    torch.cuda.synchronize()
+    loss = float(ep['loss_terms'].cpu().numpy()[0])
+    assert abs(loss - want['loss'][0]) <= 2e-4 * max(1.0, abs(want['loss'][0])), (loss, want['loss'][0])
+    for k in ('stage1_center', 'F_center', 'F_heading_scores', 'F_size_residuals', 'boxpc_fit_prob', 'F2_center', 'F2_heading_residuals',
+              'F2_size_residuals'):
+        _close(ep[k], want['ep.' + k], 2e-3, k, floor=1.0)
+    _check_grads(want, g.grad)
+    _check_moving(want, g.moving)
+
+
+def test_semisup_model_a_train_step_vs_reference_fixture(built_lib):
+    want = _fixture('semisup_A_train')
+    v, feed, masks = rc._semi_inputs('A')
+    B, N = feed['pc'].shape[:2]
+    g = tsm.SemiTrainGraph(v, config.cfg(SEMI_MODEL='A', **rc.CFG_A), B, N, 6, DEV)
+    ep = g.forward_backward(feed, masks)
+    torch.cuda.synchronize()
+    assert abs(float(ep['semi_loss']) - want['loss'][0]) <= 2e-4 * max(1.0, abs(want['loss'][0])), (float(ep['semi_loss']), want['loss'][0])
+    for k in ('stage1_center', 'center', 'heading_scores', 'size_residuals'):
+        _close(ep[k], want['ep.' + k], 2e-3, k, floor=1.0)
+    _check_grads(want, g.grad)
+    _check_moving(want, g.moving)
