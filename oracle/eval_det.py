@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE (oracle): numpy float64 restatement of sunrgbd_detection/eval_det.py -- voc_ap (:24-55),
-eval_det_cls (:71-157) with get_iou = the oracle's box3d_iou (oracle/box_util.py), eval_det (:159-199).  Parity
-unpinned (no reference vectors); pinned by hand-computed cases in tests/test_oracle_cpu.py.  Only tests/, smoke() and
+eval_det_cls (:71-157) with get_iou = the oracle's box3d_iou (oracle/box_util.py), eval_det (:159-199).  Pinned
+against the reference's own eval_det.py executed here (tests/golden/ref_numpy_helpers.npz, both AP metrics; only
+box3d_iou, absent from the reference tree, is shared) and by hand-computed cases in tests/test_oracle_cpu.py.  Only tests/, smoke() and
 bench.py's cpu_baseline may import this."""
 import numpy as np
 

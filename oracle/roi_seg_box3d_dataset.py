@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE (oracle): numpy float64 restatement of the label conversions of
 sunrgbd_detection/roi_seg_box3d_dataset.py -- rotate_pc_along_y (:37-45), class2angle (:64-71), class2size (:79-82),
-from_prediction_to_label_format (:461-466).  Parity unpinned (the reference ships no vectors); pinned here by
-hand-computed cases in tests/test_oracle_cpu.py.  Only tests/, smoke() and bench.py's cpu_baseline may import this."""
+from_prediction_to_label_format (:461-466).  Pinned against the reference's own functions executed here
+(tests/golden/ref_numpy_helpers.npz, tests/test_oracle_vs_reference_cpu.py) and by hand-computed cases in tests/test_oracle_cpu.py.  Only tests/, smoke() and bench.py's cpu_baseline may import this."""
 import numpy as np
 
 from transferable3d_b200.constants import NUM_HEADING_BIN, type_mean_size, class2type

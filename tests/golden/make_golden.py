@@ -1,6 +1,5 @@
-"""Generates tests/golden/*.npz from the oracle.  The reference itself cannot run in this
-environment (TF1 / Python 2), so these fixtures pin the ORACLE (regression) -- parity with
-TensorFlow stays unpinned, as stated in oracle/__init__.py."""
+"""Generates tests/golden/model_F_tiny.npz from the oracle: a regression fixture of the ORACLE itself.  The fixtures that
+pin the oracle against the reference's source are the ref_*.npz files (make_reference_golden.py)."""
 import os
 import sys
 
