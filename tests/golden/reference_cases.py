@@ -725,6 +725,78 @@ def _boxpc_model_oracle():
     return out
 
 
+# ---- case 10: ROISegBoxDataset.__getitem__ / get_batch over a synthetic frustum pickle (numpy's global stream) -----------------
+DATASET_CLASSES = ['bed', 'table', 'sofa', 'chair', 'toilet', 'desk', 'dresser', 'night_stand', 'bookshelf', 'bathtub']
+DATASET_VARIANTS = [(True, False, False, True), (False, False, False, False), (True, True, True, True)]      # rotate, flip, shift, one_hot
+
+
+def _frustum_lists(F=40, seed=3):
+    from oracle import box_util as ob
+    from transferable3d_b200.constants import type_mean_size
+    rng = np.random.RandomState(seed)
+    L = [[] for _ in range(13)]
+    for i in range(F):
+        cls = DATASET_CLASSES[rng.randint(10)] if i % 9 != 4 else 'lamp'       # 'lamp' is filtered out by `classes`
+        n = rng.randint(40, 400)
+        size = type_mean_size.get(cls, np.ones(3)) * rng.uniform(0.8, 1.2, 3)
+        heading = rng.uniform(-np.pi, np.pi)
+        center = np.array([rng.uniform(-2, 2), rng.uniform(-0.5, 0.5), rng.uniform(1.5, 5)])
+        pts = np.concatenate([center + rng.randn(n, 3) * 0.5, rng.rand(n, 3)], axis=1)
+        rec = [1000 + i, rng.rand(4) * 400, ob.get_3d_box(size, heading, center), None, pts, rng.randint(0, 2, n).astype(np.int64), cls,
+               heading, size, np.eye(3) + rng.randn(3, 3) * 0.01, np.diag([520.0, 520.0, 1.0]) + rng.rand(3, 3), rng.uniform(-0.6, 0.6),
+               np.array([640.0, 480.0])]
+        for l, v in zip(L, rec):
+            l.append(v)
+    return L
+
+
+def _pack_batch(out, tag, batch, one_hot):
+    names = ('data', 'image', 'label', 'center', 'hcls', 'hres', 'scls', 'sres', 'box2d', 'rtilts', 'ks', 'rot_angle', 'img_dims', 'one_hot')
+    assert len(batch) == (14 if one_hot else 13)
+    for name, v in zip(names, batch):
+        if name != 'image':                     # the reference's image slot is an all-NaN (B, 300, 300, 3) array (img = None)
+            pack(out, '%s.%s' % (tag, name), np.asarray(v))
+
+
+def _dataset_reference():
+    import gzip
+    import pickle
+    import tempfile
+    lists = _frustum_lists()
+    out = {}
+    with tempfile.TemporaryDirectory() as d, rr.Reference() as R:
+        path = os.path.join(d, 'frustums.zip.pickle')
+        with gzip.open(path, 'wb') as f:
+            pickle.dump(lists, f, 2)
+        ds_mod = R.mod('roi_seg_box3d_dataset')
+        for i, (rotate, flip, shift, one_hot) in enumerate(DATASET_VARIANTS):
+            ds = ds_mod.ROISegBoxDataset(DATASET_CLASSES, 256, 'val', random_flip=flip, random_shift=shift, rotate_to_center=rotate,
+                                         overwritten_data_path=path, one_hot=one_hot)
+            idxs = np.random.RandomState(1).permutation(len(ds))
+            np.random.seed(77)
+            _pack_batch(out, 'v%d' % i, ds.get_batch(idxs, 4, 20, 256, 6), one_hot)
+            out['v%d.len' % i] = np.asarray([float(len(ds))])
+            pack(out, 'v%d.center_view_box3d' % i, ds.get_center_view_box3d(3))
+    return out
+
+
+def _dataset_oracle():
+    from oracle import roi_seg_box3d_dataset as OD
+    lists = _frustum_lists()
+    keep = [i for i, c in enumerate(lists[6]) if c in DATASET_CLASSES]
+    flt = [[l[i] for i in keep] for l in lists]
+    out = {}
+    for i, (rotate, flip, shift, one_hot) in enumerate(DATASET_VARIANTS):
+        ds = OD.ROISegBoxDataset(flt, 256, random_flip=flip, random_shift=shift, rotate_to_center=rotate, one_hot=one_hot)
+        idxs = np.random.RandomState(1).permutation(len(keep))
+        np.random.seed(77)
+        _pack_batch(out, 'v%d' % i, ds.get_batch(idxs, 4, 20, 256, 6), one_hot)
+        out['v%d.len' % i] = np.asarray([float(len(keep))])
+        box = flt[2][3]
+        pack(out, 'v%d.center_view_box3d' % i, OD.rotate_pc_along_y(np.copy(box), ds.get_center_view_rot_angle(3)))
+    return out
+
+
 def _case(ref, orc, *args, **kw):
     lean = kw.get('lean', False)
 
@@ -782,6 +854,7 @@ CASES = {
 }
 CASES['fpointnet_v1_helpers'] = _case(_fpn_reference, _fpn_oracle)
 CASES['numpy_helpers'] = _case(_numpy_reference, _numpy_oracle)
+CASES['dataset_get_batch'] = _case(_dataset_reference, _dataset_oracle)
 CASES['boxpc_features_model_variants'] = _case(_boxpc_model_reference, _boxpc_model_oracle)
 CASES['test_semisup_inference'] = _case(_inference_reference, _inference_oracle)
 CASES['tf_util_functions'] = _case(_tf_util_reference, _tf_util_oracle)
