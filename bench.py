@@ -266,7 +266,7 @@ def run_cfg1(args):
     fetch = ['logits', 'F2_center', 'F2_heading_scores', 'F2_heading_residuals', 'F2_size_scores', 'F2_size_residuals', 'boxpc_fit_prob']
     res = {}
     for name, graph in (('graph', True), ('eager', False)):
-        sess, ops = ts.get_model(B, N_POINTS, N_CH, FLAGS, variables, device=dev, cuda_graph=graph)
+        sess, ops = ts.get_model(B, N_POINTS, N_CH, FLAGS=FLAGS, variables=variables, device=dev, cuda_graph=graph)
         pc_d, oh_d = torch.as_tensor(pc_h).to(dev), torch.as_tensor(oh_h).to(dev)
         feed_d = {ops['pc_pl']: pc_d, ops['one_hot_vec_pl']: oh_d, ops['is_training_pl']: False}
         feed_h = {ops['pc_pl']: pc_h, ops['one_hot_vec_pl']: oh_h, ops['is_training_pl']: False}

@@ -12,7 +12,20 @@ import numpy as np
 import reference_cases as rc
 
 
+def write_json_fixtures():
+    """models/config.py defaults and the signatures of every function the reference's path modules define."""
+    import json
+    import os
+    import reference_runner as rr
+    for fname, obj in (('ref_config_defaults.json', rr.reference_config_defaults()), ('ref_signatures.json', rr.reference_signatures())):
+        with open(os.path.join(rc.HERE, fname), 'w') as f:
+            json.dump(obj, f, indent=0, sort_keys=True)
+        print('wrote', fname)
+
+
 def main(argv):
+    if not argv:
+        write_json_fixtures()
     names = argv or sorted(rc.CASES)
     for name in names:
         t0 = time.time()

@@ -155,3 +155,42 @@ def exec_train_graph(R, script, namespace):
     exec(compile(ast.Module(body=block, type_ignores=[]), path, 'exec'), ns)
     ns['_block_lines'] = (block[0].lineno, max(getattr(n, 'end_lineno', n.lineno) for n in block))
     return ns
+
+
+SIGNATURE_MODULES = ['semisup_v1_sunrgbd', 'boxpc_sunrgbd', 'semisup_models', 'model_util', 'weak_losses', 'tf_util', 'roi_seg_box3d_dataset',
+                     'eval_det', 'test_semisup']
+
+
+def encode_default(d):
+    import inspect
+    import json
+    if d is inspect.Parameter.empty:
+        return '<required>'
+    if callable(d):
+        return '<fn:%s>' % getattr(d, '__name__', str(d))
+    try:
+        json.dumps(d)
+        return d
+    except Exception:
+        return repr(d)
+
+
+def signatures_of(mod):
+    """{function name: [[parameter, default], ...]} of the functions a module defines itself."""
+    import inspect
+    out = {}
+    for name, fn in vars(mod).items():
+        if inspect.isfunction(fn) and fn.__module__ == mod.__name__ and not name.startswith('_'):
+            out[name] = [[p.name, encode_default(p.default)] for p in inspect.signature(fn).parameters.values()]
+    return out
+
+
+def reference_signatures():
+    with Reference() as R:
+        R.reset({})
+        return {m: signatures_of(R.mod(m)) for m in SIGNATURE_MODULES}
+
+
+def reference_config_defaults():
+    with Reference() as R:
+        return {k: v for k, v in vars(R.flags()).items() if k != 'config_str'}

@@ -876,9 +876,23 @@ def _l2_normalize(x, axis=None, epsilon=1e-12, name=None, dim=None):
     return T(t * torch.rsqrt(torch.clamp(ss, min=epsilon)))
 
 
+def _relu(features, name=None):
+    return T(torch.relu(_raw(features)))
+
+
+def _tanh(x, name=None):
+    return T(torch.tanh(_raw(x)))
+
+
+def _leaky_relu(features, alpha=0.2, name=None):
+    return T(torch.nn.functional.leaky_relu(_raw(features), alpha))
+
+
+_relu.__name__, _tanh.__name__, _leaky_relu.__name__ = 'relu', 'tanh', 'leaky_relu'
+
+
 nn = types.SimpleNamespace(
-    relu=_un(torch.relu), tanh=_un(torch.tanh), sigmoid=_un(torch.sigmoid),
-    leaky_relu=lambda features, alpha=0.2, name=None: T(torch.nn.functional.leaky_relu(_raw(features), alpha)),
+    relu=_relu, tanh=_tanh, sigmoid=_un(torch.sigmoid), leaky_relu=_leaky_relu,
     softmax=_softmax, log_softmax=_log_softmax,
     sparse_softmax_cross_entropy_with_logits=_sparse_xent, softmax_cross_entropy_with_logits=_xent,
     sigmoid_cross_entropy_with_logits=_sigmoid_xent,

@@ -173,7 +173,7 @@ def test_cfg1_session_batch_32(mode, built_lib):
     fetch = ['logits', 'F2_center', 'F2_heading_scores', 'F2_heading_residuals', 'F2_size_scores', 'F2_size_residuals', 'boxpc_fit_prob',
              'stage1_center']
     with rt.precision(mode):
-        sess, ops = ts.get_model(32, 2048, 6, FLAGS, st)
+        sess, ops = ts.get_model(32, 2048, 6, FLAGS=FLAGS, variables=st)
         feed = {ops['pc_pl']: batch['pc'], ops['one_hot_vec_pl']: batch['one_hot'], ops['is_training_pl']: False}
         got = dict(zip(fetch, [t.cpu().numpy() for t in sess.run(fetch, feed)]))
         got2 = dict(zip(fetch, [t.cpu().numpy() for t in sess.run(fetch, feed)]))       # graph replay

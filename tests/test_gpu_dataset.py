@@ -103,7 +103,7 @@ def test_main_batch_end_to_end(tmp_path):
     FLAGS = config.cfg()
     out_pickle, result_dir = os.path.join(str(tmp_path), 'pred.zip.pickle'), os.path.join(str(tmp_path), 'results')
     with rt.precision('fp32'):
-        sess_ops = ts.get_model(32, 1024, 6, FLAGS, variables, cuda_graph=False)
+        sess_ops = ts.get_model(32, 1024, 6, FLAGS=FLAGS, variables=variables, cuda_graph=False)
         np.random.seed(3)
         pred = ts.main_batch(ds, CLASSES, 10, 1024, 6, prefix='F2_', use_boxpc_fit_prob=True, sess_ops=sess_ops,
                              output_filename=out_pickle, result_dir=result_dir)
@@ -149,7 +149,20 @@ def test_checkpoint_to_session(tmp_path):
     outs = []
     for v in (variables, loaded):
         with rt.precision('fp32'):
-            sess, ops = ts.get_model(4, 1024, 6, FLAGS, v, cuda_graph=False)
+            sess, ops = ts.get_model(4, 1024, 6, FLAGS=FLAGS, variables=v, cuda_graph=False)
             outs.append(sess.run([ops['logits'], ops['end_points']['F2_center']],
                                  {ops['pc_pl']: b['pc'], ops['one_hot_vec_pl']: b['one_hot'], ops['is_training_pl']: False}))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    # the reference's own calling convention: flags and checkpoint path in module globals, get_model(B, N, C) positional
+    # (test_semisup.py:22, :61, :158-159, :545-548)
+    with pytest.raises(ValueError):
+        ts.get_model(4, 1024, 6)
+    ts.FLAGS, ts.MODEL_PATH = FLAGS, prefix
+    try:
+        with rt.precision('fp32'):
+            sess, ops = ts.get_model(4, 1024, 6, False, cuda_graph=False)
+            out = sess.run([ops['logits'], ops['end_points']['F2_center']],
+                           {ops['pc_pl']: b['pc'], ops['one_hot_vec_pl']: b['one_hot'], ops['is_training_pl']: False})
+    finally:
+        ts.FLAGS = ts.MODEL_PATH = None
+    assert torch.equal(out[0], outs[0][0]) and torch.equal(out[1], outs[0][1])

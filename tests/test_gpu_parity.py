@@ -276,7 +276,7 @@ def test_inference_runner_matches_oracle_runner(built_lib, setup):
     from oracle import test_semisup as ots
     b, FLAGS = setup['batch'], setup['FLAGS']
     rt.set_default_store(setup['store'])
-    sess, ops = ts.get_model(4, 2048, 6, FLAGS, setup['store'])
+    sess, ops = ts.get_model(4, 2048, 6, FLAGS=FLAGS, variables=setup['store'])
     with rt.precision('fp32'):
         res = ts.inference(sess, ops, b['pc'], b['one_hot'], 2, prefix='F2_', use_boxpc_fit_prob=True)
     ores = ots.inference(VarStore(setup['variables']), FLAGS, b['pc'], b['one_hot'], 2, prefix='F2_', use_boxpc_fit_prob=True)
@@ -307,8 +307,8 @@ def test_session_cuda_graph_replay_equals_eager(built_lib, setup, mode):
     b, FLAGS = setup['batch'], setup['FLAGS']
     fetch = ['logits', 'F2_center', 'F2_heading_scores', 'F2_heading_residuals', 'F2_size_scores', 'F2_size_residuals', 'boxpc_fit_prob']
     with rt.precision(mode):
-        sess_g, ops = ts.get_model(4, 2048, 6, FLAGS, setup['store'], cuda_graph=True)
-        sess_e, _ = ts.get_model(4, 2048, 6, FLAGS, setup['store'], cuda_graph=False)
+        sess_g, ops = ts.get_model(4, 2048, 6, FLAGS=FLAGS, variables=setup['store'], cuda_graph=True)
+        sess_e, _ = ts.get_model(4, 2048, 6, FLAGS=FLAGS, variables=setup['store'], cuda_graph=False)
         for rep in range(3):
             pc = np.roll(b['pc'], rep, axis=0)
             oh = np.roll(b['one_hot'], rep, axis=0)

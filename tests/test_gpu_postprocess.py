@@ -88,7 +88,7 @@ def test_inference_device_matches_host_inference():
     b = synth.make_batch(8, 2048, 6, seed=21)
     FLAGS = config.cfg()
     with rt.precision('fp32'):
-        sess, ops = ts.get_model(4, 2048, 6, FLAGS, variables, cuda_graph=False)
+        sess, ops = ts.get_model(4, 2048, 6, FLAGS=FLAGS, variables=variables, cuda_graph=False)
         ref = ts.inference(sess, ops, b['pc'], b['one_hot'], 4, prefix='F2_', use_boxpc_fit_prob=True)
         got = ts.inference_device(sess, ops, b['pc'], b['one_hot'], 4, prefix='F2_', use_boxpc_fit_prob=True)
     assert np.array_equal(got[0], ref[0]) and np.array_equal(got[2], ref[2]) and np.array_equal(got[4], ref[4])

@@ -160,8 +160,8 @@ def test_x2_session_cuda_graph_replay_equals_eager(built_lib, setup, mode):
     b, FLAGS = setup['batch'], setup['FLAGS']
     fetch = ['logits', 'F2_center', 'F2_heading_residuals', 'F2_size_residuals', 'boxpc_fit_prob']
     with rt.precision(mode):
-        sess_g, ops = ts.get_model(4, 2048, 6, FLAGS, setup['store'], cuda_graph=True)
-        sess_e, _ = ts.get_model(4, 2048, 6, FLAGS, setup['store'], cuda_graph=False)
+        sess_g, ops = ts.get_model(4, 2048, 6, FLAGS=FLAGS, variables=setup['store'], cuda_graph=True)
+        sess_e, _ = ts.get_model(4, 2048, 6, FLAGS=FLAGS, variables=setup['store'], cuda_graph=False)
         for rep in range(2):
             feed = {ops['pc_pl']: np.roll(b['pc'], rep, axis=0), ops['one_hot_vec_pl']: np.roll(b['one_hot'], rep, axis=0),
                     ops['is_training_pl']: False}

@@ -207,3 +207,17 @@ class ROISegBoxDataset(object):
         out = (data, None, label, center, hcls, hres, scls, sres, self._box2d[lsel], self._rtilt[lsel], self._k[lsel], rot,
                self._img_dims[lsel])
         return out + ((one_hot,) if self.one_hot else ())
+
+
+def get_3d_box(box_size, heading_angle, center):
+    """roi_seg_box3d_dataset.py:84-100 (the training scripts import it from this module: train_boxpc.py:29); kernel in box_util."""
+    from . import box_util
+    return box_util.get_3d_box(box_size, heading_angle, center)
+
+
+def compute_box3d_iou(center_pred, heading_logits, heading_residuals, size_logits, size_residuals, center_label,
+                      heading_class_label, heading_residual_label, size_class_label, size_residual_label):
+    """roi_seg_box3d_dataset.py:102-139 (imported from this module by semisup_v1_sunrgbd.py:23); kernel in box_util."""
+    from . import box_util
+    return box_util.compute_box3d_iou(center_pred, heading_logits, heading_residuals, size_logits, size_residuals, center_label,
+                                      heading_class_label, heading_residual_label, size_class_label, size_residual_label)

@@ -225,3 +225,9 @@ def get_strong_loss(pred, labels, end_points, prefix='', reg_weight=0.001, reduc
     if reduce_loss:
         return mask_losses.mean(), box_losses.mean()
     return mask_losses, box_losses
+
+
+def convert_raw_y_box_to_reg_format(y_box, one_hot_vec):
+    """semisup_v1_sunrgbd.py:588-607: the reference defines this twice, verbatim (boxpc_sunrgbd.py:208-229); one implementation here."""
+    from . import boxpc_sunrgbd
+    return boxpc_sunrgbd.convert_raw_y_box_to_reg_format(y_box, one_hot_vec)

@@ -132,11 +132,25 @@ def _clone_value(v):
     return v
 
 
-def get_model(batch_size, num_point, num_channel, FLAGS, variables, use_oracle_mask=False, device='cuda', cuda_graph=True):
-    """test_semisup.get_model (test_semisup.py:61-179) -> (sess, ops). `variables` = {TF name: array}
-    (what saver.restore would load, :158-159)."""
+FLAGS = None            # the reference's module-level flags (test_semisup.py:545-548): set by the driver before get_model()
+MODEL_PATH = None       # checkpoint prefix get_model() restores when no `variables` are handed in (test_semisup.py:22, :158-159)
+
+
+def get_model(batch_size, num_point, num_channel, use_oracle_mask=False, FLAGS=None, variables=None, device='cuda', cuda_graph=True):
+    """test_semisup.get_model (test_semisup.py:61-179; same positional signature) -> (sess, ops).  The reference reads its flags
+    and the checkpoint path from module globals; so does this one when the keyword arguments are left out:
+    `variables` = {TF name: array} or a VariableStore (what saver.restore would load, :158-159), default: the TF checkpoint at
+    test_semisup.MODEL_PATH; `FLAGS` default: test_semisup.FLAGS."""
+    flags = FLAGS if FLAGS is not None else globals()['FLAGS']
+    if flags is None:
+        raise ValueError('get_model: pass FLAGS= or set test_semisup.FLAGS (the reference parses them into a module global)')
+    if variables is None:
+        if MODEL_PATH is None:
+            raise ValueError('get_model: pass variables= or set test_semisup.MODEL_PATH to a TensorFlow checkpoint prefix')
+        from . import tf_checkpoint
+        variables = tf_checkpoint.load_checkpoint(MODEL_PATH)
     store = variables if isinstance(variables, rt.VariableStore) else rt.VariableStore(variables, device)
-    sess = Session(FLAGS, store, use_oracle_mask, batch_size, num_point, num_channel, cuda_graph)
+    sess = Session(flags, store, use_oracle_mask, batch_size, num_point, num_channel, cuda_graph)
     ops = {k: k for k in ('pc_pl', 'one_hot_vec_pl', 'y_seg_pl', 'y_centers_pl', 'y_orient_cls_pl', 'y_orient_reg_pl',
                           'y_dims_cls_pl', 'y_dims_reg_pl', 'R0_rect_pl', 'P_pl', 'Rtilt_pl', 'K_pl', 'rot_frust_pl',
                           'box2D_pl', 'img_dim_pl', 'is_training_pl')}
@@ -330,7 +344,7 @@ def main_batch(test_dataset, test_classes, num_class, num_point, num_channel, pr
     lists = [[] for _ in range(14)]
     test_idxs = np.arange(0, len(test_dataset))
     num_batches = int((len(test_dataset) + batch_size - 1) / batch_size)
-    sess, ops = sess_ops if sess_ops is not None else get_model(batch_size, num_point, num_channel, FLAGS, variables)
+    sess, ops = sess_ops if sess_ops is not None else get_model(batch_size, num_point, num_channel, FLAGS=FLAGS, variables=variables)
     idx, iou_sum = 0, 0.0
     for batch_idx in range(num_batches):
         start_idx, end_idx = batch_idx * batch_size, min(len(test_dataset), (batch_idx + 1) * batch_size)
@@ -374,8 +388,8 @@ def main_batch_from_rgb_detection(test_dataset, test_classes, num_class, num_poi
     lists[1] = lists[13] = None
     test_idxs = np.arange(0, len(test_dataset))
     num_batches = int((len(test_dataset) + batch_size - 1) / batch_size)
-    sess, ops = sess_ops if sess_ops is not None else get_model(batch_size, num_point, num_channel, FLAGS, variables,
-                                                                 use_oracle_mask=use_oracle_mask)
+    sess, ops = sess_ops if sess_ops is not None else get_model(batch_size, num_point, num_channel, use_oracle_mask=use_oracle_mask,
+                                                                 FLAGS=FLAGS, variables=variables)
     idx = 0
     for batch_idx in range(num_batches):
         start_idx, end_idx = batch_idx * batch_size, min(len(test_dataset), (batch_idx + 1) * batch_size)

@@ -24,10 +24,13 @@ def _act_name(activation_fn):
     raise ValueError('unsupported activation_fn %r' % (activation_fn,))
 
 
-def conv2d(inputs, num_output_channels, kernel_size, scope, stride=[1, 1], padding='SAME', bn=False,
-           bn_decay=None, is_training=None, activation_fn='relu'):
-    """tf_util.conv2d (tf_util.py:1258-1323) for the 1x1 / [1,D] kernels of the hot path.
-    inputs (B,N,Cin) -> (B,N,Cout)."""
+def conv2d(inputs, num_output_channels, kernel_size, scope, stride=[1, 1], padding='SAME', data_format='NHWC', use_xavier=True,
+           stddev=1e-3, weight_decay=None, activation_fn='relu', bn=False, bn_decay=None, is_training=None):
+    """tf_util.conv2d (tf_util.py:1258-1323; same positional order) for the 1x1 / [1,D] kernels of the hot path.
+    inputs (B,N,Cin) -> (B,N,Cout).  use_xavier / stddev / weight_decay describe how the reference CREATES the variable; here the
+    weights come from the variable store, so they are accepted and unused."""
+    if data_format != 'NHWC':
+        raise ValueError('conv2d: only NHWC (points x channels) is on the hot path')
     rt.require_eval(is_training)
     st = rt.store()
     layer = st.scope_name(scope)
@@ -39,8 +42,10 @@ def conv2d(inputs, num_output_channels, kernel_size, scope, stride=[1, 1], paddi
     return y.reshape(B, N, num_output_channels)
 
 
-def fully_connected(inputs, num_outputs, scope, bn=False, bn_decay=None, is_training=None, activation_fn='relu'):
-    """tf_util.fully_connected (tf_util.py:1463-1499). inputs (B,Cin)."""
+def fully_connected(inputs, num_outputs, scope, use_xavier=True, stddev=1e-3, weight_decay=None, activation_fn='relu', bn=False,
+                    bn_decay=None, is_training=None):
+    """tf_util.fully_connected (tf_util.py:1463-1499; same positional order). inputs (B,Cin).  The initialiser arguments are
+    accepted and unused (weights come from the variable store)."""
     rt.require_eval(is_training)
     st = rt.store()
     layer = st.scope_name(scope)
