@@ -62,3 +62,53 @@ def test_reference_parameters_are_a_positional_prefix(mod, name):
 @pytest.mark.skipif(not rr.available(), reason='reference tree not present')
 def test_signature_fixture_is_live():
     assert json.loads(json.dumps(rr.reference_signatures())) == REF
+
+
+def _error_cases(M, sm, cfg, T, tf_const_bool=None):
+    """The reference's own `raise` sites on the path (semisup_v1_sunrgbd.py:79, :96, :254; semisup_models.py:323, :343, :421),
+    each reached before any variable or kernel is touched.  M / sm: the two modules of one side; cfg(**kw): its flags; T: tensor
+    constructor.  -> [(exception type name, message)]."""
+    pc, oh = T((3, 8, 6)), T((3, 10))          # batch >= 3: tf_get_box_pc_representation reads dims_reg[2] (tf_util.py:780, unused)
+    box = (T((3, 3)), T((3, 3)), T((3,)))
+    f = False if tf_const_bool is None else tf_const_bool
+    calls = [
+        lambda: M.get_semi_model(pc, None, None, oh, f, True, c=cfg(SEMI_MODEL='Q')),
+        lambda: M.get_semi_loss((None, None), (None,) * 14, {}, c=cfg(SEMI_MODEL='Q')),
+        lambda: M.get_semi_model_backbone(pc, None, None, oh, f, True, oracle_mask=T((3, 8)), c=cfg(SEMI_MODEL='A')),
+        lambda: sm.box_pc_mask_features_model(box, pc, None, 9, f, {}, None, False, c=cfg(BOX_PC_MASK_REPRESENTATION='Z')),
+        lambda: sm.box_pc_mask_features_model(box, pc, None, 9, f, {}, None, False, normalize_pc=True, normalize_method='bad',
+                                              c=cfg(BOX_PC_MASK_REPRESENTATION='A')),
+    ]
+    out = []
+    for call in calls:
+        try:
+            call()
+            out.append(('no exception', ''))
+        except Exception as e:          # noqa: BLE001
+            out.append((type(e).__name__, str(e)))
+    return out
+
+
+EXPECTED_ERRORS = [('Exception', 'Not implemented SEMI_MODEL: Q'), ('Exception', 'Not implemented SEMI_MODEL: Q'), ('NotImplementedError', ''),
+                   ('Exception', 'Box pc mask representation not implemented: Z'), ('Exception', 'Invalid normalization method')]
+
+
+def test_error_behaviour_matches_the_reference_raise_sites():
+    import torch
+    from transferable3d_b200 import semisup_v1_sunrgbd as M, semisup_models as sm, config
+    assert _error_cases(M, sm, config.cfg, lambda shape: torch.zeros(shape)) == EXPECTED_ERRORS
+
+
+@pytest.mark.skipif(not rr.available(), reason='reference tree not present')
+def test_expected_errors_are_what_the_reference_raises():
+    import numpy as np
+    with rr.Reference() as R:
+        tf = R.tf
+        R.reset({})
+        R.quiet()
+        try:
+            got = _error_cases(R.mod('semisup_v1_sunrgbd'), R.mod('semisup_models'), lambda **kw: R.flags(**kw),
+                               lambda shape: tf.constant(np.zeros(shape), dtype=tf.float32), tf.constant(False))
+        finally:
+            R.quiet(False)
+    assert got == EXPECTED_ERRORS, got

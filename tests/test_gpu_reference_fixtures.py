@@ -58,6 +58,10 @@ def test_model_F_test_graph_vs_reference_fixture(case, refine, mask_pc, oracle_m
         logits, ep = ts.build_graph(FLAGS, t(b['pc']), t(b['one_hot']), box2D=t(b['box2D']), img_dim=t(b['img_dim']),
                                     oracle_mask=t(b['labels']) if oracle_mask else None)
     torch.cuda.synchronize()
+    # every end point the reference's graph exposes exists under the same key
+    ref_keys = {k[3:].split('#')[0] for k in want if k.startswith('ep.')}
+    ref_keys = {k[:-2] if k.startswith('F_pred_box_reg.') else k for k in ref_keys}
+    assert not [k for k in sorted(ref_keys) if k not in ep], [k for k in sorted(ref_keys) if k not in ep]
     wl = want['logits']
     margin = np.abs(wl[..., 1] - wl[..., 0]).min()
     assert margin > 1e-2 * np.abs(wl).mean()                       # no point near the strict compare: the masks must be identical

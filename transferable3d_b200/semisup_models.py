@@ -273,6 +273,8 @@ def combined_box_pc_mask_features_model(box_reg, pc, mask, num_outputs, is_train
     """semisup_models.py:326-398.  mask=None, normalize_pc=False (what every caller in the reference passes) runs the fused
     chain with the plane distances in its prologue; a normalised representation or a mask channel takes the layer-wise
     path on the materialised (B,N,C+6[+1]) representation."""
+    if normalize_pc and normalize_method not in ('SD', 'Spread'):
+        raise Exception('Invalid normalization method')        # semisup_models.py:343, before anything is built
     rt.require_eval(is_training)
     st = rt.store()
     pc = rt.f32(pc)
@@ -311,6 +313,8 @@ def independent_box_pc_mask_features_model(box_reg, pc, mask, num_outputs, is_tr
     """semisup_models.py:400-471 (BoxPC representation B): the box (B,7) goes through the `extract_box_feats` FC stack, the
     raw points through conv 128-128-256-512 + max (one fused chain, CHAIN_BOXPCB, in the bf16 / f16x2 modes), and the
     concatenation [box_feat, point_feat (, norm_box2D) (, one_hot)] through the 4-layer FC head."""
+    if normalize_pc and normalize_method not in ('SD', 'Spread'):
+        raise Exception('Invalid normalization method')        # semisup_models.py:421
     rt.require_eval(is_training)
     st = rt.store()
     pc = rt.f32(pc)

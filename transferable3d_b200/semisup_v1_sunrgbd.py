@@ -50,12 +50,12 @@ def get_semi_model(pc, bg_pc, img, one_hot_vec, is_training, use_one_hot, oracle
 def get_semi_model_backbone(pc, bg_pc, img, one_hot_vec, is_training, use_one_hot, oracle_mask=None, norm_box2D=None,
                             bn_decay=None, c=None):
     """semisup_v1_sunrgbd.py:81-130 (model A)."""
+    if oracle_mask is not None:
+        raise NotImplementedError          # semisup_v1_sunrgbd.py:96: model A takes no oracle mask
     end_points = _base_end_points(pc, one_hot_vec)
     img_feats = None
     if not use_one_hot:
         one_hot_vec = None
-    if oracle_mask is not None:
-        raise NotImplementedError
     if not c.USE_NORMALIZED_BOX2D_AS_FEATS:
         norm_box2D = None
     logits = semisup_models.v1_inst_seg(pc, img_feats, one_hot_vec, end_points, is_training, bn_decay=bn_decay,
