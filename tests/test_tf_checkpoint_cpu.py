@@ -27,8 +27,8 @@ def test_entry_and_footer_byte_layout(tmp_path):
     idx = open(prefix + '.index', 'rb').read()
     assert struct.unpack('<Q', idx[-8:])[0] == 0xdb4775248b80fb57 and len(idx) >= 48
     # BundleEntryProto of 'w': dtype DT_FLOAT (08 01), shape {dim{size 2} dim{size 3}} (12 08 12 02 08 02 12 02 08 03),
-    # offset 0 (20 00), size 24 (28 18), crc32c fixed32 (35 ....)
-    want = bytes([0x08, 0x01, 0x12, 0x08, 0x12, 0x02, 0x08, 0x02, 0x12, 0x02, 0x08, 0x03, 0x20, 0x00, 0x28, 0x18, 0x35])
+    # offset 0 (omitted: proto3 does not serialise a zero scalar), size 24 (28 18), crc32c fixed32 (35 ....)
+    want = bytes([0x08, 0x01, 0x12, 0x08, 0x12, 0x02, 0x08, 0x02, 0x12, 0x02, 0x08, 0x03, 0x28, 0x18, 0x35])
     assert want in idx
     raw = open(prefix + '.data-00000-of-00001', 'rb').read()
     assert raw == v['w'].tobytes()
@@ -152,3 +152,101 @@ def test_v1_checkpoint_is_named_as_such(tmp_path):
     open(p, 'wb').write(b'\x00' * 64)
     with pytest.raises(ValueError, match='V1'):
         ck.load_checkpoint(p)
+
+
+# ---- independent implementations found in the image: TensorBoard ships TensorFlow's generated protos and a CRC32C ---------------
+def _bundle_entry_class():
+    """BundleEntryProto (tensorflow/core/protobuf/tensor_bundle.proto) built with google.protobuf on top of TensorFlow's OWN
+    generated TensorShapeProto (tensorboard.compat.proto.tensor_shape_pb2); the field numbers are the published ones."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    from tensorboard.compat.proto import tensor_shape_pb2
+    pool = descriptor_pool.Default()
+    name = 't3d_test/tensor_bundle_entry.proto'
+    try:
+        fd = pool.FindFileByName(name)
+    except KeyError:
+        f = descriptor_pb2.FileDescriptorProto(name=name, package='t3d_test', syntax='proto3',
+                                               dependency=[tensor_shape_pb2.DESCRIPTOR.name])
+        m = f.message_type.add(name='BundleEntryProto')
+        L, T = descriptor_pb2.FieldDescriptorProto.LABEL_OPTIONAL, descriptor_pb2.FieldDescriptorProto
+        m.field.add(name='dtype', number=1, label=L, type=T.TYPE_INT32)
+        m.field.add(name='shape', number=2, label=L, type=T.TYPE_MESSAGE, type_name='.' + tensor_shape_pb2.TensorShapeProto.DESCRIPTOR.full_name)
+        m.field.add(name='shard_id', number=3, label=L, type=T.TYPE_INT32)
+        m.field.add(name='offset', number=4, label=L, type=T.TYPE_INT64)
+        m.field.add(name='size', number=5, label=L, type=T.TYPE_INT64)
+        m.field.add(name='crc32c', number=6, label=L, type=T.TYPE_FIXED32)
+        fd = pool.Add(f) if hasattr(pool, 'Add') and not hasattr(pool, 'AddSerializedFile') else pool.AddSerializedFile(f.SerializeToString())
+    return message_factory.GetMessageClass(pool.FindMessageTypeByName('t3d_test.BundleEntryProto'))
+
+
+def _raw_entries(prefix):
+    """(key, raw value bytes) of every data-block entry of <prefix>.index, through the reader's own table walk."""
+    import struct
+    from transferable3d_b200 import tf_checkpoint as ck
+    buf = open(prefix + '.index', 'rb').read()
+    footer = buf[len(buf) - 48:]
+    pos = 0
+    _, pos = ck._varint(footer, pos)
+    _, pos = ck._varint(footer, pos)
+    idx_off, pos = ck._varint(footer, pos)
+    idx_size, pos = ck._varint(footer, pos)
+    out = []
+    for _, handle in ck._block_entries(ck._read_block(buf, idx_off, idx_size, True)):
+        off, p = ck._varint(handle, 0)
+        size, p = ck._varint(handle, p)
+        out.extend(ck._block_entries(ck._read_block(buf, off, size, True)))
+    return out
+
+
+def test_crc32c_against_tensorboards_implementation():
+    from tensorboard.compat.tensorflow_stub import pywrap_tensorflow as tb
+    from transferable3d_b200 import tf_checkpoint as ck
+    rng = np.random.RandomState(0)
+    for n in (0, 1, 2, 7, 8, 9, 63, 64, 1000, 4097):
+        data = rng.randint(0, 256, n).astype(np.uint8).tobytes()
+        assert ck.crc32c(data) == tb.crc32c(data), n
+        assert ck.masked_crc(data) == tb.masked_crc32c(data), n
+
+
+def test_dtype_table_against_tensorflows_types_proto():
+    from tensorboard.compat.proto import types_pb2
+    from tensorboard.compat.tensorflow_stub import dtypes
+    from transferable3d_b200 import tf_checkpoint as ck
+    for enum_id, np_type in ck.DTYPES.items():
+        name = types_pb2.DataType.Name(enum_id)                    # raises for an id TensorFlow does not define
+        assert dtypes.as_dtype(enum_id).as_numpy_dtype == np_type, (enum_id, name)
+    assert types_pb2.DataType.Value('DT_FLOAT') == ck.DTYPE_IDS[np.dtype(np.float32)]
+    assert types_pb2.DataType.Value('DT_STRING') not in ck.DTYPES         # skipped by load_checkpoint
+
+
+@pytest.mark.parametrize('which', ['written', 'handmade'])
+def test_index_entries_parse_with_google_protobuf_and_tensorflows_shape_proto(which, tmp_path):
+    """Every BundleEntryProto of an index file, parsed by google.protobuf into TensorFlow's own TensorShapeProto, gives the dtype,
+    shape, offset, size and checksum the hand-written parser of tf_checkpoint.read_index reports (and nothing is left unparsed)."""
+    from transferable3d_b200 import tf_checkpoint as ck
+    if which == 'written':
+        rng = np.random.RandomState(1)
+        prefix = os.path.join(str(tmp_path), 'm.ckpt')
+        ck.save_checkpoint(prefix, {'a/weights': rng.randn(1, 6, 64).astype(np.float32), 'a/biases': rng.randn(64).astype(np.float32),
+                                    'global_step': np.asarray(12345678901, dtype=np.int64), 'b/x' * 30: rng.randint(0, 9, (3, 0, 2)).astype(np.int32),
+                                    'flags': np.asarray([True, False])}, block_size=128)
+    else:
+        prefix = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'tf_ckpt_handmade')
+    Entry = _bundle_entry_class()
+    _, entries = ck.read_index(prefix)
+    seen = 0
+    for key, value in _raw_entries(prefix):
+        if key == b'':
+            continue
+        e = Entry()
+        e.ParseFromString(bytes(value))
+        mine = entries[key.decode()]
+        assert (e.dtype, [d.size for d in e.shape.dim], e.shard_id, e.offset, e.size) == \
+            (mine['dtype'], mine['shape'], mine['shard_id'], mine['offset'], mine['size']), key
+        assert mine['crc32c'] is None or e.crc32c == mine['crc32c']
+        # nothing unparsed: re-serialising the parsed message reproduces the entry byte for byte (unknown fields would be kept too,
+        # so also check the length of what the known fields alone encode)
+        assert e.SerializeToString() == bytes(value), key
+        assert len(bytes(value)) == e.ByteSize()
+        seen += 1
+    assert seen == len(entries) >= 3

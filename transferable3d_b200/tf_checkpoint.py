@@ -6,7 +6,9 @@ without TensorFlow: `load_checkpoint(prefix)` returns the `{variable name: ndarr
 Format (restated from TensorFlow's published tensor_bundle / table sources; no TensorFlow-written file exists in this
 environment, so the reader is pinned by (a) tests/golden/tf_ckpt_handmade.*, a fixture assembled byte by byte by an
 independent script in TensorFlow's own layout -- restart interval 16, shortened separator keys in the index block, a
-DT_STRING entry, bit-serial CRC -- and (b) round trips through the writer below):
+DT_STRING entry, bit-serial CRC --, (b) round trips through the writer below, and (c) independent implementations that ARE in the
+image: TensorBoard's bundled copy of TensorFlow's generated protos (types.proto's DataType enum, TensorShapeProto) and its CRC32C,
+with every BundleEntryProto also parsed by google.protobuf (tests/test_tf_checkpoint_cpu.py)):
 
 * `<prefix>.index` is a LevelDB-style sorted table.  Footer = last 48 bytes: metaindex BlockHandle, index BlockHandle
   (each two varint64: offset, size), zero padding to 40 bytes, 8-byte little-endian magic 0xdb4775248b80fb57.
@@ -266,9 +268,13 @@ def save_checkpoint(prefix, variables, block_size=4096):
                 raise ValueError('%s: dtype %s has no TensorFlow type id here' % (name, a.dtype))
             raw = a.astype(a.dtype.newbyteorder('<'), copy=False).tobytes()
             f.write(raw)
-            shape = b''.join(_put_proto_bytes(2, _put_proto_varint(1, int(s))) for s in a.shape)
-            entry = _put_proto_varint(1, DTYPE_IDS[a.dtype]) + _put_proto_bytes(2, shape) + _put_proto_varint(4, off) + \
-                _put_proto_varint(5, len(raw)) + _put_varint((6 << 3) | 5) + struct.pack('<I', masked_crc(raw))
+            # canonical proto3, as TensorFlow's C++ serialiser writes it: scalar fields equal to zero are omitted (the first
+            # tensor's offset, an empty tensor's size, a zero dimension); the shape message is always present
+            nz = lambda field, v: _put_proto_varint(field, v) if v else b''
+            shape = b''.join(_put_proto_bytes(2, nz(1, int(s))) for s in a.shape)
+            crc = masked_crc(raw)
+            entry = _put_proto_varint(1, DTYPE_IDS[a.dtype]) + _put_proto_bytes(2, shape) + nz(4, off) + nz(5, len(raw)) + \
+                ((_put_varint((6 << 3) | 5) + struct.pack('<I', crc)) if crc else b'')
             items.append((name.encode(), entry))
             off += len(raw)
     header = _put_proto_varint(1, 1) + _put_proto_bytes(3, _put_proto_varint(1, 1))       # num_shards = 1, version.producer = 1
