@@ -431,7 +431,7 @@ def _scene(seed, nimg=40, classes=('bed', 'chair', 'table')):
     return pred_all, gt_all
 
 
-def _numpy_side(ds, ed, perturb, make_rng):
+def _numpy_side(ds, ed, perturb, make_rng, host_scalars_only=False):
     """ds / ed: the dataset-helper and eval_det modules of one side; perturb(center, size, heading, bounds, rng) -> tuple."""
     out = {}
     rng = np.random.RandomState(21)
@@ -446,6 +446,12 @@ def _numpy_side(ds, ed, perturb, make_rng):
     out['class2size'] = np.array([ds.class2size(int(c), r) for c, r in s2c])
     pc = rng.standard_normal((50, 6))
     out['rotate_pc_along_y'] = np.array([ds.rotate_pc_along_y(pc.copy(), a) for a in (0.3, -1.2, np.pi)])
+    rng2 = np.random.RandomState(22)
+    rec = np.sort(rng2.rand(30))
+    prec = np.sort(rng2.rand(30))[::-1].copy()
+    out['voc_ap'] = np.array([ed.voc_ap(rec, prec, False), ed.voc_ap(rec, prec, True)])
+    if host_scalars_only:            # the functions that are host numpy in the product as well (tests/test_oracle_vs_reference_cpu.py)
+        return out
     lab = [ds.from_prediction_to_label_format(rng.standard_normal(3), int(rng.randint(12)), rng.uniform(-0.26, 0.26), int(rng.randint(10)),
                                               rng.uniform(-0.2, 0.2, 3), rng.uniform(-1, 1)) for _ in range(8)]
     out['from_prediction_to_label_format'] = np.array([[h, w, l, tx, ty, tz, ry] for h, w, l, tx, ty, tz, ry in lab])
@@ -456,9 +462,6 @@ def _numpy_side(ds, ed, perturb, make_rng):
                                         rng.standard_normal((B, 10)), rng.uniform(-0.1, 0.1, (B, 10, 3)), rng.standard_normal((B, 3)) * 0.1,
                                         rng.randint(0, 12, B), rng.uniform(-0.2, 0.2, B), rng.randint(0, 10, B), rng.uniform(-0.1, 0.1, (B, 3)))
     out['compute_box3d_iou'] = np.stack([iou2d, iou3d])
-    rec = np.sort(rng.rand(30))
-    prec = np.sort(rng.rand(30))[::-1].copy()
-    out['voc_ap'] = np.array([ed.voc_ap(rec, prec, False), ed.voc_ap(rec, prec, True)])
     pred_all, gt_all = _scene(0)
     for tag, thr, m07 in (('a', 0.25, False), ('b', {'bed': 0.25, 'chair': 0.5, 'table': 0.1}, True)):
         r, p, ap = ed.eval_det(pred_all, gt_all, thr, use_07_metric=m07)

@@ -87,3 +87,13 @@ def test_config_fixture_is_live():
         live = {k: v for k, v in vars(flags).items() if k != 'config_str'}
     ref = json.load(open(os.path.join(GOLDEN, 'ref_config_defaults.json')))
     assert json.loads(json.dumps(live)) == ref
+
+
+def test_product_host_helpers_reproduce_reference_fixture():
+    """The label codecs and voc_ap are host numpy in the product too (transferable3d_b200.roi_seg_box3d_dataset / eval_det): held
+    to the reference's outputs directly (the device-side counterparts are compared in the -m gpu tests)."""
+    from transferable3d_b200 import roi_seg_box3d_dataset as D, eval_det as E
+    want = dict(np.load(rc.fixture_path('numpy_helpers')))
+    got = rc._numpy_side(D, E, None, None, host_scalars_only=True)
+    assert sorted(got) == ['angle2class', 'class2angle', 'class2size', 'rotate_pc_along_y', 'size2class.cls', 'size2class.res', 'voc_ap']
+    assert not rc.compare(got, {k: want[k] for k in got}, rtol=1e-12, atol=1e-13)
