@@ -458,9 +458,12 @@ def _numpy_side(ds, ed, perturb, make_rng, host_scalars_only=False):
     if hasattr(ds, 'get_3d_box'):
         out['get_3d_box'] = np.array([ds.get_3d_box(rng.uniform(0.5, 2, 3), rng.uniform(-3, 3), rng.standard_normal(3)) for _ in range(6)])
     B = 6
-    iou2d, iou3d = ds.compute_box3d_iou(rng.standard_normal((B, 3)) * 0.1, rng.standard_normal((B, 12)), rng.uniform(-0.2, 0.2, (B, 12)),
-                                        rng.standard_normal((B, 10)), rng.uniform(-0.1, 0.1, (B, 10, 3)), rng.standard_normal((B, 3)) * 0.1,
-                                        rng.randint(0, 12, B), rng.uniform(-0.2, 0.2, B), rng.randint(0, 10, B), rng.uniform(-0.1, 0.1, (B, 3)))
+    iou_args = (rng.standard_normal((B, 3)) * 0.1, rng.standard_normal((B, 12)), rng.uniform(-0.2, 0.2, (B, 12)),
+                rng.standard_normal((B, 10)), rng.uniform(-0.1, 0.1, (B, 10, 3)), rng.standard_normal((B, 3)) * 0.1,
+                rng.randint(0, 12, B), rng.uniform(-0.2, 0.2, B), rng.randint(0, 10, B), rng.uniform(-0.1, 0.1, (B, 3)))
+    if perturb is None:              # argument recorder of tests/test_gpu_reference_fixtures.py: same draws, no evaluation
+        return {'_compute_box3d_iou_args': iou_args}
+    iou2d, iou3d = ds.compute_box3d_iou(*iou_args)
     out['compute_box3d_iou'] = np.stack([iou2d, iou3d])
     pred_all, gt_all = _scene(0)
     for tag, thr, m07 in (('a', 0.25, False), ('b', {'bed': 0.25, 'chair': 0.5, 'table': 0.1}, True)):

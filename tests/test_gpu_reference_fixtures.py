@@ -153,3 +153,81 @@ def test_semisup_model_a_train_step_vs_reference_fixture(built_lib):
         _close(ep[k], want['ep.' + k], 2e-3, k, floor=1.0)
     _check_grads(want, g.grad)
     _check_moving(want, g.moving)
+
+
+# ---- the numpy side of the reference, device counterparts -----------------------------------------------------------------------
+def test_dataset_get_batch_vs_reference_fixture(tmp_path, built_lib):
+    """transferable3d_b200.roi_seg_box3d_dataset.ROISegBoxDataset (pickle read on the host, batch assembly in one kernel) against what
+    the reference's own class returned for the same gzip-pickled file, the same index permutation and the same numpy seed."""
+    import gzip
+    import pickle
+    from transferable3d_b200 import roi_seg_box3d_dataset as D
+    want = _fixture('dataset_get_batch')
+    path = os.path.join(str(tmp_path), 'frustums.zip.pickle')
+    with gzip.open(path, 'wb') as f:
+        pickle.dump(rc._frustum_lists(), f, 2)
+    names = ('data', 'image', 'label', 'center', 'hcls', 'hres', 'scls', 'sres', 'box2d', 'rtilts', 'ks', 'rot_angle', 'img_dims', 'one_hot')
+    tol = dict(data=2e-5, center=2e-5, hres=1e-5, sres=1e-6, box2d=1e-4, rtilts=1e-6, ks=1e-4, rot_angle=1e-6, img_dims=1e-4)
+    for i, (rotate, flip, shift, one_hot) in enumerate(rc.DATASET_VARIANTS):
+        ds = D.ROISegBoxDataset(rc.DATASET_CLASSES, 256, 'val', random_flip=flip, random_shift=shift, rotate_to_center=rotate,
+                                overwritten_data_path=path, one_hot=one_hot)
+        assert len(ds) == int(want['v%d.len' % i][0])
+        idxs = np.random.RandomState(1).permutation(len(ds))
+        np.random.seed(77)
+        got = ds.get_batch(idxs, 4, 20, 256, 6)
+        assert len(got) == (14 if one_hot else 13) and got[1] is None
+        for name, g in zip(names, got):
+            if name == 'image':
+                continue
+            g = g.cpu().numpy().astype(np.float64)
+            key = 'v%d.%s' % (i, name)
+            if key in want:
+                w = want[key]
+                if name in ('label', 'hcls', 'scls', 'one_hot'):
+                    assert np.array_equal(g.reshape(w.shape), w), key
+                else:
+                    assert np.abs(g.reshape(w.shape) - w).max() <= tol[name] * max(1.0, np.abs(w).max()), key
+            else:                                       # stored as a signature (the point tensor and the labels)
+                w = want[key + '#sig']
+                s = rc.sig(g)
+                if name == 'label':
+                    assert np.abs(s - w).max() <= 1e-9 * max(1.0, w[0]), key
+                else:
+                    assert abs(s[0] - w[0]) <= 1e-5 * w[0] and np.abs(s[2:] - w[2:]).max() <= 1e-4 * w[0], (key, s, w)
+
+
+def test_eval_det_and_box_iou_vs_reference_fixture(built_lib):
+    """eval_det (matching loop on the device) and compute_box3d_iou against the reference's eval_det.py / roi_seg_box3d_dataset.py run
+    on the same detections; 3D IoU itself comes from the restated box_util in both (the reference tree lacks that file)."""
+    from transferable3d_b200 import eval_det as E, box_util as gbu
+    want = _fixture('numpy_helpers')
+    pred_all, gt_all = rc._scene(0)
+    for tag, thr, m07 in (('a', 0.25, False), ('b', {'bed': 0.25, 'chair': 0.5, 'table': 0.1}, True)):
+        rec, prec, ap = E.eval_det(pred_all, gt_all, thr, use_07_metric=m07)
+        assert sorted(ap) == ['bed', 'chair', 'table']
+        for c in ap:
+            assert np.array_equal(np.asarray(rec[c], dtype=np.float64), want['eval_det.%s.%s.rec' % (tag, c)]), (tag, c)
+            assert np.array_equal(np.asarray(prec[c], dtype=np.float64), want['eval_det.%s.%s.prec' % (tag, c)]), (tag, c)
+            assert abs(ap[c] - want['eval_det.%s.%s.ap' % (tag, c)][0]) < 1e-12
+    # the same draws as reference_cases._numpy_side makes before compute_box3d_iou
+    side = rc._numpy_side(_Recorder(), _Recorder(), None, None, host_scalars_only=False)
+    args = side['_compute_box3d_iou_args']
+    i2, i3 = gbu.compute_box3d_iou(*args)
+    got = np.stack([i2.cpu().numpy(), i3.cpu().numpy()]).astype(np.float64)
+    assert np.abs(got - want['compute_box3d_iou']).max() < 2e-5
+    assert (want['compute_box3d_iou'] > 0.01).any()
+
+
+class _Recorder(object):
+    """Stands in for a module in reference_cases._numpy_side: every function accepts its arguments and returns a placeholder, so the
+    random draws up to compute_box3d_iou are consumed in the same order and its arguments come back."""
+    def __getattr__(self, name):
+        if name in ('angle2class', 'size2class'):
+            return lambda *a, **k: (0, np.zeros(3) if name == 'size2class' else 0.0)
+        if name == 'from_prediction_to_label_format':
+            return lambda *a, **k: (0.0,) * 7
+        if name == 'rotate_pc_along_y':
+            return lambda pc, a: pc
+        if name == 'get_3d_box':
+            return lambda *a, **k: np.zeros((8, 3))
+        return lambda *a, **k: 0.0
