@@ -10,6 +10,10 @@ inputs, weights, flags and dropout masks, with no oracle in between:
     tests/util.py:assert_grad_close -- ReLU flips near zero move a weight gradient by ~1e-3), the updated moving statistics.
     The batches are drawn with seeds whose max-pooled columns have no near-tie (reference_cases.find_tie_free_seed) and whose
     smallest mask-logit margin is > 4e-4, so every assertion is unconditional.
+  * the same training steps under every flag set the fixtures hold (8 BoxPC loss / weighting sets, 7 reprojection / intra-class /
+    inactive-volume sets of the cfg5 graph, T-Net-only training, model A with the softmax projection): loss, trained-variable set,
+    gradient signatures;
+  * the numpy side on the device: ROISegBoxDataset batch assembly, eval_det, compute_box3d_iou.
 """
 import os
 import sys
@@ -231,3 +235,54 @@ class _Recorder(object):
         if name == 'get_3d_box':
             return lambda *a, **k: np.zeros((8, 3))
         return lambda *a, **k: 0.0
+
+
+# ---- every flag set of the training graphs (loss, trained-variable set and gradient signatures; fixtures keep nothing else) --------
+@pytest.mark.parametrize('i', range(8))
+def test_boxpc_flag_variants_vs_reference_fixture(i, built_lib):
+    want = _fixture('boxpc_train_variant%d' % i)
+    rep = 'A' if i != 7 else 'B'
+    v, feed, masks = rc._boxpc_inputs(rep)
+    B, N = feed['pc'].shape[:2]
+    g = tb.BoxPCTrainGraph(v, config.cfg(BOXPC_WEIGHT_DELTA=4., BOX_PC_MASK_REPRESENTATION=rep, **rc.BOXPC_VARIANTS[i]), B, N, 6, DEV)
+    out = g.forward_backward(feed, masks)
+    torch.cuda.synchronize()
+    assert abs(float(out['loss']) - want['loss'][0]) <= 2e-4 * max(1.0, abs(want['loss'][0])), (float(out['loss']), want['loss'][0])
+    _check_grads(want, g.grad, strip='box_pc_mask_model/')
+
+
+@pytest.mark.parametrize('i', range(7))          # variant 7 (two refinement steps) is refused by the training graph: see below
+def test_semisup_adv_flag_variants_vs_reference_fixture(i, built_lib):
+    want = _fixture('semisup_adv_train_variant%d' % i)
+    v, feed, masks = rc._semi_inputs('F')
+    B, N = feed['pc'].shape[:2]
+    g = tsa.SemiAdvTrainGraph(v, config.cfg(**dict(rc.CFG5, **rc.REPROJ_VARIANTS[i])), B, N, 6, DEV)
+    ep = g.forward_backward(feed, masks)
+    torch.cuda.synchronize()
+    loss = float(ep['loss_terms'].cpu().numpy()[0])
+    assert abs(loss - want['loss'][0]) <= 2e-4 * max(1.0, abs(want['loss'][0])), (loss, want['loss'][0])
+    _check_grads(want, g.grad)
+
+
+def test_semisup_adv_variants_outside_the_recipe_fail_loudly(built_lib):
+    v, feed, masks = rc._semi_inputs('F')
+    with pytest.raises(NotImplementedError):
+        tsa.SemiAdvTrainGraph(v, config.cfg(**dict(rc.CFG5, **rc.REPROJ_VARIANTS[7])), 8, 256, 6, DEV)
+
+
+def test_semisup_adv_tnet_only_and_model_a_softmax_vs_reference_fixture(built_lib):
+    want = _fixture('semisup_adv_train_tnet_only')
+    v, feed, masks = rc._semi_inputs('F')
+    g = tsa.SemiAdvTrainGraph(v, config.cfg(**dict(rc.CFG5, SEMI_TRAIN_BOX_TRAIN_CLASS_AG_BOX=False)), 8, 256, 6, DEV)
+    ep = g.forward_backward(feed, masks)
+    torch.cuda.synchronize()
+    assert abs(float(ep['loss_terms'].cpu().numpy()[0]) - want['loss'][0]) <= 2e-4 * max(1.0, abs(want['loss'][0]))
+    _check_grads(want, g.grad)
+    want = _fixture('semisup_A_train_softmax_proj')
+    v, feed, masks = rc._semi_inputs('A')
+    flags = dict(rc.CFG_A, WEAK_TRAIN_BOX_W_SURFACE=[True, False, True], WEAK_REPROJECTION_USE_SOFTMAX_PROJ=True)
+    g = tsm.SemiTrainGraph(v, config.cfg(SEMI_MODEL='A', **flags), 8, 256, 6, DEV)
+    ep = g.forward_backward(feed, masks)
+    torch.cuda.synchronize()
+    assert abs(float(ep['semi_loss']) - want['loss'][0]) <= 2e-4 * max(1.0, abs(want['loss'][0]))
+    _check_grads(want, g.grad)
