@@ -51,10 +51,13 @@ def _close(got, want, tol, what, floor=1e-6):
 
 @pytest.mark.parametrize('mode', ['fp32', 'f16x2'])
 @pytest.mark.parametrize('case,refine,mask_pc,oracle_mask,box2d', [('refine2', 2, False, False, False), ('masked_pc', 1, True, False, False),
-                                                                   ('oracle_mask', 1, False, True, False), ('box2d_feats', 1, False, False, True)])
+                                                                   ('oracle_mask', 1, False, True, False), ('box2d_feats', 1, False, False, True),
+                                                                   # an empty, a full and a one-point oracle mask; two refinement steps on the
+                                                                   # masked cloud
+                                                                   ('edge_masks', 2, True, True, False)])
 def test_model_F_test_graph_vs_reference_fixture(case, refine, mask_pc, oracle_mask, box2d, mode, built_lib):
     want = _fixture('model_F_test_graph_' + case)
-    v, b = rc._model_F_inputs(box2d_feats=box2d)
+    v, b = rc._model_F_inputs(box2d_feats=box2d, edge_masks=(case == 'edge_masks'))
     FLAGS = config.cfg(refine=refine, mask_pc_for_boxpc=mask_pc, USE_NORMALIZED_BOX2D_AS_FEATS=box2d)
     rt.set_default_store(rt.VariableStore(v, DEV))
     t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32)).to(DEV)
