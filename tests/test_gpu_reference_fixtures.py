@@ -289,3 +289,52 @@ def test_semisup_adv_tnet_only_and_model_a_softmax_vs_reference_fixture(built_li
     torch.cuda.synchronize()
     assert abs(float(ep['semi_loss']) - want['loss'][0]) <= 2e-4 * max(1.0, abs(want['loss'][0]))
     _check_grads(want, g.grad)
+
+
+def test_fpointnet_v1_helpers_vs_reference_fixture(built_lib):
+    """models/model_util.py on the device against the reference's own functions: mask + centroid, the 512-point gather on numpy's
+    legacy stream (same seed: > 512, a handful and no selected points), the T-Net on the gathered points, the KITTI-sized output
+    parse, the corner builders with the double residual add."""
+    from transferable3d_b200 import model_util as mu
+    want = _fixture('fpointnet_v1_helpers')
+    v, b, logits, lab, out59 = rc._fpn_inputs()
+    rt.set_default_store(rt.VariableStore(v, DEV))
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32)).to(DEV)
+
+    def sig_close(got, key, rel):
+        w = want[key + '#sig']
+        s = rc.sig(got.detach().float().cpu().numpy())
+        assert abs(s[0] - w[0]) <= rel * max(w[0], 1e-6) and np.abs(s[2:] - w[2:]).max() <= 10 * rel * max(w[0], 1e-6), (key, s, w)
+    try:
+        with rt.precision('fp32'), torch.no_grad():
+            ep = {}
+            mu.set_resample_rng('numpy_legacy', seed=1234)
+            obj, mean, ep = mu.point_cloud_masking(t(b['pc']), t(logits), ep)
+            with rt.variable_scope('tnet'):
+                delta, ep = mu.get_center_regression_net(obj, t(b['one_hot']), False, None, ep)
+            mu.set_resample_rng('numpy_legacy', seed=99)
+            obj6, _, _ = mu.point_cloud_masking(t(b['pc']), t(logits), {}, xyz_only=False)
+            ep = mu.parse_output_to_tensors(t(out59), ep)
+            center = ep['center_boxnet'] + delta + mean
+            sun_res = t((np.random.RandomState(3).standard_normal((4, 10, 3)) * 0.1).astype(np.float32))
+            ck = mu.get_box3d_corners(center, ep['heading_residuals'], ep['size_residuals'])
+            cs = mu.get_box3d_corners_sunrgbd(center, ep['heading_residuals'], sun_res)
+            ch = mu.get_box3d_corners_helper(t(lab['center']), t(lab['hres']), t(np.abs(lab['sres']) + 0.5))
+        torch.cuda.synchronize()
+    finally:
+        mu.set_resample_rng('philox', 0)
+    assert tuple(obj.shape) == (4, 512, 3) and tuple(obj6.shape) == (4, 512, 6)
+    sig_close(obj, 'object_pc', 1e-5)                                   # the same 512 picks per frustum, in the same order
+    sig_close(obj6, 'object_pc_6ch', 1e-5)
+    sig_close(ep['mask'], 'ep.mask', 1e-9)
+    _close(mean, want['mask_xyz_mean'], 1e-5, 'mask_xyz_mean', floor=1.0)
+    _close(delta, want['tnet_delta'], 2e-4, 'tnet_delta', floor=1e-2)
+    for k in ('center_boxnet', 'heading_scores', 'heading_residuals_normalized', 'heading_residuals', 'size_scores',
+              'size_residuals_normalized', 'size_residuals'):
+        _close(ep[k], want['ep.' + k], 1e-5, k, floor=1e-2)
+    sig_close(ck, 'corners_kitti', 2e-5)
+    sig_close(cs, 'corners_sunrgbd', 2e-5)
+    _close(ch, want['corners_helper'], 1e-5, 'corners_helper', floor=1.0)
+    from transferable3d_b200.constants import g_mean_size_arr, MEAN_DIMS_ARR
+    assert np.array_equal(np.asarray(g_mean_size_arr, dtype=np.float64), want['g_mean_size_arr'])
+    assert np.array_equal(np.asarray(MEAN_DIMS_ARR, dtype=np.float64), want['sun_mean_size_arr'])
