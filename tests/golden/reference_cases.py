@@ -68,7 +68,9 @@ def _np(t):
 
 
 # ---- case 1: the test graph of model F (test_semisup.get_model, test_semisup.py:61-180, called as is) -------------------
-def _model_F_inputs(B=4, N=128, box2d_feats=False, edge_masks=False):
+def _model_F_inputs(B=4, N=128, box2d_feats=False, edge_masks=False, full_size=False):
+    if full_size:                     # the reference's point count (BASELINE: 2048 points per frustum)
+        B, N = 8, 2048
     b = synth.make_batch(B, N, 6, seed=2024)
     if edge_masks:                    # the oracle-mask input with an empty mask, a full one and a single point
         lab = np.array(b['labels']).copy()
@@ -80,8 +82,8 @@ def _model_F_inputs(B=4, N=128, box2d_feats=False, edge_masks=False):
     return weights.make_weights_model_F(seed=11, norm_box2d=box2d_feats), b
 
 
-def _model_F_reference(refine, mask_pc, oracle_mask=False, box2d_feats=False, edge_masks=False):
-    v, b = _model_F_inputs(box2d_feats=box2d_feats, edge_masks=edge_masks)
+def _model_F_reference(refine, mask_pc, oracle_mask=False, box2d_feats=False, edge_masks=False, full_size=False):
+    v, b = _model_F_inputs(box2d_feats=box2d_feats, edge_masks=edge_masks, full_size=full_size)
     B, N = b['pc'].shape[:2]
     out = {}
     with rr.Reference() as R:
@@ -100,10 +102,10 @@ def _model_F_reference(refine, mask_pc, oracle_mask=False, box2d_feats=False, ed
     return out
 
 
-def _model_F_oracle(refine, mask_pc, oracle_mask=False, box2d_feats=False, edge_masks=False):
+def _model_F_oracle(refine, mask_pc, oracle_mask=False, box2d_feats=False, edge_masks=False, full_size=False):
     from oracle.tf_layers import VarStore
     from oracle import test_semisup as ots
-    v, b = _model_F_inputs(box2d_feats=box2d_feats, edge_masks=edge_masks)
+    v, b = _model_F_inputs(box2d_feats=box2d_feats, edge_masks=edge_masks, full_size=full_size)
     FLAGS = config.cfg(refine=refine, mask_pc_for_boxpc=mask_pc, USE_NORMALIZED_BOX2D_AS_FEATS=box2d_feats)
     vs = VarStore(v, dtype=F64)
     t = lambda a: torch.as_tensor(np.asarray(a)).to(F64)
@@ -858,6 +860,7 @@ CASES = {
     'model_F_test_graph_masked_pc': _case(_model_F_reference, _model_F_oracle, 1, True),
     'model_F_test_graph_oracle_mask': _case(_model_F_reference, _model_F_oracle, 1, False, True, False),
     'model_F_test_graph_edge_masks': _case(_model_F_reference, _model_F_oracle, 2, True, True, False, True),
+    'model_F_test_graph_2048_points': _case(_model_F_reference, _model_F_oracle, 1, False, False, False, False, True),
     'model_F_test_graph_box2d_feats': _case(_model_F_reference, _model_F_oracle, 1, False, False, True),
     'boxpc_train_rep_A': _case(_boxpc_train_reference, _boxpc_train_oracle, 'A', dict(BOXPC_WEIGHT_DELTA=4.)),
     'boxpc_train_rep_B': _case(_boxpc_train_reference, _boxpc_train_oracle, 'B', dict(BOXPC_WEIGHT_DELTA=4.)),

@@ -338,3 +338,29 @@ def test_fpointnet_v1_helpers_vs_reference_fixture(built_lib):
     from transferable3d_b200.constants import g_mean_size_arr, MEAN_DIMS_ARR
     assert np.array_equal(np.asarray(g_mean_size_arr, dtype=np.float64), want['g_mean_size_arr'])
     assert np.array_equal(np.asarray(MEAN_DIMS_ARR, dtype=np.float64), want['sun_mean_size_arr'])
+
+
+@pytest.mark.parametrize('mode', ['fp32', 'f16x2'])
+def test_model_F_test_graph_2048_points_vs_reference_fixture(mode, built_lib):
+    """The test graph at the reference's own point count (8 frustums x 2048 points: 16 tiles per frustum through the fused
+    chains) against what the reference's source computes; the 32768 logits are compared through their signature."""
+    want = _fixture('model_F_test_graph_2048_points')
+    v, b = rc._model_F_inputs(full_size=True)
+    rt.set_default_store(rt.VariableStore(v, DEV))
+    t = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float32)).to(DEV)
+    with rt.precision(mode), torch.no_grad():
+        logits, ep = ts.build_graph(config.cfg(refine=1), t(b['pc']), t(b['one_hot']), box2D=t(b['box2D']), img_dim=t(b['img_dim']))
+    torch.cuda.synchronize()
+    assert tuple(logits.shape) == (8, 2048, 2)
+    w = want['logits#sig']
+    s = rc.sig(logits.float().cpu().numpy())
+    assert abs(s[0] - w[0]) <= 1e-5 * w[0] and np.abs(s[2:] - w[2:]).max() <= 1e-4 * w[0], (s, w)
+    # every reference margin is > 0.04 (9 % of the logit scale; reference_cases / make_reference_golden print it): all points masked in
+    assert bool((logits[..., 0] < logits[..., 1]).all())
+    for k in ('stage1_center', 'F_center', 'F_heading_scores', 'F_heading_residuals', 'F_size_scores', 'F_size_residuals', 'F2_center',
+              'F2_heading_residuals', 'F2_size_residuals', 'boxpc_fit_prob', 'box_params'):
+        _close(ep[k], want['ep.' + k], 2e-4, k)
+    for key in ('feats_lv1', 'feats_lv2', 'feats_lv3'):
+        w = want['ep.%s#sig' % key]
+        s = rc.sig(ep[key].float().cpu().numpy())
+        assert abs(s[0] - w[0]) <= 1e-4 * w[0] and np.abs(s[2:] - w[2:]).max() <= 1e-3 * w[0], (key, s, w)
