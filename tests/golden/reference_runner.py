@@ -194,3 +194,21 @@ def reference_signatures():
 def reference_config_defaults():
     with Reference() as R:
         return {k: v for k, v in vars(R.flags()).items() if k != 'config_str'}
+
+
+def reference_variables():
+    """{graph: {TF variable name: shape}}: every variable the reference's graph code creates (tf.get_variable calls recorded by the
+    stand-in) for the graphs on the path -- the checkpoint contract."""
+    import reference_cases as rc
+    import tf1_shim
+    out = {}
+
+    def grab(name, thunk):
+        thunk()
+        out[name] = {k: list(v) for k, v in sorted(tf1_shim.STATE.requested_shapes.items())}
+    grab('model_F_test_graph', lambda: rc._model_F_reference(1, False))
+    grab('model_F_test_graph_box2d_feats', lambda: rc._model_F_reference(1, False, False, True))
+    grab('model_A_train_graph', lambda: rc._semi_train_reference('A', rc.CFG_A))
+    grab('boxpc_rep_A_train_graph', lambda: rc._boxpc_train_reference('A', dict(BOXPC_WEIGHT_DELTA=4.)))
+    grab('boxpc_rep_B_train_graph', lambda: rc._boxpc_train_reference('B', dict(BOXPC_WEIGHT_DELTA=4.)))
+    return out

@@ -289,6 +289,7 @@ class _State(object):
         self.dropout_masks = {}            # full scope name -> keep mask; consumed by tf.nn.dropout
         self.dropout_log = []
         self.created = []
+        self.requested_shapes = {}         # full TF name -> the shape the graph code asked for
         self.requires_grad = trainable_grad
         self.summaries = {}
         self.feeds = []
@@ -346,6 +347,7 @@ def get_variable(name, shape=None, initializer=None, dtype=None, trainable=True,
     v = torch.as_tensor(np.asarray(STATE.values[full])).to(_dt(dtype) or _FLOAT[0]).clone()
     if shape is not None:
         shape = _ints(shape)
+        STATE.requested_shapes[full] = list(shape)
         assert int(np.prod(shape)) == v.numel(), (full, shape, tuple(v.shape))
         v = v.reshape(shape)
     if STATE.requires_grad and trainable and v.is_floating_point():

@@ -112,3 +112,34 @@ def test_expected_errors_are_what_the_reference_raises():
         finally:
             R.quiet(False)
     assert got == EXPECTED_ERRORS, got
+
+
+# ---- the checkpoint contract: variable names and shapes -------------------------------------------------------------
+VARIABLES = json.load(open(os.path.join(GOLDEN, 'ref_variables.json')))
+
+
+def _product_tables():
+    from transferable3d_b200 import weights
+    return {'model_F_test_graph': weights.make_weights_model_F(seed=11),
+            'model_F_test_graph_box2d_feats': weights.make_weights_model_F(seed=11, norm_box2d=True),
+            'model_A_train_graph': weights.make_weights_model_A(),
+            'boxpc_rep_A_train_graph': weights.make_weights_boxpc(rep='A'),
+            'boxpc_rep_B_train_graph': weights.make_weights_boxpc(rep='B')}
+
+
+@pytest.mark.parametrize('graph', sorted(VARIABLES))
+def test_variable_names_and_shapes_are_the_ones_the_reference_graph_creates(graph):
+    """Every tf.get_variable(name, shape) the reference's graph code issues (recorded while its own get_model / train() graphs
+    were built on the stand-in) against the weight tables of transferable3d_b200.weights: the same set of names, the same
+    shapes -- what a TensorFlow checkpoint of the reference holds is what the variable store expects, and nothing else."""
+    import numpy as np
+    want = VARIABLES[graph]
+    got = {k: list(np.shape(v)) for k, v in _product_tables()[graph].items()}
+    assert sorted(got) == sorted(want), (sorted(set(got) ^ set(want))[:8])
+    assert got == {k: list(v) for k, v in want.items()}
+    assert len(want) >= 38
+
+
+@pytest.mark.skipif(not rr.available(), reason='reference tree not present')
+def test_variable_fixture_is_live():
+    assert json.loads(json.dumps(rr.reference_variables())) == VARIABLES
