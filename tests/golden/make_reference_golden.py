@@ -18,7 +18,7 @@ def write_json_fixtures():
     import os
     import reference_runner as rr
     for fname, obj in (('ref_config_defaults.json', rr.reference_config_defaults()), ('ref_signatures.json', rr.reference_signatures()),
-                       ('ref_variables.json', rr.reference_variables())):
+                       ('ref_variables.json', rr.reference_variables()), ('ref_restore_maps.json', rr.reference_restore_maps())):
         with open(os.path.join(rc.HERE, fname), 'w') as f:
             json.dump(obj, f, indent=0, sort_keys=True)
         print('wrote', fname)

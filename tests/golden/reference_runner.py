@@ -212,3 +212,32 @@ def reference_variables():
     grab('boxpc_rep_A_train_graph', lambda: rc._boxpc_train_reference('A', dict(BOXPC_WEIGHT_DELTA=4.)))
     grab('boxpc_rep_B_train_graph', lambda: rc._boxpc_train_reference('B', dict(BOXPC_WEIGHT_DELTA=4.)))
     return out
+
+
+def reference_restore_maps():
+    """{scope: {name in the pretrained checkpoint: variable of the scoped graph}} as the reference's own
+    load_variable_scopes_from_ckpt builds them for tf.train.Saver(var_list=...) (train_semisup_adv.py:224-237, called at :450-467
+    with ['class_agnostic'] / [''] and ['D_boxpc_branch'] / ['']), on the cfg5 training graph."""
+    import reference_cases as rc
+    import tf1_shim
+    from transferable3d_b200 import weights
+    v, feed, masks = rc._semi_inputs('F')
+    B, N = feed['pc'].shape[:2]
+    out = {}
+    with Reference() as R:
+        FLAGS = R.flags(use_one_hot=True, use_one_hot_boxpc=False, NUM_CHANNELS=6, restore_model_path=None, init_model_path=None,
+                        init_class_ag_path=None, init_boxpc_path=None, SEMI_MODEL='F', BOX_PC_MASK_REPRESENTATION='A', **rc.CFG5)
+        FLAGS.TRAIN_CLS, FLAGS.TEST_CLS = FLAGS.SUNRGBD_SEMI_TRAIN_CLS, FLAGS.SUNRGBD_SEMI_TEST_CLS
+        R.reset(v, dropout_masks=masks, feeds=[None if k is None else feed[k] for k in rc.SEMI_FEED_ORDER] + [True])
+        R.quiet()
+        ns = exec_train_graph(R, 'train_semisup_adv.py', dict(
+            FLAGS=FLAGS, MODEL=R.mod('semisup_v1_sunrgbd'), tf_util=R.mod('tf_util'), weak_losses=R.mod('weak_losses'), BATCH_SIZE=B,
+            NUM_POINT=N, GPU_INDEX=0, BASE_LEARNING_RATE=0.001, BASE_LEARNING_RATE_D=0.001, DECAY_STEP=800000, DECAY_RATE=0.5,
+            OPTIMIZER='adam', OPTIMIZER_D='sgd', MOMENTUM=0.9, BN_DECAY_DECAY_STEP=800000.))
+        R.quiet(False)
+        for scope in ('class_agnostic', 'D_boxpc_branch'):
+            n0 = len(tf1_shim.STATE.collections.get('savers', []))
+            ns['load_variable_scopes_from_ckpt']([scope], [''], None, 'pretrained.ckpt')
+            saver = tf1_shim.STATE.collections['savers'][n0]
+            out[scope] = {k: var.op.name for k, var in sorted(saver.var_list.items())}
+    return out

@@ -1006,6 +1006,19 @@ def _exp_decay(learning_rate, global_step, decay_steps, decay_rate, staircase=Fa
     return T(torch.as_tensor(float(learning_rate) * float(decay_rate) ** p).to(_FLOAT[0]))
 
 
+class _Saver(object):
+    """tf.train.Saver: records the var_list it is built with ({checkpoint name: variable}); restore / save do nothing."""
+    def __init__(self, var_list=None, **kw):
+        self.var_list = var_list
+        STATE.collections.setdefault('savers', []).append(self)
+
+    def restore(self, sess, path):
+        self.restored_from = path
+
+    def save(self, *a, **k):
+        return None
+
+
 class _Optimizer(object):
     """tf.train.*Optimizer: minimize() only records what the step would differentiate (loss, var_list, global_step); the
     caller takes the gradients with torch.autograd."""
@@ -1018,7 +1031,7 @@ class _Optimizer(object):
         return op
 
 
-train = types.SimpleNamespace(ExponentialMovingAverage=_EMA, exponential_decay=_exp_decay, Saver=_Anything,
+train = types.SimpleNamespace(ExponentialMovingAverage=_EMA, exponential_decay=_exp_decay, Saver=_Saver,
                               AdamOptimizer=_Optimizer, MomentumOptimizer=_Optimizer, GradientDescentOptimizer=_Optimizer)
 
 

@@ -143,3 +143,28 @@ def test_variable_names_and_shapes_are_the_ones_the_reference_graph_creates(grap
 @pytest.mark.skipif(not rr.available(), reason='reference tree not present')
 def test_variable_fixture_is_live():
     assert json.loads(json.dumps(rr.reference_variables())) == VARIABLES
+
+
+# ---- the restore maps of the pretrained branches ----------------------------------------------------------------------------------------
+RESTORE_MAPS = json.load(open(os.path.join(GOLDEN, 'ref_restore_maps.json')))
+
+
+def test_remap_scope_reproduces_the_reference_restore_maps():
+    """load_variable_scopes_from_ckpt (train_semisup_adv.py:224-237), run as is on the cfg5 graph with the scope lists of :450-467,
+    hands tf.train.Saver {name in the pretrained checkpoint: graph variable}: tf_checkpoint.remap_scope must send exactly those
+    checkpoint names (a model-A checkpoint, a BoxPC checkpoint) to exactly those variables, dropping the optimizer slots."""
+    from transferable3d_b200 import tf_checkpoint as ck, weights
+    tables = {'class_agnostic': weights.make_weights_model_A(), 'D_boxpc_branch': weights.make_weights_boxpc(rep='A')}
+    for scope, m in RESTORE_MAPS.items():
+        assert sorted(m) == sorted(tables[scope])                          # what such a checkpoint holds
+        ckpt = dict(tables[scope])
+        ckpt.update({'beta1_power': 0.9, 'beta2_power': 0.999, sorted(m)[0] + '/Adam': 0, sorted(m)[0] + '/Adam_1': 0})
+        got = ck.remap_scope(ckpt, scope + '/')
+        assert sorted(got) == sorted(m.values())
+        assert all(got[v] is ckpt[k] for k, v in m.items())
+    assert len(RESTORE_MAPS['class_agnostic']) == 126 and len(RESTORE_MAPS['D_boxpc_branch']) == 38
+
+
+@pytest.mark.skipif(not rr.available(), reason='reference tree not present')
+def test_restore_map_fixture_is_live():
+    assert json.loads(json.dumps(rr.reference_restore_maps())) == RESTORE_MAPS
