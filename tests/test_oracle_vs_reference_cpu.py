@@ -41,7 +41,7 @@ def test_fixture_is_what_the_reference_computes(name):
     want = dict(np.load(rc.fixture_path(name)))
     got = rc.CASES[name][0]()
     assert sorted(got) == sorted(want), (sorted(set(got) ^ set(want))[:8])
-    bad = rc.compare(got, want, rtol=1e-12, atol=1e-13)
+    bad = rc.compare(got, want, rtol=1e-10, atol=1e-11)      # float64 round-off only (thread count changes the summation order)
     assert not bad, (name, bad[:8])
 
 
